@@ -1,0 +1,95 @@
+"""TEST INFRASTRUCTURE ONLY -- the seeded cases behind ``tests/golden/*.npz``.
+
+Shared by ``oracle/make_golden.py`` (runs the real reference on them, build container only) and by
+``tests/`` (runs the oracle and the CUDA path on the same inputs).  Inputs and weights come from
+numpy's legacy ``RandomState`` (bit-stable across numpy versions), NOT from torch's RNG, so the
+fixtures stay valid if the torch version on the GPU box differs.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+# name -> (model kwargs, batch size B, n yield timesteps)
+CASES = {
+    # the reference's own test yaml (tests/configs/model/conv3d.yaml): 11 ch, 16x16, hist 60 / fcst 60 => T=25
+    "test_yaml_pv": dict(
+        model=dict(include_pv_yield=False, include_nwp=False, forecast_minutes=60, history_minutes=60,
+                   number_of_conv3d_layers=4, conv3d_channels=32, image_size_pixels=16, number_sat_channels=11,
+                   fc1_output_features=16, fc2_output_features=16, fc3_output_features=16),
+        batch=2,
+    ),
+    # tests/configs/model/conv3d_gsp.yaml
+    "test_yaml_gsp": dict(
+        model=dict(include_pv_yield=False, include_nwp=False, forecast_minutes=60, history_minutes=60,
+                   number_of_conv3d_layers=4, conv3d_channels=32, image_size_pixels=16, number_sat_channels=11,
+                   fc1_output_features=16, fc2_output_features=16, fc3_output_features=16,
+                   output_variable="gsp_yield"),
+        batch=2,
+    ),
+    # BASELINE config 3 in miniature: NWP + PV-history branches on (model.py:129-148), 12 ch, T=19
+    "nwp_pv_small": dict(
+        model=dict(include_pv_yield=True, include_nwp=True, forecast_minutes=60, history_minutes=30,
+                   number_of_conv3d_layers=4, conv3d_channels=32, image_size_pixels=16, number_sat_channels=12,
+                   fc1_output_features=128, fc2_output_features=128, fc3_output_features=64),
+        batch=3,
+    ),
+    # production yaml in miniature (configs/model/conv3d.yaml: 6 layers, gsp_yield, hist 30 / fcst 120 => T=31)
+    "prod_yaml_small": dict(
+        model=dict(include_pv_yield=True, include_nwp=True, forecast_minutes=120, history_minutes=30,
+                   number_of_conv3d_layers=6, conv3d_channels=32, image_size_pixels=16, number_sat_channels=11,
+                   fc1_output_features=128, fc2_output_features=128, fc3_output_features=64,
+                   output_variable="gsp_yield"),
+        batch=2,
+    ),
+}
+
+SUBSAMPLE = 97  # stride used to thin out large tensors (fc1.weight and its grad) in the fixtures
+
+
+def seq_len_of(kw: dict) -> int:
+    return kw["forecast_minutes"] // 5 + kw["history_minutes"] // 5 + 1
+
+
+def golden_batch(name: str, seed: int = 518) -> dict:
+    """Deterministic nested batch dict for CASES[name] (int16 satellite, NaNs in PV history row 0)."""
+    case = CASES[name]
+    kw, B = case["model"], case["batch"]
+    rs = np.random.RandomState(seed)
+    C, T, S = kw["number_sat_channels"], seq_len_of(kw), kw["image_size_pixels"]
+    sat = rs.randint(0, 1024, size=(B, C, T, S, S)).astype(np.int16)
+    sat[rs.rand(*sat.shape) < 2e-3] = -1
+    var = kw.get("output_variable", "pv_yield")
+    n_sys = 128 if var == "pv_yield" else 32
+    # yield time axis: 5-min steps for pv (T), 30-min steps for gsp (history_len_30 + 1 + forecast_len_30)
+    n_t = T if var == "pv_yield" else (kw["history_minutes"] // 30 + 1 + kw["forecast_minutes"] // 30)
+    yld = rs.rand(B, n_t, n_sys).astype(np.float32)
+    legacy = yld.copy()
+    legacy[:, 0, :][rs.rand(B, n_sys) < 0.05] = np.nan
+    nwp = rs.randn(B, 10, 19, 2, 2).astype(np.float32)
+    b = {"satellite": {"data": torch.from_numpy(sat)}, "nwp": torch.from_numpy(nwp), var: torch.from_numpy(legacy)}
+    b["pv" if var == "pv_yield" else "gsp"] = {var: torch.from_numpy(yld)}
+    return b
+
+
+def golden_state_dict(model: torch.nn.Module, seed: int = 1234) -> dict:
+    """Deterministic weights: U(-1/sqrt(fan_in), +1/sqrt(fan_in)) from numpy RandomState, in
+    ``state_dict`` key order (same bound as torch's default init, probe in SURVEY.md section 8b)."""
+    rs = np.random.RandomState(seed)
+    sd = {}
+    for k, v in model.state_dict().items():
+        shape = tuple(v.shape)
+        if k.endswith(".weight"):
+            fan_in = int(np.prod(shape[1:]))
+        else:
+            w = model.state_dict()[k[: -len("bias")] + "weight"]
+            fan_in = int(np.prod(tuple(w.shape)[1:]))
+        bound = 1.0 / np.sqrt(fan_in)
+        sd[k] = torch.from_numpy(rs.uniform(-bound, bound, size=shape).astype(np.float32))
+    return sd
+
+
+def thin(t: torch.Tensor) -> np.ndarray:
+    """Flatten; keep everything for small tensors (<= 4096 elements), every SUBSAMPLE-th element for big ones."""
+    a = t.detach().cpu().reshape(-1).numpy()
+    return a if a.size <= 4096 else a[::SUBSAMPLE].copy()
