@@ -1,0 +1,156 @@
+/*
+ * pvb200.h -- C ABI of libpvb200.so: the B200 (sm_100a) kernels behind the Conv3d PV-yield step.
+ *
+ * This is the drop-in boundary for ONE hot path of openclimatefix/predict_pv_yield: the Conv3d
+ * model's train / inference step.  The reference is pure Python + torch and has no FFI of its own
+ * (SURVEY.md section 2a); every entry point below therefore replaces a torch operator call site in the
+ * reference, cited as file:line relative to the reference root.  A maintainer binds these with
+ * ctypes; predict_pv_yield_b200/lib.py is exactly that binding.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, explicit sizes, caller-owned workspaces, a cudaStream_t passed
+ *     as void*.  No allocation, no retained pointers, no implicit synchronisation inside.
+ *   - every function returns 0 (PVB200_OK) or a non-zero status; pvb200_last_error() returns the
+ *     message of the last failure on the calling thread.
+ *   - tensors are dense, row-major, in torch's native layouts: activations NCDHW
+ *     ([B][C][T][H][W]), Conv3d weights [Cout][Cin][3][3][3], Linear weights [out][in].
+ *   - fp32 functions end in _f32; bf16 tensor-core functions end in _bf16 (bf16 storage as
+ *     uint16_t, fp32 accumulation).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PVB200_H
+#define PVB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVB200_ABI_VERSION 1
+
+#define PVB200_OK 0
+#define PVB200_ERR_INVALID 1   /* bad argument / unsupported shape */
+#define PVB200_ERR_CUDA 2      /* CUDA runtime error (message has cudaGetErrorString) */
+#define PVB200_ERR_WORKSPACE 3 /* workspace too small */
+
+typedef void* pvb200_stream_t; /* cudaStream_t */
+
+/* ---- library state ------------------------------------------------------------------------ */
+int pvb200_abi_version(void);
+const char* pvb200_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's "gpu_launches") */
+unsigned long long pvb200_launch_count(void);
+void pvb200_reset_launch_count(void);
+/* SM count of the current device (grid sizing), or <0 on error */
+int pvb200_sm_count(void);
+/* diagnostic: launch an FP32 FMA saturation kernel; *flops_out = FLOPs it performs.  bench.py times it
+ * with CUDA events to get the FP32-FMA roofline denominator (not in MEASURED_PEAKS.json). */
+int pvb200_probe_fp32_fma(float* sink, int iters, double* flops_out, pvb200_stream_t stream);
+
+/* ---- a1/a2: int16 satellite normalisation ---------------------------------------------------
+ * replaces: predict_pv_yield/netcdf_dataset.py:96-101 (astype(float32); - SAT_MEAN; /= SAT_STD)
+ *           + the cast at predict_pv_yield/models/conv3d/model.py:113.
+ * y[b,c,...] = (float(x[b,c,...]) - mean[c]) / std[c]   two IEEE roundings, true division:
+ * bit-identical to the reference fp32 arithmetic.  thw = T*H*W elements per (b,c) plane.
+ * _bf16 writes round-to-nearest-even bf16 of that fp32 value. */
+int pvb200_sat_normalise_f32(const int16_t* x, float* y, const float* mean, const float* std,
+                             int B, int C, long long thw, pvb200_stream_t stream);
+int pvb200_sat_normalise_bf16(const int16_t* x, uint16_t* y, const float* mean, const float* std,
+                              int B, int C, long long thw, pvb200_stream_t stream);
+
+/* ---- a3/a4: Conv3d 3x3x3, stride 1, padding 0, + bias (+ ReLU) -------------------------------
+ * replaces: F.relu(self.sat_conv0(sat_data)) / F.relu(layer(out)), model.py:117-120.
+ * x: [B,Cin,Ti,Hi,Wi] fp32, or int16 when x_is_i16 != 0 (normalisation fused into the load, then
+ * mean/std must be given);  w: [Cout,Cin,3,3,3];  y: [B,Cout,Ti-2,Hi-2,Wi-2]. */
+size_t pvb200_conv3d_workspace_bytes(int Cin, int Cout); /* for _fwd and _dgrad (weight re-layout) */
+int pvb200_conv3d_fwd_f32(const void* x, int x_is_i16, const float* mean, const float* std,
+                          const float* w, const float* bias, float* y,
+                          void* workspace, size_t workspace_bytes,
+                          int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu,
+                          pvb200_stream_t stream);
+
+/* data gradient (autograd of model.py:118-120): gx = conv_transpose(gz, w), optionally masked by the
+ * ReLU of the layer below: gx *= (mask_src > 0).  gz: [B,Cout,Ti-2,Hi-2,Wi-2] (already ReLU-masked
+ * gradient w.r.t. the pre-activation), mask_src/gx: [B,Cin,Ti,Hi,Wi] (mask_src may be NULL). */
+int pvb200_conv3d_dgrad_f32(const float* gz, const float* w, const float* mask_src, float* gx,
+                            void* workspace, size_t workspace_bytes,
+                            int B, int Cin, int Ti, int Hi, int Wi, int Cout,
+                            pvb200_stream_t stream);
+
+/* weight + bias gradient (autograd of model.py:117-120): dw[co,ci,kt,kh,kw] = sum gz * x(shifted),
+ * db[co] = sum gz.  Deterministic two-pass reduction through the caller's workspace. */
+size_t pvb200_conv3d_wgrad_workspace_bytes(int Cin, int Cout);
+int pvb200_conv3d_wgrad_f32(const void* x, int x_is_i16, const float* mean, const float* std,
+                            const float* gz, float* dw, float* db,
+                            void* workspace, size_t workspace_bytes,
+                            int B, int Cin, int Ti, int Hi, int Wi, int Cout,
+                            pvb200_stream_t stream);
+
+/* ---- a6-a9: the fully connected head --------------------------------------------------------
+ * replaces model.py:122-154 (reshape, fc1, fc2, PV-history cat, fc_nwp, NWP cat, fc3, fc4) and its
+ * autograd.  All matrices fp32, torch Linear layout [out][in]. */
+typedef struct pvb200_head {
+  size_t struct_size; /* = sizeof(pvb200_head_t), ABI check */
+  int B;              /* samples */
+  int F1, F2, F3, FO; /* fc1 / fc2 / fc3 out features, forecast_len (fc4 out) */
+  int NPV;            /* PV-history features appended to fc2's output (0 = branch off), model.py:130-136 */
+  int NNWP;           /* NWP input features (0 = branch off), model.py:139-148 */
+  int FNWP;           /* fc_nwp out features (128, model.py:99) */
+  int pv_ns;          /* systems per history row: NPV = pv_nt * pv_ns */
+  long long K1;       /* cnn_output_size (fc1 in features) */
+  long long pv_sb, pv_st; /* PV-history element (b,t,s) lives at pv[b*pv_sb + t*pv_st + s] */
+  /* parameters */
+  const float *w1, *b1, *w2, *b2, *wn, *bn, *w3, *b3, *w4, *b4;
+  /* inputs */
+  const float* x;   /* [B,K1]  flattened last conv activation (post-ReLU), NCDHW order (model.py:122) */
+  const float* pv;  /* PV / GSP history (may hold NaN: nan_to_num(0), model.py:131) */
+  const float* nwp; /* [B,NNWP] */
+  /* saved activations (written by fwd, read by bwd) */
+  float* h1;  /* [B,F1]  relu(fc1) */
+  float* cat; /* [B,F2+NPV+FNWP']  = [relu(fc2) | pv history | relu(fc_nwp)] (FNWP' = FNWP if NNWP else 0) */
+  float* h3;  /* [B,F3]  relu(fc3) */
+  float* out; /* [B,FO]  forecast */
+  /* backward: input gradient and outputs */
+  const float* g_out; /* [B,FO] */
+  float* g_h3;  /* [B,F3]   grad wrt fc3 pre-activation */
+  float* g_cat; /* [B,F2+NPV+FNWP']  grad wrt fc2 / fc_nwp PRE-activations in their slots (pv slot: unused) */
+  float* g_h1;  /* [B,F1]   grad wrt fc1 pre-activation */
+  float* g_x;   /* [B,K1]   grad wrt the last conv layer's PRE-activation (ReLU mask of x applied) */
+  float *dw1, *db1, *dw2, *db2, *dwn, *dbn, *dw3, *db3, *dw4, *db4;
+  /* workspace for the split-K fc1 forward */
+  void* workspace;
+  size_t workspace_bytes;
+} pvb200_head_t;
+
+size_t pvb200_head_fwd_workspace_bytes(int B, int F1, long long K1);
+/* forward: fills h1, cat, h3, out */
+int pvb200_head_fwd_f32(const pvb200_head_t* h, pvb200_stream_t stream);
+/* backward: from g_out fills g_h3, g_cat, g_h1, g_x and all dw / db */
+int pvb200_head_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream);
+
+/* ---- a10: loss -------------------------------------------------------------------------------
+ * replaces base_model.py:95-103: y = yield[0:B, -FO:, 0] (strided view: element (b,f) at
+ * y[b*y_sb + f*y_sf]); losses[0..3] = {nmae (L1, the returned loss), mse, mse_exp, mae_exp} with
+ * nowcasting_utils WeightedLosses weights w[FO].  bwd: g[b,f] = gscale * sign(y_hat - y) / (B*FO). */
+int pvb200_l1_loss_fwd_f32(const float* y_hat, const float* y, long long y_sb, long long y_sf,
+                           const float* weights, float* losses, int B, int FO, pvb200_stream_t stream);
+int pvb200_l1_loss_bwd_f32(const float* y_hat, const float* y, long long y_sb, long long y_sf,
+                           const float* gscale /* device scalar: upstream grad */, float* g,
+                           int B, int FO, pvb200_stream_t stream);
+
+/* ---- a12: Adam -------------------------------------------------------------------------------
+ * replaces torch.optim.Adam(self.parameters(), lr=0.0005).step(), base_model.py:255-257 (single-tensor
+ * arithmetic of torch.optim.adam: lerp / addcmul / sqrt / addcdiv, bias-corrected, no weight decay).
+ * Multi-tensor: n tensors described by parallel arrays (HOST arrays of device pointers).
+ * grad_scale multiplies every gradient first (1/world_size under data parallelism). */
+int pvb200_adam_step_f32(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                         float* const* exp_avg_sq, const long long* numel,
+                         float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                         pvb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVB200_H */

@@ -1,0 +1,292 @@
+// conv3d_f32.cu -- a3/a4/a11: Conv3d 3x3x3 (stride 1) forward and data-gradient in fp32 on the FMA pipe.
+//
+// Reference call sites: predict_pv_yield/models/conv3d/model.py:80-90 (layers), :117-120 (forward);
+// the data gradient is the autograd of the same lines.
+//
+// fp32 mode must match torch to <= 1e-5 (normalised), which rules out TF32/bf16 tensor-core math,
+// so this is a register-blocked direct convolution on CUDA cores, bounded by the FP32 FMA pipe
+// (128 FMA/clk/SM).  Design (one CTA = 512 output positions x 32 output channels):
+//   * "flattened pitch" tiling: an output plane (Ho x Wo) is addressed as q = ho*Wps + wo with
+//     Wps = round_up(Wi + 2P, 4).  A tile is 512 consecutive q, so the input window a tile needs
+//     for tap (kh,kw) is simply the contiguous run [q0 + kh*Wps + kw, ... + 512): no im2col, no
+//     per-row halo logic.  Columns wo >= Wo are computed and discarded (<= 6 % waste).
+//   * input channels are consumed 8 at a time: 8 x 3 (kt) planes of 512 + 2*Wps + 8 floats are staged
+//     in shared memory (coalesced loads; zero fill implements the padding of the data gradient,
+//     and the int16 normalisation of layer 0 is fused here), with the matching [8][27][32]
+//     weight slab (pre-transposed once per call so the copy is contiguous).
+//   * 256 threads = 64 position-threads x 4 channel groups; each thread owns 2 x 4 positions
+//     x 8 output channels = 64 accumulators and performs 192 FMAs per (ci,kt,kh) from
+//     4 x LDS.128 of input (conflict-free: 16 B lane stride) + 6 x LDS.128 of weights (warp
+//     broadcast).
+//   * epilogue fused: bias + ReLU (forward) or the ReLU mask of the layer below (data gradient).
+//   * data gradient = the same kernel with P = 2, taps flipped and the weight roles swapped.
+#include "common.cuh"
+
+namespace pvb {
+
+constexpr int kQT = 512;       // output positions per CTA tile
+constexpr int kCoT = 32;       // output channels per CTA tile
+constexpr int kCC = 8;         // input channels per shared-memory chunk
+constexpr int kConvThreads = 256;
+
+struct ConvArgs {
+  const void* x;      // [B,Ci,Ti,Hi,Wi] fp32 or int16
+  const float* mean;  // per input channel (int16 input only)
+  const float* stdv;
+  const float* wt;    // pre-transposed weights [Ci][27][CoPad]  (CoPad = round_up(Co,32))
+  const float* bias;  // [Co] or null
+  const float* mask;  // [B,Co,To,Ho,Wo] or null: y = mask > 0 ? y : 0
+  float* y;           // [B,Co,To,Ho,Wo]
+  int B, Ci, Ti, Hi, Wi;
+  int Co, To, Ho, Wo;
+  int P;      // implicit zero padding on every side of T,H,W (0: forward, 2: data gradient)
+  int Wps;    // pitch of the flattened position space, multiple of 4, >= Wi + 2P
+  int NP;     // staged positions per (ci,kt) plane = kQT + 2*Wps + 8
+  int tiles_per_plane;
+  int co_tiles;
+  int CoPad;
+  int relu;
+};
+
+// dw layout transform: wt[ci_role][tap][co_role] = w[co_role*s_co + ci_role*s_ci + (flip ? 26-tap : tap)]
+__global__ void conv_weight_prep_kernel(const float* __restrict__ w, float* __restrict__ wt, int Ci, int Co, int CoPad,
+                                        long long s_co, long long s_ci, int flip) {
+  const int total = Ci * 27 * CoPad;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int co = idx % CoPad;
+    const int tap = (idx / CoPad) % 27;
+    const int ci = idx / (CoPad * 27);
+    float v = 0.f;
+    if (co < Co) v = w[co * s_co + ci * s_ci + (flip ? 26 - tap : tap)];
+    wt[idx] = v;
+  }
+}
+
+template <bool kI16>
+__global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(const ConvArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* in_s = smem;                                  // [kCC][3][NP]
+  float* w_s = smem + kCC * 3 * a.NP;                  // [kCC][27][32]
+  int* off_s = reinterpret_cast<int*>(w_s + kCC * 27 * kCoT);  // [NP] offset inside an input plane, or -1
+
+  const int tid = threadIdx.x;
+  const int tp = tid & 63;   // position thread: positions {4tp..4tp+3} and {256+4tp..256+4tp+3}
+  const int cg = tid >> 6;   // channel group: output channels 8cg..8cg+7 of the tile (warp-uniform)
+
+  // tile decode
+  int t = blockIdx.x;
+  const int cot = t % a.co_tiles; t /= a.co_tiles;
+  const int tile = t % a.tiles_per_plane; t /= a.tiles_per_plane;
+  const int to = t % a.To;
+  const int b = t / a.To;
+  const int q0 = tile * kQT;
+  const int co0 = cot * kCoT;
+
+  // per-tile offset table: staged position i <-> padded position q0+i <-> input (hi,wi)
+  for (int i = tid; i < a.NP; i += kConvThreads) {
+    const int pos = q0 + i;
+    const int hp = pos / a.Wps;
+    const int wp = pos - hp * a.Wps;
+    const int hi = hp - a.P, wi = wp - a.P;
+    off_s[i] = (hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi) ? hi * a.Wi + wi : -1;
+  }
+
+  float acc[8][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+
+  const long long plane_sz = static_cast<long long>(a.Hi) * a.Wi;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  for (int c0 = 0; c0 < a.Ci; c0 += kCC) {
+    __syncthreads();  // previous chunk fully consumed (and off_s visible on the first pass)
+    // ---- stage input: (c,kt) planes round-robin over warps, lanes stride over positions ----
+    for (int pl = warp; pl < kCC * 3; pl += kConvThreads / 32) {
+      const int c = pl / 3, kt = pl - c * 3;
+      const int ci = c0 + c;
+      const int ti = to + kt - a.P;
+      float* dst = in_s + pl * a.NP;
+      const bool plane_ok = (ci < a.Ci) && (ti >= 0) && (ti < a.Ti);
+      if (plane_ok) {
+        const long long base = ((static_cast<long long>(b) * a.Ci + ci) * a.Ti + ti) * plane_sz;
+        if (kI16) {
+          const int16_t* src = static_cast<const int16_t*>(a.x) + base;
+          const float m = __ldg(a.mean + ci), s = __ldg(a.stdv + ci);
+          for (int i = lane; i < a.NP; i += 32) {
+            const int o = off_s[i];
+            dst[i] = (o >= 0) ? sat_norm(__ldg(src + o), m, s) : 0.f;
+          }
+        } else {
+          const float* src = static_cast<const float*>(a.x) + base;
+          for (int i = lane; i < a.NP; i += 32) {
+            const int o = off_s[i];
+            dst[i] = (o >= 0) ? __ldg(src + o) : 0.f;
+          }
+        }
+      } else {
+        for (int i = lane; i < a.NP; i += 32) dst[i] = 0.f;
+      }
+    }
+    // ---- stage weights: contiguous [kCC][27][32] slab out of wt[Ci][27][CoPad] ----
+    for (int idx = tid; idx < kCC * 27 * kCoT; idx += kConvThreads) {
+      const int co = idx & (kCoT - 1);
+      const int r = idx >> 5;  // c*27 + tap
+      const int c = r / 27;
+      float v = 0.f;
+      if (c0 + c < a.Ci) v = __ldg(a.wt + (static_cast<long long>(c0) * 27 + r) * a.CoPad + co0 + co);
+      w_s[idx] = v;
+    }
+    __syncthreads();
+
+    // ---- compute ----
+    const int cmax = min(kCC, a.Ci - c0);
+    for (int c = 0; c < cmax; ++c) {
+#pragma unroll 1
+      for (int kt = 0; kt < 3; ++kt) {
+        const float* ip = in_s + (c * 3 + kt) * a.NP + 4 * tp;
+        const float* wp = w_s + (c * 27 + kt * 9) * kCoT + 8 * cg;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          float in[2][8];
+          {
+            const float4 v0 = *reinterpret_cast<const float4*>(ip + kh * a.Wps);
+            const float4 v1 = *reinterpret_cast<const float4*>(ip + kh * a.Wps + 4);
+            const float4 v2 = *reinterpret_cast<const float4*>(ip + kh * a.Wps + 256);
+            const float4 v3 = *reinterpret_cast<const float4*>(ip + kh * a.Wps + 260);
+            in[0][0] = v0.x; in[0][1] = v0.y; in[0][2] = v0.z; in[0][3] = v0.w;
+            in[0][4] = v1.x; in[0][5] = v1.y; in[0][6] = v1.z; in[0][7] = v1.w;
+            in[1][0] = v2.x; in[1][1] = v2.y; in[1][2] = v2.z; in[1][3] = v2.w;
+            in[1][4] = v3.x; in[1][5] = v3.y; in[1][6] = v3.z; in[1][7] = v3.w;
+          }
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wp + (kh * 3 + kw) * kCoT);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + (kh * 3 + kw) * kCoT + 4);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                acc[j][i] = fmaf(wv[j], in[0][i + kw], acc[j][i]);
+                acc[j][4 + i] = fmaf(wv[j], in[1][i + kw], acc[j][4 + i]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue ----
+  const long long oplane = static_cast<long long>(a.Ho) * a.Wo;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int q = q0 + g * 256 + 4 * tp;
+    const int ho = q / a.Wps;
+    const int wo0 = q - ho * a.Wps;
+    if (ho >= a.Ho) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = co0 + 8 * cg + j;
+      if (co >= a.Co) continue;
+      const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
+      const long long obase = ((static_cast<long long>(b) * a.Co + co) * a.To + to) * oplane + static_cast<long long>(ho) * a.Wo;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int wo = wo0 + i;
+        if (wo < a.Wo) {
+          float v = acc[j][g * 4 + i] + bv;
+          if (a.relu) v = (v < 0.f) ? 0.f : v;
+          if (a.mask) v = (__ldg(a.mask + obase + wo) > 0.f) ? v : 0.f;
+          a.y[obase + wo] = v;
+        }
+      }
+    }
+  }
+}
+
+static size_t conv_ws_bytes(int Ci_role, int Co_role) {
+  return static_cast<size_t>(Ci_role) * 27 * round_up(Co_role, kCoT) * sizeof(float);
+}
+
+// role-level launcher shared by forward and data gradient
+static int launch_conv(const void* x, bool i16, const float* mean, const float* stdv, const float* w, long long s_co,
+                       long long s_ci, int flip, const float* bias, const float* mask, float* y, int B, int Ci, int Ti,
+                       int Hi, int Wi, int Co, int P, int relu, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  ConvArgs a;
+  a.x = x; a.mean = mean; a.stdv = stdv; a.bias = bias; a.mask = mask; a.y = y;
+  a.B = B; a.Ci = Ci; a.Ti = Ti; a.Hi = Hi; a.Wi = Wi; a.Co = Co;
+  a.P = P;
+  a.To = Ti + 2 * P - 2; a.Ho = Hi + 2 * P - 2; a.Wo = Wi + 2 * P - 2;
+  PVB_REQUIRE(a.To > 0 && a.Ho > 0 && a.Wo > 0, "conv3d: input %dx%dx%d too small for a 3x3x3 kernel", Ti, Hi, Wi);
+  a.Wps = round_up(Wi + 2 * P, 4);
+  a.NP = kQT + 2 * a.Wps + 8;
+  const int Qtot = (a.Ho - 1) * a.Wps + a.Wo;
+  a.tiles_per_plane = ceil_div(Qtot, kQT);
+  a.co_tiles = ceil_div(Co, kCoT);
+  a.CoPad = a.co_tiles * kCoT;
+  a.relu = relu;
+  const size_t need = conv_ws_bytes(Ci, Co);
+  if (ws == nullptr || ws_bytes < need) {
+    set_error("conv3d: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return PVB200_ERR_WORKSPACE;
+  }
+  float* wt = static_cast<float*>(ws);
+  a.wt = wt;
+  {
+    const int total = Ci * 27 * a.CoPad;
+    conv_weight_prep_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, wt, Ci, Co, a.CoPad, s_co, s_ci, flip);
+    PVB_LAUNCHED("conv_weight_prep");
+  }
+  const size_t smem = (static_cast<size_t>(kCC) * 3 * a.NP + kCC * 27 * kCoT) * sizeof(float) + a.NP * sizeof(int);
+  PVB_REQUIRE(smem <= 227 * 1024, "conv3d: image width %d needs %zu B of shared memory (> 227 KB)", Wi, smem);
+  const long long tiles = static_cast<long long>(B) * a.To * a.tiles_per_plane * a.co_tiles;
+  PVB_REQUIRE(tiles <= 0x7fffffffLL, "conv3d: too many tiles");
+  if (i16) {
+    PVB_CUDA(cudaFuncSetAttribute(conv3d_direct_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_direct_f32_kernel<true><<<static_cast<unsigned>(tiles), kConvThreads, smem, stream>>>(a);
+  } else {
+    PVB_CUDA(cudaFuncSetAttribute(conv3d_direct_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_direct_f32_kernel<false><<<static_cast<unsigned>(tiles), kConvThreads, smem, stream>>>(a);
+  }
+  PVB_LAUNCHED("conv3d_direct_f32");
+  return PVB200_OK;
+}
+
+}  // namespace pvb
+
+extern "C" {
+
+size_t pvb200_conv3d_workspace_bytes(int Cin, int Cout) {
+  // forward needs [Cin][27][pad32(Cout)], the data gradient [Cout][27][pad32(Cin)]
+  const size_t f = pvb::conv_ws_bytes(Cin, Cout), d = pvb::conv_ws_bytes(Cout, Cin);
+  return f > d ? f : d;
+}
+
+int pvb200_conv3d_fwd_f32(const void* x, int x_is_i16, const float* mean, const float* std, const float* w,
+                          const float* bias, float* y, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
+                          int Hi, int Wi, int Cout, int relu, pvb200_stream_t stream) {
+  PVB_REQUIRE(x && w && y, "conv3d_fwd: null pointer");
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0, "conv3d_fwd: bad shape");
+  PVB_REQUIRE(!x_is_i16 || (mean && std), "conv3d_fwd: int16 input needs mean/std");
+  return pvb::launch_conv(x, x_is_i16 != 0, mean, std, w, /*s_co=*/static_cast<long long>(Cin) * 27, /*s_ci=*/27,
+                          /*flip=*/0, bias, nullptr, y, B, Cin, Ti, Hi, Wi, Cout, /*P=*/0, relu, workspace,
+                          workspace_bytes, pvb::as_stream(stream));
+}
+
+int pvb200_conv3d_dgrad_f32(const float* gz, const float* w, const float* mask_src, float* gx, void* workspace,
+                            size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
+                            pvb200_stream_t stream) {
+  PVB_REQUIRE(gz && w && gx, "conv3d_dgrad: null pointer");
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti > 2 && Hi > 2 && Wi > 2, "conv3d_dgrad: bad shape");
+  // roles: the kernel's "input" is gz [B,Cout,Ti-2,Hi-2,Wi-2] padded by 2, its "output" is gx [B,Cin,Ti,Hi,Wi];
+  // real weight w[co][ci][tap] is read as w[in-role=co][out-role=ci][26-tap]
+  return pvb::launch_conv(gz, false, nullptr, nullptr, w, /*s_co (out-role=ci)=*/27,
+                          /*s_ci (in-role=co)=*/static_cast<long long>(Cin) * 27, /*flip=*/1, nullptr, mask_src, gx, B,
+                          /*Ci role=*/Cout, Ti - 2, Hi - 2, Wi - 2, /*Co role=*/Cin, /*P=*/2, /*relu=*/0, workspace,
+                          workspace_bytes, pvb::as_stream(stream));
+}
+
+}  // extern "C"

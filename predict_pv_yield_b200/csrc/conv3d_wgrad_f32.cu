@@ -1,0 +1,264 @@
+// conv3d_wgrad_f32.cu -- a11: Conv3d weight + bias gradient in fp32 (autograd of model.py:117-120).
+//
+//   dw[co,ci,kt,kh,kw] = sum_{b,t,h,w} gz[b,co,t,h,w] * x[b,ci,t+kt,h+kh,w+kw]      db[co] = sum gz
+//
+// A GEMM with M = Cout, N = Cin*27 and a reduction over B*To*Ho*Wo (1.1-2.1 M positions at B=32), so
+// the whole [Cout x Cin*27] result lives in REGISTERS of one CTA (each thread: 4 output channels x
+// 27 (or 9) taps for one input channel) while persistent CTAs stream disjoint position ranges through
+// shared memory ("split-K"); a second tiny kernel sums the per-CTA partials in a fixed order
+// (deterministic, no atomics).  FP32 FMA pipe bound: 432 FMAs per 22 LDS per thread iteration.
+// Positions use the same flattened-pitch trick as the forward kernel (q = ho*Wps + wo): taps are plain
+// offsets kh*Wps + kw into a contiguous staged window; gz is zero-filled at the wrap columns.
+#include "common.cuh"
+
+namespace pvb {
+
+constexpr int kWgQC = 128;        // output positions staged per chunk
+constexpr int kWgMaxCtas = 320;   // upper bound on persistent CTAs (workspace sizing)
+constexpr int kWgMaxCi = 64;
+
+struct WgradArgs {
+  const void* x;      // [B,Ci,Ti,Hi,Wi] fp32 or int16
+  const float* mean;
+  const float* stdv;
+  const float* gz;    // [B,Co,To,Ho,Wo]
+  float* partial;     // [gridDim.x][Co*Ci*27 + Co]
+  int B, Ci, Ti, Hi, Wi, Co, To, Ho, Wo;
+  int Wps, NP, NPs;   // pitch, staged positions per plane, padded plane stride (NPs % 8 == 4)
+  int chunks_per_plane;
+  long long total_chunks;
+  int ncog;           // ceil(Co / 4)
+  int items;          // ncog * Ci * KTS
+};
+
+template <bool kI16, int KTS>
+__global__ void __launch_bounds__(KTS == 1 ? 256 : 384, 1) conv3d_wgrad_f32_kernel(const WgradArgs a) {
+  constexpr int NKT = 3 / KTS;  // kt values handled by one thread
+  extern __shared__ __align__(16) float smem[];
+  float* x_s = smem;                                        // [3][Ci][NPs]
+  float* gz_s = x_s + 3 * a.Ci * a.NPs;                     // [4*ncog][kWgQC]
+  int* off_s = reinterpret_cast<int*>(gz_s + 4 * a.ncog * kWgQC);  // [NP] input-plane offsets
+  int* goff_s = off_s + a.NP;                               // [kWgQC] gz-plane offsets
+
+  const int tid = threadIdx.x;
+  const int item = blockIdx.y * blockDim.x + tid;
+  const bool active = item < a.items;
+  int ci = 0, cog = 0, ktg = 0;
+  if (active) {
+    ci = item % a.Ci;
+    const int r = item / a.Ci;
+    cog = r % a.ncog;
+    ktg = r / a.ncog;
+  }
+
+  float acc[NKT * 9][4];
+#pragma unroll
+  for (int t = 0; t < NKT * 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+
+  // contiguous chunk range of this CTA
+  const long long c_begin = a.total_chunks * blockIdx.x / gridDim.x;
+  const long long c_end = a.total_chunks * (blockIdx.x + 1) / gridDim.x;
+  const long long xplane = static_cast<long long>(a.Hi) * a.Wi;
+  const long long gplane = static_cast<long long>(a.Ho) * a.Wo;
+  int cur_tile = -1;
+
+  for (long long ch = c_begin; ch < c_end; ++ch) {
+    const int tile = static_cast<int>(ch % a.chunks_per_plane);
+    const long long pl = ch / a.chunks_per_plane;
+    const int to = static_cast<int>(pl % a.To);
+    const int b = static_cast<int>(pl / a.To);
+    const int q0 = tile * kWgQC;
+
+    __syncthreads();  // previous chunk consumed
+    if (tile != cur_tile) {  // offset tables depend only on the tile index (block-uniform branch)
+      for (int i = tid; i < a.NP; i += blockDim.x) {
+        const int pos = q0 + i;
+        const int hp = pos / a.Wps, wp = pos - hp * a.Wps;
+        off_s[i] = (hp < a.Hi && wp < a.Wi) ? hp * a.Wi + wp : -1;
+      }
+      for (int i = tid; i < kWgQC; i += blockDim.x) {
+        const int pos = q0 + i;
+        const int ho = pos / a.Wps, wo = pos - ho * a.Wps;
+        goff_s[i] = (ho < a.Ho && wo < a.Wo) ? ho * a.Wo + wo : -1;
+      }
+      cur_tile = tile;
+      __syncthreads();
+    }
+    // ---- stage x: 3*Ci planes round-robin over warps ----
+    {
+      const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+      for (int p = warp; p < 3 * a.Ci; p += nwarp) {
+        const int kt = p / a.Ci, c = p - kt * a.Ci;
+        float* dst = x_s + p * a.NPs;
+        const long long base = ((static_cast<long long>(b) * a.Ci + c) * a.Ti + (to + kt)) * xplane;
+        if (kI16) {
+          const int16_t* src = static_cast<const int16_t*>(a.x) + base;
+          const float m = __ldg(a.mean + c), s = __ldg(a.stdv + c);
+          for (int i = lane; i < a.NP; i += 32) {
+            const int o = off_s[i];
+            dst[i] = (o >= 0) ? sat_norm(__ldg(src + o), m, s) : 0.f;
+          }
+        } else {
+          const float* src = static_cast<const float*>(a.x) + base;
+          for (int i = lane; i < a.NP; i += 32) {
+            const int o = off_s[i];
+            dst[i] = (o >= 0) ? __ldg(src + o) : 0.f;
+          }
+        }
+      }
+      // ---- stage gz: [co][q] ----
+      for (int p = warp; p < 4 * a.ncog; p += nwarp) {
+        float* dst = gz_s + p * kWgQC;
+        if (p < a.Co) {
+          const float* src = a.gz + ((static_cast<long long>(b) * a.Co + p) * a.To + to) * gplane;
+          for (int i = lane; i < kWgQC; i += 32) {
+            const int o = goff_s[i];
+            dst[i] = (o >= 0) ? __ldg(src + o) : 0.f;
+          }
+        } else {
+          for (int i = lane; i < kWgQC; i += 32) dst[i] = 0.f;
+        }
+      }
+    }
+    __syncthreads();
+
+    if (active) {
+      const float* gp = gz_s + (4 * cog) * kWgQC;
+#pragma unroll 1
+      for (int q = 0; q < kWgQC; q += 4) {
+        float g[4][4];  // [co j][pos i]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(gp + j * kWgQC + q);
+          g[j][0] = v.x; g[j][1] = v.y; g[j][2] = v.z; g[j][3] = v.w;
+          bacc[j] += (v.x + v.y) + (v.z + v.w);
+        }
+#pragma unroll
+        for (int k = 0; k < NKT; ++k) {
+          const int kt = (KTS == 1) ? k : ktg;
+          const float* xp = x_s + (kt * a.Ci + ci) * a.NPs + q;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const float4 v0 = *reinterpret_cast<const float4*>(xp + kh * a.Wps);
+            const float2 v1 = *reinterpret_cast<const float2*>(xp + kh * a.Wps + 4);
+            const float xv[6] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y};
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  acc[k * 9 + kh * 3 + kw][j] = fmaf(g[j][i], xv[i + kw], acc[k * 9 + kh * 3 + kw][j]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- write this CTA's partial ----
+  if (active) {
+    float* part = a.partial + static_cast<long long>(blockIdx.x) * (static_cast<long long>(a.Co) * a.Ci * 27 + a.Co);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = 4 * cog + j;
+      if (co >= a.Co) continue;
+#pragma unroll
+      for (int k = 0; k < NKT; ++k) {
+        const int kt = (KTS == 1) ? k : ktg;
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          part[(static_cast<long long>(co) * a.Ci + ci) * 27 + kt * 9 + t] = acc[k * 9 + t][j];
+      }
+      if (ci == 0 && ktg == 0) part[static_cast<long long>(a.Co) * a.Ci * 27 + co] = bacc[j];
+    }
+  }
+}
+
+// dw[i] = sum over CTAs (fixed order) ; the last Co entries are db
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
+                                    int n_w, int n_b, int n_part) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = n_w + n_b;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < n_part; ++p) s += partial[static_cast<long long>(p) * n + i];
+  if (i < n_w) dw[i] = s;
+  else if (db) db[i - n_w] = s;
+}
+
+template <bool kI16, int KTS>
+static int launch_wgrad(WgradArgs a, int grid_x, int grid_y, int threads, size_t smem, cudaStream_t stream) {
+  PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_kernel<kI16, KTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv3d_wgrad_f32_kernel<kI16, KTS><<<dim3(grid_x, grid_y), threads, smem, stream>>>(a);
+  PVB_LAUNCHED("conv3d_wgrad_f32");
+  return PVB200_OK;
+}
+
+}  // namespace pvb
+
+extern "C" {
+
+size_t pvb200_conv3d_wgrad_workspace_bytes(int Cin, int Cout) {
+  return static_cast<size_t>(pvb::kWgMaxCtas) * (static_cast<size_t>(Cout) * Cin * 27 + Cout) * sizeof(float);
+}
+
+int pvb200_conv3d_wgrad_f32(const void* x, int x_is_i16, const float* mean, const float* std, const float* gz,
+                            float* dw, float* db, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
+                            int Hi, int Wi, int Cout, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(x && gz && dw, "conv3d_wgrad: null pointer");
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti > 2 && Hi > 2 && Wi > 2, "conv3d_wgrad: bad shape");
+  PVB_REQUIRE(Cin <= kWgMaxCi, "conv3d_wgrad: Cin=%d > %d not supported", Cin, kWgMaxCi);
+  PVB_REQUIRE(!x_is_i16 || (mean && std), "conv3d_wgrad: int16 input needs mean/std");
+  const size_t need = pvb200_conv3d_wgrad_workspace_bytes(Cin, Cout);
+  if (!workspace || workspace_bytes < need) {
+    set_error("conv3d_wgrad: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return PVB200_ERR_WORKSPACE;
+  }
+  WgradArgs a;
+  a.x = x; a.mean = mean; a.stdv = std; a.gz = gz; a.partial = static_cast<float*>(workspace);
+  a.B = B; a.Ci = Cin; a.Ti = Ti; a.Hi = Hi; a.Wi = Wi; a.Co = Cout;
+  a.To = Ti - 2; a.Ho = Hi - 2; a.Wo = Wi - 2;
+  a.Wps = round_up(Wi, 4);
+  a.NP = kWgQC + 2 * a.Wps + 8;
+  a.NPs = round_up(a.NP, 8) + 4;
+  const int Qtot = (a.Ho - 1) * a.Wps + a.Wo;
+  a.chunks_per_plane = ceil_div(Qtot, kWgQC);
+  a.total_chunks = static_cast<long long>(B) * a.To * a.chunks_per_plane;
+  a.ncog = ceil_div(Cout, 4);
+  // narrow layers (conv0: Cin = 12) split the 27 taps over 3 threads to keep the CTA full
+  const int kts = (a.ncog * Cin <= 128) ? 3 : 1;
+  a.items = a.ncog * Cin * kts;
+  const int cap = (kts == 1) ? 256 : 384;
+  const int grid_y = ceil_div(a.items, cap);
+  const int threads = round_up(ceil_div(a.items, grid_y), 32);
+  const int sms = sm_count();
+  PVB_REQUIRE(sms > 0, "conv3d_wgrad: no CUDA device");
+  long long gx = sms;  // one persistent CTA per SM (register- and smem-limited to 1 CTA/SM)
+  if (gx > kWgMaxCtas) gx = kWgMaxCtas;
+  if (gx > a.total_chunks) gx = a.total_chunks;
+  const size_t smem = (static_cast<size_t>(3) * Cin * a.NPs + 4 * a.ncog * kWgQC) * sizeof(float) +
+                      (a.NP + kWgQC) * sizeof(int);
+  PVB_REQUIRE(smem <= 227 * 1024, "conv3d_wgrad: Cin=%d, width %d needs %zu B of shared memory (> 227 KB)", Cin, Wi, smem);
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (x_is_i16)
+    rc = (kts == 1) ? launch_wgrad<true, 1>(a, (int)gx, grid_y, threads, smem, st)
+                    : launch_wgrad<true, 3>(a, (int)gx, grid_y, threads, smem, st);
+  else
+    rc = (kts == 1) ? launch_wgrad<false, 1>(a, (int)gx, grid_y, threads, smem, st)
+                    : launch_wgrad<false, 3>(a, (int)gx, grid_y, threads, smem, st);
+  if (rc != PVB200_OK) return rc;
+  // when the item space is split over grid_y, every y-slice wrote disjoint entries of the same partial rows
+  const int n_w = Cout * Cin * 27;
+  wgrad_reduce_kernel<<<ceil_div(n_w + Cout, 256), 256, 0, st>>>(a.partial, dw, db, n_w, Cout, (int)gx);
+  PVB_LAUNCHED("wgrad_reduce");
+  return PVB200_OK;
+}
+
+}  // extern "C"

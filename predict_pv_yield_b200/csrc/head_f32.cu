@@ -1,0 +1,500 @@
+// head_f32.cu -- a5-a9/a11: the fully connected head of the Conv3d PV model, forward and backward, fp32.
+//
+// Reference: predict_pv_yield/models/conv3d/model.py:122-154
+//   out = reshape(B, cnn_output_size); relu(fc1); relu(fc2); cat(PV history); cat(relu(fc_nwp(nwp)));
+//   relu(fc3); fc4; reshape(B, forecast_len)            (+ the autograd of those lines)
+//
+// fc1 is [F1=128] x [K1=1 103 872]: 565 MB of fp32 weights against a 32..256-row batch, i.e. a
+// weight-streaming GEMM that is HBM-bound on W1 for per-GPU batches <~ 200.  Kernels:
+//   fc1_fwd_splitk   : split-K over ~4 CTAs/SM, each streams a K-range of W1 and x through smem and
+//                      writes a [B x F1] partial (deterministic: partials summed in order by the tail)
+//   head_tail_fwd    : per-sample CTA: sum partials + bias + ReLU, fc2, concat, fc_nwp, fc3, fc4
+//   head_tail_bwd    : per-sample CTA: back through fc4, fc3, concat split, fc2 (ReLU masks fused)
+//   linear_wgrad_small: dW = Gz^T In, db = sum Gz for the small layers (fc2, fc3, fc4, fc_nwp, fc1 bias)
+//   fc1_wgrad        : dW1 tile [128 j x 128 k] = G1^T X, written once (565 MB, HBM-write-bound)
+//   fc1_dgrad        : gx = (G1 W1) * (x > 0): streams W1 once more, ReLU mask of the last conv fused
+#include <float.h>
+
+#include "common.cuh"
+
+namespace pvb {
+
+constexpr int kHeadThreads = 256;
+constexpr int kFc1KT = 64;          // K columns per smem stage (forward)
+constexpr int kFc1BT = 32;          // batch rows per tile
+constexpr int kFc1JT = 128;         // fc1 output features per tile
+constexpr int kFc1TargetCtas = 592; // ~4 CTAs per SM on 148 SMs
+
+// ---- split-K planning shared by the workspace query and the launcher --------------------------------
+struct Fc1Plan {
+  int nbt;              // batch tiles
+  int njt;              // feature tiles
+  int S;                // K splits
+  long long k_per_split;
+};
+
+static Fc1Plan fc1_plan(int B, int F1, long long K1) {
+  Fc1Plan p;
+  p.nbt = ceil_div(B, kFc1BT);
+  p.njt = ceil_div(F1, kFc1JT);
+  long long stages = ceil_div(K1, (long long)kFc1KT);
+  long long S = kFc1TargetCtas / (p.nbt * p.njt);
+  if (S < 1) S = 1;
+  if (S > stages) S = stages;
+  p.k_per_split = ceil_div(stages, S) * kFc1KT;
+  p.S = static_cast<int>(ceil_div(K1, p.k_per_split));
+  return p;
+}
+
+// ---- fc1 forward, split-K -----------------------------------------------------------------------------
+// partial[s][b][j] = sum_{k in split s} x[b][k] * w[j][k]
+__global__ void __launch_bounds__(kHeadThreads)
+fc1_fwd_splitk_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ partial, int B,
+                      int F1, long long K1, int nbt, int njt, long long k_per_split, int vec_ok) {
+  constexpr int LD = kFc1KT + 4;  // row stride 68 words: == 4 (mod 32) -> conflict-free LDS.128 across rows
+  __shared__ __align__(16) float ws[kFc1JT * LD];
+  __shared__ __align__(16) float xs[kFc1BT * LD];
+
+  int id = blockIdx.x;
+  const int bt = id % nbt; id /= nbt;
+  const int jt = id % njt;
+  const int s = id / njt;
+  const int b0 = bt * kFc1BT, j0 = jt * kFc1JT;
+  const long long kb = s * k_per_split;
+  const long long ke = min(K1, kb + k_per_split);
+
+  const int tid = threadIdx.x;
+  const int jg = tid & 31;  // rows jg, jg+32, jg+64, jg+96 of the feature tile
+  const int bg = tid >> 5;  // batch rows 4bg..4bg+3 (warp-uniform -> x reads broadcast)
+
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+  for (long long k0 = kb; k0 < ke; k0 += kFc1KT) {
+    __syncthreads();
+    const bool full = vec_ok && (k0 + kFc1KT <= ke);
+    if (full) {
+      // W tile: 128 rows x 16 float4
+      for (int idx = tid; idx < kFc1JT * (kFc1KT / 4); idx += kHeadThreads) {
+        const int r = idx >> 4, c4 = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 + r < F1) v = __ldcs(reinterpret_cast<const float4*>(w + static_cast<long long>(j0 + r) * K1 + k0) + c4);
+        *reinterpret_cast<float4*>(ws + r * LD + 4 * c4) = v;
+      }
+      for (int idx = tid; idx < kFc1BT * (kFc1KT / 4); idx += kHeadThreads) {
+        const int r = idx >> 4, c4 = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + r < B) v = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(b0 + r) * K1 + k0) + c4);
+        *reinterpret_cast<float4*>(xs + r * LD + 4 * c4) = v;
+      }
+    } else {
+      for (int idx = tid; idx < kFc1JT * kFc1KT; idx += kHeadThreads) {
+        const int r = idx / kFc1KT, c = idx % kFc1KT;
+        float v = 0.f;
+        if (j0 + r < F1 && k0 + c < ke) v = w[static_cast<long long>(j0 + r) * K1 + k0 + c];
+        ws[r * LD + c] = v;
+      }
+      for (int idx = tid; idx < kFc1BT * kFc1KT; idx += kHeadThreads) {
+        const int r = idx / kFc1KT, c = idx % kFc1KT;
+        float v = 0.f;
+        if (b0 + r < B && k0 + c < ke) v = x[static_cast<long long>(b0 + r) * K1 + k0 + c];
+        xs[r * LD + c] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k4 = 0; k4 < kFc1KT; k4 += 4) {
+      float4 wv[4], xv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) wv[r] = *reinterpret_cast<const float4*>(ws + (jg + 32 * r) * LD + k4);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (4 * bg + c) * LD + k4);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[r][c] = fmaf(wv[r].x, xv[c].x, acc[r][c]);
+          acc[r][c] = fmaf(wv[r].y, xv[c].y, acc[r][c]);
+          acc[r][c] = fmaf(wv[r].z, xv[c].z, acc[r][c]);
+          acc[r][c] = fmaf(wv[r].w, xv[c].w, acc[r][c]);
+        }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int j = j0 + jg + 32 * r;
+    if (j >= F1) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int b = b0 + 4 * bg + c;
+      if (b < B) partial[(static_cast<long long>(s) * B + b) * F1 + j] = acc[r][c];
+    }
+  }
+}
+
+__device__ __forceinline__ float nan_to_num_f(float v) {  // torch.nan_to_num defaults (model.py:131)
+  if (isnan(v)) return 0.f;
+  if (isinf(v)) return v > 0.f ? FLT_MAX : -FLT_MAX;
+  return v;
+}
+
+// warp-cooperative dot product of a weight row with a shared-memory vector
+__device__ __forceinline__ float warp_dot(const float* __restrict__ wrow, const float* vec, int n, int lane) {
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) s = fmaf(__ldg(wrow + i), vec[i], s);
+  return warp_sum(s);
+}
+
+// ---- tail forward: one CTA per sample -------------------------------------------------------------------
+__global__ void __launch_bounds__(kHeadThreads) head_tail_fwd_kernel(const pvb200_head_t h, const float* __restrict__ partial, int S) {
+  extern __shared__ float sm[];
+  const int NCAT = h.F2 + h.NPV + (h.NNWP > 0 ? h.FNWP : 0);
+  float* h1 = sm;                 // [F1]
+  float* cat = h1 + h.F1;         // [NCAT]
+  float* h3 = cat + NCAT;         // [F3]
+  float* nw = h3 + h.F3;          // [NNWP]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kHeadThreads / 32;
+
+  for (int j = tid; j < h.F1; j += kHeadThreads) {
+    float s = 0.f;
+    for (int p = 0; p < S; ++p) s += partial[(static_cast<long long>(p) * h.B + b) * h.F1 + j];
+    s += __ldg(h.b1 + j);
+    s = (s < 0.f) ? 0.f : s;
+    h1[j] = s;
+    h.h1[static_cast<long long>(b) * h.F1 + j] = s;
+  }
+  for (int i = tid; i < h.NNWP; i += kHeadThreads) nw[i] = h.nwp[static_cast<long long>(b) * h.NNWP + i];
+  for (int i = tid; i < h.NPV; i += kHeadThreads) {
+    const int t = i / h.pv_ns, s = i - t * h.pv_ns;
+    cat[h.F2 + i] = nan_to_num_f(h.pv[b * h.pv_sb + t * h.pv_st + s]);
+  }
+  __syncthreads();
+  for (int i = warp; i < h.F2; i += nwarp) {  // fc2 + ReLU
+    float s = warp_dot(h.w2 + static_cast<long long>(i) * h.F1, h1, h.F1, lane) + __ldg(h.b2 + i);
+    if (lane == 0) cat[i] = (s < 0.f) ? 0.f : s;
+  }
+  if (h.NNWP > 0) {
+    for (int i = warp; i < h.FNWP; i += nwarp) {  // fc_nwp + ReLU
+      float s = warp_dot(h.wn + static_cast<long long>(i) * h.NNWP, nw, h.NNWP, lane) + __ldg(h.bn + i);
+      if (lane == 0) cat[h.F2 + h.NPV + i] = (s < 0.f) ? 0.f : s;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < NCAT; i += kHeadThreads) h.cat[static_cast<long long>(b) * NCAT + i] = cat[i];
+  for (int i = warp; i < h.F3; i += nwarp) {  // fc3 + ReLU
+    float s = warp_dot(h.w3 + static_cast<long long>(i) * NCAT, cat, NCAT, lane) + __ldg(h.b3 + i);
+    s = (s < 0.f) ? 0.f : s;
+    if (lane == 0) { h3[i] = s; h.h3[static_cast<long long>(b) * h.F3 + i] = s; }
+  }
+  __syncthreads();
+  for (int i = warp; i < h.FO; i += nwarp) {  // fc4
+    float s = warp_dot(h.w4 + static_cast<long long>(i) * h.F3, h3, h.F3, lane) + __ldg(h.b4 + i);
+    if (lane == 0) h.out[static_cast<long long>(b) * h.FO + i] = s;
+  }
+}
+
+// ---- tail backward: one CTA per sample ------------------------------------------------------------------
+__global__ void __launch_bounds__(kHeadThreads) head_tail_bwd_kernel(const pvb200_head_t h) {
+  extern __shared__ float sm[];
+  const int NCAT = h.F2 + h.NPV + (h.NNWP > 0 ? h.FNWP : 0);
+  float* go = sm;            // [FO]
+  float* g3 = go + h.FO;     // [F3]
+  float* gc = g3 + h.F3;     // [NCAT]
+  const int b = blockIdx.x, tid = threadIdx.x;
+
+  for (int i = tid; i < h.FO; i += kHeadThreads) go[i] = h.g_out[static_cast<long long>(b) * h.FO + i];
+  __syncthreads();
+  for (int i = tid; i < h.F3; i += kHeadThreads) {  // through fc4, ReLU mask of fc3
+    float s = 0.f;
+    for (int o = 0; o < h.FO; ++o) s = fmaf(__ldg(h.w4 + static_cast<long long>(o) * h.F3 + i), go[o], s);
+    s = (h.h3[static_cast<long long>(b) * h.F3 + i] > 0.f) ? s : 0.f;
+    g3[i] = s;
+    h.g_h3[static_cast<long long>(b) * h.F3 + i] = s;
+  }
+  __syncthreads();
+  for (int c = tid; c < NCAT; c += kHeadThreads) {  // through fc3, split the concat, ReLU masks of fc2 / fc_nwp
+    float s = 0.f;
+    for (int i = 0; i < h.F3; ++i) s = fmaf(__ldg(h.w3 + static_cast<long long>(i) * NCAT + c), g3[i], s);
+    const bool is_pv = (c >= h.F2) && (c < h.F2 + h.NPV);
+    if (is_pv) s = 0.f;  // inputs need no gradient
+    else s = (h.cat[static_cast<long long>(b) * NCAT + c] > 0.f) ? s : 0.f;
+    gc[c] = s;
+    h.g_cat[static_cast<long long>(b) * NCAT + c] = s;
+  }
+  __syncthreads();
+  for (int j = tid; j < h.F1; j += kHeadThreads) {  // through fc2, ReLU mask of fc1
+    float s = 0.f;
+    for (int i = 0; i < h.F2; ++i) s = fmaf(__ldg(h.w2 + static_cast<long long>(i) * h.F1 + j), gc[i], s);
+    s = (h.h1[static_cast<long long>(b) * h.F1 + j] > 0.f) ? s : 0.f;
+    h.g_h1[static_cast<long long>(b) * h.F1 + j] = s;
+  }
+}
+
+// ---- small weight gradients: dW[o][i] = sum_b gz[b*ldg + o] * in[b*ldi + i];  db[o] = sum_b gz -----------
+__global__ void linear_wgrad_small_kernel(const float* __restrict__ gz, int ldg, const float* __restrict__ in, int ldi,
+                                          float* __restrict__ dW, float* __restrict__ db, int B, int O, int I) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(O) * I;
+  if (idx < n) {
+    const int o = static_cast<int>(idx / I), i = static_cast<int>(idx - static_cast<long long>(o) * I);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(gz[static_cast<long long>(b) * ldg + o], in[static_cast<long long>(b) * ldi + i], s);
+    dW[idx] = s;
+  } else if (idx < n + O && db) {
+    const int o = static_cast<int>(idx - n);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += gz[static_cast<long long>(b) * ldg + o];
+    db[o] = s;
+  }
+}
+
+// ---- fc1 weight gradient: dW1[j][k] = sum_b g1[b][j] * x[b][k] ----------------------------------------------
+__global__ void __launch_bounds__(kHeadThreads)
+fc1_wgrad_kernel(const float* __restrict__ g1, const float* __restrict__ x, float* __restrict__ dW, int B, int F1,
+                 long long K1, int njt, int vec_ok) {
+  constexpr int KT = 128;
+  __shared__ __align__(16) float gs[kFc1BT * kFc1JT];  // [b][j]
+  __shared__ __align__(16) float xs[kFc1BT * KT];      // [b][k]
+  int id = blockIdx.x;
+  const int jt = id % njt;
+  const long long k0 = static_cast<long long>(id / njt) * KT;
+  const int j0 = jt * kFc1JT;
+  const int tid = threadIdx.x;
+  const int tk = tid & 15;  // k columns 4tk..4tk+3 and 64+4tk..64+4tk+3
+  const int tj = tid >> 4;  // j rows 8tj..8tj+7
+
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+  for (int b0 = 0; b0 < B; b0 += kFc1BT) {
+    __syncthreads();
+    for (int idx = tid; idx < kFc1BT * kFc1JT; idx += kHeadThreads) {
+      const int r = idx >> 7, c = idx & 127;
+      gs[idx] = (b0 + r < B && j0 + c < F1) ? g1[static_cast<long long>(b0 + r) * F1 + j0 + c] : 0.f;
+    }
+    if (vec_ok && k0 + KT <= K1) {
+      for (int idx = tid; idx < kFc1BT * (KT / 4); idx += kHeadThreads) {
+        const int r = idx >> 5, c4 = idx & 31;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + r < B) v = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(b0 + r) * K1 + k0) + c4);
+        *reinterpret_cast<float4*>(xs + r * KT + 4 * c4) = v;
+      }
+    } else {
+      for (int idx = tid; idx < kFc1BT * KT; idx += kHeadThreads) {
+        const int r = idx >> 7, c = idx & 127;
+        xs[idx] = (b0 + r < B && k0 + c < K1) ? x[static_cast<long long>(b0 + r) * K1 + k0 + c] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int b = 0; b < kFc1BT; ++b) {
+      const float4 ga = *reinterpret_cast<const float4*>(gs + b * kFc1JT + 8 * tj);
+      const float4 gb = *reinterpret_cast<const float4*>(gs + b * kFc1JT + 8 * tj + 4);
+      const float4 xa = *reinterpret_cast<const float4*>(xs + b * KT + 4 * tk);
+      const float4 xb = *reinterpret_cast<const float4*>(xs + b * KT + 64 + 4 * tk);
+      const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(gv[r], xv[c], acc[r][c]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int j = j0 + 8 * tj + r;
+    if (j >= F1) continue;
+    float* row = dW + static_cast<long long>(j) * K1 + k0;
+    if (vec_ok && k0 + KT <= K1) {
+      __stcs(reinterpret_cast<float4*>(row + 4 * tk), make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+      __stcs(reinterpret_cast<float4*>(row + 64 + 4 * tk), make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]));
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const long long k = k0 + (c < 4 ? 4 * tk + c : 64 + 4 * tk + (c - 4));
+        if (k < K1) dW[static_cast<long long>(j) * K1 + k] = acc[r][c];
+      }
+    }
+  }
+}
+
+// ---- fc1 data gradient: gx[b][k] = (sum_j g1[b][j] * w[j][k]) * (x[b][k] > 0) ----------------------------------
+__global__ void __launch_bounds__(kHeadThreads)
+fc1_dgrad_kernel(const float* __restrict__ g1, const float* __restrict__ w, const float* __restrict__ x,
+                 float* __restrict__ gx, int B, int F1, long long K1, int nbt, int vec_ok) {
+  constexpr int KT = 128, JT = 32;
+  __shared__ __align__(16) float ws[JT * KT];       // [j][k]
+  __shared__ __align__(16) float gsT[JT * kFc1BT];  // [j][b]
+  int id = blockIdx.x;
+  const int bt = id % nbt;
+  const long long k0 = static_cast<long long>(id / nbt) * KT;
+  const int b0 = bt * kFc1BT;
+  const int tid = threadIdx.x;
+  const int tk = tid & 31;  // k columns 4tk..4tk+3
+  const int tb = tid >> 5;  // batch rows 4tb..4tb+3 (warp-uniform)
+  const bool full = vec_ok && (k0 + KT <= K1);
+
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+  for (int j0 = 0; j0 < F1; j0 += JT) {
+    __syncthreads();
+    if (full) {
+      for (int idx = tid; idx < JT * (KT / 4); idx += kHeadThreads) {
+        const int r = idx >> 5, c4 = idx & 31;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 + r < F1) v = __ldcs(reinterpret_cast<const float4*>(w + static_cast<long long>(j0 + r) * K1 + k0) + c4);
+        *reinterpret_cast<float4*>(ws + r * KT + 4 * c4) = v;
+      }
+    } else {
+      for (int idx = tid; idx < JT * KT; idx += kHeadThreads) {
+        const int r = idx >> 7, c = idx & 127;
+        ws[idx] = (j0 + r < F1 && k0 + c < K1) ? w[static_cast<long long>(j0 + r) * K1 + k0 + c] : 0.f;
+      }
+    }
+    for (int idx = tid; idx < JT * kFc1BT; idx += kHeadThreads) {
+      const int r = idx >> 5, c = idx & 31;  // r: j, c: b
+      gsT[idx] = (j0 + r < F1 && b0 + c < B) ? g1[static_cast<long long>(b0 + c) * F1 + j0 + r] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < JT; ++j) {
+      const float4 wv = *reinterpret_cast<const float4*>(ws + j * KT + 4 * tk);
+      const float4 gv = *reinterpret_cast<const float4*>(gsT + j * kFc1BT + 4 * tb);
+      const float g[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        acc[r][0] = fmaf(g[r], wv.x, acc[r][0]);
+        acc[r][1] = fmaf(g[r], wv.y, acc[r][1]);
+        acc[r][2] = fmaf(g[r], wv.z, acc[r][2]);
+        acc[r][3] = fmaf(g[r], wv.w, acc[r][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int b = b0 + 4 * tb + r;
+    if (b >= B) continue;
+    const long long base = static_cast<long long>(b) * K1 + k0 + 4 * tk;
+    if (full) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + base));
+      float4 o;
+      o.x = xv.x > 0.f ? acc[r][0] : 0.f;
+      o.y = xv.y > 0.f ? acc[r][1] : 0.f;
+      o.z = xv.z > 0.f ? acc[r][2] : 0.f;
+      o.w = xv.w > 0.f ? acc[r][3] : 0.f;
+      *reinterpret_cast<float4*>(gx + base) = o;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (k0 + 4 * tk + c < K1) gx[base + c] = (x[base + c] > 0.f) ? acc[r][c] : 0.f;
+    }
+  }
+}
+
+static int check_head(const pvb200_head_t* h) {
+  PVB_REQUIRE(h != nullptr, "head: null descriptor");
+  PVB_REQUIRE(h->struct_size == sizeof(pvb200_head_t), "head: struct_size %zu != %zu (ABI mismatch)", h->struct_size,
+              sizeof(pvb200_head_t));
+  PVB_REQUIRE(h->B > 0 && h->F1 > 0 && h->F2 > 0 && h->F3 > 0 && h->FO > 0 && h->K1 > 0, "head: bad sizes");
+  PVB_REQUIRE(h->NPV >= 0 && h->NNWP >= 0, "head: bad branch sizes");
+  PVB_REQUIRE(h->NPV == 0 || (h->pv && h->pv_ns > 0 && h->NPV % h->pv_ns == 0), "head: bad PV-history description");
+  PVB_REQUIRE(h->NNWP == 0 || (h->nwp && h->wn && h->bn && h->FNWP > 0), "head: NWP branch needs nwp, wn, bn");
+  PVB_REQUIRE(h->w1 && h->b1 && h->w2 && h->b2 && h->w3 && h->b3 && h->w4 && h->b4 && h->x, "head: null parameter");
+  return PVB200_OK;
+}
+
+static bool vec4_ok(const void* p, long long ld) { return (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(p) % 16 == 0); }
+
+}  // namespace pvb
+
+extern "C" {
+
+size_t pvb200_head_fwd_workspace_bytes(int B, int F1, long long K1) {
+  if (B <= 0 || F1 <= 0 || K1 <= 0) return 0;
+  const pvb::Fc1Plan p = pvb::fc1_plan(B, F1, K1);
+  return static_cast<size_t>(p.S) * B * F1 * sizeof(float);
+}
+
+int pvb200_head_fwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
+  using namespace pvb;
+  int rc = check_head(h);
+  if (rc) return rc;
+  PVB_REQUIRE(h->h1 && h->cat && h->h3 && h->out, "head_fwd: null output");
+  const Fc1Plan p = fc1_plan(h->B, h->F1, h->K1);
+  const size_t need = static_cast<size_t>(p.S) * h->B * h->F1 * sizeof(float);
+  if (!h->workspace || h->workspace_bytes < need) {
+    set_error("head_fwd: workspace too small (%zu < %zu bytes)", h->workspace_bytes, need);
+    return PVB200_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  float* partial = static_cast<float*>(h->workspace);
+  const int vec = vec4_ok(h->x, h->K1) && vec4_ok(h->w1, h->K1);
+  const long long ctas = static_cast<long long>(p.S) * p.nbt * p.njt;
+  fc1_fwd_splitk_kernel<<<static_cast<unsigned>(ctas), kHeadThreads, 0, st>>>(h->x, h->w1, partial, h->B, h->F1, h->K1,
+                                                                               p.nbt, p.njt, p.k_per_split, vec);
+  PVB_LAUNCHED("fc1_fwd_splitk");
+  const int NCAT = h->F2 + h->NPV + (h->NNWP > 0 ? h->FNWP : 0);
+  const size_t smem = static_cast<size_t>(h->F1 + NCAT + h->F3 + h->NNWP) * sizeof(float);
+  PVB_REQUIRE(smem <= 48 * 1024, "head_fwd: feature sizes too large for the tail kernel (%zu B smem)", smem);
+  head_tail_fwd_kernel<<<h->B, kHeadThreads, smem, st>>>(*h, partial, p.S);
+  PVB_LAUNCHED("head_tail_fwd");
+  return PVB200_OK;
+}
+
+int pvb200_head_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
+  using namespace pvb;
+  int rc = check_head(h);
+  if (rc) return rc;
+  PVB_REQUIRE(h->h1 && h->cat && h->h3 && h->g_out && h->g_h3 && h->g_cat && h->g_h1, "head_bwd: null buffer");
+  PVB_REQUIRE(h->dw1 && h->db1 && h->dw2 && h->db2 && h->dw3 && h->db3 && h->dw4 && h->db4, "head_bwd: null grad");
+  PVB_REQUIRE(h->NNWP == 0 || (h->dwn && h->dbn), "head_bwd: NWP branch needs dwn, dbn");
+  cudaStream_t st = as_stream(stream);
+  const int NCAT = h->F2 + h->NPV + (h->NNWP > 0 ? h->FNWP : 0);
+  const size_t smem = static_cast<size_t>(h->FO + h->F3 + NCAT) * sizeof(float);
+  PVB_REQUIRE(smem <= 48 * 1024, "head_bwd: feature sizes too large for the tail kernel (%zu B smem)", smem);
+  head_tail_bwd_kernel<<<h->B, kHeadThreads, smem, st>>>(*h);
+  PVB_LAUNCHED("head_tail_bwd");
+
+  auto small = [&](const float* gz, int ldg, const float* in, int ldi, float* dW, float* db, int O, int I) -> int {
+    const long long n = static_cast<long long>(O) * I + O;
+    linear_wgrad_small_kernel<<<static_cast<unsigned>(ceil_div(n, 256LL)), 256, 0, st>>>(gz, ldg, in, ldi, dW, db, h->B, O, I);
+    PVB_LAUNCHED("linear_wgrad_small");
+    return PVB200_OK;
+  };
+  if ((rc = small(h->g_out, h->FO, h->h3, h->F3, h->dw4, h->db4, h->FO, h->F3))) return rc;
+  if ((rc = small(h->g_h3, h->F3, h->cat, NCAT, h->dw3, h->db3, h->F3, NCAT))) return rc;
+  if ((rc = small(h->g_cat, NCAT, h->h1, h->F1, h->dw2, h->db2, h->F2, h->F1))) return rc;
+  if (h->NNWP > 0)
+    if ((rc = small(h->g_cat + h->F2 + h->NPV, NCAT, h->nwp, h->NNWP, h->dwn, h->dbn, h->FNWP, h->NNWP))) return rc;
+  // fc1 bias gradient (I = 0 columns: only the db part of the kernel runs)
+  {
+    linear_wgrad_small_kernel<<<ceil_div(h->F1, 256), 256, 0, st>>>(h->g_h1, h->F1, h->g_h1, h->F1, h->dw1, h->db1, h->B,
+                                                                    h->F1, 0);
+    PVB_LAUNCHED("fc1_bias_grad");
+  }
+  const int vec = vec4_ok(h->x, h->K1) && vec4_ok(h->w1, h->K1) && vec4_ok(h->dw1, h->K1) && (!h->g_x || vec4_ok(h->g_x, h->K1));
+  const int njt = ceil_div(h->F1, kFc1JT);
+  const long long kt = ceil_div(h->K1, 128LL);
+  PVB_REQUIRE(kt * njt <= 0x7fffffffLL, "head_bwd: K1 too large");
+  fc1_wgrad_kernel<<<static_cast<unsigned>(kt * njt), kHeadThreads, 0, st>>>(h->g_h1, h->x, h->dw1, h->B, h->F1, h->K1, njt, vec);
+  PVB_LAUNCHED("fc1_wgrad");
+  if (h->g_x) {
+    const int nbt = ceil_div(h->B, kFc1BT);
+    PVB_REQUIRE(kt * nbt <= 0x7fffffffLL, "head_bwd: K1*B too large");
+    fc1_dgrad_kernel<<<static_cast<unsigned>(kt * nbt), kHeadThreads, 0, st>>>(h->g_h1, h->w1, h->x, h->g_x, h->B, h->F1, h->K1, nbt, vec);
+    PVB_LAUNCHED("fc1_dgrad");
+  }
+  return PVB200_OK;
+}
+
+}  // extern "C"

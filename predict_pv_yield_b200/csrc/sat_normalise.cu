@@ -1,0 +1,136 @@
+// sat_normalise.cu -- a1/a2: int16 satellite cube -> normalised fp32 / bf16, NCDHW in, NCDHW out.
+//
+// Reference arithmetic: predict_pv_yield/netcdf_dataset.py:96-101
+//     sat = sat.astype(np.float32); sat = sat - SAT_MEAN; sat /= SAT_STD
+// i.e. two separately rounded IEEE fp32 operations with a true division; reproduced with
+// __fsub_rn / __fdiv_rn so the compiler can neither contract to FMA nor use a reciprocal.
+//
+// HBM-bound streaming kernel: one (b,c) plane per blockIdx.x so the per-channel constants are
+// block-uniform; each thread moves 8 int16 per 128-bit load (4 loads in flight) and writes
+// 2 x 128-bit (fp32) or 1 x 128-bit (bf16) stores.  Algorithmic bytes per element: 2 in + 4 (2) out.
+#include "common.cuh"
+
+namespace pvb {
+
+constexpr int kNormThreads = 256;
+constexpr int kNormUnroll = 4;
+
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void norm8(const uint4& q, float mean, float stdv, float (&o)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[2 * i + 0] = sat_norm(static_cast<int16_t>(w[i] & 0xffffu), mean, stdv);
+    o[2 * i + 1] = sat_norm(static_cast<int16_t>(w[i] >> 16), mean, stdv);
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  // RNE conversion of each half (cvt.rn.bf16.f32)
+  __nv_bfloat16 a = __float2bfloat16_rn(lo), b = __float2bfloat16_rn(hi);
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kNormThreads)
+sat_normalise_vec_kernel(const int16_t* __restrict__ x, void* __restrict__ y, const float* __restrict__ mean,
+                         const float* __restrict__ stdv, int C, long long thw) {
+  const long long plane = blockIdx.x;
+  const int c = static_cast<int>(plane % C);
+  const float m = __ldg(mean + c), s = __ldg(stdv + c);
+  const long long nvec = thw >> 3;
+  const uint4* xin = reinterpret_cast<const uint4*>(x + plane * thw);
+  long long v0 = (static_cast<long long>(blockIdx.y) * kNormUnroll) * kNormThreads + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.y) * kNormUnroll * kNormThreads;
+  for (; v0 < nvec; v0 += stride) {
+    uint4 q[kNormUnroll];
+#pragma unroll
+    for (int u = 0; u < kNormUnroll; ++u) {
+      const long long v = v0 + static_cast<long long>(u) * kNormThreads;
+      if (v < nvec) q[u] = ld_stream_u4(xin + v);
+    }
+#pragma unroll
+    for (int u = 0; u < kNormUnroll; ++u) {
+      const long long v = v0 + static_cast<long long>(u) * kNormThreads;
+      if (v < nvec) {
+        float o[8];
+        norm8(q[u], m, s, o);
+        if (kBf16) {
+          uint4 r = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                               pack_bf16x2(o[6], o[7]));
+          __stcs(reinterpret_cast<uint4*>(static_cast<uint16_t*>(y) + plane * thw) + v, r);
+        } else {
+          float4* yo = reinterpret_cast<float4*>(static_cast<float*>(y) + plane * thw) + 2 * v;
+          __stcs(yo, make_float4(o[0], o[1], o[2], o[3]));
+          __stcs(yo + 1, make_float4(o[4], o[5], o[6], o[7]));
+        }
+      }
+    }
+  }
+}
+
+// scalar fallback for planes whose size is not a multiple of 8 (or misaligned pointers)
+template <bool kBf16>
+__global__ void __launch_bounds__(kNormThreads)
+sat_normalise_scalar_kernel(const int16_t* __restrict__ x, void* __restrict__ y, const float* __restrict__ mean,
+                            const float* __restrict__ stdv, int C, long long thw) {
+  const long long plane = blockIdx.x;
+  const int c = static_cast<int>(plane % C);
+  const float m = __ldg(mean + c), s = __ldg(stdv + c);
+  for (long long i = static_cast<long long>(blockIdx.y) * kNormThreads + threadIdx.x; i < thw;
+       i += static_cast<long long>(gridDim.y) * kNormThreads) {
+    const float o = sat_norm(x[plane * thw + i], m, s);
+    if (kBf16)
+      static_cast<uint16_t*>(y)[plane * thw + i] = __bfloat16_as_ushort(__float2bfloat16_rn(o));
+    else
+      static_cast<float*>(y)[plane * thw + i] = o;
+  }
+}
+
+template <bool kBf16>
+static int launch_normalise(const int16_t* x, void* y, const float* mean, const float* stdv, int B, int C,
+                            long long thw, cudaStream_t stream) {
+  PVB_REQUIRE(x && y && mean && stdv, "sat_normalise: null pointer");
+  PVB_REQUIRE(B > 0 && C > 0 && thw > 0, "sat_normalise: bad shape B=%d C=%d thw=%lld", B, C, thw);
+  const long long planes = static_cast<long long>(B) * C;
+  PVB_REQUIRE(planes <= 0x7fffffffLL, "sat_normalise: too many planes");
+  const bool vec = (thw % 8 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(y) % 16 == 0);
+  if (vec) {
+    const long long per_block = static_cast<long long>(kNormThreads) * kNormUnroll;
+    long long gy = ceil_div(thw >> 3, per_block);
+    if (gy > 64) gy = 64;
+    dim3 grid(static_cast<unsigned>(planes), static_cast<unsigned>(gy));
+    sat_normalise_vec_kernel<kBf16><<<grid, kNormThreads, 0, stream>>>(x, y, mean, stdv, C, thw);
+  } else {
+    long long gy = ceil_div(thw, static_cast<long long>(kNormThreads) * 8);
+    if (gy > 64) gy = 64;
+    dim3 grid(static_cast<unsigned>(planes), static_cast<unsigned>(gy));
+    sat_normalise_scalar_kernel<kBf16><<<grid, kNormThreads, 0, stream>>>(x, y, mean, stdv, C, thw);
+  }
+  PVB_LAUNCHED("sat_normalise");
+  return PVB200_OK;
+}
+
+}  // namespace pvb
+
+extern "C" {
+
+int pvb200_sat_normalise_f32(const int16_t* x, float* y, const float* mean, const float* std, int B, int C,
+                             long long thw, pvb200_stream_t stream) {
+  return pvb::launch_normalise<false>(x, y, mean, std, B, C, thw, pvb::as_stream(stream));
+}
+
+int pvb200_sat_normalise_bf16(const int16_t* x, uint16_t* y, const float* mean, const float* std, int B, int C,
+                              long long thw, pvb200_stream_t stream) {
+  return pvb::launch_normalise<true>(x, y, mean, std, B, C, thw, pvb::as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+"""Conv3d PV-yield model -- drop-in for ``predict_pv_yield.models.conv3d.model.Model``.
+
+Mirrors ``predict_pv_yield/models/conv3d/model.py:14-156``: same constructor arguments and defaults
+(``:18-32``), same attributes (``cnn_output_size`` ``:74-78``), same sub-module names and shapes
+(``sat_conv0``, ``conv3d_{i}``, ``fc1``..``fc4``, ``fc_nwp``; ``:80-103``) so ``state_dict`` /
+``load_state_dict`` interoperate with reference checkpoints, same ``forward(x)`` contract (dict or
+BatchML in, fp32 ``[B, forecast_len]`` out; ``:107-156``).
+
+What differs is where the arithmetic runs.  The ``nn.Conv3d`` / ``nn.Linear`` members only HOLD the
+parameters (torch default init, reference key names); their ``forward`` is never called.  The step is
+executed by hand-written sm_100a kernels in ``libpvb200.so``:
+
+  int16 satellite cube --(fused normalise, netcdf_dataset.py:96-101)--> conv0+ReLU -> conv_l+ReLU ...
+     -> flatten (NCDHW order, model.py:122) -> fc1 (split-K weight-streaming GEMM) -> fused tail
+     [fc2, PV-history nan_to_num+concat, fc_nwp, concat, fc3, fc4]
+
+There is no CPU fallback: tensors must live on a CUDA device and ``libpvb200.so`` must be built.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+from torch import nn
+
+from ..base_model import BaseModel
+from ...batch import as_batch
+from ... import ops
+
+logging.basicConfig()
+_LOG = logging.getLogger("predict_pv_yield_b200")
+
+# predict_pv_yield/netcdf_dataset.py:16-32 (channel order HRV, IR_016, IR_039, IR_087, IR_097, IR_108,
+# IR_120, IR_134, VIS006, VIS008, WV_062, WV_073)
+SAT_MEAN = np.array(
+    [93.23458, 131.71373, 843.7779, 736.6148, 771.1189, 589.66034,
+     862.29816, 927.69586, 90.70885, 107.58985, 618.4583, 532.47394], dtype=np.float32)
+SAT_STD = np.array(
+    [115.34247, 139.92636, 36.99538, 57.366386, 30.346825,
+     149.68007, 51.70631, 35.872967, 115.77212, 120.997154,
+     98.57828, 99.76469], dtype=np.float32)
+
+
+class Model(BaseModel):
+
+    name = "conv3d"
+
+    def __init__(
+        self,
+        include_pv_yield: bool = True,
+        include_nwp: bool = True,
+        forecast_minutes: int = 30,
+        history_minutes: int = 60,
+        number_of_conv3d_layers: int = 4,
+        conv3d_channels: int = 32,
+        image_size_pixels: int = 64,
+        number_sat_channels: int = 12,
+        fc1_output_features: int = 128,
+        fc2_output_features: int = 128,
+        fc3_output_features: int = 64,
+        output_variable: str = "pv_yield",
+    ):
+        """
+        3d conv model, that takes in different data streams (same arguments as the reference model).
+
+        include_pv_yield: include pv yield history
+        include_nwp: include nwp data
+        forecast_minutes / history_minutes: forecast horizon / history length in minutes
+        number_of_conv3d_layers, conv3d_channels: depth and width of the Conv3d encoder
+        image_size_pixels: the input satellite image size
+        number_sat_channels: number of satellite channels
+        fc{1,2,3}_output_features: widths of the fully connected layers
+        output_variable: 'pv_yield' or 'gsp_yield'
+        """
+        # stored BEFORE BaseModel.__init__, which reads them (model.py:57-68)
+        self.include_pv_yield = include_pv_yield
+        self.include_nwp = include_nwp
+        self.number_of_conv3d_layers = number_of_conv3d_layers
+        self.number_of_nwp_features = 10 * 19 * 2 * 2
+        self.fc1_output_features = fc1_output_features
+        self.fc2_output_features = fc2_output_features
+        self.fc3_output_features = fc3_output_features
+        self.forecast_minutes = forecast_minutes
+        self.history_minutes = history_minutes
+        self.output_variable = output_variable
+
+        super().__init__()
+
+        self.number_sat_channels = number_sat_channels
+        self.cnn_output_size = (
+            conv3d_channels
+            * ((image_size_pixels - 2 * self.number_of_conv3d_layers) ** 2)
+            * (self.forecast_len_5 + self.history_len_5 + 1 - 2 * self.number_of_conv3d_layers)
+        )
+        if self.cnn_output_size <= 0:
+            raise ValueError("image / sequence too small for this many 3x3x3 layers")
+
+        # parameter containers, constructed in the reference's order (same init stream under a seed)
+        self.sat_conv0 = nn.Conv3d(
+            in_channels=number_sat_channels, out_channels=conv3d_channels, kernel_size=(3, 3, 3), padding=0
+        )
+        for i in range(0, self.number_of_conv3d_layers - 1):
+            layer = nn.Conv3d(
+                in_channels=conv3d_channels, out_channels=conv3d_channels, kernel_size=(3, 3, 3), padding=0
+            )
+            setattr(self, f"conv3d_{i + 1}", layer)
+
+        self.fc1 = nn.Linear(in_features=self.cnn_output_size, out_features=self.fc1_output_features)
+        self.fc2 = nn.Linear(in_features=self.fc1_output_features, out_features=self.fc2_output_features)
+
+        fc3_in_features = self.fc2_output_features
+        if include_pv_yield:
+            fc3_in_features += self.number_of_samples_per_batch * (self.history_len_30 + 1)
+        if include_nwp:
+            self.fc_nwp = nn.Linear(in_features=self.number_of_nwp_features, out_features=128)
+            fc3_in_features += 128
+
+        self.fc3 = nn.Linear(in_features=fc3_in_features, out_features=self.fc3_output_features)
+        self.fc4 = nn.Linear(in_features=self.fc3_output_features, out_features=self.forecast_len)
+
+        # normalisation constants for int16 input; non-persistent => state_dict keys equal the reference's.
+        # Fewer than 12 channels: the LAST n constants (HRV, index 0, is what the 11-channel production
+        # config drops); override the buffers for any other channel selection.
+        n = number_sat_channels
+        if n <= 12:
+            mean, std = SAT_MEAN[12 - n:], SAT_STD[12 - n:]
+        else:
+            mean, std = np.zeros(n, np.float32), np.ones(n, np.float32)
+        self.register_buffer("sat_mean", torch.from_numpy(mean.copy()), persistent=False)
+        self.register_buffer("sat_std", torch.from_numpy(std.copy()), persistent=False)
+
+    def _conv_params(self):
+        wb = [self.sat_conv0.weight, self.sat_conv0.bias]
+        for i in range(0, self.number_of_conv3d_layers - 1):
+            layer = getattr(self, f"conv3d_{i + 1}")
+            wb += [layer.weight, layer.bias]
+        return wb
+
+    def forward(self, x):
+        x = as_batch(x)
+
+        # ******************* Satellite imagery *************************
+        # Shape: batch_size, channel, seq_length, height, width
+        sat_data = x.satellite.data
+        if not sat_data.is_cuda:
+            raise RuntimeError(
+                "predict_pv_yield_b200.Model is CUDA (sm_100a) only: move the batch to the GPU "
+                "(there is no CPU fallback)"
+            )
+        if sat_data.dtype == torch.int16:
+            # raw SEVIRI counts: normalisation (netcdf_dataset.py:96-101) is fused into conv0's loads
+            mean, std = self.sat_mean, self.sat_std
+        else:
+            sat_data = sat_data.float()  # model.py:113 (already-normalised input)
+            mean = std = None
+        sat_data = sat_data.contiguous()
+        batch_size = sat_data.shape[0]
+
+        # Conv3d + ReLU stack, flattened in NCDHW order (model.py:117-122)
+        out = ops.EncoderFn.apply(sat_data, mean, std, *self._conv_params())
+        if out.shape[1] != self.cnn_output_size:
+            raise RuntimeError(
+                f"satellite cube {tuple(sat_data.shape)} gives {out.shape[1]} conv features, "
+                f"model expects cnn_output_size={self.cnn_output_size}"
+            )
+
+        # add pv yield history (model.py:130-136); nan_to_num + concat are fused into the head kernel
+        pv_yield_history = None
+        if self.include_pv_yield:
+            pv_yield_history = x[self.output_variable][:, : self.history_len_30 + 1]
+            if pv_yield_history.dtype != torch.float32:
+                pv_yield_history = pv_yield_history.float()
+            if pv_yield_history.stride(-1) != 1:
+                pv_yield_history = pv_yield_history.contiguous()
+
+        # NWP data (model.py:139-148)
+        nwp_data = None
+        wn = bn = None
+        if self.include_nwp:
+            nwp_data = x["nwp"].float().flatten(start_dim=1).contiguous()
+            wn, bn = self.fc_nwp.weight, self.fc_nwp.bias
+
+        out = ops.HeadFn.apply(
+            out, pv_yield_history, nwp_data,
+            self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, wn, bn,
+            self.fc3.weight, self.fc3.bias, self.fc4.weight, self.fc4.bias,
+        )
+        out = out.reshape(batch_size, self.forecast_len)
+        return out

@@ -1,0 +1,383 @@
+"""Host side of the hot path: torch tensors in, C-ABI calls (``lib.py``) on the current CUDA stream.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every FLOP of the step runs
+in ``libpvb200.so``.  Nothing in this file computes on the CPU and nothing falls back to torch
+operators: a CPU tensor or a missing library raises.
+
+Autograd nodes (private protocol between them is documented on each class):
+  ``EncoderFn``  sat cube -> flattened last conv activation   (model.py:113-122 of the reference)
+  ``HeadFn``     features (+PV history, +NWP) -> forecast     (model.py:125-154)
+  ``StepLossFn`` forecast, target -> [nmae, mse, mse_exp, mae_exp]  (base_model.py:95-103)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as _lib
+
+# ---------------------------------------------------------------------------------------------
+# plumbing
+# ---------------------------------------------------------------------------------------------
+_workspaces: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=None) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"predict_pv_yield_b200: '{name}' is on {t.device}; this implementation is CUDA (sm_100a) only "
+            "and has no CPU fallback"
+        )
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"predict_pv_yield_b200: '{name}' must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"predict_pv_yield_b200: '{name}' must be contiguous")
+
+
+def _workspace(name: str, nbytes: int, device: torch.device) -> torch.Tensor:
+    """Per-device grow-only scratch buffers (single compute stream => stream-ordered reuse is safe)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), name)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+class KernelTimer:
+    """Optional per-call device timing (CUDA events on the launching stream) with the algorithmic FLOPs and
+    bytes of each call, used by bench.py for the roofline numbers.  Off unless ``set_timer`` is called."""
+
+    def __init__(self):
+        self.records = []  # (name, flops, nbytes, start_event, end_event)
+
+    def summary(self) -> Dict[str, dict]:
+        """Call after a device synchronize."""
+        out: Dict[str, dict] = {}
+        for name, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+_timer: Optional[KernelTimer] = None
+
+
+def set_timer(t: Optional[KernelTimer]) -> None:
+    global _timer
+    _timer = t
+
+
+class _timed:
+    def __init__(self, name: str, flops: float = 0.0, nbytes: float = 0.0):
+        self.args = (name, flops, nbytes)
+
+    def __enter__(self):
+        if _timer is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timer is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _timer.records.append((*self.args, self.e0, e1))
+        return False
+
+
+# ---------------------------------------------------------------------------------------------
+# thin operator wrappers (one C-ABI call each)
+# ---------------------------------------------------------------------------------------------
+def sat_normalise(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, out_dtype=torch.float32) -> torch.Tensor:
+    """(float32(x) - mean[c]) / std[c], bit-identical to netcdf_dataset.py:96-101.  x: int16 [B,C,T,H,W]."""
+    L = _lib.load()
+    _need_cuda(x, "satellite.data", torch.int16)
+    _need_cuda(mean, "sat_mean", torch.float32)
+    _need_cuda(std, "sat_std", torch.float32)
+    B, Cc = x.shape[0], x.shape[1]
+    thw = x[0, 0].numel()
+    if mean.numel() != Cc or std.numel() != Cc:
+        raise RuntimeError(f"sat_normalise: {Cc} channels but {mean.numel()} means / {std.numel()} stds")
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"sat_normalise: unsupported output dtype {out_dtype}")
+    with _timed("sat_normalise", 0.0, x.numel() * (2 + y.element_size())):
+        if out_dtype == torch.float32:
+            rc = L.pvb200_sat_normalise_f32(_p(x), _p(y), _p(mean), _p(std), B, Cc, thw, _stream())
+        else:
+            rc = L.pvb200_sat_normalise_bf16(_p(x), _p(y), _p(mean), _p(std), B, Cc, thw, _stream())
+    _lib.check(rc, "sat_normalise")
+    return y
+
+
+def conv3d_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = True,
+               mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """relu(conv3d(x, w, b)) with 3x3x3 kernel, padding 0 (model.py:117-120).  x fp32, or int16 with fused normalise."""
+    L = _lib.load()
+    i16 = x.dtype == torch.int16
+    _need_cuda(x, "conv input", torch.int16 if i16 else torch.float32)
+    _need_cuda(w, "conv weight", torch.float32)
+    if b is not None:
+        _need_cuda(b, "conv bias", torch.float32)
+    B, Ci, Ti, Hi, Wi = x.shape
+    Co = w.shape[0]
+    if tuple(w.shape) != (Co, Ci, 3, 3, 3):
+        raise RuntimeError(f"conv3d: weight shape {tuple(w.shape)} does not match input channels {Ci}")
+    if min(Ti, Hi, Wi) < 3:
+        raise RuntimeError(f"conv3d: input {Ti}x{Hi}x{Wi} smaller than the 3x3x3 kernel")
+    if i16 and (mean is None or std is None):
+        raise RuntimeError("conv3d: int16 input needs mean/std")
+    y = torch.empty((B, Co, Ti - 2, Hi - 2, Wi - 2), dtype=torch.float32, device=x.device)
+    nb = L.pvb200_conv3d_workspace_bytes(Ci, Co)
+    ws = _workspace("conv", nb, x.device)
+    with _timed(f"conv3d_fwd_f32[Ci={Ci}]", 2.0 * 27 * Ci * y.numel(), x.numel() * x.element_size() + 4.0 * y.numel()):
+        rc = L.pvb200_conv3d_fwd_f32(_p(x), int(i16), _p(mean) if i16 else None, _p(std) if i16 else None, _p(w), _p(b),
+                                     _p(y), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, int(relu), _stream())
+    _lib.check(rc, "conv3d_fwd")
+    return y
+
+
+def conv3d_dgrad(gz: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Tensor], x_shape: Sequence[int]) -> torch.Tensor:
+    """gx = conv_transpose3d(gz, w) * (mask_src > 0).  gz: gradient w.r.t. the conv's pre-activation output."""
+    L = _lib.load()
+    _need_cuda(gz, "gz", torch.float32)
+    _need_cuda(w, "conv weight", torch.float32)
+    B, Ci, Ti, Hi, Wi = x_shape
+    Co = w.shape[0]
+    if tuple(gz.shape) != (B, Co, Ti - 2, Hi - 2, Wi - 2):
+        raise RuntimeError(f"conv3d_dgrad: gz shape {tuple(gz.shape)} inconsistent with input {tuple(x_shape)}")
+    if mask_src is not None:
+        _need_cuda(mask_src, "mask_src", torch.float32)
+        if tuple(mask_src.shape) != tuple(x_shape):
+            raise RuntimeError("conv3d_dgrad: mask_src shape mismatch")
+    gx = torch.empty(tuple(x_shape), dtype=torch.float32, device=gz.device)
+    nb = L.pvb200_conv3d_workspace_bytes(Ci, Co)
+    ws = _workspace("conv", nb, gz.device)
+    with _timed(f"conv3d_dgrad_f32[Ci={Ci}]", 2.0 * 27 * Ci * gz.numel(),
+                4.0 * (gz.numel() + gx.numel() * (2 if mask_src is not None else 1))):
+        rc = L.pvb200_conv3d_dgrad_f32(_p(gz), _p(w), _p(mask_src), _p(gx), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, _stream())
+    _lib.check(rc, "conv3d_dgrad")
+    return gx
+
+
+def conv3d_wgrad(x: torch.Tensor, gz: torch.Tensor, mean: Optional[torch.Tensor] = None,
+                 std: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(dw [Co,Ci,3,3,3], db [Co]) from the layer input x and the pre-activation gradient gz."""
+    L = _lib.load()
+    i16 = x.dtype == torch.int16
+    _need_cuda(x, "conv input", torch.int16 if i16 else torch.float32)
+    _need_cuda(gz, "gz", torch.float32)
+    B, Ci, Ti, Hi, Wi = x.shape
+    Co = gz.shape[1]
+    if tuple(gz.shape) != (B, Co, Ti - 2, Hi - 2, Wi - 2):
+        raise RuntimeError(f"conv3d_wgrad: gz shape {tuple(gz.shape)} inconsistent with input {tuple(x.shape)}")
+    dw = torch.empty((Co, Ci, 3, 3, 3), dtype=torch.float32, device=x.device)
+    db = torch.empty((Co,), dtype=torch.float32, device=x.device)
+    nb = L.pvb200_conv3d_wgrad_workspace_bytes(Ci, Co)
+    ws = _workspace("wgrad", nb, x.device)
+    with _timed(f"conv3d_wgrad_f32[Ci={Ci}]", 2.0 * 27 * Ci * gz.numel(), x.numel() * x.element_size() + 4.0 * gz.numel()):
+        rc = L.pvb200_conv3d_wgrad_f32(_p(x), int(i16), _p(mean) if i16 else None, _p(std) if i16 else None, _p(gz), _p(dw),
+                                       _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, _stream())
+    _lib.check(rc, "conv3d_wgrad")
+    return dw, db
+
+
+def adam_step(params: List[torch.Tensor], grads: List[torch.Tensor], exp_avg: List[torch.Tensor],
+              exp_avg_sq: List[torch.Tensor], lr: float, beta1: float, beta2: float, eps: float, step: int,
+              grad_scale: float = 1.0) -> None:
+    """One multi-tensor Adam update in place (torch.optim.Adam arithmetic, base_model.py:255-257)."""
+    L = _lib.load()
+    n = len(params)
+    for i in range(n):
+        for t, nm in ((params[i], "param"), (grads[i], "grad"), (exp_avg[i], "exp_avg"), (exp_avg_sq[i], "exp_avg_sq")):
+            _need_cuda(t, nm, torch.float32)
+        if not (params[i].numel() == grads[i].numel() == exp_avg[i].numel() == exp_avg_sq[i].numel()):
+            raise RuntimeError("adam_step: size mismatch")
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
+    numel = (C.c_longlong * n)(*[p.numel() for p in params])
+    with _timed("adam_step_f32", 0.0, 28.0 * sum(p.numel() for p in params)):
+        rc = L.pvb200_adam_step_f32(n, arr(params), arr(grads), arr(exp_avg), arr(exp_avg_sq), numel, lr, beta1, beta2,
+                                    eps, step, grad_scale, _stream())
+    _lib.check(rc, "adam_step")
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd nodes
+# ---------------------------------------------------------------------------------------------
+class EncoderFn(torch.autograd.Function):
+    """Conv3d stack.  forward(sat, mean, std, w0, b0, w1, b1, ...) -> features [B, cnn_output_size].
+
+    ``sat`` is int16 (normalisation fused into layer 0's loads) or already-normalised fp32.
+    PRIVATE PROTOCOL: the incoming gradient must already carry the ReLU mask of the last layer
+    (``HeadFn`` applies it inside its fc1 data-gradient kernel), i.e. it is the gradient w.r.t. the last
+    layer's pre-activation.  Layer l's data-gradient kernel fuses the mask of layer l-1.
+    """
+
+    @staticmethod
+    def forward(ctx, sat, mean, std, *wb):
+        n_layers = len(wb) // 2
+        acts = []
+        x = sat
+        for l in range(n_layers):
+            x = conv3d_fwd(x, wb[2 * l], wb[2 * l + 1], relu=True, mean=mean, std=std)
+            acts.append(x)
+        ctx.save_for_backward(sat, mean, std, *wb, *acts)
+        ctx.n_layers = n_layers
+        return acts[-1].view(sat.shape[0], -1)
+
+    @staticmethod
+    def backward(ctx, g):
+        n = ctx.n_layers
+        saved = ctx.saved_tensors
+        sat, mean, std = saved[0], saved[1], saved[2]
+        wb = saved[3: 3 + 2 * n]
+        acts = saved[3 + 2 * n:]
+        gz = g.contiguous().view(acts[-1].shape)
+        grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
+        for l in range(n - 1, -1, -1):
+            x = sat if l == 0 else acts[l - 1]
+            dw, db = conv3d_wgrad(x, gz, mean, std)
+            grads[2 * l], grads[2 * l + 1] = dw, db
+            if l > 0:
+                gz = conv3d_dgrad(gz, wb[2 * l], acts[l - 1], acts[l - 1].shape)
+        return (None, None, None, *grads)
+
+
+class HeadFn(torch.autograd.Function):
+    """Fully connected head.  forward(feats, pv_hist|None, nwp|None, w1,b1,w2,b2,wn|None,bn|None,w3,b3,w4,b4).
+
+    ``pv_hist``: [B, nt, ns] view with unit stride on the last axis (NaNs allowed: nan_to_num fused);
+    ``nwp``: [B, NNWP] contiguous.  The returned gradient w.r.t. ``feats`` carries the ReLU mask
+    ``feats > 0`` (see ``EncoderFn``)."""
+
+    @staticmethod
+    def _desc(feats, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4):
+        h = _lib.Head()
+        h.struct_size = C.sizeof(_lib.Head)
+        h.B, h.K1 = feats.shape[0], feats.shape[1]
+        h.F1, h.F2, h.F3, h.FO = w1.shape[0], w2.shape[0], w3.shape[0], w4.shape[0]
+        if pv_hist is not None:
+            h.NPV = pv_hist.shape[1] * pv_hist.shape[2]
+            h.pv_ns = pv_hist.shape[2]
+            h.pv_sb, h.pv_st = pv_hist.stride(0), pv_hist.stride(1)
+            h.pv = pv_hist.data_ptr()
+        else:
+            h.NPV, h.pv_ns, h.pv_sb, h.pv_st, h.pv = 0, 0, 0, 0, None
+        if nwp is not None:
+            h.NNWP, h.FNWP = nwp.shape[1], wn.shape[0]
+            h.nwp, h.wn, h.bn = nwp.data_ptr(), wn.data_ptr(), bn.data_ptr()
+        else:
+            h.NNWP, h.FNWP = 0, 0
+        ncat = h.F2 + h.NPV + (h.FNWP if nwp is not None else 0)
+        if tuple(w1.shape) != (h.F1, h.K1) or tuple(w2.shape) != (h.F2, h.F1) or tuple(w3.shape) != (h.F3, ncat) \
+                or tuple(w4.shape) != (h.FO, h.F3) or (nwp is not None and tuple(wn.shape) != (h.FNWP, h.NNWP)):
+            raise RuntimeError("head: weight shapes inconsistent with the inputs")
+        h.w1, h.b1, h.w2, h.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+        h.w3, h.b3, h.w4, h.b4 = w3.data_ptr(), b3.data_ptr(), w4.data_ptr(), b4.data_ptr()
+        h.x = feats.data_ptr()
+        return h, ncat
+
+    @staticmethod
+    def forward(ctx, feats, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4):
+        L = _lib.load()
+        _need_cuda(feats, "features", torch.float32)
+        for t, nm in ((w1, "fc1.weight"), (b1, "fc1.bias"), (w2, "fc2.weight"), (b2, "fc2.bias"), (w3, "fc3.weight"),
+                      (b3, "fc3.bias"), (w4, "fc4.weight"), (b4, "fc4.bias")):
+            _need_cuda(t, nm, torch.float32)
+        if pv_hist is not None:
+            if not pv_hist.is_cuda or pv_hist.dtype != torch.float32 or pv_hist.stride(2) != 1:
+                raise RuntimeError("head: pv history must be a CUDA fp32 [B,nt,ns] view with unit last stride")
+        if nwp is not None:
+            _need_cuda(nwp, "nwp", torch.float32)
+            _need_cuda(wn, "fc_nwp.weight", torch.float32)
+            _need_cuda(bn, "fc_nwp.bias", torch.float32)
+        h, ncat = HeadFn._desc(feats, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4)
+        dev, B = feats.device, feats.shape[0]
+        h1 = torch.empty((B, h.F1), dtype=torch.float32, device=dev)
+        cat = torch.empty((B, ncat), dtype=torch.float32, device=dev)
+        h3 = torch.empty((B, h.F3), dtype=torch.float32, device=dev)
+        out = torch.empty((B, h.FO), dtype=torch.float32, device=dev)
+        h.h1, h.cat, h.h3, h.out = h1.data_ptr(), cat.data_ptr(), h3.data_ptr(), out.data_ptr()
+        ws = _workspace("head", L.pvb200_head_fwd_workspace_bytes(B, h.F1, h.K1), dev)
+        h.workspace, h.workspace_bytes = ws.data_ptr(), ws.numel()
+        with _timed("head_fwd_f32", 2.0 * B * h.F1 * h.K1, 4.0 * (B * h.K1 + h.F1 * h.K1)):
+            rc = L.pvb200_head_fwd_f32(C.byref(h), _stream())
+        _lib.check(rc, "head_fwd")
+        ctx.save_for_backward(feats, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4, h1, cat, h3)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        L = _lib.load()
+        feats, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4, h1, cat, h3 = ctx.saved_tensors
+        h, ncat = HeadFn._desc(feats, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4)
+        dev, B = feats.device, feats.shape[0]
+        g_out = g_out.contiguous()
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
+        g_h3, g_cat, g_h1 = e(B, h.F3), e(B, ncat), e(B, h.F1)
+        need_gx = ctx.needs_input_grad[0]
+        g_x = e(B, h.K1) if need_gx else None
+        dw1, db1, dw2, db2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
+        dw3, db3, dw4, db4 = torch.empty_like(w3), torch.empty_like(b3), torch.empty_like(w4), torch.empty_like(b4)
+        dwn = torch.empty_like(wn) if nwp is not None else None
+        dbn = torch.empty_like(bn) if nwp is not None else None
+        h.h1, h.cat, h.h3 = h1.data_ptr(), cat.data_ptr(), h3.data_ptr()
+        h.g_out, h.g_h3, h.g_cat, h.g_h1, h.g_x = g_out.data_ptr(), g_h3.data_ptr(), g_cat.data_ptr(), g_h1.data_ptr(), _p(g_x)
+        h.dw1, h.db1, h.dw2, h.db2 = dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr()
+        h.dw3, h.db3, h.dw4, h.db4 = dw3.data_ptr(), db3.data_ptr(), dw4.data_ptr(), db4.data_ptr()
+        h.dwn, h.dbn = _p(dwn), _p(dbn)
+        # fc1 wgrad: read x, write dW1; fc1 dgrad: read W1 + x (mask), write gx
+        with _timed("head_bwd_f32", (4.0 if need_gx else 2.0) * B * h.F1 * h.K1,
+                    4.0 * (B * h.K1 + h.F1 * h.K1) + (4.0 * (h.F1 * h.K1 + 2 * B * h.K1) if need_gx else 0.0)):
+            rc = L.pvb200_head_bwd_f32(C.byref(h), _stream())
+        _lib.check(rc, "head_bwd")
+        return g_x, None, None, dw1, db1, dw2, db2, dwn, dbn, dw3, db3, dw4, db4
+
+
+class StepLossFn(torch.autograd.Function):
+    """forward(y_hat [B,FO], y [B,FO] strided view, weights [FO]) -> losses [4] = nmae, mse, mse_exp, mae_exp.
+
+    Only ``losses[0]`` (the L1 loss the reference returns, base_model.py:99,146) is differentiable."""
+
+    @staticmethod
+    def forward(ctx, y_hat, y, weights):
+        L = _lib.load()
+        _need_cuda(y_hat, "y_hat", torch.float32)
+        if not y.is_cuda or y.dtype != torch.float32:
+            raise RuntimeError("loss: target must be a CUDA fp32 tensor")
+        if tuple(y.shape) != tuple(y_hat.shape):
+            # the reference's F.mse_loss raises here too (base_model.py:95-98: batch_size class attr truncates y)
+            raise RuntimeError(f"loss: target shape {tuple(y.shape)} != forecast shape {tuple(y_hat.shape)} "
+                               "(set model.batch_size to the real batch size)")
+        _need_cuda(weights, "loss weights", torch.float32)
+        B, FO = y_hat.shape
+        losses = torch.empty((4,), dtype=torch.float32, device=y_hat.device)
+        rc = L.pvb200_l1_loss_fwd_f32(_p(y_hat), _p(y), y.stride(0), y.stride(1), _p(weights), _p(losses), B, FO, _stream())
+        _lib.check(rc, "l1_loss_fwd")
+        ctx.save_for_backward(y_hat, y)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g_losses):
+        L = _lib.load()
+        y_hat, y = ctx.saved_tensors
+        B, FO = y_hat.shape
+        g_losses = g_losses.contiguous()  # element 0 is the upstream gradient of nmae (device scalar, no sync)
+        g = torch.empty_like(y_hat)
+        rc = L.pvb200_l1_loss_bwd_f32(_p(y_hat), _p(y), y.stride(0), y.stride(1), _p(g_losses), _p(g), B, FO, _stream())
+        _lib.check(rc, "l1_loss_bwd")
+        return g, None, None

@@ -1,0 +1,60 @@
+"""FusedAdam -- ``torch.optim.Optimizer`` surface over the multi-tensor Adam kernel.
+
+Replaces ``torch.optim.Adam(self.parameters(), lr=0.0005)`` returned by the reference's
+``configure_optimizers`` (``predict_pv_yield/models/base_model.py:255-257``): same defaults
+(betas (0.9, 0.999), eps 1e-8, no weight decay, bias-corrected), same state names
+(``step``, ``exp_avg``, ``exp_avg_sq``) so optimizer checkpoints keep their layout.  One kernel launch
+updates every parameter; under data parallelism ``grad_scale = 1 / world_size`` folds the gradient
+averaging into the same pass.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from . import ops
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        if lr < 0.0 or eps < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
+            raise ValueError("FusedAdam: invalid hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.grad_scale = 1.0
+        self.pre_step_hook: Optional[Callable[[], None]] = None  # e.g. wait for the gradient all-reduce
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if self.pre_step_hook is not None:
+            self.pre_step_hook()
+        for group in self.param_groups:
+            ps, gs, ms, vs = [], [], [], []
+            step = None
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if p.grad.is_sparse:
+                    raise RuntimeError("FusedAdam does not support sparse gradients")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] = int(st["step"]) + 1
+                if step is None:
+                    step = st["step"]
+                elif step != st["step"]:
+                    raise RuntimeError("FusedAdam: parameters of one group must share a step count")
+                ps.append(p.data)
+                gs.append(p.grad.data if p.grad.is_contiguous() else p.grad.data.contiguous())
+                ms.append(st["exp_avg"])
+                vs.append(st["exp_avg_sq"])
+            if ps:
+                b1, b2 = group["betas"]
+                ops.adam_step(ps, gs, ms, vs, group["lr"], b1, b2, group["eps"], step, self.grad_scale)
+        return loss

@@ -1,0 +1,155 @@
+"""GPU parity tests of the whole step (Model.forward / training_step / backward / FusedAdam) through the
+C ABI, against (a) the committed golden vectors produced by the UNMODIFIED reference
+(tests/golden/*.npz, oracle/make_golden.py) and (b) the fp64 oracle on the same seeded inputs.
+
+fp32-mode tolerances (normalised max error): forecast / loss <= 1e-5 (north star).
+END-TO-END gradients are gated looser than the isolated kernels (1e-4, test_gpu_kernels.py): any two fp32
+implementations differ in a few ReLU decisions near zero, and on these tiny batches one flipped mask moves a
+conv weight-gradient by up to ~6e-3 of max|g| -- torch-fp32 itself sits that far from torch-fp64 on these
+very cases (tools/parity_report.py prints the table; profiles/parity_r01.txt).  Gates: conv grads 2e-2,
+fc grads 2e-3, of max|g| per tensor.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import conv3d_oracle as O
+from oracle.golden_cases import CASES, golden_batch, golden_state_dict, thin
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _model(kw, dev):
+    from predict_pv_yield_b200.models.conv3d.model import Model
+
+    return Model(**kw).to(dev)
+
+
+def _grad_tol(name):
+    return 2e-2 if "conv" in name else 2e-3
+
+
+def _nerr_np(a, b):
+    scale = max(float(np.abs(b).max()), 1e-30)
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max()) / scale
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_model_matches_reference_golden(dev, golden_dir, name):
+    g = dict(np.load(os.path.join(golden_dir, f"{name}.npz")))
+    case = CASES[name]
+    m = _model(case["model"], dev)
+    m.batch_size = case["batch"]
+    m.load_state_dict(golden_state_dict(m))
+    batch = O.batch_to(golden_batch(name), dev)
+    opt = m.configure_optimizers()
+    for step in range(2):
+        opt.zero_grad()
+        loss = m.training_step(batch, step)
+        loss.backward()
+        if step == 0:
+            with torch.no_grad():
+                y_hat = m(batch)
+            assert _nerr_np(y_hat.cpu().numpy(), g["y_hat"]) <= 1e-5
+            assert abs(float(loss) - float(g["nmae"])) <= 1e-5 * abs(float(g["nmae"]))
+            logged = m.logged_metrics
+            for key, gk in (("MSE/Train", "mse"), ("NMAE/Train", "nmae"), ("MSE_EXP/Train", "mse_exp"), ("MAE_EXP/Train", "mae_exp")):
+                assert abs(float(logged[key]) - float(g[gk])) <= 1e-5 * abs(float(g[gk])), key
+            for k, p in m.named_parameters():
+                e = _nerr_np(thin(p.grad), g["grad." + k])
+                assert e <= _grad_tol(k), (k, e)
+        opt.step()
+    for k, p in m.named_parameters():
+        ref = g["adam2." + k]
+        got = thin(p)
+        # Adam normalises the step to ~lr, so sign flips of ~0 gradients move a weight by up to 2*lr*2 steps;
+        # compare against the weight scale with an absolute floor of a few lr-quanta on the rare flipped entries
+        diff = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+        assert float(np.quantile(diff, 0.999)) <= 1e-5 * max(float(np.abs(ref).max()), 1e-30) + 1e-7, k
+        assert float(diff.max()) <= 2.1e-3, k
+
+
+@pytest.mark.parametrize("name", ["test_yaml_pv", "nwp_pv_small"])
+def test_model_matches_fp64_oracle(dev, name):
+    case = CASES[name]
+    m = _model(case["model"], dev)
+    m.batch_size = case["batch"]
+    sd = golden_state_dict(m)
+    m.load_state_dict(sd)
+    om = O.OracleModel(**case["model"]).double()
+    om.batch_size = case["batch"]
+    om.load_state_dict({k: v.double() for k, v in sd.items()})
+    batch = golden_batch(name)
+    r = om.step_losses(O.batch_to(batch, float_dtype=torch.float64))
+    r["nmae"].backward()
+    loss = m.training_step(O.batch_to(batch, dev), 0)
+    loss.backward()
+    assert abs(float(loss) - float(r["nmae"])) <= 1e-5 * abs(float(r["nmae"]))
+    for (k, p), (_, q) in zip(m.named_parameters(), om.named_parameters()):
+        assert O.normalised_max_err(p.grad, q.grad) <= _grad_tol(k), k
+
+
+def test_model_float_input_equals_int16_input(dev):
+    """Already-normalised fp32 cubes (the reference's model input) and raw int16 cubes give the same bits."""
+    case = CASES["nwp_pv_small"]
+    m = _model(case["model"], dev)
+    m.load_state_dict(golden_state_dict(m))
+    batch = golden_batch("nwp_pv_small")
+    sat = batch["satellite"]["data"]
+    mean, std = O.sat_constants(sat.shape[1])
+    fb = dict(batch)
+    fb["satellite"] = {"data": O.sat_normalise(sat, torch.from_numpy(mean), torch.from_numpy(std))}
+    with torch.no_grad():
+        a = m(O.batch_to(batch, dev))
+        b = m(O.batch_to(fb, dev))
+    assert torch.equal(a, b)
+
+
+def test_batch_size_attribute_truncates_target_like_reference(dev):
+    """base_model.py:30,95: y[0:batch_size] -- a batch larger than the class default 32 must fail loudly."""
+    case = CASES["test_yaml_pv"]
+    m = _model(case["model"], dev)
+    m.batch_size = 1
+    with pytest.raises(RuntimeError, match="batch_size"):
+        m.training_step(O.batch_to(golden_batch("test_yaml_pv"), dev), 0)
+
+
+def test_full_size_config2_vs_oracle(dev):
+    """BASELINE config 2 shape at a reduced batch (B=4; the oracle needs seconds on CPU): 12x19x64x64 int16,
+    sat-only, fp32, forward + backward, size-independent checks on top."""
+    kw = dict(include_pv_yield=False, include_nwp=False, forecast_minutes=60, history_minutes=30)
+    B = 4
+    torch.manual_seed(518)
+    om = O.OracleModel(**kw)
+    om.batch_size = B
+    m = _model(kw, dev)
+    m.batch_size = B
+    m.load_state_dict(om.state_dict())
+    batch = O.make_synthetic_batch(B, seed=518)
+    r = om.step_losses(batch)
+    r["nmae"].backward()
+    loss = m.training_step(O.batch_to(batch, dev), 0)
+    loss.backward()
+    with torch.no_grad():
+        y_hat = m(O.batch_to(batch, dev))
+    assert O.normalised_max_err(y_hat, r["y_hat"]) <= 1e-5
+    assert abs(float(loss) - float(r["nmae"])) <= 1e-5 * abs(float(r["nmae"]))
+    for (k, p), (_, q) in zip(m.named_parameters(), om.named_parameters()):
+        # fp32-vs-fp32 end-to-end: ReLU-mask flips make torch itself differ from fp64 by ~1e-3 of max|g| on
+        # the conv weights; isolated kernels are gated at 1e-4 in test_gpu_kernels.py
+        assert O.normalised_max_err(p.grad, q.grad) <= _grad_tol(k), k
+    # size-independent property: samples are independent -> permuting the batch permutes the forecast
+    perm = torch.tensor([2, 0, 3, 1])
+    pb = {"satellite": {"data": batch["satellite"]["data"][perm]}, "pv": {"pv_yield": batch["pv"]["pv_yield"][perm]}}
+    with torch.no_grad():
+        y_perm = m(O.batch_to(pb, dev))
+    assert torch.equal(y_perm, y_hat[perm.to(dev)])
