@@ -79,6 +79,29 @@ int pvb200_conv3d_dgrad_f32(const float* gz, const float* w, const float* mask_s
                             int B, int Cin, int Ti, int Hi, int Wi, int Cout,
                             pvb200_stream_t stream);
 
+/* ---- bf16 tensor-core path (tcgen05 / TMEM / TMA engine) ----------------------------------------------
+ * Activations are "blocked" bf16: [B][Cg][T][H][W][8] with Cg = pvb200_blocked_channel_groups(C) channel groups
+ * of 8 (padded with zero channels to an even group count).  Same reference call sites as the _f32 functions
+ * (model.py:117-120 and autograd); fp32 master weights are converted per call.
+ *   nc_to_blocked_bf16: [B][C][T][H][W] fp32 -> blocked bf16 written into the interior of a tensor padded by
+ *                       `pad` on every side of T,H,W (caller zero-fills the border once).
+ *   conv3d_fwd_bf16   : yb = relu(conv(xb) + bias), written into the interior of an out_pad-padded blocked tensor.
+ *   conv3d_dgrad_bf16 : gx = conv_transpose(gz) * (mask_src > 0); gz_padded is gz zero-padded by 2:
+ *                       [B][Cg(Cout)][Ti+2][Hi+2][Wi+2][8]; mask_src (unpadded, [B][Cg(Cin)][Ti][Hi][Wi][8]) may be NULL. */
+int pvb200_blocked_channel_groups(int C);
+size_t pvb200_conv3d_bf16_workspace_bytes(int Cin, int Cout);
+int pvb200_nc_to_blocked_bf16(const float* x, uint16_t* y, int B, int C, int T, int H, int W, int pad,
+                              pvb200_stream_t stream);
+int pvb200_blocked_to_nc_f32(const uint16_t* x, float* y, int B, int C, int T, int H, int W, pvb200_stream_t stream);
+int pvb200_conv3d_fwd_bf16(const uint16_t* xb, const float* w, const float* bias, uint16_t* yb,
+                           void* workspace, size_t workspace_bytes,
+                           int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int out_pad,
+                           pvb200_stream_t stream);
+int pvb200_conv3d_dgrad_bf16(const uint16_t* gz_padded, const float* w, const uint16_t* mask_src, uint16_t* gx,
+                             void* workspace, size_t workspace_bytes,
+                             int B, int Cin, int Ti, int Hi, int Wi, int Cout, int out_pad,
+                             pvb200_stream_t stream);
+
 /* weight + bias gradient (autograd of model.py:117-120): dw[co,ci,kt,kh,kw] = sum gz * x(shifted),
  * db[co] = sum gz.  Deterministic two-pass reduction through the caller's workspace. */
 size_t pvb200_conv3d_wgrad_workspace_bytes(int Cin, int Cout);

@@ -1,0 +1,496 @@
+// conv3d_igemm_bf16.cu -- a3/a4/a11 in bf16: Conv3d 3x3x3 forward and data-gradient as an implicit GEMM on the
+// 5th-generation tensor cores (tcgen05.mma, fp32 accumulators in TMEM), operands staged by the TMA engine.
+//
+// Reference call sites: predict_pv_yield/models/conv3d/model.py:80-90,117-120 (and their autograd).
+//
+// Data layout ("blocked", NC8DHW8c): activations are [B][Cg][T][H][W][8] bf16 -- channel groups of 8 (16 bytes)
+// innermost.  With it the implicit GEMM needs NO im2col and no swizzle:
+//   * GEMM M = output positions, N = output channels, K = 27 taps x Cin.
+//   * positions are flattened with the INPUT pitch: q = ho*Wi + wo, so the A operand of tap (kt,kh,kw) for rows
+//     q0..q0+127 is the contiguous run of 16-byte elements starting at q0 + kh*Wi + kw of input plane t+kt:
+//     exactly the SWIZZLE_NONE K-major canonical layout (8 rows x 16 B core matrices, SBO = 128 B, LBO = the
+//     stride between channel-group planes).  A tap is just a different descriptor start address.
+//   * one input plane segment (all channel groups, 256 + 2*Wi + 2 positions) is ONE bulk copy per channel group
+//     (cp.async.bulk, completion on an mbarrier); a 4-slot ring keeps 3 time planes live + 1 in flight, so walking
+//     along t re-loads nothing (each plane is fetched once per t-segment).
+//   * all 27 x Cin x Cout weights (55 KB bf16) stay resident in shared memory for the whole persistent CTA.
+//   * wrap columns (wo >= Wo) are computed and dropped in the epilogue (2/Wi ~ 3 % waste).
+// Warp roles (320 threads): warp 0 = copy producer, warp 1 = MMA issuer (one elected thread) + TMEM owner,
+// warps 2-9 = epilogue (TMEM -> registers -> bias/ReLU or ReLU-mask -> bf16 -> 16-byte stores); accumulators are
+// double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// The data gradient is the same kernel on a zero-padded gz (padding 2) with flipped / transposed weights.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace pvb {
+
+constexpr int kIgThreads = 320;  // producer warp, MMA warp, 8 epilogue warps
+constexpr int kIgSlots = 4;
+constexpr int kIgTileM = 256;    // MMA rows per tile = 2 row blocks of 128
+constexpr int kIgTileOut = 254;  // outputs per tile: the kw shift-add needs rows r, r+1, r+2
+
+struct IgemmArgs {
+  const uint4* x;     // [B][Cg][Ti][Hi][Wi] 16-byte elements (8 bf16 channels)
+  const uint4* wq;    // [9 (kt,kh)][Cg][3 (kw)][CoP] 16-byte elements: 8 input channels of one (kw, output channel)
+  const float* bias;  // [Co] or null
+  const uint4* mask;  // [B][CogOut][To][Ho][Wo] or null
+  uint4* y;           // [B][CogOut][To+2p][Ho+2p][Wo+2p]
+  int B, Cg, Ti, Hi, Wi;
+  int CoP, Co, CogOut, To, Ho, Wo;  // CoP = Cout padded to 16/32; MMA N = 3*CoP (the three kw taps side by side)
+  int out_pad, relu;
+  int NP;       // staged positions per (plane, channel group)
+  int tiles_q;  // q tiles per output plane
+  int tseg, nseg;
+  long long units;
+};
+
+// weights fp32 [Co][Ci][27] -> bf16 [(kt,kh)][Cg][kw*CoP + co][8 ci]; flipped / transposed roles for the data gradient
+__global__ void igemm_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wq, int Ci_role,
+                                         int Co_role, int Cg, int CoP, long long s_co, long long s_ci, int flip) {
+  const int N = 3 * CoP;
+  const int total = 9 * Cg * N * 8;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c8 = idx & 7;
+    const int n = (idx >> 3) % N;
+    const int cg = (idx / (8 * N)) % Cg;
+    const int tg = idx / (8 * N * Cg);  // kt*3 + kh
+    const int kw = n / CoP, co = n - kw * CoP;
+    const int ci = cg * 8 + c8;
+    const int tap = tg * 3 + kw;
+    float v = 0.f;
+    if (co < Co_role && ci < Ci_role) v = w[co * s_co + ci * s_ci + (flip ? 26 - tap : tap)];
+    wq[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// D[tmem] (+)= A * B with descriptors given as (lo, hi) halves: only `lo` changes between MMAs of a tile
+__device__ __forceinline__ void igemm_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
+}
+
+template <int CG>
+__global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const IgemmArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [4]
+  uint64_t* empty = full + kIgSlots;                        // [4]
+  uint64_t* wfull = empty + kIgSlots;                       // [1]
+  uint64_t* tfull = wfull + 1;                              // [2]
+  uint64_t* tempty = tfull + 2;                             // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + 128);     // [32]
+  float* xch = reinterpret_cast<float*>(smem + 256);        // [2 parity][2 rb][4 qd][3*32] boundary rows of the shift-add
+  uint8_t* w_s = smem + 256 + 2 * 2 * 4 * 96 * 4;
+  const int N = 3 * a.CoP;
+  const uint32_t w_bytes = 9u * CG * N * 16u;
+  const uint32_t slot_bytes = static_cast<uint32_t>(CG) * a.NP * 16u;
+  uint8_t* slot_s = w_s + ((w_bytes + 127u) & ~127u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (4u * N <= 256u) ? 256u : 512u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kIgSlots; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+    tc::mbar_init(wfull, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 8); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
+  if (threadIdx.x >= 64 && threadIdx.x < 96) bias_s[lane] = (a.bias && lane < a.Co) ? __ldg(a.bias + lane) : 0.f;
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const long long u_begin = a.units * blockIdx.x / gridDim.x;
+  const long long u_end = a.units * (blockIdx.x + 1) / gridDim.x;
+  const long long in_plane = static_cast<long long>(a.Hi) * a.Wi;
+
+  if (warp == 0) {
+    // =============================== producer ===============================
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(wfull, w_bytes);
+      for (uint32_t off = 0; off < w_bytes; off += 32768u) {
+        const uint32_t n = (w_bytes - off < 32768u) ? (w_bytes - off) : 32768u;
+        tc::bulk_g2s(w_s + off, reinterpret_cast<const uint8_t*>(a.wq) + off, n, wfull);
+      }
+      uint32_t seq = 0;
+      for (long long u = u_begin; u < u_end; ++u) {
+        const int seg = static_cast<int>(u % a.nseg);
+        const long long r = u / a.nseg;
+        const int qt = static_cast<int>(r % a.tiles_q);
+        const int b = static_cast<int>(r / a.tiles_q);
+        const int t0 = seg * a.tseg;
+        const int ntiles = min(a.tseg, a.To - t0);
+        const int q0 = qt * kIgTileOut;
+        long long avail = in_plane - q0;
+        const uint32_t npos = static_cast<uint32_t>(avail < a.NP ? avail : a.NP);
+        for (int p = 0; p < ntiles + 2; ++p, ++seq) {
+          const uint32_t slot = seq & (kIgSlots - 1);
+          const uint32_t n = seq / kIgSlots;
+          tc::mbar_wait(empty + slot, (n & 1u) ^ 1u);
+          tc::mbar_arrive_expect_tx(full + slot, npos * 16u * CG);
+#pragma unroll
+          for (int cg = 0; cg < CG; ++cg) {
+            const uint4* src = a.x + ((static_cast<long long>(b) * CG + cg) * a.Ti + (t0 + p)) * in_plane + q0;
+            tc::bulk_g2s(slot_s + slot * slot_bytes + static_cast<uint32_t>(cg) * a.NP * 16u, src, npos * 16u, full + slot);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc = tc::umma_idesc(128, N, /*bf16*/ 1, /*K-major*/ 0, 0);
+      const uint32_t a_lbo = static_cast<uint32_t>(a.NP) * 16u;
+      const uint32_t b_lbo = static_cast<uint32_t>(N) * 16u;
+      // descriptor halves: hi = SBO (128 B) | version; lo = start address | LBO
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo_base = ((a_lbo >> 4) << 16);
+      const uint32_t b_lo_base = ((b_lbo >> 4) << 16) | ((tc::smem_u32(w_s) >> 4) & 0x3fffu);
+      const uint32_t slot_addr16 = tc::smem_u32(slot_s) >> 4;  // in 16-byte units
+      const uint32_t slot_16 = slot_bytes >> 4;
+      const uint32_t wi = static_cast<uint32_t>(a.Wi);
+      tc::mbar_wait(wfull, 0);
+      uint32_t base_seq = 0, waited = 0, tile_ctr = 0;
+      for (long long u = u_begin; u < u_end; ++u) {
+        const int seg = static_cast<int>(u % a.nseg);
+        const int t0 = seg * a.tseg;
+        const int ntiles = min(a.tseg, a.To - t0);
+        for (int ti = 0; ti < ntiles; ++ti, ++tile_ctr) {
+          for (; waited < base_seq + ti + 3; ++waited) tc::mbar_wait(full + (waited & (kIgSlots - 1)), (waited / kIgSlots) & 1u);
+          const uint32_t acc = tile_ctr & 1u;
+          tc::mbar_wait(tempty + acc, ((tile_ctr >> 1) & 1u) ^ 1u);
+          tc::tc_fence_after();
+          uint32_t pl16[3];
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) pl16[kt] = slot_addr16 + ((base_seq + ti + kt) & (kIgSlots - 1)) * slot_16;
+          // the two row blocks accumulate into different TMEM tiles: alternate them so that back-to-back MMAs are
+          // independent (consecutive MMAs into the SAME accumulator serialise on its read-modify-write)
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int ks = 0; ks < CG / 2; ++ks) {
+#pragma unroll
+                for (int rb = 0; rb < 2; ++rb) {
+                  const uint32_t d_tmem = tmem_base + (acc * 2u + rb) * N;
+                  // A: rows rb*128.. of plane kt shifted by kh input rows; channel groups 2ks, 2ks+1
+                  const uint32_t a16 = pl16[kt] + static_cast<uint32_t>(2 * ks) * (a_lbo >> 4) + rb * 128u + kh * wi;
+                  const uint32_t b16 = static_cast<uint32_t>(((kt * 3 + kh) * CG + 2 * ks)) * (b_lbo >> 4);
+                  igemm_mma(d_tmem, a_lo_base | (a16 & 0x3fffu), desc_hi, b_lo_base + b16, desc_hi, idesc,
+                            (kt | kh | ks) ? 1u : 0u);
+                }
+              }
+            }
+          }
+          tc::umma_commit(tfull + acc);                                     // accumulators ready for the epilogue
+          tc::umma_commit(empty + ((base_seq + ti) & (kIgSlots - 1)));      // oldest time plane is free
+          if (ti == ntiles - 1) {
+            tc::umma_commit(empty + ((base_seq + ti + 1) & (kIgSlots - 1)));
+            tc::umma_commit(empty + ((base_seq + ti + 2) & (kIgSlots - 1)));
+          }
+        }
+        base_seq += ntiles + 2;
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..9) ===============================
+    // out[r][co] = D[r][co] + D[r+1][CoP + co] + D[r+2][2 CoP + co]   (the kw shift-add; rows = TMEM lanes)
+    // warps 2-5 own row block 0, warps 6-9 row block 1; warp % 4 = the TMEM lane quadrant a warp may access.
+    const int qd = warp & 3;
+    const int rb = (warp - 2) >> 2;
+    const int Cog = a.CogOut;
+    const int CoP = a.CoP;
+    const int Top = a.To + 2 * a.out_pad, Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
+    const long long oplane = static_cast<long long>(Hop) * Wop;
+    const long long mplane = static_cast<long long>(a.Ho) * a.Wo;
+    const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
+    const int row = rb * 128 + qd * 32 + lane;
+    const int me = rb * 4 + qd;
+    const int nb = me + 1;  // block holding rows row+1, row+2 beyond this quadrant (8 = none: rows 254/255 are not emitted)
+    uint32_t tile_ctr = 0;
+    for (long long u = u_begin; u < u_end; ++u) {
+      const int seg = static_cast<int>(u % a.nseg);
+      const long long r = u / a.nseg;
+      const int qt = static_cast<int>(r % a.tiles_q);
+      const int b = static_cast<int>(r / a.tiles_q);
+      const int t0 = seg * a.tseg;
+      const int ntiles = min(a.tseg, a.To - t0);
+      const int q = qt * kIgTileOut + row;
+      const int ho = q / a.Wi, wo = q - ho * a.Wi;
+      const bool valid = (row < kIgTileOut) && (ho < a.Ho) && (wo < a.Wo);
+      for (int ti = 0; ti < ntiles; ++ti, ++tile_ctr) {
+        const uint32_t acc = tile_ctr & 1u;
+        tc::mbar_wait(tfull + acc, (tile_ctr >> 1) & 1u);
+        tc::tc_fence_after();
+        const int t = t0 + ti;
+        float* xp = xch + (tile_ctr & 1u) * (2 * 4 * 96);
+        uint32_t v0[32], v1[32], v2[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + (acc * 2u + rb) * N;
+        tc::tmem_ld_32x32(taddr, v0);
+        tc::tmem_ld_32x32(taddr + CoP, v1);
+        tc::tmem_ld_32x32(taddr + 2 * CoP, v2);
+        tc::tmem_ld_wait();
+        // all TMEM reads of this warp are done: release the accumulator as early as possible
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty + acc);
+        // publish this quadrant's first two rows of the kw=1 / kw=2 partial sums for the quadrant below
+        if (lane < 2) {
+          float4* dst = reinterpret_cast<float4*>(xp + me * 96);
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              dst[c] = make_float4(__uint_as_float(v1[4 * c]), __uint_as_float(v1[4 * c + 1]), __uint_as_float(v1[4 * c + 2]),
+                                   __uint_as_float(v1[4 * c + 3]));
+              dst[8 + c] = make_float4(__uint_as_float(v2[4 * c]), __uint_as_float(v2[4 * c + 1]),
+                                       __uint_as_float(v2[4 * c + 2]), __uint_as_float(v2[4 * c + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              dst[16 + c] = make_float4(__uint_as_float(v2[4 * c]), __uint_as_float(v2[4 * c + 1]),
+                                        __uint_as_float(v2[4 * c + 2]), __uint_as_float(v2[4 * c + 3]));
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
+        // neighbour rows for lanes 30 / 31 (other lanes read a harmless in-range address and ignore it)
+        const float4* n1 = reinterpret_cast<const float4*>(xp + (nb < 8 ? nb : me) * 96);  // kw=1 row of lane 0 below
+        const float4* n2 = n1 + ((lane == 30) ? 8 : 16);  // lane 30: kw=2 row of lane 0; lane 31: kw=2 row of lane 1
+        float o[32];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 f1 = n1[c4];
+          const float4 f2 = n2[c4];
+          const float4 fb = bias4[c4];
+          const float e1[4] = {f1.x, f1.y, f1.z, f1.w};
+          const float e2[4] = {f2.x, f2.y, f2.z, f2.w};
+          const float eb[4] = {fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = 4 * c4 + j;
+            float s1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c]), 1);
+            float s2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 2);
+            s1 = (lane == 31) ? e1[j] : s1;
+            s2 = (lane >= 30) ? e2[j] : s2;
+            o[c] = (__uint_as_float(v0[c]) + s1) + (s2 + eb[j]);
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g >= Cog) continue;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = o[g * 8 + j];
+              if (a.relu) x = (x < 0.f) ? 0.f : x;
+              f[j] = x;
+            }
+            if (a.mask) {
+              const uint4 m = __ldg(a.mask + ((static_cast<long long>(b) * Cog + g) * a.To + t) * mplane +
+                                    static_cast<long long>(ho) * a.Wo + wo);
+              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
+                const float mv = __uint_as_float(bits << 16);
+                f[j] = (mv > 0.f) ? f[j] : 0.f;
+              }
+            }
+            uint4 ov = make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]),
+                                  tc::pack_bf16(f[6], f[7]));
+            a.y[((static_cast<long long>(b) * Cog + g) * Top + (t + a.out_pad)) * oplane +
+                static_cast<long long>(ho + a.out_pad) * Wop + (wo + a.out_pad)] = ov;
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// [B][C][T][H][W] fp32 -> blocked bf16 [B][Cg][T+2p][H+2p][W+2p][8] interior (channels >= C are zero)
+__global__ void nc_to_blocked_bf16_kernel(const float* __restrict__ x, uint4* __restrict__ y, int C, int Cg, int T, int H,
+                                          int W, int pad, long long total) {
+  const long long thw = static_cast<long long>(T) * H * W;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, Tp = T + 2 * pad;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pos = idx % thw;
+    const long long r = idx / thw;
+    const int cg = static_cast<int>(r % Cg);
+    const long long b = r / Cg;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      f[j] = (c < C) ? x[(b * C + c) * thw + pos] : 0.f;
+    }
+    const int w = static_cast<int>(pos % W);
+    const int h = static_cast<int>((pos / W) % H);
+    const int t = static_cast<int>(pos / (static_cast<long long>(W) * H));
+    y[((b * Cg + cg) * Tp + (t + pad)) * Hp * Wp + static_cast<long long>(h + pad) * Wp + (w + pad)] =
+        make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]), tc::pack_bf16(f[6], f[7]));
+  }
+}
+
+// blocked bf16 [B][Cg][T][H][W][8] -> [B][C][T][H][W] fp32
+__global__ void blocked_to_nc_f32_kernel(const uint4* __restrict__ x, float* __restrict__ y, int C, int Cg, long long thw,
+                                         long long total) {
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pos = idx % thw;
+    const long long r = idx / thw;
+    const int cg = static_cast<int>(r % Cg);
+    const long long b = r / Cg;
+    const uint4 v = x[idx];
+    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      const uint32_t bits = (j & 1) ? (wv[j >> 1] >> 16) : (wv[j >> 1] & 0xffffu);
+      if (c < C) y[(b * C + c) * thw + pos] = __uint_as_float(bits << 16);
+    }
+  }
+}
+
+static int igemm_cg(int C) { return 2 * ceil_div(C, 16); }  // channel groups of 8, padded to an even count (UMMA K = 16)
+
+static int igemm_cop(int Co) { return Co <= 16 ? 16 : 32; }
+
+static size_t igemm_ws_bytes(int Ci_role, int Co_role) {
+  return static_cast<size_t>(27) * igemm_cg(Ci_role) * igemm_cop(Co_role) * 16;
+}
+
+static int launch_igemm(const void* xb, const float* w, long long s_co, long long s_ci, int flip, const float* bias,
+                        const void* mask, void* yb, void* ws, size_t ws_bytes, int B, int Ci, int Ti, int Hi, int Wi, int Co,
+                        int out_pad, int relu, cudaStream_t stream) {
+  IgemmArgs a;
+  a.x = static_cast<const uint4*>(xb);
+  a.bias = bias;
+  a.mask = static_cast<const uint4*>(mask);
+  a.y = static_cast<uint4*>(yb);
+  a.B = B; a.Cg = igemm_cg(Ci); a.Ti = Ti; a.Hi = Hi; a.Wi = Wi;
+  PVB_REQUIRE(Co <= 32, "conv3d_bf16: Cout=%d > 32 is not supported by the tensor-core path (use fp32 mode)", Co);
+  a.CoP = igemm_cop(Co); a.Co = Co; a.CogOut = igemm_cg(Co);
+  a.To = Ti - 2; a.Ho = Hi - 2; a.Wo = Wi - 2;
+  PVB_REQUIRE(a.To > 0 && a.Ho > 0 && a.Wo > 0, "conv3d_bf16: input %dx%dx%d too small", Ti, Hi, Wi);
+  PVB_REQUIRE(a.Cg == 2 || a.Cg == 4, "conv3d_bf16: Cin=%d > 32 is not supported by the tensor-core path (use fp32 mode)", Ci);
+  a.out_pad = out_pad; a.relu = relu;
+  a.NP = round_up(kIgTileM + 2 * Wi, 8);
+  const int Qtot = (a.Ho - 1) * Wi + a.Wo;
+  a.tiles_q = ceil_div(Qtot, kIgTileOut);
+  const int sms = sm_count();
+  PVB_REQUIRE(sms > 0, "conv3d_bf16: no CUDA device");
+  // t-segments: long enough to amortise the 2 extra planes, short enough for >= ~8 units per CTA
+  int tseg = a.To;
+  while (tseg > 4 && static_cast<long long>(B) * a.tiles_q * ceil_div(a.To, tseg) < 8LL * sms) tseg = ceil_div(tseg, 2);
+  a.tseg = tseg;
+  a.nseg = ceil_div(a.To, tseg);
+  a.units = static_cast<long long>(B) * a.tiles_q * a.nseg;
+  const size_t need = igemm_ws_bytes(Ci, Co);
+  if (!ws || ws_bytes < need) {
+    set_error("conv3d_bf16: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return PVB200_ERR_WORKSPACE;
+  }
+  PVB_REQUIRE(reinterpret_cast<uintptr_t>(xb) % 16 == 0 && reinterpret_cast<uintptr_t>(yb) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(ws) % 16 == 0, "conv3d_bf16: pointers must be 16-byte aligned");
+  a.wq = static_cast<const uint4*>(ws);
+  {
+    const int total = 27 * a.Cg * a.CoP * 8;
+    igemm_weight_prep_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(ws), Ci, Co, a.Cg, a.CoP,
+                                                                      s_co, s_ci, flip);
+    PVB_LAUNCHED("igemm_weight_prep");
+  }
+  const size_t w_bytes = static_cast<size_t>(27) * a.Cg * a.CoP * 16;
+  const size_t smem = 256 + 2 * 2 * 4 * 96 * 4 + round_up(w_bytes, static_cast<size_t>(128)) +
+                      static_cast<size_t>(kIgSlots) * a.Cg * a.NP * 16;
+  PVB_REQUIRE(smem <= 227 * 1024, "conv3d_bf16: Cin=%d Cout=%d width=%d needs %zu B of shared memory (> 227 KB)", Ci, Co, Wi, smem);
+  long long grid = a.units < sms ? a.units : sms;
+  if (a.Cg == 2) {
+    PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_igemm_bf16_kernel<2><<<static_cast<unsigned>(grid), kIgThreads, smem, stream>>>(a);
+  } else {
+    PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_bf16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_igemm_bf16_kernel<4><<<static_cast<unsigned>(grid), kIgThreads, smem, stream>>>(a);
+  }
+  PVB_LAUNCHED("conv3d_igemm_bf16");
+  return PVB200_OK;
+}
+
+}  // namespace pvb
+
+extern "C" {
+
+int pvb200_blocked_channel_groups(int C) { return pvb::igemm_cg(C); }
+
+size_t pvb200_conv3d_bf16_workspace_bytes(int Cin, int Cout) {
+  const size_t f = pvb::igemm_ws_bytes(Cin, Cout), d = pvb::igemm_ws_bytes(Cout, Cin);
+  return f > d ? f : d;
+}
+
+int pvb200_nc_to_blocked_bf16(const float* x, uint16_t* y, int B, int C, int T, int H, int W, int pad,
+                              pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(x && y && B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && pad >= 0, "nc_to_blocked_bf16: bad argument");
+  const int Cg = igemm_cg(C);
+  const long long total = static_cast<long long>(B) * Cg * T * H * W;
+  long long grid = ceil_div(total, 256LL);
+  if (grid > 148 * 32) grid = 148 * 32;
+  nc_to_blocked_bf16_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<uint4*>(y), C, Cg,
+                                                                                         T, H, W, pad, total);
+  PVB_LAUNCHED("nc_to_blocked_bf16");
+  return PVB200_OK;
+}
+
+int pvb200_blocked_to_nc_f32(const uint16_t* x, float* y, int B, int C, int T, int H, int W, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(x && y && B > 0 && C > 0 && T > 0 && H > 0 && W > 0, "blocked_to_nc_f32: bad argument");
+  const int Cg = igemm_cg(C);
+  const long long thw = static_cast<long long>(T) * H * W;
+  const long long total = static_cast<long long>(B) * Cg * thw;
+  long long grid = ceil_div(total, 256LL);
+  if (grid > 148 * 32) grid = 148 * 32;
+  blocked_to_nc_f32_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(x), y, C,
+                                                                                        Cg, thw, total);
+  PVB_LAUNCHED("blocked_to_nc_f32");
+  return PVB200_OK;
+}
+
+int pvb200_conv3d_fwd_bf16(const uint16_t* xb, const float* w, const float* bias, uint16_t* yb, void* workspace,
+                           size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int out_pad,
+                           pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(xb && w && yb, "conv3d_fwd_bf16: null pointer");
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && out_pad >= 0, "conv3d_fwd_bf16: bad shape");
+  return launch_igemm(xb, w, static_cast<long long>(Cin) * 27, 27, 0, bias, nullptr, yb, workspace, workspace_bytes, B, Cin,
+                      Ti, Hi, Wi, Cout, out_pad, relu, as_stream(stream));
+}
+
+int pvb200_conv3d_dgrad_bf16(const uint16_t* gz_padded, const float* w, const uint16_t* mask_src, uint16_t* gx,
+                             void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
+                             int out_pad, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(gz_padded && w && gx, "conv3d_dgrad_bf16: null pointer");
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti > 2 && Hi > 2 && Wi > 2 && out_pad >= 0, "conv3d_dgrad_bf16: bad shape");
+  // kernel input = gz zero-padded by 2: [B][Cg(Cout)][Ti+2][Hi+2][Wi+2]; kernel output = gx [B][Cg(Cin)][Ti][Hi][Wi]
+  return launch_igemm(gz_padded, w, /*s_co (out role = ci)*/ 27, /*s_ci (in role = co)*/ static_cast<long long>(Cin) * 27, 1,
+                      nullptr, mask_src, gx, workspace, workspace_bytes, B, /*Ci role*/ Cout, Ti + 2, Hi + 2, Wi + 2,
+                      /*Co role*/ Cin, out_pad, 0, as_stream(stream));
+}
+
+}  // extern "C"

