@@ -15,17 +15,19 @@
 //     along t re-loads nothing (each plane is fetched once per t-segment).
 //   * all 27 x Cin x Cout weights (55 KB bf16) stay resident in shared memory for the whole persistent CTA.
 //   * wrap columns (wo >= Wo) are computed and dropped in the epilogue (2/Wi ~ 3 % waste).
-// Warp roles (320 threads): warp 0 = copy producer, warp 1 = MMA issuer (one elected thread) + TMEM owner,
-// warps 2-9 = epilogue (TMEM -> registers -> bias/ReLU or ReLU-mask -> bf16 -> 16-byte stores); accumulators are
+// Warp roles (576 threads): warp 0 = copy producer, warp 1 = MMA issuer (one elected thread) + TMEM owner,
+// warps 2-17 = epilogue (TMEM -> registers -> bias/ReLU or ReLU-mask -> bf16 -> 16-byte stores); accumulators are
 // double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 // The data gradient is the same kernel on a zero-padded gz (padding 2) with flipped / transposed weights.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace pvb {
 
-constexpr int kIgThreads = 320;  // producer warp, MMA warp, 8 epilogue warps
-constexpr int kIgSlots = 4;
+constexpr int kIgThreads = 576;  // producer warp, MMA warp, 16 epilogue warps
+constexpr int kIgMaxSlots = 8;  // time-plane ring: 3 planes live per tile + (nslot - 3) planes of prefetch distance
 constexpr int kIgTileM = 256;    // MMA rows per tile = 2 row blocks of 128
 constexpr int kIgTileOut = 254;  // outputs per tile: the kw shift-add needs rows r, r+1, r+2
 
@@ -41,6 +43,9 @@ struct IgemmArgs {
   int NP;       // staged positions per (plane, channel group)
   int tiles_q;  // q tiles per output plane
   int tseg, nseg;
+  int nslot;  // ring slots (4..8), as many as fit in shared memory
+  int dbg_flags;   // experiments: 1 = skip stores, 2 = skip the shift-add, 4 = skip LDS/bar exchange
+  long long* dbg;  // optional [grid][8] cycle counters (profiling builds of the tools; null in production)
   long long units;
 };
 
@@ -81,27 +86,28 @@ __device__ __forceinline__ void igemm_mma(uint32_t d_tmem, uint32_t a_lo, uint32
 template <int CG>
 __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const IgemmArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [4]
-  uint64_t* empty = full + kIgSlots;                        // [4]
-  uint64_t* wfull = empty + kIgSlots;                       // [1]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]
+  uint64_t* empty = full + kIgMaxSlots;                     // [8]
+  uint64_t* wfull = empty + kIgMaxSlots;                    // [1]
   uint64_t* tfull = wfull + 1;                              // [2]
   uint64_t* tempty = tfull + 2;                             // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* bias_s = reinterpret_cast<float*>(smem + 128);     // [32]
-  float* xch = reinterpret_cast<float*>(smem + 256);        // [2 parity][2 rb][4 qd][3*32] boundary rows of the shift-add
-  uint8_t* w_s = smem + 256 + 2 * 2 * 4 * 96 * 4;
+  float* bias_s = reinterpret_cast<float*>(smem + 256);     // [32]
+  float* xch = reinterpret_cast<float*>(smem + 384);        // [2 parity][2 rb][4 qd][3*32] boundary rows of the shift-add
+  uint8_t* w_s = smem + 384 + 2 * 2 * 4 * 96 * 4;
   const int N = 3 * a.CoP;
   const uint32_t w_bytes = 9u * CG * N * 16u;
   const uint32_t slot_bytes = static_cast<uint32_t>(CG) * a.NP * 16u;
   uint8_t* slot_s = w_s + ((w_bytes + 127u) & ~127u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long dbg_tfull_out = 0, dbg_bar_out = 0, dbg_ld_out = 0, dbg_rest_out = 0;
   const uint32_t tmem_cols = (4u * N <= 256u) ? 256u : 512u;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kIgSlots; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+    for (int i = 0; i < kIgMaxSlots; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
     tc::mbar_init(wfull, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 8); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 16); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
@@ -124,6 +130,7 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
         tc::bulk_g2s(w_s + off, reinterpret_cast<const uint8_t*>(a.wq) + off, n, wfull);
       }
       uint32_t seq = 0;
+      const uint32_t nslot = static_cast<uint32_t>(a.nslot);
       for (long long u = u_begin; u < u_end; ++u) {
         const int seg = static_cast<int>(u % a.nseg);
         const long long r = u / a.nseg;
@@ -135,8 +142,8 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
         long long avail = in_plane - q0;
         const uint32_t npos = static_cast<uint32_t>(avail < a.NP ? avail : a.NP);
         for (int p = 0; p < ntiles + 2; ++p, ++seq) {
-          const uint32_t slot = seq & (kIgSlots - 1);
-          const uint32_t n = seq / kIgSlots;
+          const uint32_t slot = seq % nslot;
+          const uint32_t n = seq / nslot;
           tc::mbar_wait(empty + slot, (n & 1u) ^ 1u);
           tc::mbar_arrive_expect_tx(full + slot, npos * 16u * CG);
 #pragma unroll
@@ -149,7 +156,10 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow so that descriptor arithmetic stays in uniform registers;
+    // only the tcgen05.mma / tcgen05.commit instructions themselves are issued by one elected lane.
+    {
+      const bool leader = tc::elect_one();
       const uint32_t idesc = tc::umma_idesc(128, N, /*bf16*/ 1, /*K-major*/ 0, 0);
       const uint32_t a_lbo = static_cast<uint32_t>(a.NP) * 16u;
       const uint32_t b_lbo = static_cast<uint32_t>(N) * 16u;
@@ -161,19 +171,26 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
       const uint32_t slot_16 = slot_bytes >> 4;
       const uint32_t wi = static_cast<uint32_t>(a.Wi);
       tc::mbar_wait(wfull, 0);
+      const uint32_t nslot = static_cast<uint32_t>(a.nslot);
       uint32_t base_seq = 0, waited = 0, tile_ctr = 0;
+      long long dbg_full = 0, dbg_tempty = 0, dbg_issue = 0;
+      const long long dbg_t0 = a.dbg ? clock64() : 0;
       for (long long u = u_begin; u < u_end; ++u) {
         const int seg = static_cast<int>(u % a.nseg);
         const int t0 = seg * a.tseg;
         const int ntiles = min(a.tseg, a.To - t0);
         for (int ti = 0; ti < ntiles; ++ti, ++tile_ctr) {
-          for (; waited < base_seq + ti + 3; ++waited) tc::mbar_wait(full + (waited & (kIgSlots - 1)), (waited / kIgSlots) & 1u);
+          const long long c0 = a.dbg ? clock64() : 0;
+          for (; waited < base_seq + ti + 3; ++waited) tc::mbar_wait(full + (waited % nslot), (waited / nslot) & 1u);
+          const long long c1 = a.dbg ? clock64() : 0;
           const uint32_t acc = tile_ctr & 1u;
           tc::mbar_wait(tempty + acc, ((tile_ctr >> 1) & 1u) ^ 1u);
           tc::tc_fence_after();
+          const long long c2 = a.dbg ? clock64() : 0;
+          dbg_full += c1 - c0; dbg_tempty += c2 - c1;
           uint32_t pl16[3];
 #pragma unroll
-          for (int kt = 0; kt < 3; ++kt) pl16[kt] = slot_addr16 + ((base_seq + ti + kt) & (kIgSlots - 1)) * slot_16;
+          for (int kt = 0; kt < 3; ++kt) pl16[kt] = slot_addr16 + ((base_seq + ti + kt) % nslot) * slot_16;
           // the two row blocks accumulate into different TMEM tiles: alternate them so that back-to-back MMAs are
           // independent (consecutive MMAs into the SAME accumulator serialise on its read-modify-write)
 #pragma unroll
@@ -188,38 +205,52 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
                   // A: rows rb*128.. of plane kt shifted by kh input rows; channel groups 2ks, 2ks+1
                   const uint32_t a16 = pl16[kt] + static_cast<uint32_t>(2 * ks) * (a_lbo >> 4) + rb * 128u + kh * wi;
                   const uint32_t b16 = static_cast<uint32_t>(((kt * 3 + kh) * CG + 2 * ks)) * (b_lbo >> 4);
-                  igemm_mma(d_tmem, a_lo_base | (a16 & 0x3fffu), desc_hi, b_lo_base + b16, desc_hi, idesc,
-                            (kt | kh | ks) ? 1u : 0u);
+                  if (leader)
+                    igemm_mma(d_tmem, a_lo_base | (a16 & 0x3fffu), desc_hi, b_lo_base + b16, desc_hi, idesc,
+                              (kt | kh | ks) ? 1u : 0u);
                 }
               }
             }
           }
-          tc::umma_commit(tfull + acc);                                     // accumulators ready for the epilogue
-          tc::umma_commit(empty + ((base_seq + ti) & (kIgSlots - 1)));      // oldest time plane is free
-          if (ti == ntiles - 1) {
-            tc::umma_commit(empty + ((base_seq + ti + 1) & (kIgSlots - 1)));
-            tc::umma_commit(empty + ((base_seq + ti + 2) & (kIgSlots - 1)));
+          __syncwarp();
+          if (leader) {
+            tc::umma_commit(tfull + acc);                                     // accumulators ready for the epilogue
+            tc::umma_commit(empty + ((base_seq + ti) % nslot));      // oldest time plane is free
+            if (ti == ntiles - 1) {
+              tc::umma_commit(empty + ((base_seq + ti + 1) % nslot));
+              tc::umma_commit(empty + ((base_seq + ti + 2) % nslot));
+            }
           }
+          __syncwarp();
+          dbg_issue += (a.dbg ? clock64() : 0) - c2;
         }
         base_seq += ntiles + 2;
       }
+      if (a.dbg && lane == 0) {
+        long long* d = a.dbg + blockIdx.x * 8;
+        d[0] = clock64() - dbg_t0; d[1] = dbg_full; d[2] = dbg_tempty; d[3] = dbg_issue; d[4] = tile_ctr;
+      }
     }
   } else {
-    // =============================== epilogue (warps 2..9) ===============================
+    // =============================== epilogue (warps 2..17) ===============================
     // out[r][co] = D[r][co] + D[r+1][CoP + co] + D[r+2][2 CoP + co]   (the kw shift-add; rows = TMEM lanes)
-    // warps 2-5 own row block 0, warps 6-9 row block 1; warp % 4 = the TMEM lane quadrant a warp may access.
+    // 16 warps: warp % 4 = the TMEM lane quadrant a warp may access; (warp-2)/4 selects (row block, half of the
+    // output channels), so four warps per scheduler hide each other's TMEM / shuffle / store latencies.
     const int qd = warp & 3;
-    const int rb = (warp - 2) >> 2;
+    const int rbh = (warp - 2) >> 2;
+    const int rb = rbh >> 1, half = rbh & 1;
     const int Cog = a.CogOut;
     const int CoP = a.CoP;
     const int Top = a.To + 2 * a.out_pad, Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
     const long long oplane = static_cast<long long>(Hop) * Wop;
     const long long mplane = static_cast<long long>(a.Ho) * a.Wo;
-    const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
+    const float4* bias4 = reinterpret_cast<const float4*>(bias_s) + 4 * half;
     const int row = rb * 128 + qd * 32 + lane;
     const int me = rb * 4 + qd;
     const int nb = me + 1;  // block holding rows row+1, row+2 beyond this quadrant (8 = none: rows 254/255 are not emitted)
+    const bool active = (2 * half) < Cog;  // this warp's two channel groups exist in the output tensor
     uint32_t tile_ctr = 0;
+    long long dbg_tfull = 0, dbg_bar = 0, dbg_ld = 0, dbg_rest = 0;
     for (long long u = u_begin; u < u_end; ++u) {
       const int seg = static_cast<int>(u % a.nseg);
       const long long r = u / a.nseg;
@@ -229,29 +260,42 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
       const int ntiles = min(a.tseg, a.To - t0);
       const int q = qt * kIgTileOut + row;
       const int ho = q / a.Wi, wo = q - ho * a.Wi;
-      const bool valid = (row < kIgTileOut) && (ho < a.Ho) && (wo < a.Wo);
+      const bool valid = active && (row < kIgTileOut) && (ho < a.Ho) && (wo < a.Wo);
       for (int ti = 0; ti < ntiles; ++ti, ++tile_ctr) {
         const uint32_t acc = tile_ctr & 1u;
+        const int t = t0 + ti;
+        // ReLU-mask source of the data gradient: issue the loads before waiting for the accumulators
+        uint4 mk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (a.mask && valid) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            if (2 * half + g < Cog)
+              mk[g] = __ldg(a.mask + ((static_cast<long long>(b) * Cog + 2 * half + g) * a.To + t) * mplane +
+                            static_cast<long long>(ho) * a.Wo + wo);
+        }
+        const long long e0 = a.dbg ? clock64() : 0;
         tc::mbar_wait(tfull + acc, (tile_ctr >> 1) & 1u);
         tc::tc_fence_after();
-        const int t = t0 + ti;
+        dbg_tfull += (a.dbg ? clock64() : 0) - e0;
         float* xp = xch + (tile_ctr & 1u) * (2 * 4 * 96);
-        uint32_t v0[32], v1[32], v2[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + (acc * 2u + rb) * N;
-        tc::tmem_ld_32x32(taddr, v0);
-        tc::tmem_ld_32x32(taddr + CoP, v1);
-        tc::tmem_ld_32x32(taddr + 2 * CoP, v2);
+        uint32_t v0[16], v1[16], v2[16];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + (acc * 2u + rb) * N + 16 * half;
+        const long long l0 = a.dbg ? clock64() : 0;
+        tc::tmem_ld_32x16(taddr, v0);
+        tc::tmem_ld_32x16(taddr + CoP, v1);
+        tc::tmem_ld_32x16(taddr + 2 * CoP, v2);
         tc::tmem_ld_wait();
+        dbg_ld += (a.dbg ? clock64() : 0) - l0;
         // all TMEM reads of this warp are done: release the accumulator as early as possible
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tempty + acc);
-        // publish this quadrant's first two rows of the kw=1 / kw=2 partial sums for the quadrant below
+        // publish this quadrant's first two rows of the kw=1 / kw=2 partial sums for the quadrant above
         if (lane < 2) {
-          float4* dst = reinterpret_cast<float4*>(xp + me * 96);
+          float4* dst = reinterpret_cast<float4*>(xp + me * 96 + 16 * half);
           if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
               dst[c] = make_float4(__uint_as_float(v1[4 * c]), __uint_as_float(v1[4 * c + 1]), __uint_as_float(v1[4 * c + 2]),
                                    __uint_as_float(v1[4 * c + 3]));
               dst[8 + c] = make_float4(__uint_as_float(v2[4 * c]), __uint_as_float(v2[4 * c + 1]),
@@ -259,38 +303,45 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
             }
           } else {
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
+            for (int c = 0; c < 4; ++c)
               dst[16 + c] = make_float4(__uint_as_float(v2[4 * c]), __uint_as_float(v2[4 * c + 1]),
                                         __uint_as_float(v2[4 * c + 2]), __uint_as_float(v2[4 * c + 3]));
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
+        const long long e1 = a.dbg ? clock64() : 0;
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // the sixteen epilogue warps
+        const long long e2 = a.dbg ? clock64() : 0;
+        dbg_bar += e2 - e1;
         // neighbour rows for lanes 30 / 31 (other lanes read a harmless in-range address and ignore it)
-        const float4* n1 = reinterpret_cast<const float4*>(xp + (nb < 8 ? nb : me) * 96);  // kw=1 row of lane 0 below
+        const float4* n1 = reinterpret_cast<const float4*>(xp + (nb < 8 ? nb : me) * 96 + 16 * half);  // kw=1 row of lane 0
         const float4* n2 = n1 + ((lane == 30) ? 8 : 16);  // lane 30: kw=2 row of lane 0; lane 31: kw=2 row of lane 1
-        float o[32];
+        float o[16];
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
+        for (int c4 = 0; c4 < 4; ++c4) {
           const float4 f1 = n1[c4];
           const float4 f2 = n2[c4];
           const float4 fb = bias4[c4];
-          const float e1[4] = {f1.x, f1.y, f1.z, f1.w};
-          const float e2[4] = {f2.x, f2.y, f2.z, f2.w};
+          const float e1v[4] = {f1.x, f1.y, f1.z, f1.w};
+          const float e2v[4] = {f2.x, f2.y, f2.z, f2.w};
           const float eb[4] = {fb.x, fb.y, fb.z, fb.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c = 4 * c4 + j;
-            float s1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v1[c]), 1);
-            float s2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 2);
-            s1 = (lane == 31) ? e1[j] : s1;
-            s2 = (lane >= 30) ? e2[j] : s2;
+            float s1 = __uint_as_float(v1[c]), s2 = __uint_as_float(v2[c]);
+            if (!(a.dbg_flags & 2)) {
+              s1 = __shfl_down_sync(0xffffffffu, s1, 1);
+              s2 = __shfl_down_sync(0xffffffffu, s2, 2);
+            }
+            s1 = (lane == 31) ? e1v[j] : s1;
+            s2 = (lane >= 30) ? e2v[j] : s2;
             o[c] = (__uint_as_float(v0[c]) + s1) + (s2 + eb[j]);
           }
         }
         if (valid) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g >= Cog) continue;
+          for (int g = 0; g < 2; ++g) {
+            const int cog = 2 * half + g;
+            if (cog >= Cog) continue;
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -299,9 +350,7 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
               f[j] = x;
             }
             if (a.mask) {
-              const uint4 m = __ldg(a.mask + ((static_cast<long long>(b) * Cog + g) * a.To + t) * mplane +
-                                    static_cast<long long>(ho) * a.Wo + wo);
-              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+              const uint32_t mw[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
@@ -311,13 +360,17 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
             }
             uint4 ov = make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]),
                                   tc::pack_bf16(f[6], f[7]));
-            a.y[((static_cast<long long>(b) * Cog + g) * Top + (t + a.out_pad)) * oplane +
-                static_cast<long long>(ho + a.out_pad) * Wop + (wo + a.out_pad)] = ov;
+            if (!(a.dbg_flags & 1) || ov.x == 0x12345678u)
+              a.y[((static_cast<long long>(b) * Cog + cog) * Top + (t + a.out_pad)) * oplane +
+                  static_cast<long long>(ho + a.out_pad) * Wop + (wo + a.out_pad)] = ov;
           }
         }
+        dbg_rest += (a.dbg ? clock64() : 0) - e2;
       }
     }
+    dbg_tfull_out = dbg_tfull; dbg_bar_out = dbg_bar; dbg_ld_out = dbg_ld; dbg_rest_out = dbg_rest;
   }
+  if (a.dbg && threadIdx.x == 64) { a.dbg[blockIdx.x * 8 + 5] = dbg_tfull_out; a.dbg[blockIdx.x * 8 + 6] = dbg_bar_out; a.dbg[blockIdx.x * 8 + 7] = dbg_ld_out; a.dbg[blockIdx.x * 8 + 4] = -dbg_rest_out; }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
@@ -368,6 +421,8 @@ __global__ void blocked_to_nc_f32_kernel(const uint4* __restrict__ x, float* __r
   }
 }
 
+long long* g_igemm_dbg = nullptr;  // set through pvb200_debug_set_igemm_counters (tools only)
+
 static int igemm_cg(int C) { return 2 * ceil_div(C, 16); }  // channel groups of 8, padded to an even count (UMMA K = 16)
 
 static int igemm_cop(int Co) { return Co <= 16 ? 16 : 32; }
@@ -417,9 +472,15 @@ static int launch_igemm(const void* xb, const float* w, long long s_co, long lon
     PVB_LAUNCHED("igemm_weight_prep");
   }
   const size_t w_bytes = static_cast<size_t>(27) * a.Cg * a.CoP * 16;
-  const size_t smem = 256 + 2 * 2 * 4 * 96 * 4 + round_up(w_bytes, static_cast<size_t>(128)) +
-                      static_cast<size_t>(kIgSlots) * a.Cg * a.NP * 16;
-  PVB_REQUIRE(smem <= 227 * 1024, "conv3d_bf16: Cin=%d Cout=%d width=%d needs %zu B of shared memory (> 227 KB)", Ci, Co, Wi, smem);
+  const size_t fixed = 384 + 2 * 2 * 4 * 96 * 4 + round_up(w_bytes, static_cast<size_t>(128));
+  const size_t slot_bytes = static_cast<size_t>(a.Cg) * a.NP * 16;
+  long long nslot = (227 * 1024 - static_cast<long long>(fixed)) / static_cast<long long>(slot_bytes);
+  if (nslot > kIgMaxSlots) nslot = kIgMaxSlots;
+  PVB_REQUIRE(nslot >= 4, "conv3d_bf16: Cin=%d Cout=%d width=%d does not fit in shared memory", Ci, Co, Wi);
+  a.nslot = static_cast<int>(nslot);
+  a.dbg = g_igemm_dbg;
+  { const char* e = getenv("PVB200_IGEMM_DBG"); a.dbg_flags = e ? atoi(e) : 0; }
+  const size_t smem = fixed + nslot * slot_bytes;
   long long grid = a.units < sms ? a.units : sms;
   if (a.Cg == 2) {
     PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -435,6 +496,9 @@ static int launch_igemm(const void* xb, const float* w, long long s_co, long lon
 }  // namespace pvb
 
 extern "C" {
+
+/* tools only (not declared in pvb200.h): per-CTA cycle counters of the igemm kernel, [grid][8] long long */
+void pvb200_debug_set_igemm_counters(long long* p) { pvb::g_igemm_dbg = p; }
 
 int pvb200_blocked_channel_groups(int C) { return pvb::igemm_cg(C); }
 

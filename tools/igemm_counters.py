@@ -1,0 +1,38 @@
+"""Print the igemm kernel's internal cycle counters (MMA warp: waiting for data / for the epilogue / issuing;
+epilogue warp: waiting for accumulators / at the exchange barrier) for one layer.  python tools/igemm_counters.py fwd 1"""
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from predict_pv_yield_b200 import lib, ops  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
+layer = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+L = lib.load()
+dev = torch.device("cuda:0")
+B = 32
+T, S, C = 19, 64, 12
+for _ in range(layer):
+    C, T, S = 32, T - 2, S - 2
+w = torch.randn(32, C, 3, 3, 3, device=dev) / (C * 27) ** 0.5
+b = torch.randn(32, device=dev)
+x = torch.randn(B, C, T, S, S, device=dev)
+gz = torch.randn(B, 32, T - 2, S - 2, S - 2, device=dev)
+xb = ops.to_blocked_bf16(x)
+gzp = ops.to_blocked_bf16(gz, pad=2)
+run = (lambda: ops.conv3d_fwd_bf16(xb, w, b)) if which == "fwd" else (lambda: ops.conv3d_dgrad_bf16(gzp, w, xb))
+run()
+dbg = torch.zeros((148, 8), dtype=torch.int64, device=dev)
+L.pvb200_debug_set_igemm_counters.argtypes = [ctypes.c_void_p]
+L.pvb200_debug_set_igemm_counters(dbg.data_ptr())
+run()
+torch.cuda.synchronize()
+L.pvb200_debug_set_igemm_counters(None)
+d = dbg.double().cpu()
+names = ["mma_total", "mma_wait_full", "mma_wait_tempty", "mma_issue", "epi_rest(neg)", "epi_wait_tfull", "epi_wait_bar", "epi_ld"]
+m = d.mean(0)
+print(which, "layer", layer, {n: round(float(m[i])) for i, n in enumerate(names)})

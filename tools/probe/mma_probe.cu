@@ -1,0 +1,89 @@
+// mma_probe.cu -- microbenchmark: cycles per tcgen05.mma (cta_group::1, kind::f16, M=128) for different shared-memory
+// operand layouts (SWIZZLE_NONE / 32B / 64B / 128B, K-major) and N.  Decides the operand layout of the conv kernels.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mma_probe mma_probe.cu ; run on a B200.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../predict_pv_yield_b200/csrc/tc_common.cuh"
+using namespace pvb;
+
+__device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(d),
+               "l"(a), "l"(b), "r"(idesc), "r"(acc));
+}
+
+// layout: 0 none, 1 = 128B_base32B, 2 = 128B, 4 = 64B, 6 = 32B
+__global__ void probe(int layout, int N, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, int iters, int nacc,
+                      long long* out, int M = 128, int nissuers = 1, int always_overwrite = 0) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { tc::mbar_init(&bar, nissuers); tc::fence_barrier_init(); }
+  tc::fence_proxy_async();
+  if (warp == 0) tc::tmem_alloc(&tptr, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tptr;
+  if ((threadIdx.x & 31) == 0 && warp < nissuers) {
+    const uint32_t idesc = tc::umma_idesc(M, N, 1, 0, 0);
+    const uint32_t a_addr = tc::smem_u32(smem), b_addr = a_addr + 96 * 1024;
+    uint64_t ad = tc::umma_desc(a_addr, a_lbo, a_sbo) | (static_cast<uint64_t>(layout) << 61);
+    uint64_t bd = tc::umma_desc(b_addr, b_lbo, b_sbo) | (static_cast<uint64_t>(layout) << 61);
+    long long t0 = clock64();
+    const uint32_t tbase = tmem + warp * (512 / nissuers);
+    const uint32_t accflag = always_overwrite ? 0u : 1u;
+    const uint32_t nmask = static_cast<uint32_t>(nacc - 1);  // nacc is a power of two
+    for (int i = 0; i < nacc; ++i) mma(tbase + i * N, ad, bd, idesc, 0);
+    for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mma(tbase + ((j & nmask) * N), ad + j * 8, bd, idesc, accflag);
+    }
+    tc::umma_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (warp == 0) out[blockIdx.x] = t1 - t0;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+int main() {
+  long long* out;
+  cudaMalloc(&out, 148 * sizeof(long long));
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  struct Cfg { const char* name; int layout, N; uint32_t a_lbo, a_sbo, b_lbo, b_sbo; int nacc, M, nissuers, ow; };
+  Cfg cfgs[] = {
+      {"sw128 N=32 nacc1", 2, 32, 16, 1024, 16, 1024, 1, 128, 1, 0},
+      {"sw128 N=32 nacc4", 2, 32, 16, 1024, 16, 1024, 4, 128, 1, 0},
+      {"sw128 N=32 nacc8", 2, 32, 16, 1024, 16, 1024, 8, 128, 1, 0},
+      {"sw128 N=32 overwrite", 2, 32, 16, 1024, 16, 1024, 4, 128, 1, 1},
+      {"sw128 N=32 2 issuers", 2, 32, 16, 1024, 16, 1024, 2, 128, 2, 0},
+      {"sw128 N=32 4 issuers", 2, 32, 16, 1024, 16, 1024, 2, 128, 4, 0},
+      {"sw128 N=96 4 issuers", 2, 96, 16, 1024, 16, 1024, 1, 128, 4, 0},
+      {"sw128 N=32 M=64", 2, 32, 16, 1024, 16, 1024, 4, 64, 1, 0},
+      {"sw128 N=64 nacc4", 2, 64, 16, 1024, 16, 1024, 4, 128, 1, 0},
+      {"sw128 N=128 nacc2", 2, 128, 16, 1024, 16, 1024, 2, 128, 1, 0},
+      {"sw128 N=192 nacc2", 2, 192, 16, 1024, 16, 1024, 2, 128, 1, 0},
+      {"sw128 N=256 nacc2", 2, 256, 16, 1024, 16, 1024, 2, 128, 1, 0},
+      {"none  N=256 nacc2", 0, 256, 6144, 128, 4096, 128, 2, 128, 1, 0},
+      {"none  N=192 nacc2", 0, 192, 6144, 128, 3072, 128, 2, 128, 1, 0},
+  };
+  const int iters = 2000;
+  for (auto& c : cfgs) {
+    const int grid = 148;
+    probe<<<grid, 128, 160 * 1024>>>(c.layout, c.N, c.a_lbo, c.a_sbo, c.b_lbo, c.b_sbo, iters, c.nacc, out, c.M, c.nissuers, c.ow);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: CUDA error %s\n", c.name, cudaGetErrorString(e)); return 1; }
+    long long h[148];
+    cudaMemcpy(h, out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+    const double cyc = double(mx) / iters;
+    printf("%-26s %7.1f cycles/iter  -> %6.0f MAC/cycle/SM (peak ~4096)\n", c.name, cyc, double(c.M) * c.N * 16 * c.nissuers / cyc);
+  }
+  return 0;
+}
