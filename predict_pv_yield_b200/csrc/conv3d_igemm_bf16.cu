@@ -42,11 +42,9 @@ struct IgemmArgs {
   int out_pad, relu;
   int NP;       // staged positions per (plane, channel group)
   int tiles_q;  // q tiles per output plane
-  int tseg, nseg;
   int nslot;  // ring slots (4..8), as many as fit in shared memory
-  int dbg_flags;   // experiments: 1 = skip stores, 2 = skip the shift-add, 4 = skip LDS/bar exchange
   long long* dbg;  // optional [grid][8] cycle counters (profiling builds of the tools; null in production)
-  long long units;
+  long long tiles;  // B * tiles_q * To
 };
 
 // weights fp32 [Co][Ci][27] -> bf16 [(kt,kh)][Cg][kw*CoP + co][8 ci]; flipped / transposed roles for the data gradient
@@ -83,7 +81,24 @@ __device__ __forceinline__ void igemm_mma(uint32_t d_tmem, uint32_t a_lo, uint32
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
 }
 
-template <int CG>
+// A "run" = consecutive output time steps of one (sample, q-tile) column handled by one CTA.  Tiles are numbered
+// g = (b * tiles_q + qt) * To + t and split evenly (tile-granular) over the persistent CTAs; every role walks the same
+// sequence of runs.  The first tile of a run needs three fresh input planes, every further tile one.
+struct IgRun {
+  int b, qt, t0, ntiles;
+};
+__device__ __forceinline__ IgRun ig_run(long long g, long long g_end, int To, int tiles_q) {
+  IgRun r;
+  const long long col = g / To;
+  r.t0 = static_cast<int>(g - col * To);
+  r.qt = static_cast<int>(col % tiles_q);
+  r.b = static_cast<int>(col / tiles_q);
+  const long long left = g_end - g;
+  r.ntiles = static_cast<int>(left < (To - r.t0) ? left : (To - r.t0));
+  return r;
+}
+
+template <int CG, bool DBG>
 __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const IgemmArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]
@@ -101,7 +116,6 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
   uint8_t* slot_s = w_s + ((w_bytes + 127u) & ~127u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long dbg_tfull_out = 0, dbg_bar_out = 0, dbg_ld_out = 0, dbg_rest_out = 0;
   const uint32_t tmem_cols = (4u * N <= 256u) ? 256u : 512u;
 
   if (threadIdx.x == 0) {
@@ -117,9 +131,10 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const long long u_begin = a.units * blockIdx.x / gridDim.x;
-  const long long u_end = a.units * (blockIdx.x + 1) / gridDim.x;
+  const long long g_begin = a.tiles * blockIdx.x / gridDim.x;
+  const long long g_end = a.tiles * (blockIdx.x + 1) / gridDim.x;
   const long long in_plane = static_cast<long long>(a.Hi) * a.Wi;
+  const uint32_t nslot = static_cast<uint32_t>(a.nslot);
 
   if (warp == 0) {
     // =============================== producer ===============================
@@ -130,112 +145,102 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
         tc::bulk_g2s(w_s + off, reinterpret_cast<const uint8_t*>(a.wq) + off, n, wfull);
       }
       uint32_t seq = 0;
-      const uint32_t nslot = static_cast<uint32_t>(a.nslot);
-      for (long long u = u_begin; u < u_end; ++u) {
-        const int seg = static_cast<int>(u % a.nseg);
-        const long long r = u / a.nseg;
-        const int qt = static_cast<int>(r % a.tiles_q);
-        const int b = static_cast<int>(r / a.tiles_q);
-        const int t0 = seg * a.tseg;
-        const int ntiles = min(a.tseg, a.To - t0);
-        const int q0 = qt * kIgTileOut;
-        long long avail = in_plane - q0;
+      for (long long g = g_begin; g < g_end;) {
+        const IgRun r = ig_run(g, g_end, a.To, a.tiles_q);
+        const int q0 = r.qt * kIgTileOut;
+        const long long avail = in_plane - q0;
         const uint32_t npos = static_cast<uint32_t>(avail < a.NP ? avail : a.NP);
-        for (int p = 0; p < ntiles + 2; ++p, ++seq) {
+        for (int p = 0; p < r.ntiles + 2; ++p, ++seq) {
           const uint32_t slot = seq % nslot;
-          const uint32_t n = seq / nslot;
-          tc::mbar_wait(empty + slot, (n & 1u) ^ 1u);
+          tc::mbar_wait(empty + slot, ((seq / nslot) & 1u) ^ 1u);
           tc::mbar_arrive_expect_tx(full + slot, npos * 16u * CG);
 #pragma unroll
           for (int cg = 0; cg < CG; ++cg) {
-            const uint4* src = a.x + ((static_cast<long long>(b) * CG + cg) * a.Ti + (t0 + p)) * in_plane + q0;
+            const uint4* src = a.x + ((static_cast<long long>(r.b) * CG + cg) * a.Ti + (r.t0 + p)) * in_plane + q0;
             tc::bulk_g2s(slot_s + slot * slot_bytes + static_cast<uint32_t>(cg) * a.NP * 16u, src, npos * 16u, full + slot);
           }
         }
+        g += r.ntiles;
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     // The whole warp runs the (warp-uniform) control flow so that descriptor arithmetic stays in uniform registers;
     // only the tcgen05.mma / tcgen05.commit instructions themselves are issued by one elected lane.
-    {
-      const bool leader = tc::elect_one();
-      const uint32_t idesc = tc::umma_idesc(128, N, /*bf16*/ 1, /*K-major*/ 0, 0);
-      const uint32_t a_lbo = static_cast<uint32_t>(a.NP) * 16u;
-      const uint32_t b_lbo = static_cast<uint32_t>(N) * 16u;
-      // descriptor halves: hi = SBO (128 B) | version; lo = start address | LBO
-      const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-      const uint32_t a_lo_base = ((a_lbo >> 4) << 16);
-      const uint32_t b_lo_base = ((b_lbo >> 4) << 16) | ((tc::smem_u32(w_s) >> 4) & 0x3fffu);
-      const uint32_t slot_addr16 = tc::smem_u32(slot_s) >> 4;  // in 16-byte units
-      const uint32_t slot_16 = slot_bytes >> 4;
-      const uint32_t wi = static_cast<uint32_t>(a.Wi);
-      tc::mbar_wait(wfull, 0);
-      const uint32_t nslot = static_cast<uint32_t>(a.nslot);
-      uint32_t base_seq = 0, waited = 0, tile_ctr = 0;
-      long long dbg_full = 0, dbg_tempty = 0, dbg_issue = 0;
-      const long long dbg_t0 = a.dbg ? clock64() : 0;
-      for (long long u = u_begin; u < u_end; ++u) {
-        const int seg = static_cast<int>(u % a.nseg);
-        const int t0 = seg * a.tseg;
-        const int ntiles = min(a.tseg, a.To - t0);
-        for (int ti = 0; ti < ntiles; ++ti, ++tile_ctr) {
-          const long long c0 = a.dbg ? clock64() : 0;
-          for (; waited < base_seq + ti + 3; ++waited) tc::mbar_wait(full + (waited % nslot), (waited / nslot) & 1u);
-          const long long c1 = a.dbg ? clock64() : 0;
-          const uint32_t acc = tile_ctr & 1u;
-          tc::mbar_wait(tempty + acc, ((tile_ctr >> 1) & 1u) ^ 1u);
-          tc::tc_fence_after();
-          const long long c2 = a.dbg ? clock64() : 0;
-          dbg_full += c1 - c0; dbg_tempty += c2 - c1;
-          uint32_t pl16[3];
+    const bool leader = tc::elect_one();
+    const uint32_t idesc = tc::umma_idesc(128, N, /*bf16*/ 1, /*K-major*/ 0, 0);
+    const uint32_t a_lbo = static_cast<uint32_t>(a.NP) * 16u;
+    const uint32_t b_lbo = static_cast<uint32_t>(N) * 16u;
+    // descriptor halves: hi = SBO (128 B) | version; lo = start address | LBO
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo_base = ((a_lbo >> 4) << 16);
+    const uint32_t b_lo_base = ((b_lbo >> 4) << 16) | ((tc::smem_u32(w_s) >> 4) & 0x3fffu);
+    const uint32_t slot_addr16 = tc::smem_u32(slot_s) >> 4;  // in 16-byte units
+    const uint32_t slot_16 = slot_bytes >> 4;
+    const uint32_t wi = static_cast<uint32_t>(a.Wi);
+    tc::mbar_wait(wfull, 0);
+    uint32_t base_seq = 0, waited = 0, tile_ctr = 0;
+    long long dbg_full = 0, dbg_tempty = 0, dbg_issue = 0;
+    const long long dbg_t0 = DBG ? clock64() : 0;
+    for (long long g = g_begin; g < g_end;) {
+      const IgRun r = ig_run(g, g_end, a.To, a.tiles_q);
+      for (int ti = 0; ti < r.ntiles; ++ti, ++tile_ctr) {
+        const long long c0 = DBG ? clock64() : 0;
+        for (; waited < base_seq + ti + 3; ++waited) tc::mbar_wait(full + (waited % nslot), (waited / nslot) & 1u);
+        const long long c1 = DBG ? clock64() : 0;
+        const uint32_t acc = tile_ctr & 1u;
+        tc::mbar_wait(tempty + acc, ((tile_ctr >> 1) & 1u) ^ 1u);
+        tc::tc_fence_after();
+        const long long c2 = DBG ? clock64() : 0;
+        uint32_t pl16[3];
 #pragma unroll
-          for (int kt = 0; kt < 3; ++kt) pl16[kt] = slot_addr16 + ((base_seq + ti + kt) % nslot) * slot_16;
-          // the two row blocks accumulate into different TMEM tiles: alternate them so that back-to-back MMAs are
-          // independent (consecutive MMAs into the SAME accumulator serialise on its read-modify-write)
+        for (int kt = 0; kt < 3; ++kt) pl16[kt] = slot_addr16 + ((base_seq + ti + kt) % nslot) * slot_16;
+        // the two row blocks accumulate into different TMEM tiles and are interleaved
 #pragma unroll
-          for (int kt = 0; kt < 3; ++kt) {
+        for (int kt = 0; kt < 3; ++kt) {
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
+          for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-              for (int ks = 0; ks < CG / 2; ++ks) {
+            for (int ks = 0; ks < CG / 2; ++ks) {
 #pragma unroll
-                for (int rb = 0; rb < 2; ++rb) {
-                  const uint32_t d_tmem = tmem_base + (acc * 2u + rb) * N;
-                  // A: rows rb*128.. of plane kt shifted by kh input rows; channel groups 2ks, 2ks+1
-                  const uint32_t a16 = pl16[kt] + static_cast<uint32_t>(2 * ks) * (a_lbo >> 4) + rb * 128u + kh * wi;
-                  const uint32_t b16 = static_cast<uint32_t>(((kt * 3 + kh) * CG + 2 * ks)) * (b_lbo >> 4);
-                  if (leader)
-                    igemm_mma(d_tmem, a_lo_base | (a16 & 0x3fffu), desc_hi, b_lo_base + b16, desc_hi, idesc,
-                              (kt | kh | ks) ? 1u : 0u);
-                }
+              for (int rb = 0; rb < 2; ++rb) {
+                const uint32_t d_tmem = tmem_base + (acc * 2u + rb) * N;
+                // A: rows rb*128.. of plane kt shifted by kh input rows; channel groups 2ks, 2ks+1
+                const uint32_t a16 = pl16[kt] + static_cast<uint32_t>(2 * ks) * (a_lbo >> 4) + rb * 128u + kh * wi;
+                const uint32_t b16 = static_cast<uint32_t>(((kt * 3 + kh) * CG + 2 * ks)) * (b_lbo >> 4);
+                if (leader)
+                  igemm_mma(d_tmem, a_lo_base | (a16 & 0x3fffu), desc_hi, b_lo_base + b16, desc_hi, idesc,
+                            (kt | kh | ks) ? 1u : 0u);
               }
             }
           }
-          __syncwarp();
-          if (leader) {
-            tc::umma_commit(tfull + acc);                                     // accumulators ready for the epilogue
-            tc::umma_commit(empty + ((base_seq + ti) % nslot));      // oldest time plane is free
-            if (ti == ntiles - 1) {
-              tc::umma_commit(empty + ((base_seq + ti + 1) % nslot));
-              tc::umma_commit(empty + ((base_seq + ti + 2) % nslot));
-            }
-          }
-          __syncwarp();
-          dbg_issue += (a.dbg ? clock64() : 0) - c2;
         }
-        base_seq += ntiles + 2;
+        __syncwarp();
+        if (leader) {
+          tc::umma_commit(tfull + acc);                       // accumulators ready for the epilogue
+          tc::umma_commit(empty + ((base_seq + ti) % nslot));  // oldest time plane is free
+          if (ti == r.ntiles - 1) {
+            tc::umma_commit(empty + ((base_seq + ti + 1) % nslot));
+            tc::umma_commit(empty + ((base_seq + ti + 2) % nslot));
+          }
+        }
+        __syncwarp();
+        if (DBG) { dbg_full += c1 - c0; dbg_tempty += c2 - c1; dbg_issue += clock64() - c2; }
       }
-      if (a.dbg && lane == 0) {
-        long long* d = a.dbg + blockIdx.x * 8;
-        d[0] = clock64() - dbg_t0; d[1] = dbg_full; d[2] = dbg_tempty; d[3] = dbg_issue; d[4] = tile_ctr;
-      }
+      base_seq += r.ntiles + 2;
+      g += r.ntiles;
+    }
+    if (DBG && a.dbg && lane == 0) {
+      long long* d = a.dbg + blockIdx.x * 8;
+      d[0] = clock64() - dbg_t0; d[1] = dbg_full; d[2] = dbg_tempty; d[3] = dbg_issue; d[4] = tile_ctr;
     }
   } else {
     // =============================== epilogue (warps 2..17) ===============================
     // out[r][co] = D[r][co] + D[r+1][CoP + co] + D[r+2][2 CoP + co]   (the kw shift-add; rows = TMEM lanes)
     // 16 warps: warp % 4 = the TMEM lane quadrant a warp may access; (warp-2)/4 selects (row block, half of the
-    // output channels), so four warps per scheduler hide each other's TMEM / shuffle / store latencies.
+    // output channels).  Rows r+1 / r+2 come from the neighbouring lanes by shuffle; the two rows that live in the
+    // next quadrant (another warp) are exchanged through shared memory and patched into lanes 0 / 1 BEFORE a rotating
+    // shuffle, so no per-element select is needed.
     const int qd = warp & 3;
     const int rbh = (warp - 2) >> 2;
     const int rb = rbh >> 1, half = rbh & 1;
@@ -244,113 +249,103 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
     const int Top = a.To + 2 * a.out_pad, Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
     const long long oplane = static_cast<long long>(Hop) * Wop;
     const long long mplane = static_cast<long long>(a.Ho) * a.Wo;
-    const float4* bias4 = reinterpret_cast<const float4*>(bias_s) + 4 * half;
     const int row = rb * 128 + qd * 32 + lane;
     const int me = rb * 4 + qd;
-    const int nb = me + 1;  // block holding rows row+1, row+2 beyond this quadrant (8 = none: rows 254/255 are not emitted)
+    const bool has_nb = me < 7;  // the last quadrant of the tile has no neighbour: its rows 254/255 are not emitted
     const bool active = (2 * half) < Cog;  // this warp's two channel groups exist in the output tensor
+    const int src1 = (lane + 1) & 31, src2 = (lane + 2) & 31;
+    const float4* bias4 = reinterpret_cast<const float4*>(bias_s) + 4 * half;
     uint32_t tile_ctr = 0;
     long long dbg_tfull = 0, dbg_bar = 0, dbg_ld = 0, dbg_rest = 0;
-    for (long long u = u_begin; u < u_end; ++u) {
-      const int seg = static_cast<int>(u % a.nseg);
-      const long long r = u / a.nseg;
-      const int qt = static_cast<int>(r % a.tiles_q);
-      const int b = static_cast<int>(r / a.tiles_q);
-      const int t0 = seg * a.tseg;
-      const int ntiles = min(a.tseg, a.To - t0);
-      const int q = qt * kIgTileOut + row;
+    for (long long g = g_begin; g < g_end;) {
+      const IgRun r = ig_run(g, g_end, a.To, a.tiles_q);
+      const int q = r.qt * kIgTileOut + row;
       const int ho = q / a.Wi, wo = q - ho * a.Wi;
       const bool valid = active && (row < kIgTileOut) && (ho < a.Ho) && (wo < a.Wo);
-      for (int ti = 0; ti < ntiles; ++ti, ++tile_ctr) {
+      // element offsets of this thread's position in the output / mask tensors at t = t0, channel group 2*half
+      long long o_off = ((static_cast<long long>(r.b) * Cog + 2 * half) * Top + (r.t0 + a.out_pad)) * oplane +
+                        static_cast<long long>(ho + a.out_pad) * Wop + (wo + a.out_pad);
+      long long m_off = ((static_cast<long long>(r.b) * Cog + 2 * half) * a.To + r.t0) * mplane +
+                        static_cast<long long>(ho) * a.Wo + wo;
+      const long long o_cg = static_cast<long long>(Top) * oplane, m_cg = static_cast<long long>(a.To) * mplane;
+      for (int ti = 0; ti < r.ntiles; ++ti, ++tile_ctr, o_off += oplane, m_off += mplane) {
         const uint32_t acc = tile_ctr & 1u;
-        const int t = t0 + ti;
         // ReLU-mask source of the data gradient: issue the loads before waiting for the accumulators
         uint4 mk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
         if (a.mask && valid) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g)
-            if (2 * half + g < Cog)
-              mk[g] = __ldg(a.mask + ((static_cast<long long>(b) * Cog + 2 * half + g) * a.To + t) * mplane +
-                            static_cast<long long>(ho) * a.Wo + wo);
+          mk[0] = __ldg(a.mask + m_off);
+          if (2 * half + 1 < Cog) mk[1] = __ldg(a.mask + m_off + m_cg);
         }
-        const long long e0 = a.dbg ? clock64() : 0;
+        const long long e0 = DBG ? clock64() : 0;
         tc::mbar_wait(tfull + acc, (tile_ctr >> 1) & 1u);
         tc::tc_fence_after();
-        dbg_tfull += (a.dbg ? clock64() : 0) - e0;
+        const long long l0 = DBG ? clock64() : 0;
         float* xp = xch + (tile_ctr & 1u) * (2 * 4 * 96);
         uint32_t v0[16], v1[16], v2[16];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + (acc * 2u + rb) * N + 16 * half;
-        const long long l0 = a.dbg ? clock64() : 0;
         tc::tmem_ld_32x16(taddr, v0);
         tc::tmem_ld_32x16(taddr + CoP, v1);
         tc::tmem_ld_32x16(taddr + 2 * CoP, v2);
         tc::tmem_ld_wait();
-        dbg_ld += (a.dbg ? clock64() : 0) - l0;
         // all TMEM reads of this warp are done: release the accumulator as early as possible
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tempty + acc);
-        // publish this quadrant's first two rows of the kw=1 / kw=2 partial sums for the quadrant above
+        const long long l1 = DBG ? clock64() : 0;
+        // publish this quadrant's first two rows of the kw=1 / kw=2 partial sums for the quadrant above it
         if (lane < 2) {
-          float4* dst = reinterpret_cast<float4*>(xp + me * 96 + 16 * half);
+          uint4* dst = reinterpret_cast<uint4*>(xp + me * 96 + 16 * half);
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(v1[4 * c], v1[4 * c + 1], v1[4 * c + 2], v1[4 * c + 3]);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            dst[8 * (lane + 1) + c] = make_uint4(v2[4 * c], v2[4 * c + 1], v2[4 * c + 2], v2[4 * c + 3]);
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");  // the sixteen epilogue warps
+        const long long e2 = DBG ? clock64() : 0;
+        // patch lanes 0 / 1 with the first two rows of the next quadrant, then rotate-shuffle
+        if (lane < 2 && has_nb) {
+          const uint4* nsrc = reinterpret_cast<const uint4*>(xp + (me + 1) * 96 + 16 * half);
           if (lane == 0) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              dst[c] = make_float4(__uint_as_float(v1[4 * c]), __uint_as_float(v1[4 * c + 1]), __uint_as_float(v1[4 * c + 2]),
-                                   __uint_as_float(v1[4 * c + 3]));
-              dst[8 + c] = make_float4(__uint_as_float(v2[4 * c]), __uint_as_float(v2[4 * c + 1]),
-                                       __uint_as_float(v2[4 * c + 2]), __uint_as_float(v2[4 * c + 3]));
+              const uint4 t4 = nsrc[c];
+              v1[4 * c] = t4.x; v1[4 * c + 1] = t4.y; v1[4 * c + 2] = t4.z; v1[4 * c + 3] = t4.w;
             }
-          } else {
+          }
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              dst[16 + c] = make_float4(__uint_as_float(v2[4 * c]), __uint_as_float(v2[4 * c + 1]),
-                                        __uint_as_float(v2[4 * c + 2]), __uint_as_float(v2[4 * c + 3]));
+          for (int c = 0; c < 4; ++c) {
+            const uint4 t4 = nsrc[8 * (lane + 1) + c];
+            v2[4 * c] = t4.x; v2[4 * c + 1] = t4.y; v2[4 * c + 2] = t4.z; v2[4 * c + 3] = t4.w;
           }
         }
-        const long long e1 = a.dbg ? clock64() : 0;
-        asm volatile("bar.sync 1, 512;" ::: "memory");  // the sixteen epilogue warps
-        const long long e2 = a.dbg ? clock64() : 0;
-        dbg_bar += e2 - e1;
-        // neighbour rows for lanes 30 / 31 (other lanes read a harmless in-range address and ignore it)
-        const float4* n1 = reinterpret_cast<const float4*>(xp + (nb < 8 ? nb : me) * 96 + 16 * half);  // kw=1 row of lane 0
-        const float4* n2 = n1 + ((lane == 30) ? 8 : 16);  // lane 30: kw=2 row of lane 0; lane 31: kw=2 row of lane 1
+        __syncwarp();
         float o[16];
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 f1 = n1[c4];
-          const float4 f2 = n2[c4];
           const float4 fb = bias4[c4];
-          const float e1v[4] = {f1.x, f1.y, f1.z, f1.w};
-          const float e2v[4] = {f2.x, f2.y, f2.z, f2.w};
           const float eb[4] = {fb.x, fb.y, fb.z, fb.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c = 4 * c4 + j;
-            float s1 = __uint_as_float(v1[c]), s2 = __uint_as_float(v2[c]);
-            if (!(a.dbg_flags & 2)) {
-              s1 = __shfl_down_sync(0xffffffffu, s1, 1);
-              s2 = __shfl_down_sync(0xffffffffu, s2, 2);
-            }
-            s1 = (lane == 31) ? e1v[j] : s1;
-            s2 = (lane >= 30) ? e2v[j] : s2;
-            o[c] = (__uint_as_float(v0[c]) + s1) + (s2 + eb[j]);
+            const float s1 = __shfl_sync(0xffffffffu, __uint_as_float(v1[c]), src1);
+            const float s2 = __shfl_sync(0xffffffffu, __uint_as_float(v2[c]), src2);
+            float x = (__uint_as_float(v0[c]) + eb[j]) + (s1 + s2);
+            if (a.relu) x = fmaxf(x, 0.f);
+            o[c] = x;
           }
         }
         if (valid) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int cog = 2 * half + g;
-            if (cog >= Cog) continue;
+          for (int g2 = 0; g2 < 2; ++g2) {
+            if (2 * half + g2 >= Cog) continue;
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = o[g * 8 + j];
-              if (a.relu) x = (x < 0.f) ? 0.f : x;
-              f[j] = x;
-            }
+            for (int j = 0; j < 8; ++j) f[j] = o[g2 * 8 + j];
             if (a.mask) {
-              const uint32_t mw[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
+              const uint32_t mw[4] = {mk[g2].x, mk[g2].y, mk[g2].z, mk[g2].w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
@@ -358,19 +353,19 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
                 f[j] = (mv > 0.f) ? f[j] : 0.f;
               }
             }
-            uint4 ov = make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]),
-                                  tc::pack_bf16(f[6], f[7]));
-            if (!(a.dbg_flags & 1) || ov.x == 0x12345678u)
-              a.y[((static_cast<long long>(b) * Cog + cog) * Top + (t + a.out_pad)) * oplane +
-                  static_cast<long long>(ho + a.out_pad) * Wop + (wo + a.out_pad)] = ov;
+            a.y[o_off + g2 * o_cg] = make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]),
+                                                tc::pack_bf16(f[4], f[5]), tc::pack_bf16(f[6], f[7]));
           }
         }
-        dbg_rest += (a.dbg ? clock64() : 0) - e2;
+        if (DBG) { dbg_tfull += l0 - e0; dbg_ld += l1 - l0; dbg_bar += e2 - l1; dbg_rest += clock64() - e2; }
       }
+      g += r.ntiles;
     }
-    dbg_tfull_out = dbg_tfull; dbg_bar_out = dbg_bar; dbg_ld_out = dbg_ld; dbg_rest_out = dbg_rest;
+    if (DBG && a.dbg && threadIdx.x == 64) {
+      long long* d = a.dbg + blockIdx.x * 8;
+      d[5] = dbg_tfull; d[6] = dbg_bar; d[7] = dbg_ld; d[4] = -dbg_rest;
+    }
   }
-  if (a.dbg && threadIdx.x == 64) { a.dbg[blockIdx.x * 8 + 5] = dbg_tfull_out; a.dbg[blockIdx.x * 8 + 6] = dbg_bar_out; a.dbg[blockIdx.x * 8 + 7] = dbg_ld_out; a.dbg[blockIdx.x * 8 + 4] = -dbg_rest_out; }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
@@ -451,12 +446,7 @@ static int launch_igemm(const void* xb, const float* w, long long s_co, long lon
   a.tiles_q = ceil_div(Qtot, kIgTileOut);
   const int sms = sm_count();
   PVB_REQUIRE(sms > 0, "conv3d_bf16: no CUDA device");
-  // t-segments: long enough to amortise the 2 extra planes, short enough for >= ~8 units per CTA
-  int tseg = a.To;
-  while (tseg > 4 && static_cast<long long>(B) * a.tiles_q * ceil_div(a.To, tseg) < 8LL * sms) tseg = ceil_div(tseg, 2);
-  a.tseg = tseg;
-  a.nseg = ceil_div(a.To, tseg);
-  a.units = static_cast<long long>(B) * a.tiles_q * a.nseg;
+  a.tiles = static_cast<long long>(B) * a.tiles_q * a.To;
   const size_t need = igemm_ws_bytes(Ci, Co);
   if (!ws || ws_bytes < need) {
     set_error("conv3d_bf16: workspace too small (%zu < %zu bytes)", ws_bytes, need);
@@ -479,16 +469,19 @@ static int launch_igemm(const void* xb, const float* w, long long s_co, long lon
   PVB_REQUIRE(nslot >= 4, "conv3d_bf16: Cin=%d Cout=%d width=%d does not fit in shared memory", Ci, Co, Wi);
   a.nslot = static_cast<int>(nslot);
   a.dbg = g_igemm_dbg;
-  { const char* e = getenv("PVB200_IGEMM_DBG"); a.dbg_flags = e ? atoi(e) : 0; }
   const size_t smem = fixed + nslot * slot_bytes;
-  long long grid = a.units < sms ? a.units : sms;
-  if (a.Cg == 2) {
-    PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3d_igemm_bf16_kernel<2><<<static_cast<unsigned>(grid), kIgThreads, smem, stream>>>(a);
+  long long grid = a.tiles < sms ? a.tiles : sms;
+#define PVB_IG_LAUNCH(CG, DBG)                                                                                           \
+  do {                                                                                                                   \
+    PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_bf16_kernel<CG, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv3d_igemm_bf16_kernel<CG, DBG><<<static_cast<unsigned>(grid), kIgThreads, smem, stream>>>(a);                    \
+  } while (0)
+  if (a.dbg) {
+    if (a.Cg == 2) PVB_IG_LAUNCH(2, true); else PVB_IG_LAUNCH(4, true);
   } else {
-    PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_bf16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3d_igemm_bf16_kernel<4><<<static_cast<unsigned>(grid), kIgThreads, smem, stream>>>(a);
+    if (a.Cg == 2) PVB_IG_LAUNCH(2, false); else PVB_IG_LAUNCH(4, false);
   }
+#undef PVB_IG_LAUNCH
   PVB_LAUNCHED("conv3d_igemm_bf16");
   return PVB200_OK;
 }
