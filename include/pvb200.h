@@ -87,7 +87,10 @@ int pvb200_conv3d_dgrad_f32(const float* gz, const float* w, const float* mask_s
  *                       `pad` on every side of T,H,W (caller zero-fills the border once).
  *   conv3d_fwd_bf16   : yb = relu(conv(xb) + bias), written into the interior of an out_pad-padded blocked tensor.
  *   conv3d_dgrad_bf16 : gx = conv_transpose(gz) * (mask_src > 0); gz_padded is gz zero-padded by 2:
- *                       [B][Cg(Cout)][Ti+2][Hi+2][Wi+2][8]; mask_src (unpadded, [B][Cg(Cin)][Ti][Hi][Wi][8]) may be NULL. */
+ *                       [B][Cg(Cout)][Ti+2][Hi+2][Wi+2][8]; mask_src (unpadded, [B][Cg(Cin)][Ti][Hi][Wi][8]) may be NULL.
+ *                       gx_gzw (may be NULL): a second copy of gx in the weight-gradient operand layout of the layer
+ *                       BELOW ([B][Cg(Cin)][Ti][QP][8], pitch Wi + 2, caller zero-fills once), so gx is never re-laid out.
+ *   sat_normalise_blocked_bf16: int16 cube -> normalised blocked bf16 (a1 fused with the layout change). */
 int pvb200_blocked_channel_groups(int C);
 size_t pvb200_conv3d_bf16_workspace_bytes(int Cin, int Cout);
 int pvb200_nc_to_blocked_bf16(const float* x, uint16_t* y, int B, int C, int T, int H, int W, int pad,
@@ -97,9 +100,23 @@ int pvb200_conv3d_fwd_bf16(const uint16_t* xb, const float* w, const float* bias
                            void* workspace, size_t workspace_bytes,
                            int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int out_pad,
                            pvb200_stream_t stream);
+int pvb200_sat_normalise_blocked_bf16(const int16_t* x, uint16_t* yb, const float* mean, const float* std,
+                                      int B, int C, int T, int H, int W, pvb200_stream_t stream);
 int pvb200_conv3d_dgrad_bf16(const uint16_t* gz_padded, const float* w, const uint16_t* mask_src, uint16_t* gx,
-                             void* workspace, size_t workspace_bytes,
+                             uint16_t* gx_gzw, void* workspace, size_t workspace_bytes,
                              int B, int Cin, int Ti, int Hi, int Wi, int Cout, int out_pad,
+                             pvb200_stream_t stream);
+
+/* bf16 weight + bias gradient on the tensor cores.  gzw is the pre-activation gradient in blocked bf16 with the INPUT
+ * pitch: [B][Cg(Cout)][To][QP][8], position q = ho*Wi + wo, QP = pvb200_conv3d_wgrad_bf16_gz_plane(Hi, Wi) (zero in
+ * the wrap columns wo >= Wo and in the tail); pvb200_nc_to_gzw_bf16 builds it from [B][Cout][To][Ho][Wo] fp32. */
+long long pvb200_conv3d_wgrad_bf16_gz_plane(int Hi, int Wi);
+size_t pvb200_conv3d_wgrad_bf16_workspace_bytes(int Cin, int Cout);
+int pvb200_nc_to_gzw_bf16(const float* gz, uint16_t* gzw, int B, int Cout, int To, int Ho, int Wo,
+                          pvb200_stream_t stream);
+int pvb200_conv3d_wgrad_bf16(const uint16_t* xb, const uint16_t* gzw, float* dw, float* db,
+                             void* workspace, size_t workspace_bytes,
+                             int B, int Cin, int Ti, int Hi, int Wi, int Cout,
                              pvb200_stream_t stream);
 
 /* weight + bias gradient (autograd of model.py:117-120): dw[co,ci,kt,kh,kw] = sum gz * x(shifted),

@@ -37,6 +37,8 @@ struct IgemmArgs {
   const float* bias;  // [Co] or null
   const uint4* mask;  // [B][CogOut][To][Ho][Wo] or null
   uint4* y;           // [B][CogOut][To+2p][Ho+2p][Wo+2p]
+  uint4* y2;          // optional second copy in the wgrad operand layout [B][CogOut][To][QP2], pitch Wo + 2 (or null)
+  int QP2;
   int B, Cg, Ti, Hi, Wi;
   int CoP, Co, CogOut, To, Ho, Wo;  // CoP = Cout padded to 16/32; MMA N = 3*CoP (the three kw taps side by side)
   int out_pad, relu;
@@ -267,8 +269,11 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
                         static_cast<long long>(ho + a.out_pad) * Wop + (wo + a.out_pad);
       long long m_off = ((static_cast<long long>(r.b) * Cog + 2 * half) * a.To + r.t0) * mplane +
                         static_cast<long long>(ho) * a.Wo + wo;
+      long long o2_off = ((static_cast<long long>(r.b) * Cog + 2 * half) * a.To + r.t0) * a.QP2 +
+                         static_cast<long long>(ho) * (a.Wo + 2) + wo;
+      const long long o2_cg = static_cast<long long>(a.To) * a.QP2;
       const long long o_cg = static_cast<long long>(Top) * oplane, m_cg = static_cast<long long>(a.To) * mplane;
-      for (int ti = 0; ti < r.ntiles; ++ti, ++tile_ctr, o_off += oplane, m_off += mplane) {
+      for (int ti = 0; ti < r.ntiles; ++ti, ++tile_ctr, o_off += oplane, m_off += mplane, o2_off += a.QP2) {
         const uint32_t acc = tile_ctr & 1u;
         // ReLU-mask source of the data gradient: issue the loads before waiting for the accumulators
         uint4 mk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
@@ -353,8 +358,10 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
                 f[j] = (mv > 0.f) ? f[j] : 0.f;
               }
             }
-            a.y[o_off + g2 * o_cg] = make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]),
-                                                tc::pack_bf16(f[4], f[5]), tc::pack_bf16(f[6], f[7]));
+            const uint4 ov = make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]),
+                                        tc::pack_bf16(f[6], f[7]));
+            a.y[o_off + g2 * o_cg] = ov;
+            if (a.y2) a.y2[o2_off + g2 * o2_cg] = ov;
           }
         }
         if (DBG) { dbg_tfull += l0 - e0; dbg_ld += l1 - l0; dbg_bar += e2 - l1; dbg_rest += clock64() - e2; }
@@ -427,13 +434,14 @@ static size_t igemm_ws_bytes(int Ci_role, int Co_role) {
 }
 
 static int launch_igemm(const void* xb, const float* w, long long s_co, long long s_ci, int flip, const float* bias,
-                        const void* mask, void* yb, void* ws, size_t ws_bytes, int B, int Ci, int Ti, int Hi, int Wi, int Co,
+                        const void* mask, void* yb, void* yb2, void* ws, size_t ws_bytes, int B, int Ci, int Ti, int Hi, int Wi, int Co,
                         int out_pad, int relu, cudaStream_t stream) {
   IgemmArgs a;
   a.x = static_cast<const uint4*>(xb);
   a.bias = bias;
   a.mask = static_cast<const uint4*>(mask);
   a.y = static_cast<uint4*>(yb);
+  a.y2 = static_cast<uint4*>(yb2);
   a.B = B; a.Cg = igemm_cg(Ci); a.Ti = Ti; a.Hi = Hi; a.Wi = Wi;
   PVB_REQUIRE(Co <= 32, "conv3d_bf16: Cout=%d > 32 is not supported by the tensor-core path (use fp32 mode)", Co);
   a.CoP = igemm_cop(Co); a.Co = Co; a.CogOut = igemm_cg(Co);
@@ -441,6 +449,7 @@ static int launch_igemm(const void* xb, const float* w, long long s_co, long lon
   PVB_REQUIRE(a.To > 0 && a.Ho > 0 && a.Wo > 0, "conv3d_bf16: input %dx%dx%d too small", Ti, Hi, Wi);
   PVB_REQUIRE(a.Cg == 2 || a.Cg == 4, "conv3d_bf16: Cin=%d > 32 is not supported by the tensor-core path (use fp32 mode)", Ci);
   a.out_pad = out_pad; a.relu = relu;
+  a.QP2 = static_cast<int>(round_up(static_cast<long long>(a.Ho) * (a.Wo + 2), 128LL));
   a.NP = round_up(kIgTileM + 2 * Wi, 8);
   const int Qtot = (a.Ho - 1) * Wi + a.Wo;
   a.tiles_q = ceil_div(Qtot, kIgTileOut);
@@ -534,19 +543,19 @@ int pvb200_conv3d_fwd_bf16(const uint16_t* xb, const float* w, const float* bias
   using namespace pvb;
   PVB_REQUIRE(xb && w && yb, "conv3d_fwd_bf16: null pointer");
   PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && out_pad >= 0, "conv3d_fwd_bf16: bad shape");
-  return launch_igemm(xb, w, static_cast<long long>(Cin) * 27, 27, 0, bias, nullptr, yb, workspace, workspace_bytes, B, Cin,
+  return launch_igemm(xb, w, static_cast<long long>(Cin) * 27, 27, 0, bias, nullptr, yb, nullptr, workspace, workspace_bytes, B, Cin,
                       Ti, Hi, Wi, Cout, out_pad, relu, as_stream(stream));
 }
 
 int pvb200_conv3d_dgrad_bf16(const uint16_t* gz_padded, const float* w, const uint16_t* mask_src, uint16_t* gx,
-                             void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
+                             uint16_t* gx_gzw, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
                              int out_pad, pvb200_stream_t stream) {
   using namespace pvb;
   PVB_REQUIRE(gz_padded && w && gx, "conv3d_dgrad_bf16: null pointer");
   PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti > 2 && Hi > 2 && Wi > 2 && out_pad >= 0, "conv3d_dgrad_bf16: bad shape");
   // kernel input = gz zero-padded by 2: [B][Cg(Cout)][Ti+2][Hi+2][Wi+2]; kernel output = gx [B][Cg(Cin)][Ti][Hi][Wi]
   return launch_igemm(gz_padded, w, /*s_co (out role = ci)*/ 27, /*s_ci (in role = co)*/ static_cast<long long>(Cin) * 27, 1,
-                      nullptr, mask_src, gx, workspace, workspace_bytes, B, /*Ci role*/ Cout, Ti + 2, Hi + 2, Wi + 2,
+                      nullptr, mask_src, gx, gx_gzw, workspace, workspace_bytes, B, /*Ci role*/ Cout, Ti + 2, Hi + 2, Wi + 2,
                       /*Co role*/ Cin, out_pad, 0, as_stream(stream));
 }
 

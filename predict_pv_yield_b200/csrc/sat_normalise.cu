@@ -134,3 +134,44 @@ int pvb200_sat_normalise_bf16(const int16_t* x, uint16_t* y, const float* mean, 
 }
 
 }  // extern "C"
+
+// ---- int16 [B][C][T][H][W] -> normalised blocked bf16 [B][Cg][T][H][W][8] (bf16 tensor-core path input) ------------
+// Same two-rounding fp32 arithmetic, then RNE to bf16; channels >= C are zero.  One thread per (channel group,
+// position): 8 coalesced 2-byte loads (one per channel plane), one 16-byte store.
+namespace pvb {
+__global__ void __launch_bounds__(256)
+sat_normalise_blocked_kernel(const int16_t* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ mean,
+                             const float* __restrict__ stdv, int C, int Cg, long long thw, long long total) {
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pos = idx % thw;
+    const long long r = idx / thw;
+    const int cg = static_cast<int>(r % Cg);
+    const long long b = r / Cg;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      f[j] = (c < C) ? sat_norm(__ldg(x + (b * C + c) * thw + pos), __ldg(mean + c), __ldg(stdv + c)) : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+    y[idx] = o;
+  }
+}
+}  // namespace pvb
+
+extern "C" int pvb200_sat_normalise_blocked_bf16(const int16_t* x, uint16_t* yb, const float* mean, const float* std,
+                                                 int B, int C, int T, int H, int W, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(x && yb && mean && std && B > 0 && C > 0 && T > 0 && H > 0 && W > 0, "sat_normalise_blocked_bf16: bad argument");
+  const int Cg = 2 * ceil_div(C, 16);
+  const long long thw = static_cast<long long>(T) * H * W;
+  const long long total = static_cast<long long>(B) * Cg * thw;
+  long long grid = ceil_div(total, 256LL);
+  if (grid > 148 * 32) grid = 148 * 32;
+  sat_normalise_blocked_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<uint4*>(yb), mean,
+                                                                                            std, C, Cg, thw, total);
+  PVB_LAUNCHED("sat_normalise_blocked_bf16");
+  return PVB200_OK;
+}

@@ -59,8 +59,15 @@ SIGNATURES = {
     "pvb200_blocked_to_nc_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "pvb200_conv3d_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+    "pvb200_sat_normalise_blocked_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                                  c_int, c_void_p]),
+    "pvb200_conv3d_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_wgrad_bf16_gz_plane": (c_ll, [c_int, c_int]),
+    "pvb200_conv3d_wgrad_bf16_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "pvb200_nc_to_gzw_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pvb200_conv3d_wgrad_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

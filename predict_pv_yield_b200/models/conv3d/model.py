@@ -60,9 +60,12 @@ class Model(BaseModel):
         fc2_output_features: int = 128,
         fc3_output_features: int = 64,
         output_variable: str = "pv_yield",
+        precision: str = "fp32",
     ):
         """
-        3d conv model, that takes in different data streams (same arguments as the reference model).
+        3d conv model, that takes in different data streams (same arguments as the reference model, plus
+        ``precision``: "fp32" = exact-fp32 CUDA-core kernels (parity <= 1e-5), "bf16" = bf16 tensor-core
+        (tcgen05) convolutions with fp32 accumulation and fp32 master weights (parity <= 2e-2)).
 
         include_pv_yield: include pv yield history
         include_nwp: include nwp data
@@ -84,6 +87,9 @@ class Model(BaseModel):
         self.forecast_minutes = forecast_minutes
         self.history_minutes = history_minutes
         self.output_variable = output_variable
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
 
         super().__init__()
 
@@ -158,7 +164,8 @@ class Model(BaseModel):
         batch_size = sat_data.shape[0]
 
         # Conv3d + ReLU stack, flattened in NCDHW order (model.py:117-122)
-        out = ops.EncoderFn.apply(sat_data, mean, std, *self._conv_params())
+        encoder = ops.EncoderBf16Fn if self.precision == "bf16" else ops.EncoderFn
+        out = encoder.apply(sat_data, mean, std, *self._conv_params())
         if out.shape[1] != self.cnn_output_size:
             raise RuntimeError(
                 f"satellite cube {tuple(sat_data.shape)} gives {out.shape[1]} conv features, "

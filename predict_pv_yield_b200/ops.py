@@ -251,8 +251,10 @@ def conv3d_fwd_bf16(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]
     return yb
 
 
-def conv3d_dgrad_bf16(gz_padded: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Tensor], out_pad: int = 0) -> torch.Tensor:
-    """gx (blocked bf16, optionally written into a padded tensor) from gz zero-padded by 2 on T,H,W."""
+def conv3d_dgrad_bf16(gz_padded: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Tensor], out_pad: int = 0,
+                      also_gzw: bool = False):
+    """gx (blocked bf16, optionally written into a padded tensor) from gz zero-padded by 2 on T,H,W.
+    ``also_gzw``: additionally return gx in the weight-gradient operand layout of the layer below."""
     L = _lib.load()
     _need_cuda(gz_padded, "gz_padded", torch.bfloat16)
     _need_cuda(w, "conv weight", torch.float32)
@@ -268,14 +270,64 @@ def conv3d_dgrad_bf16(gz_padded: torch.Tensor, w: torch.Tensor, mask_src: Option
             raise RuntimeError("conv3d_dgrad_bf16: mask_src shape mismatch")
     alloc = torch.zeros if out_pad > 0 else torch.empty
     gx = alloc((B, Cgi, Ti + 2 * out_pad, Hi + 2 * out_pad, Wi + 2 * out_pad, 8), dtype=torch.bfloat16, device=gz_padded.device)
+    gzw = None
+    if also_gzw:
+        QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(Hi + 2, Wi + 2))
+        gzw = torch.zeros((B, Cgi, Ti, QP, 8), dtype=torch.bfloat16, device=gz_padded.device)
     ws = _workspace("conv_bf16", L.pvb200_conv3d_bf16_workspace_bytes(Ci, Co), gz_padded.device)
     npos = B * Ti * Hi * Wi
     with _timed(f"conv3d_dgrad_bf16[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
-                2.0 * (gz_padded.numel() + 8 * Cgi * npos * (2 if mask_src is not None else 1))):
-        rc = L.pvb200_conv3d_dgrad_bf16(_p(gz_padded), _p(w), _p(mask_src), _p(gx), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co,
-                                        out_pad, _stream())
+                2.0 * (gz_padded.numel() + 8 * Cgi * npos * ((2 if mask_src is not None else 1) + (1 if also_gzw else 0)))):
+        rc = L.pvb200_conv3d_dgrad_bf16(_p(gz_padded), _p(w), _p(mask_src), _p(gx), _p(gzw), _p(ws), ws.numel(), B, Ci, Ti, Hi,
+                                        Wi, Co, out_pad, _stream())
     _lib.check(rc, "conv3d_dgrad_bf16")
-    return gx
+    return (gx, gzw) if also_gzw else gx
+
+
+def sat_normalise_blocked_bf16(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor) -> torch.Tensor:
+    """int16 [B,C,T,H,W] -> normalised blocked bf16 [B,Cg,T,H,W,8] (a1 fused with the layout change)."""
+    L = _lib.load()
+    _need_cuda(x, "satellite.data", torch.int16)
+    _need_cuda(mean, "sat_mean", torch.float32)
+    _need_cuda(std, "sat_std", torch.float32)
+    B, Cc, T, H, W = x.shape
+    y = torch.empty((B, blocked_groups(Cc), T, H, W, 8), dtype=torch.bfloat16, device=x.device)
+    with _timed("sat_normalise_blocked_bf16", 0.0, 2.0 * x.numel() + 2.0 * y.numel()):
+        rc = L.pvb200_sat_normalise_blocked_bf16(_p(x), _p(y), _p(mean), _p(std), B, Cc, T, H, W, _stream())
+    _lib.check(rc, "sat_normalise_blocked_bf16")
+    return y
+
+
+def to_gzw_bf16(gz: torch.Tensor) -> torch.Tensor:
+    """[B,Co,To,Ho,Wo] fp32 -> the wgrad operand layout: blocked bf16 with the input pitch, [B,Cg,To,QP,8]."""
+    L = _lib.load()
+    _need_cuda(gz, "gz", torch.float32)
+    B, Co, To, Ho, Wo = gz.shape
+    QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(Ho + 2, Wo + 2))
+    out = torch.empty((B, blocked_groups(Co), To, QP, 8), dtype=torch.bfloat16, device=gz.device)
+    with _timed("nc_to_gzw_bf16", 0.0, 4.0 * gz.numel() + 2.0 * out.numel()):
+        rc = L.pvb200_nc_to_gzw_bf16(_p(gz), _p(out), B, Co, To, Ho, Wo, _stream())
+    _lib.check(rc, "nc_to_gzw_bf16")
+    return out
+
+
+def conv3d_wgrad_bf16(xb: torch.Tensor, gzw: torch.Tensor, Ci: int, Co: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(dw [Co,Ci,3,3,3], db [Co]) fp32 from blocked bf16 x [B,Cg,Ti,Hi,Wi,8] and gzw [B,Cg,To,QP,8]."""
+    L = _lib.load()
+    _need_cuda(xb, "xb", torch.bfloat16)
+    _need_cuda(gzw, "gzw", torch.bfloat16)
+    B, Cgx, Ti, Hi, Wi, e = xb.shape
+    QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(Hi, Wi))
+    if e != 8 or Cgx != blocked_groups(Ci) or tuple(gzw.shape) != (B, blocked_groups(Co), Ti - 2, QP, 8):
+        raise RuntimeError(f"conv3d_wgrad_bf16: shapes {tuple(xb.shape)} / {tuple(gzw.shape)} inconsistent")
+    dw = torch.empty((Co, Ci, 3, 3, 3), dtype=torch.float32, device=xb.device)
+    db = torch.empty((Co,), dtype=torch.float32, device=xb.device)
+    ws = _workspace("wgrad_bf16", L.pvb200_conv3d_wgrad_bf16_workspace_bytes(Ci, Co), xb.device)
+    npos = B * (Ti - 2) * (Hi - 2) * (Wi - 2)
+    with _timed(f"conv3d_wgrad_bf16[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 2.0 * (xb.numel() + gzw.numel())):
+        rc = L.pvb200_conv3d_wgrad_bf16(_p(xb), _p(gzw), _p(dw), _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, _stream())
+    _lib.check(rc, "conv3d_wgrad_bf16")
+    return dw, db
 
 
 def adam_step(params: List[torch.Tensor], grads: List[torch.Tensor], exp_avg: List[torch.Tensor],
@@ -336,6 +388,54 @@ class EncoderFn(torch.autograd.Function):
             grads[2 * l], grads[2 * l + 1] = dw, db
             if l > 0:
                 gz = conv3d_dgrad(gz, wb[2 * l], acts[l - 1], acts[l - 1].shape)
+        return (None, None, None, *grads)
+
+
+class EncoderBf16Fn(torch.autograd.Function):
+    """Conv3d stack in bf16 on the tensor cores (tcgen05 implicit GEMM), fp32 master weights.
+
+    forward(sat, mean, std, w0, b0, ...) -> features fp32 [B, cnn_output_size] in the reference's NCDHW flatten order.
+    Activations are kept blocked bf16 ([B,Cg,T,H,W,8]).  Same private protocol as ``EncoderFn``: the incoming gradient
+    already carries the ReLU mask of the last layer.  Backward, per layer: weight gradient (tensor cores, MN-major
+    operands) from the blocked input and the gradient in "gzw" layout; data gradient (same implicit-GEMM kernel on the
+    zero-padded gradient) writes the next gradient in BOTH layouts it is needed in, with the ReLU mask fused."""
+
+    @staticmethod
+    def forward(ctx, sat, mean, std, *wb):
+        n_layers = len(wb) // 2
+        if sat.dtype == torch.int16:
+            x = sat_normalise_blocked_bf16(sat, mean, std)
+        else:
+            x = to_blocked_bf16(sat)
+        acts = [x]
+        for l in range(n_layers):
+            x = conv3d_fwd_bf16(x, wb[2 * l], wb[2 * l + 1], relu=True)
+            acts.append(x)
+        ctx.save_for_backward(*wb, *acts)
+        ctx.n_layers = n_layers
+        ctx.channels = [wb[2 * l].shape[1] for l in range(n_layers)] + [wb[-2].shape[0]]
+        feats = from_blocked_bf16(acts[-1], ctx.channels[-1])
+        return feats.view(sat.shape[0], -1)
+
+    @staticmethod
+    def backward(ctx, g):
+        n = ctx.n_layers
+        saved = ctx.saved_tensors
+        wb, acts = saved[: 2 * n], saved[2 * n:]
+        ch = ctx.channels
+        B, _, To, Ho, Wo, _ = acts[-1].shape
+        g = g.contiguous().view(B, ch[-1], To, Ho, Wo)
+        gz_pad = to_blocked_bf16(g, pad=2) if n > 1 else None
+        gzw = to_gzw_bf16(g)
+        grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
+        for l in range(n - 1, -1, -1):
+            dw, db = conv3d_wgrad_bf16(acts[l], gzw, ch[l], ch[l + 1])
+            grads[2 * l], grads[2 * l + 1] = dw, db
+            if l > 0:
+                if l > 1:
+                    gz_pad, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=2, also_gzw=True)
+                else:  # the gradient w.r.t. layer 0's output only feeds layer 0's weight gradient
+                    _, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=0, also_gzw=True)
         return (None, None, None, *grads)
 
 
