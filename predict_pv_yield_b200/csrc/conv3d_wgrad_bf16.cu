@@ -49,9 +49,17 @@ __global__ void __launch_bounds__(kWbThreads, 1) conv3d_wgrad_bf16_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = (9u * a.N <= 256u) ? 256u : 512u;
 
-  // zero the stages once: clamped copies at plane ends leave tails untouched, and stale bits must stay finite
-  for (uint32_t i = threadIdx.x; i < (stage_bytes * a.nstage) / 16u; i += kWbThreads)
-    reinterpret_cast<uint4*>(stage_s)[i] = make_uint4(0, 0, 0, 0);
+  // initialise the stages once: clamped copies at plane ends leave tails untouched, and stale bits must stay finite.
+  // The never-loaded time plane p = 3 gets a constant 1.0 in its channel 0, so row 3*CiP of the (kh,kw) = (0,0)
+  // accumulator becomes sum(gz) = the BIAS gradient, for free.
+  {
+    const uint32_t per_stage16 = stage_bytes / 16u;
+    const uint32_t ones_lo = 3u * a.Cgx * a.NPOS, ones_hi = ones_lo + a.NPOS;  // 16-byte elements of plane (p=3, cg=0)
+    for (uint32_t i = threadIdx.x; i < per_stage16 * a.nstage; i += kWbThreads) {
+      const uint32_t e = i % per_stage16;
+      reinterpret_cast<uint4*>(stage_s)[i] = (e >= ones_lo && e < ones_hi) ? make_uint4(0x00003f80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
+    }
+  }
   tc::fence_proxy_async();
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWbMaxStages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
@@ -164,11 +172,20 @@ __global__ void __launch_bounds__(kWbThreads, 1) conv3d_wgrad_bf16_kernel(const 
   if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// dw[co][ci][kt][kh][kw] = sum_cta partial[cta][kh*3+kw][kt*CiP + ci][co]
-__global__ void wgrad_bf16_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Co, int Ci, int CiP,
-                                         int M, int N, int n_part) {
+// dw[co][ci][kt][kh][kw] = sum_cta partial[cta][kh*3+kw][kt*CiP + ci][co];  db[co] = sum_cta partial[cta][0][3*CiP][co]
+__global__ void wgrad_bf16_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
+                                         int Co, int Ci, int CiP, int M, int N, int n_part) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Co * Ci * 27) return;
+  if (idx >= Co * Ci * 27) {
+    const int co = idx - Co * Ci * 27;
+    if (db && co < Co) {
+      const long long off = static_cast<long long>(3 * CiP) * N + co, stride = 9LL * M * N;
+      float s = 0.f;
+      for (int p = 0; p < n_part; ++p) s += partial[p * stride + off];
+      db[co] = s;
+    }
+    return;
+  }
   const int tap = idx % 27;
   const int ci = (idx / 27) % Ci;
   const int co = idx / (27 * Ci);
@@ -178,38 +195,6 @@ __global__ void wgrad_bf16_reduce_kernel(const float* __restrict__ partial, floa
   float s = 0.f;
   for (int p = 0; p < n_part; ++p) s += partial[p * stride + off];
   dw[idx] = s;
-}
-
-// db[co] = sum over all positions of gzw (blocked bf16); one CTA per (channel group), deterministic tree
-__global__ void __launch_bounds__(256) bias_grad_blocked_kernel(const uint4* __restrict__ gzw, float* __restrict__ db, int B,
-                                                               int Cg, long long per_bc, int Co) {
-  __shared__ float red[8][8];
-  const int cg = blockIdx.x;
-  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int b = 0; b < B; ++b) {
-    const uint4* p = gzw + (static_cast<long long>(b) * Cg + cg) * per_bc;
-    for (long long i = threadIdx.x; i < per_bc; i += 256) {
-      const uint4 v = __ldg(p + i);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s[2 * j] += __uint_as_float(w[j] << 16);
-        s[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = warp_sum(s[j]);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0)
-    for (int j = 0; j < 8; ++j) red[warp][j] = s[j];
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    float t = 0.f;
-    for (int w2 = 0; w2 < 8; ++w2) t += red[w2][threadIdx.x];
-    const int co = cg * 8 + threadIdx.x;
-    if (co < Co) db[co] = t;
-  }
 }
 
 }  // namespace pvb
@@ -264,12 +249,9 @@ int pvb200_conv3d_wgrad_bf16(const uint16_t* xb, const uint16_t* gzw, float* dw,
   PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   conv3d_wgrad_bf16_kernel<<<static_cast<unsigned>(grid), kWbThreads, smem, st>>>(a);
   PVB_LAUNCHED("conv3d_wgrad_bf16");
-  wgrad_bf16_reduce_kernel<<<ceil_div(Cout * Cin * 27, 256), 256, 0, st>>>(a.partial, dw, Cout, Cin, 8 * a.Cgx, a.M, a.N, (int)grid);
+  wgrad_bf16_reduce_kernel<<<ceil_div(Cout * Cin * 27 + Cout, 256), 256, 0, st>>>(a.partial, dw, db, Cout, Cin, 8 * a.Cgx, a.M,
+                                                                                 a.N, (int)grid);
   PVB_LAUNCHED("wgrad_bf16_reduce");
-  if (db) {
-    bias_grad_blocked_kernel<<<a.Cgo, 256, 0, st>>>(a.gzw, db, B, a.Cgo, static_cast<long long>(a.To) * a.QP, Cout);
-    PVB_LAUNCHED("bias_grad_blocked");
-  }
   return PVB200_OK;
 }
 

@@ -69,6 +69,9 @@ def main():
                 gzp = ops.to_blocked_bf16(gz, pad=2)
                 ms = timeit(lambda: ops.conv3d_dgrad_bf16(gzp, w, xb), flush=flush)
                 print(f"conv{l} dgrad bf16{'':<18}{ms:9.3f}{flops / ms / 1e9:10.1f}")
+            gzw = ops.to_gzw_bf16(gz)
+            ms = timeit(lambda: ops.conv3d_wgrad_bf16(xb, gzw, Ci, Co), flush=flush)
+            print(f"conv{l} wgrad bf16{'':<18}{ms:9.3f}{flops / ms / 1e9:10.1f}")
             ms = timeit(lambda: ops.to_blocked_bf16(x), flush=flush)
             print(f"conv{l} to_blocked{'':<18}{ms:9.3f}{'':>10}{(4 * x.numel() + 2 * xb.numel()) / ms / 1e6:9.0f}")
 

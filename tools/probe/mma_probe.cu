@@ -14,7 +14,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 
 // layout: 0 none, 1 = 128B_base32B, 2 = 128B, 4 = 64B, 6 = 32B
 __global__ void probe(int layout, int N, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, int iters, int nacc,
-                      long long* out, int M = 128, int nissuers = 1, int always_overwrite = 0) {
+                      long long* out, int M = 128, int nissuers = 1, int always_overwrite = 0, int amaj = 0, int bmaj = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tptr;
@@ -28,7 +28,7 @@ __global__ void probe(int layout, int N, uint32_t a_lbo, uint32_t a_sbo, uint32_
   tc::tc_fence_after();
   const uint32_t tmem = tptr;
   if ((threadIdx.x & 31) == 0 && warp < nissuers) {
-    const uint32_t idesc = tc::umma_idesc(M, N, 1, 0, 0);
+    const uint32_t idesc = tc::umma_idesc(M, N, 1, amaj, bmaj);
     const uint32_t a_addr = tc::smem_u32(smem), b_addr = a_addr + 96 * 1024;
     uint64_t ad = tc::umma_desc(a_addr, a_lbo, a_sbo) | (static_cast<uint64_t>(layout) << 61);
     uint64_t bd = tc::umma_desc(b_addr, b_lbo, b_sbo) | (static_cast<uint64_t>(layout) << 61);
@@ -55,27 +55,25 @@ int main() {
   long long* out;
   cudaMalloc(&out, 148 * sizeof(long long));
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  struct Cfg { const char* name; int layout, N; uint32_t a_lbo, a_sbo, b_lbo, b_sbo; int nacc, M, nissuers, ow; };
+  struct Cfg { const char* name; int layout, N; uint32_t a_lbo, a_sbo, b_lbo, b_sbo; int nacc, M, nissuers, ow, amaj, bmaj; };
   Cfg cfgs[] = {
-      {"sw128 N=32 nacc1", 2, 32, 16, 1024, 16, 1024, 1, 128, 1, 0},
-      {"sw128 N=32 nacc4", 2, 32, 16, 1024, 16, 1024, 4, 128, 1, 0},
-      {"sw128 N=32 nacc8", 2, 32, 16, 1024, 16, 1024, 8, 128, 1, 0},
-      {"sw128 N=32 overwrite", 2, 32, 16, 1024, 16, 1024, 4, 128, 1, 1},
-      {"sw128 N=32 2 issuers", 2, 32, 16, 1024, 16, 1024, 2, 128, 2, 0},
-      {"sw128 N=32 4 issuers", 2, 32, 16, 1024, 16, 1024, 2, 128, 4, 0},
-      {"sw128 N=96 4 issuers", 2, 96, 16, 1024, 16, 1024, 1, 128, 4, 0},
-      {"sw128 N=32 M=64", 2, 32, 16, 1024, 16, 1024, 4, 64, 1, 0},
-      {"sw128 N=64 nacc4", 2, 64, 16, 1024, 16, 1024, 4, 128, 1, 0},
-      {"sw128 N=128 nacc2", 2, 128, 16, 1024, 16, 1024, 2, 128, 1, 0},
-      {"sw128 N=192 nacc2", 2, 192, 16, 1024, 16, 1024, 2, 128, 1, 0},
-      {"sw128 N=256 nacc2", 2, 256, 16, 1024, 16, 1024, 2, 128, 1, 0},
-      {"none  N=256 nacc2", 0, 256, 6144, 128, 4096, 128, 2, 128, 1, 0},
-      {"none  N=192 nacc2", 0, 192, 6144, 128, 3072, 128, 2, 128, 1, 0},
+      // name, layout, N, a_lbo, a_sbo, b_lbo, b_sbo, nacc, M, issuers, overwrite, amaj, bmaj
+      {"K/K   none  N=32", 0, 32, 6144, 128, 512, 128, 1, 128, 1, 0, 0, 0},
+      {"MN/MN none  N=32", 0, 32, 128, 4096, 128, 2048, 1, 128, 1, 0, 1, 1},
+      {"MN/K  none  N=32", 0, 32, 128, 4096, 512, 128, 1, 128, 1, 0, 1, 0},
+      {"K/MN  none  N=32", 0, 32, 6144, 128, 128, 2048, 1, 128, 1, 0, 0, 1},
+      {"MN/MN sw64  N=32", 4, 32, 8192, 512, 8192, 512, 1, 128, 1, 0, 1, 1},
+      {"MN/MN sw128 N=32", 2, 32, 8192, 1024, 8192, 1024, 1, 128, 1, 0, 1, 1},
+      {"MN/MN sw128 N=64", 2, 64, 8192, 1024, 8192, 1024, 1, 128, 1, 0, 1, 1},
+      {"MN/MN sw32  N=32", 6, 32, 8192, 256, 8192, 256, 1, 128, 1, 0, 1, 1},
+      {"MN/MN none  N=128", 0, 128, 128, 4096, 128, 2048, 1, 128, 1, 0, 1, 1},
+      {"MN/MN sw128 N=128", 2, 128, 8192, 1024, 8192, 1024, 1, 128, 1, 0, 1, 1},
+      {"MN/MN sw128 N=256", 2, 256, 8192, 1024, 8192, 1024, 1, 128, 1, 0, 1, 1},
   };
   const int iters = 2000;
   for (auto& c : cfgs) {
     const int grid = 148;
-    probe<<<grid, 128, 160 * 1024>>>(c.layout, c.N, c.a_lbo, c.a_sbo, c.b_lbo, c.b_sbo, iters, c.nacc, out, c.M, c.nissuers, c.ow);
+    probe<<<grid, 128, 160 * 1024>>>(c.layout, c.N, c.a_lbo, c.a_sbo, c.b_lbo, c.b_sbo, iters, c.nacc, out, c.M, c.nissuers, c.ow, c.amaj, c.bmaj);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: CUDA error %s\n", c.name, cudaGetErrorString(e)); return 1; }
     long long h[148];
