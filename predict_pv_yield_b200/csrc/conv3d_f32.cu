@@ -10,10 +10,11 @@
 //     Wps = round_up(Wi + 2P, 4).  A tile is 512 consecutive q, so the input window a tile needs
 //     for tap (kh,kw) is simply the contiguous run [q0 + kh*Wps + kw, ... + 512): no im2col, no
 //     per-row halo logic.  Columns wo >= Wo are computed and discarded (<= 6 % waste).
-//   * input channels are consumed 8 at a time: 8 x 3 (kt) planes of 512 + 2*Wps + 8 floats are staged
-//     in shared memory (coalesced loads; zero fill implements the padding of the data gradient,
-//     and the int16 normalisation of layer 0 is fused here), with the matching [8][27][32]
-//     weight slab (pre-transposed once per call so the copy is contiguous).
+//   * input channels are consumed 4 at a time through a 2-stage cp.async pipeline: 4 x 3 (kt) planes of
+//     512 + 2*Wps + 8 floats are copied global->shared without registers while the previous chunk is in
+//     the FMA loop (zero fill implements the padding of the data gradient; the int16 normalisation of
+//     layer 0 is fused into a synchronous staging path), with the matching [4][27][32] weight slab
+//     (pre-transposed once per call so the copy is contiguous).
 //   * 256 threads = 64 position-threads x 4 channel groups; each thread owns 2 x 4 positions
 //     x 8 output channels = 64 accumulators and performs 192 FMAs per (ci,kt,kh) from
 //     4 x LDS.128 of input (conflict-free: 16 B lane stride) + 6 x LDS.128 of weights (warp
@@ -26,7 +27,7 @@ namespace pvb {
 
 constexpr int kQT = 512;       // output positions per CTA tile
 constexpr int kCoT = 32;       // output channels per CTA tile
-constexpr int kCC = 8;         // input channels per shared-memory chunk
+constexpr int kCC = 4;         // input channels per shared-memory chunk (double-buffered)
 constexpr int kConvThreads = 256;
 
 struct ConvArgs {
@@ -65,9 +66,9 @@ __global__ void conv_weight_prep_kernel(const float* __restrict__ w, float* __re
 template <bool kI16>
 __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(const ConvArgs a) {
   extern __shared__ __align__(16) float smem[];
-  float* in_s = smem;                                  // [kCC][3][NP]
-  float* w_s = smem + kCC * 3 * a.NP;                  // [kCC][27][32]
-  int* off_s = reinterpret_cast<int*>(w_s + kCC * 27 * kCoT);  // [NP] offset inside an input plane, or -1
+  float* in_s = smem;                                  // [2][kCC][3][NP]
+  float* w_s = smem + 2 * kCC * 3 * a.NP;              // [2][kCC][27][32]
+  int* off_s = reinterpret_cast<int*>(w_s + 2 * kCC * 27 * kCoT);  // [NP] offset inside an input plane, or -1
 
   const int tid = threadIdx.x;
   const int tp = tid & 63;   // position thread: positions {4tp..4tp+3} and {256+4tp..256+4tp+3}
@@ -100,53 +101,61 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
   const long long plane_sz = static_cast<long long>(a.Hi) * a.Wi;
   const int warp = tid >> 5, lane = tid & 31;
 
-  for (int c0 = 0; c0 < a.Ci; c0 += kCC) {
-    __syncthreads();  // previous chunk fully consumed (and off_s visible on the first pass)
-    // ---- stage input: (c,kt) planes round-robin over warps, lanes stride over positions ----
+  // ---- staging of one chunk of kCC input channels (+ its weight slab) into buffer `buf` ----
+  // fp32 inputs go through cp.async (LDGSTS: global -> shared without registers, zero-fill for the padding), so the
+  // NEXT chunk streams in while the FMA loop runs on the current one; int16 inputs are converted on the fly
+  // (normalisation fused) and therefore staged synchronously.
+  auto stage = [&](int c0, int buf) {
+    float* in_b = in_s + buf * (kCC * 3 * a.NP);
+    float* w_b = w_s + buf * (kCC * 27 * kCoT);
     for (int pl = warp; pl < kCC * 3; pl += kConvThreads / 32) {
       const int c = pl / 3, kt = pl - c * 3;
       const int ci = c0 + c;
       const int ti = to + kt - a.P;
-      float* dst = in_s + pl * a.NP;
+      float* dst = in_b + pl * a.NP;
       const bool plane_ok = (ci < a.Ci) && (ti >= 0) && (ti < a.Ti);
-      if (plane_ok) {
-        const long long base = ((static_cast<long long>(b) * a.Ci + ci) * a.Ti + ti) * plane_sz;
-        if (kI16) {
-          const int16_t* src = static_cast<const int16_t*>(a.x) + base;
-          const float m = __ldg(a.mean + ci), s = __ldg(a.stdv + ci);
-          for (int i = lane; i < a.NP; i += 32) {
-            const int o = off_s[i];
-            dst[i] = (o >= 0) ? sat_norm(__ldg(src + o), m, s) : 0.f;
-          }
-        } else {
-          const float* src = static_cast<const float*>(a.x) + base;
-          for (int i = lane; i < a.NP; i += 32) {
-            const int o = off_s[i];
-            dst[i] = (o >= 0) ? __ldg(src + o) : 0.f;
-          }
+      const long long base = plane_ok ? ((static_cast<long long>(b) * a.Ci + ci) * a.Ti + ti) * plane_sz : 0;
+      if (kI16) {
+        const int16_t* src = static_cast<const int16_t*>(a.x) + base;
+        const float m = plane_ok ? __ldg(a.mean + ci) : 0.f, s = plane_ok ? __ldg(a.stdv + ci) : 1.f;
+        for (int i = lane; i < a.NP; i += 32) {
+          const int o = off_s[i];
+          dst[i] = (plane_ok && o >= 0) ? sat_norm(__ldg(src + o), m, s) : 0.f;
         }
       } else {
-        for (int i = lane; i < a.NP; i += 32) dst[i] = 0.f;
+        const float* src = static_cast<const float*>(a.x) + base;
+        const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+        for (int i = lane; i < a.NP; i += 32) {
+          const int o = off_s[i];
+          const bool ok = plane_ok && (o >= 0);
+          // src-size 0 => 4 bytes of zeros are written (the implicit padding); the source pointer stays in range
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? o : 0)),
+                       "r"(ok ? 4 : 0)
+                       : "memory");
+        }
       }
     }
-    // ---- stage weights: contiguous [kCC][27][32] slab out of wt[Ci][27][CoPad] ----
-    for (int idx = tid; idx < kCC * 27 * kCoT; idx += kConvThreads) {
-      const int co = idx & (kCoT - 1);
-      const int r = idx >> 5;  // c*27 + tap
+    // weights: contiguous [kCC][27][32] slab out of wt[Ci][27][CoPad], 16 bytes per copy
+    const uint32_t w0 = static_cast<uint32_t>(__cvta_generic_to_shared(w_b));
+    for (int idx = tid; idx < kCC * 27 * kCoT / 4; idx += kConvThreads) {
+      const int co4 = idx & (kCoT / 4 - 1);
+      const int r = idx >> 3;  // c*27 + tap
       const int c = r / 27;
-      float v = 0.f;
-      if (c0 + c < a.Ci) v = __ldg(a.wt + (static_cast<long long>(c0) * 27 + r) * a.CoPad + co0 + co);
-      w_s[idx] = v;
+      const bool ok = (c0 + c) < a.Ci;
+      const float* src = a.wt + (static_cast<long long>(ok ? c0 : 0) * 27 + (ok ? r : 0)) * a.CoPad + co0 + 4 * co4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(w0 + 16u * idx), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 
-    // ---- compute ----
-    const int cmax = min(kCC, a.Ci - c0);
+  auto compute = [&](int buf, int cmax) {
+    const float* in_b = in_s + buf * (kCC * 3 * a.NP);
+    const float* w_b = w_s + buf * (kCC * 27 * kCoT);
     for (int c = 0; c < cmax; ++c) {
 #pragma unroll 1
       for (int kt = 0; kt < 3; ++kt) {
-        const float* ip = in_s + (c * 3 + kt) * a.NP + 4 * tp;
-        const float* wp = w_s + (c * 27 + kt * 9) * kCoT + 8 * cg;
+        const float* ip = in_b + (c * 3 + kt) * a.NP + 4 * tp;
+        const float* wp = w_b + (c * 27 + kt * 9) * kCoT + 8 * cg;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
           float in[2][8];
@@ -177,6 +186,22 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
         }
       }
     }
+  };
+
+  // ---- main loop: 2-stage software pipeline over chunks of kCC input channels ----
+  const int nchunk = (a.Ci + kCC - 1) / kCC;
+  __syncthreads();  // off_s visible
+  stage(0, 0);
+  for (int k = 0; k < nchunk; ++k) {
+    if (k + 1 < nchunk) {
+      stage((k + 1) * kCC, (k + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // chunk k landed for every thread
+    compute(k & 1, min(kCC, a.Ci - k * kCC));
+    __syncthreads();  // buffer k&1 may be overwritten by the stage issued in the next iteration
   }
 
   // ---- epilogue ----
@@ -240,7 +265,7 @@ static int launch_conv(const void* x, bool i16, const float* mean, const float* 
     conv_weight_prep_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, wt, Ci, Co, a.CoPad, s_co, s_ci, flip);
     PVB_LAUNCHED("conv_weight_prep");
   }
-  const size_t smem = (static_cast<size_t>(kCC) * 3 * a.NP + kCC * 27 * kCoT) * sizeof(float) + a.NP * sizeof(int);
+  const size_t smem = 2 * (static_cast<size_t>(kCC) * 3 * a.NP + kCC * 27 * kCoT) * sizeof(float) + a.NP * sizeof(int);
   PVB_REQUIRE(smem <= 227 * 1024, "conv3d: image width %d needs %zu B of shared memory (> 227 KB)", Wi, smem);
   const long long tiles = static_cast<long long>(B) * a.To * a.tiles_per_plane * a.co_tiles;
   PVB_REQUIRE(tiles <= 0x7fffffffLL, "conv3d: too many tiles");

@@ -13,7 +13,7 @@
 
 namespace pvb {
 
-constexpr int kWgQC = 128;        // output positions staged per chunk
+constexpr int kWgQC = 64;         // output positions staged per step
 constexpr int kWgMaxCtas = 320;   // upper bound on persistent CTAs (workspace sizing)
 constexpr int kWgMaxCi = 64;
 
@@ -25,22 +25,26 @@ struct WgradArgs {
   float* partial;     // [gridDim.x][Co*Ci*27 + Co]
   int B, Ci, Ti, Hi, Wi, Co, To, Ho, Wo;
   int Wps, NP, NPs;   // pitch, staged positions per plane, padded plane stride (NPs % 8 == 4)
-  int chunks_per_plane;
-  long long total_chunks;
+  int tiles_per_plane;
+  long long total_steps;  // B * tiles_per_plane * To
   int ncog;           // ceil(Co / 4)
   int items;          // ncog * Ci * KTS
 };
 
+// Work is ordered (b, tile, to) with `to` fastest: a CTA walks DOWN the time axis of one (sample, position tile)
+// column, so consecutive steps share two of their three input planes.  Planes live in a 4-slot ring filled by
+// cp.async (LDGSTS, zero-fill for out-of-range positions) one step ahead of the FMA loop.
 template <bool kI16, int KTS>
 __global__ void __launch_bounds__(KTS == 1 ? 256 : 384, 1) conv3d_wgrad_f32_kernel(const WgradArgs a) {
   constexpr int NKT = 3 / KTS;  // kt values handled by one thread
   extern __shared__ __align__(16) float smem[];
-  float* x_s = smem;                                        // [3][Ci][NPs]
-  float* gz_s = x_s + 3 * a.Ci * a.NPs;                     // [4*ncog][kWgQC]
-  int* off_s = reinterpret_cast<int*>(gz_s + 4 * a.ncog * kWgQC);  // [NP] input-plane offsets
+  float* x_s = smem;                                        // [4 slots][Ci][NPs]
+  float* gz_s = x_s + 4 * a.Ci * a.NPs;                     // [2][4*ncog][kWgQC]
+  int* off_s = reinterpret_cast<int*>(gz_s + 2 * 4 * a.ncog * kWgQC);  // [NP] input-plane offsets
   int* goff_s = off_s + a.NP;                               // [kWgQC] gz-plane offsets
 
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
   const int item = blockIdx.y * blockDim.x + tid;
   const bool active = item < a.items;
   int ci = 0, cog = 0, ktg = 0;
@@ -58,106 +62,133 @@ __global__ void __launch_bounds__(KTS == 1 ? 256 : 384, 1) conv3d_wgrad_f32_kern
     for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
   float bacc[4] = {0.f, 0.f, 0.f, 0.f};
 
-  // contiguous chunk range of this CTA
-  const long long c_begin = a.total_chunks * blockIdx.x / gridDim.x;
-  const long long c_end = a.total_chunks * (blockIdx.x + 1) / gridDim.x;
+  const long long g_begin = a.total_steps * blockIdx.x / gridDim.x;
+  const long long g_end = a.total_steps * (blockIdx.x + 1) / gridDim.x;
   const long long xplane = static_cast<long long>(a.Hi) * a.Wi;
   const long long gplane = static_cast<long long>(a.Ho) * a.Wo;
-  int cur_tile = -1;
 
-  for (long long ch = c_begin; ch < c_end; ++ch) {
-    const int tile = static_cast<int>(ch % a.chunks_per_plane);
-    const long long pl = ch / a.chunks_per_plane;
-    const int to = static_cast<int>(pl % a.To);
-    const int b = static_cast<int>(pl / a.To);
+  // stage input time plane `ti` of sample b (all Ci channels) into ring slot `slot`
+  auto stage_x = [&](int b, int ti, int slot) {
+    for (int c = warp; c < a.Ci; c += nwarp) {
+      float* dst = x_s + (slot * a.Ci + c) * a.NPs;
+      const long long base = ((static_cast<long long>(b) * a.Ci + c) * a.Ti + ti) * xplane;
+      if (kI16) {
+        const int16_t* src = static_cast<const int16_t*>(a.x) + base;
+        const float m = __ldg(a.mean + c), s = __ldg(a.stdv + c);
+        for (int i = lane; i < a.NP; i += 32) {
+          const int o = off_s[i];
+          dst[i] = (o >= 0) ? sat_norm(__ldg(src + o), m, s) : 0.f;
+        }
+      } else {
+        const float* src = static_cast<const float*>(a.x) + base;
+        const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+        for (int i = lane; i < a.NP; i += 32) {
+          const int o = off_s[i];
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * i), "l"(src + (o >= 0 ? o : 0)),
+                       "r"(o >= 0 ? 4 : 0)
+                       : "memory");
+        }
+      }
+    }
+  };
+  // stage gz of output time `to` into buffer `buf`: [co][q], zero at the wrap columns / beyond the plane
+  auto stage_gz = [&](int b, int to, int buf) {
+    for (int p = warp; p < 4 * a.ncog; p += nwarp) {
+      float* dst = gz_s + (buf * 4 * a.ncog + p) * kWgQC;
+      const bool ok_p = p < a.Co;
+      const float* src = a.gz + ((static_cast<long long>(b) * a.Co + (ok_p ? p : 0)) * a.To + to) * gplane;
+      const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+      for (int i = lane; i < kWgQC; i += 32) {
+        const int o = goff_s[i];
+        const bool ok = ok_p && (o >= 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? o : 0)),
+                     "r"(ok ? 4 : 0)
+                     : "memory");
+      }
+    }
+  };
+
+  for (long long g = g_begin; g < g_end;) {
+    // ---- a run: consecutive output times of one (b, tile) column ----
+    const long long col = g / a.To;
+    const int t0 = static_cast<int>(g - col * a.To);
+    const int tile = static_cast<int>(col % a.tiles_per_plane);
+    const int b = static_cast<int>(col / a.tiles_per_plane);
+    const long long left = g_end - g;
+    const int nstep = static_cast<int>(left < (a.To - t0) ? left : (a.To - t0));
     const int q0 = tile * kWgQC;
 
-    __syncthreads();  // previous chunk consumed
-    if (tile != cur_tile) {  // offset tables depend only on the tile index (block-uniform branch)
-      for (int i = tid; i < a.NP; i += blockDim.x) {
-        const int pos = q0 + i;
-        const int hp = pos / a.Wps, wp = pos - hp * a.Wps;
-        off_s[i] = (hp < a.Hi && wp < a.Wi) ? hp * a.Wi + wp : -1;
-      }
-      for (int i = tid; i < kWgQC; i += blockDim.x) {
-        const int pos = q0 + i;
-        const int ho = pos / a.Wps, wo = pos - ho * a.Wps;
-        goff_s[i] = (ho < a.Ho && wo < a.Wo) ? ho * a.Wo + wo : -1;
-      }
-      cur_tile = tile;
-      __syncthreads();
+    __syncthreads();  // previous run fully consumed
+    for (int i = tid; i < a.NP; i += blockDim.x) {
+      const int pos = q0 + i;
+      const int hp = pos / a.Wps, wp = pos - hp * a.Wps;
+      off_s[i] = (hp < a.Hi && wp < a.Wi) ? hp * a.Wi + wp : -1;
     }
-    // ---- stage x: 3*Ci planes round-robin over warps ----
-    {
-      const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
-      for (int p = warp; p < 3 * a.Ci; p += nwarp) {
-        const int kt = p / a.Ci, c = p - kt * a.Ci;
-        float* dst = x_s + p * a.NPs;
-        const long long base = ((static_cast<long long>(b) * a.Ci + c) * a.Ti + (to + kt)) * xplane;
-        if (kI16) {
-          const int16_t* src = static_cast<const int16_t*>(a.x) + base;
-          const float m = __ldg(a.mean + c), s = __ldg(a.stdv + c);
-          for (int i = lane; i < a.NP; i += 32) {
-            const int o = off_s[i];
-            dst[i] = (o >= 0) ? sat_norm(__ldg(src + o), m, s) : 0.f;
-          }
-        } else {
-          const float* src = static_cast<const float*>(a.x) + base;
-          for (int i = lane; i < a.NP; i += 32) {
-            const int o = off_s[i];
-            dst[i] = (o >= 0) ? __ldg(src + o) : 0.f;
-          }
-        }
-      }
-      // ---- stage gz: [co][q] ----
-      for (int p = warp; p < 4 * a.ncog; p += nwarp) {
-        float* dst = gz_s + p * kWgQC;
-        if (p < a.Co) {
-          const float* src = a.gz + ((static_cast<long long>(b) * a.Co + p) * a.To + to) * gplane;
-          for (int i = lane; i < kWgQC; i += 32) {
-            const int o = goff_s[i];
-            dst[i] = (o >= 0) ? __ldg(src + o) : 0.f;
-          }
-        } else {
-          for (int i = lane; i < kWgQC; i += 32) dst[i] = 0.f;
-        }
-      }
+    for (int i = tid; i < kWgQC; i += blockDim.x) {
+      const int pos = q0 + i;
+      const int ho = pos / a.Wps, wo = pos - ho * a.Wps;
+      goff_s[i] = (ho < a.Ho && wo < a.Wo) ? ho * a.Wo + wo : -1;
     }
     __syncthreads();
+    // prologue: the three planes of the first step + its gz
+    stage_x(b, t0, 0);
+    stage_x(b, t0 + 1, 1);
+    stage_x(b, t0 + 2, 2);
+    stage_gz(b, t0, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
-    if (active) {
-      const float* gp = gz_s + (4 * cog) * kWgQC;
-#pragma unroll 1
-      for (int q = 0; q < kWgQC; q += 4) {
-        float g[4][4];  // [co j][pos i]
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(gp + j * kWgQC + q);
-          g[j][0] = v.x; g[j][1] = v.y; g[j][2] = v.z; g[j][3] = v.w;
-          bacc[j] += (v.x + v.y) + (v.z + v.w);
-        }
+    for (int s = 0; s < nstep; ++s) {
+      if (s + 1 < nstep) {  // prefetch the one new plane of the next step, and its gz
+        stage_x(b, t0 + s + 3, (s + 3) & 3);
+        stage_gz(b, t0 + s + 1, (s + 1) & 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+
+      if (active) {
+        const float* gp = gz_s + ((s & 1) * 4 * a.ncog + 4 * cog) * kWgQC;
+        const float* xk[NKT];
 #pragma unroll
         for (int k = 0; k < NKT; ++k) {
           const int kt = (KTS == 1) ? k : ktg;
-          const float* xp = x_s + (kt * a.Ci + ci) * a.NPs + q;
+          xk[k] = x_s + (((s + kt) & 3) * a.Ci + ci) * a.NPs;
+        }
+#pragma unroll 1
+        for (int q = 0; q < kWgQC; q += 4) {
+          float gv[4][4];  // [co j][pos i]
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const float4 v0 = *reinterpret_cast<const float4*>(xp + kh * a.Wps);
-            const float2 v1 = *reinterpret_cast<const float2*>(xp + kh * a.Wps + 4);
-            const float xv[6] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y};
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(gp + j * kWgQC + q);
+            gv[j][0] = v.x; gv[j][1] = v.y; gv[j][2] = v.z; gv[j][3] = v.w;
+            bacc[j] += (v.x + v.y) + (v.z + v.w);
+          }
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
+          for (int k = 0; k < NKT; ++k) {
+            const float* xp = xk[k] + q;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+            for (int kh = 0; kh < 3; ++kh) {
+              const float4 v0 = *reinterpret_cast<const float4*>(xp + kh * a.Wps);
+              const float2 v1 = *reinterpret_cast<const float2*>(xp + kh * a.Wps + 4);
+              const float xv[6] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  acc[k * 9 + kh * 3 + kw][j] = fmaf(g[j][i], xv[i + kw], acc[k * 9 + kh * 3 + kw][j]);
+              for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    acc[k * 9 + kh * 3 + kw][j] = fmaf(gv[j][i], xv[i + kw], acc[k * 9 + kh * 3 + kw][j]);
+                }
               }
             }
           }
         }
       }
+      __syncthreads();  // slot (s & 3) and gz buffer (s & 1) may be overwritten by the next prefetch
     }
+    g += nstep;
   }
 
   // ---- write this CTA's partial ----
@@ -228,8 +259,8 @@ int pvb200_conv3d_wgrad_f32(const void* x, int x_is_i16, const float* mean, cons
   a.NP = kWgQC + 2 * a.Wps + 8;
   a.NPs = round_up(a.NP, 8) + 4;
   const int Qtot = (a.Ho - 1) * a.Wps + a.Wo;
-  a.chunks_per_plane = ceil_div(Qtot, kWgQC);
-  a.total_chunks = static_cast<long long>(B) * a.To * a.chunks_per_plane;
+  a.tiles_per_plane = ceil_div(Qtot, kWgQC);
+  a.total_steps = static_cast<long long>(B) * a.tiles_per_plane * a.To;
   a.ncog = ceil_div(Cout, 4);
   // narrow layers (conv0: Cin = 12) split the 27 taps over 3 threads to keep the CTA full
   const int kts = (a.ncog * Cin <= 128) ? 3 : 1;
@@ -241,8 +272,8 @@ int pvb200_conv3d_wgrad_f32(const void* x, int x_is_i16, const float* mean, cons
   PVB_REQUIRE(sms > 0, "conv3d_wgrad: no CUDA device");
   long long gx = sms;  // one persistent CTA per SM (register- and smem-limited to 1 CTA/SM)
   if (gx > kWgMaxCtas) gx = kWgMaxCtas;
-  if (gx > a.total_chunks) gx = a.total_chunks;
-  const size_t smem = (static_cast<size_t>(3) * Cin * a.NPs + 4 * a.ncog * kWgQC) * sizeof(float) +
+  if (gx > a.total_steps) gx = a.total_steps;
+  const size_t smem = (static_cast<size_t>(4) * Cin * a.NPs + 2 * 4 * a.ncog * kWgQC) * sizeof(float) +
                       (a.NP + kWgQC) * sizeof(int);
   PVB_REQUIRE(smem <= 227 * 1024, "conv3d_wgrad: Cin=%d, width %d needs %zu B of shared memory (> 227 KB)", Cin, Wi, smem);
   cudaStream_t st = as_stream(stream);
