@@ -86,7 +86,8 @@ class GradientExchange:
         else:
             self._wait_all()
         self._small = []
-        self.bytes_reduced_last_step, self._bytes = self._bytes, 0
+        if self._bytes:
+            self.bytes_reduced_last_step, self._bytes = self._bytes, 0
 
     def _wait_all(self) -> None:
         for work, ev in self._pending:

@@ -1,0 +1,93 @@
+"""CPU, world_size 2, gloo: host logic of the data-parallel gradient exchange (predict_pv_yield_b200/dp.py).
+
+The exchange is tensor-agnostic (it hooks ``p.grad``), so a small torch model on CPU exercises exactly the code
+that runs under NCCL: the immediate in-place all-reduce of "large" gradients, the packed bucket of small ones,
+``finish()`` ordering, the optimizer wiring and the packed logged-scalar reduction.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from predict_pv_yield_b200.dp import GradientExchange, reduce_logged_scalars
+
+        torch.manual_seed(0)  # identical replicas
+        model = torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.ReLU(), torch.nn.Linear(128, 3))
+        ex = GradientExchange(model, large_numel=4096)  # first weight (8192 el) is "large", the rest go in the bucket
+        opt = torch.optim.SGD(model.parameters(), lr=0.1)
+        ex.attach_optimizer(opt)
+        g = torch.Generator().manual_seed(100 + rank)  # different shard per rank
+        x = torch.randn(8, 64, generator=g)
+        y = torch.randn(8, 3, generator=g)
+        before = [p.detach().clone() for p in model.parameters()]
+        loss = ((model(x) - y) ** 2).mean()
+        loss.backward()
+        local = [p.grad.detach().clone() for p in model.parameters()]
+        ex.finish()
+        summed = [p.grad.detach().clone() for p in model.parameters()]
+        # reference: explicit all-reduce of the local gradients
+        want = []
+        for t in local:
+            t = t.clone()
+            dist.all_reduce(t)
+            want.append(t)
+        ok_sum = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(summed, want))
+        # a second finish() is a no-op; the optimizer hook averages and steps
+        opt.step()
+        after = [p.detach().clone() for p in model.parameters()]
+        ok_step = all(torch.allclose(a, b0 - 0.1 * w / world, atol=1e-6) for a, b0, w in zip(after, before, want))
+        # replicas stay identical
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        other = flat.clone()
+        dist.broadcast(other, src=0)
+        ok_same = torch.allclose(flat, other)
+        red = reduce_logged_scalars({"MSE/Train": torch.tensor(float(rank + 1)), "NMAE/Train": torch.tensor(2.0 * rank)})
+        ok_log = abs(float(red["MSE/Train"]) - 1.5) < 1e-6 and abs(float(red["NMAE/Train"]) - 1.0) < 1e-6
+        q.put((rank, ok_sum, ok_step, ok_same, ok_log, ex.bytes_reduced_last_step))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_exchange_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_sum, ok_step, ok_same, ok_log, nbytes in res:
+        assert ok_sum, f"rank {rank}: summed gradients differ from an explicit all-reduce"
+        assert ok_step, f"rank {rank}: optimizer step did not use the averaged gradient"
+        assert ok_same, f"rank {rank}: replicas diverged"
+        assert ok_log, f"rank {rank}: logged-scalar reduction wrong"
+        assert nbytes == 4 * (64 * 128 + 128 + 128 * 3 + 3)
+
+
+def test_gradient_exchange_requires_process_group():
+    from predict_pv_yield_b200.dp import GradientExchange
+
+    if dist.is_initialized():
+        pytest.skip("a process group is already initialised")
+    with pytest.raises(RuntimeError, match="process group"):
+        GradientExchange(torch.nn.Linear(2, 2))
