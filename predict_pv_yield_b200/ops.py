@@ -365,11 +365,15 @@ class EncoderFn(torch.autograd.Function):
     def forward(ctx, sat, mean, std, *wb):
         n_layers = len(wb) // 2
         acts = []
-        x = sat
+        # int16 cube: one streaming pass of the normalise kernel (128-bit loads, 6 B/element), so that layer 0's
+        # forward and weight gradient use the cp.async-pipelined fp32 loaders (measured 1.5x faster than converting
+        # inside their staging loops); the conv kernels keep their fused-int16 loaders for callers that want them.
+        x = sat_normalise(sat, mean, std) if sat.dtype == torch.int16 else sat
+        x0 = x
         for l in range(n_layers):
-            x = conv3d_fwd(x, wb[2 * l], wb[2 * l + 1], relu=True, mean=mean, std=std)
+            x = conv3d_fwd(x, wb[2 * l], wb[2 * l + 1], relu=True)
             acts.append(x)
-        ctx.save_for_backward(sat, mean, std, *wb, *acts)
+        ctx.save_for_backward(x0, mean, std, *wb, *acts)
         ctx.n_layers = n_layers
         return acts[-1].view(sat.shape[0], -1)
 
@@ -384,7 +388,7 @@ class EncoderFn(torch.autograd.Function):
         grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
         for l in range(n - 1, -1, -1):
             x = sat if l == 0 else acts[l - 1]
-            dw, db = conv3d_wgrad(x, gz, mean, std)
+            dw, db = conv3d_wgrad(x, gz)
             grads[2 * l], grads[2 * l + 1] = dw, db
             if l > 0:
                 gz = conv3d_dgrad(gz, wb[2 * l], acts[l - 1], acts[l - 1].shape)
