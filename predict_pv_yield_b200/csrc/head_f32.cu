@@ -23,7 +23,7 @@ constexpr int kHeadThreads = 256;
 constexpr int kFc1KT = 64;          // K columns per smem stage (forward)
 constexpr int kFc1BT = 32;          // batch rows per tile
 constexpr int kFc1JT = 128;         // fc1 output features per tile
-constexpr int kFc1TargetCtas = 592; // ~4 CTAs per SM on 148 SMs
+constexpr int kFc1TargetCtas = 296; // K splits per feature tile: 2 CTAs per SM on 148 SMs at one batch tile
 
 // ---- split-K planning shared by the workspace query and the launcher --------------------------------
 struct Fc1Plan {
@@ -38,7 +38,8 @@ static Fc1Plan fc1_plan(int B, int F1, long long K1) {
   p.nbt = ceil_div(B, kFc1BT);
   p.njt = ceil_div(F1, kFc1JT);
   long long stages = ceil_div(K1, (long long)kFc1KT);
-  long long S = kFc1TargetCtas / (p.nbt * p.njt);
+  // the K split does NOT depend on the batch size: a sample's forecast is bit-identical whatever batch it rides in
+  long long S = kFc1TargetCtas / p.njt;
   if (S < 1) S = 1;
   if (S > stages) S = stages;
   p.k_per_split = ceil_div(stages, S) * kFc1KT;

@@ -46,6 +46,10 @@ class Model(BaseModel):
 
     name = "conv3d"
 
+    # inference (no_grad) batches larger than this are streamed through the kernels in micro-batches, so the
+    # activation workspace stays fixed when forecasting all GB PV systems at once (BASELINE config 4: B = 512..8192)
+    inference_micro_batch = 256
+
     def __init__(
         self,
         include_pv_yield: bool = True,
@@ -145,10 +149,21 @@ class Model(BaseModel):
 
     def forward(self, x):
         x = as_batch(x)
+        n = x.satellite.data.shape[0]
+        if not torch.is_grad_enabled() and n > self.inference_micro_batch:
+            outs = []
+            for i in range(0, n, self.inference_micro_batch):
+                outs.append(self._forward(x, slice(i, min(i + self.inference_micro_batch, n))))
+            return torch.cat(outs, dim=0)
+        return self._forward(x, None)
+
+    def _forward(self, x, rows):
+        """One pass of the step's forward on the batch rows ``rows`` (None = all)."""
+        sel = (lambda t: t) if rows is None else (lambda t: t[rows])
 
         # ******************* Satellite imagery *************************
         # Shape: batch_size, channel, seq_length, height, width
-        sat_data = x.satellite.data
+        sat_data = sel(x.satellite.data)
         if not sat_data.is_cuda:
             raise RuntimeError(
                 "predict_pv_yield_b200.Model is CUDA (sm_100a) only: move the batch to the GPU "
@@ -175,7 +190,7 @@ class Model(BaseModel):
         # add pv yield history (model.py:130-136); nan_to_num + concat are fused into the head kernel
         pv_yield_history = None
         if self.include_pv_yield:
-            pv_yield_history = x[self.output_variable][:, : self.history_len_30 + 1]
+            pv_yield_history = sel(x[self.output_variable])[:, : self.history_len_30 + 1]
             if pv_yield_history.dtype != torch.float32:
                 pv_yield_history = pv_yield_history.float()
             if pv_yield_history.stride(-1) != 1:
@@ -185,7 +200,7 @@ class Model(BaseModel):
         nwp_data = None
         wn = bn = None
         if self.include_nwp:
-            nwp_data = x["nwp"].float().flatten(start_dim=1).contiguous()
+            nwp_data = sel(x["nwp"]).float().flatten(start_dim=1).contiguous()
             wn, bn = self.fc_nwp.weight, self.fc_nwp.bias
 
         out = ops.HeadFn.apply(

@@ -156,3 +156,60 @@ def test_full_size_config2_vs_oracle(dev):
     with torch.no_grad():
         y_perm = m(O.batch_to(pb, dev))
     assert torch.equal(y_perm, y_hat[perm.to(dev)])
+
+
+def test_inference_sweep_micro_batching(dev):
+    """BASELINE config 4 (inference sweep): a no_grad forward over a batch larger than the micro-batch equals the
+    concatenation of per-chunk forwards bit for bit (samples are independent), with the NWP / PV-history branches on."""
+    case = CASES["nwp_pv_small"]
+    m = _model(case["model"], dev)
+    m.load_state_dict(golden_state_dict(m))
+    m.inference_micro_batch = 5
+    B = 13
+    b = O.batch_to(O.make_synthetic_batch(B, 12, 19, 16, seed=7), dev)
+    with torch.no_grad():
+        y = m(b)
+        assert y.shape == (B, m.forecast_len)
+        m.inference_micro_batch = 256
+        y_one = m(b)
+    assert torch.equal(y, y_one)
+
+
+def test_inference_full_size_batch_512(dev):
+    """Config 4 at its smallest sweep point, full-size cubes: B = 512 streams through 256-sample micro-batches."""
+    kw = dict(include_pv_yield=False, include_nwp=False, forecast_minutes=60, history_minutes=30)
+    m = _model(kw, dev)
+    g = torch.Generator().manual_seed(1)
+    sat = torch.randint(0, 1024, (512, 12, 19, 64, 64), generator=g, dtype=torch.int32).to(torch.int16).to(dev)
+    with torch.no_grad():
+        y = m({"satellite": {"data": sat}})
+        y_head = m({"satellite": {"data": sat[:8]}})
+    assert y.shape == (512, 12) and bool(torch.isfinite(y).all())
+    assert torch.equal(y[:8], y_head)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_deep_variant_config5_vs_oracle(dev, precision, tol):
+    """BASELINE config 5 (deep variant): 8 conv layers x 32 channels on 128x128 crops, forward + loss vs the oracle
+    (B = 1: the oracle needs ~56 GFLOP per sample on the CPU)."""
+    from predict_pv_yield_b200.models.conv3d.model import Model
+
+    kw = dict(include_pv_yield=False, include_nwp=False, forecast_minutes=60, history_minutes=30,
+              number_of_conv3d_layers=8, image_size_pixels=128)
+    torch.manual_seed(5)
+    om = O.OracleModel(**kw)
+    om.batch_size = 1
+    m = Model(**kw, precision=precision).to(dev)
+    m.batch_size = 1
+    m.load_state_dict(om.state_dict())
+    assert m.cnn_output_size == 32 * 112 * 112 * 3
+    batch = O.make_synthetic_batch(1, image_size_pixels=128, seed=3)
+    with torch.no_grad():
+        r = om.step_losses(batch)
+    loss = m.training_step(O.batch_to(batch, dev), 0)
+    loss.backward()
+    with torch.no_grad():
+        y_hat = m(O.batch_to(batch, dev))
+    assert O.normalised_max_err(y_hat, r["y_hat"]) <= tol
+    assert abs(float(loss.detach()) - float(r["nmae"])) <= tol * abs(float(r["nmae"]))
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
