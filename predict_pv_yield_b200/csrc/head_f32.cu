@@ -136,6 +136,107 @@ fc1_fwd_splitk_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   }
 }
 
+// ---- fc1 forward, split-K, fast path (K1 % 4 == 0, 16-byte aligned) ---------------------------------------
+// Same contract as fc1_fwd_splitk_kernel.  256 threads = 4 k-groups x 64 threads; a 64-thread group owns the
+// whole 32 (batch) x 128 (feature) tile with 8 x 8 register tiles (W rows interleaved by 16 so that LDS.128 across
+// lanes is conflict-free, x rows warp-half-uniform -> broadcast) and takes every 4th k4-step of a stage, so a W
+// element is read from shared memory by 4 threads instead of 8 and smem bandwidth stops being the limit; stages of
+// 64 K columns stream in through a 2-stage cp.async pipeline; the four groups are summed through smem at the end.
+constexpr int kFc1V2Threads = 256;
+__global__ void __launch_bounds__(kFc1V2Threads, 2)
+fc1_fwd_splitk_v2_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ partial, int B, int F1,
+                         long long K1, int nbt, int njt, long long k_per_split) {
+  constexpr int LD = kFc1KT + 4;                       // 68 words
+  constexpr int STAGE = (kFc1JT + kFc1BT) * LD;        // floats per stage
+  extern __shared__ __align__(16) float sm2[];         // [2][STAGE]; reused as [4][32][128] for the final reduce
+
+  int id = blockIdx.x;
+  const int bt = id % nbt; id /= nbt;
+  const int jt = id % njt;
+  const int s = id / njt;
+  const int b0 = bt * kFc1BT, j0 = jt * kFc1JT;
+  const long long kb = s * k_per_split;
+  const long long ke = min(K1, kb + k_per_split);
+  const int nstage = static_cast<int>((ke - kb + kFc1KT - 1) / kFc1KT);
+
+  const int tid = threadIdx.x;
+  const int grp = tid >> 6;          // k-group 0..3
+  const int t64 = tid & 63;
+  const int jl = t64 & 15;           // rows jl + 16 r, r = 0..7
+  const int bg = t64 >> 4;           // batch rows 8 bg .. 8 bg + 7
+
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+  auto issue = [&](int st, int buf) {
+    const long long k0 = kb + static_cast<long long>(st) * kFc1KT;
+    float* ws = sm2 + buf * STAGE;
+    float* xs = ws + kFc1JT * LD;
+    const uint32_t ws0 = static_cast<uint32_t>(__cvta_generic_to_shared(ws));
+    const uint32_t xs0 = static_cast<uint32_t>(__cvta_generic_to_shared(xs));
+    for (int idx = tid; idx < kFc1JT * (kFc1KT / 4); idx += kFc1V2Threads) {
+      const int r = idx >> 4, c4 = idx & 15;
+      const bool ok = (j0 + r < F1) && (k0 + 4 * c4 < ke);
+      const float* src = w + static_cast<long long>(ok ? j0 + r : 0) * K1 + (ok ? k0 + 4 * c4 : 0);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ws0 + 4u * (r * LD + 4 * c4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    for (int idx = tid; idx < kFc1BT * (kFc1KT / 4); idx += kFc1V2Threads) {
+      const int r = idx >> 4, c4 = idx & 15;
+      const bool ok = (b0 + r < B) && (k0 + 4 * c4 < ke);
+      const float* src = x + static_cast<long long>(ok ? b0 + r : 0) * K1 + (ok ? k0 + 4 * c4 : 0);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(xs0 + 4u * (r * LD + 4 * c4)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  issue(0, 0);
+  for (int st = 0; st < nstage; ++st) {
+    if (st + 1 < nstage) {
+      issue(st + 1, (st + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* ws = sm2 + (st & 1) * STAGE;
+    const float* xs = ws + kFc1JT * LD;
+#pragma unroll
+    for (int kk = 0; kk < kFc1KT / 16; ++kk) {
+      const int k4 = 16 * kk + 4 * grp;  // this group's k4-step
+      float4 wv[8], xv[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) wv[r] = *reinterpret_cast<const float4*>(ws + (jl + 16 * r) * LD + k4);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) xv[c] = *reinterpret_cast<const float4*>(xs + (8 * bg + c) * LD + k4);
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          acc[r][c] = fmaf(wv[r].x, xv[c].x, acc[r][c]);
+          acc[r][c] = fmaf(wv[r].y, xv[c].y, acc[r][c]);
+          acc[r][c] = fmaf(wv[r].z, xv[c].z, acc[r][c]);
+          acc[r][c] = fmaf(wv[r].w, xv[c].w, acc[r][c]);
+        }
+    }
+    __syncthreads();
+  }
+  // ---- sum the four k-groups (fixed order) and write the partial ----
+  float* red = sm2;  // [4][32 b][128 j]
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) red[(grp * kFc1BT + 8 * bg + c) * kFc1JT + jl + 16 * r] = acc[r][c];
+  __syncthreads();
+  for (int idx = tid; idx < kFc1BT * kFc1JT; idx += kFc1V2Threads) {
+    const int b = idx >> 7, j = idx & 127;
+    const float v = (red[idx] + red[kFc1BT * kFc1JT + idx]) + (red[2 * kFc1BT * kFc1JT + idx] + red[3 * kFc1BT * kFc1JT + idx]);
+    if (b0 + b < B && j0 + j < F1) partial[(static_cast<long long>(s) * B + b0 + b) * F1 + j0 + j] = v;
+  }
+}
+
 __device__ __forceinline__ float nan_to_num_f(float v) {  // torch.nan_to_num defaults (model.py:131)
   if (isnan(v)) return 0.f;
   if (isinf(v)) return v > 0.f ? FLT_MAX : -FLT_MAX;
@@ -159,13 +260,26 @@ __global__ void __launch_bounds__(kHeadThreads) head_tail_fwd_kernel(const pvb20
   float* nw = h3 + h.F3;          // [NNWP]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kHeadThreads / 32;
 
-  for (int j = tid; j < h.F1; j += kHeadThreads) {
-    float s = 0.f;
-    for (int p = 0; p < S; ++p) s += partial[(static_cast<long long>(p) * h.B + b) * h.F1 + j];
-    s += __ldg(h.b1 + j);
-    s = (s < 0.f) ? 0.f : s;
-    h1[j] = s;
-    h.h1[static_cast<long long>(b) * h.F1 + j] = s;
+  // sum the split-K partials: warp w takes partials w, w+8, ... (coalesced rows of F1 floats), then the eight warp
+  // sums are added in warp order -- a fixed order, so the result is deterministic
+  {
+    float* wsum = nw + h.NNWP;  // [8][F1] scratch
+    for (int j0 = 0; j0 < h.F1; j0 += 32) {
+      const int j = j0 + lane;
+      float s = 0.f;
+      if (j < h.F1)
+        for (int p = warp; p < S; p += nwarp) s += partial[(static_cast<long long>(p) * h.B + b) * h.F1 + j];
+      if (j < h.F1) wsum[warp * h.F1 + j] = s;
+    }
+    __syncthreads();
+    for (int j = tid; j < h.F1; j += kHeadThreads) {
+      float s = 0.f;
+      for (int w = 0; w < nwarp; ++w) s += wsum[w * h.F1 + j];
+      s += __ldg(h.b1 + j);
+      s = (s < 0.f) ? 0.f : s;
+      h1[j] = s;
+      h.h1[static_cast<long long>(b) * h.F1 + j] = s;
+    }
   }
   for (int i = tid; i < h.NNWP; i += kHeadThreads) nw[i] = h.nwp[static_cast<long long>(b) * h.NNWP + i];
   for (int i = tid; i < h.NPV; i += kHeadThreads) {
@@ -402,6 +516,190 @@ fc1_dgrad_kernel(const float* __restrict__ g1, const float* __restrict__ w, cons
   }
 }
 
+// ---- fc1 data gradient, fast path: gx[b][k] = (sum_j g1[b][j] * w[j][k]) * (x[b][k] > 0) ---------------------------------
+// Persistent CTAs (one per SM and batch tile) stream [128 j][128 k] slabs of W1 (64 KB) through a 2-stage cp.async
+// pipeline: the next slab lands while the current one is in the FMA loop and while the result is reduced, masked and
+// stored.  256 threads = 4 j-groups (j = grp mod 4) x 64 threads with 8 (b) x 8 (k) register tiles (k columns split
+// 4 + 4 so LDS.128 across lanes is conflict-free); the j-groups are summed through smem in fixed order.
+constexpr int kFc1DgThreads = 256;
+__global__ void __launch_bounds__(kFc1DgThreads, 1)
+fc1_dgrad_v2_kernel(const float* __restrict__ g1, const float* __restrict__ w, const float* __restrict__ x,
+                    float* __restrict__ gx, int B, int F1, long long K1, long long ktiles) {
+  constexpr int KT = 128;
+  extern __shared__ __align__(16) float smd[];
+  float* gsT = smd;                       // [128 j][32 b]
+  float* wbuf = smd + 128 * kFc1BT;       // [2][128 j][128 k]; a consumed buffer is reused as [4][32 b][128 k]
+  const int b0 = blockIdx.y * kFc1BT;
+  const int tid = threadIdx.x;
+  const int grp = tid >> 6, t64 = tid & 63;
+  const int tk = t64 & 15;  // k columns 4tk..4tk+3 and 64+4tk..64+4tk+3
+  const int tb = t64 >> 4;  // batch rows 8tb..8tb+7
+
+  auto issue = [&](long long tile, int buf) {
+    const long long k0 = tile * KT;
+    const uint32_t ws0 = static_cast<uint32_t>(__cvta_generic_to_shared(wbuf + buf * 128 * KT));
+    for (int idx = tid; idx < 128 * (KT / 4); idx += kFc1DgThreads) {
+      const int r = idx >> 5, c4 = idx & 31;
+      const bool ok = (r < F1) && (k0 + 4 * c4 < K1);
+      const float* src = w + static_cast<long long>(ok ? r : 0) * K1 + (ok ? k0 + 4 * c4 : 0);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ws0 + 16u * idx), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  for (int idx = tid; idx < 128 * kFc1BT; idx += kFc1DgThreads) {
+    const int j = idx >> 5, b = idx & 31;
+    gsT[idx] = (j < F1 && b0 + b < B) ? g1[static_cast<long long>(b0 + b) * F1 + j] : 0.f;
+  }
+  long long tile = blockIdx.x;
+  if (tile < ktiles) issue(tile, 0);
+  for (int it = 0; tile < ktiles; ++it, tile += gridDim.x) {
+    const long long next = tile + gridDim.x;
+    if (next < ktiles) {
+      issue(next, (it + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    float* ws = wbuf + (it & 1) * 128 * KT;
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = 4 * jj + grp;
+      const float4 wa = *reinterpret_cast<const float4*>(ws + j * KT + 4 * tk);
+      const float4 wb = *reinterpret_cast<const float4*>(ws + j * KT + 64 + 4 * tk);
+      const float4 ga = *reinterpret_cast<const float4*>(gsT + j * kFc1BT + 8 * tb);
+      const float4 gb = *reinterpret_cast<const float4*>(gsT + j * kFc1BT + 8 * tb + 4);
+      const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(gv[r], wv[c], acc[r][c]);
+    }
+    __syncthreads();  // everyone is done reading this W slab
+    float* red = ws;  // [4][32 b][128 k]
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float* row = red + (grp * kFc1BT + 8 * tb + r) * KT;
+      *reinterpret_cast<float4*>(row + 4 * tk) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      *reinterpret_cast<float4*>(row + 64 + 4 * tk) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+    }
+    __syncthreads();
+    const long long k0 = tile * KT;
+    for (int idx = tid; idx < kFc1BT * (KT / 4); idx += kFc1DgThreads) {
+      const int b = idx >> 5, c4 = idx & 31;
+      if (b0 + b >= B || k0 + 4 * c4 >= K1) continue;
+      const float4 p0 = *reinterpret_cast<const float4*>(red + (0 * kFc1BT + b) * KT + 4 * c4);
+      const float4 p1 = *reinterpret_cast<const float4*>(red + (1 * kFc1BT + b) * KT + 4 * c4);
+      const float4 p2 = *reinterpret_cast<const float4*>(red + (2 * kFc1BT + b) * KT + 4 * c4);
+      const float4 p3 = *reinterpret_cast<const float4*>(red + (3 * kFc1BT + b) * KT + 4 * c4);
+      const long long off = static_cast<long long>(b0 + b) * K1 + k0 + 4 * c4;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + off));
+      float4 o;
+      o.x = xv.x > 0.f ? (p0.x + p1.x) + (p2.x + p3.x) : 0.f;
+      o.y = xv.y > 0.f ? (p0.y + p1.y) + (p2.y + p3.y) : 0.f;
+      o.z = xv.z > 0.f ? (p0.z + p1.z) + (p2.z + p3.z) : 0.f;
+      o.w = xv.w > 0.f ? (p0.w + p1.w) + (p2.w + p3.w) : 0.f;
+      __stcs(reinterpret_cast<float4*>(gx + off), o);
+    }
+    __syncthreads();  // the buffer may be refilled by the prefetch issued at the top of the next iteration
+  }
+}
+
+// ---- fc1 weight gradient, fast path: dW1[j][k] = sum_b g1[b][j] * x[b][k] ---------------------------------------------
+// Persistent CTAs; pipeline items are (k tile, batch tile) pairs: x [32 b][128 k] + g1 [32 b][128 j] arrive by cp.async
+// one item ahead; 8 (j) x 8 (k) register tiles accumulate over the batch tiles and are streamed out (565 MB, the
+// HBM-write-bound part of the step) while the next item is already in flight.
+__global__ void __launch_bounds__(kHeadThreads, 2)
+fc1_wgrad_v2_kernel(const float* __restrict__ g1, const float* __restrict__ x, float* __restrict__ dW, int B, int F1,
+                    long long K1, long long ktiles, int nbt) {
+  constexpr int KT = 128;
+  constexpr int STAGE = kFc1BT * (kFc1JT + KT);
+  extern __shared__ __align__(16) float smw[];  // [2][ gs 32x128 | xs 32x128 ]
+  const int tid = threadIdx.x;
+  const int tk = tid & 15;  // k columns 4tk..4tk+3 and 64+4tk..64+4tk+3
+  const int tj = tid >> 4;  // j rows 8tj..8tj+7
+  const long long items = ktiles * nbt;
+
+  auto issue = [&](long long item, int buf) {
+    const long long k0 = (item / nbt) * KT;
+    const int b0 = static_cast<int>(item % nbt) * kFc1BT;
+    const uint32_t gs0 = static_cast<uint32_t>(__cvta_generic_to_shared(smw + buf * STAGE));
+    const uint32_t xs0 = gs0 + 4u * kFc1BT * kFc1JT;
+    for (int idx = tid; idx < kFc1BT * (kFc1JT / 4); idx += kHeadThreads) {
+      const int r = idx >> 5, c4 = idx & 31;
+      const bool ok = (b0 + r < B) && (4 * c4 < F1);  // F1 % 4 == 0 on this path
+      const float* src = g1 + static_cast<long long>(ok ? b0 + r : 0) * F1 + (ok ? 4 * c4 : 0);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(gs0 + 16u * idx), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    for (int idx = tid; idx < kFc1BT * (KT / 4); idx += kHeadThreads) {
+      const int r = idx >> 5, c4 = idx & 31;
+      const bool ok = (b0 + r < B) && (k0 + 4 * c4 < K1);
+      const float* src = x + static_cast<long long>(ok ? b0 + r : 0) * K1 + (ok ? k0 + 4 * c4 : 0);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xs0 + 16u * idx), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[8][8];
+  long long item = static_cast<long long>(blockIdx.x) * nbt;  // a CTA owns whole k tiles (all their batch tiles)
+  const long long stride = static_cast<long long>(gridDim.x) * nbt;
+  if (item < items) issue(item, 0);
+  int it = 0;
+  for (; item < items; item += stride) {
+    for (int bt = 0; bt < nbt; ++bt, ++it) {
+      const long long cur = item + bt;
+      long long next = cur + 1;
+      if (bt == nbt - 1) next = item + stride;
+      if (next < items) {
+        issue(next, (it + 1) & 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const float* gs = smw + (it & 1) * STAGE;
+      const float* xs = gs + kFc1BT * kFc1JT;
+      if (bt == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+      }
+#pragma unroll 4
+      for (int b = 0; b < kFc1BT; ++b) {
+        const float4 ga = *reinterpret_cast<const float4*>(gs + b * kFc1JT + 8 * tj);
+        const float4 gb = *reinterpret_cast<const float4*>(gs + b * kFc1JT + 8 * tj + 4);
+        const float4 xa = *reinterpret_cast<const float4*>(xs + b * KT + 4 * tk);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + b * KT + 64 + 4 * tk);
+        const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(gv[r], xv[c], acc[r][c]);
+      }
+      __syncthreads();  // stage consumed
+    }
+    const long long k0 = (item / nbt) * KT;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int j = 8 * tj + r;
+      if (j >= F1) continue;
+      float* row = dW + static_cast<long long>(j) * K1 + k0;
+      if (k0 + 4 * tk < K1) __stcs(reinterpret_cast<float4*>(row + 4 * tk), make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+      if (k0 + 64 + 4 * tk < K1)
+        __stcs(reinterpret_cast<float4*>(row + 64 + 4 * tk), make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]));
+    }
+  }
+}
+
 static int check_head(const pvb200_head_t* h) {
   PVB_REQUIRE(h != nullptr, "head: null descriptor");
   PVB_REQUIRE(h->struct_size == sizeof(pvb200_head_t), "head: struct_size %zu != %zu (ABI mismatch)", h->struct_size,
@@ -441,11 +739,18 @@ int pvb200_head_fwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
   float* partial = static_cast<float*>(h->workspace);
   const int vec = vec4_ok(h->x, h->K1) && vec4_ok(h->w1, h->K1);
   const long long ctas = static_cast<long long>(p.S) * p.nbt * p.njt;
-  fc1_fwd_splitk_kernel<<<static_cast<unsigned>(ctas), kHeadThreads, 0, st>>>(h->x, h->w1, partial, h->B, h->F1, h->K1,
-                                                                               p.nbt, p.njt, p.k_per_split, vec);
+  if (vec) {
+    const size_t smem2 = 2 * static_cast<size_t>(kFc1JT + kFc1BT) * (kFc1KT + 4) * sizeof(float);  // 87 KB >= the 64 KB reduce buffer
+    PVB_CUDA(cudaFuncSetAttribute(fc1_fwd_splitk_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    fc1_fwd_splitk_v2_kernel<<<static_cast<unsigned>(ctas), kFc1V2Threads, smem2, st>>>(h->x, h->w1, partial, h->B, h->F1, h->K1,
+                                                                                        p.nbt, p.njt, p.k_per_split);
+  } else {
+    fc1_fwd_splitk_kernel<<<static_cast<unsigned>(ctas), kHeadThreads, 0, st>>>(h->x, h->w1, partial, h->B, h->F1, h->K1,
+                                                                                 p.nbt, p.njt, p.k_per_split, vec);
+  }
   PVB_LAUNCHED("fc1_fwd_splitk");
   const int NCAT = h->F2 + h->NPV + (h->NNWP > 0 ? h->FNWP : 0);
-  const size_t smem = static_cast<size_t>(h->F1 + NCAT + h->F3 + h->NNWP) * sizeof(float);
+  const size_t smem = static_cast<size_t>(h->F1 + NCAT + h->F3 + h->NNWP + 8 * h->F1) * sizeof(float);
   PVB_REQUIRE(smem <= 48 * 1024, "head_fwd: feature sizes too large for the tail kernel (%zu B smem)", smem);
   head_tail_fwd_kernel<<<h->B, kHeadThreads, smem, st>>>(*h, partial, p.S);
   PVB_LAUNCHED("head_tail_fwd");
@@ -487,12 +792,32 @@ int pvb200_head_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
   const int njt = ceil_div(h->F1, kFc1JT);
   const long long kt = ceil_div(h->K1, 128LL);
   PVB_REQUIRE(kt * njt <= 0x7fffffffLL, "head_bwd: K1 too large");
-  fc1_wgrad_kernel<<<static_cast<unsigned>(kt * njt), kHeadThreads, 0, st>>>(h->g_h1, h->x, h->dw1, h->B, h->F1, h->K1, njt, vec);
+  if (vec && h->F1 <= 128 && h->F1 % 4 == 0 && vec4_ok(h->g_h1, h->F1)) {
+    const size_t smemw = 2 * static_cast<size_t>(kFc1BT) * (kFc1JT + 128) * sizeof(float);
+    PVB_CUDA(cudaFuncSetAttribute(fc1_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+    const int sms = sm_count();
+    PVB_REQUIRE(sms > 0, "head_bwd: no CUDA device");
+    const long long gw = kt < 2LL * sms ? kt : 2LL * sms;
+    fc1_wgrad_v2_kernel<<<static_cast<unsigned>(gw), kHeadThreads, smemw, st>>>(h->g_h1, h->x, h->dw1, h->B, h->F1, h->K1, kt,
+                                                                               ceil_div(h->B, kFc1BT));
+  } else {
+    fc1_wgrad_kernel<<<static_cast<unsigned>(kt * njt), kHeadThreads, 0, st>>>(h->g_h1, h->x, h->dw1, h->B, h->F1, h->K1, njt, vec);
+  }
   PVB_LAUNCHED("fc1_wgrad");
   if (h->g_x) {
     const int nbt = ceil_div(h->B, kFc1BT);
     PVB_REQUIRE(kt * nbt <= 0x7fffffffLL, "head_bwd: K1*B too large");
-    fc1_dgrad_kernel<<<static_cast<unsigned>(kt * nbt), kHeadThreads, 0, st>>>(h->g_h1, h->w1, h->x, h->g_x, h->B, h->F1, h->K1, nbt, vec);
+    if (vec && h->F1 <= 128) {
+      const size_t smemd = (128 * kFc1BT + 2 * 128 * 128) * sizeof(float);
+      PVB_CUDA(cudaFuncSetAttribute(fc1_dgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemd));
+      const int sms = sm_count();
+      PVB_REQUIRE(sms > 0, "head_bwd: no CUDA device");
+      const long long gx_ = kt < sms ? kt : sms;
+      fc1_dgrad_v2_kernel<<<dim3(static_cast<unsigned>(gx_), nbt), kFc1DgThreads, smemd, st>>>(h->g_h1, h->w1, h->x, h->g_x, h->B,
+                                                                                                h->F1, h->K1, kt);
+    } else {
+      fc1_dgrad_kernel<<<static_cast<unsigned>(kt * nbt), kHeadThreads, 0, st>>>(h->g_h1, h->w1, h->x, h->g_x, h->B, h->F1, h->K1, nbt, vec);
+    }
     PVB_LAUNCHED("fc1_dgrad");
   }
   return PVB200_OK;

@@ -139,6 +139,38 @@ int pvb200_sat_normalise_bf16(const int16_t* x, uint16_t* y, const float* mean, 
 // Same two-rounding fp32 arithmetic, then RNE to bf16; channels >= C are zero.  One thread per (channel group,
 // position): 8 coalesced 2-byte loads (one per channel plane), one 16-byte store.
 namespace pvb {
+// vector path: one thread = 8 consecutive positions x the 8 channels of one group: eight 128-bit streaming loads
+// (one per channel plane) and eight 16-byte stores that form one contiguous 128-byte run of the blocked tensor.
+__global__ void __launch_bounds__(256)
+sat_normalise_blocked_vec_kernel(const int16_t* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ mean,
+                                 const float* __restrict__ stdv, int C, int Cg, long long thw, long long total8) {
+  const long long thw8 = thw >> 3;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total8;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p8 = idx % thw8;
+    const long long r = idx / thw8;
+    const int cg = static_cast<int>(r % Cg);
+    const long long b = r / Cg;
+    float f[8][8];  // [channel][position]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      if (c < C) {
+        const uint4 q = ld_stream_u4(reinterpret_cast<const uint4*>(x + (b * C + c) * thw) + p8);
+        norm8(q, __ldg(mean + c), __ldg(stdv + c), f[j]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[j][i] = 0.f;
+      }
+    }
+    uint4* dst = y + (b * Cg + cg) * thw + 8 * p8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      dst[i] = make_uint4(pack_bf16x2(f[0][i], f[1][i]), pack_bf16x2(f[2][i], f[3][i]), pack_bf16x2(f[4][i], f[5][i]),
+                          pack_bf16x2(f[6][i], f[7][i]));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sat_normalise_blocked_kernel(const int16_t* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ mean,
                              const float* __restrict__ stdv, int C, int Cg, long long thw, long long total) {
@@ -168,10 +200,18 @@ extern "C" int pvb200_sat_normalise_blocked_bf16(const int16_t* x, uint16_t* yb,
   const int Cg = 2 * ceil_div(C, 16);
   const long long thw = static_cast<long long>(T) * H * W;
   const long long total = static_cast<long long>(B) * Cg * thw;
-  long long grid = ceil_div(total, 256LL);
-  if (grid > 148 * 32) grid = 148 * 32;
-  sat_normalise_blocked_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<uint4*>(yb), mean,
-                                                                                            std, C, Cg, thw, total);
+  if (thw % 8 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+    const long long total8 = total / 8;
+    long long grid = ceil_div(total8, 256LL);
+    if (grid > 148 * 16) grid = 148 * 16;
+    sat_normalise_blocked_vec_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(
+        x, reinterpret_cast<uint4*>(yb), mean, std, C, Cg, thw, total8);
+  } else {
+    long long grid = ceil_div(total, 256LL);
+    if (grid > 148 * 32) grid = 148 * 32;
+    sat_normalise_blocked_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<uint4*>(yb), mean,
+                                                                                              std, C, Cg, thw, total);
+  }
   PVB_LAUNCHED("sat_normalise_blocked_bf16");
   return PVB200_OK;
 }

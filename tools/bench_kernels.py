@@ -44,6 +44,27 @@ def main():
         layers.append((C, T, S))
         C, T, S = 32, T - 2, S - 2
     print(f"{'kernel':<34}{'ms':>9}{'TFLOP/s':>10}{'GB/s':>9}")
+    if args.only in ("", "f32", "head"):
+        K1, F1 = 32 * 11 * 56 * 56, 128
+        feats = torch.relu(torch.randn(B, K1, device=dev)).requires_grad_(True)
+        P = [torch.randn(F1, K1, device=dev) / K1 ** 0.5, torch.zeros(F1, device=dev), torch.randn(128, F1, device=dev) / 11,
+             torch.zeros(128, device=dev), None, None, torch.randn(64, 128, device=dev) / 11, torch.zeros(64, device=dev),
+             torch.randn(12, 64, device=dev) / 8, torch.zeros(12, device=dev)]
+        P = [p.requires_grad_(True) if p is not None else None for p in P]
+        tm = ops.KernelTimer()
+        for it in range(4):
+            flush.zero_()
+            if it == 1:
+                ops.set_timer(tm)
+            out = ops.HeadFn.apply(feats, None, None, *P)
+            out.backward(torch.ones_like(out))
+        torch.cuda.synchronize()
+        ops.set_timer(None)
+        for k, v in tm.summary().items():
+            ms = v["ms"] / v["calls"]
+            print(f"{k:<34}{ms:9.3f}{v['flops'] / v['calls'] / ms / 1e9:10.1f}{v['bytes'] / v['calls'] / ms / 1e6:9.0f}")
+        if args.only == "head":
+            return
     for l, (Ci, Ti, Si) in enumerate(layers):
         Co = 32
         npos = B * (Ti - 2) * (Si - 2) ** 2
