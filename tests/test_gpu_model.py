@@ -213,3 +213,24 @@ def test_deep_variant_config5_vs_oracle(dev, precision, tol):
     assert O.normalised_max_err(y_hat, r["y_hat"]) <= tol
     assert abs(float(loss.detach()) - float(r["nmae"])) <= tol * abs(float(r["nmae"]))
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+
+
+def test_device_prefetcher_preserves_batches(dev):
+    """Input pipeline (SURVEY 8f #3): int16 cubes arrive intact and in order, one batch ahead, and feed the model."""
+    from predict_pv_yield_b200.data import DevicePrefetcher
+
+    case = CASES["test_yaml_pv"]
+    m = _model(case["model"], dev)
+    m.batch_size = case["batch"]
+    host = [O.make_synthetic_batch(2, 11, 25, 16, seed=s, include_legacy_keys=False) for s in range(5)]
+    got = []
+    for i, b in enumerate(DevicePrefetcher(iter(host), dev)):
+        assert b["satellite"]["data"].is_cuda and b["satellite"]["data"].dtype == torch.int16
+        assert torch.equal(b["satellite"]["data"].cpu(), host[i]["satellite"]["data"])
+        assert torch.equal(b["pv"]["pv_yield"].cpu(), host[i]["pv"]["pv_yield"])
+        with torch.no_grad():
+            got.append(m(b).cpu())
+    assert len(got) == 5
+    with torch.no_grad():
+        want = m(O.batch_to(host[3], dev)).cpu()
+    assert torch.equal(got[3], want)

@@ -176,3 +176,10 @@ def test_c_oracle_agrees_with_torch_oracle(built):
     t = rs.rand(B, 4).astype(np.float32)
     l1 = lib.ora_l1_loss(_fp(out), _fp(t), ctypes.c_long(out.size))
     assert abs(l1 - np.abs(out - t).mean()) <= 1e-6
+
+
+def test_device_prefetcher_rejects_cpu():
+    from predict_pv_yield_b200.data import DevicePrefetcher
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        DevicePrefetcher([], torch.device("cpu"))
