@@ -170,6 +170,31 @@ int pvb200_head_fwd_f32(const pvb200_head_t* h, pvb200_stream_t stream);
 /* backward: from g_out fills g_h3, g_cat, g_h1, g_x and all dw / db */
 int pvb200_head_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream);
 
+/* tail-only variants for callers that compute fc1 themselves (the bf16 tensor-core path): _tail_fwd consumes S
+ * split-K partials [S][B][F1] passed as h->workspace (h->x may be NULL); _tail_bwd produces everything except fc1's
+ * weight / data gradient (g_h1 and db1 ARE produced; dw1, x, g_x may be NULL). */
+int pvb200_head_tail_fwd_f32(const pvb200_head_t* h, int S, pvb200_stream_t stream);
+int pvb200_head_tail_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream);
+
+/* ---- a6/a11 in bf16: fc1 as weight-streaming tensor-core GEMMs ------------------------------------------------
+ * replaces self.fc1 / F.relu(self.fc1(out)), model.py:92,125 and autograd.  Features are the last conv activation in
+ * blocked bf16 [B][Cg][T][H][W][8]; `shadow` is a bf16 copy of fc1.weight permuted to [Cg*T*H*W][128][8]
+ * (pvb200_fc1_make_shadow_bf16, once per optimiser step).  B <= 256, fc1_output_features <= 128.
+ *   fwd  : partial[s][b][j], s < pvb200_fc1_fwd_bf16_splits()   (feed to pvb200_head_tail_fwd_f32)
+ *   dgrad: gradient w.r.t. the last conv layer's pre-activation (ReLU mask fused), written in the two layouts of
+ *          pvb200_conv3d_dgrad_bf16 / pvb200_conv3d_wgrad_bf16 (gz_pad zero-bordered by 2, gzw at pitch W+2)
+ *   wgrad: dw1 fp32 [F1][K1] in the reference layout */
+size_t pvb200_fc1_bf16_shadow_bytes(int Cg, int T, int H, int W);
+int pvb200_fc1_make_shadow_bf16(const float* w1, uint16_t* shadow, int F1, int Cg, int T, int H, int W,
+                                pvb200_stream_t stream);
+int pvb200_fc1_fwd_bf16_splits(void);
+int pvb200_fc1_fwd_bf16(const uint16_t* xb, const uint16_t* shadow, float* partial, int B, int F1, int Cg, int T, int H,
+                        int W, pvb200_stream_t stream);
+int pvb200_fc1_dgrad_bf16(const float* g1, const uint16_t* shadow, const uint16_t* xb, uint16_t* gz_pad, uint16_t* gzw,
+                          int B, int F1, int Cg, int T, int H, int W, pvb200_stream_t stream);
+int pvb200_fc1_wgrad_bf16(const float* g1, const uint16_t* xb, float* dw1, int B, int F1, int Cg, int T, int H, int W,
+                          pvb200_stream_t stream);
+
 /* ---- a10: loss -------------------------------------------------------------------------------
  * replaces base_model.py:95-103: y = yield[0:B, -FO:, 0] (strided view: element (b,f) at
  * y[b*y_sb + f*y_sf]); losses[0..3] = {nmae (L1, the returned loss), mse, mse_exp, mae_exp} with

@@ -1,0 +1,435 @@
+// fc1_bf16.cu -- a6/a11 in bf16: the 128 x 1.1 M fc1 layer of the head as weight-streaming tensor-core GEMMs.
+//
+// Reference: self.fc1 = nn.Linear(cnn_output_size, 128) and F.relu(self.fc1(out)), predict_pv_yield/models/conv3d/
+// model.py:92,125 (and their autograd).  fc1.weight is 99.9 % of the parameters; at per-GPU batches <~ 200 every pass
+// over it is HBM-bound, so the bf16 path keeps a bf16 SHADOW of the fp32 master weight (half the bytes) in the layout
+// the tensor cores consume directly:
+//
+//     W1s[kg][j][8]    kg = 8-channel group of the blocked feature index (kg = cg*THW + pos), j = output feature
+//
+// The conv stack's last activation stays blocked bf16, [b][kg][8], so its feature order matches kg without any
+// re-layout; only the shadow is permuted (by fc1_make_shadow, once per optimiser step).
+//   * forward   D[j, b]  = sum_k' W1s[j,k'] X[b,k']   A = W1s tile as K-major  SWIZZLE_NONE (LBO 2 KB, SBO 128 B)
+//   * dgrad     D[k', b] = sum_j  W1s[k',j] G[b,j]    A = the SAME tile read as MN-major (SBO 2 KB, LBO 128 B)
+//   * wgrad     D[j, k'] = sum_b  G[b,j] X[b,k']      B = X tile [kg][b][8] read as MN-major
+// W1s tiles are single bulk copies (TMA engine); the small X / G operands are transposed into the canonical
+// [k-group][row][8] form by the producer warp.  fp32 accumulation in TMEM; the forward writes split-K partials for the
+// existing fused tail kernel, the data gradient fuses the ReLU mask and writes the two layouts the conv backward
+// consumes, the weight gradient writes fp32 in the REFERENCE layout [128][K1] (what Adam / the all-reduce see).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace pvb {
+
+constexpr int kF1J = 128;       // fc1 output features (padded)
+constexpr int kF1KG = 16;       // k-groups per tile  (128 feature columns)
+constexpr int kF1Threads = 192; // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+
+__device__ __forceinline__ uint32_t f2bf(float v) { return static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(v))); }
+
+// ---- shadow: W1 fp32 [F1][K1] (reference layout, k = (cg*8+c8)*THW + pos) -> W1s bf16 [K1/8][128][8] -----------------
+__global__ void __launch_bounds__(256)
+fc1_make_shadow_kernel(const float* __restrict__ w, uint4* __restrict__ ws, int F1, long long THW, int Cg) {
+  // one CTA = 32 positions x 32 features x one channel group; smem transpose so reads run along pos, writes along j
+  __shared__ float tile[8][32][33];
+  const long long pos0 = static_cast<long long>(blockIdx.x) * 32;
+  const int j0 = blockIdx.y * 32;
+  const int cg = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
+  for (int c8 = 0; c8 < 8; ++c8)
+    for (int jj = ty; jj < 32; jj += 8) {
+      const int j = j0 + jj;
+      const long long pos = pos0 + tx;
+      tile[c8][jj][tx] = (j < F1 && pos < THW) ? w[static_cast<long long>(j) * (Cg * 8 * THW) + (cg * 8 + c8) * THW + pos] : 0.f;
+    }
+  __syncthreads();
+  for (int pp = ty; pp < 32; pp += 8) {
+    const long long pos = pos0 + pp;
+    if (pos >= THW) continue;
+    const int j = j0 + tx;
+    uint4 o;
+    o.x = f2bf(tile[0][tx][pp]) | (f2bf(tile[1][tx][pp]) << 16);
+    o.y = f2bf(tile[2][tx][pp]) | (f2bf(tile[3][tx][pp]) << 16);
+    o.z = f2bf(tile[4][tx][pp]) | (f2bf(tile[5][tx][pp]) << 16);
+    o.w = f2bf(tile[6][tx][pp]) | (f2bf(tile[7][tx][pp]) << 16);
+    ws[(cg * THW + pos) * kF1J + j] = o;
+  }
+}
+
+struct Fc1Bf16Args {
+  const uint4* ws;     // shadow [KG][128]
+  const uint4* xb;     // features blocked [B][KG]
+  const float* g1;     // [B][F1] fp32 (dgrad / wgrad)
+  float* partial;      // forward: [S][B][F1]
+  float* dw;           // wgrad: [F1][K1] fp32 reference layout
+  uint4* gz_pad;       // dgrad out: [B][Cg][T+4][H+4][W+4] (zero border kept by the caller)
+  uint4* gzw;          // dgrad out: [B][Cg][T][QP]
+  int B, BP;           // batch, batch padded to a multiple of 16 (MMA N / K)
+  int F1;
+  long long KG;        // K1 / 8
+  long long tiles;     // ceil(KG / 16)
+  int Cg, T, H, W, QP;
+  long long THW;
+  int S;               // forward K splits
+  long long tiles_per_split;
+};
+
+// transposing load of the X tile: smem [kgl][b][8] <- xb[b][kg0 + kgl]   (16 x BP chunks of 16 B), executed by one warp
+__device__ __forceinline__ void fc1_load_x_tile(uint4* dst, const Fc1Bf16Args& a, long long kg0, int lane) {
+  for (int b = lane; b < a.BP; b += 32) {
+    const bool okb = b < a.B;
+#pragma unroll 4
+    for (int kgl = 0; kgl < kF1KG; ++kgl) {
+      const long long kg = kg0 + kgl;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (okb && kg < a.KG) v = __ldg(a.xb + static_cast<long long>(b) * a.KG + kg);
+      dst[kgl * a.BP + b] = v;
+    }
+  }
+}
+
+// MODE 0: forward, 1: data gradient, 2: weight gradient
+template <int MODE>
+__global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int NST = 4;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [4]
+  uint64_t* empty = full + NST;                         // [4]
+  uint64_t* tfull = empty + NST;                        // [2]
+  uint64_t* tempty = tfull + 2;                         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* g_s = smem + 128;                            // G operand (dgrad / wgrad): BP*128 bf16 = up to 64 KB... sized BP*256 B
+  const uint32_t g_bytes = (MODE == 0) ? 0u : static_cast<uint32_t>(a.BP) * 256u;
+  const uint32_t w_bytes = (MODE == 2) ? 0u : kF1KG * kF1J * 16u;           // 32 KB W1s tile (not needed by wgrad)
+  const uint32_t x_bytes = (MODE == 1) ? 0u : kF1KG * static_cast<uint32_t>(a.BP) * 16u;  // X tile (not needed by dgrad)
+  const uint32_t stage_bytes = w_bytes + x_bytes;
+  uint8_t* stage_s = g_s + ((g_bytes + 127u) & ~127u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // accumulator columns per tile: forward / dgrad N = BP, wgrad N = 128; double-buffered
+  const uint32_t ncol = (MODE == 2) ? 128u : static_cast<uint32_t>(a.BP);
+  const uint32_t tmem_cols = (2u * ncol <= 32u) ? 32u : (2u * ncol <= 64u) ? 64u : (2u * ncol <= 128u) ? 128u : (2u * ncol <= 256u) ? 256u : 512u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
+  // stages start zeroed: a partial last tile leaves rows untouched, and stale bits must be finite (0 * NaN = NaN)
+  for (uint32_t i = threadIdx.x; i < (NST * stage_bytes) / 16u; i += kF1Threads) reinterpret_cast<uint4*>(stage_s)[i] = make_uint4(0, 0, 0, 0);
+  tc::fence_proxy_async();
+  if (MODE != 0) {
+    // G operand, once per CTA.  dgrad: B-operand K-major [j/8][b][8 j]; wgrad: A-operand K-major [b/8][j][8 b]
+    uint16_t* gs = reinterpret_cast<uint16_t*>(g_s);
+    for (int idx = threadIdx.x; idx < a.BP * kF1J; idx += kF1Threads) {
+      const int b = idx / kF1J, j = idx - b * kF1J;
+      const float v = (b < a.B && j < a.F1) ? a.g1[static_cast<long long>(b) * a.F1 + j] : 0.f;
+      const int o = (MODE == 1) ? ((j >> 3) * a.BP + b) * 8 + (j & 7) : ((b >> 3) * kF1J + j) * 8 + (b & 7);
+      gs[o] = static_cast<uint16_t>(f2bf(v));
+    }
+    tc::fence_proxy_async();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // tile range of this CTA
+  long long t_begin, t_end;
+  int split = 0;
+  if (MODE == 0) {
+    split = blockIdx.x;
+    t_begin = split * a.tiles_per_split;
+    t_end = min(a.tiles, t_begin + a.tiles_per_split);
+  } else {
+    t_begin = a.tiles * blockIdx.x / gridDim.x;
+    t_end = a.tiles * (blockIdx.x + 1) / gridDim.x;
+  }
+
+  if (warp == 0) {
+    // =============================== producer ===============================
+    uint32_t seq = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++seq) {
+      const uint32_t st = seq % NST;
+      tc::mbar_wait(empty + st, ((seq / NST) & 1u) ^ 1u);
+      uint8_t* dst = stage_s + st * stage_bytes;
+      const long long kg0 = t * kF1KG;
+      if (MODE != 1) {
+        fc1_load_x_tile(reinterpret_cast<uint4*>(dst + w_bytes), a, kg0, lane);
+        tc::fence_proxy_async();
+      }
+      __syncwarp();
+      if (lane == 0) {
+        if (MODE != 2) {
+          const long long left = a.KG - kg0;
+          const uint32_t nkg = static_cast<uint32_t>(left < kF1KG ? left : kF1KG);
+          tc::mbar_arrive_expect_tx(full + st, nkg * kF1J * 16u);
+          tc::bulk_g2s(dst, a.ws + kg0 * kF1J, nkg * kF1J * 16u, full + st);
+        } else {
+          tc::mbar_arrive(full + st);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    const bool leader = tc::elect_one();
+    const uint32_t hi_ver = 1u << 14;
+    const uint32_t stage16 = tc::smem_u32(stage_s) >> 4;
+    const uint32_t g16 = tc::smem_u32(g_s) >> 4;
+    uint32_t seq = 0;
+    if (MODE == 0) {
+      // one accumulator for the whole K range of this split
+      const uint32_t idesc = tc::umma_idesc(128, a.BP, 1, 0, 0);
+      for (long long t = t_begin; t < t_end; ++t, ++seq) {
+        const uint32_t st = seq % NST;
+        tc::mbar_wait(full + st, (seq / NST) & 1u);
+        tc::tc_fence_after();
+        const uint32_t w16 = stage16 + st * (stage_bytes >> 4);
+        const uint32_t x16 = w16 + (w_bytes >> 4);
+#pragma unroll
+        for (int ks = 0; ks < kF1KG / 2; ++ks) {
+          // A = W1s tile K-major: k-groups 2 KB apart (LBO), 8-row groups 128 B apart (SBO)
+          const uint32_t a_lo = ((2048u >> 4) << 16) | ((w16 + 2u * ks * 128u) & 0x3fffu);
+          // B = X tile K-major: k-groups BP*16 B apart, 8-row groups 128 B apart
+          const uint32_t b_lo = (((static_cast<uint32_t>(a.BP) * 16u) >> 4) << 16) | ((x16 + 2u * ks * a.BP) & 0x3fffu);
+          if (leader) tc::umma_bf16_lohi(tmem_base, a_lo, (128u >> 4) | hi_ver, b_lo, (128u >> 4) | hi_ver, idesc, (seq | ks) ? 1u : 0u);
+        }
+        __syncwarp();
+        if (leader) tc::umma_commit(empty + st);
+        __syncwarp();
+      }
+      if (leader) tc::umma_commit(tfull);
+      __syncwarp();
+    } else {
+      const uint32_t idesc = (MODE == 1) ? tc::umma_idesc(128, a.BP, 1, /*A MN*/ 1, /*B K*/ 0)
+                                         : tc::umma_idesc(128, 128, 1, /*A K*/ 0, /*B MN*/ 1);
+      const int nk = (MODE == 1) ? kF1J / 16 : a.BP / 16;  // K steps: over j (dgrad) or over b (wgrad)
+      for (long long t = t_begin; t < t_end; ++t, ++seq) {
+        const uint32_t st = seq % NST;
+        const uint32_t acc = seq & 1u;
+        tc::mbar_wait(full + st, (seq / NST) & 1u);
+        tc::mbar_wait(tempty + acc, ((seq >> 1) & 1u) ^ 1u);
+        tc::tc_fence_after();
+        const uint32_t s16 = stage16 + st * (stage_bytes >> 4);
+        const uint32_t d_tmem = tmem_base + acc * ncol;
+        for (int ks = 0; ks < nk; ++ks) {
+          uint32_t a_lo, a_hi, b_lo, b_hi;
+          if (MODE == 1) {
+            // A = W1s tile MN-major (M = k'): 8-j groups 128 B apart (LBO), k-groups 2 KB apart (SBO); step = 16 j = 256 B
+            a_lo = ((128u >> 4) << 16) | ((s16 + 16u * ks) & 0x3fffu);
+            a_hi = (2048u >> 4) | hi_ver;
+            // B = G [j/8][b][8] K-major: k-groups BP*16 B apart (LBO), 8-b groups 128 B apart (SBO)
+            b_lo = (((static_cast<uint32_t>(a.BP) * 16u) >> 4) << 16) | ((g16 + 2u * ks * a.BP) & 0x3fffu);
+            b_hi = (128u >> 4) | hi_ver;
+          } else {
+            // A = G^T [b/8][j][8] K-major: k-groups 2 KB apart, 8-j groups 128 B apart; step = 16 b = 2 groups
+            a_lo = ((2048u >> 4) << 16) | ((g16 + 2u * ks * 128u) & 0x3fffu);
+            a_hi = (128u >> 4) | hi_ver;
+            // B = X tile [kg][b][8] MN-major (N = k'): 8-b groups 128 B apart (LBO), k-groups BP*16 B apart (SBO)
+            b_lo = ((128u >> 4) << 16) | ((s16 + 16u * ks) & 0x3fffu);
+            b_hi = ((static_cast<uint32_t>(a.BP) * 16u) >> 4) | hi_ver;
+          }
+          if (leader) tc::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, ks ? 1u : 0u);
+        }
+        __syncwarp();
+        if (leader) { tc::umma_commit(empty + st); tc::umma_commit(tfull + acc); }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;  // accumulator row owned by this thread
+    if (MODE == 0) {
+      tc::mbar_wait(tfull, 0);
+      tc::tc_fence_after();
+      const bool any = t_end > t_begin;
+      for (int c0 = 0; c0 < a.BP; c0 += 16) {
+        uint32_t v[16];
+        tc::tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + c0, v);
+        tc::tmem_ld_wait();
+        if (row < a.F1) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c0 + c < a.B) a.partial[(static_cast<long long>(split) * a.B + c0 + c) * a.F1 + row] = any ? __uint_as_float(v[c]) : 0.f;
+        }
+      }
+    } else {
+      uint32_t seq = 0;
+      const long long plane_pad = static_cast<long long>(a.H + 4) * (a.W + 4);
+      for (long long t = t_begin; t < t_end; ++t, ++seq) {
+        const uint32_t acc = seq & 1u;
+        tc::mbar_wait(tfull + acc, (seq >> 1) & 1u);
+        tc::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * ncol;
+        if (MODE == 1) {
+          // row = k' within the tile: k-group kg0 + row/8, channel row%8; columns = batch
+          const long long kg = t * kF1KG + (row >> 3);
+          const int c8 = row & 7;
+          const bool okk = kg < a.KG;
+          const int cg = okk ? static_cast<int>(kg / a.THW) : 0;
+          const long long pos = okk ? kg - cg * a.THW : 0;
+          const int tt = static_cast<int>(pos / (a.H * a.W));
+          const int hw = static_cast<int>(pos - static_cast<long long>(tt) * a.H * a.W);
+          const int hh = hw / a.W, ww = hw - hh * a.W;
+          const long long o_pad = ((static_cast<long long>(cg) * (a.T + 4) + (tt + 2)) * plane_pad +
+                                   static_cast<long long>(hh + 2) * (a.W + 4) + (ww + 2)) * 8 + c8;
+          const long long o_gzw = ((static_cast<long long>(cg) * a.T + tt) * a.QP + static_cast<long long>(hh) * (a.W + 2) + ww) * 8 + c8;
+          const long long sb_pad = static_cast<long long>(a.Cg) * (a.T + 4) * plane_pad * 8;
+          const long long sb_gzw = static_cast<long long>(a.Cg) * a.T * a.QP * 8;
+          uint16_t* ypad = reinterpret_cast<uint16_t*>(a.gz_pad);
+          uint16_t* ygzw = reinterpret_cast<uint16_t*>(a.gzw);
+          const uint16_t* xm = reinterpret_cast<const uint16_t*>(a.xb);
+          for (int c0 = 0; c0 < a.BP; c0 += 16) {
+            uint32_t v[16];
+            tc::tmem_ld_32x16(taddr + c0, v);
+            tc::tmem_ld_wait();
+            if (okk) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const int b = c0 + c;
+                if (b < a.B) {
+                  const uint16_t m = __ldg(xm + (static_cast<long long>(b) * a.KG + kg) * 8 + c8);
+                  // bf16 > 0  <=>  sign bit clear and not zero (activations are finite, post-ReLU)
+                  const float g = ((m & 0x8000u) == 0 && (m & 0x7fffu) != 0) ? __uint_as_float(v[c]) : 0.f;
+                  const uint16_t o = static_cast<uint16_t>(f2bf(g));
+                  ypad[b * sb_pad + o_pad] = o;
+                  ygzw[b * sb_gzw + o_gzw] = o;
+                }
+              }
+            }
+          }
+        } else {
+          // row = feature j; columns = (kgl, c8) -> dw[j][(cg*8+c8)*THW + pos]
+          float vals[128];
+#pragma unroll
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tc::tmem_ld_32x32(taddr + c0, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) vals[c0 + c] = __uint_as_float(v[c]);
+          }
+          if (row < a.F1) {
+            const long long kg0 = t * kF1KG;
+            const long long K1 = a.KG * 8;
+            float* drow = a.dw + static_cast<long long>(row) * K1;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+#pragma unroll
+              for (int kgl = 0; kgl < kF1KG; ++kgl) {
+                const long long kg = kg0 + kgl;
+                if (kg < a.KG) {
+                  const int cg = static_cast<int>(kg / a.THW);
+                  const long long pos = kg - cg * a.THW;
+                  drow[(cg * 8 + c8) * a.THW + pos] = vals[kgl * 8 + c8];
+                }
+              }
+            }
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty + acc);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static int fc1_bf16_fill(Fc1Bf16Args& a, int B, int F1, int Cg, int T, int H, int W) {
+  PVB_REQUIRE(B > 0 && B <= 256, "fc1_bf16: batch %d not in 1..256 (split larger batches)", B);
+  PVB_REQUIRE(F1 > 0 && F1 <= 128, "fc1_bf16: fc1_output_features=%d > 128 is not supported by the tensor-core path", F1);
+  PVB_REQUIRE(Cg > 0 && T > 0 && H > 0 && W > 0, "fc1_bf16: bad feature geometry");
+  a.B = B; a.BP = round_up(B, 16); a.F1 = F1;
+  a.Cg = Cg; a.T = T; a.H = H; a.W = W;
+  a.THW = static_cast<long long>(T) * H * W;
+  a.KG = static_cast<long long>(Cg) * a.THW;
+  a.tiles = ceil_div(a.KG, static_cast<long long>(kF1KG));
+  a.QP = static_cast<int>(round_up(static_cast<long long>(H) * (W + 2), 128LL));
+  return PVB200_OK;
+}
+
+template <int MODE>
+static int fc1_bf16_launch(const Fc1Bf16Args& a, long long grid, cudaStream_t st) {
+  const size_t g_bytes = (MODE == 0) ? 0 : static_cast<size_t>(a.BP) * 256;
+  const size_t w_bytes = (MODE == 2) ? 0 : static_cast<size_t>(kF1KG) * kF1J * 16;
+  const size_t x_bytes = (MODE == 1) ? 0 : static_cast<size_t>(kF1KG) * a.BP * 16;
+  const size_t smem = 128 + round_up(g_bytes, static_cast<size_t>(128)) + 4 * (w_bytes + x_bytes);
+  PVB_REQUIRE(smem <= 227 * 1024, "fc1_bf16: batch %d needs %zu B of shared memory", a.B, smem);
+  PVB_CUDA(cudaFuncSetAttribute(fc1_bf16_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fc1_bf16_kernel<MODE><<<static_cast<unsigned>(grid), kF1Threads, smem, st>>>(a);
+  PVB_LAUNCHED("fc1_bf16");
+  return PVB200_OK;
+}
+
+constexpr int kF1FwdSplits = 148;
+
+}  // namespace pvb
+
+extern "C" {
+
+size_t pvb200_fc1_bf16_shadow_bytes(int Cg, int T, int H, int W) {
+  return static_cast<size_t>(Cg) * T * H * W * pvb::kF1J * 16;
+}
+
+int pvb200_fc1_make_shadow_bf16(const float* w1, uint16_t* shadow, int F1, int Cg, int T, int H, int W,
+                                pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(w1 && shadow && F1 > 0 && F1 <= kF1J && Cg > 0 && T > 0 && H > 0 && W > 0, "fc1_make_shadow: bad argument");
+  const long long THW = static_cast<long long>(T) * H * W;
+  dim3 grid(static_cast<unsigned>(ceil_div(THW, 32LL)), kF1J / 32, Cg);
+  fc1_make_shadow_kernel<<<grid, 256, 0, as_stream(stream)>>>(w1, reinterpret_cast<uint4*>(shadow), F1, THW, Cg);
+  PVB_LAUNCHED("fc1_make_shadow");
+  return PVB200_OK;
+}
+
+int pvb200_fc1_fwd_bf16_splits(void) { return pvb::kF1FwdSplits; }
+
+/* partial[s][b][j] (s < pvb200_fc1_fwd_bf16_splits()) = split-K partial sums of xb . W1s^T; summed by pvb200_head_fwd_f32's
+ * tail (pass partials as the head workspace with x = NULL) */
+int pvb200_fc1_fwd_bf16(const uint16_t* xb, const uint16_t* shadow, float* partial, int B, int F1, int Cg, int T, int H,
+                        int W, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(xb && shadow && partial, "fc1_fwd_bf16: null pointer");
+  Fc1Bf16Args a{};
+  int rc = fc1_bf16_fill(a, B, F1, Cg, T, H, W);
+  if (rc) return rc;
+  a.ws = reinterpret_cast<const uint4*>(shadow); a.xb = reinterpret_cast<const uint4*>(xb); a.partial = partial;
+  a.S = kF1FwdSplits;
+  a.tiles_per_split = ceil_div(a.tiles, static_cast<long long>(a.S));
+  return fc1_bf16_launch<0>(a, a.S, as_stream(stream));
+}
+
+int pvb200_fc1_dgrad_bf16(const float* g1, const uint16_t* shadow, const uint16_t* xb, uint16_t* gz_pad, uint16_t* gzw,
+                          int B, int F1, int Cg, int T, int H, int W, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(g1 && shadow && xb && gz_pad && gzw, "fc1_dgrad_bf16: null pointer");
+  Fc1Bf16Args a{};
+  int rc = fc1_bf16_fill(a, B, F1, Cg, T, H, W);
+  if (rc) return rc;
+  a.ws = reinterpret_cast<const uint4*>(shadow); a.xb = reinterpret_cast<const uint4*>(xb); a.g1 = g1;
+  a.gz_pad = reinterpret_cast<uint4*>(gz_pad); a.gzw = reinterpret_cast<uint4*>(gzw);
+  const int sms = sm_count();
+  PVB_REQUIRE(sms > 0, "fc1_dgrad_bf16: no CUDA device");
+  return fc1_bf16_launch<1>(a, a.tiles < sms ? a.tiles : sms, as_stream(stream));
+}
+
+int pvb200_fc1_wgrad_bf16(const float* g1, const uint16_t* xb, float* dw1, int B, int F1, int Cg, int T, int H, int W,
+                          pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(g1 && xb && dw1, "fc1_wgrad_bf16: null pointer");
+  Fc1Bf16Args a{};
+  int rc = fc1_bf16_fill(a, B, F1, Cg, T, H, W);
+  if (rc) return rc;
+  a.xb = reinterpret_cast<const uint4*>(xb); a.g1 = g1; a.dw = dw1;
+  const int sms = sm_count();
+  PVB_REQUIRE(sms > 0, "fc1_wgrad_bf16: no CUDA device");
+  return fc1_bf16_launch<2>(a, a.tiles < sms ? a.tiles : sms, as_stream(stream));
+}
+
+}  // extern "C"

@@ -708,7 +708,7 @@ static int check_head(const pvb200_head_t* h) {
   PVB_REQUIRE(h->NPV >= 0 && h->NNWP >= 0, "head: bad branch sizes");
   PVB_REQUIRE(h->NPV == 0 || (h->pv && h->pv_ns > 0 && h->NPV % h->pv_ns == 0), "head: bad PV-history description");
   PVB_REQUIRE(h->NNWP == 0 || (h->nwp && h->wn && h->bn && h->FNWP > 0), "head: NWP branch needs nwp, wn, bn");
-  PVB_REQUIRE(h->w1 && h->b1 && h->w2 && h->b2 && h->w3 && h->b3 && h->w4 && h->b4 && h->x, "head: null parameter");
+  PVB_REQUIRE(h->w1 && h->b1 && h->w2 && h->b2 && h->w3 && h->b3 && h->w4 && h->b4, "head: null parameter");
   return PVB200_OK;
 }
 
@@ -724,10 +724,27 @@ size_t pvb200_head_fwd_workspace_bytes(int B, int F1, long long K1) {
   return static_cast<size_t>(p.S) * B * F1 * sizeof(float);
 }
 
+/* tail only: h->workspace holds S split-K partials [S][B][F1] of fc1 (e.g. from pvb200_fc1_fwd_bf16); fills h1, cat, h3, out */
+int pvb200_head_tail_fwd_f32(const pvb200_head_t* h, int S, pvb200_stream_t stream) {
+  using namespace pvb;
+  int rc = check_head(h);
+  if (rc) return rc;
+  PVB_REQUIRE(h->h1 && h->cat && h->h3 && h->out && S > 0, "head_tail_fwd: null output");
+  PVB_REQUIRE(h->workspace && h->workspace_bytes >= static_cast<size_t>(S) * h->B * h->F1 * sizeof(float),
+              "head_tail_fwd: partials buffer too small");
+  const int NCAT = h->F2 + h->NPV + (h->NNWP > 0 ? h->FNWP : 0);
+  const size_t smem = static_cast<size_t>(h->F1 + NCAT + h->F3 + h->NNWP + 8 * h->F1) * sizeof(float);
+  PVB_REQUIRE(smem <= 48 * 1024, "head_tail_fwd: feature sizes too large for the tail kernel (%zu B smem)", smem);
+  head_tail_fwd_kernel<<<h->B, kHeadThreads, smem, as_stream(stream)>>>(*h, static_cast<const float*>(h->workspace), S);
+  PVB_LAUNCHED("head_tail_fwd");
+  return PVB200_OK;
+}
+
 int pvb200_head_fwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
   using namespace pvb;
   int rc = check_head(h);
   if (rc) return rc;
+  PVB_REQUIRE(h->x, "head_fwd: null features");
   PVB_REQUIRE(h->h1 && h->cat && h->h3 && h->out, "head_fwd: null output");
   const Fc1Plan p = fc1_plan(h->B, h->F1, h->K1);
   const size_t need = static_cast<size_t>(p.S) * h->B * h->F1 * sizeof(float);
@@ -757,12 +774,22 @@ int pvb200_head_fwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
   return PVB200_OK;
 }
 
-int pvb200_head_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
+static int head_bwd_impl(const pvb200_head_t* h, bool with_fc1, pvb200_stream_t stream);
+
+int pvb200_head_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) { return head_bwd_impl(h, true, stream); }
+
+/* tail only: everything except fc1's weight / data gradient (g_h1 and db1 ARE produced); dw1 and x may be NULL */
+int pvb200_head_tail_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) { return head_bwd_impl(h, false, stream); }
+
+}  // extern "C"
+
+static int head_bwd_impl(const pvb200_head_t* h, bool with_fc1, pvb200_stream_t stream) {
   using namespace pvb;
   int rc = check_head(h);
   if (rc) return rc;
   PVB_REQUIRE(h->h1 && h->cat && h->h3 && h->g_out && h->g_h3 && h->g_cat && h->g_h1, "head_bwd: null buffer");
-  PVB_REQUIRE(h->dw1 && h->db1 && h->dw2 && h->db2 && h->dw3 && h->db3 && h->dw4 && h->db4, "head_bwd: null grad");
+  PVB_REQUIRE(h->db1 && h->dw2 && h->db2 && h->dw3 && h->db3 && h->dw4 && h->db4, "head_bwd: null grad");
+  PVB_REQUIRE(!with_fc1 || (h->dw1 && h->x), "head_bwd: null fc1 gradient / features");
   PVB_REQUIRE(h->NNWP == 0 || (h->dwn && h->dbn), "head_bwd: NWP branch needs dwn, dbn");
   cudaStream_t st = as_stream(stream);
   const int NCAT = h->F2 + h->NPV + (h->NNWP > 0 ? h->FNWP : 0);
@@ -784,10 +811,11 @@ int pvb200_head_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
     if ((rc = small(h->g_cat + h->F2 + h->NPV, NCAT, h->nwp, h->NNWP, h->dwn, h->dbn, h->FNWP, h->NNWP))) return rc;
   // fc1 bias gradient (I = 0 columns: only the db part of the kernel runs)
   {
-    linear_wgrad_small_kernel<<<ceil_div(h->F1, 256), 256, 0, st>>>(h->g_h1, h->F1, h->g_h1, h->F1, h->dw1, h->db1, h->B,
+    linear_wgrad_small_kernel<<<ceil_div(h->F1, 256), 256, 0, st>>>(h->g_h1, h->F1, h->g_h1, h->F1, h->db1, h->db1, h->B,
                                                                     h->F1, 0);
     PVB_LAUNCHED("fc1_bias_grad");
   }
+  if (!with_fc1) return PVB200_OK;
   const int vec = vec4_ok(h->x, h->K1) && vec4_ok(h->w1, h->K1) && vec4_ok(h->dw1, h->K1) && (!h->g_x || vec4_ok(h->g_x, h->K1));
   const int njt = ceil_div(h->F1, kFc1JT);
   const long long kt = ceil_div(h->K1, 128LL);
@@ -823,4 +851,4 @@ int pvb200_head_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
   return PVB200_OK;
 }
 
-}  // extern "C"
+

@@ -74,6 +74,15 @@ SIGNATURES = {
     "pvb200_head_fwd_workspace_bytes": (c_size_t, [c_int, c_int, c_ll]),
     "pvb200_head_fwd_f32": (c_int, [C.POINTER(Head), c_void_p]),
     "pvb200_head_bwd_f32": (c_int, [C.POINTER(Head), c_void_p]),
+    "pvb200_head_tail_fwd_f32": (c_int, [C.POINTER(Head), c_int, c_void_p]),
+    "pvb200_head_tail_bwd_f32": (c_int, [C.POINTER(Head), c_void_p]),
+    "pvb200_fc1_bf16_shadow_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "pvb200_fc1_make_shadow_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_fc1_fwd_bf16_splits": (c_int, []),
+    "pvb200_fc1_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_fc1_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_void_p]),
+    "pvb200_fc1_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_l1_loss_fwd_f32": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pvb200_l1_loss_bwd_f32": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pvb200_adam_step_f32": (c_int, [c_int, C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p),

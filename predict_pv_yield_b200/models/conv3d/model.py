@@ -179,11 +179,19 @@ class Model(BaseModel):
         batch_size = sat_data.shape[0]
 
         # Conv3d + ReLU stack, flattened in NCDHW order (model.py:117-122)
-        encoder = ops.EncoderBf16Fn if self.precision == "bf16" else ops.EncoderFn
-        out = encoder.apply(sat_data, mean, std, *self._conv_params())
-        if out.shape[1] != self.cnn_output_size:
+        # tensor-core fc1 needs B <= 256, fc1_output_features <= 128 and channels in whole (even) groups of 8
+        bf16_head = (self.precision == "bf16" and batch_size <= 256 and self.fc1_output_features <= 128
+                     and self.sat_conv0.out_channels % 16 == 0)
+        link = {} if bf16_head else None
+        if self.precision == "bf16":
+            out = ops.EncoderBf16Fn.apply(link, sat_data, mean, std, *self._conv_params())
+            n_feat = out[0].numel() if bf16_head else out.shape[1]
+        else:
+            out = ops.EncoderFn.apply(sat_data, mean, std, *self._conv_params())
+            n_feat = out.shape[1]
+        if n_feat != self.cnn_output_size:
             raise RuntimeError(
-                f"satellite cube {tuple(sat_data.shape)} gives {out.shape[1]} conv features, "
+                f"satellite cube {tuple(sat_data.shape)} gives {n_feat} conv features, "
                 f"model expects cnn_output_size={self.cnn_output_size}"
             )
 
@@ -203,10 +211,11 @@ class Model(BaseModel):
             nwp_data = sel(x["nwp"]).float().flatten(start_dim=1).contiguous()
             wn, bn = self.fc_nwp.weight, self.fc_nwp.bias
 
-        out = ops.HeadFn.apply(
+        head_args = (
             out, pv_yield_history, nwp_data,
             self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, wn, bn,
             self.fc3.weight, self.fc3.bias, self.fc4.weight, self.fc4.bias,
         )
+        out = ops.HeadBf16Fn.apply(link, *head_args) if bf16_head else ops.HeadFn.apply(*head_args)
         out = out.reshape(batch_size, self.forecast_len)
         return out

@@ -405,7 +405,10 @@ class EncoderBf16Fn(torch.autograd.Function):
     zero-padded gradient) writes the next gradient in BOTH layouts it is needed in, with the ReLU mask fused."""
 
     @staticmethod
-    def forward(ctx, sat, mean, std, *wb):
+    def forward(ctx, link, sat, mean, std, *wb):
+        """``link``: None -> return fp32 NCDHW features (consumed by the fp32 ``HeadFn``); a dict -> return the last
+        activation itself in blocked bf16 (consumed by ``HeadBf16Fn``, which hands the gradient back through
+        ``link["gz"]`` already in the two layouts the conv backward needs)."""
         n_layers = len(wb) // 2
         if sat.dtype == torch.int16:
             x = sat_normalise_blocked_bf16(sat, mean, std)
@@ -418,6 +421,9 @@ class EncoderBf16Fn(torch.autograd.Function):
         ctx.save_for_backward(*wb, *acts)
         ctx.n_layers = n_layers
         ctx.channels = [wb[2 * l].shape[1] for l in range(n_layers)] + [wb[-2].shape[0]]
+        ctx.link = link
+        if link is not None:
+            return acts[-1]
         feats = from_blocked_bf16(acts[-1], ctx.channels[-1])
         return feats.view(sat.shape[0], -1)
 
@@ -428,9 +434,14 @@ class EncoderBf16Fn(torch.autograd.Function):
         wb, acts = saved[: 2 * n], saved[2 * n:]
         ch = ctx.channels
         B, _, To, Ho, Wo, _ = acts[-1].shape
-        g = g.contiguous().view(B, ch[-1], To, Ho, Wo)
-        gz_pad = to_blocked_bf16(g, pad=2) if n > 1 else None
-        gzw = to_gzw_bf16(g)
+        if ctx.link is not None:
+            if "gz" not in ctx.link:
+                raise RuntimeError("EncoderBf16Fn: the blocked activation must be consumed by HeadBf16Fn (private protocol)")
+            gz_pad, gzw = ctx.link.pop("gz")
+        else:
+            g = g.contiguous().view(B, ch[-1], To, Ho, Wo)
+            gz_pad = to_blocked_bf16(g, pad=2) if n > 1 else None
+            gzw = to_gzw_bf16(g)
         grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
         for l in range(n - 1, -1, -1):
             dw, db = conv3d_wgrad_bf16(acts[l], gzw, ch[l], ch[l + 1])
@@ -440,7 +451,7 @@ class EncoderBf16Fn(torch.autograd.Function):
                     gz_pad, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=2, also_gzw=True)
                 else:  # the gradient w.r.t. layer 0's output only feeds layer 0's weight gradient
                     _, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=0, also_gzw=True)
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
 class HeadFn(torch.autograd.Function):
@@ -532,6 +543,97 @@ class HeadFn(torch.autograd.Function):
             rc = L.pvb200_head_bwd_f32(C.byref(h), _stream())
         _lib.check(rc, "head_bwd")
         return g_x, None, None, dw1, db1, dw2, db2, dwn, dbn, dw3, db3, dw4, db4
+
+
+_persistent: Dict[Tuple, torch.Tensor] = {}
+
+
+def _zero_bordered(name: str, shape: Tuple[int, ...], device: torch.device) -> torch.Tensor:
+    """A bf16 buffer allocated ONCE with zeros and reused every step: the kernels that fill it only ever write the
+    interior (valid positions), so the zero border / wrap columns never need a per-step memset."""
+    key = (name, tuple(shape), device.index)
+    buf = _persistent.get(key)
+    if buf is None:
+        buf = torch.zeros(shape, dtype=torch.bfloat16, device=device)
+        _persistent[key] = buf
+    return buf
+
+
+class HeadBf16Fn(torch.autograd.Function):
+    """FC head of the bf16 mode: fc1 as weight-streaming tcgen05 GEMMs over a bf16 shadow of the fp32 master weight,
+    the rest of the head (fc2, concat, fc_nwp, fc3, fc4) in the fused fp32 tail kernels.
+
+    forward(link, act, pv_hist|None, nwp|None, w1,b1,w2,b2,wn|None,bn|None,w3,b3,w4,b4); ``act`` is the last conv
+    activation in blocked bf16 [B,Cg,T,H,W,8] from ``EncoderBf16Fn``.  The gradient w.r.t. ``act`` is handed to the
+    encoder through ``link["gz"]`` (ReLU mask fused, both layouts); the tensor returned to autograd is a placeholder."""
+
+    @staticmethod
+    def forward(ctx, link, act, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4):
+        L = _lib.load()
+        _need_cuda(act, "activation", torch.bfloat16)
+        B, Cg, T, H, W, _ = act.shape
+        feats_stub = act.view(B, -1)  # only its shape is used by the descriptor
+        h, ncat = HeadFn._desc(feats_stub, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4)
+        h.x = None
+        dev = act.device
+        shadow = _workspace(f"fc1_shadow_{w1.data_ptr()}", L.pvb200_fc1_bf16_shadow_bytes(Cg, T, H, W), dev)
+        with _timed("fc1_make_shadow_bf16", 0.0, 4.0 * w1.numel() + 2.0 * w1.numel()):
+            rc = L.pvb200_fc1_make_shadow_bf16(_p(w1), _p(shadow), h.F1, Cg, T, H, W, _stream())
+        _lib.check(rc, "fc1_make_shadow_bf16")
+        S = int(L.pvb200_fc1_fwd_bf16_splits())
+        partial = _workspace("head", S * B * h.F1 * 4, dev)
+        with _timed("fc1_fwd_bf16", 2.0 * B * h.F1 * h.K1, 2.0 * (B * h.K1 + 128 * h.K1)):
+            rc = L.pvb200_fc1_fwd_bf16(_p(act), _p(shadow), _p(partial), B, h.F1, Cg, T, H, W, _stream())
+        _lib.check(rc, "fc1_fwd_bf16")
+        h1 = torch.empty((B, h.F1), dtype=torch.float32, device=dev)
+        cat = torch.empty((B, ncat), dtype=torch.float32, device=dev)
+        h3 = torch.empty((B, h.F3), dtype=torch.float32, device=dev)
+        out = torch.empty((B, h.FO), dtype=torch.float32, device=dev)
+        h.h1, h.cat, h.h3, h.out = h1.data_ptr(), cat.data_ptr(), h3.data_ptr(), out.data_ptr()
+        h.workspace, h.workspace_bytes = partial.data_ptr(), partial.numel()
+        _lib.check(L.pvb200_head_tail_fwd_f32(C.byref(h), S, _stream()), "head_tail_fwd")
+        ctx.save_for_backward(act, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4, h1, cat, h3)
+        ctx.link = link
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        L = _lib.load()
+        act, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4, h1, cat, h3 = ctx.saved_tensors
+        B, Cg, T, H, W, _ = act.shape
+        h, ncat = HeadFn._desc(act.view(B, -1), pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4)
+        h.x = None
+        dev = act.device
+        g_out = g_out.contiguous()
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)  # noqa: E731
+        g_h3, g_cat, g_h1 = e(B, h.F3), e(B, ncat), e(B, h.F1)
+        dw1, db1, dw2, db2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2), torch.empty_like(b2)
+        dw3, db3, dw4, db4 = torch.empty_like(w3), torch.empty_like(b3), torch.empty_like(w4), torch.empty_like(b4)
+        dwn = torch.empty_like(wn) if nwp is not None else None
+        dbn = torch.empty_like(bn) if nwp is not None else None
+        h.h1, h.cat, h.h3 = h1.data_ptr(), cat.data_ptr(), h3.data_ptr()
+        h.g_out, h.g_h3, h.g_cat, h.g_h1, h.g_x = g_out.data_ptr(), g_h3.data_ptr(), g_cat.data_ptr(), g_h1.data_ptr(), None
+        h.dw1, h.db1, h.dw2, h.db2 = None, db1.data_ptr(), dw2.data_ptr(), db2.data_ptr()
+        h.dw3, h.db3, h.dw4, h.db4 = dw3.data_ptr(), db3.data_ptr(), dw4.data_ptr(), db4.data_ptr()
+        h.dwn, h.dbn = _p(dwn), _p(dbn)
+        _lib.check(L.pvb200_head_tail_bwd_f32(C.byref(h), _stream()), "head_tail_bwd")
+        with _timed("fc1_wgrad_bf16", 2.0 * B * h.F1 * h.K1, 2.0 * B * h.K1 + 4.0 * h.F1 * h.K1):
+            rc = L.pvb200_fc1_wgrad_bf16(_p(g_h1), _p(act), _p(dw1), B, h.F1, Cg, T, H, W, _stream())
+        _lib.check(rc, "fc1_wgrad_bf16")
+        g_act = None
+        if ctx.needs_input_grad[1]:
+            QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(H + 2, W + 2))
+            gz_pad = _zero_bordered("gz_pad_head", (B, Cg, T + 4, H + 4, W + 4, 8), dev)
+            gzw = _zero_bordered("gzw_head", (B, Cg, T, QP, 8), dev)
+            shadow = _workspace(f"fc1_shadow_{w1.data_ptr()}", L.pvb200_fc1_bf16_shadow_bytes(Cg, T, H, W), dev)
+            with _timed("fc1_dgrad_bf16", 2.0 * B * h.F1 * h.K1, 2.0 * (128 * h.K1 + 4 * B * h.K1)):
+                rc = L.pvb200_fc1_dgrad_bf16(_p(g_h1), _p(shadow), _p(act), _p(gz_pad), _p(gzw), B, h.F1, Cg, T, H, W, _stream())
+            _lib.check(rc, "fc1_dgrad_bf16")
+            if ctx.link is None:
+                raise RuntimeError("HeadBf16Fn: no link to hand the activation gradient to EncoderBf16Fn")
+            ctx.link["gz"] = (gz_pad, gzw)
+            g_act = torch.empty_like(act)  # placeholder: the real gradient travels through the link
+        return None, g_act, None, None, dw1, db1, dw2, db2, dwn, dbn, dw3, db3, dw4, db4
 
 
 class StepLossFn(torch.autograd.Function):

@@ -165,3 +165,60 @@ def test_bf16_model_within_tolerance_of_oracle(dev, name):
     for (k, p), (_, q) in zip(m.named_parameters(), om.named_parameters()):
         e = O.normalised_max_err(p.grad, q.grad)
         assert e <= 1e-1, (k, e)  # gradients through bf16 activations: sanity gate (same direction, same scale)
+
+
+FC1_CASES = [
+    # B, C, T, H, W, F1
+    (5, 16, 3, 5, 6, 24),      # KG = 180: partial last tile; B padded 5 -> 16; F1 < 128
+    (33, 32, 2, 4, 4, 128),    # B padded 33 -> 48
+    (32, 32, 3, 8, 8, 128),
+]
+
+
+@pytest.mark.parametrize("case", FC1_CASES)
+def test_fc1_bf16_kernels(ops, dev, case):
+    """fc1 forward / data gradient / weight gradient on the tensor cores against torch fp64 on bf16-rounded operands."""
+    import ctypes as C
+
+    from predict_pv_yield_b200 import lib
+
+    L = lib.load()
+    B, Cc, T, H, W, F1 = case
+    Cg = Cc // 8
+    K1 = Cc * T * H * W
+    g = torch.Generator().manual_seed(6)
+    act = F.relu(r16(torch.randn((B, Cc, T, H, W), generator=g)))       # post-ReLU activation, NCDHW
+    w1 = torch.randn((F1, K1), generator=g) / np.sqrt(K1)                 # reference layout (k = NCDHW flatten)
+    g1 = torch.randn((B, F1), generator=g)
+    stream = torch.cuda.current_stream().cuda_stream
+    actb = ops.to_blocked_bf16(act.to(dev))
+    w1d, g1d = w1.to(dev), g1.to(dev)
+    shadow = torch.empty(L.pvb200_fc1_bf16_shadow_bytes(Cg, T, H, W), dtype=torch.uint8, device=dev)
+    lib.check(L.pvb200_fc1_make_shadow_bf16(w1d.data_ptr(), shadow.data_ptr(), F1, Cg, T, H, W, stream), "shadow")
+    # shadow layout: [kg][128][8] with kg = cg*THW + pos, zero rows j >= F1
+    sh = shadow.view(torch.bfloat16).view(Cg * T * H * W, 128, 8).float().cpu()
+    ref = torch.zeros((Cg, T * H * W, 128, 8))
+    ref[:, :, :F1, :] = r16(w1).view(F1, Cg, 8, T * H * W).permute(1, 3, 0, 2)
+    assert torch.equal(sh, ref.view(-1, 128, 8))
+    # forward: sum of the split-K partials == x . W^T
+    S = L.pvb200_fc1_fwd_bf16_splits()
+    partial = torch.empty((S, B, F1), dtype=torch.float32, device=dev)
+    lib.check(L.pvb200_fc1_fwd_bf16(actb.data_ptr(), shadow.data_ptr(), partial.data_ptr(), B, F1, Cg, T, H, W, stream), "fwd")
+    want = act.reshape(B, K1).double() @ r16(w1).double().t()
+    assert O.normalised_max_err(partial.sum(0), want) <= 1e-5
+    # weight gradient (fp32, reference layout): g1 is rounded to bf16 by the kernel
+    dw = torch.empty((F1, K1), dtype=torch.float32, device=dev)
+    lib.check(L.pvb200_fc1_wgrad_bf16(g1d.data_ptr(), actb.data_ptr(), dw.data_ptr(), B, F1, Cg, T, H, W, stream), "wgrad")
+    want_dw = r16(g1).double().t() @ act.reshape(B, K1).double()
+    assert O.normalised_max_err(dw, want_dw) <= 1e-5
+    # data gradient with the ReLU mask, in both layouts
+    QP = L.pvb200_conv3d_wgrad_bf16_gz_plane(H + 2, W + 2)
+    gz_pad = torch.zeros((B, Cg, T + 4, H + 4, W + 4, 8), dtype=torch.bfloat16, device=dev)
+    gzw = torch.zeros((B, Cg, T, QP, 8), dtype=torch.bfloat16, device=dev)
+    lib.check(L.pvb200_fc1_dgrad_bf16(g1d.data_ptr(), shadow.data_ptr(), actb.data_ptr(), gz_pad.data_ptr(), gzw.data_ptr(),
+                                      B, F1, Cg, T, H, W, stream), "dgrad")
+    want_gx = ((r16(g1).double() @ r16(w1).double()).view(B, Cc, T, H, W)) * (act > 0).double()
+    got = ops.from_blocked_bf16(gz_pad[:, :, 2:-2, 2:-2, 2:-2].contiguous(), Cc)
+    assert O.normalised_max_err(got, want_gx) <= BF16_TOL
+    assert float(gz_pad.float().abs().sum()) == pytest.approx(float(got.abs().sum()), rel=1e-3)  # border stayed zero
+    assert torch.equal(gzw, ops.to_gzw_bf16(got))
