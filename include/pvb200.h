@@ -187,6 +187,11 @@ int pvb200_head_tail_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream);
 size_t pvb200_fc1_bf16_shadow_bytes(int Cg, int T, int H, int W);
 int pvb200_fc1_make_shadow_bf16(const float* w1, uint16_t* shadow, int F1, int Cg, int T, int H, int W,
                                 pvb200_stream_t stream);
+/* Adam step on fc1.weight (same arithmetic as pvb200_adam_step_f32) that also rewrites the bf16 shadow in the same pass */
+int pvb200_adam_fc1_shadow(float* w1, const float* grad, float* exp_avg, float* exp_avg_sq, uint16_t* shadow,
+                           int F1, int Cg, int T, int H, int W,
+                           float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                           pvb200_stream_t stream);
 int pvb200_fc1_fwd_bf16_splits(void);
 int pvb200_fc1_fwd_bf16(const uint16_t* xb, const uint16_t* shadow, float* partial, int B, int F1, int Cg, int T, int H,
                         int W, pvb200_stream_t stream);

@@ -16,6 +16,8 @@
 // [k-group][row][8] form by the producer warp.  fp32 accumulation in TMEM; the forward writes split-K partials for the
 // existing fused tail kernel, the data gradient fuses the ReLU mask and writes the two layouts the conv backward
 // consumes, the weight gradient writes fp32 in the REFERENCE layout [128][K1] (what Adam / the all-reduce see).
+#include <math.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -53,6 +55,58 @@ fc1_make_shadow_kernel(const float* __restrict__ w, uint4* __restrict__ ws, int 
     o.z = f2bf(tile[4][tx][pp]) | (f2bf(tile[5][tx][pp]) << 16);
     o.w = f2bf(tile[6][tx][pp]) | (f2bf(tile[7][tx][pp]) << 16);
     ws[(cg * THW + pos) * kF1J + j] = o;
+  }
+}
+
+// ---- Adam on fc1.weight fused with the shadow refresh ------------------------------------------------------------
+// Same arithmetic as adam_multi_kernel (loss_adam.cu; torch.optim.Adam single-tensor update, base_model.py:255-257),
+// walked in the shadow's tile order so that the freshly updated weights are written out a second time as the bf16
+// shadow [kg][128][8] in the same pass: the 565 MB master weight is not re-read by a separate conversion kernel.
+struct AdamFc1Scalars {
+  float beta1, beta2, one_minus_beta1, one_minus_beta2, eps, neg_step_size, bc2_sqrt, grad_scale;
+};
+__global__ void __launch_bounds__(256)
+adam_fc1_shadow_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       uint4* __restrict__ ws, int F1, long long THW, int Cg, const AdamFc1Scalars s) {
+  __shared__ float tile[8][32][33];
+  const long long pos0 = static_cast<long long>(blockIdx.x) * 32;
+  const int j0 = blockIdx.y * 32;
+  const int cg = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long K1 = static_cast<long long>(Cg) * 8 * THW;
+  const long long pos = pos0 + tx;
+#pragma unroll
+  for (int c8 = 0; c8 < 8; ++c8) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int jj = ty + 8 * r;
+      const int j = j0 + jj;
+      float pn = 0.f;
+      if (j < F1 && pos < THW) {
+        const long long i = static_cast<long long>(j) * K1 + (cg * 8 + c8) * THW + pos;
+        float gg = __ldcs(g + i) * s.grad_scale;
+        float mm = m[i], vv = v[i];
+        pn = p[i];
+        mm = fmaf(gg - mm, s.one_minus_beta1, mm);
+        vv = fmaf(s.one_minus_beta2 * gg, gg, vv * s.beta2);
+        const float denom = __fdiv_rn(sqrtf(vv), s.bc2_sqrt) + s.eps;
+        pn = fmaf(s.neg_step_size, __fdiv_rn(mm, denom), pn);
+        p[i] = pn; m[i] = mm; v[i] = vv;
+      }
+      tile[c8][jj][tx] = pn;
+    }
+  }
+  __syncthreads();
+  for (int pp = ty; pp < 32; pp += 8) {
+    const long long q = pos0 + pp;
+    if (q >= THW) continue;
+    const int j = j0 + tx;
+    uint4 o;
+    o.x = f2bf(tile[0][tx][pp]) | (f2bf(tile[1][tx][pp]) << 16);
+    o.y = f2bf(tile[2][tx][pp]) | (f2bf(tile[3][tx][pp]) << 16);
+    o.z = f2bf(tile[4][tx][pp]) | (f2bf(tile[5][tx][pp]) << 16);
+    o.w = f2bf(tile[6][tx][pp]) | (f2bf(tile[7][tx][pp]) << 16);
+    ws[(cg * THW + q) * kF1J + j] = o;
   }
 }
 
@@ -104,6 +158,9 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
   const uint32_t x_bytes = (MODE == 1) ? 0u : kF1KG * static_cast<uint32_t>(a.BP) * 16u;  // X tile (not needed by dgrad)
   const uint32_t stage_bytes = w_bytes + x_bytes;
   uint8_t* stage_s = g_s + ((g_bytes + 127u) & ~127u);
+  // epilogue staging (transposes the accumulator tile so that global stores are wide and contiguous):
+  //   dgrad: bf16 [BP][128 rows = (kgl, c8)]      wgrad: fp32 [128 cols = (c8, kgl)][129] (j fastest, padded)
+  uint8_t* epi_s = stage_s + NST * stage_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // accumulator columns per tile: forward / dgrad N = BP, wgrad N = 128; double-buffered
@@ -264,75 +321,93 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
         tc::mbar_wait(tfull + acc, (seq >> 1) & 1u);
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * ncol;
+        const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
         if (MODE == 1) {
-          // row = k' within the tile: k-group kg0 + row/8, channel row%8; columns = batch
-          const long long kg = t * kF1KG + (row >> 3);
-          const int c8 = row & 7;
-          const bool okk = kg < a.KG;
-          const int cg = okk ? static_cast<int>(kg / a.THW) : 0;
-          const long long pos = okk ? kg - cg * a.THW : 0;
-          const int tt = static_cast<int>(pos / (a.H * a.W));
-          const int hw = static_cast<int>(pos - static_cast<long long>(tt) * a.H * a.W);
-          const int hh = hw / a.W, ww = hw - hh * a.W;
-          const long long o_pad = ((static_cast<long long>(cg) * (a.T + 4) + (tt + 2)) * plane_pad +
-                                   static_cast<long long>(hh + 2) * (a.W + 4) + (ww + 2)) * 8 + c8;
-          const long long o_gzw = ((static_cast<long long>(cg) * a.T + tt) * a.QP + static_cast<long long>(hh) * (a.W + 2) + ww) * 8 + c8;
-          const long long sb_pad = static_cast<long long>(a.Cg) * (a.T + 4) * plane_pad * 8;
-          const long long sb_gzw = static_cast<long long>(a.Cg) * a.T * a.QP * 8;
-          uint16_t* ypad = reinterpret_cast<uint16_t*>(a.gz_pad);
-          uint16_t* ygzw = reinterpret_cast<uint16_t*>(a.gzw);
-          const uint16_t* xm = reinterpret_cast<const uint16_t*>(a.xb);
+          // accumulator row = k' within the tile (k-group kg0 + row/8, channel row%8); columns = batch.
+          // stage as bf16 [b][row] so that a (b, k-group) pair becomes one 16-byte vector
+          uint16_t* es = reinterpret_cast<uint16_t*>(epi_s);
           for (int c0 = 0; c0 < a.BP; c0 += 16) {
             uint32_t v[16];
             tc::tmem_ld_32x16(taddr + c0, v);
             tc::tmem_ld_wait();
-            if (okk) {
 #pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const int b = c0 + c;
-                if (b < a.B) {
-                  const uint16_t m = __ldg(xm + (static_cast<long long>(b) * a.KG + kg) * 8 + c8);
-                  // bf16 > 0  <=>  sign bit clear and not zero (activations are finite, post-ReLU)
-                  const float g = ((m & 0x8000u) == 0 && (m & 0x7fffu) != 0) ? __uint_as_float(v[c]) : 0.f;
-                  const uint16_t o = static_cast<uint16_t>(f2bf(g));
-                  ypad[b * sb_pad + o_pad] = o;
-                  ygzw[b * sb_gzw + o_gzw] = o;
-                }
-              }
-            }
+            for (int c = 0; c < 16; ++c) es[(c0 + c) * 128 + row] = static_cast<uint16_t>(f2bf(__uint_as_float(v[c])));
           }
+          // accumulator fully read: hand it back to the MMA warp before the (slow) global phase
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tempty + acc);
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const long long kg0 = t * kF1KG;
+          for (int item = et; item < a.B * kF1KG; item += 128) {
+            const int b = item >> 4, kgl = item & 15;
+            const long long kg = kg0 + kgl;
+            if (kg >= a.KG) continue;
+            const int cg = static_cast<int>(kg / a.THW);
+            const int pos = static_cast<int>(kg - cg * a.THW);
+            const int tt = pos / (a.H * a.W);
+            const int hw = pos - tt * a.H * a.W;
+            const int hh = hw / a.W, ww = hw - hh * a.W;
+            const uint4 g = *reinterpret_cast<const uint4*>(es + b * 128 + kgl * 8);
+            const uint4 m = __ldg(a.xb + static_cast<long long>(b) * a.KG + kg);
+            // keep a gradient lane where the activation (bf16, post-ReLU, finite) is > 0: sign clear and non-zero
+            auto sel = [](uint32_t gv, uint32_t mv) {
+              const uint32_t lo = ((mv & 0x8000u) == 0 && (mv & 0x7fffu) != 0) ? (gv & 0xffffu) : 0u;
+              const uint32_t hi = ((mv & 0x80000000u) == 0 && (mv & 0x7fff0000u) != 0) ? (gv & 0xffff0000u) : 0u;
+              return lo | hi;
+            };
+            const uint4 o = make_uint4(sel(g.x, m.x), sel(g.y, m.y), sel(g.z, m.z), sel(g.w, m.w));
+            a.gz_pad[((static_cast<long long>(b) * a.Cg + cg) * (a.T + 4) + (tt + 2)) * plane_pad +
+                     static_cast<long long>(hh + 2) * (a.W + 4) + (ww + 2)] = o;
+            a.gzw[((static_cast<long long>(b) * a.Cg + cg) * a.T + tt) * a.QP + static_cast<long long>(hh) * (a.W + 2) + ww] = o;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");  // staging buffer free for the next tile
         } else {
-          // row = feature j; columns = (kgl, c8) -> dw[j][(cg*8+c8)*THW + pos]
-          float vals[128];
+          // accumulator row = feature j; columns = (kgl, c8).  Stage transposed as fp32 [(c8, kgl)][j] (row 129 floats:
+          // conflict-free both ways) so that each store instruction writes eight 64-byte runs of dw[j][(cg*8+c8)*THW+pos]
+          float* es = reinterpret_cast<float*>(epi_s);
 #pragma unroll
           for (int c0 = 0; c0 < 128; c0 += 32) {
             uint32_t v[32];
             tc::tmem_ld_32x32(taddr + c0, v);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) vals[c0 + c] = __uint_as_float(v[c]);
+            for (int c = 0; c < 32; ++c) {
+              const int col = c0 + c, kgl = col >> 3, c8 = col & 7;
+              es[(c8 * kF1KG + kgl) * 129 + row] = __uint_as_float(v[c]);
+            }
           }
-          if (row < a.F1) {
-            const long long kg0 = t * kF1KG;
-            const long long K1 = a.KG * 8;
-            float* drow = a.dw + static_cast<long long>(row) * K1;
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-#pragma unroll
-              for (int kgl = 0; kgl < kF1KG; ++kgl) {
-                const long long kg = kg0 + kgl;
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tempty + acc);
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const long long kg0 = t * kF1KG;
+          const int cg0 = static_cast<int>(kg0 / a.THW);
+          const int pos0 = static_cast<int>(kg0 - cg0 * a.THW);
+          const bool simple = (kg0 + kF1KG <= a.KG) && (pos0 + kF1KG <= a.THW) && (a.THW % 4 == 0) && (pos0 % 4 == 0);
+          const long long K1 = a.KG * 8;
+          // item = (j, c8, quad of positions): lanes = (quad, c8) for one j -> eight 64-byte runs per store instruction
+          for (int item = et; item < 128 * 32; item += 128) {
+            const int j = item >> 5, c8 = (item >> 2) & 7, q = item & 3;
+            if (j >= a.F1) continue;
+            const float* src = es + (c8 * kF1KG + 4 * q) * 129 + j;
+            const float4 v4 = make_float4(src[0], src[129], src[258], src[387]);
+            float* drow = a.dw + static_cast<long long>(j) * K1;
+            if (simple) {
+              __stcs(reinterpret_cast<float4*>(drow + (cg0 * 8 + c8) * a.THW + pos0 + 4 * q), v4);
+            } else {
+              const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+              for (int i = 0; i < 4; ++i) {
+                const long long kg = kg0 + 4 * q + i;
                 if (kg < a.KG) {
                   const int cg = static_cast<int>(kg / a.THW);
-                  const long long pos = kg - cg * a.THW;
-                  drow[(cg * 8 + c8) * a.THW + pos] = vals[kgl * 8 + c8];
+                  drow[(cg * 8 + c8) * a.THW + (kg - cg * a.THW)] = vv[i];
                 }
               }
             }
           }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
         }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tempty + acc);
       }
     }
   }
@@ -359,7 +434,8 @@ static int fc1_bf16_launch(const Fc1Bf16Args& a, long long grid, cudaStream_t st
   const size_t g_bytes = (MODE == 0) ? 0 : static_cast<size_t>(a.BP) * 256;
   const size_t w_bytes = (MODE == 2) ? 0 : static_cast<size_t>(kF1KG) * kF1J * 16;
   const size_t x_bytes = (MODE == 1) ? 0 : static_cast<size_t>(kF1KG) * a.BP * 16;
-  const size_t smem = 128 + round_up(g_bytes, static_cast<size_t>(128)) + 4 * (w_bytes + x_bytes);
+  const size_t epi_bytes = (MODE == 1) ? static_cast<size_t>(a.BP) * 256 : (MODE == 2 ? static_cast<size_t>(128) * 129 * 4 : 0);
+  const size_t smem = 128 + round_up(g_bytes, static_cast<size_t>(128)) + 4 * (w_bytes + x_bytes) + epi_bytes;
   PVB_REQUIRE(smem <= 227 * 1024, "fc1_bf16: batch %d needs %zu B of shared memory", a.B, smem);
   PVB_CUDA(cudaFuncSetAttribute(fc1_bf16_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fc1_bf16_kernel<MODE><<<static_cast<unsigned>(grid), kF1Threads, smem, st>>>(a);
@@ -385,6 +461,30 @@ int pvb200_fc1_make_shadow_bf16(const float* w1, uint16_t* shadow, int F1, int C
   dim3 grid(static_cast<unsigned>(ceil_div(THW, 32LL)), kF1J / 32, Cg);
   fc1_make_shadow_kernel<<<grid, 256, 0, as_stream(stream)>>>(w1, reinterpret_cast<uint4*>(shadow), F1, THW, Cg);
   PVB_LAUNCHED("fc1_make_shadow");
+  return PVB200_OK;
+}
+
+int pvb200_adam_fc1_shadow(float* w1, const float* grad, float* exp_avg, float* exp_avg_sq, uint16_t* shadow, int F1, int Cg,
+                           int T, int H, int W, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                           pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(w1 && grad && exp_avg && exp_avg_sq && shadow, "adam_fc1_shadow: null pointer");
+  PVB_REQUIRE(F1 > 0 && F1 <= kF1J && Cg > 0 && T > 0 && H > 0 && W > 0 && step >= 1, "adam_fc1_shadow: bad argument");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  AdamFc1Scalars s;
+  s.beta1 = beta1; s.beta2 = beta2;
+  s.one_minus_beta1 = static_cast<float>(1.0 - static_cast<double>(beta1));
+  s.one_minus_beta2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+  s.eps = eps;
+  s.neg_step_size = static_cast<float>(-(static_cast<double>(lr) / bc1));
+  s.bc2_sqrt = static_cast<float>(sqrt(bc2));
+  s.grad_scale = grad_scale;
+  const long long THW = static_cast<long long>(T) * H * W;
+  dim3 grid(static_cast<unsigned>(ceil_div(THW, 32LL)), kF1J / 32, Cg);
+  adam_fc1_shadow_kernel<<<grid, 256, 0, as_stream(stream)>>>(w1, grad, exp_avg, exp_avg_sq, reinterpret_cast<uint4*>(shadow), F1,
+                                                              THW, Cg, s);
+  PVB_LAUNCHED("adam_fc1_shadow");
   return PVB200_OK;
 }
 

@@ -78,6 +78,8 @@ SIGNATURES = {
     "pvb200_head_tail_bwd_f32": (c_int, [C.POINTER(Head), c_void_p]),
     "pvb200_fc1_bf16_shadow_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "pvb200_fc1_make_shadow_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_adam_fc1_shadow": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                       c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
     "pvb200_fc1_fwd_bf16_splits": (c_int, []),
     "pvb200_fc1_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_fc1_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -137,6 +137,10 @@ class Model(BaseModel):
             mean, std = SAT_MEAN[12 - n:], SAT_STD[12 - n:]
         else:
             mean, std = np.zeros(n, np.float32), np.ones(n, np.float32)
+        # bf16 mode: tensor-core shadow of fc1.weight; FusedAdam finds it through the parameter and keeps it fresh
+        self._fc1_shadow = ops.Fc1Shadow()
+        if precision == "bf16":
+            self.fc1.weight._pvb_shadow = self._fc1_shadow
         self.register_buffer("sat_mean", torch.from_numpy(mean.copy()), persistent=False)
         self.register_buffer("sat_std", torch.from_numpy(std.copy()), persistent=False)
 
@@ -182,7 +186,7 @@ class Model(BaseModel):
         # tensor-core fc1 needs B <= 256, fc1_output_features <= 128 and channels in whole (even) groups of 8
         bf16_head = (self.precision == "bf16" and batch_size <= 256 and self.fc1_output_features <= 128
                      and self.sat_conv0.out_channels % 16 == 0)
-        link = {} if bf16_head else None
+        link = {"shadow": self._fc1_shadow} if bf16_head else None
         if self.precision == "bf16":
             out = ops.EncoderBf16Fn.apply(link, sat_data, mean, std, *self._conv_params())
             n_feat = out[0].numel() if bf16_head else out.shape[1]

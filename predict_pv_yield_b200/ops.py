@@ -559,6 +559,55 @@ def _zero_bordered(name: str, shape: Tuple[int, ...], device: torch.device) -> t
     return buf
 
 
+class Fc1Shadow:
+    """bf16 shadow of ``fc1.weight`` in the tensor-core layout [Cg*T*H*W][128][8], refreshed lazily.
+
+    The shadow is valid for one (storage, version) of the master weight: ``_version`` changes when torch writes the
+    parameter in place (``load_state_dict``, manual edits), ``_pvb_gen`` when ``FusedAdam`` updates it through the C ABI
+    (which torch cannot see).  ``FusedAdam`` refreshes the shadow itself, inside the Adam pass, when it is attached."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.geom: Optional[Tuple[int, int, int, int]] = None
+        self.key = None
+
+    @staticmethod
+    def _key(w1: torch.Tensor):
+        return (w1.data_ptr(), w1._version, getattr(w1, "_pvb_gen", 0))
+
+    def ensure(self, w1: torch.Tensor, F1: int, Cg: int, T: int, H: int, W: int) -> torch.Tensor:
+        L = _lib.load()
+        geom = (Cg, T, H, W)
+        if self.buf is None or self.geom != geom or self.buf.device != w1.device:
+            self.buf = torch.empty(L.pvb200_fc1_bf16_shadow_bytes(Cg, T, H, W), dtype=torch.uint8, device=w1.device)
+            self.geom, self.key = geom, None
+        if self.key != self._key(w1):
+            with _timed("fc1_make_shadow_bf16", 0.0, 6.0 * w1.numel()):
+                rc = L.pvb200_fc1_make_shadow_bf16(_p(w1), _p(self.buf), F1, Cg, T, H, W, _stream())
+            _lib.check(rc, "fc1_make_shadow_bf16")
+            self.key = self._key(w1)
+        return self.buf
+
+    def adam_step(self, w1: "torch.nn.Parameter", grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float,
+                  beta1: float, beta2: float, eps: float, step: int, grad_scale: float) -> bool:
+        """Adam update of ``w1`` that rewrites the shadow in the same pass; False if no shadow geometry is known yet."""
+        if self.buf is None or self.geom is None or self.buf.device != w1.device:
+            return False
+        L = _lib.load()
+        Cg, T, H, W = self.geom
+        if w1.shape[1] != Cg * 8 * T * H * W or w1.shape[0] > 128:
+            return False
+        for t, nm in ((w1.data, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+            _need_cuda(t, nm, torch.float32)
+        with _timed("adam_fc1_shadow", 0.0, 30.0 * w1.numel()):
+            rc = L.pvb200_adam_fc1_shadow(_p(w1), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(self.buf), w1.shape[0], Cg, T, H, W,
+                                          lr, beta1, beta2, eps, step, grad_scale, _stream())
+        _lib.check(rc, "adam_fc1_shadow")
+        w1._pvb_gen = getattr(w1, "_pvb_gen", 0) + 1
+        self.key = self._key(w1)
+        return True
+
+
 class HeadBf16Fn(torch.autograd.Function):
     """FC head of the bf16 mode: fc1 as weight-streaming tcgen05 GEMMs over a bf16 shadow of the fp32 master weight,
     the rest of the head (fc2, concat, fc_nwp, fc3, fc4) in the fused fp32 tail kernels.
@@ -576,10 +625,11 @@ class HeadBf16Fn(torch.autograd.Function):
         h, ncat = HeadFn._desc(feats_stub, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4)
         h.x = None
         dev = act.device
-        shadow = _workspace(f"fc1_shadow_{w1.data_ptr()}", L.pvb200_fc1_bf16_shadow_bytes(Cg, T, H, W), dev)
-        with _timed("fc1_make_shadow_bf16", 0.0, 4.0 * w1.numel() + 2.0 * w1.numel()):
-            rc = L.pvb200_fc1_make_shadow_bf16(_p(w1), _p(shadow), h.F1, Cg, T, H, W, _stream())
-        _lib.check(rc, "fc1_make_shadow_bf16")
+        shadow_state = link.get("shadow") if link is not None else None
+        if shadow_state is None:
+            shadow_state = Fc1Shadow()
+        shadow = shadow_state.ensure(w1, h.F1, Cg, T, H, W)
+        ctx.shadow = shadow  # the very buffer the forward used (kept alive for the data gradient)
         S = int(L.pvb200_fc1_fwd_bf16_splits())
         partial = _workspace("head", S * B * h.F1 * 4, dev)
         with _timed("fc1_fwd_bf16", 2.0 * B * h.F1 * h.K1, 2.0 * (B * h.K1 + 128 * h.K1)):
@@ -625,7 +675,7 @@ class HeadBf16Fn(torch.autograd.Function):
             QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(H + 2, W + 2))
             gz_pad = _zero_bordered("gz_pad_head", (B, Cg, T + 4, H + 4, W + 4, 8), dev)
             gzw = _zero_bordered("gzw_head", (B, Cg, T, QP, 8), dev)
-            shadow = _workspace(f"fc1_shadow_{w1.data_ptr()}", L.pvb200_fc1_bf16_shadow_bytes(Cg, T, H, W), dev)
+            shadow = ctx.shadow
             with _timed("fc1_dgrad_bf16", 2.0 * B * h.F1 * h.K1, 2.0 * (128 * h.K1 + 4 * B * h.K1)):
                 rc = L.pvb200_fc1_dgrad_bf16(_p(g_h1), _p(shadow), _p(act), _p(gz_pad), _p(gzw), B, h.F1, Cg, T, H, W, _stream())
             _lib.check(rc, "fc1_dgrad_bf16")

@@ -46,12 +46,21 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] = int(st["step"]) + 1
+                grad = p.grad.data if p.grad.is_contiguous() else p.grad.data.contiguous()
+                shadow = getattr(p, "_pvb_shadow", None)
+                if shadow is not None:
+                    # fc1.weight in bf16 mode: Adam + refresh of the tensor-core shadow in one pass over the weight
+                    b1, b2 = group["betas"]
+                    if shadow.adam_step(p, grad, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
+                                        st["step"], self.grad_scale):
+                        continue
+                p._pvb_gen = getattr(p, "_pvb_gen", 0) + 1  # updated behind torch's back: derived copies are stale
                 if step is None:
                     step = st["step"]
                 elif step != st["step"]:
                     raise RuntimeError("FusedAdam: parameters of one group must share a step count")
                 ps.append(p.data)
-                gs.append(p.grad.data if p.grad.is_contiguous() else p.grad.data.contiguous())
+                gs.append(grad)
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
             if ps:

@@ -222,3 +222,45 @@ def test_fc1_bf16_kernels(ops, dev, case):
     assert O.normalised_max_err(got, want_gx) <= BF16_TOL
     assert float(gz_pad.float().abs().sum()) == pytest.approx(float(got.abs().sum()), rel=1e-3)  # border stayed zero
     assert torch.equal(gzw, ops.to_gzw_bf16(got))
+
+
+def test_bf16_shadow_tracks_weight_updates(dev):
+    """The tensor-core shadow of fc1.weight must follow every way the master weight can change: FusedAdam's fused
+    update, an Adam step by a foreign optimiser, and in-place edits / load_state_dict through torch."""
+    from oracle.golden_cases import CASES, golden_batch, golden_state_dict
+    from predict_pv_yield_b200.models.conv3d.model import Model
+
+    case = CASES["nwp_pv_small"]
+    m = Model(**case["model"], precision="bf16").to(dev)
+    m.batch_size = case["batch"]
+    m.load_state_dict(golden_state_dict(m))
+    batch = O.batch_to(golden_batch("nwp_pv_small"), dev)
+
+    def fresh_forward():
+        ref = Model(**case["model"], precision="bf16").to(dev)  # a model that has never cached anything
+        ref.load_state_dict(m.state_dict())
+        with torch.no_grad():
+            return ref(batch)
+
+    opt = m.configure_optimizers()
+    for step in range(2):  # fused Adam + shadow path
+        opt.zero_grad()
+        m.training_step(batch, step).backward()
+        opt.step()
+        with torch.no_grad():
+            assert torch.equal(m(batch), fresh_forward())
+    # the fused update equals the plain multi-tensor update bit for bit
+    m2 = Model(**case["model"], precision="bf16").to(dev)
+    m2.batch_size = case["batch"]
+    m2.load_state_dict(golden_state_dict(m2))
+    del m2.fc1.weight._pvb_shadow  # force the generic Adam kernel
+    opt2 = m2.configure_optimizers()
+    for step in range(2):
+        opt2.zero_grad()
+        m2.training_step(batch, step).backward()
+        opt2.step()
+    assert torch.equal(m.fc1.weight, m2.fc1.weight)
+    with torch.no_grad():
+        assert torch.equal(m2(batch), m(batch))  # generic path bumped the generation -> shadow recomputed
+        m.fc1.weight.mul_(0.5)  # in-place edit through torch
+        assert torch.equal(m(batch), fresh_forward())
