@@ -65,48 +65,81 @@ fc1_make_shadow_kernel(const float* __restrict__ w, uint4* __restrict__ ws, int 
 struct AdamFc1Scalars {
   float beta1, beta2, one_minus_beta1, one_minus_beta2, eps, neg_step_size, bc2_sqrt, grad_scale;
 };
+// one CTA = 64 positions x 32 features x one channel group: 256-byte runs for p / g / m / v (float2 per lane) and
+// 512-byte runs for the shadow (32 features x 16 B per position); the updated weights cross from "pos-major" to
+// "feature-major" through a bf16 staging tile in shared memory (row padded to 66 elements: conflict-free both ways).
+// All 32 x 4 loads of a thread are issued before the arithmetic so that enough bytes are in flight per SM.
+constexpr int kAdamShPos = 64;
+constexpr int kAdamShLd = 66;
 __global__ void __launch_bounds__(256)
 adam_fc1_shadow_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                        uint4* __restrict__ ws, int F1, long long THW, int Cg, const AdamFc1Scalars s) {
-  __shared__ float tile[8][32][33];
-  const long long pos0 = static_cast<long long>(blockIdx.x) * 32;
+  __shared__ __align__(16) uint16_t tile16[8 * 32 * kAdamShLd];  // [8 c8][32 j][66]
+  const long long pos0 = static_cast<long long>(blockIdx.x) * kAdamShPos;
   const int j0 = blockIdx.y * 32;
   const int cg = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long K1 = static_cast<long long>(Cg) * 8 * THW;
-  const long long pos = pos0 + tx;
+  const long long pos = pos0 + 2 * tx;
+  const bool vec = (THW % 2 == 0) && (pos + 1 < THW);
 #pragma unroll
-  for (int c8 = 0; c8 < 8; ++c8) {
+  for (int r = 0; r < 4; ++r) {
+    const int jj = ty + 8 * r;
+    const int j = j0 + jj;
+    const bool ok = (j < F1) && (pos < THW);
+    float2 pv[8], gv[8], mv[8], vv[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int jj = ty + 8 * r;
-      const int j = j0 + jj;
-      float pn = 0.f;
-      if (j < F1 && pos < THW) {
+    for (int c8 = 0; c8 < 8; ++c8) {
+      pv[c8] = gv[c8] = mv[c8] = vv[c8] = make_float2(0.f, 0.f);
+      if (ok) {
         const long long i = static_cast<long long>(j) * K1 + (cg * 8 + c8) * THW + pos;
-        float gg = __ldcs(g + i) * s.grad_scale;
-        float mm = m[i], vv = v[i];
-        pn = p[i];
-        mm = fmaf(gg - mm, s.one_minus_beta1, mm);
-        vv = fmaf(s.one_minus_beta2 * gg, gg, vv * s.beta2);
-        const float denom = __fdiv_rn(sqrtf(vv), s.bc2_sqrt) + s.eps;
-        pn = fmaf(s.neg_step_size, __fdiv_rn(mm, denom), pn);
-        p[i] = pn; m[i] = mm; v[i] = vv;
+        if (vec) {
+          gv[c8] = __ldcs(reinterpret_cast<const float2*>(g + i));
+          mv[c8] = *reinterpret_cast<const float2*>(m + i);
+          vv[c8] = *reinterpret_cast<const float2*>(v + i);
+          pv[c8] = *reinterpret_cast<const float2*>(p + i);
+        } else {
+          gv[c8].x = g[i]; mv[c8].x = m[i]; vv[c8].x = v[i]; pv[c8].x = p[i];
+        }
       }
-      tile[c8][jj][tx] = pn;
+    }
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+      float ge[2] = {gv[c8].x * s.grad_scale, gv[c8].y * s.grad_scale};
+      float me[2] = {mv[c8].x, mv[c8].y}, ve[2] = {vv[c8].x, vv[c8].y}, pe[2] = {pv[c8].x, pv[c8].y};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        me[e] = fmaf(ge[e] - me[e], s.one_minus_beta1, me[e]);
+        ve[e] = fmaf(s.one_minus_beta2 * ge[e], ge[e], ve[e] * s.beta2);
+        const float denom = __fdiv_rn(sqrtf(ve[e]), s.bc2_sqrt) + s.eps;
+        pe[e] = fmaf(s.neg_step_size, __fdiv_rn(me[e], denom), pe[e]);
+      }
+      if (ok) {
+        const long long i = static_cast<long long>(j) * K1 + (cg * 8 + c8) * THW + pos;
+        if (vec) {
+          *reinterpret_cast<float2*>(p + i) = make_float2(pe[0], pe[1]);
+          *reinterpret_cast<float2*>(m + i) = make_float2(me[0], me[1]);
+          *reinterpret_cast<float2*>(v + i) = make_float2(ve[0], ve[1]);
+        } else {
+          p[i] = pe[0]; m[i] = me[0]; v[i] = ve[0];
+        }
+      } else {
+        pe[0] = pe[1] = 0.f;
+      }
+      *reinterpret_cast<uint32_t*>(tile16 + (c8 * 32 + jj) * kAdamShLd + 2 * tx) = f2bf(pe[0]) | (f2bf(pe[1]) << 16);
     }
   }
   __syncthreads();
-  for (int pp = ty; pp < 32; pp += 8) {
+  for (int pp = ty; pp < kAdamShPos; pp += 8) {
     const long long q = pos0 + pp;
     if (q >= THW) continue;
-    const int j = j0 + tx;
+    const uint16_t* src = tile16 + tx * kAdamShLd + pp;  // feature tx, position pp, channel stride 32*66
     uint4 o;
-    o.x = f2bf(tile[0][tx][pp]) | (f2bf(tile[1][tx][pp]) << 16);
-    o.y = f2bf(tile[2][tx][pp]) | (f2bf(tile[3][tx][pp]) << 16);
-    o.z = f2bf(tile[4][tx][pp]) | (f2bf(tile[5][tx][pp]) << 16);
-    o.w = f2bf(tile[6][tx][pp]) | (f2bf(tile[7][tx][pp]) << 16);
-    ws[(cg * THW + q) * kF1J + j] = o;
+    o.x = src[0 * 32 * kAdamShLd] | (static_cast<uint32_t>(src[1 * 32 * kAdamShLd]) << 16);
+    o.y = src[2 * 32 * kAdamShLd] | (static_cast<uint32_t>(src[3 * 32 * kAdamShLd]) << 16);
+    o.z = src[4 * 32 * kAdamShLd] | (static_cast<uint32_t>(src[5 * 32 * kAdamShLd]) << 16);
+    o.w = src[6 * 32 * kAdamShLd] | (static_cast<uint32_t>(src[7 * 32 * kAdamShLd]) << 16);
+    ws[(cg * THW + q) * kF1J + j0 + tx] = o;
   }
 }
 
@@ -481,9 +514,9 @@ int pvb200_adam_fc1_shadow(float* w1, const float* grad, float* exp_avg, float* 
   s.bc2_sqrt = static_cast<float>(sqrt(bc2));
   s.grad_scale = grad_scale;
   const long long THW = static_cast<long long>(T) * H * W;
-  dim3 grid(static_cast<unsigned>(ceil_div(THW, 32LL)), kF1J / 32, Cg);
-  adam_fc1_shadow_kernel<<<grid, 256, 0, as_stream(stream)>>>(w1, grad, exp_avg, exp_avg_sq, reinterpret_cast<uint4*>(shadow), F1,
-                                                              THW, Cg, s);
+  dim3 grid(static_cast<unsigned>(ceil_div(THW, static_cast<long long>(kAdamShPos))), kF1J / 32, Cg);
+  adam_fc1_shadow_kernel<<<grid, 256, 0, as_stream(stream)>>>(w1, grad, exp_avg, exp_avg_sq, reinterpret_cast<uint4*>(shadow),
+                                                                 F1, THW, Cg, s);
   PVB_LAUNCHED("adam_fc1_shadow");
   return PVB200_OK;
 }
