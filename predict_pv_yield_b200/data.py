@@ -15,55 +15,87 @@ from typing import Any, Iterable, Iterator, Optional
 import torch
 
 
-def _to_device(obj: Any, device: torch.device, pin: bool):
+def _flatten(obj: Any, prefix=()):
     if isinstance(obj, dict):
-        return {k: _to_device(v, device, pin) for k, v in obj.items()}
-    if torch.is_tensor(obj):
-        if obj.is_cuda:
-            return obj
-        if pin and not obj.is_pinned():
-            obj = obj.pin_memory()
-        return obj.to(device, non_blocking=True)
-    return obj
+        for k, v in obj.items():
+            yield from _flatten(v, prefix + (k,))
+    else:
+        yield prefix, obj
 
 
-def _record_stream(obj: Any, stream: torch.cuda.Stream) -> None:
-    if isinstance(obj, dict):
-        for v in obj.values():
-            _record_stream(v, stream)
-    elif torch.is_tensor(obj) and obj.is_cuda:
-        obj.record_stream(stream)
+def _unflatten(items) -> dict:
+    out: dict = {}
+    for path, v in items:
+        d = out
+        for k in path[:-1]:
+            d = d.setdefault(k, {})
+        d[path[-1]] = v
+    return out
+
+
+class _Slot:
+    """One set of device staging buffers (allocated once per tensor shape) + the event that says it is free again."""
+
+    def __init__(self):
+        self.bufs = {}
+        self.free: Optional[torch.cuda.Event] = None
 
 
 class DevicePrefetcher:
-    """Iterate over ``batches`` (nested dicts of CPU tensors) yielding device-resident dicts, one batch ahead."""
+    """Iterate over ``batches`` (nested dicts of CPU tensors) yielding device-resident dicts, one batch ahead.
 
-    def __init__(self, batches: Iterable[dict], device: torch.device, pin: bool = True):
+    Device memory is a ring of ``depth`` pre-allocated buffer sets: no allocator traffic per step (a side-stream
+    allocation per batch would end in synchronising ``cudaMalloc`` / delayed block reuse), and a yielded batch stays
+    valid until ``depth - 1`` further batches have been requested."""
+
+    def __init__(self, batches: Iterable[dict], device: torch.device, pin: bool = True, depth: int = 3):
         if torch.device(device).type != "cuda":
             raise RuntimeError("DevicePrefetcher targets a CUDA device (predict_pv_yield_b200 has no CPU path)")
+        if depth < 2:
+            raise ValueError("DevicePrefetcher needs depth >= 2")
         self.batches = batches
         self.device = torch.device(device)
         self.pin = pin
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = [_Slot() for _ in range(depth)]
 
-    def _launch(self, it: Iterator[dict]):
+    def _launch(self, it: Iterator[dict], index: int):
         try:
             host = next(it)
         except StopIteration:
             return None
+        slot = self.slots[index % len(self.slots)]
+        items = []
         with torch.cuda.stream(self.copy_stream):
-            dev = _to_device(host, self.device, self.pin)
+            if slot.free is not None:
+                self.copy_stream.wait_event(slot.free)  # the consumer of this slot's previous batch has been queued past it
+            for path, v in _flatten(host):
+                if torch.is_tensor(v) and not v.is_cuda:
+                    if self.pin and not v.is_pinned():
+                        v = v.pin_memory()
+                    key = (path, tuple(v.shape), v.dtype)
+                    buf = slot.bufs.get(key)
+                    if buf is None:
+                        buf = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                        slot.bufs[key] = buf
+                    buf.copy_(v, non_blocking=True)
+                    v = buf
+                items.append((path, v))
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
-        return dev, ready
+        return _unflatten(items), ready, slot
 
     def __iter__(self) -> Iterator[dict]:
         it = iter(self.batches)
-        nxt: Optional[tuple] = self._launch(it)
+        i = 0
+        nxt = self._launch(it, i)
         while nxt is not None:
-            dev, ready = nxt
-            nxt = self._launch(it)  # batch i+1 starts copying before batch i is consumed
+            dev, ready, slot = nxt
+            i += 1
+            nxt = self._launch(it, i)  # batch i+1 starts copying before batch i is consumed
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ready)
-            _record_stream(dev, cur)
             yield dev
+            # the consumer has queued all its work on this batch: the slot is free once the compute stream gets here
+            slot.free = torch.cuda.Event()
+            slot.free.record(torch.cuda.current_stream(self.device))
