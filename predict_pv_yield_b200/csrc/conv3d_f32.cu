@@ -154,6 +154,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
     for (int c = 0; c < cmax; ++c) {
 #pragma unroll 1
       for (int kt = 0; kt < 3; ++kt) {
+        // a time plane that lies entirely in the zero padding of the data gradient contributes nothing (block-uniform)
+        const int ti = to + kt - a.P;
+        if (ti < 0 || ti >= a.Ti) continue;
         const float* ip = in_b + (c * 3 + kt) * a.NP + 4 * tp;
         const float* wp = w_b + (c * 27 + kt * 9) * kCoT + 8 * cg;
 #pragma unroll

@@ -42,6 +42,7 @@ struct IgemmArgs {
   int B, Cg, Ti, Hi, Wi;
   int CoP, Co, CogOut, To, Ho, Wo;  // CoP = Cout padded to 16/32; MMA N = 3*CoP (the three kw taps side by side)
   int out_pad, relu;
+  int zero_planes;  // the first / last `zero_planes` input time planes are all zero (padded gz): their MMAs are skipped
   int NP;       // staged positions per (plane, channel group)
   int tiles_q;  // q tiles per output plane
   int nslot;  // ring slots (4..8), as many as fit in shared memory
@@ -198,8 +199,12 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) pl16[kt] = slot_addr16 + ((base_seq + ti + kt) % nslot) * slot_16;
         // the two row blocks accumulate into different TMEM tiles and are interleaved
+        uint32_t acc_flag = 0;
+        const int tin = r.t0 + ti;  // first input time plane of this tile
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
+          // a plane that lies entirely in the zero border of a padded gradient contributes nothing (warp-uniform)
+          if (tin + kt < a.zero_planes || tin + kt >= a.Ti - a.zero_planes) continue;
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
@@ -211,9 +216,9 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
                 const uint32_t a16 = pl16[kt] + static_cast<uint32_t>(2 * ks) * (a_lbo >> 4) + rb * 128u + kh * wi;
                 const uint32_t b16 = static_cast<uint32_t>(((kt * 3 + kh) * CG + 2 * ks)) * (b_lbo >> 4);
                 if (leader)
-                  igemm_mma(d_tmem, a_lo_base | (a16 & 0x3fffu), desc_hi, b_lo_base + b16, desc_hi, idesc,
-                            (kt | kh | ks) ? 1u : 0u);
+                  igemm_mma(d_tmem, a_lo_base | (a16 & 0x3fffu), desc_hi, b_lo_base + b16, desc_hi, idesc, acc_flag);
               }
+              acc_flag = 1;
             }
           }
         }
@@ -435,7 +440,7 @@ static size_t igemm_ws_bytes(int Ci_role, int Co_role) {
 
 static int launch_igemm(const void* xb, const float* w, long long s_co, long long s_ci, int flip, const float* bias,
                         const void* mask, void* yb, void* yb2, void* ws, size_t ws_bytes, int B, int Ci, int Ti, int Hi, int Wi, int Co,
-                        int out_pad, int relu, cudaStream_t stream) {
+                        int out_pad, int relu, int zero_planes, cudaStream_t stream) {
   IgemmArgs a;
   a.x = static_cast<const uint4*>(xb);
   a.bias = bias;
@@ -449,6 +454,7 @@ static int launch_igemm(const void* xb, const float* w, long long s_co, long lon
   PVB_REQUIRE(a.To > 0 && a.Ho > 0 && a.Wo > 0, "conv3d_bf16: input %dx%dx%d too small", Ti, Hi, Wi);
   PVB_REQUIRE(a.Cg == 2 || a.Cg == 4, "conv3d_bf16: Cin=%d > 32 is not supported by the tensor-core path (use fp32 mode)", Ci);
   a.out_pad = out_pad; a.relu = relu;
+  a.zero_planes = zero_planes;
   a.QP2 = static_cast<int>(round_up(static_cast<long long>(a.Ho) * (a.Wo + 2), 128LL));
   a.NP = round_up(kIgTileM + 2 * Wi, 8);
   const int Qtot = (a.Ho - 1) * Wi + a.Wo;
@@ -544,7 +550,7 @@ int pvb200_conv3d_fwd_bf16(const uint16_t* xb, const float* w, const float* bias
   PVB_REQUIRE(xb && w && yb, "conv3d_fwd_bf16: null pointer");
   PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && out_pad >= 0, "conv3d_fwd_bf16: bad shape");
   return launch_igemm(xb, w, static_cast<long long>(Cin) * 27, 27, 0, bias, nullptr, yb, nullptr, workspace, workspace_bytes, B, Cin,
-                      Ti, Hi, Wi, Cout, out_pad, relu, as_stream(stream));
+                      Ti, Hi, Wi, Cout, out_pad, relu, /*zero_planes=*/0, as_stream(stream));
 }
 
 int pvb200_conv3d_dgrad_bf16(const uint16_t* gz_padded, const float* w, const uint16_t* mask_src, uint16_t* gx,
@@ -556,7 +562,7 @@ int pvb200_conv3d_dgrad_bf16(const uint16_t* gz_padded, const float* w, const ui
   // kernel input = gz zero-padded by 2: [B][Cg(Cout)][Ti+2][Hi+2][Wi+2]; kernel output = gx [B][Cg(Cin)][Ti][Hi][Wi]
   return launch_igemm(gz_padded, w, /*s_co (out role = ci)*/ 27, /*s_ci (in role = co)*/ static_cast<long long>(Cin) * 27, 1,
                       nullptr, mask_src, gx, gx_gzw, workspace, workspace_bytes, B, /*Ci role*/ Cout, Ti + 2, Hi + 2, Wi + 2,
-                      /*Co role*/ Cin, out_pad, 0, as_stream(stream));
+                      /*Co role*/ Cin, out_pad, 0, /*zero_planes=*/2, as_stream(stream));
 }
 
 }  // extern "C"
