@@ -9,15 +9,21 @@
 //   * positions are flattened with the INPUT pitch: q = ho*Wi + wo, so the A operand of tap (kt,kh,kw) for rows
 //     q0..q0+127 is the contiguous run of 16-byte elements starting at q0 + kh*Wi + kw of input plane t+kt:
 //     exactly the SWIZZLE_NONE K-major canonical layout (8 rows x 16 B core matrices, SBO = 128 B, LBO = the
-//     stride between channel-group planes).  A tap is just a different descriptor start address.
-//   * one input plane segment (all channel groups, 256 + 2*Wi + 2 positions) is ONE bulk copy per channel group
-//     (cp.async.bulk, completion on an mbarrier); a 4-slot ring keeps 3 time planes live + 1 in flight, so walking
-//     along t re-loads nothing (each plane is fetched once per t-segment).
+//     stride between channel-group planes).  A tap is just a different descriptor start address (measured with
+//     tools/probe/mma_probe.cu: start addresses that are not 128-byte aligned cost nothing).
+//   * one input plane segment (all channel groups, 128 + 2*Wi positions) is ONE bulk copy per channel group
+//     (cp.async.bulk, completion on an mbarrier; many small per-row copies were measured ~50 clk each and lose); a ring
+//     keeps 3 time planes live + the rest in flight, so walking along t re-loads nothing.
 //   * all 27 x Cin x Cout weights (55 KB bf16) stay resident in shared memory for the whole persistent CTA.
 //   * wrap columns (wo >= Wo) are computed and dropped in the epilogue (2/Wi ~ 3 % waste).
-// Warp roles (576 threads): warp 0 = copy producer, warp 1 = MMA issuer (one elected thread) + TMEM owner,
+// Warp roles (608 threads): warp 0 = copy producer, warps 1 and 18 = MMA issuers (one elected thread each; warp 1
+// owns the TMEM allocation).  One thread cannot issue tcgen05.mma faster than one per ~54 clk plus the descriptor
+// arithmetic in between (measured 74 clk per MMA in this loop, against 56 clk of tensor-pipe time at N = 96), so the
+// two issuers take alternate tiles (different TMEM accumulators) and their issue latencies overlap.
 // warps 2-17 = epilogue (TMEM -> registers -> bias/ReLU or ReLU-mask -> bf16 -> 16-byte stores); accumulators are
-// double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// quadruple-buffered in TMEM (4 x 96 columns) and the epilogue warps form FOUR groups of four (one warp per TMEM lane
+// quadrant) that own every fourth tile (group = TMEM buffer), so the latency chain of one tile's epilogue (TMEM load,
+// boundary-row exchange, shuffles, stores) spans four tiles of MMA time and the MMA warp runs three tiles ahead.
 // The data gradient is the same kernel on a zero-padded gz (padding 2) with flipped / transposed weights.
 #include <stdlib.h>
 
@@ -26,10 +32,12 @@
 
 namespace pvb {
 
-constexpr int kIgThreads = 576;  // producer warp, MMA warp, 16 epilogue warps
+constexpr int kIgThreads = 608;  // producer warp, MMA warp, 16 epilogue warps, second MMA warp
+constexpr int kIgMmaWarp2 = 18;  // the second MMA issuer
 constexpr int kIgMaxSlots = 8;  // time-plane ring: 3 planes live per tile + (nslot - 3) planes of prefetch distance
-constexpr int kIgTileM = 256;    // MMA rows per tile = 2 row blocks of 128
-constexpr int kIgTileOut = 254;  // outputs per tile: the kw shift-add needs rows r, r+1, r+2
+constexpr int kIgTileM = 128;    // MMA rows per tile
+constexpr int kIgTileOut = 126;  // outputs per tile: the kw shift-add needs rows r, r+1, r+2
+constexpr int kIgAcc = 4;        // TMEM accumulator buffers = epilogue groups
 
 struct IgemmArgs {
   const uint4* x;     // [B][Cg][Ti][Hi][Wi] 16-byte elements (8 bf16 channels)
@@ -47,6 +55,7 @@ struct IgemmArgs {
   int tiles_q;  // q tiles per output plane
   int nslot;  // ring slots (4..8), as many as fit in shared memory
   long long* dbg;  // optional [grid][8] cycle counters (profiling builds of the tools; null in production)
+  int dbg_flags;   // profiling builds only: 1 = skip the plane copies (stale shared memory), 2 = skip the output stores
   long long tiles;  // B * tiles_q * To
 };
 
@@ -107,11 +116,11 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]
   uint64_t* empty = full + kIgMaxSlots;                     // [8]
   uint64_t* wfull = empty + kIgMaxSlots;                    // [1]
-  uint64_t* tfull = wfull + 1;                              // [2]
-  uint64_t* tempty = tfull + 2;                             // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tfull = wfull + 1;                              // [4]
+  uint64_t* tempty = tfull + kIgAcc;                        // [4]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + kIgAcc);
   float* bias_s = reinterpret_cast<float*>(smem + 256);     // [32]
-  float* xch = reinterpret_cast<float*>(smem + 384);        // [2 parity][2 rb][4 qd][3*32] boundary rows of the shift-add
+  float* xch = reinterpret_cast<float*>(smem + 384);        // [4 groups][4 qd][3*32] boundary rows of the shift-add
   uint8_t* w_s = smem + 384 + 2 * 2 * 4 * 96 * 4;
   const int N = 3 * a.CoP;
   const uint32_t w_bytes = 9u * CG * N * 16u;
@@ -122,9 +131,10 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
   const uint32_t tmem_cols = (4u * N <= 256u) ? 256u : 512u;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kIgMaxSlots; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+    // a plane slot is released by BOTH MMA warps (tcgen05.commit only tracks the MMAs of the committing thread)
+    for (int i = 0; i < kIgMaxSlots; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 2); }
     tc::mbar_init(wfull, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 16); }
+    for (int i = 0; i < kIgAcc; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
@@ -156,6 +166,7 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
         for (int p = 0; p < r.ntiles + 2; ++p, ++seq) {
           const uint32_t slot = seq % nslot;
           tc::mbar_wait(empty + slot, ((seq / nslot) & 1u) ^ 1u);
+          if (DBG && (a.dbg_flags & 1)) { tc::mbar_arrive(full + slot); continue; }
           tc::mbar_arrive_expect_tx(full + slot, npos * 16u * CG);
 #pragma unroll
           for (int cg = 0; cg < CG; ++cg) {
@@ -166,8 +177,9 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
         g += r.ntiles;
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
+  } else if (warp == 1 || warp == kIgMmaWarp2) {
+    // =============================== MMA issuers ===============================
+    const uint32_t mw = (warp == 1) ? 0u : 1u;  // this warp issues the tiles with tile_ctr % 2 == mw
     // The whole warp runs the (warp-uniform) control flow so that descriptor arithmetic stays in uniform registers;
     // only the tcgen05.mma / tcgen05.commit instructions themselves are issued by one elected lane.
     const bool leader = tc::elect_one();
@@ -182,50 +194,56 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
     const uint32_t slot_16 = slot_bytes >> 4;
     const uint32_t wi = static_cast<uint32_t>(a.Wi);
     tc::mbar_wait(wfull, 0);
-    uint32_t base_seq = 0, waited = 0, tile_ctr = 0;
+    uint32_t base_seq = 0, tile_ctr = 0;
     long long dbg_full = 0, dbg_tempty = 0, dbg_issue = 0;
     const long long dbg_t0 = DBG ? clock64() : 0;
     for (long long g = g_begin; g < g_end;) {
       const IgRun r = ig_run(g, g_end, a.To, a.tiles_q);
       for (int ti = 0; ti < r.ntiles; ++ti, ++tile_ctr) {
         const long long c0 = DBG ? clock64() : 0;
-        for (; waited < base_seq + ti + 3; ++waited) tc::mbar_wait(full + (waited % nslot), (waited / nslot) & 1u);
-        const long long c1 = DBG ? clock64() : 0;
-        const uint32_t acc = tile_ctr & 1u;
-        tc::mbar_wait(tempty + acc, ((tile_ctr >> 1) & 1u) ^ 1u);
-        tc::tc_fence_after();
-        const long long c2 = DBG ? clock64() : 0;
-        uint32_t pl16[3];
+        long long c1 = c0, c2 = c0;
+        const uint32_t acc = tile_ctr & (kIgAcc - 1);
+        const bool mine = (tile_ctr & 1u) == mw;
+        if (mine) {
+          // the three planes of this tile (none of them can have been recycled: this warp has not released them yet)
 #pragma unroll
-        for (int kt = 0; kt < 3; ++kt) pl16[kt] = slot_addr16 + ((base_seq + ti + kt) % nslot) * slot_16;
-        // the two row blocks accumulate into different TMEM tiles and are interleaved
-        uint32_t acc_flag = 0;
-        const int tin = r.t0 + ti;  // first input time plane of this tile
+          for (int kt = 0; kt < 3; ++kt) {
+            const uint32_t pseq = base_seq + ti + kt;
+            tc::mbar_wait(full + (pseq % nslot), (pseq / nslot) & 1u);
+          }
+          c1 = DBG ? clock64() : 0;
+          tc::mbar_wait(tempty + acc, ((tile_ctr >> 2) & 1u) ^ 1u);
+          tc::tc_fence_after();
+          c2 = DBG ? clock64() : 0;
+          uint32_t pl16[3];
 #pragma unroll
-        for (int kt = 0; kt < 3; ++kt) {
-          // a plane that lies entirely in the zero border of a padded gradient contributes nothing (warp-uniform)
-          if (tin + kt < a.zero_planes || tin + kt >= a.Ti - a.zero_planes) continue;
+          for (int kt = 0; kt < 3; ++kt) pl16[kt] = slot_addr16 + ((base_seq + ti + kt) % nslot) * slot_16;
+          uint32_t acc_flag = 0;
+          const uint32_t d_tmem = tmem_base + acc * N;
+          const int tin = r.t0 + ti;  // first input time plane of this tile
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
+          for (int kt = 0; kt < 3; ++kt) {
+            // a plane that lies entirely in the zero border of a padded gradient contributes nothing (warp-uniform)
+            if (tin + kt < a.zero_planes || tin + kt >= a.Ti - a.zero_planes) continue;
 #pragma unroll
-            for (int ks = 0; ks < CG / 2; ++ks) {
+            for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-              for (int rb = 0; rb < 2; ++rb) {
-                const uint32_t d_tmem = tmem_base + (acc * 2u + rb) * N;
-                // A: rows rb*128.. of plane kt shifted by kh input rows; channel groups 2ks, 2ks+1
-                const uint32_t a16 = pl16[kt] + static_cast<uint32_t>(2 * ks) * (a_lbo >> 4) + rb * 128u + kh * wi;
+              for (int ks = 0; ks < CG / 2; ++ks) {
+                // A: the 128 rows of plane kt shifted by kh input rows; channel groups 2ks, 2ks+1
+                const uint32_t a16 = pl16[kt] + static_cast<uint32_t>(2 * ks) * (a_lbo >> 4) + kh * wi;
                 const uint32_t b16 = static_cast<uint32_t>(((kt * 3 + kh) * CG + 2 * ks)) * (b_lbo >> 4);
                 if (leader)
                   igemm_mma(d_tmem, a_lo_base | (a16 & 0x3fffu), desc_hi, b_lo_base + b16, desc_hi, idesc, acc_flag);
+                acc_flag = 1;
               }
-              acc_flag = 1;
             }
           }
         }
         __syncwarp();
         if (leader) {
-          tc::umma_commit(tfull + acc);                       // accumulators ready for the epilogue
-          tc::umma_commit(empty + ((base_seq + ti) % nslot));  // oldest time plane is free
+          if (mine) tc::umma_commit(tfull + acc);              // accumulators ready for the epilogue
+          // both warps: this warp's MMAs that read the oldest time plane (its own earlier tiles) are done
+          tc::umma_commit(empty + ((base_seq + ti) % nslot));
           if (ti == r.ntiles - 1) {
             tc::umma_commit(empty + ((base_seq + ti + 1) % nslot));
             tc::umma_commit(empty + ((base_seq + ti + 2) % nslot));
@@ -237,139 +255,180 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
       base_seq += r.ntiles + 2;
       g += r.ntiles;
     }
-    if (DBG && a.dbg && lane == 0) {
+    if (DBG && a.dbg && lane == 0 && warp == 1) {
       long long* d = a.dbg + blockIdx.x * 8;
       d[0] = clock64() - dbg_t0; d[1] = dbg_full; d[2] = dbg_tempty; d[3] = dbg_issue; d[4] = tile_ctr;
     }
   } else {
     // =============================== epilogue (warps 2..17) ===============================
     // out[r][co] = D[r][co] + D[r+1][CoP + co] + D[r+2][2 CoP + co]   (the kw shift-add; rows = TMEM lanes)
-    // 16 warps: warp % 4 = the TMEM lane quadrant a warp may access; (warp-2)/4 selects (row block, half of the
-    // output channels).  Rows r+1 / r+2 come from the neighbouring lanes by shuffle; the two rows that live in the
-    // next quadrant (another warp) are exchanged through shared memory and patched into lanes 0 / 1 BEFORE a rotating
-    // shuffle, so no per-element select is needed.
-    const int qd = warp & 3;
-    const int rbh = (warp - 2) >> 2;
-    const int rb = rbh >> 1, half = rbh & 1;
+    // 16 warps = 4 groups x 4 TMEM lane quadrants.  Group g owns the tiles whose accumulators live in TMEM buffer g
+    // (tile_ctr % 4 == g); a warp handles its 32 rows in two passes of 16 output channels.  Rows r+1 / r+2
+    // come from the neighbouring lanes by shuffle; the two rows that live in the next quadrant (another warp) are
+    // exchanged through shared memory and patched into lanes 0 / 1 BEFORE a rotating shuffle, so no per-element select
+    // is needed.
+    const int e = warp - 2;
+    const int qd = warp & 3;               // the TMEM lane quadrant this warp may access
+    const uint32_t grp = e >> 2;           // epilogue group = TMEM accumulator buffer
     const int Cog = a.CogOut;
     const int CoP = a.CoP;
+    const int nhalf = Cog > 2 ? 2 : 1;     // passes of 16 output channels (2 channel groups)
     const int Top = a.To + 2 * a.out_pad, Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
     const long long oplane = static_cast<long long>(Hop) * Wop;
     const long long mplane = static_cast<long long>(a.Ho) * a.Wo;
-    const int row = rb * 128 + qd * 32 + lane;
-    const int me = rb * 4 + qd;
-    const bool has_nb = me < 7;  // the last quadrant of the tile has no neighbour: its rows 254/255 are not emitted
-    const bool active = (2 * half) < Cog;  // this warp's two channel groups exist in the output tensor
+    const int row = qd * 32 + lane;
+    const bool has_nb = qd < 3;  // the last quadrant of the tile has no neighbour: its rows 126/127 are not emitted
     const int src1 = (lane + 1) & 31, src2 = (lane + 2) & 31;
-    const float4* bias4 = reinterpret_cast<const float4*>(bias_s) + 4 * half;
+    float* xp = xch + (grp * 4 + qd) * 96;
     uint32_t tile_ctr = 0;
     long long dbg_tfull = 0, dbg_bar = 0, dbg_ld = 0, dbg_rest = 0;
     for (long long g = g_begin; g < g_end;) {
       const IgRun r = ig_run(g, g_end, a.To, a.tiles_q);
       const int q = r.qt * kIgTileOut + row;
       const int ho = q / a.Wi, wo = q - ho * a.Wi;
-      const bool valid = active && (row < kIgTileOut) && (ho < a.Ho) && (wo < a.Wo);
-      // element offsets of this thread's position in the output / mask tensors at t = t0, channel group 2*half
-      long long o_off = ((static_cast<long long>(r.b) * Cog + 2 * half) * Top + (r.t0 + a.out_pad)) * oplane +
+      const bool valid = (row < kIgTileOut) && (ho < a.Ho) && (wo < a.Wo);
+      // element offsets of this thread's position in the output / mask tensors at t = t0, channel group 0
+      long long o_off = (static_cast<long long>(r.b) * Cog * Top + (r.t0 + a.out_pad)) * oplane +
                         static_cast<long long>(ho + a.out_pad) * Wop + (wo + a.out_pad);
-      long long m_off = ((static_cast<long long>(r.b) * Cog + 2 * half) * a.To + r.t0) * mplane +
-                        static_cast<long long>(ho) * a.Wo + wo;
-      long long o2_off = ((static_cast<long long>(r.b) * Cog + 2 * half) * a.To + r.t0) * a.QP2 +
-                         static_cast<long long>(ho) * (a.Wo + 2) + wo;
+      long long m_off = (static_cast<long long>(r.b) * Cog * a.To + r.t0) * mplane + static_cast<long long>(ho) * a.Wo + wo;
+      long long o2_off = (static_cast<long long>(r.b) * Cog * a.To + r.t0) * a.QP2 + static_cast<long long>(ho) * (a.Wo + 2) + wo;
       const long long o2_cg = static_cast<long long>(a.To) * a.QP2;
       const long long o_cg = static_cast<long long>(Top) * oplane, m_cg = static_cast<long long>(a.To) * mplane;
       for (int ti = 0; ti < r.ntiles; ++ti, ++tile_ctr, o_off += oplane, m_off += mplane, o2_off += a.QP2) {
-        const uint32_t acc = tile_ctr & 1u;
+        if ((tile_ctr & (kIgAcc - 1)) != grp) continue;
         // ReLU-mask source of the data gradient: issue the loads before waiting for the accumulators
         uint4 mk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
         if (a.mask && valid) {
           mk[0] = __ldg(a.mask + m_off);
-          if (2 * half + 1 < Cog) mk[1] = __ldg(a.mask + m_off + m_cg);
+          mk[1] = __ldg(a.mask + m_off + m_cg);
         }
         const long long e0 = DBG ? clock64() : 0;
-        tc::mbar_wait(tfull + acc, (tile_ctr >> 1) & 1u);
+        tc::mbar_wait(tfull + grp, (tile_ctr >> 2) & 1u);
         tc::tc_fence_after();
-        const long long l0 = DBG ? clock64() : 0;
-        float* xp = xch + (tile_ctr & 1u) * (2 * 4 * 96);
-        uint32_t v0[16], v1[16], v2[16];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + (acc * 2u + rb) * N + 16 * half;
-        tc::tmem_ld_32x16(taddr, v0);
-        tc::tmem_ld_32x16(taddr + CoP, v1);
-        tc::tmem_ld_32x16(taddr + 2 * CoP, v2);
-        tc::tmem_ld_wait();
-        // all TMEM reads of this warp are done: release the accumulator as early as possible
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tempty + acc);
-        const long long l1 = DBG ? clock64() : 0;
-        // publish this quadrant's first two rows of the kw=1 / kw=2 partial sums for the quadrant above it
-        if (lane < 2) {
-          uint4* dst = reinterpret_cast<uint4*>(xp + me * 96 + 16 * half);
-          if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(v1[4 * c], v1[4 * c + 1], v1[4 * c + 2], v1[4 * c + 3]);
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            dst[8 * (lane + 1) + c] = make_uint4(v2[4 * c], v2[4 * c + 1], v2[4 * c + 2], v2[4 * c + 3]);
+        long long l0 = DBG ? clock64() : 0;
+        if (DBG) dbg_tfull += l0 - e0;
+        if (DBG && (a.dbg_flags & 16)) {  // profiling: no epilogue work at all
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tempty + grp);
+          continue;
         }
-        asm volatile("bar.sync 1, 512;" ::: "memory");  // the sixteen epilogue warps
-        const long long e2 = DBG ? clock64() : 0;
-        // patch lanes 0 / 1 with the first two rows of the next quadrant, then rotate-shuffle
-        if (lane < 2 && has_nb) {
-          const uint4* nsrc = reinterpret_cast<const uint4*>(xp + (me + 1) * 96 + 16 * half);
-          if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 t4 = nsrc[c];
-              v1[4 * c] = t4.x; v1[4 * c + 1] = t4.y; v1[4 * c + 2] = t4.z; v1[4 * c + 3] = t4.w;
+        for (int half = 0; half < 2; ++half) {
+          if (half >= nhalf) break;
+          uint32_t v0[16], v1[16], v2[16];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + grp * N + 16 * half;
+          if (DBG && (a.dbg_flags & 4)) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { v0[c] = lane; v1[c] = c; v2[c] = tile_ctr; }
+          } else {
+            tc::tmem_ld_32x16(taddr, v0);
+            if (!(DBG && (a.dbg_flags & 8))) {
+              tc::tmem_ld_32x16(taddr + CoP, v1);
+              tc::tmem_ld_32x16(taddr + 2 * CoP, v2);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) { v1[c] = c; v2[c] = tile_ctr; }
             }
+            tc::tmem_ld_wait();
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 t4 = nsrc[8 * (lane + 1) + c];
-            v2[4 * c] = t4.x; v2[4 * c + 1] = t4.y; v2[4 * c + 2] = t4.z; v2[4 * c + 3] = t4.w;
+          if (half == nhalf - 1) {
+            // all TMEM reads of this warp are done: release the accumulator as early as possible
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tempty + grp);
           }
-        }
-        __syncwarp();
-        float o[16];
+          const long long l1 = DBG ? clock64() : 0;
+          // publish this quadrant's first two rows of the kw=1 / kw=2 partial sums for the quadrant above it
+          if (lane < 2) {
+            uint4* dst = reinterpret_cast<uint4*>(xp + 16 * half);
+            if (lane == 0) {
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 fb = bias4[c4];
-          const float eb[4] = {fb.x, fb.y, fb.z, fb.w};
+              for (int c = 0; c < 4; ++c) dst[c] = make_uint4(v1[4 * c], v1[4 * c + 1], v1[4 * c + 2], v1[4 * c + 3]);
+            }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c = 4 * c4 + j;
-            const float s1 = __shfl_sync(0xffffffffu, __uint_as_float(v1[c]), src1);
-            const float s2 = __shfl_sync(0xffffffffu, __uint_as_float(v2[c]), src2);
-            float x = (__uint_as_float(v0[c]) + eb[j]) + (s1 + s2);
-            if (a.relu) x = fmaxf(x, 0.f);
-            o[c] = x;
+            for (int c = 0; c < 4; ++c)
+              dst[8 * (lane + 1) + c] = make_uint4(v2[4 * c], v2[4 * c + 1], v2[4 * c + 2], v2[4 * c + 3]);
           }
-        }
-        if (valid) {
+          // the four warps of this group
+          if (DBG && (a.dbg_flags & 64)) {}
+          else if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else if (grp == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+          else if (grp == 2) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 4, 128;" ::: "memory");
+          const long long e2 = DBG ? clock64() : 0;
+          // patch lanes 0 / 1 with the first two rows of the next quadrant, then rotate-shuffle
+          if (lane < 2 && has_nb) {
+            const uint4* nsrc = reinterpret_cast<const uint4*>(xp + 96 + 16 * half);
+            if (lane == 0) {
 #pragma unroll
-          for (int g2 = 0; g2 < 2; ++g2) {
-            if (2 * half + g2 >= Cog) continue;
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = o[g2 * 8 + j];
-            if (a.mask) {
-              const uint32_t mw[4] = {mk[g2].x, mk[g2].y, mk[g2].z, mk[g2].w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
-                const float mv = __uint_as_float(bits << 16);
-                f[j] = (mv > 0.f) ? f[j] : 0.f;
+              for (int c = 0; c < 4; ++c) {
+                const uint4 t4 = nsrc[c];
+                v1[4 * c] = t4.x; v1[4 * c + 1] = t4.y; v1[4 * c + 2] = t4.z; v1[4 * c + 3] = t4.w;
               }
             }
-            const uint4 ov = make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]),
-                                        tc::pack_bf16(f[6], f[7]));
-            a.y[o_off + g2 * o_cg] = ov;
-            if (a.y2) a.y2[o2_off + g2 * o2_cg] = ov;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 t4 = nsrc[8 * (lane + 1) + c];
+              v2[4 * c] = t4.x; v2[4 * c + 1] = t4.y; v2[4 * c + 2] = t4.z; v2[4 * c + 3] = t4.w;
+            }
+          }
+          __syncwarp();
+          const float4* bias4 = reinterpret_cast<const float4*>(bias_s) + 4 * half;
+          float o[16];
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 fb = bias4[c4];
+            const float eb[4] = {fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = 4 * c4 + j;
+              float s1, s2;
+              if (DBG && (a.dbg_flags & 32)) {
+                s1 = __uint_as_float(v1[c]); s2 = __uint_as_float(v2[c]);
+              } else {
+                s1 = __shfl_sync(0xffffffffu, __uint_as_float(v1[c]), src1);
+                s2 = __shfl_sync(0xffffffffu, __uint_as_float(v2[c]), src2);
+              }
+              float x = (__uint_as_float(v0[c]) + eb[j]) + (s1 + s2);
+              if (a.relu) x = fmaxf(x, 0.f);
+              o[c] = x;
+            }
+          }
+          if (valid && !(DBG && (a.dbg_flags & 2))) {
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+              const int cgi = 2 * half + g2;
+              if (cgi >= Cog) continue;
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = o[g2 * 8 + j];
+              if (a.mask) {
+                const uint32_t mw[4] = {mk[g2].x, mk[g2].y, mk[g2].z, mk[g2].w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
+                  const float mv = __uint_as_float(bits << 16);
+                  f[j] = (mv > 0.f) ? f[j] : 0.f;
+                }
+              }
+              const uint4 ov = make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]),
+                                          tc::pack_bf16(f[6], f[7]));
+              a.y[o_off + cgi * o_cg] = ov;
+              if (a.y2) a.y2[o2_off + cgi * o2_cg] = ov;
+            }
+          }
+          // mask of the second pass: in flight while this pass's stores drain
+          if (half == 0 && nhalf == 2 && a.mask && valid) {
+            mk[0] = __ldg(a.mask + m_off + 2 * m_cg);
+            mk[1] = __ldg(a.mask + m_off + 3 * m_cg);
+          }
+          if (DBG) {
+            const long long e3 = clock64();
+            dbg_ld += l1 - l0; dbg_bar += e2 - l1; dbg_rest += e3 - e2;
+            l0 = e3;
           }
         }
-        if (DBG) { dbg_tfull += l0 - e0; dbg_ld += l1 - l0; dbg_bar += e2 - l1; dbg_rest += clock64() - e2; }
       }
       g += r.ntiles;
     }
@@ -429,6 +488,7 @@ __global__ void blocked_to_nc_f32_kernel(const uint4* __restrict__ x, float* __r
 }
 
 long long* g_igemm_dbg = nullptr;  // set through pvb200_debug_set_igemm_counters (tools only)
+int g_igemm_dbg_flags = 0;
 
 static int igemm_cg(int C) { return 2 * ceil_div(C, 16); }  // channel groups of 8, padded to an even count (UMMA K = 16)
 
@@ -484,6 +544,7 @@ static int launch_igemm(const void* xb, const float* w, long long s_co, long lon
   PVB_REQUIRE(nslot >= 4, "conv3d_bf16: Cin=%d Cout=%d width=%d does not fit in shared memory", Ci, Co, Wi);
   a.nslot = static_cast<int>(nslot);
   a.dbg = g_igemm_dbg;
+  a.dbg_flags = g_igemm_dbg_flags;
   const size_t smem = fixed + nslot * slot_bytes;
   long long grid = a.tiles < sms ? a.tiles : sms;
 #define PVB_IG_LAUNCH(CG, DBG)                                                                                           \
@@ -507,6 +568,7 @@ extern "C" {
 
 /* tools only (not declared in pvb200.h): per-CTA cycle counters of the igemm kernel, [grid][8] long long */
 void pvb200_debug_set_igemm_counters(long long* p) { pvb::g_igemm_dbg = p; }
+void pvb200_debug_set_igemm_flags(int f) { pvb::g_igemm_dbg_flags = f; }
 
 int pvb200_blocked_channel_groups(int C) { return pvb::igemm_cg(C); }
 

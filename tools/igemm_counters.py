@@ -26,13 +26,16 @@ xb = ops.to_blocked_bf16(x)
 gzp = ops.to_blocked_bf16(gz, pad=2)
 run = (lambda: ops.conv3d_fwd_bf16(xb, w, b)) if which == "fwd" else (lambda: ops.conv3d_dgrad_bf16(gzp, w, xb))
 run()
-dbg = torch.zeros((148, 8), dtype=torch.int64, device=dev)
 L.pvb200_debug_set_igemm_counters.argtypes = [ctypes.c_void_p]
-L.pvb200_debug_set_igemm_counters(dbg.data_ptr())
-run()
-torch.cuda.synchronize()
-L.pvb200_debug_set_igemm_counters(None)
-d = dbg.double().cpu()
 names = ["mma_total", "mma_wait_full", "mma_wait_tempty", "mma_issue", "epi_rest(neg)", "epi_wait_tfull", "epi_wait_bar", "epi_ld"]
-m = d.mean(0)
-print(which, "layer", layer, {n: round(float(m[i])) for i, n in enumerate(names)})
+for flags in (0, 32, 64, 96, 98):
+    dbg = torch.zeros((148, 8), dtype=torch.int64, device=dev)
+    L.pvb200_debug_set_igemm_counters(dbg.data_ptr())
+    L.pvb200_debug_set_igemm_flags(flags)
+    run()
+    torch.cuda.synchronize()
+    L.pvb200_debug_set_igemm_counters(None)
+    L.pvb200_debug_set_igemm_flags(0)
+    d = dbg.double().cpu()
+    m = d.mean(0)
+    print(which, "layer", layer, "flags", flags, {n: round(float(m[i])) for i, n in enumerate(names)}, "max total", int(d[:, 0].max()))

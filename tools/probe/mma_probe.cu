@@ -14,7 +14,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 
 // layout: 0 none, 1 = 128B_base32B, 2 = 128B, 4 = 64B, 6 = 32B
 __global__ void probe(int layout, int N, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, int iters, int nacc,
-                      long long* out, int M = 128, int nissuers = 1, int always_overwrite = 0, int amaj = 0, int bmaj = 0) {
+                      long long* out, int M = 128, int nissuers = 1, int always_overwrite = 0, int amaj = 0, int bmaj = 0, int a_step = 8, int b_step = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tptr;
@@ -39,7 +39,7 @@ __global__ void probe(int layout, int N, uint32_t a_lbo, uint32_t a_sbo, uint32_
     for (int i = 0; i < nacc; ++i) mma(tbase + i * N, ad, bd, idesc, 0);
     for (int i = 0; i < iters; i += 8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) mma(tbase + ((j & nmask) * N), ad + j * 8, bd, idesc, accflag);
+      for (int j = 0; j < 8; ++j) mma(tbase + ((j & nmask) * N), ad + j * a_step, bd + j * b_step, idesc, accflag);
     }
     tc::umma_commit(&bar);
     tc::mbar_wait(&bar, 0);
@@ -55,7 +55,7 @@ int main() {
   long long* out;
   cudaMalloc(&out, 148 * sizeof(long long));
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  struct Cfg { const char* name; int layout, N; uint32_t a_lbo, a_sbo, b_lbo, b_sbo; int nacc, M, nissuers, ow, amaj, bmaj; };
+  struct Cfg { const char* name; int layout, N; uint32_t a_lbo, a_sbo, b_lbo, b_sbo; int nacc, M, nissuers, ow, amaj, bmaj; int a_step = 8, b_step = 0; };
   Cfg cfgs[] = {
       // name, layout, N, a_lbo, a_sbo, b_lbo, b_sbo, nacc, M, issuers, overwrite, amaj, bmaj
       {"K/K   none  N=32", 0, 32, 6144, 128, 512, 128, 1, 128, 1, 0, 0, 0},
@@ -69,11 +69,33 @@ int main() {
       {"MN/MN none  N=128", 0, 128, 128, 4096, 128, 2048, 1, 128, 1, 0, 1, 1},
       {"MN/MN sw128 N=128", 2, 128, 8192, 1024, 8192, 1024, 1, 128, 1, 0, 1, 1},
       {"MN/MN sw128 N=256", 2, 256, 8192, 1024, 8192, 1024, 1, 128, 1, 0, 1, 1},
+      {"K/K   none  N=96", 0, 96, 6144, 128, 1536, 128, 1, 128, 1, 0, 0, 0},
+      {"K/K   none  N=128", 0, 128, 6144, 128, 2048, 128, 1, 128, 1, 0, 0, 0},
+      {"K/K   none  N=256", 0, 256, 6144, 128, 4096, 128, 1, 128, 1, 0, 0, 0},
+      {"K/K   none  N=32 x2 issuers", 0, 32, 6144, 128, 512, 128, 1, 128, 2, 0, 0, 0},
+      {"K/K   none  N=32 x4 issuers", 0, 32, 6144, 128, 512, 128, 1, 128, 4, 0, 0, 0},
+      {"K/K   none  N=32 4 acc", 0, 32, 6144, 128, 512, 128, 4, 128, 1, 0, 0, 0},
+      {"K/K   none  N=96 4 acc", 0, 96, 6144, 128, 1536, 128, 4, 128, 1, 0, 0, 0},
+      {"K/K   none  N=32 M=64", 0, 32, 6144, 128, 512, 128, 1, 64, 1, 0, 0, 0},
+      {"K/K   none  N=96 M=64", 0, 96, 6144, 128, 1536, 128, 1, 64, 1, 0, 0, 0},
+      {"MN/MN none  N=96", 0, 96, 128, 4096, 128, 2048, 1, 128, 1, 0, 1, 1},
+      {"MN/MN none  N=96 4 acc", 0, 96, 128, 4096, 128, 2048, 4, 128, 1, 0, 1, 1},
+      {"K/K none N=96 A fixed B fixed", 0, 96, 6144, 128, 1536, 128, 1, 128, 1, 0, 0, 0, 0, 0},
+      {"K/K none N=96 A var(2KB) B fixed", 0, 96, 6144, 128, 1536, 128, 1, 128, 1, 0, 0, 0, 128, 0},
+      {"K/K none N=96 A fixed B var(3KB)", 0, 96, 6144, 128, 1536, 128, 1, 128, 1, 0, 0, 0, 0, 192},
+      {"K/K none N=96 A var B var", 0, 96, 6144, 128, 1536, 128, 1, 128, 1, 0, 0, 0, 128, 192},
+      {"K/K none N=96 A var misaligned B var", 0, 96, 6144, 128, 1536, 128, 1, 128, 1, 0, 0, 0, 62, 192},
+      {"K/K none N=32 A var B var", 0, 32, 6144, 128, 512, 128, 1, 128, 1, 0, 0, 0, 128, 64},
+      {"K/K none N=32 A var B var x2 issuers", 0, 32, 6144, 128, 512, 128, 1, 128, 2, 0, 0, 0, 128, 64},
+      {"K/K none N=128 A var B var", 0, 128, 6144, 128, 2048, 128, 1, 128, 1, 0, 0, 0, 128, 256},
+      {"K/K none N=256 A var B var", 0, 256, 6144, 128, 4096, 128, 1, 128, 1, 0, 0, 0, 128, 512},
+      {"K/K sw128 N=256 A var B var", 2, 256, 8192, 1024, 8192, 1024, 1, 128, 1, 0, 0, 0, 128, 512},
+      {"K/K sw128 N=96 A var B var", 2, 96, 8192, 1024, 8192, 1024, 1, 128, 1, 0, 0, 0, 128, 192},
   };
   const int iters = 2000;
   for (auto& c : cfgs) {
     const int grid = 148;
-    probe<<<grid, 128, 160 * 1024>>>(c.layout, c.N, c.a_lbo, c.a_sbo, c.b_lbo, c.b_sbo, iters, c.nacc, out, c.M, c.nissuers, c.ow, c.amaj, c.bmaj);
+    probe<<<grid, 128, 160 * 1024>>>(c.layout, c.N, c.a_lbo, c.a_sbo, c.b_lbo, c.b_sbo, iters, c.nacc, out, c.M, c.nissuers, c.ow, c.amaj, c.bmaj, c.a_step, c.b_step);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: CUDA error %s\n", c.name, cudaGetErrorString(e)); return 1; }
     long long h[148];
