@@ -5,26 +5,33 @@
 //
 // Data layout ("blocked", NC8DHW8c): activations are [B][Cg][T][H][W][8] bf16 -- channel groups of 8 (16 bytes)
 // innermost.  With it the implicit GEMM needs NO im2col and no swizzle:
-//   * GEMM M = output positions, N = output channels, K = 27 taps x Cin.
-//   * positions are flattened with the INPUT pitch: q = ho*Wi + wo, so the A operand of tap (kt,kh,kw) for rows
-//     q0..q0+127 is the contiguous run of 16-byte elements starting at q0 + kh*Wi + kw of input plane t+kt:
-//     exactly the SWIZZLE_NONE K-major canonical layout (8 rows x 16 B core matrices, SBO = 128 B, LBO = the
-//     stride between channel-group planes).  A tap is just a different descriptor start address (measured with
+//   * GEMM M = output positions, K = Cin per tap, N = output channels.
+//   * positions are flattened with the INPUT pitch: q = ho*Wi + wo, so the A operand of tap (kh,kw) for rows
+//     q0..q0+127 is the contiguous run of 16-byte elements starting at q0 + kh*Wi + kw of an input plane: exactly the
+//     SWIZZLE_NONE K-major canonical layout (8 rows x 16 B core matrices, SBO = 128 B, LBO = the stride between
+//     channel-group planes).  A tap is just a different descriptor start address (measured with
 //     tools/probe/mma_probe.cu: start addresses that are not 128-byte aligned cost nothing).
-//   * one input plane segment (all channel groups, 128 + 2*Wi positions) is ONE bulk copy per channel group
-//     (cp.async.bulk, completion on an mbarrier; many small per-row copies were measured ~50 clk each and lose); a ring
-//     keeps 3 time planes live + the rest in flight, so walking along t re-loads nothing.
+//   * Cout = 32 alone would make N = 32 MMAs, which one thread cannot issue faster than one per ~54 clk (16 clk of
+//     math).  So the three TIME taps are merged into N = 96 and the loop runs over INPUT planes ("scatter" form):
+//     for input plane p,  D[r, kt*32+co] += sum_{kh,kw,ci} x[p, r + kh*Wi + kw, ci] * w[co,ci,kt,kh,kw]  is the
+//     contribution of plane p to the outputs t = p - kt.  The accumulators of consecutive output planes sit side by
+//     side in TMEM in DESCENDING order (output j of a run in columns (15-j)*32 ...), so the three blocks of one MMA
+//     are one contiguous 96-column window that slides down by 32 columns per input plane: the kt sum happens inside
+//     the tensor core, an output plane is complete after three input planes, and the epilogue is a plain
+//     TMEM -> bias/ReLU -> bf16 -> store with no cross-row traffic.  (An earlier version merged the kw taps instead;
+//     its shift-add epilogue -- 3x the TMEM reads, 2 shuffles per output, a cross-warp exchange -- cost twice the
+//     MMA time.)  The first and last two planes of a run use a narrower window (N = 32 / 64).
+//   * the first MMA that touches an accumulator must overwrite it: the first MMA of a plane is split into the
+//     blocks that are fresh (accumulate = 0) and the rest.
+//   * one input plane segment (all channel groups, 128 + 2*Wi + 2 positions) is ONE bulk copy per channel group
+//     (cp.async.bulk, completion on an mbarrier) into a ring; each plane is consumed by 18 MMAs and released.
 //   * all 27 x Cin x Cout weights (55 KB bf16) stay resident in shared memory for the whole persistent CTA.
 //   * wrap columns (wo >= Wo) are computed and dropped in the epilogue (2/Wi ~ 3 % waste).
-// Warp roles (608 threads): warp 0 = copy producer, warps 1 and 18 = MMA issuers (one elected thread each; warp 1
-// owns the TMEM allocation).  One thread cannot issue tcgen05.mma faster than one per ~54 clk plus the descriptor
-// arithmetic in between (measured 74 clk per MMA in this loop, against 56 clk of tensor-pipe time at N = 96), so the
-// two issuers take alternate tiles (different TMEM accumulators) and their issue latencies overlap.
-// warps 2-17 = epilogue (TMEM -> registers -> bias/ReLU or ReLU-mask -> bf16 -> 16-byte stores); accumulators are
-// quadruple-buffered in TMEM (4 x 96 columns) and the epilogue warps form FOUR groups of four (one warp per TMEM lane
-// quadrant) that own every fourth tile (group = TMEM buffer), so the latency chain of one tile's epilogue (TMEM load,
-// boundary-row exchange, shuffles, stores) spans four tiles of MMA time and the MMA warp runs three tiles ahead.
-// The data gradient is the same kernel on a zero-padded gz (padding 2) with flipped / transposed weights.
+// Warp roles (576 threads): warp 0 = copy producer, warp 1 = MMA issuer (one elected thread) + TMEM owner,
+// warps 2-17 = epilogue: four groups of four warps (one per TMEM lane quadrant), accumulator slot s is read by group
+// s % 4; up to 16 output planes of a run live in TMEM (512 columns), so the epilogue has a whole run of slack.
+// The data gradient is the same kernel on a zero-padded gz (padding 2) with flipped / transposed weights; input
+// planes that lie in the zero padding are skipped.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -32,34 +39,32 @@
 
 namespace pvb {
 
-constexpr int kIgThreads = 608;  // producer warp, MMA warp, 16 epilogue warps, second MMA warp
-constexpr int kIgMmaWarp2 = 18;  // the second MMA issuer
-constexpr int kIgMaxSlots = 8;  // time-plane ring: 3 planes live per tile + (nslot - 3) planes of prefetch distance
-constexpr int kIgTileM = 128;    // MMA rows per tile
-constexpr int kIgTileOut = 126;  // outputs per tile: the kw shift-add needs rows r, r+1, r+2
-constexpr int kIgAcc = 4;        // TMEM accumulator buffers = epilogue groups
+constexpr int kIgThreads = 576;  // producer warp, MMA warp, 16 epilogue warps
+constexpr int kIgMaxSlots = 8;   // input-plane ring
+constexpr int kIgTileM = 128;    // MMA rows = output positions per tile
+constexpr int kIgAccSlots = 16;  // output-plane accumulators resident in TMEM = longest run segment
 
 struct IgemmArgs {
   const uint4* x;     // [B][Cg][Ti][Hi][Wi] 16-byte elements (8 bf16 channels)
-  const uint4* wq;    // [9 (kt,kh)][Cg][3 (kw)][CoP] 16-byte elements: 8 input channels of one (kw, output channel)
+  const uint4* wq;    // [9 (kh,kw)][Cg][3 (kt)][CoP] 16-byte elements: 8 input channels of one (kt, output channel)
   const float* bias;  // [Co] or null
   const uint4* mask;  // [B][CogOut][To][Ho][Wo] or null
   uint4* y;           // [B][CogOut][To+2p][Ho+2p][Wo+2p]
   uint4* y2;          // optional second copy in the wgrad operand layout [B][CogOut][To][QP2], pitch Wo + 2 (or null)
   int QP2;
   int B, Cg, Ti, Hi, Wi;
-  int CoP, Co, CogOut, To, Ho, Wo;  // CoP = Cout padded to 16/32; MMA N = 3*CoP (the three kw taps side by side)
+  int CoP, Co, CogOut, To, Ho, Wo;  // CoP = Cout padded to 16/32; MMA N = 3*CoP (the three kt taps side by side)
   int out_pad, relu;
   int zero_planes;  // the first / last `zero_planes` input time planes are all zero (padded gz): their MMAs are skipped
   int NP;       // staged positions per (plane, channel group)
   int tiles_q;  // q tiles per output plane
-  int nslot;  // ring slots (4..8), as many as fit in shared memory
+  int nslot;    // ring slots, as many as fit in shared memory (<= 8)
   long long* dbg;  // optional [grid][8] cycle counters (profiling builds of the tools; null in production)
-  int dbg_flags;   // profiling builds only: 1 = skip the plane copies (stale shared memory), 2 = skip the output stores
+  int dbg_flags;   // profiling builds only: 1 = skip the plane copies, 2 = skip the output stores, 16 = no epilogue
   long long tiles;  // B * tiles_q * To
 };
 
-// weights fp32 [Co][Ci][27] -> bf16 [(kt,kh)][Cg][kw*CoP + co][8 ci]; flipped / transposed roles for the data gradient
+// weights fp32 [Co][Ci][27] -> bf16 [(kh,kw)][Cg][kt*CoP + co][8 ci]; flipped / transposed roles for the data gradient
 __global__ void igemm_weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wq, int Ci_role,
                                          int Co_role, int Cg, int CoP, long long s_co, long long s_ci, int flip) {
   const int N = 3 * CoP;
@@ -68,10 +73,10 @@ __global__ void igemm_weight_prep_kernel(const float* __restrict__ w, __nv_bfloa
     const int c8 = idx & 7;
     const int n = (idx >> 3) % N;
     const int cg = (idx / (8 * N)) % Cg;
-    const int tg = idx / (8 * N * Cg);  // kt*3 + kh
-    const int kw = n / CoP, co = n - kw * CoP;
+    const int hw = idx / (8 * N * Cg);  // kh*3 + kw
+    const int kt = n / CoP, co = n - kt * CoP;
     const int ci = cg * 8 + c8;
-    const int tap = tg * 3 + kw;
+    const int tap = kt * 9 + hw;
     float v = 0.f;
     if (co < Co_role && ci < Ci_role) v = w[co * s_co + ci * s_ci + (flip ? 26 - tap : tap)];
     wq[idx] = __float2bfloat16_rn(v);
@@ -93,9 +98,9 @@ __device__ __forceinline__ void igemm_mma(uint32_t d_tmem, uint32_t a_lo, uint32
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
 }
 
-// A "run" = consecutive output time steps of one (sample, q-tile) column handled by one CTA.  Tiles are numbered
-// g = (b * tiles_q + qt) * To + t and split evenly (tile-granular) over the persistent CTAs; every role walks the same
-// sequence of runs.  The first tile of a run needs three fresh input planes, every further tile one.
+// A "run" = consecutive output time steps of one (sample, q-tile) column handled by one CTA (at most 16: they all
+// live in TMEM).  Output tiles are numbered g = (b * tiles_q + qt) * To + t and split evenly (tile-granular) over the
+// persistent CTAs; every role walks the same sequence of runs.  A run of n outputs consumes n + 2 input planes.
 struct IgRun {
   int b, qt, t0, ntiles;
 };
@@ -106,35 +111,35 @@ __device__ __forceinline__ IgRun ig_run(long long g, long long g_end, int To, in
   r.qt = static_cast<int>(col % tiles_q);
   r.b = static_cast<int>(col / tiles_q);
   const long long left = g_end - g;
-  r.ntiles = static_cast<int>(left < (To - r.t0) ? left : (To - r.t0));
+  int n = static_cast<int>(left < (To - r.t0) ? left : (To - r.t0));
+  r.ntiles = n < kIgAccSlots ? n : kIgAccSlots;
   return r;
 }
 
 template <int CG, bool DBG>
 __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const IgemmArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]
-  uint64_t* empty = full + kIgMaxSlots;                     // [8]
-  uint64_t* wfull = empty + kIgMaxSlots;                    // [1]
-  uint64_t* tfull = wfull + 1;                              // [4]
-  uint64_t* tempty = tfull + kIgAcc;                        // [4]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + kIgAcc);
-  float* bias_s = reinterpret_cast<float*>(smem + 256);     // [32]
-  float* xch = reinterpret_cast<float*>(smem + 384);        // [4 groups][4 qd][3*32] boundary rows of the shift-add
-  uint8_t* w_s = smem + 384 + 2 * 2 * 4 * 96 * 4;
-  const int N = 3 * a.CoP;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]  input plane landed
+  uint64_t* empty = full + kIgMaxSlots;                     // [8]  input plane consumed
+  uint64_t* wfull = empty + kIgMaxSlots;                    // [1]  weights landed
+  uint64_t* tfull = wfull + 1;                              // [16] output accumulator complete
+  uint64_t* tempty = tfull + kIgAccSlots;                   // [16] output accumulator read out
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + kIgAccSlots);
+  float* bias_s = reinterpret_cast<float*>(smem + 512);     // [32]
+  uint8_t* w_s = smem + 640;
+  const int CoP = a.CoP;
+  const int N = 3 * CoP;
   const uint32_t w_bytes = 9u * CG * N * 16u;
   const uint32_t slot_bytes = static_cast<uint32_t>(CG) * a.NP * 16u;
   uint8_t* slot_s = w_s + ((w_bytes + 127u) & ~127u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (4u * N <= 256u) ? 256u : 512u;
+  const uint32_t tmem_cols = static_cast<uint32_t>(kIgAccSlots * CoP);  // 512 or 256
 
   if (threadIdx.x == 0) {
-    // a plane slot is released by BOTH MMA warps (tcgen05.commit only tracks the MMAs of the committing thread)
-    for (int i = 0; i < kIgMaxSlots; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 2); }
+    for (int i = 0; i < kIgMaxSlots; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
     tc::mbar_init(wfull, 1);
-    for (int i = 0; i < kIgAcc; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
+    for (int i = 0; i < kIgAccSlots; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
@@ -160,30 +165,31 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
       uint32_t seq = 0;
       for (long long g = g_begin; g < g_end;) {
         const IgRun r = ig_run(g, g_end, a.To, a.tiles_q);
-        const int q0 = r.qt * kIgTileOut;
+        const int q0 = r.qt * kIgTileM;
         const long long avail = in_plane - q0;
         const uint32_t npos = static_cast<uint32_t>(avail < a.NP ? avail : a.NP);
-        for (int p = 0; p < r.ntiles + 2; ++p, ++seq) {
+        for (int p = 0; p < r.ntiles + 2; ++p) {
+          const int pa = r.t0 + p;  // absolute input plane
+          if (pa < a.zero_planes || pa >= a.Ti - a.zero_planes) continue;  // all-zero plane: never staged
           const uint32_t slot = seq % nslot;
           tc::mbar_wait(empty + slot, ((seq / nslot) & 1u) ^ 1u);
+          ++seq;
           if (DBG && (a.dbg_flags & 1)) { tc::mbar_arrive(full + slot); continue; }
           tc::mbar_arrive_expect_tx(full + slot, npos * 16u * CG);
 #pragma unroll
           for (int cg = 0; cg < CG; ++cg) {
-            const uint4* src = a.x + ((static_cast<long long>(r.b) * CG + cg) * a.Ti + (r.t0 + p)) * in_plane + q0;
+            const uint4* src = a.x + ((static_cast<long long>(r.b) * CG + cg) * a.Ti + pa) * in_plane + q0;
             tc::bulk_g2s(slot_s + slot * slot_bytes + static_cast<uint32_t>(cg) * a.NP * 16u, src, npos * 16u, full + slot);
           }
         }
         g += r.ntiles;
       }
     }
-  } else if (warp == 1 || warp == kIgMmaWarp2) {
-    // =============================== MMA issuers ===============================
-    const uint32_t mw = (warp == 1) ? 0u : 1u;  // this warp issues the tiles with tile_ctr % 2 == mw
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
     // The whole warp runs the (warp-uniform) control flow so that descriptor arithmetic stays in uniform registers;
     // only the tcgen05.mma / tcgen05.commit instructions themselves are issued by one elected lane.
     const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::umma_idesc(128, N, /*bf16*/ 1, /*K-major*/ 0, 0);
     const uint32_t a_lbo = static_cast<uint32_t>(a.NP) * 16u;
     const uint32_t b_lbo = static_cast<uint32_t>(N) * 16u;
     // descriptor halves: hi = SBO (128 B) | version; lo = start address | LBO
@@ -192,101 +198,104 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
     const uint32_t b_lo_base = ((b_lbo >> 4) << 16) | ((tc::smem_u32(w_s) >> 4) & 0x3fffu);
     const uint32_t slot_addr16 = tc::smem_u32(slot_s) >> 4;  // in 16-byte units
     const uint32_t slot_16 = slot_bytes >> 4;
-    const uint32_t wi = static_cast<uint32_t>(a.Wi);
+    const uint32_t a_ks16 = 2u * (a_lbo >> 4), b_ks16 = 2u * (b_lbo >> 4), b_tap16 = static_cast<uint32_t>(CG) * (b_lbo >> 4);
+    uint32_t tap16[9];  // A start offset of tap (kh,kw) in 16-byte units
+#pragma unroll
+    for (int hw = 0; hw < 9; ++hw) tap16[hw] = static_cast<uint32_t>((hw / 3) * a.Wi + (hw % 3));
+    // instruction descriptor for N = nb blocks of CoP columns: idesc0 + nb * idesc_blk
+    const uint32_t idesc0 = tc::umma_idesc(128, 0, /*bf16*/ 1, /*K-major*/ 0, 0);
+    const uint32_t idesc_blk = static_cast<uint32_t>(CoP >> 3) << 17;
     tc::mbar_wait(wfull, 0);
-    uint32_t base_seq = 0, tile_ctr = 0;
-    long long dbg_full = 0, dbg_tempty = 0, dbg_issue = 0;
+    uint32_t seq = 0;            // staged input planes consumed so far
+    uint32_t acc_phase = 0;      // bit s = number of uses of accumulator slot s so far, mod 2
+    long long dbg_full = 0, dbg_tempty = 0, dbg_issue = 0, dbg_planes = 0;
     const long long dbg_t0 = DBG ? clock64() : 0;
     for (long long g = g_begin; g < g_end;) {
       const IgRun r = ig_run(g, g_end, a.To, a.tiles_q);
-      for (int ti = 0; ti < r.ntiles; ++ti, ++tile_ctr) {
+      const int nt = r.ntiles;
+      int skipped = 0;  // number of consecutive skipped planes immediately before plane i
+      for (int i = 0; i < nt + 2; ++i) {
         const long long c0 = DBG ? clock64() : 0;
         long long c1 = c0, c2 = c0;
-        const uint32_t acc = tile_ctr & (kIgAcc - 1);
-        const bool mine = (tile_ctr & 1u) == mw;
-        if (mine) {
-          // the three planes of this tile (none of them can have been recycled: this warp has not released them yet)
-#pragma unroll
-          for (int kt = 0; kt < 3; ++kt) {
-            const uint32_t pseq = base_seq + ti + kt;
-            tc::mbar_wait(full + (pseq % nslot), (pseq / nslot) & 1u);
-          }
-          c1 = DBG ? clock64() : 0;
-          tc::mbar_wait(tempty + acc, ((tile_ctr >> 2) & 1u) ^ 1u);
+        // the accumulator of output i is first written by this plane: it must have been read out by the epilogue
+        if (i < nt) {
+          const uint32_t s = static_cast<uint32_t>(kIgAccSlots - 1 - i);
+          tc::mbar_wait(tempty + s, ((acc_phase >> s) & 1u) ^ 1u);
+          tc::tc_fence_after();
+        }
+        c1 = DBG ? clock64() : 0;
+        const int pa = r.t0 + i;
+        const bool skip = pa < a.zero_planes || pa >= a.Ti - a.zero_planes;
+        if (!skip) {
+          const uint32_t slot = seq % nslot;
+          tc::mbar_wait(full + slot, (seq / nslot) & 1u);
           tc::tc_fence_after();
           c2 = DBG ? clock64() : 0;
-          uint32_t pl16[3];
+          // blocks kt_lo..kt_hi of this plane exist (output i - kt inside the run); blocks kt < nfresh_end are fresh
+          const int kt_lo = (i - (nt - 1)) > 0 ? (i - (nt - 1)) : 0;
+          const int kt_hi = i < 2 ? i : 2;
+          const int fresh_hi = skipped < kt_hi ? skipped : kt_hi;  // blocks kt <= fresh_hi have not been written yet
+          const uint32_t a_base = a_lo_base | ((slot_addr16 + slot * slot_16) & 0x3fffu);
+          // accumulator column of block kt: output i - kt lives in slot 15 - (i - kt)
+          const uint32_t d_lo = tmem_base + static_cast<uint32_t>((kIgAccSlots - 1 - i + kt_lo) * CoP);
+          const uint32_t b_base = b_lo_base + static_cast<uint32_t>(kt_lo * CoP);
+          const int nb_all = kt_hi - kt_lo + 1;
+          const int nb_fresh = fresh_hi >= kt_lo ? (fresh_hi - kt_lo + 1) : 0;
+          if (leader) {
+            // first MMA (tap 0, channel groups 0,1): overwrite the fresh blocks, accumulate into the others
+            if (nb_fresh > 0) igemm_mma(d_lo, a_base, desc_hi, b_base, desc_hi, idesc0 + nb_fresh * idesc_blk, 0u);
+            if (nb_all > nb_fresh)
+              igemm_mma(d_lo + static_cast<uint32_t>(nb_fresh * CoP), a_base, desc_hi, b_base + static_cast<uint32_t>(nb_fresh * CoP),
+                        desc_hi, idesc0 + (nb_all - nb_fresh) * idesc_blk, 1u);
+            const uint32_t idesc = idesc0 + nb_all * idesc_blk;
 #pragma unroll
-          for (int kt = 0; kt < 3; ++kt) pl16[kt] = slot_addr16 + ((base_seq + ti + kt) % nslot) * slot_16;
-          uint32_t acc_flag = 0;
-          const uint32_t d_tmem = tmem_base + acc * N;
-          const int tin = r.t0 + ti;  // first input time plane of this tile
-#pragma unroll
-          for (int kt = 0; kt < 3; ++kt) {
-            // a plane that lies entirely in the zero border of a padded gradient contributes nothing (warp-uniform)
-            if (tin + kt < a.zero_planes || tin + kt >= a.Ti - a.zero_planes) continue;
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
+            for (int hw = 0; hw < 9; ++hw) {
 #pragma unroll
               for (int ks = 0; ks < CG / 2; ++ks) {
-                // A: the 128 rows of plane kt shifted by kh input rows; channel groups 2ks, 2ks+1
-                const uint32_t a16 = pl16[kt] + static_cast<uint32_t>(2 * ks) * (a_lbo >> 4) + kh * wi;
-                const uint32_t b16 = static_cast<uint32_t>(((kt * 3 + kh) * CG + 2 * ks)) * (b_lbo >> 4);
-                if (leader)
-                  igemm_mma(d_tmem, a_lo_base | (a16 & 0x3fffu), desc_hi, b_lo_base + b16, desc_hi, idesc, acc_flag);
-                acc_flag = 1;
+                if (hw == 0 && ks == 0) continue;
+                igemm_mma(d_lo, a_base + tap16[hw] + ks * a_ks16, desc_hi, b_base + hw * b_tap16 + ks * b_ks16, desc_hi, idesc, 1u);
               }
             }
+            tc::umma_commit(empty + slot);  // the input plane is consumed
           }
+          ++seq;
+          skipped = 0;
+        } else {
+          ++skipped;
+        }
+        // output i - 2 has received its last contribution
+        if (i >= 2) {
+          const uint32_t s = static_cast<uint32_t>(kIgAccSlots - 1 - (i - 2));
+          if (leader) tc::umma_commit(tfull + s);
+          acc_phase ^= 1u << s;
         }
         __syncwarp();
-        if (leader) {
-          if (mine) tc::umma_commit(tfull + acc);              // accumulators ready for the epilogue
-          // both warps: this warp's MMAs that read the oldest time plane (its own earlier tiles) are done
-          tc::umma_commit(empty + ((base_seq + ti) % nslot));
-          if (ti == r.ntiles - 1) {
-            tc::umma_commit(empty + ((base_seq + ti + 1) % nslot));
-            tc::umma_commit(empty + ((base_seq + ti + 2) % nslot));
-          }
-        }
-        __syncwarp();
-        if (DBG) { dbg_full += c1 - c0; dbg_tempty += c2 - c1; dbg_issue += clock64() - c2; }
+        if (DBG) { dbg_tempty += c1 - c0; dbg_full += c2 - c1; dbg_issue += clock64() - c2; ++dbg_planes; }
       }
-      base_seq += r.ntiles + 2;
-      g += r.ntiles;
+      g += nt;
     }
-    if (DBG && a.dbg && lane == 0 && warp == 1) {
+    if (DBG && a.dbg && lane == 0) {
       long long* d = a.dbg + blockIdx.x * 8;
-      d[0] = clock64() - dbg_t0; d[1] = dbg_full; d[2] = dbg_tempty; d[3] = dbg_issue; d[4] = tile_ctr;
+      d[0] = clock64() - dbg_t0; d[1] = dbg_full; d[2] = dbg_tempty; d[3] = dbg_issue; d[4] = dbg_planes;
     }
   } else {
     // =============================== epilogue (warps 2..17) ===============================
-    // out[r][co] = D[r][co] + D[r+1][CoP + co] + D[r+2][2 CoP + co]   (the kw shift-add; rows = TMEM lanes)
-    // 16 warps = 4 groups x 4 TMEM lane quadrants.  Group g owns the tiles whose accumulators live in TMEM buffer g
-    // (tile_ctr % 4 == g); a warp handles its 32 rows in two passes of 16 output channels.  Rows r+1 / r+2
-    // come from the neighbouring lanes by shuffle; the two rows that live in the next quadrant (another warp) are
-    // exchanged through shared memory and patched into lanes 0 / 1 BEFORE a rotating shuffle, so no per-element select
-    // is needed.
+    // four groups x four TMEM lane quadrants; group g reads the accumulator slots s with s % 4 == g
     const int e = warp - 2;
     const int qd = warp & 3;               // the TMEM lane quadrant this warp may access
-    const uint32_t grp = e >> 2;           // epilogue group = TMEM accumulator buffer
+    const uint32_t grp = e >> 2;
     const int Cog = a.CogOut;
-    const int CoP = a.CoP;
-    const int nhalf = Cog > 2 ? 2 : 1;     // passes of 16 output channels (2 channel groups)
     const int Top = a.To + 2 * a.out_pad, Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
     const long long oplane = static_cast<long long>(Hop) * Wop;
     const long long mplane = static_cast<long long>(a.Ho) * a.Wo;
     const int row = qd * 32 + lane;
-    const bool has_nb = qd < 3;  // the last quadrant of the tile has no neighbour: its rows 126/127 are not emitted
-    const int src1 = (lane + 1) & 31, src2 = (lane + 2) & 31;
-    float* xp = xch + (grp * 4 + qd) * 96;
-    uint32_t tile_ctr = 0;
-    long long dbg_tfull = 0, dbg_bar = 0, dbg_ld = 0, dbg_rest = 0;
+    uint32_t acc_phase = 0;
+    long long dbg_tfull = 0, dbg_ld = 0, dbg_rest = 0;
     for (long long g = g_begin; g < g_end;) {
       const IgRun r = ig_run(g, g_end, a.To, a.tiles_q);
-      const int q = r.qt * kIgTileOut + row;
+      const int q = r.qt * kIgTileM + row;
       const int ho = q / a.Wi, wo = q - ho * a.Wi;
-      const bool valid = (row < kIgTileOut) && (ho < a.Ho) && (wo < a.Wo);
+      const bool valid = (ho < a.Ho) && (wo < a.Wo);
       // element offsets of this thread's position in the output / mask tensors at t = t0, channel group 0
       long long o_off = (static_cast<long long>(r.b) * Cog * Top + (r.t0 + a.out_pad)) * oplane +
                         static_cast<long long>(ho + a.out_pad) * Wop + (wo + a.out_pad);
@@ -294,147 +303,78 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
       long long o2_off = (static_cast<long long>(r.b) * Cog * a.To + r.t0) * a.QP2 + static_cast<long long>(ho) * (a.Wo + 2) + wo;
       const long long o2_cg = static_cast<long long>(a.To) * a.QP2;
       const long long o_cg = static_cast<long long>(Top) * oplane, m_cg = static_cast<long long>(a.To) * mplane;
-      for (int ti = 0; ti < r.ntiles; ++ti, ++tile_ctr, o_off += oplane, m_off += mplane, o2_off += a.QP2) {
-        if ((tile_ctr & (kIgAcc - 1)) != grp) continue;
+      for (int j = 0; j < r.ntiles; ++j, o_off += oplane, m_off += mplane, o2_off += a.QP2) {
+        const uint32_t s = static_cast<uint32_t>(kIgAccSlots - 1 - j);
+        const uint32_t ph = (acc_phase >> s) & 1u;
+        acc_phase ^= 1u << s;
+        // an accumulator slot always belongs to the same group: its warps then wait on consecutive phases of
+        // tfull[s] in order (a parity wait issued a whole phase early would pass immediately)
+        if ((s & 3u) != grp) continue;
         // ReLU-mask source of the data gradient: issue the loads before waiting for the accumulators
-        uint4 mk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        uint4 mk[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
         if (a.mask && valid) {
-          mk[0] = __ldg(a.mask + m_off);
-          mk[1] = __ldg(a.mask + m_off + m_cg);
+#pragma unroll
+          for (int cgi = 0; cgi < 4; ++cgi)
+            if (cgi < Cog) mk[cgi] = __ldg(a.mask + m_off + cgi * m_cg);
         }
         const long long e0 = DBG ? clock64() : 0;
-        tc::mbar_wait(tfull + grp, (tile_ctr >> 2) & 1u);
+        tc::mbar_wait(tfull + s, ph);
         tc::tc_fence_after();
-        long long l0 = DBG ? clock64() : 0;
-        if (DBG) dbg_tfull += l0 - e0;
-        if (DBG && (a.dbg_flags & 16)) {  // profiling: no epilogue work at all
-          tc::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(tempty + grp);
-          continue;
+        const long long l0 = DBG ? clock64() : 0;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + s * CoP;
+        uint32_t v[32];
+        if (DBG && (a.dbg_flags & 16)) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = 0;
+        } else if (CoP == 32) {
+          tc::tmem_ld_32x32(taddr, v);
+        } else {
+          uint32_t h[16];
+          tc::tmem_ld_32x16(taddr, h);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { v[c] = h[c]; v[16 + c] = 0; }
         }
+        tc::tmem_ld_wait();
+        // all TMEM reads of this warp are done: release the accumulator
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty + s);
+        const long long l1 = DBG ? clock64() : 0;
+        if (valid && !(DBG && (a.dbg_flags & 2))) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (half >= nhalf) break;
-          uint32_t v0[16], v1[16], v2[16];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + grp * N + 16 * half;
-          if (DBG && (a.dbg_flags & 4)) {
+          for (int cgi = 0; cgi < 4; ++cgi) {
+            if (cgi >= Cog) continue;
+            const float4 b0 = reinterpret_cast<const float4*>(bias_s)[2 * cgi], b1 = reinterpret_cast<const float4*>(bias_s)[2 * cgi + 1];
+            const float eb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float f[8];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) { v0[c] = lane; v1[c] = c; v2[c] = tile_ctr; }
-          } else {
-            tc::tmem_ld_32x16(taddr, v0);
-            if (!(DBG && (a.dbg_flags & 8))) {
-              tc::tmem_ld_32x16(taddr + CoP, v1);
-              tc::tmem_ld_32x16(taddr + 2 * CoP, v2);
-            } else {
-#pragma unroll
-              for (int c = 0; c < 16; ++c) { v1[c] = c; v2[c] = tile_ctr; }
+            for (int jj = 0; jj < 8; ++jj) {
+              float xv = __uint_as_float(v[cgi * 8 + jj]) + eb[jj];
+              if (a.relu) xv = fmaxf(xv, 0.f);
+              f[jj] = xv;
             }
-            tc::tmem_ld_wait();
-          }
-          if (half == nhalf - 1) {
-            // all TMEM reads of this warp are done: release the accumulator as early as possible
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(tempty + grp);
-          }
-          const long long l1 = DBG ? clock64() : 0;
-          // publish this quadrant's first two rows of the kw=1 / kw=2 partial sums for the quadrant above it
-          if (lane < 2) {
-            uint4* dst = reinterpret_cast<uint4*>(xp + 16 * half);
-            if (lane == 0) {
+            if (a.mask) {
+              const uint32_t mw[4] = {mk[cgi].x, mk[cgi].y, mk[cgi].z, mk[cgi].w};
 #pragma unroll
-              for (int c = 0; c < 4; ++c) dst[c] = make_uint4(v1[4 * c], v1[4 * c + 1], v1[4 * c + 2], v1[4 * c + 3]);
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              dst[8 * (lane + 1) + c] = make_uint4(v2[4 * c], v2[4 * c + 1], v2[4 * c + 2], v2[4 * c + 3]);
-          }
-          // the four warps of this group
-          if (DBG && (a.dbg_flags & 64)) {}
-          else if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-          else if (grp == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
-          else if (grp == 2) asm volatile("bar.sync 3, 128;" ::: "memory");
-          else asm volatile("bar.sync 4, 128;" ::: "memory");
-          const long long e2 = DBG ? clock64() : 0;
-          // patch lanes 0 / 1 with the first two rows of the next quadrant, then rotate-shuffle
-          if (lane < 2 && has_nb) {
-            const uint4* nsrc = reinterpret_cast<const uint4*>(xp + 96 + 16 * half);
-            if (lane == 0) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint4 t4 = nsrc[c];
-                v1[4 * c] = t4.x; v1[4 * c + 1] = t4.y; v1[4 * c + 2] = t4.z; v1[4 * c + 3] = t4.w;
+              for (int jj = 0; jj < 8; ++jj) {
+                const uint32_t bits = (jj & 1) ? (mw[jj >> 1] >> 16) : (mw[jj >> 1] & 0xffffu);
+                const float mv = __uint_as_float(bits << 16);
+                f[jj] = (mv > 0.f) ? f[jj] : 0.f;
               }
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 t4 = nsrc[8 * (lane + 1) + c];
-              v2[4 * c] = t4.x; v2[4 * c + 1] = t4.y; v2[4 * c + 2] = t4.z; v2[4 * c + 3] = t4.w;
-            }
-          }
-          __syncwarp();
-          const float4* bias4 = reinterpret_cast<const float4*>(bias_s) + 4 * half;
-          float o[16];
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 fb = bias4[c4];
-            const float eb[4] = {fb.x, fb.y, fb.z, fb.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int c = 4 * c4 + j;
-              float s1, s2;
-              if (DBG && (a.dbg_flags & 32)) {
-                s1 = __uint_as_float(v1[c]); s2 = __uint_as_float(v2[c]);
-              } else {
-                s1 = __shfl_sync(0xffffffffu, __uint_as_float(v1[c]), src1);
-                s2 = __shfl_sync(0xffffffffu, __uint_as_float(v2[c]), src2);
-              }
-              float x = (__uint_as_float(v0[c]) + eb[j]) + (s1 + s2);
-              if (a.relu) x = fmaxf(x, 0.f);
-              o[c] = x;
-            }
-          }
-          if (valid && !(DBG && (a.dbg_flags & 2))) {
-#pragma unroll
-            for (int g2 = 0; g2 < 2; ++g2) {
-              const int cgi = 2 * half + g2;
-              if (cgi >= Cog) continue;
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = o[g2 * 8 + j];
-              if (a.mask) {
-                const uint32_t mw[4] = {mk[g2].x, mk[g2].y, mk[g2].z, mk[g2].w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
-                  const float mv = __uint_as_float(bits << 16);
-                  f[j] = (mv > 0.f) ? f[j] : 0.f;
-                }
-              }
-              const uint4 ov = make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]),
-                                          tc::pack_bf16(f[6], f[7]));
-              a.y[o_off + cgi * o_cg] = ov;
-              if (a.y2) a.y2[o2_off + cgi * o2_cg] = ov;
-            }
-          }
-          // mask of the second pass: in flight while this pass's stores drain
-          if (half == 0 && nhalf == 2 && a.mask && valid) {
-            mk[0] = __ldg(a.mask + m_off + 2 * m_cg);
-            mk[1] = __ldg(a.mask + m_off + 3 * m_cg);
-          }
-          if (DBG) {
-            const long long e3 = clock64();
-            dbg_ld += l1 - l0; dbg_bar += e2 - l1; dbg_rest += e3 - e2;
-            l0 = e3;
+            const uint4 ov = make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]),
+                                        tc::pack_bf16(f[6], f[7]));
+            a.y[o_off + cgi * o_cg] = ov;
+            if (a.y2) a.y2[o2_off + cgi * o2_cg] = ov;
           }
         }
+        if (DBG) { dbg_tfull += l0 - e0; dbg_ld += l1 - l0; dbg_rest += clock64() - l1; }
       }
       g += r.ntiles;
     }
     if (DBG && a.dbg && threadIdx.x == 64) {
       long long* d = a.dbg + blockIdx.x * 8;
-      d[5] = dbg_tfull; d[6] = dbg_bar; d[7] = dbg_ld; d[4] = -dbg_rest;
+      d[5] = dbg_tfull; d[6] = 0; d[7] = dbg_ld; d[4] = -dbg_rest;
     }
   }
   tc::tc_fence_before();
@@ -516,9 +456,9 @@ static int launch_igemm(const void* xb, const float* w, long long s_co, long lon
   a.out_pad = out_pad; a.relu = relu;
   a.zero_planes = zero_planes;
   a.QP2 = static_cast<int>(round_up(static_cast<long long>(a.Ho) * (a.Wo + 2), 128LL));
-  a.NP = round_up(kIgTileM + 2 * Wi, 8);
+  a.NP = round_up(kIgTileM + 2 * Wi + 2, 8);
   const int Qtot = (a.Ho - 1) * Wi + a.Wo;
-  a.tiles_q = ceil_div(Qtot, kIgTileOut);
+  a.tiles_q = ceil_div(Qtot, kIgTileM);
   const int sms = sm_count();
   PVB_REQUIRE(sms > 0, "conv3d_bf16: no CUDA device");
   a.tiles = static_cast<long long>(B) * a.tiles_q * a.To;
@@ -537,11 +477,11 @@ static int launch_igemm(const void* xb, const float* w, long long s_co, long lon
     PVB_LAUNCHED("igemm_weight_prep");
   }
   const size_t w_bytes = static_cast<size_t>(27) * a.Cg * a.CoP * 16;
-  const size_t fixed = 384 + 2 * 2 * 4 * 96 * 4 + round_up(w_bytes, static_cast<size_t>(128));
+  const size_t fixed = 640 + round_up(w_bytes, static_cast<size_t>(128));
   const size_t slot_bytes = static_cast<size_t>(a.Cg) * a.NP * 16;
   long long nslot = (227 * 1024 - static_cast<long long>(fixed)) / static_cast<long long>(slot_bytes);
   if (nslot > kIgMaxSlots) nslot = kIgMaxSlots;
-  PVB_REQUIRE(nslot >= 4, "conv3d_bf16: Cin=%d Cout=%d width=%d does not fit in shared memory", Ci, Co, Wi);
+  PVB_REQUIRE(nslot >= 2, "conv3d_bf16: Cin=%d Cout=%d width=%d does not fit in shared memory", Ci, Co, Wi);
   a.nslot = static_cast<int>(nslot);
   a.dbg = g_igemm_dbg;
   a.dbg_flags = g_igemm_dbg_flags;

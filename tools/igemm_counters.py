@@ -27,8 +27,8 @@ gzp = ops.to_blocked_bf16(gz, pad=2)
 run = (lambda: ops.conv3d_fwd_bf16(xb, w, b)) if which == "fwd" else (lambda: ops.conv3d_dgrad_bf16(gzp, w, xb))
 run()
 L.pvb200_debug_set_igemm_counters.argtypes = [ctypes.c_void_p]
-names = ["mma_total", "mma_wait_full", "mma_wait_tempty", "mma_issue", "epi_rest(neg)", "epi_wait_tfull", "epi_wait_bar", "epi_ld"]
-for flags in (0, 32, 64, 96, 98):
+names = ["mma_total", "mma_wait_full", "mma_wait_tempty", "mma_issue", "epi_rest(neg)", "epi_wait_tfull", "-", "epi_ld"]
+for flags in (0, 1, 2, 16):
     dbg = torch.zeros((148, 8), dtype=torch.int64, device=dev)
     L.pvb200_debug_set_igemm_counters(dbg.data_ptr())
     L.pvb200_debug_set_igemm_flags(flags)
@@ -39,3 +39,20 @@ for flags in (0, 32, 64, 96, 98):
     d = dbg.double().cpu()
     m = d.mean(0)
     print(which, "layer", layer, "flags", flags, {n: round(float(m[i])) for i, n in enumerate(names)}, "max total", int(d[:, 0].max()))
+
+
+def timed(n=20):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    run(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        run()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+print("production kernel: %.1f us/call (back to back, incl. weight prep)" % timed())
+dbg = torch.zeros((148, 8), dtype=torch.int64, device=dev)
+L.pvb200_debug_set_igemm_counters(dbg.data_ptr())
+print("profiling kernel:  %.1f us/call" % timed())
+L.pvb200_debug_set_igemm_counters(None)
