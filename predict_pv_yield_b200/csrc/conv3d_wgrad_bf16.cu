@@ -13,13 +13,16 @@
 //     rows are discarded (M = 96 is not a legal UMMA shape).  N = Cout.  The nine (kh,kw) taps are nine accumulators in TMEM
 //     (9 x 32 columns) that live for the whole kernel; each persistent CTA streams its share of (b,t,q-chunk) tiles
 //     and writes ONE partial at the end; a second kernel reduces the partials in fixed order (deterministic).
-// Warp roles: warp 0 = bulk-copy producer (3-stage ring), warp 1 = MMA issuer, warps 2-5 = final TMEM read-out.
+// Warp roles: warp 0 = bulk-copy producer (3-stage ring; lane i issues copy i of a tile -- a single thread issuing the
+// 16 copies was the bottleneck), warps 1-3 = MMA issuers for kh = 0,1,2 (one thread cannot issue more than one
+// tcgen05.mma per ~54 clk whatever its size; the three issuers own disjoint accumulators, so no ordering between
+// them is needed), warps 4-7 = final TMEM read-out.
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace pvb {
 
-constexpr int kWbThreads = 192;
+constexpr int kWbThreads = 256;
 constexpr int kWbQ = 128;  // positions (GEMM K) per tile
 constexpr int kWbMaxStages = 4;
 
@@ -62,8 +65,8 @@ __global__ void __launch_bounds__(kWbThreads, 1) conv3d_wgrad_bf16_kernel(const 
   }
   tc::fence_proxy_async();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kWbMaxStages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
-    tc::mbar_init(done, 1);
+    for (int i = 0; i < kWbMaxStages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 3); }
+    tc::mbar_init(done, 3);
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
@@ -78,35 +81,37 @@ __global__ void __launch_bounds__(kWbThreads, 1) conv3d_wgrad_bf16_kernel(const 
   const uint32_t nstage = static_cast<uint32_t>(a.nstage);
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t seq = 0;
-      for (long long g = g_begin; g < g_end; ++g, ++seq) {
-        const int ch = static_cast<int>(g % a.chunks);
-        const long long bt = g / a.chunks;
-        const int t = static_cast<int>(bt % a.To);
-        const int b = static_cast<int>(bt / a.To);
-        const int q0 = ch * kWbQ;
-        const uint32_t st = seq % nstage;
+    // bulk-copy producer: lane i issues copy i of a tile (3 time planes x Cgx channel groups of x, then Cgo of gz)
+    uint32_t seq = 0;
+    const int ncopy_x = 3 * a.Cgx;
+    for (long long g = g_begin; g < g_end; ++g, ++seq) {
+      const int ch = static_cast<int>(g % a.chunks);
+      const long long bt = g / a.chunks;
+      const int t = static_cast<int>(bt % a.To);
+      const int b = static_cast<int>(bt / a.To);
+      const int q0 = ch * kWbQ;
+      const uint32_t st = seq % nstage;
+      const long long avail = x_plane - q0;
+      const uint32_t npos = static_cast<uint32_t>(avail < a.NPOS ? (avail > 0 ? avail : 0) : a.NPOS);
+      if (lane == 0) {
         tc::mbar_wait(empty + st, ((seq / nstage) & 1u) ^ 1u);
-        const long long avail = x_plane - q0;
-        const uint32_t npos = static_cast<uint32_t>(avail < a.NPOS ? (avail > 0 ? avail : 0) : a.NPOS);
         tc::mbar_arrive_expect_tx(full + st, 3u * a.Cgx * npos * 16u + g_bytes);
-        uint8_t* dst = stage_s + st * stage_bytes;
-        // rows of the remaining (never loaded, zero-initialised) planes are computed and discarded
-        for (int p = 0; p < 3; ++p) {
-          const int tp = t + p;
-          for (int cg = 0; cg < a.Cgx; ++cg) {
-            const uint4* src = a.x + ((static_cast<long long>(b) * a.Cgx + cg) * a.Ti + tp) * x_plane + q0;
-            if (npos) tc::bulk_g2s(dst + static_cast<uint32_t>(p * a.Cgx + cg) * a.NPOS * 16u, src, npos * 16u, full + st);
-          }
-        }
-        for (int cg = 0; cg < a.Cgo; ++cg) {
-          const uint4* src = a.gzw + ((static_cast<long long>(b) * a.Cgo + cg) * a.To + t) * a.QP + q0;
-          tc::bulk_g2s(dst + x_bytes + static_cast<uint32_t>(cg) * kWbQ * 16u, src, kWbQ * 16u, full + st);
-        }
+      }
+      __syncwarp();
+      uint8_t* dst = stage_s + st * stage_bytes;
+      // rows of the remaining (never loaded, zero-initialised) planes are computed and discarded
+      if (lane < ncopy_x) {
+        const int p = lane / a.Cgx, cg = lane - p * a.Cgx;
+        const uint4* src = a.x + ((static_cast<long long>(b) * a.Cgx + cg) * a.Ti + (t + p)) * x_plane + q0;
+        if (npos) tc::bulk_g2s(dst + static_cast<uint32_t>(lane) * a.NPOS * 16u, src, npos * 16u, full + st);
+      } else if (lane < ncopy_x + a.Cgo) {
+        const int cg = lane - ncopy_x;
+        const uint4* src = a.gzw + ((static_cast<long long>(b) * a.Cgo + cg) * a.To + t) * a.QP + q0;
+        tc::bulk_g2s(dst + x_bytes + static_cast<uint32_t>(cg) * kWbQ * 16u, src, kWbQ * 16u, full + st);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= 3) {
+    const int kh = warp - 1;
     const bool leader = tc::elect_one();
     const uint32_t idesc = tc::umma_idesc(a.M, a.N, /*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
     // MN-major SWIZZLE_NONE: LBO = stride between 8-position K groups (128 B), SBO = stride between channel groups
@@ -123,18 +128,15 @@ __global__ void __launch_bounds__(kWbThreads, 1) conv3d_wgrad_bf16_kernel(const 
       const uint32_t xs16 = stage16 + st * (stage_bytes >> 4);
       const uint32_t gs16 = xs16 + (x_bytes >> 4);
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
+      for (int kw = 0; kw < 3; ++kw) {
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(kh * 3 + kw) * a.N;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(kh * 3 + kw) * a.N;
-#pragma unroll
-          for (int ks = 0; ks < kWbQ / 16; ++ks) {
-            const uint32_t a16 = xs16 + 16u * ks + kh * wi + kw;
-            const uint32_t b16 = gs16 + 16u * ks;
-            if (leader)
-              tc::umma_bf16_lohi(d_tmem, lo_lbo | (a16 & 0x3fffu), a_hi, lo_lbo | (b16 & 0x3fffu), b_hi, idesc,
-                           (seq | static_cast<uint32_t>(ks)) ? 1u : 0u);
-          }
+        for (int ks = 0; ks < kWbQ / 16; ++ks) {
+          const uint32_t a16 = xs16 + 16u * ks + kh * wi + kw;
+          const uint32_t b16 = gs16 + 16u * ks;
+          if (leader)
+            tc::umma_bf16_lohi(d_tmem, lo_lbo | (a16 & 0x3fffu), a_hi, lo_lbo | (b16 & 0x3fffu), b_hi, idesc,
+                         (seq | static_cast<uint32_t>(ks)) ? 1u : 0u);
         }
       }
       __syncwarp();
