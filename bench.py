@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
                     help="fp32 = BASELINE configs[1] (exact fp32 kernels); bf16 = tensor-core convolutions (configs[2] dtype)")
+    ap.add_argument("--no-shard", action="store_true",
+                    help="bf16, N > 1: replicate the fc1 optimiser instead of sharding it by output feature")
     return ap.parse_args()
 
 
@@ -65,7 +67,7 @@ def workload_config(args, world):
         "conv3d_layers": 4,
         "conv3d_channels": 32,
         "params": 141414732,
-        "parallelism": f"dp{world}",
+        "parallelism": f"dp{world}" + ("+fc1-optimizer-sharded" if (world > 1 and args.precision == "bf16" and not args.no_shard) else ""),
         "l2_policy": "working set per step (~0.9 GB activations + 0.57 GB fc1 weights + 4 rotating input "
                      "batches) is far larger than the 126 MB L2; no explicit flush",
     }
@@ -246,7 +248,7 @@ def run_ours(args):
     if world > 1:
         from predict_pv_yield_b200.dp import GradientExchange
 
-        exchange = GradientExchange(model)
+        exchange = GradientExchange(model, shard_large=(args.precision == "bf16" and not args.no_shard))
         exchange.attach_optimizer(opt)
 
     # synthetic inputs: 4 rotating batches, pinned host copies + device-resident copies

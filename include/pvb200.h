@@ -192,6 +192,16 @@ int pvb200_adam_fc1_shadow(float* w1, const float* grad, float* exp_avg, float* 
                            int F1, int Cg, int T, int H, int W,
                            float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                            pvb200_stream_t stream);
+/* Data-parallel variant with the optimiser sharded by output feature (rank r owns rows [row_lo, row_lo + nrows) of
+ * fc1.weight; the gradient rows come from a reduce-scatter): updates ONLY those rows of w1 / exp_avg / exp_avg_sq and
+ * writes their bf16 copy as a contiguous shard [Cg*T*H*W][nrows][8].  After an all-gather of the shards,
+ * pvb200_fc1_shadow_from_shards interleaves them into the shadow [Cg*T*H*W][128][8]. */
+int pvb200_adam_fc1_shadow_rows(float* w1, const float* grad, float* exp_avg, float* exp_avg_sq, uint16_t* shard,
+                                int F1, int Cg, int T, int H, int W, int row_lo, int nrows,
+                                float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                                pvb200_stream_t stream);
+int pvb200_fc1_shadow_from_shards(const uint16_t* gathered, uint16_t* shadow, int nshards, int nrows, int Cg, int T,
+                                  int H, int W, pvb200_stream_t stream);
 int pvb200_fc1_fwd_bf16_splits(void);
 int pvb200_fc1_fwd_bf16(const uint16_t* xb, const uint16_t* shadow, float* partial, int B, int F1, int Cg, int T, int H,
                         int W, pvb200_stream_t stream);

@@ -71,12 +71,16 @@ struct AdamFc1Scalars {
 // All 32 x 4 loads of a thread are issued before the arithmetic so that enough bytes are in flight per SM.
 constexpr int kAdamShPos = 64;
 constexpr int kAdamShLd = 66;
+// Row-sharded use (data parallel, optimiser state sharded by output feature): only the features [j_lo, j_hi) are
+// updated and their bf16 copy goes to a contiguous shard [kg][j_hi - j_lo][8] (out_ld = j_hi - j_lo, out_j0 = j_lo)
+// instead of the full shadow (out_ld = 128, out_j0 = 0).
 __global__ void __launch_bounds__(256)
 adam_fc1_shadow_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                       uint4* __restrict__ ws, int F1, long long THW, int Cg, const AdamFc1Scalars s) {
+                       uint4* __restrict__ ws, int j_lo, int F1, int out_ld, int out_j0, long long THW, int Cg,
+                       const AdamFc1Scalars s) {
   __shared__ __align__(16) uint16_t tile16[8 * 32 * kAdamShLd];  // [8 c8][32 j][66]
   const long long pos0 = static_cast<long long>(blockIdx.x) * kAdamShPos;
-  const int j0 = blockIdx.y * 32;
+  const int j0 = j_lo + blockIdx.y * 32;
   const int cg = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long K1 = static_cast<long long>(Cg) * 8 * THW;
@@ -139,7 +143,21 @@ adam_fc1_shadow_kernel(float* __restrict__ p, const float* __restrict__ g, float
     o.y = src[2 * 32 * kAdamShLd] | (static_cast<uint32_t>(src[3 * 32 * kAdamShLd]) << 16);
     o.z = src[4 * 32 * kAdamShLd] | (static_cast<uint32_t>(src[5 * 32 * kAdamShLd]) << 16);
     o.w = src[6 * 32 * kAdamShLd] | (static_cast<uint32_t>(src[7 * 32 * kAdamShLd]) << 16);
-    ws[(cg * THW + q) * kF1J + j0 + tx] = o;
+    if (j0 + tx < F1 || out_ld == kF1J) ws[(cg * THW + q) * out_ld + (j0 + tx - out_j0)] = o;
+  }
+}
+
+// bf16 shards [nshards][KG][nrows][8] (all-gathered, one per rank) -> shadow [KG][128][8]; rows >= nshards*nrows untouched
+__global__ void __launch_bounds__(256)
+fc1_shadow_from_shards_kernel(const uint4* __restrict__ gathered, uint4* __restrict__ ws, int nshards, int nrows, long long KG) {
+  const long long total = KG * nshards * nrows;
+  const int F = nshards * nrows;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long kg = idx / F;
+    const int j = static_cast<int>(idx - kg * F);
+    const int r = j / nrows, jj = j - r * nrows;
+    ws[kg * kF1J + j] = __ldcs(gathered + (static_cast<long long>(r) * KG + kg) * nrows + jj);
   }
 }
 
@@ -516,8 +534,46 @@ int pvb200_adam_fc1_shadow(float* w1, const float* grad, float* exp_avg, float* 
   const long long THW = static_cast<long long>(T) * H * W;
   dim3 grid(static_cast<unsigned>(ceil_div(THW, static_cast<long long>(kAdamShPos))), kF1J / 32, Cg);
   adam_fc1_shadow_kernel<<<grid, 256, 0, as_stream(stream)>>>(w1, grad, exp_avg, exp_avg_sq, reinterpret_cast<uint4*>(shadow),
-                                                                 F1, THW, Cg, s);
+                                                                 0, F1, kF1J, 0, THW, Cg, s);
   PVB_LAUNCHED("adam_fc1_shadow");
+  return PVB200_OK;
+}
+
+int pvb200_adam_fc1_shadow_rows(float* w1, const float* grad, float* exp_avg, float* exp_avg_sq, uint16_t* shard, int F1, int Cg,
+                                int T, int H, int W, int row_lo, int nrows, float lr, float beta1, float beta2, float eps,
+                                int step, float grad_scale, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(w1 && grad && exp_avg && exp_avg_sq && shard, "adam_fc1_shadow_rows: null pointer");
+  PVB_REQUIRE(F1 > 0 && F1 <= kF1J && Cg > 0 && T > 0 && H > 0 && W > 0 && step >= 1, "adam_fc1_shadow_rows: bad argument");
+  PVB_REQUIRE(row_lo >= 0 && nrows > 0 && nrows < kF1J && row_lo + nrows <= F1, "adam_fc1_shadow_rows: rows [%d, %d) outside [0, %d)",
+              row_lo, row_lo + nrows, F1);
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  AdamFc1Scalars s;
+  s.beta1 = beta1; s.beta2 = beta2;
+  s.one_minus_beta1 = static_cast<float>(1.0 - static_cast<double>(beta1));
+  s.one_minus_beta2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+  s.eps = eps;
+  s.neg_step_size = static_cast<float>(-(static_cast<double>(lr) / bc1));
+  s.bc2_sqrt = static_cast<float>(sqrt(bc2));
+  s.grad_scale = grad_scale;
+  const long long THW = static_cast<long long>(T) * H * W;
+  dim3 grid(static_cast<unsigned>(ceil_div(THW, static_cast<long long>(kAdamShPos))), ceil_div(nrows, 32), Cg);
+  adam_fc1_shadow_kernel<<<grid, 256, 0, as_stream(stream)>>>(w1, grad, exp_avg, exp_avg_sq, reinterpret_cast<uint4*>(shard),
+                                                                 row_lo, row_lo + nrows, nrows, row_lo, THW, Cg, s);
+  PVB_LAUNCHED("adam_fc1_shadow_rows");
+  return PVB200_OK;
+}
+
+int pvb200_fc1_shadow_from_shards(const uint16_t* gathered, uint16_t* shadow, int nshards, int nrows, int Cg, int T, int H, int W,
+                                  pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(gathered && shadow && nshards > 0 && nrows > 0 && nshards * nrows <= kF1J && Cg > 0 && T > 0 && H > 0 && W > 0,
+              "fc1_shadow_from_shards: bad argument");
+  const long long KG = static_cast<long long>(Cg) * T * H * W;
+  fc1_shadow_from_shards_kernel<<<148 * 8, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(gathered),
+                                                                          reinterpret_cast<uint4*>(shadow), nshards, nrows, KG);
+  PVB_LAUNCHED("fc1_shadow_from_shards");
   return PVB200_OK;
 }
 

@@ -13,6 +13,13 @@ pass produces, so:
   ``finish()``;
 * averaging (1 / world_size) is folded into the Adam kernel (``FusedAdam.grad_scale``), so no extra pass.
 
+* ``shard_large=True`` (bf16 mode, where ``fc1.weight`` has a tensor-core shadow): the optimiser of the large
+  parameter is sharded by output feature.  Its gradient is REDUCE-SCATTERED (half the NVLink bytes of an
+  all-reduce): rank r receives the summed rows [r*F/N, (r+1)*F/N), runs Adam on those rows only (1/N of the 4 GB
+  optimiser pass) and the bf16 copies of the updated rows are all-gathered on the communication stream into every
+  rank's shadow, under the next step's convolution forward (fc1 is the last consumer).  The fp32 master rows owned by
+  other ranks go stale until ``gather_master_weights()`` (wired as the module's state_dict pre-hook).
+
 ``finish()`` must run before the optimizer step (``attach_optimizer`` wires it as the pre-step hook).
 Works on CPU tensors with the ``gloo`` backend too (no streams), which is how the host logic is tested.
 """
@@ -24,8 +31,25 @@ import torch
 import torch.distributed as dist
 
 
+class ShardSpec:
+    """Attached to a parameter as ``_pvb_shard``: this rank owns rows [rank*F/world, (rank+1)*F/world)."""
+
+    def __init__(self, exchange: "GradientExchange"):
+        self.rank = dist.get_rank(exchange.group)
+        self.world = exchange.world_size
+        self.group = exchange.group
+        self._exchange = exchange
+
+    def comm_stream(self, device: torch.device):
+        return self._exchange._comm(device)
+
+    def rows(self, nrows_total: int):
+        n = nrows_total // self.world
+        return self.rank * n, (self.rank + 1) * n
+
+
 class GradientExchange:
-    def __init__(self, module: torch.nn.Module, process_group=None, large_numel: int = 1 << 22):
+    def __init__(self, module: torch.nn.Module, process_group=None, large_numel: int = 1 << 22, shard_large: bool = False):
         if not dist.is_available() or not dist.is_initialized():
             raise RuntimeError("GradientExchange needs an initialised torch.distributed process group")
         self.group = process_group
@@ -38,6 +62,11 @@ class GradientExchange:
         self._comm_stream: Optional[torch.cuda.Stream] = None
         self.bytes_reduced_last_step = 0
         self._bytes = 0
+        self.shard_large = shard_large
+        self._sharded: List[torch.nn.Parameter] = []
+        self._reduce_scatter_ok = dist.get_backend(process_group) == "nccl"  # gloo has no reduce-scatter
+        if shard_large:
+            self._sd_hook = module.register_state_dict_pre_hook(lambda *a, **k: self.gather_master_weights())
 
     # -- hook ---------------------------------------------------------------------------------------
     def _comm(self, device: torch.device) -> torch.cuda.Stream:
@@ -62,13 +91,64 @@ class GradientExchange:
             work = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._pending.append((work, None))
 
+    def _can_shard(self, p: torch.nn.Parameter) -> bool:
+        shadow = getattr(p, "_pvb_shadow", None)
+        return (self.shard_large and shadow is not None and getattr(shadow, "geom", None) is not None and p.dim() == 2
+                and p.shape[0] % self.world_size == 0 and p.grad.is_contiguous())
+
+    def _reduce_scatter_async(self, p: torch.nn.Parameter) -> None:
+        """Sum of the gradient rows this rank owns, in place in ``p.grad`` (the other rows keep the local values)."""
+        if getattr(p, "_pvb_shard", None) is None:
+            p._pvb_shard = ShardSpec(self)
+            self._sharded.append(p)
+        g = p.grad
+        lo, hi = p._pvb_shard.rows(g.shape[0])
+        flat = g.view(-1)
+        n = g.shape[1]
+        mine = flat[lo * n: hi * n]
+        self._bytes += mine.numel() * g.element_size()
+        if g.is_cuda and self._reduce_scatter_ok:
+            comm = self._comm(g.device)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(g.device))
+            comm.wait_event(ready)
+            with torch.cuda.stream(comm):
+                dist.reduce_scatter_tensor(mine, flat, op=dist.ReduceOp.SUM, group=self.group)  # in place (NCCL)
+                done = torch.cuda.Event()
+                done.record(comm)
+            g.record_stream(comm)
+            self._pending.append((None, done))
+        else:  # backends without reduce-scatter (gloo, CPU tests): all-reduce, the owned rows are what is used
+            self._bytes -= mine.numel() * g.element_size()
+            self._all_reduce_async(g)
+
     def _on_grad(self, p: torch.nn.Parameter) -> None:
         if self.world_size == 1 or p.grad is None:
             return
         if p.grad.numel() >= self.large_numel:
-            self._all_reduce_async(p.grad)
+            if self._can_shard(p):
+                self._reduce_scatter_async(p)
+            else:
+                if getattr(p, "_pvb_shard", None) is not None:
+                    raise RuntimeError("GradientExchange: a sharded parameter can no longer be sharded")
+                self._all_reduce_async(p.grad)
         else:
             self._small.append(p)
+
+    @torch.no_grad()
+    def gather_master_weights(self) -> None:
+        """All-gather the fp32 master rows of the sharded parameters (each rank only keeps its own rows current).
+        Called before ``state_dict()``; a collective: every rank must call it."""
+        for p in self._sharded:
+            lo, hi = p._pvb_shard.rows(p.shape[0])
+            flat = p.data.view(-1)
+            n = p.shape[1]
+            if self._reduce_scatter_ok:
+                dist.all_gather_into_tensor(flat, flat[lo * n: hi * n].clone(), group=self.group)
+            else:
+                parts = [torch.empty_like(flat[lo * n: hi * n]) for _ in range(self.world_size)]
+                dist.all_gather(parts, flat[lo * n: hi * n].clone(), group=self.group)
+                flat.copy_(torch.cat(parts))
 
     # -- end of backward ------------------------------------------------------------------------------
     def finish(self) -> None:

@@ -80,6 +80,9 @@ SIGNATURES = {
     "pvb200_fc1_make_shadow_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_adam_fc1_shadow": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
+    "pvb200_adam_fc1_shadow_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                            c_int, c_int, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
+    "pvb200_fc1_shadow_from_shards": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_fc1_fwd_bf16_splits": (c_int, []),
     "pvb200_fc1_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_fc1_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

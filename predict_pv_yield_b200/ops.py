@@ -570,6 +570,9 @@ class Fc1Shadow:
         self.buf: Optional[torch.Tensor] = None
         self.geom: Optional[Tuple[int, int, int, int]] = None
         self.key = None
+        self.ready: Optional[torch.cuda.Event] = None  # set while a sharded refresh is in flight on the comm stream
+        self._send: Optional[torch.Tensor] = None
+        self._gathered: Optional[torch.Tensor] = None
 
     @staticmethod
     def _key(w1: torch.Tensor):
@@ -581,6 +584,9 @@ class Fc1Shadow:
         if self.buf is None or self.geom != geom or self.buf.device != w1.device:
             self.buf = torch.empty(L.pvb200_fc1_bf16_shadow_bytes(Cg, T, H, W), dtype=torch.uint8, device=w1.device)
             self.geom, self.key = geom, None
+        if self.ready is not None:  # refreshed by the sharded optimiser step on the communication stream
+            torch.cuda.current_stream(w1.device).wait_event(self.ready)
+            self.ready = None
         if self.key != self._key(w1):
             with _timed("fc1_make_shadow_bf16", 0.0, 6.0 * w1.numel()):
                 rc = L.pvb200_fc1_make_shadow_bf16(_p(w1), _p(self.buf), F1, Cg, T, H, W, _stream())
@@ -603,6 +609,50 @@ class Fc1Shadow:
             rc = L.pvb200_adam_fc1_shadow(_p(w1), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(self.buf), w1.shape[0], Cg, T, H, W,
                                           lr, beta1, beta2, eps, step, grad_scale, _stream())
         _lib.check(rc, "adam_fc1_shadow")
+        w1._pvb_gen = getattr(w1, "_pvb_gen", 0) + 1
+        self.key = self._key(w1)
+        return True
+
+
+    def adam_step_sharded(self, w1: "torch.nn.Parameter", grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                          lr: float, beta1: float, beta2: float, eps: float, step: int, grad_scale: float, rank: int, world: int,
+                          group, comm_stream: "torch.cuda.Stream") -> bool:
+        """Data-parallel step with the optimiser sharded by output feature: this rank updates rows
+        [rank*F1/world, (rank+1)*F1/world) of ``w1`` (their gradient rows must already hold the reduce-scattered sum),
+        the bf16 copies of all ranks' rows are all-gathered on ``comm_stream`` and interleaved into the shadow there, so
+        only the 1/world Adam pass sits on the compute stream; the next forward waits on ``self.ready``.
+        The fp32 master rows owned by OTHER ranks go stale (``GradientExchange.gather_master_weights`` refreshes them)."""
+        import torch.distributed as dist
+
+        if self.buf is None or self.geom is None or self.buf.device != w1.device:
+            return False
+        L = _lib.load()
+        Cg, T, H, W = self.geom
+        F1 = w1.shape[0]
+        if w1.shape[1] != Cg * 8 * T * H * W or F1 > 128 or F1 % world != 0:
+            return False
+        nrows = F1 // world
+        KG = Cg * T * H * W
+        dev = w1.device
+        if self._send is None or self._send.numel() != KG * nrows * 8 or self._send.device != dev:
+            self._send = torch.empty(KG * nrows * 8, dtype=torch.bfloat16, device=dev)
+            self._gathered = torch.empty(world * KG * nrows * 8, dtype=torch.bfloat16, device=dev)
+        for t, nm in ((w1.data, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+            _need_cuda(t, nm, torch.float32)
+        with _timed("adam_fc1_shadow_rows", 0.0, 30.0 * w1.numel() / world):
+            rc = L.pvb200_adam_fc1_shadow_rows(_p(w1), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(self._send), F1, Cg, T, H, W,
+                                               rank * nrows, nrows, lr, beta1, beta2, eps, step, grad_scale, _stream())
+        _lib.check(rc, "adam_fc1_shadow_rows")
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(dev))
+        comm_stream.wait_event(done)
+        with torch.cuda.stream(comm_stream):
+            dist.all_gather_into_tensor(self._gathered, self._send, group=group)
+            rc = L.pvb200_fc1_shadow_from_shards(_p(self._gathered), _p(self.buf), world, nrows, Cg, T, H, W,
+                                                 comm_stream.cuda_stream)
+            _lib.check(rc, "fc1_shadow_from_shards")
+            self.ready = torch.cuda.Event()
+            self.ready.record(comm_stream)
         w1._pvb_gen = getattr(w1, "_pvb_gen", 0) + 1
         self.key = self._key(w1)
         return True

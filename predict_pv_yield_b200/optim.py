@@ -51,6 +51,16 @@ class FusedAdam(torch.optim.Optimizer):
                 if shadow is not None:
                     # fc1.weight in bf16 mode: Adam + refresh of the tensor-core shadow in one pass over the weight
                     b1, b2 = group["betas"]
+                    shard = getattr(p, "_pvb_shard", None)
+                    if shard is not None:
+                        # data parallel, optimiser sharded by output feature (dp.GradientExchange reduce-scattered the
+                        # gradient rows): update 1/world of the rows, exchange the bf16 copies on the comm stream
+                        if shadow.adam_step_sharded(p, grad, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
+                                                    st["step"], self.grad_scale, shard.rank, shard.world, shard.group,
+                                                    shard.comm_stream(p.device)):
+                            continue
+                        raise RuntimeError("FusedAdam: the gradient of a sharded parameter was reduce-scattered but its "
+                                           "shadow cannot take a sharded step (geometry unknown)")
                     if shadow.adam_step(p, grad, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
                                         st["step"], self.grad_scale):
                         continue
