@@ -47,6 +47,7 @@ struct ConvArgs {
   int co_tiles;
   int CoPad;
   int relu;
+  int pairs;  // Wi even (and the tensor 8-byte aligned): stage two positions per copy (a pair never straddles a row)
 };
 
 // dw layout transform: wt[ci_role][tap][co_role] = w[co_role*s_co + ci_role*s_ci + (flip ? 26-tap : tap)]
@@ -121,6 +122,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
         for (int i = lane; i < a.NP; i += 32) {
           const int o = off_s[i];
           dst[i] = (plane_ok && o >= 0) ? sat_norm(__ldg(src + o), m, s) : 0.f;
+        }
+      } else if (a.pairs) {
+        // positions 2i, 2i+1 of the staged run are neighbours in the same input row (Wps, q0, P and Wi are even):
+        // one 8-byte copy, both valid or both padding
+        const float* src = static_cast<const float*>(a.x) + base;
+        const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+        for (int i = 2 * lane; i < a.NP; i += 64) {
+          const int o = off_s[i];
+          const bool ok = plane_ok && (o >= 0);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? o : 0)),
+                       "r"(ok ? 8 : 0)
+                       : "memory");
         }
       } else {
         const float* src = static_cast<const float*>(a.x) + base;
@@ -256,6 +269,7 @@ static int launch_conv(const void* x, bool i16, const float* mean, const float* 
   a.co_tiles = ceil_div(Co, kCoT);
   a.CoPad = a.co_tiles * kCoT;
   a.relu = relu;
+  a.pairs = (!i16 && (Wi % 2 == 0) && (P % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0)) ? 1 : 0;
   const size_t need = conv_ws_bytes(Ci, Co);
   if (ws == nullptr || ws_bytes < need) {
     set_error("conv3d: workspace too small (%zu < %zu bytes)", ws_bytes, need);

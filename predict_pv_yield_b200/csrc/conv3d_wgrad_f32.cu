@@ -29,6 +29,7 @@ struct WgradArgs {
   long long total_steps;  // B * tiles_per_plane * To
   int ncog;           // ceil(Co / 4)
   int items;          // ncog * Ci * KTS
+  int pairs;          // Wi even and 8-byte aligned tensors: stage two positions per copy (never straddles a row)
 };
 
 // Work is ordered (b, tile, to) with `to` fastest: a CTA walks DOWN the time axis of one (sample, position tile)
@@ -79,6 +80,15 @@ __global__ void __launch_bounds__(KTS == 1 ? 256 : 384, 1) conv3d_wgrad_f32_kern
           const int o = off_s[i];
           dst[i] = (o >= 0) ? sat_norm(__ldg(src + o), m, s) : 0.f;
         }
+      } else if (a.pairs) {
+        const float* src = static_cast<const float*>(a.x) + base;
+        const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+        for (int i = 2 * lane; i < a.NP; i += 64) {
+          const int o = off_s[i];
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 4u * i), "l"(src + (o >= 0 ? o : 0)),
+                       "r"(o >= 0 ? 8 : 0)
+                       : "memory");
+        }
       } else {
         const float* src = static_cast<const float*>(a.x) + base;
         const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
@@ -98,12 +108,21 @@ __global__ void __launch_bounds__(KTS == 1 ? 256 : 384, 1) conv3d_wgrad_f32_kern
       const bool ok_p = p < a.Co;
       const float* src = a.gz + ((static_cast<long long>(b) * a.Co + (ok_p ? p : 0)) * a.To + to) * gplane;
       const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
-      for (int i = lane; i < kWgQC; i += 32) {
+      if (a.pairs) {
+        const int i = 2 * lane;  // kWgQC == 64
         const int o = goff_s[i];
         const bool ok = ok_p && (o >= 0);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? o : 0)),
-                     "r"(ok ? 4 : 0)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? o : 0)),
+                     "r"(ok ? 8 : 0)
                      : "memory");
+      } else {
+        for (int i = lane; i < kWgQC; i += 32) {
+          const int o = goff_s[i];
+          const bool ok = ok_p && (o >= 0);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? o : 0)),
+                       "r"(ok ? 4 : 0)
+                       : "memory");
+        }
       }
     }
   };
@@ -265,6 +284,7 @@ int pvb200_conv3d_wgrad_f32(const void* x, int x_is_i16, const float* mean, cons
   // narrow layers (conv0: Cin = 12) split the 27 taps over 3 threads to keep the CTA full
   const int kts = (a.ncog * Cin <= 128) ? 3 : 1;
   a.items = a.ncog * Cin * kts;
+  a.pairs = (!x_is_i16 && Wi % 2 == 0 && reinterpret_cast<uintptr_t>(x) % 8 == 0 && reinterpret_cast<uintptr_t>(gz) % 8 == 0) ? 1 : 0;
   const int cap = (kts == 1) ? 256 : 384;
   const int grid_y = ceil_div(a.items, cap);
   const int threads = round_up(ceil_div(a.items, grid_y), 32);
