@@ -179,18 +179,25 @@ struct Fc1Bf16Args {
   long long tiles_per_split;
 };
 
-// transposing load of the X tile: smem [kgl][b][8] <- xb[b][kg0 + kgl]   (16 x BP chunks of 16 B), executed by one warp
-__device__ __forceinline__ void fc1_load_x_tile(uint4* dst, const Fc1Bf16Args& a, long long kg0, int lane) {
+// transposing load of the X tile: smem [kgl][b][8] <- xb[b][kg0 + kgl]   (16 x BP chunks of 16 B).  Asynchronous
+// (cp.async / LDGSTS, zero fill outside the tensor): the producer warp only issues the copies and lets each lane's
+// completion arrive on the stage's `full` barrier, so it runs ahead by the depth of the ring instead of paying one
+// memory latency per tile.
+__device__ __forceinline__ void fc1_load_x_tile_async(uint4* dst, const Fc1Bf16Args& a, long long kg0, int lane, uint64_t* bar) {
+  const uint32_t d0 = tc::smem_u32(dst);
   for (int b = lane; b < a.BP; b += 32) {
     const bool okb = b < a.B;
-#pragma unroll 4
+#pragma unroll
     for (int kgl = 0; kgl < kF1KG; ++kgl) {
       const long long kg = kg0 + kgl;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (okb && kg < a.KG) v = __ldg(a.xb + static_cast<long long>(b) * a.KG + kg);
-      dst[kgl * a.BP + b] = v;
+      const bool ok = okb && kg < a.KG;
+      const uint4* src = a.xb + (ok ? static_cast<long long>(b) * a.KG + kg : 0);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + static_cast<uint32_t>(kgl * a.BP + b) * 16u), "l"(src),
+                   "r"(ok ? 16 : 0)
+                   : "memory");
     }
   }
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
 // MODE 0: forward, 1: data gradient, 2: weight gradient
@@ -219,7 +226,8 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
   const uint32_t tmem_cols = (2u * ncol <= 32u) ? 32u : (2u * ncol <= 64u) ? 64u : (2u * ncol <= 128u) ? 128u : (2u * ncol <= 256u) ? 256u : 512u;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NST; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+    // full: lane 0's arrive (+ the W1s tile's bytes) and, where an X tile is staged, one cp.async arrival per producer lane
+    for (int i = 0; i < NST; ++i) { tc::mbar_init(full + i, MODE == 1 ? 1 : 33); tc::mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
     tc::fence_barrier_init();
   }
@@ -260,14 +268,11 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
     uint32_t seq = 0;
     for (long long t = t_begin; t < t_end; ++t, ++seq) {
       const uint32_t st = seq % NST;
-      tc::mbar_wait(empty + st, ((seq / NST) & 1u) ^ 1u);
       uint8_t* dst = stage_s + st * stage_bytes;
       const long long kg0 = t * kF1KG;
-      if (MODE != 1) {
-        fc1_load_x_tile(reinterpret_cast<uint4*>(dst + w_bytes), a, kg0, lane);
-        tc::fence_proxy_async();
-      }
+      if (lane == 0) tc::mbar_wait(empty + st, ((seq / NST) & 1u) ^ 1u);
       __syncwarp();
+      if (MODE != 1) fc1_load_x_tile_async(reinterpret_cast<uint4*>(dst + w_bytes), a, kg0, lane, full + st);
       if (lane == 0) {
         if (MODE != 2) {
           const long long left = a.KG - kg0;
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
       for (long long t = t_begin; t < t_end; ++t, ++seq) {
         const uint32_t st = seq % NST;
         tc::mbar_wait(full + st, (seq / NST) & 1u);
+        tc::fence_proxy_async();  // the X tile was written by cp.async (generic proxy), the MMA reads through the async proxy
         tc::tc_fence_after();
         const uint32_t w16 = stage16 + st * (stage_bytes >> 4);
         const uint32_t x16 = w16 + (w_bytes >> 4);
@@ -318,6 +324,7 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
         const uint32_t st = seq % NST;
         const uint32_t acc = seq & 1u;
         tc::mbar_wait(full + st, (seq / NST) & 1u);
+        tc::fence_proxy_async();
         tc::mbar_wait(tempty + acc, ((seq >> 1) & 1u) ^ 1u);
         tc::tc_fence_after();
         const uint32_t s16 = stage16 + st * (stage_bytes >> 4);
@@ -369,10 +376,23 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
       const long long plane_pad = static_cast<long long>(a.H + 4) * (a.W + 4);
       for (long long t = t_begin; t < t_end; ++t, ++seq) {
         const uint32_t acc = seq & 1u;
+        const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
+        // data gradient: this thread stores k-group (kg0 + et % 16) of the samples et / 16 + 8 i; the ReLU-mask
+        // source (the activation itself) is fetched BEFORE waiting for the accumulator
+        const long long dkg = t * kF1KG + (et & 15);
+        const bool dkg_ok = dkg < a.KG;
+        uint4 dmask[8];
+        if (MODE == 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int b = (et >> 4) + 8 * i;
+            dmask[i] = make_uint4(0, 0, 0, 0);
+            if (b < a.B && dkg_ok && i * 8 < a.B) dmask[i] = __ldg(a.xb + static_cast<long long>(b) * a.KG + dkg);
+          }
+        }
         tc::mbar_wait(tfull + acc, (seq >> 1) & 1u);
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * ncol;
-        const int et = threadIdx.x - 64;  // 0..127 within the epilogue warps
         if (MODE == 1) {
           // accumulator row = k' within the tile (k-group kg0 + row/8, channel row%8); columns = batch.
           // stage as bf16 [b][row] so that a (b, k-group) pair becomes one 16-byte vector
@@ -389,28 +409,37 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(tempty + acc);
           asm volatile("bar.sync 2, 128;" ::: "memory");
-          const long long kg0 = t * kF1KG;
-          for (int item = et; item < a.B * kF1KG; item += 128) {
-            const int b = item >> 4, kgl = item & 15;
-            const long long kg = kg0 + kgl;
-            if (kg >= a.KG) continue;
-            const int cg = static_cast<int>(kg / a.THW);
-            const int pos = static_cast<int>(kg - cg * a.THW);
+          if (dkg_ok) {
+            const int kgl = et & 15;
+            const int cg = static_cast<int>(dkg / a.THW);
+            const int pos = static_cast<int>(dkg - cg * a.THW);
             const int tt = pos / (a.H * a.W);
             const int hw = pos - tt * a.H * a.W;
             const int hh = hw / a.W, ww = hw - hh * a.W;
-            const uint4 g = *reinterpret_cast<const uint4*>(es + b * 128 + kgl * 8);
-            const uint4 m = __ldg(a.xb + static_cast<long long>(b) * a.KG + kg);
+            // offsets of sample 0; a sample is Cg planes further
+            const long long o_pad = (static_cast<long long>(cg) * (a.T + 4) + (tt + 2)) * plane_pad +
+                                    static_cast<long long>(hh + 2) * (a.W + 4) + (ww + 2);
+            const long long o_gzw = (static_cast<long long>(cg) * a.T + tt) * a.QP + static_cast<long long>(hh) * (a.W + 2) + ww;
+            const long long s_pad = static_cast<long long>(a.Cg) * (a.T + 4) * plane_pad, s_gzw = static_cast<long long>(a.Cg) * a.T * a.QP;
             // keep a gradient lane where the activation (bf16, post-ReLU, finite) is > 0: sign clear and non-zero
             auto sel = [](uint32_t gv, uint32_t mv) {
               const uint32_t lo = ((mv & 0x8000u) == 0 && (mv & 0x7fffu) != 0) ? (gv & 0xffffu) : 0u;
               const uint32_t hi = ((mv & 0x80000000u) == 0 && (mv & 0x7fff0000u) != 0) ? (gv & 0xffff0000u) : 0u;
               return lo | hi;
             };
-            const uint4 o = make_uint4(sel(g.x, m.x), sel(g.y, m.y), sel(g.z, m.z), sel(g.w, m.w));
-            a.gz_pad[((static_cast<long long>(b) * a.Cg + cg) * (a.T + 4) + (tt + 2)) * plane_pad +
-                     static_cast<long long>(hh + 2) * (a.W + 4) + (ww + 2)] = o;
-            a.gzw[((static_cast<long long>(b) * a.Cg + cg) * a.T + tt) * a.QP + static_cast<long long>(hh) * (a.W + 2) + ww] = o;
+            for (int i0 = 0; i0 * 8 < a.B; i0 += 8) {
+#pragma unroll
+              for (int ii = 0; ii < 8; ++ii) {
+                const int i = i0 + ii;
+                const int b = (et >> 4) + 8 * i;
+                if (b >= a.B) break;
+                const uint4 g = *reinterpret_cast<const uint4*>(es + b * 128 + kgl * 8);
+                const uint4 m = (i0 == 0) ? dmask[ii] : __ldg(a.xb + static_cast<long long>(b) * a.KG + dkg);
+                const uint4 o = make_uint4(sel(g.x, m.x), sel(g.y, m.y), sel(g.z, m.z), sel(g.w, m.w));
+                a.gz_pad[o_pad + b * s_pad] = o;
+                a.gzw[o_gzw + b * s_gzw] = o;
+              }
+            }
           }
           asm volatile("bar.sync 2, 128;" ::: "memory");  // staging buffer free for the next tile
         } else {
