@@ -26,6 +26,7 @@ namespace pvb {
 constexpr int kF1J = 128;       // fc1 output features (padded)
 constexpr int kF1KG = 16;       // k-groups per tile  (128 feature columns)
 constexpr int kF1Threads = 192; // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr int kF1ThreadsWgrad = 448;  // + warps 6-13: the weight gradient's global-store warps
 
 __device__ __forceinline__ uint32_t f2bf(float v) { return static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(v))); }
 
@@ -86,7 +87,9 @@ adam_fc1_shadow_kernel(float* __restrict__ p, const float* __restrict__ g, float
   const long long K1 = static_cast<long long>(Cg) * 8 * THW;
   const long long pos = pos0 + 2 * tx;
   const bool vec = (THW % 2 == 0) && (pos + 1 < THW);
-#pragma unroll
+  // not unrolled: the fully unrolled kernel was 120 KB of code and spent a third of its stall samples on
+  // instruction fetch (ncu: no_instructions 31 %)
+#pragma unroll 1
   for (int r = 0; r < 4; ++r) {
     const int jj = ty + 8 * r;
     const int j = j0 + jj;
@@ -202,7 +205,8 @@ __device__ __forceinline__ void fc1_load_x_tile_async(uint4* dst, const Fc1Bf16A
 
 // MODE 0: forward, 1: data gradient, 2: weight gradient
 template <int MODE>
-__global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Args a) {
+__global__ void __launch_bounds__(MODE == 2 ? kF1ThreadsWgrad : kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Args a) {
+  constexpr int kThr = MODE == 2 ? kF1ThreadsWgrad : kF1Threads;
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NST = 4;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [4]
@@ -233,12 +237,12 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, tmem_cols);
   // stages start zeroed: a partial last tile leaves rows untouched, and stale bits must be finite (0 * NaN = NaN)
-  for (uint32_t i = threadIdx.x; i < (NST * stage_bytes) / 16u; i += kF1Threads) reinterpret_cast<uint4*>(stage_s)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = threadIdx.x; i < (NST * stage_bytes) / 16u; i += kThr) reinterpret_cast<uint4*>(stage_s)[i] = make_uint4(0, 0, 0, 0);
   tc::fence_proxy_async();
   if (MODE != 0) {
     // G operand, once per CTA.  dgrad: B-operand K-major [j/8][b][8 j]; wgrad: A-operand K-major [b/8][j][8 b]
     uint16_t* gs = reinterpret_cast<uint16_t*>(g_s);
-    for (int idx = threadIdx.x; idx < a.BP * kF1J; idx += kF1Threads) {
+    for (int idx = threadIdx.x; idx < a.BP * kF1J; idx += kThr) {
       const int b = idx / kF1J, j = idx - b * kF1J;
       const float v = (b < a.B && j < a.F1) ? a.g1[static_cast<long long>(b) * a.F1 + j] : 0.f;
       const int o = (MODE == 1) ? ((j >> 3) * a.BP + b) * 8 + (j & 7) : ((b >> 3) * kF1J + j) * 8 + (b & 7);
@@ -353,6 +357,45 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
         __syncwarp();
       }
     }
+  } else if (MODE == 2 && warp >= 6) {
+    // =============================== weight gradient: global-store warps (6..13) ===============================
+    // The accumulator tile arrives transposed in one of two staging buffers (named barriers 2/3 = buffer full,
+    // 4/5 = buffer free, 128 staging + 256 storing threads); item = (j, c8, quad of positions): lanes = (quad, c8) for
+    // one j -> eight 64-byte runs of dw[j][(cg*8+c8)*THW+pos] per store instruction.
+    const int et = threadIdx.x - 192;  // 0..255
+    const long long ntile = t_end - t_begin;
+    const long long K1 = a.KG * 8;
+    for (long long n = 0; n < ntile; ++n) {
+      const long long t = t_begin + n;
+      const float* es = reinterpret_cast<const float*>(epi_s) + (n & 1) * (128 * 129);
+      if (n & 1) asm volatile("bar.sync 3, 384;" ::: "memory"); else asm volatile("bar.sync 2, 384;" ::: "memory");
+      const long long kg0 = t * kF1KG;
+      const int cg0 = static_cast<int>(kg0 / a.THW);
+      const int pos0 = static_cast<int>(kg0 - cg0 * a.THW);
+      const bool simple = (kg0 + kF1KG <= a.KG) && (pos0 + kF1KG <= a.THW) && (a.THW % 4 == 0) && (pos0 % 4 == 0);
+      for (int item = et; item < 128 * 32; item += 256) {
+        const int j = item >> 5, c8 = (item >> 2) & 7, q = item & 3;
+        if (j >= a.F1) continue;
+        const float* src = es + (c8 * kF1KG + 4 * q) * 129 + j;
+        const float4 v4 = make_float4(src[0], src[129], src[258], src[387]);
+        float* drow = a.dw + static_cast<long long>(j) * K1;
+        if (simple) {
+          __stcs(reinterpret_cast<float4*>(drow + (cg0 * 8 + c8) * a.THW + pos0 + 4 * q), v4);
+        } else {
+          const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+          for (int i = 0; i < 4; ++i) {
+            const long long kg = kg0 + 4 * q + i;
+            if (kg < a.KG) {
+              const int cg = static_cast<int>(kg / a.THW);
+              drow[(cg * 8 + c8) * a.THW + (kg - cg * a.THW)] = vv[i];
+            }
+          }
+        }
+      }
+      if (n + 2 < ntile) {  // the staging warps wait for this buffer again two tiles later
+        if (n & 1) asm volatile("bar.arrive 5, 384;" ::: "memory"); else asm volatile("bar.arrive 4, 384;" ::: "memory");
+      }
+    }
   } else {
     // =============================== epilogue (warps 2..5) ===============================
     const int qd = warp & 3;
@@ -444,8 +487,12 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
           asm volatile("bar.sync 2, 128;" ::: "memory");  // staging buffer free for the next tile
         } else {
           // accumulator row = feature j; columns = (kgl, c8).  Stage transposed as fp32 [(c8, kgl)][j] (row 129 floats:
-          // conflict-free both ways) so that each store instruction writes eight 64-byte runs of dw[j][(cg*8+c8)*THW+pos]
-          float* es = reinterpret_cast<float*>(epi_s);
+          // conflict-free both ways) into the staging buffer seq % 2; the store warps write it out while this
+          // warp group already stages the next tile.
+          float* es = reinterpret_cast<float*>(epi_s) + (seq & 1u) * (128 * 129);
+          if (seq >= 2) {
+            if (seq & 1u) asm volatile("bar.sync 5, 384;" ::: "memory"); else asm volatile("bar.sync 4, 384;" ::: "memory");
+          }
 #pragma unroll
           for (int c0 = 0; c0 < 128; c0 += 32) {
             uint32_t v[32];
@@ -460,33 +507,7 @@ __global__ void __launch_bounds__(kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Ar
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(tempty + acc);
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          const long long kg0 = t * kF1KG;
-          const int cg0 = static_cast<int>(kg0 / a.THW);
-          const int pos0 = static_cast<int>(kg0 - cg0 * a.THW);
-          const bool simple = (kg0 + kF1KG <= a.KG) && (pos0 + kF1KG <= a.THW) && (a.THW % 4 == 0) && (pos0 % 4 == 0);
-          const long long K1 = a.KG * 8;
-          // item = (j, c8, quad of positions): lanes = (quad, c8) for one j -> eight 64-byte runs per store instruction
-          for (int item = et; item < 128 * 32; item += 128) {
-            const int j = item >> 5, c8 = (item >> 2) & 7, q = item & 3;
-            if (j >= a.F1) continue;
-            const float* src = es + (c8 * kF1KG + 4 * q) * 129 + j;
-            const float4 v4 = make_float4(src[0], src[129], src[258], src[387]);
-            float* drow = a.dw + static_cast<long long>(j) * K1;
-            if (simple) {
-              __stcs(reinterpret_cast<float4*>(drow + (cg0 * 8 + c8) * a.THW + pos0 + 4 * q), v4);
-            } else {
-              const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-              for (int i = 0; i < 4; ++i) {
-                const long long kg = kg0 + 4 * q + i;
-                if (kg < a.KG) {
-                  const int cg = static_cast<int>(kg / a.THW);
-                  drow[(cg * 8 + c8) * a.THW + (kg - cg * a.THW)] = vv[i];
-                }
-              }
-            }
-          }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (seq & 1u) asm volatile("bar.arrive 3, 384;" ::: "memory"); else asm volatile("bar.arrive 2, 384;" ::: "memory");
         }
       }
     }
@@ -514,11 +535,11 @@ static int fc1_bf16_launch(const Fc1Bf16Args& a, long long grid, cudaStream_t st
   const size_t g_bytes = (MODE == 0) ? 0 : static_cast<size_t>(a.BP) * 256;
   const size_t w_bytes = (MODE == 2) ? 0 : static_cast<size_t>(kF1KG) * kF1J * 16;
   const size_t x_bytes = (MODE == 1) ? 0 : static_cast<size_t>(kF1KG) * a.BP * 16;
-  const size_t epi_bytes = (MODE == 1) ? static_cast<size_t>(a.BP) * 256 : (MODE == 2 ? static_cast<size_t>(128) * 129 * 4 : 0);
+  const size_t epi_bytes = (MODE == 1) ? static_cast<size_t>(a.BP) * 256 : (MODE == 2 ? static_cast<size_t>(2) * 128 * 129 * 4 : 0);
   const size_t smem = 128 + round_up(g_bytes, static_cast<size_t>(128)) + 4 * (w_bytes + x_bytes) + epi_bytes;
   PVB_REQUIRE(smem <= 227 * 1024, "fc1_bf16: batch %d needs %zu B of shared memory", a.B, smem);
   PVB_CUDA(cudaFuncSetAttribute(fc1_bf16_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fc1_bf16_kernel<MODE><<<static_cast<unsigned>(grid), kF1Threads, smem, st>>>(a);
+  fc1_bf16_kernel<MODE><<<static_cast<unsigned>(grid), MODE == 2 ? kF1ThreadsWgrad : kF1Threads, smem, st>>>(a);
   PVB_LAUNCHED("fc1_bf16");
   return PVB200_OK;
 }

@@ -264,3 +264,46 @@ def test_bf16_shadow_tracks_weight_updates(dev):
         assert torch.equal(m2(batch), m(batch))  # generic path bumped the generation -> shadow recomputed
         m.fc1.weight.mul_(0.5)  # in-place edit through torch
         assert torch.equal(m(batch), fresh_forward())
+
+
+@pytest.mark.parametrize("nshards", [2, 8])
+def test_adam_fc1_row_shards_equal_the_fused_update(dev, nshards):
+    """Optimiser sharded by output feature (data parallel): the row-wise Adam kernel run once per shard + the shard
+    interleave must reproduce the fused full update (weights, moments AND the bf16 shadow) bit for bit."""
+    from predict_pv_yield_b200 import lib
+
+    L = lib.load()
+    F1, Cg, T, H, W = 128, 2, 3, 5, 6
+    KG = Cg * T * H * W
+    K1 = KG * 8
+    g = torch.Generator().manual_seed(11)
+    stream = torch.cuda.current_stream().cuda_stream
+    w0 = (torch.randn((F1, K1), generator=g) / np.sqrt(K1)).to(dev)
+    grad = torch.randn((F1, K1), generator=g).to(dev)
+    m0 = (torch.randn((F1, K1), generator=g) * 0.1).to(dev)
+    v0 = (torch.rand((F1, K1), generator=g) * 0.01).to(dev)
+    hyper = (5e-4, 0.9, 0.999, 1e-8, 3, 0.125)
+    # fused full update
+    wa, ma, va = w0.clone(), m0.clone(), v0.clone()
+    sha = torch.zeros(L.pvb200_fc1_bf16_shadow_bytes(Cg, T, H, W), dtype=torch.uint8, device=dev)
+    lib.check(L.pvb200_adam_fc1_shadow(wa.data_ptr(), grad.data_ptr(), ma.data_ptr(), va.data_ptr(), sha.data_ptr(), F1, Cg, T, H, W,
+                                       *hyper, stream), "adam_fc1_shadow")
+    # the same update shard by shard
+    wb, mb, vb = w0.clone(), m0.clone(), v0.clone()
+    nrows = F1 // nshards
+    gathered = torch.empty((nshards, KG, nrows, 8), dtype=torch.bfloat16, device=dev)
+    for r in range(nshards):
+        lib.check(L.pvb200_adam_fc1_shadow_rows(wb.data_ptr(), grad.data_ptr(), mb.data_ptr(), vb.data_ptr(), gathered[r].data_ptr(),
+                                                F1, Cg, T, H, W, r * nrows, nrows, *hyper, stream), "adam_fc1_shadow_rows")
+    shb = torch.zeros_like(sha)
+    lib.check(L.pvb200_fc1_shadow_from_shards(gathered.data_ptr(), shb.data_ptr(), nshards, nrows, Cg, T, H, W, stream), "from_shards")
+    torch.cuda.synchronize()
+    assert torch.equal(wa, wb) and torch.equal(ma, mb) and torch.equal(va, vb)
+    assert torch.equal(sha, shb)
+    # and the update itself is torch.optim.Adam's (on the scaled gradient)
+    p = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.Adam([p], lr=hyper[0], betas=(hyper[1], hyper[2]), eps=hyper[3])
+    opt.state[p] = {"step": torch.tensor(float(hyper[4] - 1)), "exp_avg": m0.clone(), "exp_avg_sq": v0.clone()}
+    p.grad = grad * hyper[5]
+    opt.step()
+    assert O.normalised_max_err(wb, p.detach()) <= 1e-6
