@@ -252,7 +252,7 @@ def conv3d_fwd_bf16(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]
 
 
 def conv3d_dgrad_bf16(gz_padded: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Tensor], out_pad: int = 0,
-                      also_gzw: bool = False):
+                      also_gzw: bool = False, persistent: bool = False):
     """gx (blocked bf16, optionally written into a padded tensor) from gz zero-padded by 2 on T,H,W.
     ``also_gzw``: additionally return gx in the weight-gradient operand layout of the layer below."""
     L = _lib.load()
@@ -268,12 +268,20 @@ def conv3d_dgrad_bf16(gz_padded: torch.Tensor, w: torch.Tensor, mask_src: Option
         _need_cuda(mask_src, "mask_src", torch.bfloat16)
         if tuple(mask_src.shape) != (B, Cgi, Ti, Hi, Wi, 8):
             raise RuntimeError("conv3d_dgrad_bf16: mask_src shape mismatch")
-    alloc = torch.zeros if out_pad > 0 else torch.empty
-    gx = alloc((B, Cgi, Ti + 2 * out_pad, Hi + 2 * out_pad, Wi + 2 * out_pad, 8), dtype=torch.bfloat16, device=gz_padded.device)
+    # zero-bordered outputs live in persistent buffers (one per shape): the kernel rewrites every valid position, the
+    # border / wrap columns stay zero from the first allocation, so there is no per-step memset (6 x ~100 MB per step)
+    gx_shape = (B, Cgi, Ti + 2 * out_pad, Hi + 2 * out_pad, Wi + 2 * out_pad, 8)
+    if out_pad > 0 and persistent:
+        gx = _zero_bordered("gx_pad", gx_shape, gz_padded.device)
+    else:
+        gx = (torch.zeros if out_pad > 0 else torch.empty)(gx_shape, dtype=torch.bfloat16, device=gz_padded.device)
     gzw = None
     if also_gzw:
         QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(Hi + 2, Wi + 2))
-        gzw = torch.zeros((B, Cgi, Ti, QP, 8), dtype=torch.bfloat16, device=gz_padded.device)
+        if persistent:
+            gzw = _zero_bordered("gzw", (B, Cgi, Ti, QP, 8), gz_padded.device)
+        else:
+            gzw = torch.zeros((B, Cgi, Ti, QP, 8), dtype=torch.bfloat16, device=gz_padded.device)
     ws = _workspace("conv_bf16", L.pvb200_conv3d_bf16_workspace_bytes(Ci, Co), gz_padded.device)
     npos = B * Ti * Hi * Wi
     with _timed(f"conv3d_dgrad_bf16[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
@@ -448,9 +456,9 @@ class EncoderBf16Fn(torch.autograd.Function):
             grads[2 * l], grads[2 * l + 1] = dw, db
             if l > 0:
                 if l > 1:
-                    gz_pad, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=2, also_gzw=True)
+                    gz_pad, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=2, also_gzw=True, persistent=True)
                 else:  # the gradient w.r.t. layer 0's output only feeds layer 0's weight gradient
-                    _, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=0, also_gzw=True)
+                    _, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=0, also_gzw=True, persistent=True)
         return (None, None, None, None, *grads)
 
 
