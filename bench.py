@@ -374,7 +374,17 @@ def run_ours(args):
                 "frac": ach / fma_peak if fma_peak else None,
                 "peak_source": "FP32 FMA pipe measured live by pvb200_probe_fp32_fma (fp32 mode cannot use the bf16 "
                                "tensor peak of MEASURED_PEAKS.json: 1e-5 parity rules out reduced-precision MMA)"}
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch at the conv1 layer shape;
+    # the live figure above is the average over all launches of the class)
     roof["traffic"] = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01b.json"))).get(dname)
+        if tr:
+            roof["traffic"] = tr["traffic"]
+            roof["traffic_note"] = {"algorithmic_bytes_same_launch": tr["algorithmic"], "launch": tr["launch"],
+                                    "source": "profiles/traffic_r01b.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
+    except Exception:
+        pass
     roof["share_of_step"] = dd["ms"] / ms_total
     roof["ms_per_step"] = dd["ms"] / args.steps
     roof["by_kernel"] = per_kernel
