@@ -128,6 +128,20 @@ int pvb200_conv3d_wgrad_f32(const void* x, int x_is_i16, const float* mean, cons
                             int B, int Cin, int Ti, int Hi, int Wi, int Cout,
                             pvb200_stream_t stream);
 
+/* ---- time-padded variants (conv3d_sat_nwp, nn.Conv3d(..., padding=(1, 0, 0)),
+ * predict_pv_yield/models/conv3d/model_sat_nwp.py:85-100,130-143).  pad_t in {0, 1}: To = Ti + 2*pad_t - 2.
+ * Ti is always the INPUT (x / gx) time extent; gz has To planes. */
+int pvb200_conv3d_fwd_f32_tpad(const void* x, int x_is_i16, const float* mean, const float* std, const float* w,
+                               const float* bias, float* y, void* workspace, size_t workspace_bytes,
+                               int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int pad_t,
+                               pvb200_stream_t stream);
+int pvb200_conv3d_dgrad_f32_tpad(const float* gz, const float* w, const float* mask_src, float* gx,
+                                 void* workspace, size_t workspace_bytes,
+                                 int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t, pvb200_stream_t stream);
+int pvb200_conv3d_wgrad_f32_tpad(const void* x, int x_is_i16, const float* mean, const float* std,
+                                 const float* gz, float* dw, float* db, void* workspace, size_t workspace_bytes,
+                                 int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t, pvb200_stream_t stream);
+
 /* ---- a6-a9: the fully connected head --------------------------------------------------------
  * replaces model.py:122-154 (reshape, fc1, fc2, PV-history cat, fc_nwp, NWP cat, fc3, fc4) and its
  * autograd.  All matrices fp32, torch Linear layout [out][in]. */
@@ -175,6 +189,28 @@ int pvb200_head_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream);
  * weight / data gradient (g_h1 and db1 ARE produced; dw1, x, g_x may be NULL). */
 int pvb200_head_tail_fwd_f32(const pvb200_head_t* h, int S, pvb200_stream_t stream);
 int pvb200_head_tail_bwd_f32(const pvb200_head_t* h, pvb200_stream_t stream);
+
+/* ---- generic Linear (+ReLU), embedding and history flatten: the heads of conv3d_sat_nwp ------
+ * replace self.fc1 .. self.fc4, self.nwp_fc1/2, self.pv_fc1 (nn.Linear), torch.cat, nn.Embedding and
+ * .nan_to_num(0).reshape(...) of predict_pv_yield/models/conv3d/model_sat_nwp.py:102-172,196-266.  w is [N][K] (torch
+ * layout); x / y / gy / gx rows may be column slices of wider buffers (ld* = row stride in floats), which is how the
+ * concatenations are done without copies.  K >= 8192 uses the weight-streaming fc1 kernels and needs contiguous rows. */
+size_t pvb200_linear_workspace_bytes(int B, int N, long long K);
+int pvb200_linear_fwd_f32(const float* x, long long ldx, const float* w, const float* bias, float* y, long long ldy,
+                          int B, long long K, int N, int relu, void* workspace, size_t workspace_bytes,
+                          pvb200_stream_t stream);
+/* gy: gradient w.r.t. the layer OUTPUT; y: the saved output if the layer has a ReLU (else NULL).  Writes dw, db and,
+ * when gx != NULL, gx = g_pre . W -- multiplied by (x > 0) if mask_gx_with_x (x is itself a post-ReLU activation). */
+int pvb200_linear_bwd_f32(const float* x, long long ldx, const float* w, const float* y, long long ldy,
+                          const float* gy, long long ldgy, float* gx, long long ldgx, int mask_gx_with_x,
+                          float* dw, float* db, int B, long long K, int N, void* workspace, size_t workspace_bytes,
+                          pvb200_stream_t stream);
+int pvb200_embedding_fwd_f32(const float* table, const int* ids, float* y, long long ldy, int B, int V, int D,
+                             pvb200_stream_t stream);
+int pvb200_embedding_bwd_f32(const float* gy, long long ldgy, const int* ids, float* dtable, int B, int V, int D,
+                             pvb200_stream_t stream);
+int pvb200_history_flatten_f32(const float* src, long long sb, long long st, float* dst, long long lddst, int B, int nt,
+                               int ns, pvb200_stream_t stream);
 
 /* ---- a6/a11 in bf16: fc1 as weight-streaming tensor-core GEMMs ------------------------------------------------
  * replaces self.fc1 / F.relu(self.fc1(out)), model.py:92,125 and autograd.  Features are the last conv activation in

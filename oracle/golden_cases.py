@@ -44,6 +44,54 @@ CASES = {
     ),
 }
 
+# ---- the two-tower model (predict_pv_yield/models/conv3d/model_sat_nwp.py) ---------------------
+SAT_NWP_CASES = {
+    # the reference's test yaml (tests/configs/model/conv3d_sat_nwp.yaml) shape family: small crops, both towers,
+    # PV history, embedding
+    "sat_nwp_pv": dict(
+        model=dict(include_pv_or_gsp_yield_history=True, include_nwp=True, forecast_minutes=60, history_minutes=60,
+                   number_of_conv3d_layers=3, conv3d_channels=16, image_size_pixels=12, nwp_image_size_pixels=10,
+                   number_sat_channels=11, number_nwp_channels=10, fc1_output_features=32, fc2_output_features=32,
+                   fc3_output_features=16, output_variable="pv_yield", embedding_dem=16, include_pv_yield_history=True,
+                   include_future_satellite=True),
+        batch=3,
+    ),
+    # gsp target, no future satellite, no PV-history layer (the production yaml's switches, configs/model/conv3d_sat_nwp.yaml)
+    "sat_nwp_gsp": dict(
+        model=dict(include_pv_or_gsp_yield_history=False, include_nwp=True, forecast_minutes=120, history_minutes=30,
+                   number_of_conv3d_layers=2, conv3d_channels=32, image_size_pixels=10, nwp_image_size_pixels=8,
+                   number_sat_channels=12, number_nwp_channels=10, fc1_output_features=128, fc2_output_features=128,
+                   fc3_output_features=64, output_variable="gsp_yield", embedding_dem=16, include_pv_yield_history=False,
+                   include_future_satellite=False),
+        batch=2,
+    ),
+}
+
+
+def sat_nwp_batch(name: str, seed: int = 519) -> dict:
+    """Deterministic nested batch dict for SAT_NWP_CASES[name] (int16 satellite, NaNs in the first history row)."""
+    case = SAT_NWP_CASES[name]
+    kw, B = case["model"], case["batch"]
+    rs = np.random.RandomState(seed)
+    C, T, S = kw["number_sat_channels"], seq_len_of(kw), kw["image_size_pixels"]
+    sat = rs.randint(0, 1024, size=(B, C, T, S, S)).astype(np.int16)
+    sat[rs.rand(*sat.shape) < 2e-3] = -1
+    t_nwp = kw["forecast_minutes"] // 60 + int(np.ceil(kw["history_minutes"] / 60)) + 1
+    nwp = rs.randn(B, kw["number_nwp_channels"], t_nwp, kw["nwp_image_size_pixels"], kw["nwp_image_size_pixels"]).astype(np.float32)
+    pv = rs.rand(B, T, 128).astype(np.float32)
+    pv[:, 0, :][rs.rand(B, 128) < 0.05] = np.nan
+    pv[:, -kw["forecast_minutes"] // 5:, 0] = rs.rand(B, kw["forecast_minutes"] // 5).astype(np.float32)  # finite targets
+    n30 = kw["history_minutes"] // 30 + 1 + kw["forecast_minutes"] // 30
+    gsp = rs.rand(B, n30, 32).astype(np.float32)
+    b = {
+        "satellite": {"data": torch.from_numpy(sat)},
+        "nwp": {"data": torch.from_numpy(nwp)},
+        "pv": {"pv_yield": torch.from_numpy(pv), "pv_system_row_number": torch.from_numpy(rs.randint(0, 940, size=(B, 128)).astype(np.int64))},
+        "gsp": {"gsp_yield": torch.from_numpy(gsp), "gsp_id": torch.from_numpy(rs.randint(0, 338, size=(B, 32)).astype(np.int64))},
+    }
+    return b
+
+
 SUBSAMPLE = 97  # stride used to thin out large tensors (fc1.weight and its grad) in the fixtures
 
 

@@ -30,19 +30,20 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 from oracle import ref_shims  # noqa: E402
 from oracle.conv3d_oracle import sat_constants, sat_normalise_numpy  # noqa: E402
-from oracle.golden_cases import CASES, golden_batch, golden_state_dict, thin  # noqa: E402
+from oracle.golden_cases import CASES, SAT_NWP_CASES, golden_batch, golden_state_dict, sat_nwp_batch, thin  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
 def run_case(name: str) -> dict:
-    Model = ref_shims.import_reference_model()
-    case = CASES[name]
+    if name in SAT_NWP_CASES:  # models/conv3d/model_sat_nwp.py
+        Model, case, batch = ref_shims.import_reference_sat_nwp_model(), SAT_NWP_CASES[name], sat_nwp_batch(name)
+    else:
+        Model, case, batch = ref_shims.import_reference_model(), CASES[name], golden_batch(name)
     torch.manual_seed(0)
     model = Model(**case["model"])
     model.batch_size = case["batch"]  # base_model.py:30,95 (class default 32 truncates targets)
     model.load_state_dict(golden_state_dict(model))
-    batch = golden_batch(name)
     # normalise exactly as netcdf_dataset.py:96-101 does, in numpy, then hand the float cube to the reference
     sat = batch["satellite"]["data"].numpy()
     mean, std = sat_constants(sat.shape[1])
@@ -82,7 +83,7 @@ def normalise_digest() -> str:
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # the reference's conv wgrad is thread-count dependent at the 1e-5 level
-    for name in CASES:
+    for name in list(CASES) + list(SAT_NWP_CASES):
         res = run_case(name)
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **res)
         print(name, "y_hat", res["y_hat"].shape, "loss", float(res["loss"]))

@@ -127,3 +127,13 @@ def import_reference_model():
     from predict_pv_yield.models.conv3d.model import Model  # noqa: E402  (the real reference file)
 
     return Model
+
+
+def import_reference_sat_nwp_model():
+    """Return the reference two-tower ``Model`` class (``predict_pv_yield/models/conv3d/model_sat_nwp.py:14``), unmodified."""
+    install()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from predict_pv_yield.models.conv3d.model_sat_nwp import Model  # noqa: E402  (the real reference file)
+
+    return Model

@@ -40,7 +40,8 @@ struct ConvArgs {
   float* y;           // [B,Co,To,Ho,Wo]
   int B, Ci, Ti, Hi, Wi;
   int Co, To, Ho, Wo;
-  int P;      // implicit zero padding on every side of T,H,W (0: forward, 2: data gradient)
+  int P;      // implicit zero padding on every side of H,W (0: forward, 2: data gradient)
+  int Pt;     // implicit zero padding on both sides of T (forward: the layer's time padding pt; data gradient: 2 - pt)
   int Wps;    // pitch of the flattened position space, multiple of 4, >= Wi + 2P
   int NP;     // staged positions per (ci,kt) plane = kQT + 2*Wps + 8
   int tiles_per_plane;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
     for (int pl = warp; pl < kCC * 3; pl += kConvThreads / 32) {
       const int c = pl / 3, kt = pl - c * 3;
       const int ci = c0 + c;
-      const int ti = to + kt - a.P;
+      const int ti = to + kt - a.Pt;
       float* dst = in_b + pl * a.NP;
       const bool plane_ok = (ci < a.Ci) && (ti >= 0) && (ti < a.Ti);
       const long long base = plane_ok ? ((static_cast<long long>(b) * a.Ci + ci) * a.Ti + ti) * plane_sz : 0;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
 #pragma unroll 1
       for (int kt = 0; kt < 3; ++kt) {
         // a time plane that lies entirely in the zero padding of the data gradient contributes nothing (block-uniform)
-        const int ti = to + kt - a.P;
+        const int ti = to + kt - a.Pt;
         if (ti < 0 || ti >= a.Ti) continue;
         const float* ip = in_b + (c * 3 + kt) * a.NP + 4 * tp;
         const float* wp = w_b + (c * 27 + kt * 9) * kCoT + 8 * cg;
@@ -255,12 +256,12 @@ static size_t conv_ws_bytes(int Ci_role, int Co_role) {
 // role-level launcher shared by forward and data gradient
 static int launch_conv(const void* x, bool i16, const float* mean, const float* stdv, const float* w, long long s_co,
                        long long s_ci, int flip, const float* bias, const float* mask, float* y, int B, int Ci, int Ti,
-                       int Hi, int Wi, int Co, int P, int relu, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                       int Hi, int Wi, int Co, int P, int Pt, int relu, void* ws, size_t ws_bytes, cudaStream_t stream) {
   ConvArgs a;
   a.x = x; a.mean = mean; a.stdv = stdv; a.bias = bias; a.mask = mask; a.y = y;
   a.B = B; a.Ci = Ci; a.Ti = Ti; a.Hi = Hi; a.Wi = Wi; a.Co = Co;
-  a.P = P;
-  a.To = Ti + 2 * P - 2; a.Ho = Hi + 2 * P - 2; a.Wo = Wi + 2 * P - 2;
+  a.P = P; a.Pt = Pt;
+  a.To = Ti + 2 * Pt - 2; a.Ho = Hi + 2 * P - 2; a.Wo = Wi + 2 * P - 2;
   PVB_REQUIRE(a.To > 0 && a.Ho > 0 && a.Wo > 0, "conv3d: input %dx%dx%d too small for a 3x3x3 kernel", Ti, Hi, Wi);
   a.Wps = round_up(Wi + 2 * P, 4);
   a.NP = kQT + 2 * a.Wps + 8;
@@ -307,28 +308,43 @@ size_t pvb200_conv3d_workspace_bytes(int Cin, int Cout) {
   return f > d ? f : d;
 }
 
+int pvb200_conv3d_fwd_f32_tpad(const void* x, int x_is_i16, const float* mean, const float* std, const float* w,
+                               const float* bias, float* y, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
+                               int Hi, int Wi, int Cout, int relu, int pad_t, pvb200_stream_t stream) {
+  PVB_REQUIRE(x && w && y, "conv3d_fwd: null pointer");
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0, "conv3d_fwd: bad shape");
+  PVB_REQUIRE(pad_t == 0 || pad_t == 1, "conv3d_fwd: time padding %d not in {0, 1}", pad_t);
+  PVB_REQUIRE(!x_is_i16 || (mean && std), "conv3d_fwd: int16 input needs mean/std");
+  return pvb::launch_conv(x, x_is_i16 != 0, mean, std, w, /*s_co=*/static_cast<long long>(Cin) * 27, /*s_ci=*/27,
+                          /*flip=*/0, bias, nullptr, y, B, Cin, Ti, Hi, Wi, Cout, /*P=*/0, /*Pt=*/pad_t, relu, workspace,
+                          workspace_bytes, pvb::as_stream(stream));
+}
+
 int pvb200_conv3d_fwd_f32(const void* x, int x_is_i16, const float* mean, const float* std, const float* w,
                           const float* bias, float* y, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
                           int Hi, int Wi, int Cout, int relu, pvb200_stream_t stream) {
-  PVB_REQUIRE(x && w && y, "conv3d_fwd: null pointer");
-  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0, "conv3d_fwd: bad shape");
-  PVB_REQUIRE(!x_is_i16 || (mean && std), "conv3d_fwd: int16 input needs mean/std");
-  return pvb::launch_conv(x, x_is_i16 != 0, mean, std, w, /*s_co=*/static_cast<long long>(Cin) * 27, /*s_ci=*/27,
-                          /*flip=*/0, bias, nullptr, y, B, Cin, Ti, Hi, Wi, Cout, /*P=*/0, relu, workspace,
-                          workspace_bytes, pvb::as_stream(stream));
+  return pvb200_conv3d_fwd_f32_tpad(x, x_is_i16, mean, std, w, bias, y, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout, relu,
+                                    0, stream);
 }
 
 int pvb200_conv3d_dgrad_f32(const float* gz, const float* w, const float* mask_src, float* gx, void* workspace,
                             size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
                             pvb200_stream_t stream) {
+  return pvb200_conv3d_dgrad_f32_tpad(gz, w, mask_src, gx, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout, 0, stream);
+}
+
+int pvb200_conv3d_dgrad_f32_tpad(const float* gz, const float* w, const float* mask_src, float* gx, void* workspace,
+                                 size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
+                                 pvb200_stream_t stream) {
   PVB_REQUIRE(gz && w && gx, "conv3d_dgrad: null pointer");
-  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti > 2 && Hi > 2 && Wi > 2, "conv3d_dgrad: bad shape");
+  PVB_REQUIRE(pad_t == 0 || pad_t == 1, "conv3d_dgrad: time padding %d not in {0, 1}", pad_t);
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti + 2 * pad_t > 2 && Hi > 2 && Wi > 2, "conv3d_dgrad: bad shape");
   // roles: the kernel's "input" is gz [B,Cout,Ti-2,Hi-2,Wi-2] padded by 2, its "output" is gx [B,Cin,Ti,Hi,Wi];
   // real weight w[co][ci][tap] is read as w[in-role=co][out-role=ci][26-tap]
   return pvb::launch_conv(gz, false, nullptr, nullptr, w, /*s_co (out-role=ci)=*/27,
                           /*s_ci (in-role=co)=*/static_cast<long long>(Cin) * 27, /*flip=*/1, nullptr, mask_src, gx, B,
-                          /*Ci role=*/Cout, Ti - 2, Hi - 2, Wi - 2, /*Co role=*/Cin, /*P=*/2, /*relu=*/0, workspace,
-                          workspace_bytes, pvb::as_stream(stream));
+                          /*Ci role=*/Cout, Ti + 2 * pad_t - 2, Hi - 2, Wi - 2, /*Co role=*/Cin, /*P=*/2, /*Pt=*/2 - pad_t,
+                          /*relu=*/0, workspace, workspace_bytes, pvb::as_stream(stream));
 }
 
 }  // extern "C"

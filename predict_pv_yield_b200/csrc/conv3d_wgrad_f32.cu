@@ -30,6 +30,7 @@ struct WgradArgs {
   int ncog;           // ceil(Co / 4)
   int items;          // ncog * Ci * KTS
   int pairs;          // Wi even and 8-byte aligned tensors: stage two positions per copy (never straddles a row)
+  int pad_t;          // time padding of the layer (0 or 1): input plane to + kt - pad_t, zero outside [0, Ti)
 };
 
 // Work is ordered (b, tile, to) with `to` fastest: a CTA walks DOWN the time axis of one (sample, position tile)
@@ -70,6 +71,11 @@ __global__ void __launch_bounds__(KTS == 1 ? 256 : 384, 1) conv3d_wgrad_f32_kern
 
   // stage input time plane `ti` of sample b (all Ci channels) into ring slot `slot`
   auto stage_x = [&](int b, int ti, int slot) {
+    ti -= a.pad_t;
+    if (ti < 0 || ti >= a.Ti) {  // a plane of the time padding: zeros (block-uniform)
+      for (int i = tid; i < a.Ci * a.NPs; i += blockDim.x) x_s[slot * a.Ci * a.NPs + i] = 0.f;
+      return;
+    }
     for (int c = warp; c < a.Ci; c += nwarp) {
       float* dst = x_s + (slot * a.Ci + c) * a.NPs;
       const long long base = ((static_cast<long long>(b) * a.Ci + c) * a.Ti + ti) * xplane;
@@ -260,9 +266,17 @@ size_t pvb200_conv3d_wgrad_workspace_bytes(int Cin, int Cout) {
 int pvb200_conv3d_wgrad_f32(const void* x, int x_is_i16, const float* mean, const float* std, const float* gz,
                             float* dw, float* db, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
                             int Hi, int Wi, int Cout, pvb200_stream_t stream) {
+  return pvb200_conv3d_wgrad_f32_tpad(x, x_is_i16, mean, std, gz, dw, db, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout, 0,
+                                      stream);
+}
+
+int pvb200_conv3d_wgrad_f32_tpad(const void* x, int x_is_i16, const float* mean, const float* std, const float* gz,
+                                 float* dw, float* db, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
+                                 int Hi, int Wi, int Cout, int pad_t, pvb200_stream_t stream) {
   using namespace pvb;
   PVB_REQUIRE(x && gz && dw, "conv3d_wgrad: null pointer");
-  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti > 2 && Hi > 2 && Wi > 2, "conv3d_wgrad: bad shape");
+  PVB_REQUIRE(pad_t == 0 || pad_t == 1, "conv3d_wgrad: time padding %d not in {0, 1}", pad_t);
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti + 2 * pad_t > 2 && Hi > 2 && Wi > 2, "conv3d_wgrad: bad shape");
   PVB_REQUIRE(Cin <= kWgMaxCi, "conv3d_wgrad: Cin=%d > %d not supported", Cin, kWgMaxCi);
   PVB_REQUIRE(!x_is_i16 || (mean && std), "conv3d_wgrad: int16 input needs mean/std");
   const size_t need = pvb200_conv3d_wgrad_workspace_bytes(Cin, Cout);
@@ -273,7 +287,8 @@ int pvb200_conv3d_wgrad_f32(const void* x, int x_is_i16, const float* mean, cons
   WgradArgs a;
   a.x = x; a.mean = mean; a.stdv = std; a.gz = gz; a.partial = static_cast<float*>(workspace);
   a.B = B; a.Ci = Cin; a.Ti = Ti; a.Hi = Hi; a.Wi = Wi; a.Co = Cout;
-  a.To = Ti - 2; a.Ho = Hi - 2; a.Wo = Wi - 2;
+  a.To = Ti + 2 * pad_t - 2; a.Ho = Hi - 2; a.Wo = Wi - 2;
+  a.pad_t = pad_t;
   a.Wps = round_up(Wi, 4);
   a.NP = kWgQC + 2 * a.Wps + 8;
   a.NPs = round_up(a.NP, 8) + 4;

@@ -852,3 +852,249 @@ static int head_bwd_impl(const pvb200_head_t* h, bool with_fc1, pvb200_stream_t 
 }
 
 
+
+// =====================================================================================================================
+// Generic Linear (+ReLU) forward / backward, torch layout w[N][K]  (the heads of conv3d_sat_nwp,
+// predict_pv_yield/models/conv3d/model_sat_nwp.py:102-172,196-266 -- fc1/fc2 of the satellite tower, nwp_fc1/nwp_fc2,
+// pv_fc1, fc3, fc4 -- are plain nn.Linear layers joined by torch.cat).  Rows may be column slices of wider buffers
+// (ld* strides), which is how the concatenations are done without copies.  K >= 8192 ("tower" layers, 1-2 M input
+// features) goes through the weight-streaming fc1 kernels above, everything else through small per-sample kernels.
+// =====================================================================================================================
+namespace pvb {
+
+constexpr long long kLinBigK = 8192;
+
+// y[b][n] = act(bias[n] + sum_s partial[s][b][n])
+__global__ void linear_finish_kernel(const float* __restrict__ partial, int S, const float* __restrict__ bias, float* __restrict__ y,
+                                     long long ldy, int B, int N, int relu) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * N) return;
+  const int b = idx / N, n = idx - b * N;
+  float s = 0.f;
+  for (int i = 0; i < S; ++i) s += partial[(static_cast<long long>(i) * B + b) * N + n];  // fixed order: deterministic
+  s += bias ? bias[n] : 0.f;
+  y[b * ldy + n] = (relu && s < 0.f) ? 0.f : s;
+}
+
+// one CTA per sample: x row in shared memory, one warp per output feature (strided), lanes over K
+__global__ void __launch_bounds__(256) linear_fwd_small_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ y, long long ldy,
+                                                               int K, int N, int relu) {
+  extern __shared__ float xs[];
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) xs[k] = x[b * ldx + k];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = warp; n < N; n += blockDim.x >> 5) {
+    const float* wr = w + static_cast<long long>(n) * K;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(xs[k], __ldg(wr + k), s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      s += bias ? bias[n] : 0.f;
+      y[b * ldy + n] = (relu && s < 0.f) ? 0.f : s;
+    }
+  }
+}
+
+// g_pre[b][n] = gy[b][n] * (y[b][n] > 0 if relu)
+__global__ void linear_gpre_kernel(const float* __restrict__ gy, long long ldgy, const float* __restrict__ y, long long ldy,
+                                   float* __restrict__ g_pre, int B, int N) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * N) return;
+  const int b = idx / N, n = idx - b * N;
+  const float g = gy[b * ldgy + n];
+  g_pre[idx] = (y == nullptr || y[b * ldy + n] > 0.f) ? g : 0.f;
+}
+
+// gx[b][k] = sum_n g_pre[b][n] * w[n][k]   (optionally masked by x[b][k] > 0); one CTA per (sample, 256 columns)
+__global__ void __launch_bounds__(256) linear_dgrad_small_kernel(const float* __restrict__ g_pre, const float* __restrict__ w,
+                                                                 const float* __restrict__ x, long long ldx, float* __restrict__ gx,
+                                                                 long long ldgx, int K, int N) {
+  extern __shared__ float gs[];
+  const int b = blockIdx.y;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) gs[n] = g_pre[static_cast<long long>(b) * N + n];
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s = fmaf(gs[n], __ldg(w + static_cast<long long>(n) * K + k), s);
+  if (x != nullptr && !(x[b * ldx + k] > 0.f)) s = 0.f;
+  gx[b * ldgx + k] = s;
+}
+
+__global__ void embedding_fwd_kernel(const float* __restrict__ table, const int* __restrict__ ids, float* __restrict__ y,
+                                     long long ldy, int B, int V, int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * D) return;
+  const int b = idx / D, d = idx - b * D;
+  const int v = ids[b];
+  y[b * ldy + d] = (v >= 0 && v < V) ? table[static_cast<long long>(v) * D + d] : 0.f;
+}
+
+__global__ void embedding_bwd_kernel(const float* __restrict__ gy, long long ldgy, const int* __restrict__ ids,
+                                     float* __restrict__ dtable, int B, int V, int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= V * D) return;
+  const int v = idx / D, d = idx - v * D;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b)
+    if (ids[b] == v) s += gy[b * ldgy + d];
+  dtable[idx] = s;
+}
+
+__global__ void history_flatten_kernel(const float* __restrict__ src, long long sb, long long st, float* __restrict__ dst,
+                                       long long lddst, int B, int nt, int ns) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * nt * ns) return;
+  const int s = idx % ns;
+  const int t = (idx / ns) % nt;
+  const int b = idx / (ns * nt);
+  const float v = src[b * sb + t * st + s];
+  dst[b * lddst + t * ns + s] = (v != v) ? 0.f : v;  // NaN -> 0 (the history holds no infinities)
+}
+
+}  // namespace pvb
+
+extern "C" {
+
+size_t pvb200_linear_workspace_bytes(int B, int N, long long K) {
+  if (B <= 0 || N <= 0 || K <= 0) return 0;
+  size_t ws = static_cast<size_t>(B) * N * sizeof(float);  // g_pre of the backward pass
+  if (K >= pvb::kLinBigK) {
+    const pvb::Fc1Plan p = pvb::fc1_plan(B, N, K);
+    const size_t f = static_cast<size_t>(p.S) * B * N * sizeof(float);
+    if (f > ws) ws = f;
+  }
+  return ws;
+}
+
+int pvb200_linear_fwd_f32(const float* x, long long ldx, const float* w, const float* bias, float* y, long long ldy, int B,
+                          long long K, int N, int relu, void* workspace, size_t workspace_bytes, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(x && w && y && B > 0 && K > 0 && N > 0 && ldx >= K && ldy >= N, "linear_fwd: bad argument");
+  cudaStream_t st = as_stream(stream);
+  if (K >= kLinBigK) {
+    PVB_REQUIRE(ldx == K, "linear_fwd: K=%lld >= %lld needs contiguous rows", K, kLinBigK);
+    const Fc1Plan p = fc1_plan(B, N, K);
+    const size_t need = static_cast<size_t>(p.S) * B * N * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+      set_error("linear_fwd: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+      return PVB200_ERR_WORKSPACE;
+    }
+    float* partial = static_cast<float*>(workspace);
+    const long long ctas = static_cast<long long>(p.S) * p.nbt * p.njt;
+    if (vec4_ok(x, K) && vec4_ok(w, K)) {
+      const size_t smem2 = 2 * static_cast<size_t>(kFc1JT + kFc1BT) * (kFc1KT + 4) * sizeof(float);
+      PVB_CUDA(cudaFuncSetAttribute(fc1_fwd_splitk_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      fc1_fwd_splitk_v2_kernel<<<static_cast<unsigned>(ctas), kFc1V2Threads, smem2, st>>>(x, w, partial, B, N, K, p.nbt, p.njt,
+                                                                                          p.k_per_split);
+    } else {
+      fc1_fwd_splitk_kernel<<<static_cast<unsigned>(ctas), kHeadThreads, 0, st>>>(x, w, partial, B, N, K, p.nbt, p.njt, p.k_per_split, 0);
+    }
+    PVB_LAUNCHED("linear_fwd_splitk");
+    linear_finish_kernel<<<ceil_div(B * N, 256), 256, 0, st>>>(partial, p.S, bias, y, ldy, B, N, relu);
+    PVB_LAUNCHED("linear_finish");
+    return PVB200_OK;
+  }
+  PVB_REQUIRE(K * sizeof(float) <= 48 * 1024, "linear_fwd: K=%lld too large for the small kernel", K);
+  linear_fwd_small_kernel<<<B, 256, static_cast<size_t>(K) * sizeof(float), st>>>(x, ldx, w, bias, y, ldy, static_cast<int>(K), N, relu);
+  PVB_LAUNCHED("linear_fwd_small");
+  return PVB200_OK;
+}
+
+/* gy = gradient w.r.t. the layer's OUTPUT (post-activation); y = the saved output when the layer has a ReLU, else NULL.
+ * Writes dw [N][K], db [N] and, if gx != NULL, gx = g_pre . W (times (x > 0) when mask_gx_with_x: the input is itself a
+ * post-ReLU activation whose producer wants the gradient of its PRE-activation).  workspace >= B*N floats. */
+int pvb200_linear_bwd_f32(const float* x, long long ldx, const float* w, const float* y, long long ldy, const float* gy,
+                          long long ldgy, float* gx, long long ldgx, int mask_gx_with_x, float* dw, float* db, int B, long long K,
+                          int N, void* workspace, size_t workspace_bytes, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(x && w && gy && dw && db && B > 0 && K > 0 && N > 0 && ldx >= K && ldgy >= N, "linear_bwd: bad argument");
+  PVB_REQUIRE(workspace && workspace_bytes >= static_cast<size_t>(B) * N * sizeof(float), "linear_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  float* g_pre = static_cast<float*>(workspace);
+  linear_gpre_kernel<<<ceil_div(B * N, 256), 256, 0, st>>>(gy, ldgy, y, ldy, g_pre, B, N);
+  PVB_LAUNCHED("linear_gpre");
+  if (K >= kLinBigK) {
+    PVB_REQUIRE(ldx == K && (!gx || ldgx == K), "linear_bwd: K=%lld >= %lld needs contiguous rows", K, kLinBigK);
+    PVB_REQUIRE(!gx || mask_gx_with_x, "linear_bwd: the streaming data gradient always applies the input's ReLU mask");
+    // bias gradient (I = 0 columns: only the db part of the kernel runs)
+    linear_wgrad_small_kernel<<<ceil_div(N, 256), 256, 0, st>>>(g_pre, N, g_pre, N, db, db, B, N, 0);
+    PVB_LAUNCHED("linear_bias_grad");
+    const int vec = vec4_ok(x, K) && vec4_ok(w, K) && vec4_ok(dw, K) && (!gx || vec4_ok(gx, K));
+    const int njt = ceil_div(N, kFc1JT);
+    const long long kt = ceil_div(K, 128LL);
+    PVB_REQUIRE(kt * njt <= 0x7fffffffLL, "linear_bwd: K too large");
+    const int sms = sm_count();
+    PVB_REQUIRE(sms > 0, "linear_bwd: no CUDA device");
+    if (vec && N <= 128 && N % 4 == 0 && vec4_ok(g_pre, N)) {
+      const size_t smemw = 2 * static_cast<size_t>(kFc1BT) * (kFc1JT + 128) * sizeof(float);
+      PVB_CUDA(cudaFuncSetAttribute(fc1_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw));
+      const long long gw = kt < 2LL * sms ? kt : 2LL * sms;
+      fc1_wgrad_v2_kernel<<<static_cast<unsigned>(gw), kHeadThreads, smemw, st>>>(g_pre, x, dw, B, N, K, kt, ceil_div(B, kFc1BT));
+    } else {
+      fc1_wgrad_kernel<<<static_cast<unsigned>(kt * njt), kHeadThreads, 0, st>>>(g_pre, x, dw, B, N, K, njt, vec);
+    }
+    PVB_LAUNCHED("linear_wgrad_stream");
+    if (gx) {
+      const int nbt = ceil_div(B, kFc1BT);
+      if (vec && N <= 128) {
+        const size_t smemd = (128 * kFc1BT + 2 * 128 * 128) * sizeof(float);
+        PVB_CUDA(cudaFuncSetAttribute(fc1_dgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemd));
+        const long long gx_ = kt < sms ? kt : sms;
+        fc1_dgrad_v2_kernel<<<dim3(static_cast<unsigned>(gx_), nbt), kFc1DgThreads, smemd, st>>>(g_pre, w, x, gx, B, N, K, kt);
+      } else {
+        fc1_dgrad_kernel<<<static_cast<unsigned>(kt * nbt), kHeadThreads, 0, st>>>(g_pre, w, x, gx, B, N, K, nbt, vec);
+      }
+      PVB_LAUNCHED("linear_dgrad_stream");
+    }
+    return PVB200_OK;
+  }
+  PVB_REQUIRE(N * sizeof(float) <= 48 * 1024 && K <= 0x7fffffffLL && ldx <= 0x7fffffffLL, "linear_bwd: sizes too large for the small kernels");
+  {
+    const long long n = static_cast<long long>(N) * K + N;
+    linear_wgrad_small_kernel<<<static_cast<unsigned>(ceil_div(n, 256LL)), 256, 0, st>>>(g_pre, N, x, static_cast<int>(ldx), dw, db, B, N,
+                                                                                         static_cast<int>(K));
+    PVB_LAUNCHED("linear_wgrad_small");
+  }
+  if (gx) {
+    linear_dgrad_small_kernel<<<dim3(static_cast<unsigned>(ceil_div(K, 256LL)), B), 256, static_cast<size_t>(N) * sizeof(float), st>>>(
+        g_pre, w, mask_gx_with_x ? x : nullptr, ldx, gx, ldgx, static_cast<int>(K), N);
+    PVB_LAUNCHED("linear_dgrad_small");
+  }
+  return PVB200_OK;
+}
+
+
+/* y[b*ldy + d] = table[ids[b]][d]   (nn.Embedding(940, 16), model_sat_nwp.py:146-149,252-260) */
+int pvb200_embedding_fwd_f32(const float* table, const int* ids, float* y, long long ldy, int B, int V, int D, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(table && ids && y && B > 0 && V > 0 && D > 0 && ldy >= D, "embedding_fwd: bad argument");
+  embedding_fwd_kernel<<<ceil_div(B * D, 256), 256, 0, as_stream(stream)>>>(table, ids, y, ldy, B, V, D);
+  PVB_LAUNCHED("embedding_fwd");
+  return PVB200_OK;
+}
+
+/* dtable[v][d] = sum_{b: ids[b] == v} gy[b*ldgy + d]   (dense, deterministic: every entry is written) */
+int pvb200_embedding_bwd_f32(const float* gy, long long ldgy, const int* ids, float* dtable, int B, int V, int D,
+                             pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(gy && ids && dtable && B > 0 && V > 0 && D > 0 && ldgy >= D, "embedding_bwd: bad argument");
+  embedding_bwd_kernel<<<ceil_div(V * D, 256), 256, 0, as_stream(stream)>>>(gy, ldgy, ids, dtable, B, V, D);
+  PVB_LAUNCHED("embedding_bwd");
+  return PVB200_OK;
+}
+
+/* dst[b*lddst + t*ns + s] = nan_to_num(src[b*sb + t*st + s], 0)  for t < nt, s < ns
+ * (x.pv.pv_yield[:, :history_len+1, :ns].nan_to_num(0).reshape(B, -1), model_sat_nwp.py:207-232) */
+int pvb200_history_flatten_f32(const float* src, long long sb, long long st, float* dst, long long lddst, int B, int nt, int ns,
+                               pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(src && dst && B > 0 && nt > 0 && ns > 0 && lddst >= static_cast<long long>(nt) * ns, "history_flatten: bad argument");
+  history_flatten_kernel<<<ceil_div(B * nt * ns, 256), 256, 0, as_stream(stream)>>>(src, sb, st, dst, lddst, B, nt, ns);
+  PVB_LAUNCHED("history_flatten");
+  return PVB200_OK;
+}
+
+}  // extern "C"

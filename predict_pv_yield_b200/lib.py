@@ -76,6 +76,20 @@ SIGNATURES = {
     "pvb200_head_bwd_f32": (c_int, [C.POINTER(Head), c_void_p]),
     "pvb200_head_tail_fwd_f32": (c_int, [C.POINTER(Head), c_int, c_void_p]),
     "pvb200_head_tail_bwd_f32": (c_int, [C.POINTER(Head), c_void_p]),
+    "pvb200_conv3d_fwd_f32_tpad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_dgrad_f32_tpad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                             c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_wgrad_f32_tpad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_ll]),
+    "pvb200_linear_fwd_f32": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_int, c_int, c_void_p,
+                                      c_size_t, c_void_p]),
+    "pvb200_linear_bwd_f32": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p,
+                                      c_void_p, c_int, c_ll, c_int, c_void_p, c_size_t, c_void_p]),
+    "pvb200_embedding_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
+    "pvb200_embedding_bwd_f32": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pvb200_history_flatten_f32": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "pvb200_fc1_bf16_shadow_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "pvb200_fc1_make_shadow_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_adam_fc1_shadow": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

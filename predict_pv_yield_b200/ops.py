@@ -125,8 +125,9 @@ def sat_normalise(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, out_dt
 
 
 def conv3d_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = True,
-               mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """relu(conv3d(x, w, b)) with 3x3x3 kernel, padding 0 (model.py:117-120).  x fp32, or int16 with fused normalise."""
+               mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None, pad_t: int = 0) -> torch.Tensor:
+    """relu(conv3d(x, w, b)) with 3x3x3 kernel, padding (pad_t, 0, 0) (model.py:117-120; pad_t = 1: model_sat_nwp.py:85-100).
+    x fp32, or int16 with fused normalise."""
     L = _lib.load()
     i16 = x.dtype == torch.int16
     _need_cuda(x, "conv input", torch.int16 if i16 else torch.float32)
@@ -137,28 +138,29 @@ def conv3d_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu
     Co = w.shape[0]
     if tuple(w.shape) != (Co, Ci, 3, 3, 3):
         raise RuntimeError(f"conv3d: weight shape {tuple(w.shape)} does not match input channels {Ci}")
-    if min(Ti, Hi, Wi) < 3:
+    if min(Ti + 2 * pad_t, Hi, Wi) < 3:
         raise RuntimeError(f"conv3d: input {Ti}x{Hi}x{Wi} smaller than the 3x3x3 kernel")
     if i16 and (mean is None or std is None):
         raise RuntimeError("conv3d: int16 input needs mean/std")
-    y = torch.empty((B, Co, Ti - 2, Hi - 2, Wi - 2), dtype=torch.float32, device=x.device)
+    y = torch.empty((B, Co, Ti + 2 * pad_t - 2, Hi - 2, Wi - 2), dtype=torch.float32, device=x.device)
     nb = L.pvb200_conv3d_workspace_bytes(Ci, Co)
     ws = _workspace("conv", nb, x.device)
     with _timed(f"conv3d_fwd_f32[Ci={Ci}]", 2.0 * 27 * Ci * y.numel(), x.numel() * x.element_size() + 4.0 * y.numel()):
-        rc = L.pvb200_conv3d_fwd_f32(_p(x), int(i16), _p(mean) if i16 else None, _p(std) if i16 else None, _p(w), _p(b),
-                                     _p(y), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, int(relu), _stream())
+        rc = L.pvb200_conv3d_fwd_f32_tpad(_p(x), int(i16), _p(mean) if i16 else None, _p(std) if i16 else None, _p(w), _p(b),
+                                          _p(y), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, int(relu), pad_t, _stream())
     _lib.check(rc, "conv3d_fwd")
     return y
 
 
-def conv3d_dgrad(gz: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Tensor], x_shape: Sequence[int]) -> torch.Tensor:
+def conv3d_dgrad(gz: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Tensor], x_shape: Sequence[int],
+                 pad_t: int = 0) -> torch.Tensor:
     """gx = conv_transpose3d(gz, w) * (mask_src > 0).  gz: gradient w.r.t. the conv's pre-activation output."""
     L = _lib.load()
     _need_cuda(gz, "gz", torch.float32)
     _need_cuda(w, "conv weight", torch.float32)
     B, Ci, Ti, Hi, Wi = x_shape
     Co = w.shape[0]
-    if tuple(gz.shape) != (B, Co, Ti - 2, Hi - 2, Wi - 2):
+    if tuple(gz.shape) != (B, Co, Ti + 2 * pad_t - 2, Hi - 2, Wi - 2):
         raise RuntimeError(f"conv3d_dgrad: gz shape {tuple(gz.shape)} inconsistent with input {tuple(x_shape)}")
     if mask_src is not None:
         _need_cuda(mask_src, "mask_src", torch.float32)
@@ -169,13 +171,14 @@ def conv3d_dgrad(gz: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Ten
     ws = _workspace("conv", nb, gz.device)
     with _timed(f"conv3d_dgrad_f32[Ci={Ci}]", 2.0 * 27 * Ci * gz.numel(),
                 4.0 * (gz.numel() + gx.numel() * (2 if mask_src is not None else 1))):
-        rc = L.pvb200_conv3d_dgrad_f32(_p(gz), _p(w), _p(mask_src), _p(gx), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, _stream())
+        rc = L.pvb200_conv3d_dgrad_f32_tpad(_p(gz), _p(w), _p(mask_src), _p(gx), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
+                                            _stream())
     _lib.check(rc, "conv3d_dgrad")
     return gx
 
 
 def conv3d_wgrad(x: torch.Tensor, gz: torch.Tensor, mean: Optional[torch.Tensor] = None,
-                 std: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                 std: Optional[torch.Tensor] = None, pad_t: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """(dw [Co,Ci,3,3,3], db [Co]) from the layer input x and the pre-activation gradient gz."""
     L = _lib.load()
     i16 = x.dtype == torch.int16
@@ -183,15 +186,15 @@ def conv3d_wgrad(x: torch.Tensor, gz: torch.Tensor, mean: Optional[torch.Tensor]
     _need_cuda(gz, "gz", torch.float32)
     B, Ci, Ti, Hi, Wi = x.shape
     Co = gz.shape[1]
-    if tuple(gz.shape) != (B, Co, Ti - 2, Hi - 2, Wi - 2):
+    if tuple(gz.shape) != (B, Co, Ti + 2 * pad_t - 2, Hi - 2, Wi - 2):
         raise RuntimeError(f"conv3d_wgrad: gz shape {tuple(gz.shape)} inconsistent with input {tuple(x.shape)}")
     dw = torch.empty((Co, Ci, 3, 3, 3), dtype=torch.float32, device=x.device)
     db = torch.empty((Co,), dtype=torch.float32, device=x.device)
     nb = L.pvb200_conv3d_wgrad_workspace_bytes(Ci, Co)
     ws = _workspace("wgrad", nb, x.device)
     with _timed(f"conv3d_wgrad_f32[Ci={Ci}]", 2.0 * 27 * Ci * gz.numel(), x.numel() * x.element_size() + 4.0 * gz.numel()):
-        rc = L.pvb200_conv3d_wgrad_f32(_p(x), int(i16), _p(mean) if i16 else None, _p(std) if i16 else None, _p(gz), _p(dw),
-                                       _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, _stream())
+        rc = L.pvb200_conv3d_wgrad_f32_tpad(_p(x), int(i16), _p(mean) if i16 else None, _p(std) if i16 else None, _p(gz), _p(dw),
+                                            _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t, _stream())
     _lib.check(rc, "conv3d_wgrad")
     return dw, db
 
@@ -742,6 +745,134 @@ class HeadBf16Fn(torch.autograd.Function):
             ctx.link["gz"] = (gz_pad, gzw)
             g_act = torch.empty_like(act)  # placeholder: the real gradient travels through the link
         return None, g_act, None, None, dw1, db1, dw2, db2, dwn, dbn, dw3, db3, dw4, db4
+
+
+class TowerFn(torch.autograd.Function):
+    """Conv3d + ReLU stack with time padding (pad_t, 0, 0) in fp32: the satellite / NWP towers of conv3d_sat_nwp
+    (model_sat_nwp.py:85-100,130-143,187-190,237-240).  forward(pad_t, x, mean|None, std|None, w0, b0, ...) -> the last
+    activation flattened to [B, C*T*H*W] (NCDHW order, model_sat_nwp.py:192).  Same private protocol as ``EncoderFn``:
+    the incoming gradient already carries the ReLU mask of the last layer (``LinearFn(mask_input=True)``).  ``x`` needs no
+    gradient (it is data)."""
+
+    @staticmethod
+    def forward(ctx, pad_t, x, mean, std, *wb):
+        n_layers = len(wb) // 2
+        if x.dtype == torch.int16:
+            x = sat_normalise(x, mean, std)
+        elif x.dtype != torch.float32:
+            raise RuntimeError(f"TowerFn: input must be int16 or float32, got {x.dtype}")
+        x0 = x.contiguous()
+        acts = []
+        a = x0
+        for l in range(n_layers):
+            a = conv3d_fwd(a, wb[2 * l], wb[2 * l + 1], relu=True, pad_t=pad_t)
+            acts.append(a)
+        ctx.save_for_backward(x0, *wb, *acts)
+        ctx.n_layers, ctx.pad_t = n_layers, pad_t
+        return acts[-1].view(x0.shape[0], -1)
+
+    @staticmethod
+    def backward(ctx, g):
+        n, pad_t = ctx.n_layers, ctx.pad_t
+        saved = ctx.saved_tensors
+        x0 = saved[0]
+        wb = saved[1: 1 + 2 * n]
+        acts = saved[1 + 2 * n:]
+        gz = g.contiguous().view(acts[-1].shape)
+        grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
+        for l in range(n - 1, -1, -1):
+            xin = x0 if l == 0 else acts[l - 1]
+            grads[2 * l], grads[2 * l + 1] = conv3d_wgrad(xin, gz, pad_t=pad_t)
+            if l > 0:
+                gz = conv3d_dgrad(gz, wb[2 * l], acts[l - 1], acts[l - 1].shape, pad_t=pad_t)
+        return (None, None, None, None, *grads)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) through ``pvb200_linear_{fwd,bwd}_f32`` (nn.Linear layers of model_sat_nwp.py:102-172).
+
+    forward(x [B,K], w [N,K], b [N], relu, mask_input).  ``mask_input``: x is a post-ReLU activation whose producer
+    expects the gradient of its PRE-activation (the conv towers): gx is multiplied by (x > 0)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu, mask_input):
+        L = _lib.load()
+        for t, nm in ((x, "input"), (w, "weight"), (b, "bias")):
+            _need_cuda(t, nm, torch.float32)
+        if x.dim() != 2 or x.stride(1) != 1:
+            raise RuntimeError("LinearFn: input must be a 2-D tensor with unit column stride")
+        B, K = x.shape
+        N = w.shape[0]
+        if tuple(w.shape) != (N, K) or tuple(b.shape) != (N,):
+            raise RuntimeError(f"LinearFn: weight {tuple(w.shape)} / bias {tuple(b.shape)} do not match input features {K}")
+        w = w.contiguous()
+        y = torch.empty((B, N), dtype=torch.float32, device=x.device)
+        ws = _workspace("linear", L.pvb200_linear_workspace_bytes(B, N, K), x.device)
+        with _timed(f"linear_fwd_f32[K={K}]", 2.0 * B * N * K, 4.0 * (B * K + N * K)):
+            rc = L.pvb200_linear_fwd_f32(_p(x), x.stride(0), _p(w), _p(b), _p(y), N, B, K, N, int(relu), _p(ws), ws.numel(), _stream())
+        _lib.check(rc, "linear_fwd")
+        ctx.save_for_backward(x, w, y)
+        ctx.relu, ctx.mask_input = bool(relu), bool(mask_input)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.load()
+        x, w, y = ctx.saved_tensors
+        B, K = x.shape
+        N = w.shape[0]
+        g = g.contiguous()
+        dw = torch.empty_like(w)
+        db = torch.empty((N,), dtype=torch.float32, device=x.device)
+        gx = torch.empty((B, K), dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        ws = _workspace("linear", L.pvb200_linear_workspace_bytes(B, N, K), x.device)
+        with _timed(f"linear_bwd_f32[K={K}]", 4.0 * B * N * K, 4.0 * (2 * B * K + 2 * N * K)):
+            rc = L.pvb200_linear_bwd_f32(_p(x), x.stride(0), _p(w), _p(y) if ctx.relu else None, N, _p(g), N, _p(gx), K,
+                                         int(ctx.mask_input), _p(dw), _p(db), B, K, N, _p(ws), ws.numel(), _stream())
+        _lib.check(rc, "linear_bwd")
+        return gx, dw, db, None, None
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """table[ids] (nn.Embedding(940, 16) of model_sat_nwp.py:146-149,252-260) with a dense deterministic gradient.
+    forward(table [V,D], ids int32 [B]) -> [B, D]."""
+
+    @staticmethod
+    def forward(ctx, table, ids):
+        L = _lib.load()
+        _need_cuda(table, "embedding table", torch.float32)
+        _need_cuda(ids, "ids", torch.int32)
+        V, D = table.shape
+        B = ids.shape[0]
+        y = torch.empty((B, D), dtype=torch.float32, device=table.device)
+        _lib.check(L.pvb200_embedding_fwd_f32(_p(table.contiguous()), _p(ids), _p(y), D, B, V, D, _stream()), "embedding_fwd")
+        ctx.save_for_backward(ids)
+        ctx.V, ctx.D = V, D
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.load()
+        (ids,) = ctx.saved_tensors
+        g = g.contiguous()
+        dtable = torch.empty((ctx.V, ctx.D), dtype=torch.float32, device=g.device)
+        _lib.check(L.pvb200_embedding_bwd_f32(_p(g), ctx.D, _p(ids), _p(dtable), ids.shape[0], ctx.V, ctx.D, _stream()), "embedding_bwd")
+        return dtable, None
+
+
+def history_flatten(src: torch.Tensor, nt: int, ns: int) -> torch.Tensor:
+    """src[:, :nt, :ns].nan_to_num(0).reshape(B, -1) (model_sat_nwp.py:207-232); data, no gradient."""
+    L = _lib.load()
+    if not src.is_cuda or src.dtype != torch.float32:
+        raise RuntimeError(f"predict_pv_yield_b200: 'history' must be a float32 CUDA tensor (got {src.dtype} on {src.device}); "
+                           "there is no CPU fallback")
+    if src.dim() != 3 or src.stride(2) != 1 or src.shape[1] < nt or src.shape[2] < ns:
+        raise RuntimeError(f"history_flatten: history {tuple(src.shape)} has no [:, :{nt}, :{ns}] block")
+    B = src.shape[0]
+    out = torch.empty((B, nt * ns), dtype=torch.float32, device=src.device)
+    rc = L.pvb200_history_flatten_f32(_p(src), src.stride(0), src.stride(1), _p(out), nt * ns, B, nt, ns, _stream())
+    _lib.check(rc, "history_flatten")
+    return out
 
 
 class StepLossFn(torch.autograd.Function):
