@@ -356,7 +356,8 @@ def run_ours(args):
             "gbs": d["bytes"] / sec / 1e9 if sec > 0 else None,
         }
     hbm_bound = {"adam_step_f32", "head_fwd_f32", "head_bwd_f32", "sat_normalise", "sat_normalise_blocked_bf16",
-                 "nc_to_blocked_bf16", "blocked_to_nc_f32", "nc_to_gzw_bf16"}
+                 "nc_to_blocked_bf16", "blocked_to_nc_f32", "nc_to_gzw_bf16", "adam_fc1_shadow", "adam_fc1_shadow_rows",
+                 "fc1_fwd_bf16", "fc1_dgrad_bf16", "fc1_wgrad_bf16", "fc1_make_shadow_bf16"}
     dom = max(classes.items(), key=lambda kv: kv[1]["ms"])
     dname, dd = dom
     if dname in hbm_bound:
