@@ -180,6 +180,8 @@ struct Fc1Bf16Args {
   long long THW;
   int S;               // forward K splits
   long long tiles_per_split;
+  int nst;             // pipeline stages that fit in shared memory (2..4)
+  int nepi;            // weight gradient: staging buffers of the epilogue (1 or 2)
 };
 
 // transposing load of the X tile: smem [kgl][b][8] <- xb[b][kg0 + kgl]   (16 x BP chunks of 16 B).  Asynchronous
@@ -208,10 +210,11 @@ template <int MODE>
 __global__ void __launch_bounds__(MODE == 2 ? kF1ThreadsWgrad : kF1Threads, 1) fc1_bf16_kernel(const Fc1Bf16Args a) {
   constexpr int kThr = MODE == 2 ? kF1ThreadsWgrad : kF1Threads;
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int NST = 4;
+  constexpr int kMaxSt = 4;
+  const uint32_t NST = static_cast<uint32_t>(a.nst);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // [4]
-  uint64_t* empty = full + NST;                         // [4]
-  uint64_t* tfull = empty + NST;                        // [2]
+  uint64_t* empty = full + kMaxSt;                      // [4]
+  uint64_t* tfull = empty + kMaxSt;                     // [2]
   uint64_t* tempty = tfull + 2;                         // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
   uint8_t* g_s = smem + 128;                            // G operand (dgrad / wgrad): BP*128 bf16 = up to 64 KB... sized BP*256 B
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kF1ThreadsWgrad : kF1Threads, 1) f
 
   if (threadIdx.x == 0) {
     // full: lane 0's arrive (+ the W1s tile's bytes) and, where an X tile is staged, one cp.async arrival per producer lane
-    for (int i = 0; i < NST; ++i) { tc::mbar_init(full + i, MODE == 1 ? 1 : 33); tc::mbar_init(empty + i, 1); }
+    for (int i = 0; i < kMaxSt; ++i) { tc::mbar_init(full + i, MODE == 1 ? 1 : 33); tc::mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
     tc::fence_barrier_init();
   }
@@ -367,8 +370,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kF1ThreadsWgrad : kF1Threads, 1) f
     const long long K1 = a.KG * 8;
     for (long long n = 0; n < ntile; ++n) {
       const long long t = t_begin + n;
-      const float* es = reinterpret_cast<const float*>(epi_s) + (n & 1) * (128 * 129);
-      if (n & 1) asm volatile("bar.sync 3, 384;" ::: "memory"); else asm volatile("bar.sync 2, 384;" ::: "memory");
+      const int eb = (a.nepi == 2) ? static_cast<int>(n & 1) : 0;
+      const float* es = reinterpret_cast<const float*>(epi_s) + eb * (128 * 129);
+      if (eb) asm volatile("bar.sync 3, 384;" ::: "memory"); else asm volatile("bar.sync 2, 384;" ::: "memory");
       const long long kg0 = t * kF1KG;
       const int cg0 = static_cast<int>(kg0 / a.THW);
       const int pos0 = static_cast<int>(kg0 - cg0 * a.THW);
@@ -392,8 +396,8 @@ __global__ void __launch_bounds__(MODE == 2 ? kF1ThreadsWgrad : kF1Threads, 1) f
           }
         }
       }
-      if (n + 2 < ntile) {  // the staging warps wait for this buffer again two tiles later
-        if (n & 1) asm volatile("bar.arrive 5, 384;" ::: "memory"); else asm volatile("bar.arrive 4, 384;" ::: "memory");
+      if (n + a.nepi < ntile) {  // the staging warps wait for this buffer again nepi tiles later
+        if (eb) asm volatile("bar.arrive 5, 384;" ::: "memory"); else asm volatile("bar.arrive 4, 384;" ::: "memory");
       }
     }
   } else {
@@ -489,9 +493,10 @@ __global__ void __launch_bounds__(MODE == 2 ? kF1ThreadsWgrad : kF1Threads, 1) f
           // accumulator row = feature j; columns = (kgl, c8).  Stage transposed as fp32 [(c8, kgl)][j] (row 129 floats:
           // conflict-free both ways) into the staging buffer seq % 2; the store warps write it out while this
           // warp group already stages the next tile.
-          float* es = reinterpret_cast<float*>(epi_s) + (seq & 1u) * (128 * 129);
-          if (seq >= 2) {
-            if (seq & 1u) asm volatile("bar.sync 5, 384;" ::: "memory"); else asm volatile("bar.sync 4, 384;" ::: "memory");
+          const uint32_t eb = (a.nepi == 2) ? (seq & 1u) : 0u;
+          float* es = reinterpret_cast<float*>(epi_s) + eb * (128 * 129);
+          if (seq >= static_cast<uint32_t>(a.nepi)) {
+            if (eb) asm volatile("bar.sync 5, 384;" ::: "memory"); else asm volatile("bar.sync 4, 384;" ::: "memory");
           }
 #pragma unroll
           for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kF1ThreadsWgrad : kF1Threads, 1) f
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(tempty + acc);
-          if (seq & 1u) asm volatile("bar.arrive 3, 384;" ::: "memory"); else asm volatile("bar.arrive 2, 384;" ::: "memory");
+          if (eb) asm volatile("bar.arrive 3, 384;" ::: "memory"); else asm volatile("bar.arrive 2, 384;" ::: "memory");
         }
       }
     }
@@ -531,13 +536,21 @@ static int fc1_bf16_fill(Fc1Bf16Args& a, int B, int F1, int Cg, int T, int H, in
 }
 
 template <int MODE>
-static int fc1_bf16_launch(const Fc1Bf16Args& a, long long grid, cudaStream_t st) {
+static int fc1_bf16_launch(Fc1Bf16Args a, long long grid, cudaStream_t st) {
   const size_t g_bytes = (MODE == 0) ? 0 : static_cast<size_t>(a.BP) * 256;
   const size_t w_bytes = (MODE == 2) ? 0 : static_cast<size_t>(kF1KG) * kF1J * 16;
   const size_t x_bytes = (MODE == 1) ? 0 : static_cast<size_t>(kF1KG) * a.BP * 16;
-  const size_t epi_bytes = (MODE == 1) ? static_cast<size_t>(a.BP) * 256 : (MODE == 2 ? static_cast<size_t>(2) * 128 * 129 * 4 : 0);
-  const size_t smem = 128 + round_up(g_bytes, static_cast<size_t>(128)) + 4 * (w_bytes + x_bytes) + epi_bytes;
-  PVB_REQUIRE(smem <= 227 * 1024, "fc1_bf16: batch %d needs %zu B of shared memory", a.B, smem);
+  const size_t epi1 = (MODE == 1) ? static_cast<size_t>(a.BP) * 256 : (MODE == 2 ? static_cast<size_t>(128) * 129 * 4 : 0);
+  const size_t fixed = 128 + round_up(g_bytes, static_cast<size_t>(128));
+  const size_t cap = 227 * 1024;
+  // as many pipeline stages (<= 4) and, for the weight gradient, epilogue staging buffers (<= 2) as fit
+  a.nepi = (MODE == 2 && fixed + 2 * epi1 + 3 * (w_bytes + x_bytes) <= cap) ? 2 : 1;
+  const size_t epi_bytes = a.nepi * epi1;
+  PVB_REQUIRE(fixed + epi_bytes + 2 * (w_bytes + x_bytes) <= cap,
+              "fc1_bf16: batch %d does not fit the tensor-core fc1 kernels' shared memory (use batches <= 128)", a.B);
+  size_t nst = (cap - fixed - epi_bytes) / (w_bytes + x_bytes);
+  a.nst = static_cast<int>(nst > 4 ? 4 : nst);
+  const size_t smem = fixed + a.nst * (w_bytes + x_bytes) + epi_bytes;
   PVB_CUDA(cudaFuncSetAttribute(fc1_bf16_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fc1_bf16_kernel<MODE><<<static_cast<unsigned>(grid), MODE == 2 ? kF1ThreadsWgrad : kF1Threads, smem, st>>>(a);
   PVB_LAUNCHED("fc1_bf16");

@@ -183,8 +183,10 @@ class Model(BaseModel):
         batch_size = sat_data.shape[0]
 
         # Conv3d + ReLU stack, flattened in NCDHW order (model.py:117-122)
-        # tensor-core fc1 needs B <= 256, fc1_output_features <= 128 and channels in whole (even) groups of 8
-        bf16_head = (self.precision == "bf16" and batch_size <= 256 and self.fc1_output_features <= 128
+        # tensor-core fc1 needs fc1_output_features <= 128, channels in whole (even) groups of 8 and a batch that fits
+        # its shared-memory tiles: 256 for the forward alone, 128 when the weight gradient will run too
+        max_b = 128 if torch.is_grad_enabled() else 256
+        bf16_head = (self.precision == "bf16" and batch_size <= max_b and self.fc1_output_features <= 128
                      and self.sat_conv0.out_channels % 16 == 0)
         link = {"shadow": self._fc1_shadow} if bf16_head else None
         if self.precision == "bf16":

@@ -172,6 +172,7 @@ FC1_CASES = [
     (5, 16, 3, 5, 6, 24),      # KG = 180: partial last tile; B padded 5 -> 16; F1 < 128
     (33, 32, 2, 4, 4, 128),    # B padded 33 -> 48
     (32, 32, 3, 8, 8, 128),
+    (128, 32, 2, 6, 6, 128),   # largest training batch of the tensor-core head (single epilogue buffer, fewer stages)
 ]
 
 
@@ -307,3 +308,56 @@ def test_adam_fc1_row_shards_equal_the_fused_update(dev, nshards):
     p.grad = grad * hyper[5]
     opt.step()
     assert O.normalised_max_err(wb, p.detach()) <= 1e-6
+
+
+def test_fc1_bf16_forward_batch_256_and_training_limit(ops, dev):
+    """Inference micro-batches of 256 fit the forward kernel (2 pipeline stages); the weight gradient refuses them loudly."""
+    from predict_pv_yield_b200 import lib
+
+    L = lib.load()
+    B, Cc, T, H, W, F1 = 256, 32, 2, 5, 5, 128
+    Cg, K1 = Cc // 8, Cc * T * H * W
+    g = torch.Generator().manual_seed(12)
+    act = F.relu(r16(torch.randn((B, Cc, T, H, W), generator=g)))
+    w1 = torch.randn((F1, K1), generator=g) / np.sqrt(K1)
+    stream = torch.cuda.current_stream().cuda_stream
+    actb = ops.to_blocked_bf16(act.to(dev))
+    shadow = torch.empty(L.pvb200_fc1_bf16_shadow_bytes(Cg, T, H, W), dtype=torch.uint8, device=dev)
+    lib.check(L.pvb200_fc1_make_shadow_bf16(w1.to(dev).data_ptr(), shadow.data_ptr(), F1, Cg, T, H, W, stream), "shadow")
+    partial = torch.empty((L.pvb200_fc1_fwd_bf16_splits(), B, F1), dtype=torch.float32, device=dev)
+    lib.check(L.pvb200_fc1_fwd_bf16(actb.data_ptr(), shadow.data_ptr(), partial.data_ptr(), B, F1, Cg, T, H, W, stream), "fwd")
+    want = act.reshape(B, K1).double() @ r16(w1).double().t()
+    assert O.normalised_max_err(partial.sum(0), want) <= 1e-5
+    dw = torch.empty((F1, K1), dtype=torch.float32, device=dev)
+    g1 = torch.randn((B, F1), generator=g).to(dev)
+    rc = L.pvb200_fc1_wgrad_bf16(g1.data_ptr(), actb.data_ptr(), dw.data_ptr(), B, F1, Cg, T, H, W, stream)
+    assert rc != 0 and b"batches <= 128" in L.pvb200_last_error()
+
+
+@pytest.mark.parametrize("B,grad", [(128, True), (130, True), (200, False)])
+def test_bf16_model_batch_limits_of_the_tensor_core_head(dev, B, grad):
+    """Batch 128 trains through the tensor-core head, 130 falls back to the fp32 head (bf16 convolutions), 200 is a
+    no_grad forward through the tensor-core head; all within the bf16 tolerance of the oracle."""
+    from predict_pv_yield_b200.models.conv3d.model import Model
+
+    kw = dict(include_pv_yield=False, include_nwp=False, forecast_minutes=30, history_minutes=30, number_of_conv3d_layers=2,
+              conv3d_channels=32, image_size_pixels=10, number_sat_channels=12)
+    torch.manual_seed(3)
+    m = Model(**kw, precision="bf16").to(dev)
+    m.batch_size = B
+    om = O.OracleModel(**kw)
+    om.batch_size = B
+    om.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    batch = O.make_synthetic_batch(B, seq_len=13, image_size_pixels=10, seed=5, include_legacy_keys=False)
+    if grad:
+        r = om.step_losses(batch)
+        r["nmae"].backward()
+        loss = m.training_step(O.batch_to(batch, dev), 0)
+        loss.backward()
+        assert abs(float(loss.detach()) - float(r["nmae"].detach())) <= BF16_TOL * abs(float(r["nmae"].detach()))
+        assert O.normalised_max_err(m.fc1.weight.grad, om.fc1.weight.grad) <= 5e-2
+        assert O.normalised_max_err(m.sat_conv0.weight.grad, om.sat_conv0.weight.grad) <= 5e-2
+    else:
+        with torch.no_grad():
+            y, want = m(O.batch_to(batch, dev)), om(batch)
+        assert O.normalised_max_err(y, want) <= BF16_TOL
