@@ -37,7 +37,7 @@ struct WgradArgs {
 // column, so consecutive steps share two of their three input planes.  Planes live in a 4-slot ring filled by
 // cp.async (LDGSTS, zero-fill for out-of-range positions) one step ahead of the FMA loop.
 template <bool kI16, int KTS>
-__global__ void __launch_bounds__(KTS == 1 ? 256 : 384, 1) conv3d_wgrad_f32_kernel(const WgradArgs a) {
+__global__ void __launch_bounds__(KTS == 1 ? 256 : 384, KTS == 1 ? 1 : 2) conv3d_wgrad_f32_kernel(const WgradArgs a) {
   constexpr int NKT = 3 / KTS;  // kt values handled by one thread
   extern __shared__ __align__(16) float smem[];
   float* x_s = smem;                                        // [4 slots][Ci][NPs]
@@ -305,11 +305,13 @@ int pvb200_conv3d_wgrad_f32_tpad(const void* x, int x_is_i16, const float* mean,
   const int threads = round_up(ceil_div(a.items, grid_y), 32);
   const int sms = sm_count();
   PVB_REQUIRE(sms > 0, "conv3d_wgrad: no CUDA device");
-  long long gx = sms;  // one persistent CTA per SM (register- and smem-limited to 1 CTA/SM)
-  if (gx > kWgMaxCtas) gx = kWgMaxCtas;
-  if (gx > a.total_steps) gx = a.total_steps;
   const size_t smem = (static_cast<size_t>(4) * Cin * a.NPs + 2 * 4 * a.ncog * kWgQC) * sizeof(float) +
                       (a.NP + kWgQC) * sizeof(int);
+  // persistent CTAs: one per SM for the wide layers (254 registers, ~120 KB of shared memory), two per SM for the
+  // narrow ones (kts == 3: 36 accumulators per thread), which doubles the warps that hide the shared-memory latency
+  long long gx = (kts == 3 && 2 * smem <= 220 * 1024) ? 2LL * sms : sms;
+  if (gx > kWgMaxCtas) gx = kWgMaxCtas;
+  if (gx > a.total_steps) gx = a.total_steps;
   PVB_REQUIRE(smem <= 227 * 1024, "conv3d_wgrad: Cin=%d, width %d needs %zu B of shared memory (> 227 KB)", Cin, Wi, smem);
   cudaStream_t st = as_stream(stream);
   int rc;
