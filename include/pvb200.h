@@ -44,6 +44,10 @@ const char* pvb200_last_error(void);
 unsigned long long pvb200_launch_count(void);
 void pvb200_reset_launch_count(void);
 /* SM count of the current device (grid sizing), or <0 on error */
+/* Under data parallelism NCCL's kernels occupy some SMs while the convolution backward runs; persistent kernels with
+ * one CTA per SM then wait for the displaced CTAs.  pvb200_reserve_sms(n) makes every persistent kernel launched
+ * afterwards size its grid for (SM count - n) SMs (n = 0: default).  Returns the previous value. */
+int pvb200_reserve_sms(int n);
 int pvb200_sm_count(void);
 /* diagnostic: launch an FP32 FMA saturation kernel; *flops_out = FLOPs it performs.  bench.py times it
  * with CUDA events to get the FP32-FMA roofline denominator (not in MEASURED_PEAKS.json). */

@@ -18,14 +18,23 @@ void set_error(const char* fmt, ...) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static std::atomic<int> g_reserved_sms{0};
+
+// SMs the persistent kernels size their grids for: the device's SM count minus the SMs reserved for concurrently
+// running collectives (pvb200_reserve_sms).  A persistent grid of one CTA per SM with a static work split loses up to
+// half its speed when a communication kernel already occupies some SMs: the displaced CTAs only start when another
+// CTA of the same grid has finished.  Sizing the grid for the SMs that are actually free keeps the split balanced.
 int sm_count() {
   static int cached = -1;
-  if (cached > 0) return cached;
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-  cached = n;
-  return n;
+  if (cached <= 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    cached = n;
+  }
+  const int r = g_reserved_sms.load(std::memory_order_relaxed);
+  const int n = cached - r;
+  return n < 8 ? (cached < 8 ? cached : 8) : n;
 }
 
 }  // namespace pvb
@@ -39,6 +48,10 @@ const char* pvb200_last_error(void) { return pvb::g_err; }
 unsigned long long pvb200_launch_count(void) { return pvb::g_launches.load(); }
 
 void pvb200_reset_launch_count(void) { pvb::g_launches.store(0); }
+
+/* reserve `n` SMs for kernels of other libraries that run concurrently (NCCL collectives under data parallelism):
+ * every persistent kernel launched afterwards uses (SM count - n) CTAs.  n = 0 restores the default.  Returns the old value. */
+int pvb200_reserve_sms(int n) { return pvb::g_reserved_sms.exchange(n < 0 ? 0 : n); }
 
 int pvb200_sm_count(void) {
   int n = pvb::sm_count();
