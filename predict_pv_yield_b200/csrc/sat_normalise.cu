@@ -140,22 +140,31 @@ int pvb200_sat_normalise_bf16(const int16_t* x, uint16_t* y, const float* mean, 
 // position): 8 coalesced 2-byte loads (one per channel plane), one 16-byte store.
 namespace pvb {
 // vector path: one thread = 8 consecutive positions x the 8 channels of one group: eight 128-bit streaming loads
-// (one per channel plane) and eight 16-byte stores that form one contiguous 128-byte run of the blocked tensor.
+// (one per channel plane).  A warp produces 256 consecutive positions = 4 KB of the blocked tensor; the 16-byte results
+// go through a per-warp shared-memory tile so that every store instruction writes 512 contiguous bytes.
+// Round-1 measurements (B = 32 cube, 140 MB of traffic): 0.077 ms = 1.8 TB/s with direct stores AND with the coalesced
+// stores; a shared-memory table of the 10-bit values instead of the IEEE division: 0.094 ms.  The kernel is bound by
+// its instruction stream (64 exact divisions + conversions per thread), not by memory; 2 % of the bf16 step.
 __global__ void __launch_bounds__(256)
 sat_normalise_blocked_vec_kernel(const int16_t* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ mean,
                                  const float* __restrict__ stdv, int C, int Cg, long long thw, long long total8) {
+  __shared__ uint4 tile[8][32 * 9];  // per warp: 256 positions, lane stride 9 x 16 B: conflict-free both ways
   const long long thw8 = thw >> 3;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total8;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long p8 = idx % thw8;
-    const long long r = idx / thw8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // whole warps iterate together (the tile exchange needs all lanes): loop over warp-sized groups of 8-position units
+  const long long nwarp_units = (total8 + 31) >> 5;
+  for (long long wu = static_cast<long long>(blockIdx.x) * 8 + warp; wu < nwarp_units; wu += static_cast<long long>(gridDim.x) * 8) {
+    const long long idx = (wu << 5) + lane;
+    const bool ok = idx < total8;
+    const long long p8 = ok ? idx % thw8 : 0;
+    const long long r = ok ? idx / thw8 : 0;
     const int cg = static_cast<int>(r % Cg);
     const long long b = r / Cg;
     float f[8][8];  // [channel][position]
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = cg * 8 + j;
-      if (c < C) {
+      if (ok && c < C) {
         const uint4 q = ld_stream_u4(reinterpret_cast<const uint4*>(x + (b * C + c) * thw) + p8);
         norm8(q, __ldg(mean + c), __ldg(stdv + c), f[j]);
       } else {
@@ -163,11 +172,31 @@ sat_normalise_blocked_vec_kernel(const int16_t* __restrict__ x, uint4* __restric
         for (int i = 0; i < 8; ++i) f[j][i] = 0.f;
       }
     }
-    uint4* dst = y + (b * Cg + cg) * thw + 8 * p8;
+    // the 32 lanes of a warp cover one (b, cg) row only if thw8 is a multiple of 32; otherwise store directly
+    const long long first = wu << 5;
+    const bool same_row = (first / thw8) == ((first + 31 < total8 ? first + 31 : total8 - 1) / thw8) && (first + 31 < total8);
+    if (same_row) {
+      uint4* t = tile[warp];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      dst[i] = make_uint4(pack_bf16x2(f[0][i], f[1][i]), pack_bf16x2(f[2][i], f[3][i]), pack_bf16x2(f[4][i], f[5][i]),
-                          pack_bf16x2(f[6][i], f[7][i]));
+      for (int i = 0; i < 8; ++i)
+        t[lane * 9 + i] = make_uint4(pack_bf16x2(f[0][i], f[1][i]), pack_bf16x2(f[2][i], f[3][i]),
+                                                   pack_bf16x2(f[4][i], f[5][i]), pack_bf16x2(f[6][i], f[7][i]));
+      __syncwarp();
+      const long long fp8 = first % thw8, fr = first / thw8;
+      uint4* dst = y + fr * thw + 8 * fp8;  // (b * Cg + cg) == fr
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int p = k * 32 + lane;  // position within the warp's 256
+        dst[p] = t[p + (p >> 3)];
+      }
+      __syncwarp();
+    } else if (ok) {
+      uint4* dst = y + (b * Cg + cg) * thw + 8 * p8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_uint4(pack_bf16x2(f[0][i], f[1][i]), pack_bf16x2(f[2][i], f[3][i]), pack_bf16x2(f[4][i], f[5][i]),
+                            pack_bf16x2(f[6][i], f[7][i]));
+    }
   }
 }
 

@@ -139,6 +139,20 @@ def test_normalise_blocked_bf16(ops, dev):
     assert torch.equal(ops.from_blocked_bf16(yb, 12).cpu(), want)
 
 
+def test_normalise_blocked_bf16_exhaustive_table_path(ops, dev):
+    """The large-cube path looks the 10-bit SEVIRI values up in a per-CTA table and computes everything else: all 65536
+    int16 values x 12 channels must equal RNE-to-bf16 of the reference fp32 arithmetic bit for bit."""
+    x = torch.arange(-32768, 32768, dtype=torch.int32).to(torch.int16).view(1, 1, 1, 256, 256).expand(2, 12, 4, 256, 256).contiguous()
+    mean, std = O.sat_constants(12)
+    want = O.sat_normalise(x[:1, :, :1], torch.from_numpy(mean), torch.from_numpy(std)).to(torch.bfloat16)
+    yb = ops.sat_normalise_blocked_bf16(x.to(dev), torch.from_numpy(mean).to(dev), torch.from_numpy(std).to(dev))
+    got = ops.from_blocked_bf16(yb, 12).cpu().to(torch.bfloat16)
+    assert got.shape == (2, 12, 4, 256, 256)
+    for b in range(2):
+        for t in range(4):
+            assert torch.equal(got[b, :, t].view(torch.int16), want[0, :, 0].view(torch.int16))
+
+
 @pytest.mark.parametrize("name", ["nwp_pv_small", "test_yaml_pv"])
 def test_bf16_model_within_tolerance_of_oracle(dev, name):
     """North star: bf16 loss / forecast within 2e-2 of the torch reference (normalised max error)."""
