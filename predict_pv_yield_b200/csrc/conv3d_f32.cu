@@ -49,6 +49,7 @@ struct ConvArgs {
   int CoPad;
   int relu;
   int pairs;  // Wi even (and the tensor 8-byte aligned): stage two positions per copy (a pair never straddles a row)
+  int contig; // P == 0 and Wi a multiple of 4: the staged run IS a contiguous run of the input plane (16-byte copies)
 };
 
 // dw layout transform: wt[ci_role][tap][co_role] = w[co_role*s_co + ci_role*s_ci + (flip ? 26-tap : tap)]
@@ -123,6 +124,16 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
         for (int i = lane; i < a.NP; i += 32) {
           const int o = off_s[i];
           dst[i] = (plane_ok && o >= 0) ? sat_norm(__ldg(src + o), m, s) : 0.f;
+        }
+      } else if (a.contig) {
+        // Wps == Wi and no padding: staged position i is element q0 + i of the plane; 16-byte copies, zero fill past the end
+        const float* src = static_cast<const float*>(a.x) + base + q0;
+        const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+        const int left = static_cast<int>(plane_sz) - q0;  // elements of the plane from q0 on (multiple of 4)
+        for (int i = 4 * lane; i < a.NP; i += 128) {
+          const bool ok = plane_ok && (i < left);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? i : 0)), "r"(ok ? 16 : 0)
+                       : "memory");
         }
       } else if (a.pairs) {
         // positions 2i, 2i+1 of the staged run are neighbours in the same input row (Wps, q0, P and Wi are even):
@@ -271,6 +282,8 @@ static int launch_conv(const void* x, bool i16, const float* mean, const float* 
   a.CoPad = a.co_tiles * kCoT;
   a.relu = relu;
   a.pairs = (!i16 && (Wi % 2 == 0) && (P % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 8 == 0)) ? 1 : 0;
+  a.contig = (!i16 && P == 0 && (Wi % 4 == 0) && (static_cast<long long>(Hi) * Wi % 4 == 0) &&
+              (reinterpret_cast<uintptr_t>(x) % 16 == 0)) ? 1 : 0;
   const size_t need = conv_ws_bytes(Ci, Co);
   if (ws == nullptr || ws_bytes < need) {
     set_error("conv3d: workspace too small (%zu < %zu bytes)", ws_bytes, need);
