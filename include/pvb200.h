@@ -260,6 +260,14 @@ int pvb200_l1_loss_bwd_f32(const float* y_hat, const float* y, long long y_sb, l
                            const float* gscale /* device scalar: upstream grad */, float* g,
                            int B, int FO, pvb200_stream_t stream);
 
+/* ---- validation results on the device (base_model.py:121-136,222-236) ----------------------
+ * out [3][B][FO] = {forecast MW = y_hat * capacity, actual MW = y * capacity, capacity}; horizon [2][FO] = per-horizon
+ * {mean (y_hat - y)^2, mean |y_hat - y|}.  y / capacity are strided views ([:, -FO:, 0]); capacity may be NULL (= 1).
+ * One kernel and one device->host copy replace the reference's four .cpu().numpy() round trips per batch. */
+int pvb200_validation_results_f32(const float* y_hat, const float* y, long long y_sb, long long y_sf,
+                                  const float* capacity, long long c_sb, long long c_sf, float* out, float* horizon,
+                                  int B, int FO, pvb200_stream_t stream);
+
 /* ---- a12: Adam -------------------------------------------------------------------------------
  * replaces torch.optim.Adam(self.parameters(), lr=0.0005).step(), base_model.py:255-257 (single-tensor
  * arithmetic of torch.optim.adam: lerp / addcmul / sqrt / addcdiv, bias-corrected, no weight decay).

@@ -127,6 +127,39 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamTensors t, co
   }
 }
 
+
+// ---- validation results (base_model.py:222-236): capacity-scaled MW values and per-horizon errors in one pass ----------
+// out[0][b][f] = forecast MW = y_hat * capacity, out[1][b][f] = actual MW = y * capacity, out[2][b][f] = capacity;
+// horizon[0][f] = mean_b (y_hat - y)^2, horizon[1][f] = mean_b |y_hat - y|  (the per-horizon metrics of base_model.py:121-136)
+__global__ void validation_results_kernel(const float* __restrict__ y_hat, const float* __restrict__ y, long long y_sb, long long y_sf,
+                                          const float* __restrict__ cap, long long c_sb, long long c_sf, float* __restrict__ out,
+                                          float* __restrict__ horizon, int B, int FO) {
+  const int f = blockIdx.x;
+  float s_sq = 0.f, s_abs = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float p = y_hat[b * FO + f], t = y[b * y_sb + f * y_sf];
+    const float c = cap ? cap[b * c_sb + f * c_sf] : 1.f;
+    const long long o = static_cast<long long>(b) * FO + f, n = static_cast<long long>(B) * FO;
+    out[o] = p * c;
+    out[n + o] = t * c;
+    out[2 * n + o] = c;
+    const float d = p - t;
+    s_sq = fmaf(d, d, s_sq);
+    s_abs += fabsf(d);
+  }
+  __shared__ float red[2][32];
+  s_sq = warp_sum(s_sq); s_abs = warp_sum(s_abs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = s_sq; red[1][warp] = s_abs; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    float a = lane < nw ? red[0][lane] : 0.f, c = lane < nw ? red[1][lane] : 0.f;
+    a = warp_sum(a); c = warp_sum(c);
+    if (lane == 0) { horizon[f] = a / B; horizon[FO + f] = c / B; }
+  }
+}
+
 }  // namespace pvb
 
 extern "C" {
@@ -190,6 +223,17 @@ int pvb200_adam_step_f32(int n, float* const* params, const float* const* grads,
     adam_multi_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(t, s, chunks);
     PVB_LAUNCHED("adam_multi");
   }
+  return PVB200_OK;
+}
+
+
+int pvb200_validation_results_f32(const float* y_hat, const float* y, long long y_sb, long long y_sf, const float* capacity,
+                                  long long c_sb, long long c_sf, float* out, float* horizon, int B, int FO,
+                                  pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(y_hat && y && out && horizon && B > 0 && FO > 0, "validation_results: bad argument");
+  validation_results_kernel<<<FO, 256, 0, as_stream(stream)>>>(y_hat, y, y_sb, y_sf, capacity, c_sb, c_sf, out, horizon, B, FO);
+  PVB_LAUNCHED("validation_results");
   return PVB200_OK;
 }
 

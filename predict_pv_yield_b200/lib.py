@@ -105,6 +105,8 @@ SIGNATURES = {
     "pvb200_fc1_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_l1_loss_fwd_f32": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pvb200_l1_loss_bwd_f32": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "pvb200_validation_results_f32": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_int,
+                                              c_int, c_void_p]),
     "pvb200_adam_step_f32": (c_int, [c_int, C.POINTER(c_void_p), C.POINTER(c_void_p), C.POINTER(c_void_p),
                                      C.POINTER(c_void_p), C.POINTER(c_ll), c_float, c_float, c_float, c_float, c_int,
                                      c_float, c_void_p]),

@@ -9,7 +9,8 @@ the reference's key collision at ``:126-136``, kept for log compatibility) and `
 
 Works with or without ``pytorch_lightning`` installed (the reference targets Lightning 1.4-1.5, which
 is not in this image): when it is importable the class derives from ``pl.LightningModule``.
-Out of scope: the plotting / pandas CSV tail of ``validation_step`` (``:165-241``).
+The capacity-scaled validation table of ``validation_step`` (``:222-250``) is produced on the device in one kernel
+(``predict_pv_yield_b200/validation.py``); only the plotting (``:165-220``) is out of scope.
 """
 from __future__ import annotations
 
@@ -120,12 +121,13 @@ class BaseModel(_Base):
         )
 
         if tag != "Train":
-            # metrics for each forecast horizon (nowcasting_utils.models.metrics: mean over the batch axis);
-            # logging-only, tiny [B, forecast_len] tensors
+            # metrics for each forecast horizon (nowcasting_utils.models.metrics: mean over the batch axis) and the
+            # capacity-scaled validation results, in one kernel
+            cap = self._gsp_capacity_view(batch, y_hat)
             with torch.no_grad():
-                d = y_hat.detach() - y
-                mse_h = (d * d).mean(dim=0)
-                mae_h = d.abs().mean(dim=0)
+                out, horizon = ops.validation_results(y_hat.detach(), y, cap)
+            self._last_validation = (out, cap is not None)
+            mse_h, mae_h = horizon[0], horizon[1]
             metrics_mse = {f"MSE_forecast_horizon_{i}/{tag}": mse_h[i] for i in range(self.forecast_len_30)}
             # NOTE: the reference logs the MAE under the MSE key as well (base_model.py:131-134), so the MAE
             # values overwrite the MSE ones; reproduced so dashboards keyed on these names see the same numbers
@@ -140,12 +142,42 @@ class BaseModel(_Base):
     def training_step(self, batch, batch_idx):
         return self._training_or_validation_step(batch, tag="Train")
 
+    def _gsp_capacity_view(self, batch, y_hat):
+        """``batch.gsp.gsp_capacity[:, -forecast_len_30:, 0]`` (base_model.py:223) when the batch carries it and the
+        model forecasts GSP yield at 30-minute steps (the only case in which the reference's scaling is shape-correct)."""
+        gsp = getattr(batch, "gsp", None)
+        cap = getattr(gsp, "gsp_capacity", None)
+        if cap is None or self.output_variable != "gsp_yield":
+            return None
+        if not torch.is_tensor(cap) or cap.dim() != 3 or cap.shape[0] < y_hat.shape[0] or cap.shape[1] < y_hat.shape[1]:
+            return None
+        cap = cap[0: y_hat.shape[0], -y_hat.shape[1]:, 0]
+        return cap if cap.dtype == torch.float32 else cap.float()
+
     def validation_step(self, batch, batch_idx):
+        batch = as_batch(batch)
         nmae_loss, _ = self._training_or_validation_step(batch, tag="Validation", return_model_outputs=True)
+        # save validation results (base_model.py:222-241): capacity-scaled MW table, one device -> host copy per batch
+        out, has_capacity = self._last_validation
+        gsp, meta = getattr(batch, "gsp", None), getattr(batch, "metadata", None)
+        if has_capacity and getattr(gsp, "gsp_id", None) is not None and getattr(meta, "t0_datetime_utc", None) is not None:
+            from ..validation import make_validation_results
+
+            host = out.cpu().numpy()  # [3, B, forecast_len_30]
+            t0 = meta.t0_datetime_utc
+            t0 = t0.cpu().numpy() if torch.is_tensor(t0) else t0
+            results = make_validation_results(truths_mw=host[1], predictions_mw=host[0], capacity_mwp=host[2],
+                                              gsp_ids=gsp.gsp_id[0: host.shape[1], 0], batch_idx=batch_idx, t0_datetimes_utc=t0)
+            if batch_idx == 0:
+                self.results_dfs = []
+            self.results_dfs.append(results)
         return nmae_loss
 
     def validation_epoch_end(self, outputs):
         logger.info("Validation epoch end")
+        from ..validation import save_validation_results
+
+        save_validation_results(self.results_dfs, self.results_file_name, self.current_epoch)
 
     def test_step(self, batch, batch_idx):
         self._training_or_validation_step(batch, tag="Test")

@@ -875,6 +875,25 @@ def history_flatten(src: torch.Tensor, nt: int, ns: int) -> torch.Tensor:
     return out
 
 
+def validation_results(y_hat: torch.Tensor, y: torch.Tensor, capacity: Optional[torch.Tensor]):
+    """(out [3,B,FO] = forecast MW, actual MW, capacity; horizon [2,FO] = per-horizon MSE, MAE) in one kernel.
+    ``y`` / ``capacity`` are the strided views ``[:, -FO:, 0]`` of the batch tensors (base_model.py:95,222-227)."""
+    L = _lib.load()
+    _need_cuda(y_hat, "y_hat", torch.float32)
+    B, FO = y_hat.shape
+    for t, nm in ((y, "y"), (capacity, "capacity")):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != (B, FO)):
+            raise RuntimeError(f"validation_results: '{nm}' must be a float32 CUDA view of shape {(B, FO)}")
+    out = torch.empty((3, B, FO), dtype=torch.float32, device=y_hat.device)
+    horizon = torch.empty((2, FO), dtype=torch.float32, device=y_hat.device)
+    rc = L.pvb200_validation_results_f32(_p(y_hat), y.data_ptr(), y.stride(0), y.stride(1),
+                                         capacity.data_ptr() if capacity is not None else None,
+                                         capacity.stride(0) if capacity is not None else 0,
+                                         capacity.stride(1) if capacity is not None else 0, _p(out), _p(horizon), B, FO, _stream())
+    _lib.check(rc, "validation_results")
+    return out, horizon
+
+
 class StepLossFn(torch.autograd.Function):
     """forward(y_hat [B,FO], y [B,FO] strided view, weights [FO]) -> losses [4] = nmae, mse, mse_exp, mae_exp.
 
