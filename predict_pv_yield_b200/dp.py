@@ -191,9 +191,18 @@ class GradientExchange:
             optimizer.register_step_pre_hook(_hook)
 
     def remove(self) -> None:
+        """Detach from the module: gradient hooks, the state_dict pre-hook and the shard marks (gathers the master rows first)."""
+        if self._sharded:
+            self.gather_master_weights()
+            for p in self._sharded:
+                p._pvb_shard = None
+            self._sharded = []
         for h in self._handles:
             h.remove()
         self._handles = []
+        if getattr(self, "_sd_hook", None) is not None:
+            self._sd_hook.remove()
+            self._sd_hook = None
 
 
 def reduce_logged_scalars(values: Dict[str, torch.Tensor], process_group=None) -> Dict[str, torch.Tensor]:
