@@ -146,6 +146,28 @@ int pvb200_conv3d_wgrad_f32_tpad(const void* x, int x_is_i16, const float* mean,
                                  const float* gz, float* dw, float* db, void* workspace, size_t workspace_bytes,
                                  int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t, pvb200_stream_t stream);
 
+/* ---- general padding (pad_t, pad_hw, pad_hw), each 0 or 1, and MaxPool3d: the Conv3dMaxPool front-end of the Perceiver
+ * hybrid (nn.Conv3d(..., padding=(1, 1, 1)) + nn.MaxPool3d(3, stride=(1, 2, 2), padding=(1, 1, 1)),
+ * predict_pv_yield/models/perceiver/perceiver_conv3d_nwp_sat.py:42-57).  Ti/Hi/Wi are the INPUT extents. */
+int pvb200_conv3d_fwd_f32_pad(const void* x, int x_is_i16, const float* mean, const float* std, const float* w,
+                              const float* bias, float* y, void* workspace, size_t workspace_bytes,
+                              int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int pad_t, int pad_hw,
+                              pvb200_stream_t stream);
+int pvb200_conv3d_dgrad_f32_pad(const float* gz, const float* w, const float* mask_src, float* gx,
+                                void* workspace, size_t workspace_bytes,
+                                int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t, int pad_hw,
+                                pvb200_stream_t stream);
+int pvb200_conv3d_wgrad_f32_pad(const void* x, int x_is_i16, const float* mean, const float* std,
+                                const float* gz, float* dw, float* db, void* workspace, size_t workspace_bytes,
+                                int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t, int pad_hw,
+                                pvb200_stream_t stream);
+/* MaxPool3d(kernel 3, stride (1, 2, 2), padding (1, 1, 1)) over [N = B*C planes][T][H][W] -> [N][T][Ho][Wo],
+ * Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1.  fwd also writes the arg-max (flat index t*H*W + h*W + w inside the plane,
+ * first maximum in (t, h, w) scan order like torch); bwd routes each gz to its arg-max, deterministically (gather). */
+int pvb200_maxpool3d_fwd_f32(const float* x, float* y, int* argmax, long long N, int T, int H, int W, pvb200_stream_t stream);
+int pvb200_maxpool3d_bwd_f32(const float* gz, const int* argmax, float* gx, long long N, int T, int H, int W,
+                             pvb200_stream_t stream);
+
 /* ---- a6-a9: the fully connected head --------------------------------------------------------
  * replaces model.py:122-154 (reshape, fc1, fc2, PV-history cat, fc_nwp, NWP cat, fc3, fc4) and its
  * autograd.  All matrices fp32, torch Linear layout [out][in]. */

@@ -92,6 +92,23 @@ def sat_nwp_batch(name: str, seed: int = 519) -> dict:
     return b
 
 
+# ---- Conv3dMaxPool (perceiver_conv3d_nwp_sat.py:42-57) -------------------------------------------
+MAXPOOL_CASES = {
+    # name -> (B, in_channels, T, H, W, out_channels); odd and even extents (the pool's last window is partial for even ones)
+    "conv3d_maxpool_sat": (2, 11, 5, 12, 12, 16),
+    "conv3d_maxpool_odd": (1, 10, 3, 9, 7, 8),
+}
+
+
+def maxpool_inputs(name: str, seed: int = 520):
+    """(x fp32 [B,Ci,T,H,W], upstream gradient g for the output) from numpy RandomState."""
+    B, Ci, T, H, W, Co = MAXPOOL_CASES[name]
+    rs = np.random.RandomState(seed)
+    x = rs.randn(B, Ci, T, H, W).astype(np.float32)
+    g = rs.randn(B, Co, T, (H - 1) // 2 + 1, (W - 1) // 2 + 1).astype(np.float32)
+    return torch.from_numpy(x), torch.from_numpy(g)
+
+
 SUBSAMPLE = 97  # stride used to thin out large tensors (fc1.weight and its grad) in the fixtures
 
 

@@ -30,7 +30,8 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 from oracle import ref_shims  # noqa: E402
 from oracle.conv3d_oracle import sat_constants, sat_normalise_numpy  # noqa: E402
-from oracle.golden_cases import CASES, SAT_NWP_CASES, golden_batch, golden_state_dict, sat_nwp_batch, thin  # noqa: E402
+from oracle.golden_cases import (CASES, MAXPOOL_CASES, SAT_NWP_CASES, golden_batch, golden_state_dict,  # noqa: E402
+                                 maxpool_inputs, sat_nwp_batch, thin)
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
@@ -72,6 +73,20 @@ def run_case(name: str) -> dict:
     return out
 
 
+def run_maxpool_case(name: str) -> dict:
+    """The unmodified reference Conv3dMaxPool (perceiver_conv3d_nwp_sat.py:42-57): output, input / weight / bias gradients."""
+    Block = ref_shims.import_reference_conv3d_maxpool()
+    B, Ci, T, H, W, Co = MAXPOOL_CASES[name]
+    m = Block(out_channels=Co, in_channels=Ci)
+    m.load_state_dict(golden_state_dict(m))
+    x, g = maxpool_inputs(name)
+    x.requires_grad_(True)
+    y = m(x)
+    y.backward(g)
+    return {"y": y.detach().numpy().copy(), "gx": x.grad.numpy().copy(), "dw": m.sat_conv3d.weight.grad.numpy().copy(),
+            "db": m.sat_conv3d.bias.grad.numpy().copy()}
+
+
 def normalise_digest() -> str:
     """sha256 over the fp32 bits of the normalisation of ALL 65536 int16 values x 12 channels."""
     x = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16)
@@ -87,6 +102,10 @@ def main():
         res = run_case(name)
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **res)
         print(name, "y_hat", res["y_hat"].shape, "loss", float(res["loss"]))
+    for name in MAXPOOL_CASES:
+        res = run_maxpool_case(name)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **res)
+        print(name, "y", res["y"].shape)
     with open(os.path.join(OUT, "normalise_sha256.txt"), "w") as f:
         f.write(normalise_digest() + "\n")
     print("normalise digest written")

@@ -137,3 +137,18 @@ def import_reference_sat_nwp_model():
     from predict_pv_yield.models.conv3d.model_sat_nwp import Model  # noqa: E402  (the real reference file)
 
     return Model
+
+
+def import_reference_conv3d_maxpool():
+    """Return the reference ``Conv3dMaxPool`` class (``predict_pv_yield/models/perceiver/perceiver_conv3d_nwp_sat.py:42``),
+    unmodified.  Its module also imports ``perceiver_pytorch`` and ``nowcasting_dataset.consts`` (absent here): stand-ins."""
+    install()
+    if "perceiver_pytorch" not in sys.modules:
+        _mod("perceiver_pytorch", Perceiver=type("Perceiver", (torch.nn.Module,), {}))
+    if "nowcasting_dataset.consts" not in sys.modules:
+        _mod("nowcasting_dataset.consts", NWP_VARIABLE_NAMES=tuple("abcdefghijklmnop"), SAT_VARIABLE_NAMES=tuple("abcdefghijkl"))
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from predict_pv_yield.models.perceiver.perceiver_conv3d_nwp_sat import Conv3dMaxPool  # noqa: E402
+
+    return Conv3dMaxPool

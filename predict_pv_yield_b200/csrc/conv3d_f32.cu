@@ -321,16 +321,23 @@ size_t pvb200_conv3d_workspace_bytes(int Cin, int Cout) {
   return f > d ? f : d;
 }
 
+int pvb200_conv3d_fwd_f32_pad(const void* x, int x_is_i16, const float* mean, const float* std, const float* w,
+                              const float* bias, float* y, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
+                              int Hi, int Wi, int Cout, int relu, int pad_t, int pad_hw, pvb200_stream_t stream) {
+  PVB_REQUIRE(x && w && y, "conv3d_fwd: null pointer");
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0, "conv3d_fwd: bad shape");
+  PVB_REQUIRE((pad_t == 0 || pad_t == 1) && (pad_hw == 0 || pad_hw == 1), "conv3d_fwd: padding (%d, %d) not in {0, 1}", pad_t, pad_hw);
+  PVB_REQUIRE(!x_is_i16 || (mean && std), "conv3d_fwd: int16 input needs mean/std");
+  return pvb::launch_conv(x, x_is_i16 != 0, mean, std, w, /*s_co=*/static_cast<long long>(Cin) * 27, /*s_ci=*/27,
+                          /*flip=*/0, bias, nullptr, y, B, Cin, Ti, Hi, Wi, Cout, /*P=*/pad_hw, /*Pt=*/pad_t, relu, workspace,
+                          workspace_bytes, pvb::as_stream(stream));
+}
+
 int pvb200_conv3d_fwd_f32_tpad(const void* x, int x_is_i16, const float* mean, const float* std, const float* w,
                                const float* bias, float* y, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
                                int Hi, int Wi, int Cout, int relu, int pad_t, pvb200_stream_t stream) {
-  PVB_REQUIRE(x && w && y, "conv3d_fwd: null pointer");
-  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0, "conv3d_fwd: bad shape");
-  PVB_REQUIRE(pad_t == 0 || pad_t == 1, "conv3d_fwd: time padding %d not in {0, 1}", pad_t);
-  PVB_REQUIRE(!x_is_i16 || (mean && std), "conv3d_fwd: int16 input needs mean/std");
-  return pvb::launch_conv(x, x_is_i16 != 0, mean, std, w, /*s_co=*/static_cast<long long>(Cin) * 27, /*s_ci=*/27,
-                          /*flip=*/0, bias, nullptr, y, B, Cin, Ti, Hi, Wi, Cout, /*P=*/0, /*Pt=*/pad_t, relu, workspace,
-                          workspace_bytes, pvb::as_stream(stream));
+  return pvb200_conv3d_fwd_f32_pad(x, x_is_i16, mean, std, w, bias, y, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout, relu,
+                                   pad_t, 0, stream);
 }
 
 int pvb200_conv3d_fwd_f32(const void* x, int x_is_i16, const float* mean, const float* std, const float* w,
@@ -349,14 +356,21 @@ int pvb200_conv3d_dgrad_f32(const float* gz, const float* w, const float* mask_s
 int pvb200_conv3d_dgrad_f32_tpad(const float* gz, const float* w, const float* mask_src, float* gx, void* workspace,
                                  size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
                                  pvb200_stream_t stream) {
+  return pvb200_conv3d_dgrad_f32_pad(gz, w, mask_src, gx, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout, pad_t, 0, stream);
+}
+
+int pvb200_conv3d_dgrad_f32_pad(const float* gz, const float* w, const float* mask_src, float* gx, void* workspace,
+                                size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t, int pad_hw,
+                                pvb200_stream_t stream) {
   PVB_REQUIRE(gz && w && gx, "conv3d_dgrad: null pointer");
-  PVB_REQUIRE(pad_t == 0 || pad_t == 1, "conv3d_dgrad: time padding %d not in {0, 1}", pad_t);
-  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti + 2 * pad_t > 2 && Hi > 2 && Wi > 2, "conv3d_dgrad: bad shape");
+  PVB_REQUIRE((pad_t == 0 || pad_t == 1) && (pad_hw == 0 || pad_hw == 1), "conv3d_dgrad: padding (%d, %d) not in {0, 1}", pad_t, pad_hw);
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti + 2 * pad_t > 2 && Hi + 2 * pad_hw > 2 && Wi + 2 * pad_hw > 2, "conv3d_dgrad: bad shape");
   // roles: the kernel's "input" is gz [B,Cout,Ti-2,Hi-2,Wi-2] padded by 2, its "output" is gx [B,Cin,Ti,Hi,Wi];
   // real weight w[co][ci][tap] is read as w[in-role=co][out-role=ci][26-tap]
   return pvb::launch_conv(gz, false, nullptr, nullptr, w, /*s_co (out-role=ci)=*/27,
                           /*s_ci (in-role=co)=*/static_cast<long long>(Cin) * 27, /*flip=*/1, nullptr, mask_src, gx, B,
-                          /*Ci role=*/Cout, Ti + 2 * pad_t - 2, Hi - 2, Wi - 2, /*Co role=*/Cin, /*P=*/2, /*Pt=*/2 - pad_t,
+                          /*Ci role=*/Cout, Ti + 2 * pad_t - 2, Hi + 2 * pad_hw - 2, Wi + 2 * pad_hw - 2, /*Co role=*/Cin,
+                          /*P=*/2 - pad_hw, /*Pt=*/2 - pad_t,
                           /*relu=*/0, workspace, workspace_bytes, pvb::as_stream(stream));
 }
 

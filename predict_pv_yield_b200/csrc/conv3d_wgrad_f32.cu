@@ -31,6 +31,7 @@ struct WgradArgs {
   int items;          // ncog * Ci * KTS
   int pairs;          // Wi even and 8-byte aligned tensors: stage two positions per copy (never straddles a row)
   int pad_t;          // time padding of the layer (0 or 1): input plane to + kt - pad_t, zero outside [0, Ti)
+  int pad_hw;         // spatial padding (0 or 1): staged position (hp, wp) is input (hp - pad_hw, wp - pad_hw), zero outside
 };
 
 // Work is ordered (b, tile, to) with `to` fastest: a CTA walks DOWN the time axis of one (sample, position tile)
@@ -147,7 +148,8 @@ __global__ void __launch_bounds__(KTS == 1 ? 256 : 384, KTS == 1 ? 1 : 2) conv3d
     for (int i = tid; i < a.NP; i += blockDim.x) {
       const int pos = q0 + i;
       const int hp = pos / a.Wps, wp = pos - hp * a.Wps;
-      off_s[i] = (hp < a.Hi && wp < a.Wi) ? hp * a.Wi + wp : -1;
+      const int hi = hp - a.pad_hw, wi = wp - a.pad_hw;
+      off_s[i] = (hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi) ? hi * a.Wi + wi : -1;
     }
     for (int i = tid; i < kWgQC; i += blockDim.x) {
       const int pos = q0 + i;
@@ -273,10 +275,17 @@ int pvb200_conv3d_wgrad_f32(const void* x, int x_is_i16, const float* mean, cons
 int pvb200_conv3d_wgrad_f32_tpad(const void* x, int x_is_i16, const float* mean, const float* std, const float* gz,
                                  float* dw, float* db, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
                                  int Hi, int Wi, int Cout, int pad_t, pvb200_stream_t stream) {
+  return pvb200_conv3d_wgrad_f32_pad(x, x_is_i16, mean, std, gz, dw, db, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout, pad_t,
+                                     0, stream);
+}
+
+int pvb200_conv3d_wgrad_f32_pad(const void* x, int x_is_i16, const float* mean, const float* std, const float* gz,
+                                float* dw, float* db, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
+                                int Hi, int Wi, int Cout, int pad_t, int pad_hw, pvb200_stream_t stream) {
   using namespace pvb;
   PVB_REQUIRE(x && gz && dw, "conv3d_wgrad: null pointer");
-  PVB_REQUIRE(pad_t == 0 || pad_t == 1, "conv3d_wgrad: time padding %d not in {0, 1}", pad_t);
-  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti + 2 * pad_t > 2 && Hi > 2 && Wi > 2, "conv3d_wgrad: bad shape");
+  PVB_REQUIRE((pad_t == 0 || pad_t == 1) && (pad_hw == 0 || pad_hw == 1), "conv3d_wgrad: padding (%d, %d) not in {0, 1}", pad_t, pad_hw);
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti + 2 * pad_t > 2 && Hi + 2 * pad_hw > 2 && Wi + 2 * pad_hw > 2, "conv3d_wgrad: bad shape");
   PVB_REQUIRE(Cin <= kWgMaxCi, "conv3d_wgrad: Cin=%d > %d not supported", Cin, kWgMaxCi);
   PVB_REQUIRE(!x_is_i16 || (mean && std), "conv3d_wgrad: int16 input needs mean/std");
   const size_t need = pvb200_conv3d_wgrad_workspace_bytes(Cin, Cout);
@@ -287,9 +296,9 @@ int pvb200_conv3d_wgrad_f32_tpad(const void* x, int x_is_i16, const float* mean,
   WgradArgs a;
   a.x = x; a.mean = mean; a.stdv = std; a.gz = gz; a.partial = static_cast<float*>(workspace);
   a.B = B; a.Ci = Cin; a.Ti = Ti; a.Hi = Hi; a.Wi = Wi; a.Co = Cout;
-  a.To = Ti + 2 * pad_t - 2; a.Ho = Hi - 2; a.Wo = Wi - 2;
-  a.pad_t = pad_t;
-  a.Wps = round_up(Wi, 4);
+  a.To = Ti + 2 * pad_t - 2; a.Ho = Hi + 2 * pad_hw - 2; a.Wo = Wi + 2 * pad_hw - 2;
+  a.pad_t = pad_t; a.pad_hw = pad_hw;
+  a.Wps = round_up(Wi + 2 * pad_hw, 4);
   a.NP = kWgQC + 2 * a.Wps + 8;
   a.NPs = round_up(a.NP, 8) + 4;
   const int Qtot = (a.Ho - 1) * a.Wps + a.Wo;
@@ -299,7 +308,8 @@ int pvb200_conv3d_wgrad_f32_tpad(const void* x, int x_is_i16, const float* mean,
   // narrow layers (conv0: Cin = 12) split the 27 taps over 3 threads to keep the CTA full
   const int kts = (a.ncog * Cin <= 128) ? 3 : 1;
   a.items = a.ncog * Cin * kts;
-  a.pairs = (!x_is_i16 && Wi % 2 == 0 && reinterpret_cast<uintptr_t>(x) % 8 == 0 && reinterpret_cast<uintptr_t>(gz) % 8 == 0) ? 1 : 0;
+  a.pairs = (!x_is_i16 && pad_hw == 0 && Wi % 2 == 0 && reinterpret_cast<uintptr_t>(x) % 8 == 0 &&
+             reinterpret_cast<uintptr_t>(gz) % 8 == 0) ? 1 : 0;
   const int cap = (kts == 1) ? 256 : 384;
   const int grid_y = ceil_div(a.items, cap);
   const int threads = round_up(ceil_div(a.items, grid_y), 32);

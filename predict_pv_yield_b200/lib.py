@@ -82,6 +82,14 @@ SIGNATURES = {
                                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_wgrad_f32_tpad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_fwd_f32_pad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_dgrad_f32_pad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_wgrad_f32_pad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_maxpool3d_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
+    "pvb200_maxpool3d_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "pvb200_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_ll]),
     "pvb200_linear_fwd_f32": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_ll, c_int, c_int, c_void_p,
                                       c_size_t, c_void_p]),

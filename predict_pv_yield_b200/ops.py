@@ -125,7 +125,8 @@ def sat_normalise(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, out_dt
 
 
 def conv3d_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = True,
-               mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None, pad_t: int = 0) -> torch.Tensor:
+               mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None, pad_t: int = 0,
+               pad_hw: int = 0) -> torch.Tensor:
     """relu(conv3d(x, w, b)) with 3x3x3 kernel, padding (pad_t, 0, 0) (model.py:117-120; pad_t = 1: model_sat_nwp.py:85-100).
     x fp32, or int16 with fused normalise."""
     L = _lib.load()
@@ -138,29 +139,29 @@ def conv3d_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu
     Co = w.shape[0]
     if tuple(w.shape) != (Co, Ci, 3, 3, 3):
         raise RuntimeError(f"conv3d: weight shape {tuple(w.shape)} does not match input channels {Ci}")
-    if min(Ti + 2 * pad_t, Hi, Wi) < 3:
+    if min(Ti + 2 * pad_t, Hi + 2 * pad_hw, Wi + 2 * pad_hw) < 3:
         raise RuntimeError(f"conv3d: input {Ti}x{Hi}x{Wi} smaller than the 3x3x3 kernel")
     if i16 and (mean is None or std is None):
         raise RuntimeError("conv3d: int16 input needs mean/std")
-    y = torch.empty((B, Co, Ti + 2 * pad_t - 2, Hi - 2, Wi - 2), dtype=torch.float32, device=x.device)
+    y = torch.empty((B, Co, Ti + 2 * pad_t - 2, Hi + 2 * pad_hw - 2, Wi + 2 * pad_hw - 2), dtype=torch.float32, device=x.device)
     nb = L.pvb200_conv3d_workspace_bytes(Ci, Co)
     ws = _workspace("conv", nb, x.device)
     with _timed(f"conv3d_fwd_f32[Ci={Ci}]", 2.0 * 27 * Ci * y.numel(), x.numel() * x.element_size() + 4.0 * y.numel()):
-        rc = L.pvb200_conv3d_fwd_f32_tpad(_p(x), int(i16), _p(mean) if i16 else None, _p(std) if i16 else None, _p(w), _p(b),
-                                          _p(y), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, int(relu), pad_t, _stream())
+        rc = L.pvb200_conv3d_fwd_f32_pad(_p(x), int(i16), _p(mean) if i16 else None, _p(std) if i16 else None, _p(w), _p(b),
+                                         _p(y), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, int(relu), pad_t, pad_hw, _stream())
     _lib.check(rc, "conv3d_fwd")
     return y
 
 
 def conv3d_dgrad(gz: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Tensor], x_shape: Sequence[int],
-                 pad_t: int = 0) -> torch.Tensor:
+                 pad_t: int = 0, pad_hw: int = 0) -> torch.Tensor:
     """gx = conv_transpose3d(gz, w) * (mask_src > 0).  gz: gradient w.r.t. the conv's pre-activation output."""
     L = _lib.load()
     _need_cuda(gz, "gz", torch.float32)
     _need_cuda(w, "conv weight", torch.float32)
     B, Ci, Ti, Hi, Wi = x_shape
     Co = w.shape[0]
-    if tuple(gz.shape) != (B, Co, Ti + 2 * pad_t - 2, Hi - 2, Wi - 2):
+    if tuple(gz.shape) != (B, Co, Ti + 2 * pad_t - 2, Hi + 2 * pad_hw - 2, Wi + 2 * pad_hw - 2):
         raise RuntimeError(f"conv3d_dgrad: gz shape {tuple(gz.shape)} inconsistent with input {tuple(x_shape)}")
     if mask_src is not None:
         _need_cuda(mask_src, "mask_src", torch.float32)
@@ -171,14 +172,14 @@ def conv3d_dgrad(gz: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Ten
     ws = _workspace("conv", nb, gz.device)
     with _timed(f"conv3d_dgrad_f32[Ci={Ci}]", 2.0 * 27 * Ci * gz.numel(),
                 4.0 * (gz.numel() + gx.numel() * (2 if mask_src is not None else 1))):
-        rc = L.pvb200_conv3d_dgrad_f32_tpad(_p(gz), _p(w), _p(mask_src), _p(gx), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
-                                            _stream())
+        rc = L.pvb200_conv3d_dgrad_f32_pad(_p(gz), _p(w), _p(mask_src), _p(gx), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
+                                           pad_hw, _stream())
     _lib.check(rc, "conv3d_dgrad")
     return gx
 
 
 def conv3d_wgrad(x: torch.Tensor, gz: torch.Tensor, mean: Optional[torch.Tensor] = None,
-                 std: Optional[torch.Tensor] = None, pad_t: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                 std: Optional[torch.Tensor] = None, pad_t: int = 0, pad_hw: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """(dw [Co,Ci,3,3,3], db [Co]) from the layer input x and the pre-activation gradient gz."""
     L = _lib.load()
     i16 = x.dtype == torch.int16
@@ -186,15 +187,15 @@ def conv3d_wgrad(x: torch.Tensor, gz: torch.Tensor, mean: Optional[torch.Tensor]
     _need_cuda(gz, "gz", torch.float32)
     B, Ci, Ti, Hi, Wi = x.shape
     Co = gz.shape[1]
-    if tuple(gz.shape) != (B, Co, Ti + 2 * pad_t - 2, Hi - 2, Wi - 2):
+    if tuple(gz.shape) != (B, Co, Ti + 2 * pad_t - 2, Hi + 2 * pad_hw - 2, Wi + 2 * pad_hw - 2):
         raise RuntimeError(f"conv3d_wgrad: gz shape {tuple(gz.shape)} inconsistent with input {tuple(x.shape)}")
     dw = torch.empty((Co, Ci, 3, 3, 3), dtype=torch.float32, device=x.device)
     db = torch.empty((Co,), dtype=torch.float32, device=x.device)
     nb = L.pvb200_conv3d_wgrad_workspace_bytes(Ci, Co)
     ws = _workspace("wgrad", nb, x.device)
     with _timed(f"conv3d_wgrad_f32[Ci={Ci}]", 2.0 * 27 * Ci * gz.numel(), x.numel() * x.element_size() + 4.0 * gz.numel()):
-        rc = L.pvb200_conv3d_wgrad_f32_tpad(_p(x), int(i16), _p(mean) if i16 else None, _p(std) if i16 else None, _p(gz), _p(dw),
-                                            _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t, _stream())
+        rc = L.pvb200_conv3d_wgrad_f32_pad(_p(x), int(i16), _p(mean) if i16 else None, _p(std) if i16 else None, _p(gz), _p(dw),
+                                           _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t, pad_hw, _stream())
     _lib.check(rc, "conv3d_wgrad")
     return dw, db
 
@@ -786,6 +787,42 @@ class TowerFn(torch.autograd.Function):
             if l > 0:
                 gz = conv3d_dgrad(gz, wb[2 * l], acts[l - 1], acts[l - 1].shape, pad_t=pad_t)
         return (None, None, None, None, *grads)
+
+
+class Conv3dMaxPoolFn(torch.autograd.Function):
+    """MaxPool3d(3, stride (1,2,2), pad 1)(Conv3d(x, w, b, padding 1)) -- the Conv3dMaxPool block of the Perceiver hybrid
+    (perceiver_conv3d_nwp_sat.py:42-57; no ReLU between the two).  forward(x [B,Ci,T,H,W] fp32, w, b) -> [B,Co,T,Ho,Wo];
+    x may require grad (the block is a front-end, but nothing forces it to be the first layer)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        L = _lib.load()
+        x = x.contiguous()
+        y = conv3d_fwd(x, w, b, relu=False, pad_t=1, pad_hw=1)
+        B, Co, T, H, W = y.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        out = torch.empty((B, Co, T, Ho, Wo), dtype=torch.float32, device=x.device)
+        arg = torch.empty((B, Co, T, Ho, Wo), dtype=torch.int32, device=x.device)
+        with _timed("maxpool3d_fwd_f32", 0.0, 4.0 * y.numel() + 8.0 * out.numel()):
+            rc = L.pvb200_maxpool3d_fwd_f32(_p(y), _p(out), _p(arg), B * Co, T, H, W, _stream())
+        _lib.check(rc, "maxpool3d_fwd")
+        ctx.save_for_backward(x, w, arg)
+        ctx.conv_shape = tuple(y.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.load()
+        x, w, arg = ctx.saved_tensors
+        B, Co, T, H, W = ctx.conv_shape
+        g = g.contiguous()
+        gz = torch.empty(ctx.conv_shape, dtype=torch.float32, device=g.device)
+        with _timed("maxpool3d_bwd_f32", 0.0, 4.0 * gz.numel() + 8.0 * g.numel()):
+            rc = L.pvb200_maxpool3d_bwd_f32(_p(g), _p(arg), _p(gz), B * Co, T, H, W, _stream())
+        _lib.check(rc, "maxpool3d_bwd")
+        dw, db = conv3d_wgrad(x, gz, pad_t=1, pad_hw=1)
+        gx = conv3d_dgrad(gz, w, None, x.shape, pad_t=1, pad_hw=1) if ctx.needs_input_grad[0] else None
+        return gx, dw, db
 
 
 class LinearFn(torch.autograd.Function):
