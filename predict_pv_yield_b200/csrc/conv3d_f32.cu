@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
     const float* in_b = in_s + buf * (kCC * 3 * a.NP);
     const float* w_b = w_s + buf * (kCC * 27 * kCoT);
     for (int c = 0; c < cmax; ++c) {
-#pragma unroll 1
+#pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
         // a time plane that lies entirely in the zero padding of the data gradient contributes nothing (block-uniform)
         const int ti = to + kt - a.Pt;
