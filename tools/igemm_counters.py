@@ -1,5 +1,7 @@
-"""Print the igemm kernel's internal cycle counters (MMA warp: waiting for data / for the epilogue / issuing;
-epilogue warp: waiting for accumulators / at the exchange barrier) for one layer.  python tools/igemm_counters.py fwd 1"""
+"""Print the igemm kernel's internal cycle counters (MMA warp: total, waiting for input planes, waiting for a free
+accumulator, issuing; epilogue warp 2: waiting for accumulators, TMEM load, bias/ReLU/store) for one layer, for the
+profiling flags 0 (normal), 1 (no plane copies), 2 (no output stores), 16 (no epilogue work), then the time per call of
+the production and the profiling build.  python tools/igemm_counters.py fwd|dgrad [layer]"""
 import ctypes
 import os
 import sys
