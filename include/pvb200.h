@@ -146,6 +146,16 @@ int pvb200_conv3d_wgrad_f32_tpad(const void* x, int x_is_i16, const float* mean,
                                  const float* gz, float* dw, float* db, void* workspace, size_t workspace_bytes,
                                  int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t, pvb200_stream_t stream);
 
+/* bf16 tensor-core convolutions with time padding pad_t in {0, 1} (the towers of conv3d_sat_nwp in bf16): the planes
+ * of the padding are skipped inside the kernel, nothing is padded in memory.  fwd: y has Ti + 2 pad_t - 2 planes.
+ * dgrad: gz (Ti + 2 pad_t - 2 planes) arrives zero-padded by 2 on T, H, W as for pvb200_conv3d_dgrad_bf16. */
+int pvb200_conv3d_fwd_bf16_tpad(const uint16_t* xb, const float* w, const float* bias, uint16_t* yb, void* workspace,
+                                size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu,
+                                int out_pad, int pad_t, pvb200_stream_t stream);
+int pvb200_conv3d_dgrad_bf16_tpad(const uint16_t* gz_padded, const float* w, const uint16_t* mask_src, uint16_t* gx,
+                                  uint16_t* gx_gzw, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
+                                  int Hi, int Wi, int Cout, int out_pad, int pad_t, pvb200_stream_t stream);
+
 /* ---- general padding (pad_t, pad_hw, pad_hw), each 0 or 1, and MaxPool3d: the Conv3dMaxPool front-end of the Perceiver
  * hybrid (nn.Conv3d(..., padding=(1, 1, 1)) + nn.MaxPool3d(3, stride=(1, 2, 2), padding=(1, 1, 1)),
  * predict_pv_yield/models/perceiver/perceiver_conv3d_nwp_sat.py:42-57).  Ti/Hi/Wi are the INPUT extents. */

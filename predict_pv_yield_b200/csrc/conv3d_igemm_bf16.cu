@@ -56,6 +56,8 @@ struct IgemmArgs {
   int CoP, Co, CogOut, To, Ho, Wo;  // CoP = Cout padded to 16/32; MMA N = 3*CoP (the three kt taps side by side)
   int out_pad, relu;
   int zero_planes;  // the first / last `zero_planes` input time planes are all zero (padded gz): their MMAs are skipped
+  int plane_off;    // input plane of output t, tap kt: t + kt + plane_off (-pad_t forward, +pad_t data gradient); planes
+                    // outside [zero_planes, Ti - zero_planes) are zero and skipped (this is also the layer's time padding)
   int NP;       // staged positions per (plane, channel group)
   int tiles_q;  // q tiles per output plane
   int nslot;    // ring slots, as many as fit in shared memory (<= 8)
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
         const long long avail = in_plane - q0;
         const uint32_t npos = static_cast<uint32_t>(avail < a.NP ? avail : a.NP);
         for (int p = 0; p < r.ntiles + 2; ++p) {
-          const int pa = r.t0 + p;  // absolute input plane
+          const int pa = r.t0 + p + a.plane_off;  // absolute input plane
           if (pa < a.zero_planes || pa >= a.Ti - a.zero_planes) continue;  // all-zero plane: never staged
           const uint32_t slot = seq % nslot;
           tc::mbar_wait(empty + slot, ((seq / nslot) & 1u) ^ 1u);
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(kIgThreads, 1) conv3d_igemm_bf16_kernel(const 
           tc::tc_fence_after();
         }
         c1 = DBG ? clock64() : 0;
-        const int pa = r.t0 + i;
+        const int pa = r.t0 + i + a.plane_off;
         const bool skip = pa < a.zero_planes || pa >= a.Ti - a.zero_planes;
         if (!skip) {
           const uint32_t slot = seq % nslot;
@@ -440,7 +442,7 @@ static size_t igemm_ws_bytes(int Ci_role, int Co_role) {
 
 static int launch_igemm(const void* xb, const float* w, long long s_co, long long s_ci, int flip, const float* bias,
                         const void* mask, void* yb, void* yb2, void* ws, size_t ws_bytes, int B, int Ci, int Ti, int Hi, int Wi, int Co,
-                        int out_pad, int relu, int zero_planes, cudaStream_t stream) {
+                        int out_pad, int relu, int zero_planes, int To, int plane_off, cudaStream_t stream) {
   IgemmArgs a;
   a.x = static_cast<const uint4*>(xb);
   a.bias = bias;
@@ -450,7 +452,8 @@ static int launch_igemm(const void* xb, const float* w, long long s_co, long lon
   a.B = B; a.Cg = igemm_cg(Ci); a.Ti = Ti; a.Hi = Hi; a.Wi = Wi;
   PVB_REQUIRE(Co <= 32, "conv3d_bf16: Cout=%d > 32 is not supported by the tensor-core path (use fp32 mode)", Co);
   a.CoP = igemm_cop(Co); a.Co = Co; a.CogOut = igemm_cg(Co);
-  a.To = Ti - 2; a.Ho = Hi - 2; a.Wo = Wi - 2;
+  a.To = To; a.Ho = Hi - 2; a.Wo = Wi - 2;
+  a.plane_off = plane_off;
   PVB_REQUIRE(a.To > 0 && a.Ho > 0 && a.Wo > 0, "conv3d_bf16: input %dx%dx%d too small", Ti, Hi, Wi);
   PVB_REQUIRE(a.Cg == 2 || a.Cg == 4, "conv3d_bf16: Cin=%d > 32 is not supported by the tensor-core path (use fp32 mode)", Ci);
   a.out_pad = out_pad; a.relu = relu;
@@ -545,26 +548,42 @@ int pvb200_blocked_to_nc_f32(const uint16_t* x, float* y, int B, int C, int T, i
   return PVB200_OK;
 }
 
+int pvb200_conv3d_fwd_bf16_tpad(const uint16_t* xb, const float* w, const float* bias, uint16_t* yb, void* workspace,
+                                size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int out_pad,
+                                int pad_t, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(xb && w && yb, "conv3d_fwd_bf16: null pointer");
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && out_pad >= 0 && (pad_t == 0 || pad_t == 1), "conv3d_fwd_bf16: bad shape");
+  return launch_igemm(xb, w, static_cast<long long>(Cin) * 27, 27, 0, bias, nullptr, yb, nullptr, workspace, workspace_bytes, B, Cin,
+                      Ti, Hi, Wi, Cout, out_pad, relu, /*zero_planes=*/0, /*To=*/Ti + 2 * pad_t - 2, /*plane_off=*/-pad_t,
+                      as_stream(stream));
+}
+
 int pvb200_conv3d_fwd_bf16(const uint16_t* xb, const float* w, const float* bias, uint16_t* yb, void* workspace,
                            size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int out_pad,
                            pvb200_stream_t stream) {
+  return pvb200_conv3d_fwd_bf16_tpad(xb, w, bias, yb, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout, relu, out_pad, 0, stream);
+}
+
+int pvb200_conv3d_dgrad_bf16_tpad(const uint16_t* gz_padded, const float* w, const uint16_t* mask_src, uint16_t* gx,
+                                  uint16_t* gx_gzw, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi,
+                                  int Cout, int out_pad, int pad_t, pvb200_stream_t stream) {
   using namespace pvb;
-  PVB_REQUIRE(xb && w && yb, "conv3d_fwd_bf16: null pointer");
-  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && out_pad >= 0, "conv3d_fwd_bf16: bad shape");
-  return launch_igemm(xb, w, static_cast<long long>(Cin) * 27, 27, 0, bias, nullptr, yb, nullptr, workspace, workspace_bytes, B, Cin,
-                      Ti, Hi, Wi, Cout, out_pad, relu, /*zero_planes=*/0, as_stream(stream));
+  PVB_REQUIRE(gz_padded && w && gx, "conv3d_dgrad_bf16: null pointer");
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti + 2 * pad_t > 2 && Hi > 2 && Wi > 2 && out_pad >= 0 && (pad_t == 0 || pad_t == 1),
+              "conv3d_dgrad_bf16: bad shape");
+  // kernel input = gz (Ti + 2 pad_t - 2 planes) zero-padded by 2: [B][Cg(Cout)][Ti + 2 pad_t + 2][Hi+2][Wi+2];
+  // kernel output = gx [B][Cg(Cin)][Ti][Hi][Wi]: gx[t] reads the padded planes t + pad_t + {0,1,2}
+  return launch_igemm(gz_padded, w, /*s_co (out role = ci)*/ 27, /*s_ci (in role = co)*/ static_cast<long long>(Cin) * 27, 1,
+                      nullptr, mask_src, gx, gx_gzw, workspace, workspace_bytes, B, /*Ci role*/ Cout, Ti + 2 * pad_t + 2, Hi + 2, Wi + 2,
+                      /*Co role*/ Cin, out_pad, 0, /*zero_planes=*/2, /*To=*/Ti, /*plane_off=*/pad_t, as_stream(stream));
 }
 
 int pvb200_conv3d_dgrad_bf16(const uint16_t* gz_padded, const float* w, const uint16_t* mask_src, uint16_t* gx,
                              uint16_t* gx_gzw, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
                              int out_pad, pvb200_stream_t stream) {
-  using namespace pvb;
-  PVB_REQUIRE(gz_padded && w && gx, "conv3d_dgrad_bf16: null pointer");
-  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti > 2 && Hi > 2 && Wi > 2 && out_pad >= 0, "conv3d_dgrad_bf16: bad shape");
-  // kernel input = gz zero-padded by 2: [B][Cg(Cout)][Ti+2][Hi+2][Wi+2]; kernel output = gx [B][Cg(Cin)][Ti][Hi][Wi]
-  return launch_igemm(gz_padded, w, /*s_co (out role = ci)*/ 27, /*s_ci (in role = co)*/ static_cast<long long>(Cin) * 27, 1,
-                      nullptr, mask_src, gx, gx_gzw, workspace, workspace_bytes, B, /*Ci role*/ Cout, Ti + 2, Hi + 2, Wi + 2,
-                      /*Co role*/ Cin, out_pad, 0, /*zero_planes=*/2, as_stream(stream));
+  return pvb200_conv3d_dgrad_bf16_tpad(gz_padded, w, mask_src, gx, gx_gzw, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout, out_pad,
+                                       0, stream);
 }
 
 }  // extern "C"

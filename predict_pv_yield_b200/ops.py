@@ -234,7 +234,7 @@ def from_blocked_bf16(xb: torch.Tensor, C: int) -> torch.Tensor:
 
 
 def conv3d_fwd_bf16(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = True,
-                    out_pad: int = 0) -> torch.Tensor:
+                    out_pad: int = 0, pad_t: int = 0) -> torch.Tensor:
     """Blocked bf16 conv3d 3x3x3 (+bias, +ReLU) on the tensor cores; fp32 master weights [Co,Ci,3,3,3]."""
     L = _lib.load()
     _need_cuda(xb, "xb", torch.bfloat16)
@@ -244,19 +244,19 @@ def conv3d_fwd_bf16(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]
     if e != 8 or Cg != blocked_groups(Ci):
         raise RuntimeError(f"conv3d_fwd_bf16: input has {Cg} channel groups, weight expects Cin={Ci}")
     alloc = torch.zeros if out_pad > 0 else torch.empty
-    yb = alloc((B, blocked_groups(Co), Ti - 2 + 2 * out_pad, Hi - 2 + 2 * out_pad, Wi - 2 + 2 * out_pad, 8),
+    yb = alloc((B, blocked_groups(Co), Ti + 2 * pad_t - 2 + 2 * out_pad, Hi - 2 + 2 * out_pad, Wi - 2 + 2 * out_pad, 8),
                dtype=torch.bfloat16, device=xb.device)
     ws = _workspace("conv_bf16", L.pvb200_conv3d_bf16_workspace_bytes(Ci, Co), xb.device)
-    npos = B * (Ti - 2) * (Hi - 2) * (Wi - 2)
+    npos = B * (Ti + 2 * pad_t - 2) * (Hi - 2) * (Wi - 2)
     with _timed(f"conv3d_fwd_bf16[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 2.0 * (xb.numel() + 8 * blocked_groups(Co) * npos)):
-        rc = L.pvb200_conv3d_fwd_bf16(_p(xb), _p(w), _p(b), _p(yb), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, int(relu),
-                                      out_pad, _stream())
+        rc = L.pvb200_conv3d_fwd_bf16_tpad(_p(xb), _p(w), _p(b), _p(yb), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, int(relu),
+                                           out_pad, pad_t, _stream())
     _lib.check(rc, "conv3d_fwd_bf16")
     return yb
 
 
 def conv3d_dgrad_bf16(gz_padded: torch.Tensor, w: torch.Tensor, mask_src: Optional[torch.Tensor], out_pad: int = 0,
-                      also_gzw: bool = False, persistent: bool = False):
+                      also_gzw: bool = False, persistent: bool = False, pad_t: int = 0):
     """gx (blocked bf16, optionally written into a padded tensor) from gz zero-padded by 2 on T,H,W.
     ``also_gzw``: additionally return gx in the weight-gradient operand layout of the layer below."""
     L = _lib.load()
@@ -264,7 +264,7 @@ def conv3d_dgrad_bf16(gz_padded: torch.Tensor, w: torch.Tensor, mask_src: Option
     _need_cuda(w, "conv weight", torch.float32)
     B, Cgo, Tp, Hp, Wp, e = gz_padded.shape
     Co, Ci = w.shape[0], w.shape[1]
-    Ti, Hi, Wi = Tp - 2, Hp - 2, Wp - 2
+    Ti, Hi, Wi = Tp - 2 - 2 * pad_t, Hp - 2, Wp - 2
     if e != 8 or Cgo != blocked_groups(Co):
         raise RuntimeError("conv3d_dgrad_bf16: gz channel groups do not match the weight")
     Cgi = blocked_groups(Ci)
@@ -290,8 +290,8 @@ def conv3d_dgrad_bf16(gz_padded: torch.Tensor, w: torch.Tensor, mask_src: Option
     npos = B * Ti * Hi * Wi
     with _timed(f"conv3d_dgrad_bf16[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
                 2.0 * (gz_padded.numel() + 8 * Cgi * npos * ((2 if mask_src is not None else 1) + (1 if also_gzw else 0)))):
-        rc = L.pvb200_conv3d_dgrad_bf16(_p(gz_padded), _p(w), _p(mask_src), _p(gx), _p(gzw), _p(ws), ws.numel(), B, Ci, Ti, Hi,
-                                        Wi, Co, out_pad, _stream())
+        rc = L.pvb200_conv3d_dgrad_bf16_tpad(_p(gz_padded), _p(w), _p(mask_src), _p(gx), _p(gzw), _p(ws), ws.numel(), B, Ci, Ti, Hi,
+                                             Wi, Co, out_pad, pad_t, _stream())
     _lib.check(rc, "conv3d_dgrad_bf16")
     return (gx, gzw) if also_gzw else gx
 

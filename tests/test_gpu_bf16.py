@@ -375,3 +375,26 @@ def test_bf16_model_batch_limits_of_the_tensor_core_head(dev, B, grad):
         with torch.no_grad():
             y, want = m(O.batch_to(batch, dev)), om(batch)
         assert O.normalised_max_err(y, want) <= BF16_TOL
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 5, 10, 10, 32), (1, 12, 1, 9, 9, 32), (2, 32, 19, 8, 8, 32)])
+def test_conv3d_bf16_time_padded(ops, dev, shape):
+    """Tensor-core forward / data gradient with padding (1, 0, 0) (the towers of conv3d_sat_nwp): the planes of the padding
+    are skipped in the kernel.  19 time steps exercise runs longer than the 16 accumulator slots."""
+    B, Ci, T, H, W, Co = shape
+    g = torch.Generator().manual_seed(21)
+    x = r16(torch.randn((B, Ci, T, H, W), generator=g))
+    w = torch.randn((Co, Ci, 3, 3, 3), generator=g) / np.sqrt(Ci * 27)
+    b = torch.randn((Co,), generator=g) * 0.1
+    gz = r16(torch.randn((B, Co, T, H - 2, W - 2), generator=g))
+    xd = x.double().requires_grad_(True)
+    pre = F.conv3d(xd, r16(w).double(), b.double(), padding=(1, 0, 0))
+    pre.backward(gz.double())
+    xb = ops.to_blocked_bf16(x.to(dev))
+    got = ops.from_blocked_bf16(ops.conv3d_fwd_bf16(xb, w.to(dev), b.to(dev), relu=True, pad_t=1), Co)
+    assert O.normalised_max_err(got, F.relu(pre.detach())) <= BF16_TOL
+    if Ci % 16 == 0:
+        gzp = ops.to_blocked_bf16(gz.to(dev), pad=2)
+        gx = ops.from_blocked_bf16(ops.conv3d_dgrad_bf16(gzp, w.to(dev), None, pad_t=1), Ci)
+        assert tuple(gx.shape) == (B, Ci, T, H, W)
+        assert O.normalised_max_err(gx, xd.grad) <= BF16_TOL
