@@ -152,6 +152,9 @@ int pvb200_conv3d_wgrad_f32_tpad(const void* x, int x_is_i16, const float* mean,
 int pvb200_conv3d_fwd_bf16_tpad(const uint16_t* xb, const float* w, const float* bias, uint16_t* yb, void* workspace,
                                 size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu,
                                 int out_pad, int pad_t, pvb200_stream_t stream);
+int pvb200_conv3d_wgrad_bf16_tpad(const uint16_t* xb, const uint16_t* gzw, float* dw, float* db, void* workspace,
+                                  size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
+                                  pvb200_stream_t stream);
 int pvb200_conv3d_dgrad_bf16_tpad(const uint16_t* gz_padded, const float* w, const uint16_t* mask_src, uint16_t* gx,
                                   uint16_t* gx_gzw, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
                                   int Hi, int Wi, int Cout, int out_pad, int pad_t, pvb200_stream_t stream);

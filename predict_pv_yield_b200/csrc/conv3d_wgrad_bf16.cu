@@ -37,6 +37,8 @@ struct WgradBf16Args {
   int NPOS;      // staged x positions per (plane, channel group)
   int nstage;
   long long tiles;  // B * To * chunks
+  int pad_t;         // time padding of the layer: x plane of (t, kt) is t + kt - pad_t, zero outside [0, Ti)
+  const uint4* zeros;  // NPOS 16-byte zeros (source of the copies for the planes of the time padding)
 };
 
 __global__ void __launch_bounds__(kWbThreads, 1) conv3d_wgrad_bf16_kernel(const WgradBf16Args a) {
@@ -102,7 +104,8 @@ __global__ void __launch_bounds__(kWbThreads, 1) conv3d_wgrad_bf16_kernel(const 
       // rows of the remaining (never loaded, zero-initialised) planes are computed and discarded
       if (lane < ncopy_x) {
         const int p = lane / a.Cgx, cg = lane - p * a.Cgx;
-        const uint4* src = a.x + ((static_cast<long long>(b) * a.Cgx + cg) * a.Ti + (t + p)) * x_plane + q0;
+        const int tp = t + p - a.pad_t;
+        const uint4* src = (tp >= 0 && tp < a.Ti) ? a.x + ((static_cast<long long>(b) * a.Cgx + cg) * a.Ti + tp) * x_plane + q0 : a.zeros;
         if (npos) tc::bulk_g2s(dst + static_cast<uint32_t>(lane) * a.NPOS * 16u, src, npos * 16u, full + st);
       } else if (lane < ncopy_x + a.Cgo) {
         const int cg = lane - ncopy_x;
@@ -208,25 +211,35 @@ long long pvb200_conv3d_wgrad_bf16_gz_plane(int Hi, int Wi) {
   return pvb::round_up(static_cast<long long>(Hi - 2) * Wi, 128LL);
 }
 
+static const size_t kWbZeroBytes = 16 * 1024;  // zero page behind the partials (time-padding planes are copied from it)
+
 size_t pvb200_conv3d_wgrad_bf16_workspace_bytes(int Cin, int Cout) {
   const int Cgx = 2 * pvb::ceil_div(Cin, 16), Cgo = 2 * pvb::ceil_div(Cout, 16);
   (void)Cgx;
-  return static_cast<size_t>(160) * 9 * 128 * (8 * Cgo) * sizeof(float);
+  return static_cast<size_t>(160) * 9 * 128 * (8 * Cgo) * sizeof(float) + kWbZeroBytes;
 }
 
 int pvb200_conv3d_wgrad_bf16(const uint16_t* xb, const uint16_t* gzw, float* dw, float* db, void* workspace,
                              size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
                              pvb200_stream_t stream) {
+  return pvb200_conv3d_wgrad_bf16_tpad(xb, gzw, dw, db, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout, 0, stream);
+}
+
+int pvb200_conv3d_wgrad_bf16_tpad(const uint16_t* xb, const uint16_t* gzw, float* dw, float* db, void* workspace,
+                                  size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
+                                  pvb200_stream_t stream) {
   using namespace pvb;
   PVB_REQUIRE(xb && gzw && dw, "conv3d_wgrad_bf16: null pointer");
-  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti > 2 && Hi > 2 && Wi > 2, "conv3d_wgrad_bf16: bad shape");
+  PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && (pad_t == 0 || pad_t == 1) && Ti + 2 * pad_t > 2 && Hi > 2 && Wi > 2,
+              "conv3d_wgrad_bf16: bad shape");
   PVB_REQUIRE(Cin <= 32 && Cout <= 32, "conv3d_wgrad_bf16: channels > 32 are not supported by the tensor-core path");
   WgradBf16Args a;
   a.x = reinterpret_cast<const uint4*>(xb);
   a.gzw = reinterpret_cast<const uint4*>(gzw);
   a.partial = static_cast<float*>(workspace);
   a.B = B; a.Cgx = 2 * ceil_div(Cin, 16); a.Cgo = 2 * ceil_div(Cout, 16);
-  a.Ti = Ti; a.Hi = Hi; a.Wi = Wi; a.To = Ti - 2;
+  a.Ti = Ti; a.Hi = Hi; a.Wi = Wi; a.To = Ti + 2 * pad_t - 2;
+  a.pad_t = pad_t;
   a.M = 128; a.N = 8 * a.Cgo;
   a.QP = static_cast<int>(pvb200_conv3d_wgrad_bf16_gz_plane(Hi, Wi));
   a.chunks = a.QP / kWbQ;
@@ -241,12 +254,15 @@ int pvb200_conv3d_wgrad_bf16(const uint16_t* xb, const uint16_t* gzw, float* dw,
   PVB_REQUIRE(sms > 0, "conv3d_wgrad_bf16: no CUDA device");
   long long grid = a.tiles < sms ? a.tiles : sms;
   if (grid > 160) grid = 160;
-  const size_t need = static_cast<size_t>(grid) * 9 * a.M * a.N * sizeof(float);
+  const size_t need = static_cast<size_t>(grid) * 9 * a.M * a.N * sizeof(float) + kWbZeroBytes;
+  PVB_REQUIRE(static_cast<size_t>(a.NPOS) * 16 <= kWbZeroBytes, "conv3d_wgrad_bf16: width %d too large for the zero page", Wi);
   if (!workspace || workspace_bytes < need) {
     set_error("conv3d_wgrad_bf16: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     return PVB200_ERR_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
+  a.zeros = reinterpret_cast<const uint4*>(static_cast<uint8_t*>(workspace) + need - kWbZeroBytes);
+  if (pad_t) PVB_CUDA(cudaMemsetAsync(const_cast<uint4*>(a.zeros), 0, kWbZeroBytes, st));
   const size_t smem = 128 + nstage * stage_bytes;
   PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   conv3d_wgrad_bf16_kernel<<<static_cast<unsigned>(grid), kWbThreads, smem, st>>>(a);

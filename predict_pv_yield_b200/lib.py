@@ -86,6 +86,8 @@ SIGNATURES = {
                                             c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_dgrad_bf16_tpad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_wgrad_bf16_tpad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_fwd_f32_pad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_dgrad_f32_pad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -323,21 +323,22 @@ def to_gzw_bf16(gz: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def conv3d_wgrad_bf16(xb: torch.Tensor, gzw: torch.Tensor, Ci: int, Co: int) -> Tuple[torch.Tensor, torch.Tensor]:
+def conv3d_wgrad_bf16(xb: torch.Tensor, gzw: torch.Tensor, Ci: int, Co: int, pad_t: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """(dw [Co,Ci,3,3,3], db [Co]) fp32 from blocked bf16 x [B,Cg,Ti,Hi,Wi,8] and gzw [B,Cg,To,QP,8]."""
     L = _lib.load()
     _need_cuda(xb, "xb", torch.bfloat16)
     _need_cuda(gzw, "gzw", torch.bfloat16)
     B, Cgx, Ti, Hi, Wi, e = xb.shape
     QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(Hi, Wi))
-    if e != 8 or Cgx != blocked_groups(Ci) or tuple(gzw.shape) != (B, blocked_groups(Co), Ti - 2, QP, 8):
+    if e != 8 or Cgx != blocked_groups(Ci) or tuple(gzw.shape) != (B, blocked_groups(Co), Ti + 2 * pad_t - 2, QP, 8):
         raise RuntimeError(f"conv3d_wgrad_bf16: shapes {tuple(xb.shape)} / {tuple(gzw.shape)} inconsistent")
     dw = torch.empty((Co, Ci, 3, 3, 3), dtype=torch.float32, device=xb.device)
     db = torch.empty((Co,), dtype=torch.float32, device=xb.device)
     ws = _workspace("wgrad_bf16", L.pvb200_conv3d_wgrad_bf16_workspace_bytes(Ci, Co), xb.device)
-    npos = B * (Ti - 2) * (Hi - 2) * (Wi - 2)
+    npos = B * (Ti + 2 * pad_t - 2) * (Hi - 2) * (Wi - 2)
     with _timed(f"conv3d_wgrad_bf16[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 2.0 * (xb.numel() + gzw.numel())):
-        rc = L.pvb200_conv3d_wgrad_bf16(_p(xb), _p(gzw), _p(dw), _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, _stream())
+        rc = L.pvb200_conv3d_wgrad_bf16_tpad(_p(xb), _p(gzw), _p(dw), _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
+                                             _stream())
     _lib.check(rc, "conv3d_wgrad_bf16")
     return dw, db
 

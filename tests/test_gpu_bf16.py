@@ -398,3 +398,10 @@ def test_conv3d_bf16_time_padded(ops, dev, shape):
         gx = ops.from_blocked_bf16(ops.conv3d_dgrad_bf16(gzp, w.to(dev), None, pad_t=1), Ci)
         assert tuple(gx.shape) == (B, Ci, T, H, W)
         assert O.normalised_max_err(gx, xd.grad) <= BF16_TOL
+    # weight / bias gradient with the time padding (zero planes come from the workspace's zero page)
+    wd = torch.zeros((Co, Ci, 3, 3, 3), dtype=torch.float64, requires_grad=True)
+    bd = torch.zeros((Co,), dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.double(), wd, bd, padding=(1, 0, 0)).backward(gz.double())
+    dw, db = ops.conv3d_wgrad_bf16(xb, ops.to_gzw_bf16(gz.to(dev)), Ci, Co, pad_t=1)
+    assert O.normalised_max_err(dw, wd.grad) <= 1e-5
+    assert O.normalised_max_err(db, bd.grad) <= 1e-5
