@@ -244,6 +244,11 @@ int pvb200_linear_bwd_f32(const float* x, long long ldx, const float* w, const f
                           const float* gy, long long ldgy, float* gx, long long ldgx, int mask_gx_with_x,
                           float* dw, float* db, int B, long long K, int N, void* workspace, size_t workspace_bytes,
                           pvb200_stream_t stream);
+/* pieces of a Linear for callers that run the big GEMMs elsewhere (the bf16 tensor-core fc1 of the towers) */
+int pvb200_linear_finish_f32(const float* partial, int S, const float* bias, float* y, long long ldy, int B, int N,
+                             int relu, pvb200_stream_t stream);
+int pvb200_linear_gpre_f32(const float* gy, long long ldgy, const float* y, long long ldy, float* g_pre, float* db,
+                           int B, int N, pvb200_stream_t stream);
 int pvb200_embedding_fwd_f32(const float* table, const int* ids, float* y, long long ldy, int B, int V, int D,
                              pvb200_stream_t stream);
 int pvb200_embedding_bwd_f32(const float* gy, long long ldgy, const int* ids, float* dtable, int B, int V, int D,

@@ -1097,4 +1097,29 @@ int pvb200_history_flatten_f32(const float* src, long long sb, long long st, flo
   return PVB200_OK;
 }
 
+
+/* y[b*ldy + n] = act(bias[n] + sum_s partial[s][b][n]): finishes a split-K forward (pvb200_fc1_fwd_bf16) as a Linear + ReLU */
+int pvb200_linear_finish_f32(const float* partial, int S, const float* bias, float* y, long long ldy, int B, int N, int relu,
+                             pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(partial && y && S > 0 && B > 0 && N > 0 && ldy >= N, "linear_finish: bad argument");
+  linear_finish_kernel<<<ceil_div(B * N, 256), 256, 0, as_stream(stream)>>>(partial, S, bias, y, ldy, B, N, relu);
+  PVB_LAUNCHED("linear_finish");
+  return PVB200_OK;
+}
+
+/* g_pre[b][n] = gy[b][n] * (y[b][n] > 0) (y = NULL: no activation) and db[n] = sum_b g_pre[b][n]: the start of a Linear's
+ * backward when the weight / data gradients are computed elsewhere (pvb200_fc1_{wgrad,dgrad}_bf16) */
+int pvb200_linear_gpre_f32(const float* gy, long long ldgy, const float* y, long long ldy, float* g_pre, float* db, int B, int N,
+                           pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(gy && g_pre && db && B > 0 && N > 0 && ldgy >= N, "linear_gpre: bad argument");
+  cudaStream_t st = as_stream(stream);
+  linear_gpre_kernel<<<ceil_div(B * N, 256), 256, 0, st>>>(gy, ldgy, y, ldy, g_pre, B, N);
+  PVB_LAUNCHED("linear_gpre");
+  linear_wgrad_small_kernel<<<ceil_div(N, 256), 256, 0, st>>>(g_pre, N, g_pre, N, db, db, B, N, 0);
+  PVB_LAUNCHED("linear_bias_grad");
+  return PVB200_OK;
+}
+
 }  // extern "C"

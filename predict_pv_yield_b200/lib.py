@@ -101,6 +101,8 @@ SIGNATURES = {
                                       c_size_t, c_void_p]),
     "pvb200_linear_bwd_f32": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p,
                                       c_void_p, c_int, c_ll, c_int, c_void_p, c_size_t, c_void_p]),
+    "pvb200_linear_finish_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
+    "pvb200_linear_gpre_f32": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pvb200_embedding_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "pvb200_embedding_bwd_f32": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pvb200_history_flatten_f32": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),

@@ -13,8 +13,9 @@ HOLD the parameters; the arithmetic runs in ``libpvb200.so`` (fp32 mode):
   PV / GSP history -> nan_to_num + flatten;  PV history (5 min) -> pv_fc1;  system id -> embedding
   torch.cat (tiny [B, <= 600] tensors, no FLOPs) -> fc3 -> fc4
 
-There is no CPU fallback.  bf16 tensor-core kernels for this model are not wired yet (its towers would reuse
-``conv3d_igemm_bf16`` with the time padding expressed as skipped zero planes).
+``precision="bf16"`` runs both towers and their fc1 / nwp_fc1 on the tensor cores (tcgen05 implicit-GEMM convolutions
+with the time padding expressed as skipped zero planes, weight-streaming fc1 over a bf16 shadow of the fp32 master
+weights, parity <= 2e-2); the small layers stay fp32.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -56,8 +57,12 @@ class Model(BaseModel):
         embedding_dem: int = 16,
         include_pv_yield_history: int = True,
         include_future_satellite: int = True,
+        precision: str = "fp32",
     ):
-        """Same arguments as the reference model (model_sat_nwp.py:18-72)."""
+        """Same arguments as the reference model (model_sat_nwp.py:18-72), plus ``precision`` ("fp32" | "bf16")."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
         self.include_pv_or_gsp_yield_history = include_pv_or_gsp_yield_history
         self.include_nwp = include_nwp
         self.number_of_conv3d_layers = number_of_conv3d_layers
@@ -145,6 +150,13 @@ class Model(BaseModel):
             mean, std = np.zeros(n, np.float32), np.ones(n, np.float32)
         self.register_buffer("sat_mean", torch.from_numpy(mean.copy()), persistent=False)
         self.register_buffer("sat_std", torch.from_numpy(std.copy()), persistent=False)
+        # bf16 mode: tensor-core shadows of the two big fc1 weights; FusedAdam finds them through the parameters
+        self._fc1_shadow = ops.Fc1Shadow()
+        self._nwp_fc1_shadow = ops.Fc1Shadow()
+        if precision == "bf16":
+            self.fc1.weight._pvb_shadow = self._fc1_shadow
+            if include_nwp:
+                self.nwp_fc1.weight._pvb_shadow = self._nwp_fc1_shadow
 
     def _tower_params(self, prefix: str):
         wb = []
@@ -152,6 +164,25 @@ class Model(BaseModel):
             layer = getattr(self, f"{prefix}{i}")
             wb += [layer.weight, layer.bias]
         return wb
+
+    def _tower_and_fc1(self, cube, mean, std, prefix, fc1, shadow, n_features, what):
+        """[Conv3d(pad (1,0,0)) + ReLU] x L -> flatten -> relu(fc1): fp32 kernels, or tensor cores in bf16 mode (batches up to
+        128 when training / 256 forward-only, 32-channel towers; otherwise the fp32 kernels)."""
+        wb = self._tower_params(prefix)
+        B = cube.shape[0]
+        use_tc = (self.precision == "bf16" and B <= (128 if torch.is_grad_enabled() else 256) and fc1.out_features <= 128
+                  and wb[0].shape[0] % 16 == 0)
+        if use_tc:
+            link = {"shadow": shadow, "pad_t": 1, "tag": prefix}
+            act = ops.EncoderBf16Fn.apply(link, cube, mean, std, *wb)
+            if act[0].numel() != n_features:
+                raise RuntimeError(f"{what} cube {tuple(cube.shape)} gives {act[0].numel()} conv features, model expects {n_features}")
+            return ops.Fc1Bf16Fn.apply(link, act, fc1.weight, fc1.bias)
+        out = ops.TowerFn.apply(1, cube, mean, std, *wb)
+        if out.shape[1] != n_features:
+            raise RuntimeError(f"{what} cube {tuple(cube.shape)} gives {out.shape[1]} conv features, model expects {n_features}")
+        # fc1 hands the tower the gradient of its last PRE-activation (model_sat_nwp.py:195, 243)
+        return ops.LinearFn.apply(out, fc1.weight, fc1.bias, True, True)
 
     @staticmethod
     def _need_cuda(t: torch.Tensor, what: str) -> None:
@@ -174,15 +205,8 @@ class Model(BaseModel):
             mean, std = self.sat_mean, self.sat_std  # raw SEVIRI counts: normalised on the device (netcdf_dataset.py:96-101)
         else:
             sat_data, mean, std = sat_data.float(), None, None  # model_sat_nwp.py:180
-        out = ops.TowerFn.apply(1, sat_data.contiguous(), mean, std, *self._tower_params("sat_conv"))
-        if out.shape[1] != self.cnn_output_size:
-            raise RuntimeError(
-                f"satellite cube {tuple(sat_data.shape)} gives {out.shape[1]} conv features, "
-                f"model expects cnn_output_size={self.cnn_output_size}"
-            )
-
-        # Fully connected layers (model_sat_nwp.py:195-197); fc1 hands the tower the gradient of its last PRE-activation
-        out = ops.LinearFn.apply(out, self.fc1.weight, self.fc1.bias, True, True)
+        out = self._tower_and_fc1(sat_data.contiguous(), mean, std, "sat_conv", self.fc1, self._fc1_shadow,
+                                  self.cnn_output_size, "satellite")
         out = ops.LinearFn.apply(out, self.fc2.weight, self.fc2.bias, True, False)
         parts = [out]
 
@@ -203,13 +227,8 @@ class Model(BaseModel):
         if self.include_nwp:
             nwp_data = x.nwp.data.float().contiguous()  # shape: batch_size, n_chans, seq_len, height, width
             self._need_cuda(nwp_data, "nwp.data")
-            out_nwp = ops.TowerFn.apply(1, nwp_data, None, None, *self._tower_params("nwp_conv"))
-            if out_nwp.shape[1] != self.nwp_cnn_output_size:
-                raise RuntimeError(
-                    f"NWP cube {tuple(nwp_data.shape)} gives {out_nwp.shape[1]} conv features, "
-                    f"model expects nwp_cnn_output_size={self.nwp_cnn_output_size}"
-                )
-            out_nwp = ops.LinearFn.apply(out_nwp, self.nwp_fc1.weight, self.nwp_fc1.bias, True, True)
+            out_nwp = self._tower_and_fc1(nwp_data, None, None, "nwp_conv", self.nwp_fc1, self._nwp_fc1_shadow,
+                                          self.nwp_cnn_output_size, "NWP")
             out_nwp = ops.LinearFn.apply(out_nwp, self.nwp_fc2.weight, self.nwp_fc2.bias, True, False)
             parts.append(out_nwp)
 

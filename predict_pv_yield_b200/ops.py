@@ -283,7 +283,9 @@ def conv3d_dgrad_bf16(gz_padded: torch.Tensor, w: torch.Tensor, mask_src: Option
     if also_gzw:
         QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(Hi + 2, Wi + 2))
         if persistent:
-            gzw = _zero_bordered("gzw", (B, Cgi, Ti, QP, 8), gz_padded.device)
+            # keyed by the plane GEOMETRY too: two layers whose planes round up to the same QP must not share a buffer
+            # (the positions that stay zero differ with the pitch)
+            gzw = _zero_bordered(f"gzw_{Hi}x{Wi}", (B, Cgi, Ti, QP, 8), gz_padded.device)
         else:
             gzw = torch.zeros((B, Cgi, Ti, QP, 8), dtype=torch.bfloat16, device=gz_padded.device)
     ws = _workspace("conv_bf16", L.pvb200_conv3d_bf16_workspace_bytes(Ci, Co), gz_padded.device)
@@ -423,16 +425,18 @@ class EncoderBf16Fn(torch.autograd.Function):
         activation itself in blocked bf16 (consumed by ``HeadBf16Fn``, which hands the gradient back through
         ``link["gz"]`` already in the two layouts the conv backward needs)."""
         n_layers = len(wb) // 2
+        pad_t = int(link.get("pad_t", 0)) if link is not None else 0  # time padding of every layer (conv3d_sat_nwp towers: 1)
         if sat.dtype == torch.int16:
             x = sat_normalise_blocked_bf16(sat, mean, std)
         else:
             x = to_blocked_bf16(sat)
         acts = [x]
         for l in range(n_layers):
-            x = conv3d_fwd_bf16(x, wb[2 * l], wb[2 * l + 1], relu=True)
+            x = conv3d_fwd_bf16(x, wb[2 * l], wb[2 * l + 1], relu=True, pad_t=pad_t)
             acts.append(x)
         ctx.save_for_backward(*wb, *acts)
         ctx.n_layers = n_layers
+        ctx.pad_t = pad_t
         ctx.channels = [wb[2 * l].shape[1] for l in range(n_layers)] + [wb[-2].shape[0]]
         ctx.link = link
         if link is not None:
@@ -456,14 +460,16 @@ class EncoderBf16Fn(torch.autograd.Function):
             gz_pad = to_blocked_bf16(g, pad=2) if n > 1 else None
             gzw = to_gzw_bf16(g)
         grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
+        pad_t = ctx.pad_t
         for l in range(n - 1, -1, -1):
-            dw, db = conv3d_wgrad_bf16(acts[l], gzw, ch[l], ch[l + 1])
+            dw, db = conv3d_wgrad_bf16(acts[l], gzw, ch[l], ch[l + 1], pad_t=pad_t)
             grads[2 * l], grads[2 * l + 1] = dw, db
             if l > 0:
                 if l > 1:
-                    gz_pad, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=2, also_gzw=True, persistent=True)
+                    gz_pad, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=2, also_gzw=True, persistent=True,
+                                                    pad_t=pad_t)
                 else:  # the gradient w.r.t. layer 0's output only feeds layer 0's weight gradient
-                    _, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=0, also_gzw=True, persistent=True)
+                    _, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=0, also_gzw=True, persistent=True, pad_t=pad_t)
         return (None, None, None, None, *grads)
 
 
@@ -737,7 +743,7 @@ class HeadBf16Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(H + 2, W + 2))
             gz_pad = _zero_bordered("gz_pad_head", (B, Cg, T + 4, H + 4, W + 4, 8), dev)
-            gzw = _zero_bordered("gzw_head", (B, Cg, T, QP, 8), dev)
+            gzw = _zero_bordered(f"gzw_head_{H}x{W}", (B, Cg, T, QP, 8), dev)
             shadow = ctx.shadow
             with _timed("fc1_dgrad_bf16", 2.0 * B * h.F1 * h.K1, 2.0 * (128 * h.K1 + 4 * B * h.K1)):
                 rc = L.pvb200_fc1_dgrad_bf16(_p(g_h1), _p(shadow), _p(act), _p(gz_pad), _p(gzw), B, h.F1, Cg, T, H, W, _stream())
@@ -824,6 +830,65 @@ class Conv3dMaxPoolFn(torch.autograd.Function):
         dw, db = conv3d_wgrad(x, gz, pad_t=1, pad_hw=1)
         gx = conv3d_dgrad(gz, w, None, x.shape, pad_t=1, pad_hw=1) if ctx.needs_input_grad[0] else None
         return gx, dw, db
+
+
+class Fc1Bf16Fn(torch.autograd.Function):
+    """relu(fc1(flatten(act))) on the tensor cores for a tower of conv3d_sat_nwp in bf16 mode (model_sat_nwp.py:192-195,
+    242-244): weight-streaming tcgen05 GEMMs over the bf16 shadow of the fp32 master weight, exactly as ``HeadBf16Fn``
+    does for the single-tower model.  forward(link, act [B,Cg,T,H,W,8] bf16, w1 [F1,K1], b1) -> [B,F1] fp32.  The
+    gradient w.r.t. ``act`` is handed to ``EncoderBf16Fn`` through ``link["gz"]`` (ReLU mask fused, both layouts)."""
+
+    @staticmethod
+    def forward(ctx, link, act, w1, b1):
+        L = _lib.load()
+        _need_cuda(act, "activation", torch.bfloat16)
+        _need_cuda(w1, "fc1.weight", torch.float32)
+        _need_cuda(b1, "fc1.bias", torch.float32)
+        B, Cg, T, H, W, _ = act.shape
+        F1 = w1.shape[0]
+        if w1.shape[1] != Cg * 8 * T * H * W:
+            raise RuntimeError(f"Fc1Bf16Fn: weight {tuple(w1.shape)} does not match the activation {tuple(act.shape)}")
+        shadow = link["shadow"].ensure(w1, F1, Cg, T, H, W)
+        ctx.shadow = shadow
+        S = int(L.pvb200_fc1_fwd_bf16_splits())
+        partial = _workspace("head", S * B * F1 * 4, act.device)
+        K1 = w1.shape[1]
+        with _timed("fc1_fwd_bf16", 2.0 * B * F1 * K1, 2.0 * (B * K1 + 128 * K1)):
+            rc = L.pvb200_fc1_fwd_bf16(_p(act), _p(shadow), _p(partial), B, F1, Cg, T, H, W, _stream())
+        _lib.check(rc, "fc1_fwd_bf16")
+        h1 = torch.empty((B, F1), dtype=torch.float32, device=act.device)
+        _lib.check(L.pvb200_linear_finish_f32(_p(partial), S, _p(b1), _p(h1), F1, B, F1, 1, _stream()), "linear_finish")
+        ctx.save_for_backward(act, w1, h1)
+        ctx.link = link
+        return h1
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.load()
+        act, w1, h1 = ctx.saved_tensors
+        B, Cg, T, H, W, _ = act.shape
+        F1, K1 = w1.shape
+        dev = act.device
+        g = g.contiguous()
+        g_pre = torch.empty((B, F1), dtype=torch.float32, device=dev)
+        db1 = torch.empty((F1,), dtype=torch.float32, device=dev)
+        _lib.check(L.pvb200_linear_gpre_f32(_p(g), F1, _p(h1), F1, _p(g_pre), _p(db1), B, F1, _stream()), "linear_gpre")
+        dw1 = torch.empty_like(w1)
+        with _timed("fc1_wgrad_bf16", 2.0 * B * F1 * K1, 2.0 * B * K1 + 4.0 * F1 * K1):
+            rc = L.pvb200_fc1_wgrad_bf16(_p(g_pre), _p(act), _p(dw1), B, F1, Cg, T, H, W, _stream())
+        _lib.check(rc, "fc1_wgrad_bf16")
+        g_act = None
+        if ctx.needs_input_grad[1]:
+            tag = ctx.link.get("tag", "tower")
+            QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(H + 2, W + 2))
+            gz_pad = _zero_bordered("gz_pad_" + tag, (B, Cg, T + 4, H + 4, W + 4, 8), dev)
+            gzw = _zero_bordered(f"gzw_{tag}_{H}x{W}", (B, Cg, T, QP, 8), dev)
+            with _timed("fc1_dgrad_bf16", 2.0 * B * F1 * K1, 2.0 * (128 * K1 + 4 * B * K1)):
+                rc = L.pvb200_fc1_dgrad_bf16(_p(g_pre), _p(ctx.shadow), _p(act), _p(gz_pad), _p(gzw), B, F1, Cg, T, H, W, _stream())
+            _lib.check(rc, "fc1_dgrad_bf16")
+            ctx.link["gz"] = (gz_pad, gzw)
+            g_act = torch.empty_like(act)  # placeholder: the real gradient travels through the link
+        return None, g_act, dw1, db1
 
 
 class LinearFn(torch.autograd.Function):

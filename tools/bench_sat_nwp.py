@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     args = ap.parse_args()
     from predict_pv_yield_b200 import ops
     from predict_pv_yield_b200.models.conv3d.model_sat_nwp import Model
@@ -26,7 +27,7 @@ def main():
     B = args.batch
     kw = dict(forecast_minutes=30, history_minutes=60)  # defaults: T = 6 + 12 + 1 = 19, NWP T = 0 + 1 + 1 = 2
     torch.manual_seed(0)
-    m = Model(**kw).to(dev)
+    m = Model(**kw, precision=args.precision).to(dev)
     m.batch_size = B
     rs = np.random.RandomState(0)
     sat = torch.from_numpy(rs.randint(0, 1024, size=(B, 12, 19, 64, 64)).astype(np.int16))
@@ -69,7 +70,7 @@ def main():
     torch.cuda.synchronize()
     ops.set_timer(None)
     ms = e0.elapsed_time(e1) / args.steps
-    print(f"conv3d_sat_nwp train step: {ms:.2f} ms  ({B / ms * 1e3:.0f} samples/s), params {sum(p.numel() for p in m.parameters())}")
+    print(f"conv3d_sat_nwp [{args.precision}] train step: {ms:.2f} ms  ({B / ms * 1e3:.0f} samples/s), params {sum(p.numel() for p in m.parameters())}")
     for k, v in sorted(tm.summary().items(), key=lambda kv: -kv[1]["ms"]):
         print(f"  {k:<34}{v['ms'] / args.steps:8.3f} ms/step  {v['flops'] / max(v['ms'], 1e-9) / 1e9:8.1f} TF  {v['bytes'] / max(v['ms'], 1e-9) / 1e6:7.0f} GB/s")
 
