@@ -234,3 +234,56 @@ def test_bf16_model_within_tolerance_of_oracle(dev, name):
     ref.load_state_dict(m.state_dict())
     with torch.no_grad():
         assert torch.equal(m(dbatch), ref(dbatch))
+
+
+def _production_yaml():
+    import yaml
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = yaml.safe_load(open(os.path.join(root, "configs", "model", "conv3d_sat_nwp.yaml")))
+    target = cfg.pop("_target_")
+    return target, cfg
+
+
+def test_production_yaml_instantiates_the_mirror():
+    """configs/model/conv3d_sat_nwp.yaml: the reference's production keys (configs/model/conv3d_sat_nwp.yaml:3-16) with
+    only `_target_` changed; the mirror and the oracle agree on every derived size."""
+    import importlib
+
+    target, cfg = _production_yaml()
+    mod, cls = target.rsplit(".", 1)
+    m = getattr(importlib.import_module(mod), cls)(**cfg)
+    o = OracleSatNwpModel(**cfg)
+    assert (m.cnn_output_size, m.nwp_cnn_output_size, m.forecast_len) == (o.cnn_output_size, o.nwp_cnn_output_size, o.forecast_len)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(v.shape)) for k, v in o.state_dict().items()]
+    assert m.cnn_output_size == 32 * 12 * 12 * 31 and m.forecast_len == 4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_production_yaml_step_matches_oracle(dev, precision, tol):
+    """The production config (6 layers, 24x24 satellite, 64x64 NWP, gsp_yield, 31 time steps) on a 2-sample batch."""
+    from predict_pv_yield_b200.models.conv3d.model_sat_nwp import Model
+
+    _, cfg = _production_yaml()
+    B = 2
+    torch.manual_seed(4)
+    m = Model(**cfg, precision=precision).to(dev)
+    m.batch_size = B
+    om = OracleSatNwpModel(**cfg)
+    om.batch_size = B
+    om.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    rs = np.random.RandomState(8)
+    batch = {
+        "satellite": {"data": torch.from_numpy(rs.randint(0, 1024, size=(B, 11, 31, 24, 24)).astype(np.int16))},
+        "nwp": {"data": torch.from_numpy(rs.randn(B, 10, 4, 64, 64).astype(np.float32))},
+        "pv": {"pv_yield": torch.from_numpy(rs.rand(B, 31, 128).astype(np.float32))},
+        "gsp": {"gsp_yield": torch.from_numpy(rs.rand(B, 6, 32).astype(np.float32)),
+                "gsp_id": torch.from_numpy(rs.randint(0, 338, size=(B, 32)).astype(np.int64))},
+    }
+    r = om.step_losses(batch)
+    loss = m.training_step(O.batch_to(batch, dev), 0)
+    loss.backward()
+    assert O.normalised_max_err(m(O.batch_to(batch, dev)).detach(), r["y_hat"].detach()) <= tol
+    assert abs(float(loss.detach()) - float(r["nmae"].detach())) <= tol * abs(float(r["nmae"].detach()))
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
