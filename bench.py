@@ -212,13 +212,15 @@ def measure_fp32_fma_peak(torch, lib, dev):
     flops = C.c_double(0.0)
     stream = torch.cuda.current_stream().cuda_stream
     best = 0.0
-    for _ in range(6):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        lib.check(L.pvb200_probe_fp32_fma(sink.data_ptr(), 4096, C.byref(flops), stream), "probe")
-        e1.record()
-        torch.cuda.synchronize()
-        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    # scalar FFMA and packed FFMA2 chains: the denominator is whichever form of the instruction is faster on this part
+    for probe in (L.pvb200_probe_fp32_fma, L.pvb200_probe_fp32_fma2):
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            lib.check(probe(sink.data_ptr(), 4096, C.byref(flops), stream), "probe")
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     return best
 
 

@@ -52,6 +52,9 @@ int pvb200_sm_count(void);
 /* diagnostic: launch an FP32 FMA saturation kernel; *flops_out = FLOPs it performs.  bench.py times it
  * with CUDA events to get the FP32-FMA roofline denominator (not in MEASURED_PEAKS.json). */
 int pvb200_probe_fp32_fma(float* sink, int iters, double* flops_out, pvb200_stream_t stream);
+/* the same probe issued as packed fma.rn.f32x2 (SASS FFMA2, two fp32 FMAs per instruction): the convolution kernels use
+ * the packed form, so bench.py takes the HIGHER of the two probes as the roofline denominator. */
+int pvb200_probe_fp32_fma2(float* sink, int iters, double* flops_out, pvb200_stream_t stream);
 
 /* ---- a1/a2: int16 satellite normalisation ---------------------------------------------------
  * replaces: predict_pv_yield/netcdf_dataset.py:96-101 (astype(float32); - SAT_MEAN; /= SAT_STD)

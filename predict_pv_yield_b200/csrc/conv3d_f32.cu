@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
   extern __shared__ __align__(16) float smem[];
   float* in_s = smem;                                  // [2][kCC][3][NP]
   float* w_s = smem + 2 * kCC * 3 * a.NP;              // [2][kCC][27][32]
-  int* off_s = reinterpret_cast<int*>(w_s + 2 * kCC * 27 * kCoT);  // [NP] offset inside an input plane, or -1
+  int* off_s = reinterpret_cast<int*>(w_s + 2 * kCC * 27 * kCoT);  // [NP] BYTE offset inside an input plane, or -1
+  constexpr int kElemBytes = kI16 ? 2 : 4;
 
   const int tid = threadIdx.x;
   const int tp = tid & 63;   // position thread: positions {4tp..4tp+3} and {256+4tp..256+4tp+3}
@@ -92,14 +93,17 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
     const int hp = pos / a.Wps;
     const int wp = pos - hp * a.Wps;
     const int hi = hp - a.P, wi = wp - a.P;
-    off_s[i] = (hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi) ? hi * a.Wi + wi : -1;
+    off_s[i] = (hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi) ? (hi * a.Wi + wi) * kElemBytes : -1;
   }
 
-  float acc[8][8];
+  // accumulators as channel PAIRS: acc2[j][i] = {channel 2j, channel 2j+1} of position i.  The FMA loop issues the packed
+  // fma.rn.f32x2 of sm_100 (SASS FFMA2: two IEEE fp32 FMAs per issue slot, bit-identical to two fmaf) -- the scalar
+  // loop was bound by the issue rate, not by the FMA pipe (ncu: FFMA 83 % of the instructions at 77 % issue utilisation).
+  float2 acc2[4][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+    for (int i = 0; i < 8; ++i) acc2[j][i] = make_float2(0.f, 0.f);
 
   const long long plane_sz = static_cast<long long>(a.Hi) * a.Wi;
   const int warp = tid >> 5, lane = tid & 31;
@@ -119,11 +123,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
       const bool plane_ok = (ci < a.Ci) && (ti >= 0) && (ti < a.Ti);
       const long long base = plane_ok ? ((static_cast<long long>(b) * a.Ci + ci) * a.Ti + ti) * plane_sz : 0;
       if (kI16) {
-        const int16_t* src = static_cast<const int16_t*>(a.x) + base;
+        const char* src = reinterpret_cast<const char*>(static_cast<const int16_t*>(a.x) + base);
         const float m = plane_ok ? __ldg(a.mean + ci) : 0.f, s = plane_ok ? __ldg(a.stdv + ci) : 1.f;
         for (int i = lane; i < a.NP; i += 32) {
           const int o = off_s[i];
-          dst[i] = (plane_ok && o >= 0) ? sat_norm(__ldg(src + o), m, s) : 0.f;
+          dst[i] = (plane_ok && o >= 0) ? sat_norm(__ldg(reinterpret_cast<const int16_t*>(src + o)), m, s) : 0.f;
         }
       } else if (a.contig) {
         // Wps == Wi and no padding: staged position i is element q0 + i of the plane; 16-byte copies, zero fill past the end
@@ -138,36 +142,37 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
       } else if (a.pairs) {
         // positions 2i, 2i+1 of the staged run are neighbours in the same input row (Wps, q0, P and Wi are even):
         // one 8-byte copy, both valid or both padding
-        const float* src = static_cast<const float*>(a.x) + base;
+        const char* src = reinterpret_cast<const char*>(static_cast<const float*>(a.x) + base);
         const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
         for (int i = 2 * lane; i < a.NP; i += 64) {
           const int o = off_s[i];
           const bool ok = plane_ok && (o >= 0);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? o : 0)),
-                       "r"(ok ? 8 : 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 4u * i),
+                       "l"(src + (ok ? static_cast<uint32_t>(o) : 0u)), "r"(ok ? 8 : 0)
                        : "memory");
         }
       } else {
-        const float* src = static_cast<const float*>(a.x) + base;
+        const char* src = reinterpret_cast<const char*>(static_cast<const float*>(a.x) + base);
         const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
         for (int i = lane; i < a.NP; i += 32) {
           const int o = off_s[i];
           const bool ok = plane_ok && (o >= 0);
           // src-size 0 => 4 bytes of zeros are written (the implicit padding); the source pointer stays in range
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? o : 0)),
-                       "r"(ok ? 4 : 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * i),
+                       "l"(src + (ok ? static_cast<uint32_t>(o) : 0u)), "r"(ok ? 4 : 0)
                        : "memory");
         }
       }
     }
     // weights: contiguous [kCC][27][32] slab out of wt[Ci][27][CoPad], 16 bytes per copy
     const uint32_t w0 = static_cast<uint32_t>(__cvta_generic_to_shared(w_b));
+    const int rows_ok = (a.Ci - c0) * 27;  // rows (c, tap) of the slab that exist (the last chunk of Ci = 12k + r is short)
+    const float* wsrc = a.wt + static_cast<long long>(c0) * 27 * a.CoPad + co0;
     for (int idx = tid; idx < kCC * 27 * kCoT / 4; idx += kConvThreads) {
       const int co4 = idx & (kCoT / 4 - 1);
       const int r = idx >> 3;  // c*27 + tap
-      const int c = r / 27;
-      const bool ok = (c0 + c) < a.Ci;
-      const float* src = a.wt + (static_cast<long long>(ok ? c0 : 0) * 27 + (ok ? r : 0)) * a.CoPad + co0 + 4 * co4;
+      const bool ok = r < rows_ok;
+      const float* src = wsrc + (ok ? r * a.CoPad + 4 * co4 : 0);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(w0 + 16u * idx), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -186,28 +191,32 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
         const float* wp = w_b + (c * 27 + kt * 9) * kCoT + 8 * cg;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-          float in[2][8];
+          // the 6 + 6 input values a kh row needs, each duplicated into both halves of a register pair
+          float2 in2[2][6];
           {
             const float4 v0 = *reinterpret_cast<const float4*>(ip + kh * a.Wps);
-            const float4 v1 = *reinterpret_cast<const float4*>(ip + kh * a.Wps + 4);
+            const float2 v1 = *reinterpret_cast<const float2*>(ip + kh * a.Wps + 4);
             const float4 v2 = *reinterpret_cast<const float4*>(ip + kh * a.Wps + 256);
-            const float4 v3 = *reinterpret_cast<const float4*>(ip + kh * a.Wps + 260);
-            in[0][0] = v0.x; in[0][1] = v0.y; in[0][2] = v0.z; in[0][3] = v0.w;
-            in[0][4] = v1.x; in[0][5] = v1.y; in[0][6] = v1.z; in[0][7] = v1.w;
-            in[1][0] = v2.x; in[1][1] = v2.y; in[1][2] = v2.z; in[1][3] = v2.w;
-            in[1][4] = v3.x; in[1][5] = v3.y; in[1][6] = v3.z; in[1][7] = v3.w;
+            const float2 v3 = *reinterpret_cast<const float2*>(ip + kh * a.Wps + 260);
+            in2[0][0] = make_float2(v0.x, v0.x); in2[0][1] = make_float2(v0.y, v0.y);
+            in2[0][2] = make_float2(v0.z, v0.z); in2[0][3] = make_float2(v0.w, v0.w);
+            in2[0][4] = make_float2(v1.x, v1.x); in2[0][5] = make_float2(v1.y, v1.y);
+            in2[1][0] = make_float2(v2.x, v2.x); in2[1][1] = make_float2(v2.y, v2.y);
+            in2[1][2] = make_float2(v2.z, v2.z); in2[1][3] = make_float2(v2.w, v2.w);
+            in2[1][4] = make_float2(v3.x, v3.x); in2[1][5] = make_float2(v3.y, v3.y);
           }
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const float4 w0 = *reinterpret_cast<const float4*>(wp + (kh * 3 + kw) * kCoT);
             const float4 w1 = *reinterpret_cast<const float4*>(wp + (kh * 3 + kw) * kCoT + 4);
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                                  make_float2(w1.z, w1.w)};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                acc[j][i] = fmaf(wv[j], in[0][i + kw], acc[j][i]);
-                acc[j][4 + i] = fmaf(wv[j], in[1][i + kw], acc[j][4 + i]);
+                acc2[j][i] = __ffma2_rn(wv[j], in2[0][i + kw], acc2[j][i]);
+                acc2[j][4 + i] = __ffma2_rn(wv[j], in2[1][i + kw], acc2[j][4 + i]);
               }
             }
           }
@@ -234,26 +243,38 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
 
   // ---- epilogue ----
   const long long oplane = static_cast<long long>(a.Ho) * a.Wo;
+  const long long ochan = static_cast<long long>(a.To) * oplane;
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const int q = q0 + g * 256 + 4 * tp;
     const int ho = q / a.Wps;
     const int wo0 = q - ho * a.Wps;
     if (ho >= a.Ho) continue;
+    const long long obase0 =
+        ((static_cast<long long>(b) * a.Co + co0 + 8 * cg) * a.To + to) * oplane + static_cast<long long>(ho) * a.Wo + wo0;
+    // data gradient: all 32 ReLU-mask loads of the group are issued before the first store (predicated, no branches between
+    // them), so their latency is paid once per group instead of once per output row
+    float mv[8][4];
+    if (a.mask) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          mv[j][i] = (co0 + 8 * cg + j < a.Co && wo0 + i < a.Wo) ? __ldg(a.mask + obase0 + j * ochan + i) : 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int co = co0 + 8 * cg + j;
       if (co >= a.Co) continue;
       const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
-      const long long obase = ((static_cast<long long>(b) * a.Co + co) * a.To + to) * oplane + static_cast<long long>(ho) * a.Wo;
+      const long long obase = obase0 + j * ochan;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int wo = wo0 + i;
-        if (wo < a.Wo) {
-          float v = acc[j][g * 4 + i] + bv;
+        if (wo0 + i < a.Wo) {
+          float v = ((j & 1) ? acc2[j >> 1][g * 4 + i].y : acc2[j >> 1][g * 4 + i].x) + bv;
           if (a.relu) v = (v < 0.f) ? 0.f : v;
-          if (a.mask) v = (__ldg(a.mask + obase + wo) > 0.f) ? v : 0.f;
-          a.y[obase + wo] = v;
+          if (a.mask) v = (mv[j][i] > 0.f) ? v : 0.f;
+          a.y[obase + i] = v;
         }
       }
     }

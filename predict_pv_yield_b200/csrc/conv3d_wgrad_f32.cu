@@ -10,6 +10,7 @@
 // Positions use the same flattened-pitch trick as the forward kernel (q = ho*Wps + wo): taps are plain
 // offsets kh*Wps + kw into a contiguous staged window; gz is zero-filled at the wrap columns.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pvb {
 
@@ -33,6 +34,68 @@ struct WgradArgs {
   int pad_t;          // time padding of the layer (0 or 1): input plane to + kt - pad_t, zero outside [0, Ti)
   int pad_hw;         // spatial padding (0 or 1): staged position (hp, wp) is input (hp - pad_hw, wp - pad_hw), zero outside
 };
+
+// FMA work of one step (kWgQC positions) of one thread: 4 output channels (two PAIRS {2j, 2j+1}) x NKT*9 taps of one input
+// channel.  gp: this thread's two channel-pair rows of the staged gz ([pair][q][2], see stage_gz); xk[k]: its input-channel
+// row of time plane k.  The loop issues the packed fma.rn.f32x2 of sm_100 (SASS FFMA2: two IEEE fp32 FMAs per issue
+// slot, bit-identical to two fmaf) with the input value broadcast to both halves.
+template <int NKT>
+__device__ __forceinline__ void wgrad_fma_step(const float* __restrict__ gp, const float* const (&xk)[NKT], int Wps,
+                                               float2 (&acc2)[NKT * 9][2], float (&bacc)[4]) {
+#pragma unroll 1
+  for (int q = 0; q < kWgQC; q += 4) {
+    float2 gv2[2][4];  // [co pair j][pos i] = {gz[2j][i], gz[2j+1][i]}
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float4 u = *reinterpret_cast<const float4*>(gp + (2 * j) * kWgQC + 2 * q);      // positions q, q+1
+      const float4 v = *reinterpret_cast<const float4*>(gp + (2 * j) * kWgQC + 2 * q + 4);  // positions q+2, q+3
+      gv2[j][0] = make_float2(u.x, u.y); gv2[j][1] = make_float2(u.z, u.w);
+      gv2[j][2] = make_float2(v.x, v.y); gv2[j][3] = make_float2(v.z, v.w);
+      bacc[2 * j] += (u.x + u.z) + (v.x + v.z);
+      bacc[2 * j + 1] += (u.y + u.w) + (v.y + v.w);
+    }
+#pragma unroll
+    for (int k = 0; k < NKT; ++k) {
+      const float* xp = xk[k] + q;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const float4 v0 = *reinterpret_cast<const float4*>(xp + kh * Wps);
+        const float2 v1 = *reinterpret_cast<const float2*>(xp + kh * Wps + 4);
+        const float xv[6] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y};
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              acc2[k * 9 + kh * 3 + kw][j] =
+                  __ffma2_rn(gv2[j][i], make_float2(xv[i + kw], xv[i + kw]), acc2[k * 9 + kh * 3 + kw][j]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// this thread's partial: dw[4 cog + j][ci][kt][kh][kw] (+ db from the ci == 0, first-kt thread)
+template <int NKT>
+__device__ __forceinline__ void wgrad_write_partial(const WgradArgs& a, int cog, int ci, int kt0, bool writes_bias,
+                                                    const float2 (&acc2)[NKT * 9][2], const float (&bacc)[4]) {
+  float* part = a.partial + static_cast<long long>(blockIdx.x) * (static_cast<long long>(a.Co) * a.Ci * 27 + a.Co);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int co = 4 * cog + j;
+    if (co >= a.Co) continue;
+#pragma unroll
+    for (int k = 0; k < NKT; ++k) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        part[(static_cast<long long>(co) * a.Ci + ci) * 27 + (kt0 + k) * 9 + t] =
+            (j & 1) ? acc2[k * 9 + t][j >> 1].y : acc2[k * 9 + t][j >> 1].x;
+    }
+    if (writes_bias) part[static_cast<long long>(a.Co) * a.Ci * 27 + co] = bacc[j];
+  }
+}
 
 // Work is ordered (b, tile, to) with `to` fastest: a CTA walks DOWN the time axis of one (sample, position tile)
 // column, so consecutive steps share two of their three input planes.  Planes live in a 4-slot ring filled by
@@ -58,11 +121,12 @@ __global__ void __launch_bounds__(KTS == 1 ? 256 : 384, KTS == 1 ? 1 : 2) conv3d
     ktg = r / a.ncog;
   }
 
-  float acc[NKT * 9][4];
+  // accumulators as output-channel PAIRS {2j, 2j+1} (wgrad_fma_step)
+  float2 acc2[NKT * 9][2];
 #pragma unroll
   for (int t = 0; t < NKT * 9; ++t)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+    for (int j = 0; j < 2; ++j) acc2[t][j] = make_float2(0.f, 0.f);
   float bacc[4] = {0.f, 0.f, 0.f, 0.f};
 
   const long long g_begin = a.total_steps * blockIdx.x / gridDim.x;
@@ -108,28 +172,21 @@ __global__ void __launch_bounds__(KTS == 1 ? 256 : 384, KTS == 1 ? 1 : 2) conv3d
       }
     }
   };
-  // stage gz of output time `to` into buffer `buf`: [co][q], zero at the wrap columns / beyond the plane
+  // stage gz of output time `to` into buffer `buf`: channel PAIRS interleaved, [co / 2][q][2], so that one LDS.128 of the
+  // FMA loop delivers the {co, co + 1} operand pairs of two positions already aligned for the packed FMA; zero at the wrap
+  // columns / beyond the plane
   auto stage_gz = [&](int b, int to, int buf) {
     for (int p = warp; p < 4 * a.ncog; p += nwarp) {
-      float* dst = gz_s + (buf * 4 * a.ncog + p) * kWgQC;
+      float* dst = gz_s + (buf * 4 * a.ncog + (p & ~1)) * kWgQC + (p & 1);
       const bool ok_p = p < a.Co;
       const float* src = a.gz + ((static_cast<long long>(b) * a.Co + (ok_p ? p : 0)) * a.To + to) * gplane;
       const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
-      if (a.pairs) {
-        const int i = 2 * lane;  // kWgQC == 64
+      for (int i = lane; i < kWgQC; i += 32) {
         const int o = goff_s[i];
         const bool ok = ok_p && (o >= 0);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? o : 0)),
-                     "r"(ok ? 8 : 0)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 8u * i), "l"(src + (ok ? o : 0)),
+                     "r"(ok ? 4 : 0)
                      : "memory");
-      } else {
-        for (int i = lane; i < kWgQC; i += 32) {
-          const int o = goff_s[i];
-          const bool ok = ok_p && (o >= 0);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * i), "l"(src + (ok ? o : 0)),
-                       "r"(ok ? 4 : 0)
-                       : "memory");
-        }
       }
     }
   };
@@ -183,35 +240,7 @@ __global__ void __launch_bounds__(KTS == 1 ? 256 : 384, KTS == 1 ? 1 : 2) conv3d
           const int kt = (KTS == 1) ? k : ktg;
           xk[k] = x_s + (((s + kt) & 3) * a.Ci + ci) * a.NPs;
         }
-#pragma unroll 1
-        for (int q = 0; q < kWgQC; q += 4) {
-          float gv[4][4];  // [co j][pos i]
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 v = *reinterpret_cast<const float4*>(gp + j * kWgQC + q);
-            gv[j][0] = v.x; gv[j][1] = v.y; gv[j][2] = v.z; gv[j][3] = v.w;
-            bacc[j] += (v.x + v.y) + (v.z + v.w);
-          }
-#pragma unroll
-          for (int k = 0; k < NKT; ++k) {
-            const float* xp = xk[k] + q;
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              const float4 v0 = *reinterpret_cast<const float4*>(xp + kh * a.Wps);
-              const float2 v1 = *reinterpret_cast<const float2*>(xp + kh * a.Wps + 4);
-              const float xv[6] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y};
-#pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    acc[k * 9 + kh * 3 + kw][j] = fmaf(gv[j][i], xv[i + kw], acc[k * 9 + kh * 3 + kw][j]);
-                }
-              }
-            }
-          }
-        }
+wgrad_fma_step<NKT>(gp, xk, a.Wps, acc2, bacc);
       }
       __syncthreads();  // slot (s & 3) and gz buffer (s & 1) may be overwritten by the next prefetch
     }
@@ -219,22 +248,204 @@ __global__ void __launch_bounds__(KTS == 1 ? 256 : 384, KTS == 1 ? 1 : 2) conv3d
   }
 
   // ---- write this CTA's partial ----
-  if (active) {
-    float* part = a.partial + static_cast<long long>(blockIdx.x) * (static_cast<long long>(a.Co) * a.Ci * 27 + a.Co);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = 4 * cog + j;
-      if (co >= a.Co) continue;
-#pragma unroll
-      for (int k = 0; k < NKT; ++k) {
-        const int kt = (KTS == 1) ? k : ktg;
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-          part[(static_cast<long long>(co) * a.Ci + ci) * 27 + kt * 9 + t] = acc[k * 9 + t][j];
-      }
-      if (ci == 0 && ktg == 0) part[static_cast<long long>(a.Co) * a.Ci * 27 + co] = bacc[j];
+  if (active) wgrad_write_partial<NKT>(a, cog, ci, (KTS == 1) ? 0 : ktg, ci == 0 && ktg == 0, acc2, bacc);
+}
+
+// ---- warp-specialised variant (wide layers, fp32 input, even widths) -----------------------------------------------
+// ncu of the kernel above (profiles/ncu_fp32_r01c.txt): with the packed FMA the loop is no longer issue bound, but every
+// warp also runs the staging code between two barriers of every step, and the FMA pipe idles meanwhile (23 % of the stall
+// samples outside the FMA loop, pipe 65 % busy).  Here the 8 consumer warps ONLY run FMAs; four extra PRODUCER warps (one
+// per scheduler, so that every scheduler carries the same load: with a single producer warp its scheduler was 13 % slower
+// and the other three waited for it at every step) issue every cp.async of the CTA and run up to kWsD steps ahead:
+//   * per step a "package" = the step's gz tile + its NEW input planes (3 at the start of a run, else 1);
+//   * full[d] / empty[d] mbarriers per package slot d = n % kWsD (n = global step counter of the CTA): the 128 producer
+//     lanes arrive on full[d] through cp.async.mbarrier.arrive.noinc (fires when the lane's copies have landed), each
+//     consumer warp arrives on empty[d] after its FMA loop;
+//   * input planes live in a ring of kWsR = 3 * kWsD slots addressed by a running position: the planes of the (at most
+//     kWsD - 1) steps still in flight plus the package being loaded span at most 3 * kWsD positions, so a slot is never
+//     overwritten while a consumer may still read it -- also across run boundaries, which removes the exposed
+//     three-plane prologue of every run;
+//   * copy offsets of a lane are the same for every channel and plane of a run: kept in registers, no tables.  Input
+//     positions outside the plane (wrap columns, rows past the end) are only ever multiplied by zero-filled gz entries,
+//     so they need no zero fill, only finite contents: the ring is zeroed once at kernel start and their copies are
+//     redirected to a dummy pair in the padding of the row (branch-free producer loop).
+constexpr int kWsD = 2;         // packages in flight
+constexpr int kWsR = 3 * kWsD;  // input plane ring slots
+constexpr int kWsK = 6;         // 8-byte copies per lane and channel row: NP <= 64 * kWsK
+constexpr int kWsProd = 4;      // producer warps
+constexpr int kWsMaxThreads = 256 + 32 * kWsProd;
+
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(const WgradArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [kWsD]
+  uint64_t* empty = full + kWsD;                       // [kWsD]
+  float* x_s = smem + 16;                              // [kWsR][Ci][NPs]   (64 bytes reserved for the barriers)
+  float* gz_s = x_s + kWsR * a.Ci * a.NPs;             // [kWsD][4*ncog / 2][kWgQC][2]
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int ncons = blockDim.x - 32 * kWsProd;  // consumer threads (a multiple of 32); the last kWsProd warps produce
+  if (tid == 0) {
+    for (int i = 0; i < kWsD; ++i) {
+      tc::mbar_init(full + i, 32 * kWsProd);
+      tc::mbar_init(empty + i, ncons / 32);
     }
+    tc::fence_barrier_init();
   }
+  for (int i = tid; i < kWsR * a.Ci * a.NPs; i += blockDim.x) x_s[i] = 0.f;  // finite contents everywhere (see above)
+  __syncthreads();
+
+  const long long g_begin = a.total_steps * blockIdx.x / gridDim.x;
+  const long long g_end = a.total_steps * (blockIdx.x + 1) / gridDim.x;
+  uint32_t n = 0;  // global step counter: package slot n % kWsD, barrier phase (n / kWsD) & 1
+  int pos = 0;     // ring slot of the kt = 0 plane of the current step
+  int next = 0;    // ring slot of the first plane of the next run
+
+  if (tid >= ncons) {
+    // =========================== producer warps ===========================
+    const int pw = (tid - ncons) >> 5;  // this warp stages input channels / gz rows pw, pw + kWsProd, ...
+    const long long xplane = static_cast<long long>(a.Hi) * a.Wi;
+    const long long gplane = static_cast<long long>(a.Ho) * a.Wo;
+    const uint32_t x_u32 = tc::smem_u32(x_s), gz_u32 = tc::smem_u32(gz_s);
+    const uint32_t row_bytes = static_cast<uint32_t>(a.NPs) * 4u;
+    const uint32_t slot_bytes = static_cast<uint32_t>(a.Ci) * row_bytes;
+    const long long x_cstride = static_cast<long long>(a.Ti) * xplane * 4;  // bytes between channels of x
+    const long long g_cstride = static_cast<long long>(a.To) * gplane * 4;  // bytes between channels of gz
+    const int nk = (a.NP + 63) >> 6;  // copies per lane and row
+    uint32_t xo[kWsK];  // byte offset inside an input plane of staged positions 2*lane + 64k (+1); 0 for the dummy copy
+    uint32_t xd[kWsK];  // byte offset inside the shared-memory row; the row padding (float NP) for the dummy copy
+    uint32_t go[2];     // byte offset inside a gz plane of positions lane + 32k
+    uint32_t gs[2];     // 4 or 0 (zero fill at the wrap columns / beyond the plane: these MUST be zero)
+
+    auto stage_x = [&](int b, int ti, int slot) {
+      ti -= a.pad_t;
+      uint32_t dst = x_u32 + static_cast<uint32_t>(slot) * slot_bytes;
+      if (ti < 0 || ti >= a.Ti) {  // a plane of the time padding: zero-fill copies over the whole slot
+        for (uint32_t j = 8u * (pw * 32 + lane); j < slot_bytes; j += 256u * kWsProd)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, 0;" ::"r"(dst + j), "l"(a.x) : "memory");
+        return;
+      }
+      dst += pw * row_bytes;
+      const char* src = reinterpret_cast<const char*>(static_cast<const float*>(a.x) +
+                                                      (static_cast<long long>(b) * a.Ci * a.Ti + ti) * xplane) +
+                        pw * x_cstride;
+      for (int c = pw; c < a.Ci; c += kWsProd) {
+#pragma unroll
+        for (int k = 0; k < kWsK; ++k) {
+          if (k < nk)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + xd[k]), "l"(src + xo[k]) : "memory");
+        }
+        dst += kWsProd * row_bytes;
+        src += kWsProd * x_cstride;
+      }
+    };
+    // gz of output time `to`: channel PAIRS interleaved, [co / 2][q][2], so that one LDS.128 of the FMA loop delivers the
+    // {co, co + 1} operand pairs of two positions already aligned for the packed FMA
+    auto stage_gz = [&](int b, int to, int d) {
+      const uint32_t dst = gz_u32 + static_cast<uint32_t>(d * 4 * a.ncog * kWgQC) * 4u + 8u * lane;
+      const char* src = reinterpret_cast<const char*>(a.gz + (static_cast<long long>(b) * a.Co * a.To + to) * gplane);
+      for (int p = pw; p < 4 * a.ncog; p += kWsProd) {
+        const bool ok_p = p < a.Co;
+        const uint32_t dp = dst + static_cast<uint32_t>((p & ~1) * kWgQC + (p & 1)) * 4u;
+        const char* sp = src + (ok_p ? p : 0) * g_cstride;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dp + 256u * k), "l"(sp + go[k]),
+                       "r"(ok_p ? gs[k] : 0u)
+                       : "memory");
+      }
+    };
+
+    for (long long g = g_begin; g < g_end;) {
+      const long long col = g / a.To;
+      const int t0 = static_cast<int>(g - col * a.To);
+      const int tile = static_cast<int>(col % a.tiles_per_plane);
+      const int b = static_cast<int>(col / a.tiles_per_plane);
+      const long long left = g_end - g;
+      const int nstep = static_cast<int>(left < (a.To - t0) ? left : (a.To - t0));
+      const int q0 = tile * kWgQC;
+      // this lane's copy offsets for the run (pad_hw == 0 and Wi even: a pair never straddles a row)
+#pragma unroll
+      for (int k = 0; k < kWsK; ++k) {
+        const int i = 2 * lane + 64 * k;
+        const int p = q0 + i;
+        const int hi = p / a.Wps, wi = p - hi * a.Wps;
+        const bool ok = i < a.NP && hi < a.Hi && wi < a.Wi;
+        xo[k] = ok ? static_cast<uint32_t>(hi * a.Wi + wi) * 4u : 0u;
+        xd[k] = ok ? 4u * i : 4u * a.NP;
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int p = q0 + lane + 32 * k;
+        const int ho = p / a.Wps, wo = p - ho * a.Wps;
+        const bool ok = ho < a.Ho && wo < a.Wo;
+        go[k] = ok ? static_cast<uint32_t>(ho * a.Wo + wo) * 4u : 0u;
+        gs[k] = ok ? 4u : 0u;
+      }
+      for (int s = 0; s < nstep; ++s, ++n) {
+        const int d = n % kWsD;
+        tc::mbar_wait(empty + d, ((n / kWsD) & 1u) ^ 1u);  // step n - kWsD consumed (passes at once for the first kWsD)
+        if (s == 0) {
+          pos = next;
+          stage_x(b, t0, pos);
+          stage_x(b, t0 + 1, (pos + 1) % kWsR);
+          stage_x(b, t0 + 2, (pos + 2) % kWsR);
+        } else {
+          pos = (pos + 1) % kWsR;
+          stage_x(b, t0 + s + 2, (pos + 2) % kWsR);
+        }
+        next = (pos + 3) % kWsR;
+        stage_gz(b, t0 + s, d);
+        cp_async_arrive_noinc(full + d);
+      }
+      g += nstep;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    return;
+  }
+
+  // =========================== consumer warps ===========================
+  const int item = blockIdx.y * ncons + tid;
+  const bool active = item < a.items;
+  int ci = 0, cog = 0;
+  if (active) {
+    ci = item % a.Ci;
+    cog = item / a.Ci;
+  }
+  float2 acc2[27][2];
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc2[t][j] = make_float2(0.f, 0.f);
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (long long g = g_begin; g < g_end;) {
+    const long long col = g / a.To;
+    const int t0 = static_cast<int>(g - col * a.To);
+    const long long left = g_end - g;
+    const int nstep = static_cast<int>(left < (a.To - t0) ? left : (a.To - t0));
+    for (int s = 0; s < nstep; ++s, ++n) {
+      const int d = n % kWsD;
+      pos = (s == 0) ? next : (pos + 1) % kWsR;
+      next = (pos + 3) % kWsR;
+      tc::mbar_wait(full + d, (n / kWsD) & 1u);
+      if (active) {
+        const float* gp = gz_s + (d * 4 * a.ncog + 4 * cog) * kWgQC;
+        const float* xk[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xk[k] = x_s + (((pos + k) % kWsR) * a.Ci + ci) * a.NPs;
+        wgrad_fma_step<3>(gp, xk, a.Wps, acc2, bacc);
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(empty + d);  // this warp is done with package slot d (and the plane it retires)
+    }
+    g += nstep;
+  }
+  if (active) wgrad_write_partial<3>(a, cog, ci, 0, ci == 0, acc2, bacc);
 }
 
 // dw[i] = sum over CTAs (fixed order) ; the last Co entries are db
@@ -248,6 +459,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   if (i < n_w) dw[i] = s;
   else if (db) db[i - n_w] = s;
 }
+
+// PVB200_WGRAD_WS=0 in the environment selects the non-specialised kernel (A/B measurements, tools/bench_kernels.py)
+static const bool g_wgrad_ws_enabled = [] {
+  const char* e = getenv("PVB200_WGRAD_WS");
+  return !(e && e[0] == '0');
+}();
 
 template <bool kI16, int KTS>
 static int launch_wgrad(WgradArgs a, int grid_x, int grid_y, int threads, size_t smem, cudaStream_t stream) {
@@ -325,7 +542,16 @@ int pvb200_conv3d_wgrad_f32_pad(const void* x, int x_is_i16, const float* mean, 
   PVB_REQUIRE(smem <= 227 * 1024, "conv3d_wgrad: Cin=%d, width %d needs %zu B of shared memory (> 227 KB)", Cin, Wi, smem);
   cudaStream_t st = as_stream(stream);
   int rc;
-  if (x_is_i16)
+  // wide layers with fp32 input and even widths: warp-specialised kernel (producer warp + FMA-only consumer warps)
+  const size_t smem_ws = 64 + (static_cast<size_t>(kWsR) * Cin * a.NPs + kWsD * 4 * a.ncog * kWgQC) * sizeof(float);
+  const bool use_ws = kts == 1 && !x_is_i16 && pad_hw == 0 && Wi % 2 == 0 && reinterpret_cast<uintptr_t>(x) % 8 == 0 &&
+                      a.NP <= 64 * kWsK && smem_ws <= 227 * 1024 && g_wgrad_ws_enabled;
+  if (use_ws) {
+    PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+    conv3d_wgrad_f32_ws_kernel<<<dim3((unsigned)gx, grid_y), threads + 32 * kWsProd, smem_ws, st>>>(a);
+    PVB_LAUNCHED("conv3d_wgrad_f32_ws");
+    rc = PVB200_OK;
+  } else if (x_is_i16)
     rc = (kts == 1) ? launch_wgrad<true, 1>(a, (int)gx, grid_y, threads, smem, st)
                     : launch_wgrad<true, 3>(a, (int)gx, grid_y, threads, smem, st);
   else

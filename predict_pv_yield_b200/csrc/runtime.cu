@@ -79,6 +79,22 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(float* sink, int iters, 
   for (int i = 0; i < 16; ++i) s += c[i];
   if (s == 123.456f) sink[0] = s;  // never true in practice; keeps the chains alive
 }
+
+// the same chains issued as the packed fma.rn.f32x2 of sm_100 (SASS FFMA2): 16 independent pair chains per thread
+__global__ void __launch_bounds__(256) fma2_probe_kernel(float* sink, int iters, float a, float b) {
+  float2 c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = make_float2(static_cast<float>(threadIdx.x + i), static_cast<float>(threadIdx.x - i));
+  const float2 a2 = make_float2(a, a * 0.5f), b2 = make_float2(b, b * 0.5f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = __ffma2_rn(c[i], a2, b2);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i].x + c[i].y;
+  if (s == 123.456f) sink[0] = s;
+}
 }  // namespace pvb
 
 extern "C" int pvb200_probe_fp32_fma(float* sink, int iters, double* flops_out, pvb200_stream_t stream) {
@@ -90,5 +106,17 @@ extern "C" int pvb200_probe_fp32_fma(float* sink, int iters, double* flops_out, 
   fma_probe_kernel<<<grid, 256, 0, as_stream(stream)>>>(sink, iters, 0.999f, 0.001f);
   PVB_LAUNCHED("fma_probe");
   *flops_out = 2.0 * 16.0 * static_cast<double>(iters) * 256.0 * grid;
+  return PVB200_OK;
+}
+
+extern "C" int pvb200_probe_fp32_fma2(float* sink, int iters, double* flops_out, pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(sink && flops_out && iters > 0, "probe_fp32_fma2: bad argument");
+  const int sms = sm_count();
+  PVB_REQUIRE(sms > 0, "probe_fp32_fma2: no CUDA device");
+  const int grid = sms * 8;
+  fma2_probe_kernel<<<grid, 256, 0, as_stream(stream)>>>(sink, iters, 0.999f, 0.001f);
+  PVB_LAUNCHED("fma2_probe");
+  *flops_out = 2.0 * 32.0 * static_cast<double>(iters) * 256.0 * grid;
   return PVB200_OK;
 }

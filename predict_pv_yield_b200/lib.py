@@ -46,6 +46,7 @@ SIGNATURES = {
     "pvb200_reset_launch_count": (None, []),
     "pvb200_sm_count": (c_int, []),
     "pvb200_probe_fp32_fma": (c_int, [c_void_p, c_int, C.POINTER(C.c_double), c_void_p]),
+    "pvb200_probe_fp32_fma2": (c_int, [c_void_p, c_int, C.POINTER(C.c_double), c_void_p]),
     "pvb200_sat_normalise_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p]),
     "pvb200_sat_normalise_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p]),
     "pvb200_conv3d_workspace_bytes": (c_size_t, [c_int, c_int]),
