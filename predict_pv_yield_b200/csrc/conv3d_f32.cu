@@ -21,6 +21,8 @@
 //     broadcast).
 //   * epilogue fused: bias + ReLU (forward) or the ReLU mask of the layer below (data gradient).
 //   * data gradient = the same kernel with P = 2, taps flipped and the weight roles swapped.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pvb {
@@ -178,7 +180,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  auto compute = [&](int buf, int cmax) {
+  // NG = position groups of the thread that hold real outputs: 2, or 1 when the second half of the (last) tile of a plane
+  // lies beyond the plane -- its FMAs are skipped (CTA-uniform)
+  auto compute = [&](int buf, int cmax, auto ng_tag) {
+    constexpr int NG = decltype(ng_tag)::value;
     const float* in_b = in_s + buf * (kCC * 3 * a.NP);
     const float* w_b = w_s + buf * (kCC * 27 * kCoT);
     for (int c = 0; c < cmax; ++c) {
@@ -196,14 +201,16 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
           {
             const float4 v0 = *reinterpret_cast<const float4*>(ip + kh * a.Wps);
             const float2 v1 = *reinterpret_cast<const float2*>(ip + kh * a.Wps + 4);
-            const float4 v2 = *reinterpret_cast<const float4*>(ip + kh * a.Wps + 256);
-            const float2 v3 = *reinterpret_cast<const float2*>(ip + kh * a.Wps + 260);
             in2[0][0] = make_float2(v0.x, v0.x); in2[0][1] = make_float2(v0.y, v0.y);
             in2[0][2] = make_float2(v0.z, v0.z); in2[0][3] = make_float2(v0.w, v0.w);
             in2[0][4] = make_float2(v1.x, v1.x); in2[0][5] = make_float2(v1.y, v1.y);
-            in2[1][0] = make_float2(v2.x, v2.x); in2[1][1] = make_float2(v2.y, v2.y);
-            in2[1][2] = make_float2(v2.z, v2.z); in2[1][3] = make_float2(v2.w, v2.w);
-            in2[1][4] = make_float2(v3.x, v3.x); in2[1][5] = make_float2(v3.y, v3.y);
+            if (NG == 2) {
+              const float4 v2 = *reinterpret_cast<const float4*>(ip + kh * a.Wps + 256);
+              const float2 v3 = *reinterpret_cast<const float2*>(ip + kh * a.Wps + 260);
+              in2[1][0] = make_float2(v2.x, v2.x); in2[1][1] = make_float2(v2.y, v2.y);
+              in2[1][2] = make_float2(v2.z, v2.z); in2[1][3] = make_float2(v2.w, v2.w);
+              in2[1][4] = make_float2(v3.x, v3.x); in2[1][5] = make_float2(v3.y, v3.y);
+            }
           }
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 acc2[j][i] = __ffma2_rn(wv[j], in2[0][i + kw], acc2[j][i]);
-                acc2[j][4 + i] = __ffma2_rn(wv[j], in2[1][i + kw], acc2[j][4 + i]);
+                if (NG == 2) acc2[j][4 + i] = __ffma2_rn(wv[j], in2[1][i + kw], acc2[j][4 + i]);
               }
             }
           }
@@ -227,6 +234,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
 
   // ---- main loop: 2-stage software pipeline over chunks of kCC input channels ----
   const int nchunk = (a.Ci + kCC - 1) / kCC;
+  const bool half_tile = q0 + kQT / 2 >= (a.Ho - 1) * a.Wps + a.Wo;  // positions q0 + 256.. are all outside the plane
   __syncthreads();  // off_s visible
   stage(0, 0);
   for (int k = 0; k < nchunk; ++k) {
@@ -237,7 +245,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3d_direct_f32_kernel(cons
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();  // chunk k landed for every thread
-    compute(k & 1, min(kCC, a.Ci - k * kCC));
+    if (half_tile)
+      compute(k & 1, min(kCC, a.Ci - k * kCC), std::integral_constant<int, 1>());
+    else
+      compute(k & 1, min(kCC, a.Ci - k * kCC), std::integral_constant<int, 2>());
     __syncthreads();  // buffer k&1 may be overwritten by the stage issued in the next iteration
   }
 

@@ -33,6 +33,7 @@ struct WgradArgs {
   int pairs;          // Wi even and 8-byte aligned tensors: stage two positions per copy (never straddles a row)
   int pad_t;          // time padding of the layer (0 or 1): input plane to + kt - pad_t, zero outside [0, Ti)
   int pad_hw;         // spatial padding (0 or 1): staged position (hp, wp) is input (hp - pad_hw, wp - pad_hw), zero outside
+  int nprod;          // warp-specialised kernel: producer warps of the CTA (the last nprod warps)
 };
 
 // FMA work of one step (kWgQC positions) of one thread: 4 output channels (two PAIRS {2j, 2j+1}) x NKT*9 taps of one input
@@ -272,8 +273,8 @@ wgrad_fma_step<NKT>(gp, xk, a.Wps, acc2, bacc);
 constexpr int kWsD = 2;         // packages in flight
 constexpr int kWsR = 3 * kWsD;  // input plane ring slots
 constexpr int kWsK = 6;         // 8-byte copies per lane and channel row: NP <= 64 * kWsK
-constexpr int kWsProd = 4;      // producer warps
-constexpr int kWsMaxThreads = 256 + 32 * kWsProd;
+constexpr int kWsMaxProd = 4;   // producer warps of a wide layer (256 consumer threads); narrow layers use one
+constexpr int kWsMaxThreads = 256 + 32 * kWsMaxProd;
 
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
@@ -288,10 +289,11 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int ncons = blockDim.x - 32 * kWsProd;  // consumer threads (a multiple of 32); the last kWsProd warps produce
+  const int nprod = a.nprod;
+  const int ncons = blockDim.x - 32 * nprod;  // consumer threads (a multiple of 32); the last nprod warps produce
   if (tid == 0) {
     for (int i = 0; i < kWsD; ++i) {
-      tc::mbar_init(full + i, 32 * kWsProd);
+      tc::mbar_init(full + i, 32 * nprod);
       tc::mbar_init(empty + i, ncons / 32);
     }
     tc::fence_barrier_init();
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
 
   if (tid >= ncons) {
     // =========================== producer warps ===========================
-    const int pw = (tid - ncons) >> 5;  // this warp stages input channels / gz rows pw, pw + kWsProd, ...
+    const int pw = (tid - ncons) >> 5;  // this warp stages input channels / gz rows pw, pw + nprod, ...
     const long long xplane = static_cast<long long>(a.Hi) * a.Wi;
     const long long gplane = static_cast<long long>(a.Ho) * a.Wo;
     const uint32_t x_u32 = tc::smem_u32(x_s), gz_u32 = tc::smem_u32(gz_s);
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
       ti -= a.pad_t;
       uint32_t dst = x_u32 + static_cast<uint32_t>(slot) * slot_bytes;
       if (ti < 0 || ti >= a.Ti) {  // a plane of the time padding: zero-fill copies over the whole slot
-        for (uint32_t j = 8u * (pw * 32 + lane); j < slot_bytes; j += 256u * kWsProd)
+        for (uint32_t j = 8u * (pw * 32 + lane); j < slot_bytes; j += 256u * nprod)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 8, 0;" ::"r"(dst + j), "l"(a.x) : "memory");
         return;
       }
@@ -333,14 +335,14 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
       const char* src = reinterpret_cast<const char*>(static_cast<const float*>(a.x) +
                                                       (static_cast<long long>(b) * a.Ci * a.Ti + ti) * xplane) +
                         pw * x_cstride;
-      for (int c = pw; c < a.Ci; c += kWsProd) {
+      for (int c = pw; c < a.Ci; c += nprod) {
 #pragma unroll
         for (int k = 0; k < kWsK; ++k) {
           if (k < nk)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + xd[k]), "l"(src + xo[k]) : "memory");
         }
-        dst += kWsProd * row_bytes;
-        src += kWsProd * x_cstride;
+        dst += nprod * row_bytes;
+        src += nprod * x_cstride;
       }
     };
     // gz of output time `to`: channel PAIRS interleaved, [co / 2][q][2], so that one LDS.128 of the FMA loop delivers the
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
     auto stage_gz = [&](int b, int to, int d) {
       const uint32_t dst = gz_u32 + static_cast<uint32_t>(d * 4 * a.ncog * kWgQC) * 4u + 8u * lane;
       const char* src = reinterpret_cast<const char*>(a.gz + (static_cast<long long>(b) * a.Co * a.To + to) * gplane);
-      for (int p = pw; p < 4 * a.ncog; p += kWsProd) {
+      for (int p = pw; p < 4 * a.ncog; p += nprod) {
         const bool ok_p = p < a.Co;
         const uint32_t dp = dst + static_cast<uint32_t>((p & ~1) * kWgQC + (p & 1)) * 4u;
         const char* sp = src + (ok_p ? p : 0) * g_cstride;
@@ -542,13 +544,26 @@ int pvb200_conv3d_wgrad_f32_pad(const void* x, int x_is_i16, const float* mean, 
   PVB_REQUIRE(smem <= 227 * 1024, "conv3d_wgrad: Cin=%d, width %d needs %zu B of shared memory (> 227 KB)", Cin, Wi, smem);
   cudaStream_t st = as_stream(stream);
   int rc;
-  // wide layers with fp32 input and even widths: warp-specialised kernel (producer warp + FMA-only consumer warps)
+  // fp32 input and even widths: warp-specialised kernel (producer warps + FMA-only consumer warps), every consumer thread
+  // owning all 27 taps of (4 output channels, 1 input channel).  Wide layers: 256 consumer threads + 4 producer warps, one
+  // CTA per SM.  Narrow layers (conv0: 8 x 12 = 96 items): 3 consumer warps + 1 producer warp, two CTAs per SM.
+  const int ws_items = a.ncog * Cin;
+  const int ws_grid_y = ceil_div(ws_items, 256);
+  const int ws_cons = round_up(ceil_div(ws_items, ws_grid_y), 32);
+  const int ws_prod = ws_cons > 128 ? kWsMaxProd : 1;
   const size_t smem_ws = 64 + (static_cast<size_t>(kWsR) * Cin * a.NPs + kWsD * 4 * a.ncog * kWgQC) * sizeof(float);
-  const bool use_ws = kts == 1 && !x_is_i16 && pad_hw == 0 && Wi % 2 == 0 && reinterpret_cast<uintptr_t>(x) % 8 == 0 &&
+  const bool use_ws = !x_is_i16 && pad_hw == 0 && Wi % 2 == 0 && reinterpret_cast<uintptr_t>(x) % 8 == 0 &&
                       a.NP <= 64 * kWsK && smem_ws <= 227 * 1024 && g_wgrad_ws_enabled;
   if (use_ws) {
+    a.items = ws_items;
+    a.nprod = ws_prod;
+    // two CTAs per SM when both fit (registers: 168 x threads, shared memory)
+    long long wgx = (2 * (ws_cons + 32 * ws_prod) <= 384 && 2 * smem_ws <= 220 * 1024) ? 2LL * sms : sms;
+    if (wgx > kWgMaxCtas) wgx = kWgMaxCtas;
+    if (wgx > a.total_steps) wgx = a.total_steps;
+    gx = wgx;
     PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
-    conv3d_wgrad_f32_ws_kernel<<<dim3((unsigned)gx, grid_y), threads + 32 * kWsProd, smem_ws, st>>>(a);
+    conv3d_wgrad_f32_ws_kernel<<<dim3((unsigned)gx, ws_grid_y), ws_cons + 32 * ws_prod, smem_ws, st>>>(a);
     PVB_LAUNCHED("conv3d_wgrad_f32_ws");
     rc = PVB200_OK;
   } else if (x_is_i16)
