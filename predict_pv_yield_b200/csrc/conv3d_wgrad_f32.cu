@@ -78,6 +78,46 @@ __device__ __forceinline__ void wgrad_fma_step(const float* __restrict__ gp, con
   }
 }
 
+// The same step with the input window CARRIED across iterations: positions q+4 .. q+7 loaded for the tail of iteration q are
+// the head of iteration q+4, so each of the 9 (kt, kh) rows costs one LDS.128 per iteration instead of an LDS.128 + a
+// (2-way bank-conflicted) LDS.64 -- half the shared-memory wavefronts of the loop.  Needs 36 more live registers: only the
+// warp-specialised kernel, whose consumer warps take registers from the producer warps (setmaxnreg), can afford it.
+__device__ __forceinline__ void wgrad_fma_step_carry(const float* __restrict__ gp, const float* const (&xk)[3], int Wps,
+                                                     float2 (&acc2)[27][2], float (&bacc)[4]) {
+  float4 cur[9];
+#pragma unroll
+  for (int r = 0; r < 9; ++r) cur[r] = *reinterpret_cast<const float4*>(xk[r / 3] + (r % 3) * Wps);
+#pragma unroll 2
+  for (int q = 0; q < kWgQC; q += 4) {
+    float2 gv2[2][4];  // [co pair j][pos i] = {gz[2j][i], gz[2j+1][i]}
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float4 u = *reinterpret_cast<const float4*>(gp + (2 * j) * kWgQC + 2 * q);      // positions q, q+1
+      const float4 v = *reinterpret_cast<const float4*>(gp + (2 * j) * kWgQC + 2 * q + 4);  // positions q+2, q+3
+      gv2[j][0] = make_float2(u.x, u.y); gv2[j][1] = make_float2(u.z, u.w);
+      gv2[j][2] = make_float2(v.x, v.y); gv2[j][3] = make_float2(v.z, v.w);
+      bacc[2 * j] += (u.x + u.z) + (v.x + v.z);
+      bacc[2 * j + 1] += (u.y + u.w) + (v.y + v.w);
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      // the row is staged NP = kWgQC + 2 Wps + 8 floats long: q + 4 .. q + 7 stays inside for every q < kWgQC
+      const float4 nxt = *reinterpret_cast<const float4*>(xk[r / 3] + (r % 3) * Wps + q + 4);
+      const float xv[6] = {cur[r].x, cur[r].y, cur[r].z, cur[r].w, nxt.x, nxt.y};
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            acc2[r * 3 + kw][j] = __ffma2_rn(gv2[j][i], make_float2(xv[i + kw], xv[i + kw]), acc2[r * 3 + kw][j]);
+        }
+      }
+      cur[r] = nxt;
+    }
+  }
+}
+
 // this thread's partial: dw[4 cog + j][ci][kt][kh][kw] (+ db from the ci == 0, first-kt thread)
 template <int NKT>
 __device__ __forceinline__ void wgrad_write_partial(const WgradArgs& a, int cog, int ci, int kt0, bool writes_bias,
@@ -280,6 +320,9 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
+// kWide: the 8 consumer + 4 producer warp configuration of the wide layers (register reallocation + carried input window);
+// ptxas only honours setmaxnreg when it is unconditional, hence a template parameter and not a run-time flag
+template <bool kWide>
 __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(const WgradArgs a) {
   extern __shared__ __align__(16) float smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [kWsD]
@@ -307,7 +350,10 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
   int pos = 0;     // ring slot of the kt = 0 plane of the current step
   int next = 0;    // ring slot of the first plane of the next run
 
+  // register reallocation between the roles (wide layers: 8 consumer + 4 producer warps = three warpgroups of a CTA that
+  // was allocated 168 registers per thread): producers keep 56, consumers grow to 224 (8*224 + 4*56 = 12*168)
   if (tid >= ncons) {
+    if (kWide) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // =========================== producer warps ===========================
     const int pw = (tid - ncons) >> 5;  // this warp stages input channels / gz rows pw, pw + nprod, ...
     const long long xplane = static_cast<long long>(a.Hi) * a.Wi;
@@ -317,8 +363,10 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
     const uint32_t slot_bytes = static_cast<uint32_t>(a.Ci) * row_bytes;
     const long long x_cstride = static_cast<long long>(a.Ti) * xplane * 4;  // bytes between channels of x
     const long long g_cstride = static_cast<long long>(a.To) * gplane * 4;  // bytes between channels of gz
-    const int nk = (a.NP + 63) >> 6;  // copies per lane and row
-    uint32_t xo[kWsK];  // byte offset inside an input plane of staged positions 2*lane + 64k (+1); 0 for the dummy copy
+    const bool quad = (a.Wi % 4 == 0) && (reinterpret_cast<uintptr_t>(a.x) % 16 == 0);
+    const int epc = quad ? 4 : 2;                     // elements per copy
+    const int nk = (a.NP + 32 * epc - 1) / (32 * epc);  // copies per lane and row
+    uint32_t xo[kWsK];  // byte offset inside an input plane of staged positions epc * (lane + 32k) ..; 0 for the dummy copy
     uint32_t xd[kWsK];  // byte offset inside the shared-memory row; the row padding (float NP) for the dummy copy
     uint32_t go[2];     // byte offset inside a gz plane of positions lane + 32k
     uint32_t gs[2];     // 4 or 0 (zero fill at the wrap columns / beyond the plane: these MUST be zero)
@@ -335,6 +383,18 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
       const char* src = reinterpret_cast<const char*>(static_cast<const float*>(a.x) +
                                                       (static_cast<long long>(b) * a.Ci * a.Ti + ti) * xplane) +
                         pw * x_cstride;
+      if (quad) {  // 16-byte copies (Wi a multiple of 4): a quarter of the copy elements the LSU has to process
+        for (int c = pw; c < a.Ci; c += nprod) {
+#pragma unroll
+          for (int k = 0; k < kWsK / 2; ++k) {
+            if (k < nk)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + xd[k]), "l"(src + xo[k]) : "memory");
+          }
+          dst += nprod * row_bytes;
+          src += nprod * x_cstride;
+        }
+        return;
+      }
       for (int c = pw; c < a.Ci; c += nprod) {
 #pragma unroll
         for (int k = 0; k < kWsK; ++k) {
@@ -370,10 +430,10 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
       const long long left = g_end - g;
       const int nstep = static_cast<int>(left < (a.To - t0) ? left : (a.To - t0));
       const int q0 = tile * kWgQC;
-      // this lane's copy offsets for the run (pad_hw == 0 and Wi even: a pair never straddles a row)
+      // this lane's copy offsets for the run (pad_hw == 0 and Wi a multiple of epc: a copy never straddles a row)
 #pragma unroll
       for (int k = 0; k < kWsK; ++k) {
-        const int i = 2 * lane + 64 * k;
+        const int i = epc * (lane + 32 * k);
         const int p = q0 + i;
         const int hi = p / a.Wps, wi = p - hi * a.Wps;
         const bool ok = i < a.NP && hi < a.Hi && wi < a.Wi;
@@ -411,6 +471,7 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
   }
 
   // =========================== consumer warps ===========================
+  if (kWide) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
   const int item = blockIdx.y * ncons + tid;
   const bool active = item < a.items;
   int ci = 0, cog = 0;
@@ -440,7 +501,10 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
         const float* xk[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) xk[k] = x_s + (((pos + k) % kWsR) * a.Ci + ci) * a.NPs;
-        wgrad_fma_step<3>(gp, xk, a.Wps, acc2, bacc);
+        if (kWide)
+          wgrad_fma_step_carry(gp, xk, a.Wps, acc2, bacc);
+        else
+          wgrad_fma_step<3>(gp, xk, a.Wps, acc2, bacc);
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(empty + d);  // this warp is done with package slot d (and the plane it retires)
@@ -562,8 +626,13 @@ int pvb200_conv3d_wgrad_f32_pad(const void* x, int x_is_i16, const float* mean, 
     if (wgx > kWgMaxCtas) wgx = kWgMaxCtas;
     if (wgx > a.total_steps) wgx = a.total_steps;
     gx = wgx;
-    PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
-    conv3d_wgrad_f32_ws_kernel<<<dim3((unsigned)gx, ws_grid_y), ws_cons + 32 * ws_prod, smem_ws, st>>>(a);
+    if (ws_prod == kWsMaxProd && ws_cons == 256) {
+      PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+      conv3d_wgrad_f32_ws_kernel<true><<<dim3((unsigned)gx, ws_grid_y), ws_cons + 32 * ws_prod, smem_ws, st>>>(a);
+    } else {
+      PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+      conv3d_wgrad_f32_ws_kernel<false><<<dim3((unsigned)gx, ws_grid_y), ws_cons + 32 * ws_prod, smem_ws, st>>>(a);
+    }
     PVB_LAUNCHED("conv3d_wgrad_f32_ws");
     rc = PVB200_OK;
   } else if (x_is_i16)
