@@ -15,7 +15,7 @@
 namespace pvb {
 
 constexpr int kWgQC = 64;         // output positions staged per step
-constexpr int kWgMaxCtas = 320;   // upper bound on persistent CTAs (workspace sizing)
+constexpr int kWgMaxCtas = 448;   // upper bound on persistent CTAs (workspace sizing): 3 per SM on 148 SMs
 constexpr int kWgMaxCi = 64;
 
 struct WgradArgs {
@@ -320,10 +320,13 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
-// kWide: the 8 consumer + 4 producer warp configuration of the wide layers (register reallocation + carried input window);
-// ptxas only honours setmaxnreg when it is unconditional, hence a template parameter and not a run-time flag
-template <bool kWide>
-__global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(const WgradArgs a) {
+// kMode 1: the 8 consumer + 4 producer warp configuration of the wide layers (register reallocation + carried input
+// window; ptxas only honours setmaxnreg when it is unconditional, hence a template parameter and not a run-time flag).
+// kMode 2: narrow layers, <= 96 consumer threads + 1 producer warp (4 warps: two CTAs per SM put two warps on every
+// scheduler, whose 16 K registers then allow 255 per thread; a fifth warp would cap it at 168) without any
+// reallocation, so the carried window fits as well.  kMode 0: generic (168 registers, no carried window).
+template <int kMode>
+__device__ __forceinline__ void wgrad_ws_body(const WgradArgs& a) {
   extern __shared__ __align__(16) float smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [kWsD]
   uint64_t* empty = full + kWsD;                       // [kWsD]
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
   // register reallocation between the roles (wide layers: 8 consumer + 4 producer warps = three warpgroups of a CTA that
   // was allocated 168 registers per thread): producers keep 56, consumers grow to 224 (8*224 + 4*56 = 12*168)
   if (tid >= ncons) {
-    if (kWide) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (kMode == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // =========================== producer warps ===========================
     const int pw = (tid - ncons) >> 5;  // this warp stages input channels / gz rows pw, pw + nprod, ...
     const long long xplane = static_cast<long long>(a.Hi) * a.Wi;
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
   }
 
   // =========================== consumer warps ===========================
-  if (kWide) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+  if (kMode == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
   const int item = blockIdx.y * ncons + tid;
   const bool active = item < a.items;
   int ci = 0, cog = 0;
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
         const float* xk[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) xk[k] = x_s + (((pos + k) % kWsR) * a.Ci + ci) * a.NPs;
-        if (kWide)
+        if (kMode != 0)
           wgrad_fma_step_carry(gp, xk, a.Wps, acc2, bacc);
         else
           wgrad_fma_step<3>(gp, xk, a.Wps, acc2, bacc);
@@ -513,6 +516,11 @@ __global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(c
   }
   if (active) wgrad_write_partial<3>(a, cog, ci, 0, ci == 0, acc2, bacc);
 }
+
+// one entry point per mode: the launch bounds (and with them the register budget ptxas compiles for) differ
+__global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_kernel(const WgradArgs a) { wgrad_ws_body<0>(a); }
+__global__ void __launch_bounds__(kWsMaxThreads, 1) conv3d_wgrad_f32_ws_wide_kernel(const WgradArgs a) { wgrad_ws_body<1>(a); }
+__global__ void __launch_bounds__(128, 2) conv3d_wgrad_f32_ws_narrow_kernel(const WgradArgs a) { wgrad_ws_body<2>(a); }
 
 // dw[i] = sum over CTAs (fixed order) ; the last Co entries are db
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
@@ -530,6 +538,12 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 static const bool g_wgrad_ws_enabled = [] {
   const char* e = getenv("PVB200_WGRAD_WS");
   return !(e && e[0] == '0');
+}();
+
+// narrow layers: 2 = two CTAs per SM with the carried input window (default), 3 = three CTAs per SM without it, 0 = two without
+static const int g_wgrad_narrow_mode = [] {
+  const char* e = getenv("PVB200_WGRAD_NARROW");
+  return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;
 }();
 
 template <bool kI16, int KTS>
@@ -621,17 +635,25 @@ int pvb200_conv3d_wgrad_f32_pad(const void* x, int x_is_i16, const float* mean, 
   if (use_ws) {
     a.items = ws_items;
     a.nprod = ws_prod;
-    // two CTAs per SM when both fit (registers: 168 x threads, shared memory)
-    long long wgx = (2 * (ws_cons + 32 * ws_prod) <= 384 && 2 * smem_ws <= 220 * 1024) ? 2LL * sms : sms;
+    // CTAs per SM: as many as registers (168 x threads; 200 in the carried-window narrow mode, at most two) and shared memory allow
+    int per_sm = 1;
+    if (2 * (ws_cons + 32 * ws_prod) <= 384 && 2 * (smem_ws + 1024) <= 228 * 1024) per_sm = 2;
+    if (g_wgrad_narrow_mode == 3 && 3 * (ws_cons + 32 * ws_prod) <= 384 && 3 * (smem_ws + 1024) <= 228 * 1024) per_sm = 3;
+    long long wgx = static_cast<long long>(per_sm) * sms;
     if (wgx > kWgMaxCtas) wgx = kWgMaxCtas;
     if (wgx > a.total_steps) wgx = a.total_steps;
     gx = wgx;
+    const dim3 wgrid((unsigned)gx, ws_grid_y);
+    const int wthreads = ws_cons + 32 * ws_prod;
     if (ws_prod == kWsMaxProd && ws_cons == 256) {
-      PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
-      conv3d_wgrad_f32_ws_kernel<true><<<dim3((unsigned)gx, ws_grid_y), ws_cons + 32 * ws_prod, smem_ws, st>>>(a);
+      PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_ws_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+      conv3d_wgrad_f32_ws_wide_kernel<<<wgrid, wthreads, smem_ws, st>>>(a);
+    } else if (wthreads <= 128 && g_wgrad_narrow_mode == 2) {
+      PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_ws_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+      conv3d_wgrad_f32_ws_narrow_kernel<<<wgrid, wthreads, smem_ws, st>>>(a);
     } else {
-      PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
-      conv3d_wgrad_f32_ws_kernel<false><<<dim3((unsigned)gx, ws_grid_y), ws_cons + 32 * ws_prod, smem_ws, st>>>(a);
+      PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_f32_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+      conv3d_wgrad_f32_ws_kernel<<<wgrid, wthreads, smem_ws, st>>>(a);
     }
     PVB_LAUNCHED("conv3d_wgrad_f32_ws");
     rc = PVB200_OK;
