@@ -334,37 +334,49 @@ def run_ours(args):
         c1.record()
         torch.cuda.synchronize()
         h2d_gbs = 4 * host[0][0].numel() * 2 / (c0.elapsed_time(c1) * 1e-3) / 1e9
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        f0.record()
         # the public input pipeline: pinned int16 cubes, H2D of batch i+1 on a side stream under the compute of batch i.
         # Every step's loss is read back to the host (4-byte D2H into pinned memory); the host consumes it one step
         # late, the way a training loop logs, so the read does not drain the GPU queue between steps.
-        loss_pinned = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
-        loss_ready = [None, None]
-        losses_host = []
-        for i, batch in enumerate(DevicePrefetcher(host_batches(args.steps), dev)):
-            loss = step(batch, i)
-            loss_pinned[i & 1].copy_(loss.detach(), non_blocking=True)  # D2H read of the step's result
-            ev = torch.cuda.Event()
-            ev.record()
-            loss_ready[i & 1] = ev
-            if i > 0:
-                loss_ready[(i - 1) & 1].synchronize()
-                losses_host.append(float(loss_pinned[(i - 1) & 1]))
-        loss_ready[(args.steps - 1) & 1].synchronize()
-        losses_host.append(float(loss_pinned[(args.steps - 1) & 1]))
-        loss_host = losses_host[-1]
-        assert len(losses_host) == args.steps
-        f1.record()
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        ms2 = torch.tensor([max(f0.elapsed_time(f1), wall_ms)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        # The region synchronises with the host every step, so a single driver / scheduler hiccup of the box (observed:
+        # 25 ms once in 10 steps) moves a K = 10 step measurement by 10 %: it is run E2E_REPEATS times and the MEDIAN
+        # repetition is reported; every repetition is listed in "ms_per_step_all".
+        E2E_REPEATS = 3
+        reps = []
+        loss_host = None
+        for rep in range(E2E_REPEATS):
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            t0 = time.perf_counter()
+            f0.record()
+            loss_pinned = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+            loss_ready = [None, None]
+            losses_host = []
+            for i, batch in enumerate(DevicePrefetcher(host_batches(args.steps), dev)):
+                loss = step(batch, i)
+                loss_pinned[i & 1].copy_(loss.detach(), non_blocking=True)  # D2H read of the step's result
+                ev = torch.cuda.Event()
+                ev.record()
+                loss_ready[i & 1] = ev
+                if i > 0:
+                    loss_ready[(i - 1) & 1].synchronize()
+                    losses_host.append(float(loss_pinned[(i - 1) & 1]))
+            loss_ready[(args.steps - 1) & 1].synchronize()
+            losses_host.append(float(loss_pinned[(args.steps - 1) & 1]))
+            if rep == 0:
+                loss_host = losses_host[-1]  # after the same number of optimiser steps in every run of the bench
+            assert len(losses_host) == args.steps
+            f1.record()
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            ms_rep = torch.tensor([max(f0.elapsed_time(f1), wall_ms)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms_rep, op=dist.ReduceOp.MAX)
+            reps.append(float(ms_rep))
+        ms2 = sorted(reps)[len(reps) // 2]
         e2e = {"value": B * world * args.steps / (float(ms2) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": 4, "ms_per_step": float(ms2) / args.steps, "last_loss": loss_host,
-               "h2d_gbs_measured": h2d_gbs}
+               "h2d_gbs_measured": h2d_gbs, "repeats": E2E_REPEATS, "reported": "median repetition",
+               "ms_per_step_all": [r / args.steps for r in reps]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -411,11 +423,11 @@ def run_ours(args):
     # the live figure above is the average over all launches of the class)
     roof["traffic"] = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01b.json"))).get(dname)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01c.json"))).get(dname)
         if tr:
             roof["traffic"] = tr["traffic"]
             roof["traffic_note"] = {"algorithmic_bytes_same_launch": tr["algorithmic"], "launch": tr["launch"],
-                                    "source": "profiles/traffic_r01b.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
+                                    "source": "profiles/traffic_r01c.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
     except Exception:
         pass
     roof["share_of_step"] = dd["ms"] / ms_total
