@@ -6,9 +6,15 @@
 // the whole [Cout x Cin*27] result lives in REGISTERS of one CTA (each thread: 4 output channels x
 // 27 (or 9) taps for one input channel) while persistent CTAs stream disjoint position ranges through
 // shared memory ("split-K"); a second tiny kernel sums the per-CTA partials in a fixed order
-// (deterministic, no atomics).  FP32 FMA pipe bound: 432 FMAs per 22 LDS per thread iteration.
+// (deterministic, no atomics).  FP32 FMA pipe bound: 432 FMAs (216 packed FFMA2) per 22 LDS per thread iteration.
 // Positions use the same flattened-pitch trick as the forward kernel (q = ho*Wps + wo): taps are plain
 // offsets kh*Wps + kw into a contiguous staged window; gz is zero-filled at the wrap columns.
+//
+// Two kernels share the FMA step: conv3d_wgrad_f32_ws_* (warp-specialised: producer warps issue every copy, consumer warps
+// only run FMAs; fp32 input with even widths, i.e. every layer of the BASELINE models) and conv3d_wgrad_f32_kernel (every
+// warp stages and computes; int16 input fused with the normalisation, odd widths, spatial padding).  Environment switches
+// for A/B measurements (tools/bench_kernels.py): PVB200_WGRAD_WS=0 forces the second kernel, PVB200_WGRAD_NARROW=0|2|3
+// selects the narrow-layer configuration (default 2).
 #include "common.cuh"
 #include "tc_common.cuh"
 
