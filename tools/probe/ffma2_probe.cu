@@ -12,7 +12,7 @@
 // BCAST: second operand is one scalar broadcast to both halves (the R.F32 operand form of the convolution loops);
 // LDS_EVERY > 0: one LDS.128 per LDS_EVERY FFMA2 whose result feeds the multiplier (like the kernels' operand loads)
 template <int NACC, bool BCAST, int LDS_EVERY>
-__global__ void __launch_bounds__(1024) probe(float* sink, int iters, float a0) {
+__global__ void __launch_bounds__(1024) probe(float* sink, int iters, float a0, float s0) {
   __shared__ float4 tab[256];
   if (threadIdx.x < 256) tab[threadIdx.x] = make_float4(a0, a0 * 0.5f, a0 * 0.25f, a0 * 0.125f);
   __syncthreads();
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(1024) probe(float* sink, int iters, float a0) 
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = make_float2(threadIdx.x + i, threadIdx.x - i);
   float2 a = make_float2(a0, a0 * 0.5f);
-  float s = 0.999f;
+  float s = s0;  // a run-time value: the multiplier must stay a REGISTER operand (R.F32 form), not an immediate
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int i = 0; i < NACC; ++i) {
@@ -49,7 +49,7 @@ static void run(const char* name, int sms, float* sink) {
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
       cudaEventRecord(e0);
-      probe<NACC, BCAST, LDS_EVERY><<<sms * ctas_per_sm, threads>>>(sink, iters, 0.001f);
+      probe<NACC, BCAST, LDS_EVERY><<<sms * ctas_per_sm, threads>>>(sink, iters, 0.001f, 0.999f);
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1);
