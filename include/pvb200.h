@@ -162,6 +162,28 @@ int pvb200_conv3d_dgrad_bf16_tpad(const uint16_t* gz_padded, const float* w, con
                                   uint16_t* gx_gzw, void* workspace, size_t workspace_bytes, int B, int Cin, int Ti,
                                   int Hi, int Wi, int Cout, int out_pad, int pad_t, pvb200_stream_t stream);
 
+/* ---- a3/a4/a11 in fp32 MODE on the tensor cores: 3xTF32 implicit GEMM (tcgen05.mma.kind::tf32) -----------------------
+ * replaces nn.Conv3d forward / data gradient of model.py:80-90,117-120 at fp32-class accuracy (<= 1e-5): every product is
+ * x_hi.w_lo + x_lo.w_hi + x_hi.w_hi with hi = the TF32 truncation the tensor core applies, lo = the exact fp32 residual.
+ * Activations are BLOCKED fp32 [B][G][T][H][W][4] (4 channels = 16 bytes innermost, G = pvb200_blocked4_channel_groups(C),
+ * even).  Cin, Cout <= 32.  Outputs: a blocked copy (optionally zero-padded by out_pad on T, H, W: the caller keeps the
+ * border zero) and / or a plain NCDHW copy [B][Cout][To][Ho][Wo] (what the fp32 head and weight gradients read); either
+ * pointer may be null.  pad_t in {0, 1} as for the bf16 kernels.  dgrad: gz arrives blocked and zero-padded by 2 on T, H,
+ * W; mask_blk = the blocked activation whose ReLU mask is fused (or null). */
+int pvb200_blocked4_channel_groups(int C);
+size_t pvb200_conv3d_tf32x3_workspace_bytes(int Cin, int Cout);
+int pvb200_nc_to_blocked_f32(const float* x, float* y, int B, int C, int T, int H, int W, int pad, pvb200_stream_t stream);
+int pvb200_blocked_f32_to_nc(const float* x, float* y, int B, int C, int T, int H, int W, pvb200_stream_t stream);
+/* a1 fused with the layout change: int16 [B][C][T][H][W] -> normalised blocked fp32 (bit-identical arithmetic) */
+int pvb200_sat_normalise_blocked_f32(const int16_t* x, float* y, const float* mean, const float* std, int B, int C, int T,
+                                     int H, int W, pvb200_stream_t stream);
+int pvb200_conv3d_fwd_tf32x3(const float* xb, const float* w, const float* bias, float* y_blk, float* y_nc, void* workspace,
+                             size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int out_pad,
+                             int pad_t, pvb200_stream_t stream);
+int pvb200_conv3d_dgrad_tf32x3(const float* gz_padded, const float* w, const float* mask_blk, float* gx_blk, float* gx_nc,
+                               void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
+                               int out_pad, int pad_t, pvb200_stream_t stream);
+
 /* ---- general padding (pad_t, pad_hw, pad_hw), each 0 or 1, and MaxPool3d: the Conv3dMaxPool front-end of the Perceiver
  * hybrid (nn.Conv3d(..., padding=(1, 1, 1)) + nn.MaxPool3d(3, stride=(1, 2, 2), padding=(1, 1, 1)),
  * predict_pv_yield/models/perceiver/perceiver_conv3d_nwp_sat.py:42-57).  Ti/Hi/Wi are the INPUT extents. */

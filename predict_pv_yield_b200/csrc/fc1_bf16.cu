@@ -86,7 +86,10 @@ adam_fc1_shadow_kernel(float* __restrict__ p, const float* __restrict__ g, float
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long K1 = static_cast<long long>(Cg) * 8 * THW;
   const long long pos = pos0 + 2 * tx;
+  // float2 accesses need an even element offset: rows start at multiples of THW, so only when THW is even; with an
+  // odd THW (odd crops / odd sequence lengths) both positions of the lane go through scalar accesses instead
   const bool vec = (THW % 2 == 0) && (pos + 1 < THW);
+  const bool ok1 = pos + 1 < THW;  // second position of the lane exists
   // not unrolled: the fully unrolled kernel was 120 KB of code and spent a third of its stall samples on
   // instruction fetch (ncu: no_instructions 31 %)
 #pragma unroll 1
@@ -107,6 +110,7 @@ adam_fc1_shadow_kernel(float* __restrict__ p, const float* __restrict__ g, float
           pv[c8] = *reinterpret_cast<const float2*>(p + i);
         } else {
           gv[c8].x = g[i]; mv[c8].x = m[i]; vv[c8].x = v[i]; pv[c8].x = p[i];
+          if (ok1) { gv[c8].y = g[i + 1]; mv[c8].y = m[i + 1]; vv[c8].y = v[i + 1]; pv[c8].y = p[i + 1]; }
         }
       }
     }
@@ -129,6 +133,7 @@ adam_fc1_shadow_kernel(float* __restrict__ p, const float* __restrict__ g, float
           *reinterpret_cast<float2*>(v + i) = make_float2(ve[0], ve[1]);
         } else {
           p[i] = pe[0]; m[i] = me[0]; v[i] = ve[0];
+          if (ok1) { p[i + 1] = pe[1]; m[i + 1] = me[1]; v[i + 1] = ve[1]; }
         }
       } else {
         pe[0] = pe[1] = 0.f;

@@ -89,6 +89,16 @@ SIGNATURES = {
                                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_wgrad_bf16_tpad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_blocked4_channel_groups": (c_int, [c_int]),
+    "pvb200_conv3d_tf32x3_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "pvb200_nc_to_blocked_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_blocked_f32_to_nc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_sat_normalise_blocked_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                                 c_int, c_void_p]),
+    "pvb200_conv3d_fwd_tf32x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_dgrad_tf32x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_fwd_f32_pad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_dgrad_f32_pad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -49,6 +49,9 @@ class Model(BaseModel):
     # inference (no_grad) batches larger than this are streamed through the kernels in micro-batches, so the
     # activation workspace stays fixed when forecasting all GB PV systems at once (BASELINE config 4: B = 512..8192)
     inference_micro_batch = 256
+    # fp32 mode: run Conv3d forward / data gradient as 3xTF32 implicit GEMMs on the tensor cores (fp32-class accuracy);
+    # False keeps every convolution on the direct fp32 FMA kernels
+    fp32_tensor_cores = True
 
     def __init__(
         self,
@@ -68,7 +71,7 @@ class Model(BaseModel):
     ):
         """
         3d conv model, that takes in different data streams (same arguments as the reference model, plus
-        ``precision``: "fp32" = exact-fp32 CUDA-core kernels (parity <= 1e-5), "bf16" = bf16 tensor-core
+        ``precision``: "fp32" = fp32-accurate kernels, 3xTF32 tensor-core / FMA-pipe (parity <= 1e-5), "bf16" = bf16 tensor-core
         (tcgen05) convolutions with fp32 accumulation and fp32 master weights (parity <= 2e-2)).
 
         include_pv_yield: include pv yield history
@@ -193,7 +196,11 @@ class Model(BaseModel):
             out = ops.EncoderBf16Fn.apply(link, sat_data, mean, std, *self._conv_params())
             n_feat = out[0].numel() if bf16_head else out.shape[1]
         else:
-            out = ops.EncoderFn.apply(sat_data, mean, std, *self._conv_params())
+            wb = self._conv_params()
+            on_tc = self.fp32_tensor_cores and all(ops.tf32x3_supported(w.shape[1], w.shape[0]) for w in wb[0::2])
+            # fp32 mode: forward / data gradient as 3xTF32 implicit GEMMs on the tensor cores when the channel counts
+            # fit (<= 32), else the direct fp32 kernels on the FMA pipe -- both hold the 1e-5 parity bound
+            out = (ops.EncoderTf32Fn if on_tc else ops.EncoderFn).apply(sat_data, mean, std, *wb)
             n_feat = out.shape[1]
         if n_feat != self.cnn_output_size:
             raise RuntimeError(

@@ -345,6 +345,128 @@ def conv3d_wgrad_bf16(xb: torch.Tensor, gzw: torch.Tensor, Ci: int, Co: int, pad
     return dw, db
 
 
+# ---- fp32 mode on the tensor cores (3xTF32): blocked fp32 [B][G][T][H][W][4] activations ----------------------------
+def blocked4_groups(C: int) -> int:
+    return int(_lib.load().pvb200_blocked4_channel_groups(C))
+
+
+def tf32x3_supported(Ci: int, Co: int) -> bool:
+    """Shapes the 3xTF32 tensor-core convolutions take (the fp32 direct kernels cover everything else)."""
+    return Ci <= 32 and Co <= 32
+
+
+def to_blocked_f32(x: torch.Tensor, pad: int = 0, persistent: bool = False) -> torch.Tensor:
+    """[B,C,T,H,W] fp32 -> blocked fp32 [B,G,T+2p,H+2p,W+2p,4] (zero border, zero pad channels)."""
+    L = _lib.load()
+    _need_cuda(x, "x", torch.float32)
+    B, Cc, T, H, W = x.shape
+    G = blocked4_groups(Cc)
+    shape = (B, G, T + 2 * pad, H + 2 * pad, W + 2 * pad, 4)
+    if pad > 0 and persistent:
+        y = _zero_bordered("blk4_pad", shape, x.device, torch.float32)
+    else:
+        y = (torch.zeros if pad > 0 else torch.empty)(shape, dtype=torch.float32, device=x.device)
+    with _timed("nc_to_blocked_f32", 0.0, 4.0 * x.numel() + 16.0 * G * B * T * H * W):
+        rc = L.pvb200_nc_to_blocked_f32(_p(x), _p(y), B, Cc, T, H, W, pad, _stream())
+    _lib.check(rc, "nc_to_blocked_f32")
+    return y
+
+
+def from_blocked_f32(xb: torch.Tensor, C: int) -> torch.Tensor:
+    """blocked fp32 [B,G,T,H,W,4] -> [B,C,T,H,W] fp32."""
+    L = _lib.load()
+    _need_cuda(xb, "xb", torch.float32)
+    B, G, T, H, W, e = xb.shape
+    if e != 4 or G != blocked4_groups(C):
+        raise RuntimeError("from_blocked_f32: shape does not match the channel count")
+    y = torch.empty((B, C, T, H, W), dtype=torch.float32, device=xb.device)
+    with _timed("blocked_f32_to_nc", 0.0, 4.0 * xb.numel() + 4.0 * y.numel()):
+        rc = L.pvb200_blocked_f32_to_nc(_p(xb), _p(y), B, C, T, H, W, _stream())
+    _lib.check(rc, "blocked_f32_to_nc")
+    return y
+
+
+def sat_normalise_blocked_f32(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor) -> torch.Tensor:
+    """int16 [B,C,T,H,W] -> normalised blocked fp32 [B,G,T,H,W,4] (a1 fused with the layout change, bit-identical)."""
+    L = _lib.load()
+    _need_cuda(x, "satellite.data", torch.int16)
+    _need_cuda(mean, "sat_mean", torch.float32)
+    _need_cuda(std, "sat_std", torch.float32)
+    B, Cc, T, H, W = x.shape
+    if mean.numel() != Cc or std.numel() != Cc:
+        raise RuntimeError(f"sat_normalise: {Cc} channels but {mean.numel()} means / {std.numel()} stds")
+    y = torch.empty((B, blocked4_groups(Cc), T, H, W, 4), dtype=torch.float32, device=x.device)
+    with _timed("sat_normalise_blocked_f32", 0.0, 2.0 * x.numel() + 4.0 * y.numel()):
+        rc = L.pvb200_sat_normalise_blocked_f32(_p(x), _p(y), _p(mean), _p(std), B, Cc, T, H, W, _stream())
+    _lib.check(rc, "sat_normalise_blocked_f32")
+    return y
+
+
+def conv3d_fwd_tf32x3(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = True, out_pad: int = 0,
+                      pad_t: int = 0, want_blk: bool = True, want_nc: bool = False):
+    """relu(conv3d(x, w, b)) on the tensor cores at fp32 accuracy (3xTF32).  xb blocked fp32 [B,G,Ti,Hi,Wi,4]; returns
+    (blocked copy | None, NCDHW copy | None)."""
+    L = _lib.load()
+    _need_cuda(xb, "xb", torch.float32)
+    _need_cuda(w, "conv weight", torch.float32)
+    B, G, Ti, Hi, Wi, e = xb.shape
+    Co, Ci = w.shape[0], w.shape[1]
+    if e != 4 or G != blocked4_groups(Ci):
+        raise RuntimeError(f"conv3d_fwd_tf32x3: input has {G} channel groups, weight expects Cin={Ci}")
+    To, Ho, Wo = Ti + 2 * pad_t - 2, Hi - 2, Wi - 2
+    GO = blocked4_groups(Co)
+    y_blk = y_nc = None
+    if want_blk:
+        y_blk = (torch.zeros if out_pad > 0 else torch.empty)((B, GO, To + 2 * out_pad, Ho + 2 * out_pad, Wo + 2 * out_pad, 4),
+                                                              dtype=torch.float32, device=xb.device)
+    if want_nc:
+        y_nc = torch.empty((B, Co, To, Ho, Wo), dtype=torch.float32, device=xb.device)
+    ws = _workspace("conv_tf32x3", L.pvb200_conv3d_tf32x3_workspace_bytes(Ci, Co), xb.device)
+    npos = B * To * Ho * Wo
+    with _timed(f"conv3d_fwd_tf32x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
+                4.0 * xb.numel() + 4.0 * npos * (4 * GO * int(want_blk) + Co * int(want_nc))):
+        rc = L.pvb200_conv3d_fwd_tf32x3(_p(xb), _p(w), _p(b), _p(y_blk), _p(y_nc), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co,
+                                        int(relu), out_pad, pad_t, _stream())
+    _lib.check(rc, "conv3d_fwd_tf32x3")
+    return y_blk, y_nc
+
+
+def conv3d_dgrad_tf32x3(gz_padded: torch.Tensor, w: torch.Tensor, mask_blk: Optional[torch.Tensor], out_pad: int = 0,
+                        want_blk: bool = True, want_nc: bool = False, persistent: bool = False, pad_t: int = 0):
+    """gx = conv_transpose3d(gz, w) * (mask > 0) on the tensor cores (3xTF32) from gz blocked fp32 zero-padded by 2 on
+    T, H, W.  Returns (blocked copy | None, NCDHW copy | None)."""
+    L = _lib.load()
+    _need_cuda(gz_padded, "gz_padded", torch.float32)
+    _need_cuda(w, "conv weight", torch.float32)
+    B, GOz, Tp, Hp, Wp, e = gz_padded.shape
+    Co, Ci = w.shape[0], w.shape[1]
+    Ti, Hi, Wi = Tp - 2 - 2 * pad_t, Hp - 2, Wp - 2
+    if e != 4 or GOz != blocked4_groups(Co):
+        raise RuntimeError("conv3d_dgrad_tf32x3: gz channel groups do not match the weight")
+    GI = blocked4_groups(Ci)
+    if mask_blk is not None:
+        _need_cuda(mask_blk, "mask_blk", torch.float32)
+        if tuple(mask_blk.shape) != (B, GI, Ti, Hi, Wi, 4):
+            raise RuntimeError("conv3d_dgrad_tf32x3: mask shape mismatch")
+    gx_blk = gx_nc = None
+    if want_blk:
+        shape = (B, GI, Ti + 2 * out_pad, Hi + 2 * out_pad, Wi + 2 * out_pad, 4)
+        if out_pad > 0 and persistent:
+            gx_blk = _zero_bordered("gx4_pad", shape, gz_padded.device, torch.float32)
+        else:
+            gx_blk = (torch.zeros if out_pad > 0 else torch.empty)(shape, dtype=torch.float32, device=gz_padded.device)
+    if want_nc:
+        gx_nc = torch.empty((B, Ci, Ti, Hi, Wi), dtype=torch.float32, device=gz_padded.device)
+    ws = _workspace("conv_tf32x3", L.pvb200_conv3d_tf32x3_workspace_bytes(Ci, Co), gz_padded.device)
+    npos = B * Ti * Hi * Wi
+    with _timed(f"conv3d_dgrad_tf32x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
+                4.0 * gz_padded.numel() + 4.0 * npos * (4 * GI * (int(want_blk) + int(mask_blk is not None)) + Ci * int(want_nc))):
+        rc = L.pvb200_conv3d_dgrad_tf32x3(_p(gz_padded), _p(w), _p(mask_blk), _p(gx_blk), _p(gx_nc), _p(ws), ws.numel(), B, Ci, Ti,
+                                          Hi, Wi, Co, out_pad, pad_t, _stream())
+    _lib.check(rc, "conv3d_dgrad_tf32x3")
+    return gx_blk, gx_nc
+
+
 def adam_step(params: List[torch.Tensor], grads: List[torch.Tensor], exp_avg: List[torch.Tensor],
               exp_avg_sq: List[torch.Tensor], lr: float, beta1: float, beta2: float, eps: float, step: int,
               grad_scale: float = 1.0) -> None:
@@ -407,6 +529,58 @@ class EncoderFn(torch.autograd.Function):
             grads[2 * l], grads[2 * l + 1] = dw, db
             if l > 0:
                 gz = conv3d_dgrad(gz, wb[2 * l], acts[l - 1], acts[l - 1].shape)
+        return (None, None, None, *grads)
+
+
+class EncoderTf32Fn(torch.autograd.Function):
+    """Conv3d stack of the fp32 mode with forward and data gradient on the tensor cores (3xTF32, fp32-class accuracy).
+
+    forward(sat, mean, std, w0, b0, ...) -> features fp32 [B, cnn_output_size] (NCDHW flatten order, model.py:122).
+    Activations exist blocked ([B,G,T,H,W,4], what the tensor-core kernels read) and in NCDHW (what the fp32 head and
+    the fp32 weight-gradient kernels read): the convolution epilogues write both, there is no conversion pass.  Same
+    private protocol as ``EncoderFn``: the incoming gradient already carries the ReLU mask of the last layer."""
+
+    @staticmethod
+    def forward(ctx, sat, mean, std, *wb):
+        n_layers = len(wb) // 2
+        if sat.dtype == torch.int16:
+            x_blk = sat_normalise_blocked_f32(sat, mean, std)
+            x_nc = sat_normalise(sat, mean, std)  # layer 0's weight gradient reads NCDHW
+        else:
+            x_blk = to_blocked_f32(sat)
+            x_nc = sat
+        acts_blk, acts_nc = [], []
+        for l in range(n_layers):
+            last = l == n_layers - 1
+            x_blk, y_nc = conv3d_fwd_tf32x3(x_blk, wb[2 * l], wb[2 * l + 1], relu=True, want_blk=not last, want_nc=True)
+            acts_nc.append(y_nc)
+            if not last:
+                acts_blk.append(x_blk)
+        ctx.save_for_backward(x_nc, *wb, *acts_nc, *acts_blk)
+        ctx.n_layers = n_layers
+        return acts_nc[-1].view(sat.shape[0], -1)
+
+    @staticmethod
+    def backward(ctx, g):
+        n = ctx.n_layers
+        saved = ctx.saved_tensors
+        x_nc = saved[0]
+        wb = saved[1: 1 + 2 * n]
+        acts_nc = saved[1 + 2 * n: 1 + 3 * n]
+        acts_blk = saved[1 + 3 * n:]
+        gz_nc = g.contiguous().view(acts_nc[-1].shape)
+        gz_pad = None
+        grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
+        for l in range(n - 1, -1, -1):
+            x = x_nc if l == 0 else acts_nc[l - 1]
+            dw, db = conv3d_wgrad(x, gz_nc)
+            grads[2 * l], grads[2 * l + 1] = dw, db
+            if l > 0:
+                if gz_pad is None:
+                    gz_pad = to_blocked_f32(gz_nc, pad=2, persistent=True)
+                # the gradient w.r.t. layer 0's output only feeds layer 0's weight gradient: no blocked copy
+                gz_pad, gz_nc = conv3d_dgrad_tf32x3(gz_pad, wb[2 * l], acts_blk[l - 1], out_pad=2 if l > 1 else 0,
+                                                    want_blk=l > 1, want_nc=True, persistent=True)
         return (None, None, None, *grads)
 
 
@@ -567,13 +741,13 @@ class HeadFn(torch.autograd.Function):
 _persistent: Dict[Tuple, torch.Tensor] = {}
 
 
-def _zero_bordered(name: str, shape: Tuple[int, ...], device: torch.device) -> torch.Tensor:
-    """A bf16 buffer allocated ONCE with zeros and reused every step: the kernels that fill it only ever write the
+def _zero_bordered(name: str, shape: Tuple[int, ...], device: torch.device, dtype=torch.bfloat16) -> torch.Tensor:
+    """A buffer allocated ONCE with zeros and reused every step: the kernels that fill it only ever write the
     interior (valid positions), so the zero border / wrap columns never need a per-step memset."""
-    key = (name, tuple(shape), device.index)
+    key = (name, tuple(shape), device.index, dtype)
     buf = _persistent.get(key)
     if buf is None:
-        buf = torch.zeros(shape, dtype=torch.bfloat16, device=device)
+        buf = torch.zeros(shape, dtype=dtype, device=device)
         _persistent[key] = buf
     return buf
 

@@ -1,0 +1,193 @@
+"""GPU parity tests of the fp32-MODE tensor-core convolutions (3xTF32, `csrc/conv3d_igemm_tf32x3.cu`) through the C ABI.
+
+Checker = torch CPU operators in fp64 on the same seeded inputs (fp32 values, no rounding of the operands: the point of
+the 3xTF32 split is fp32-class accuracy).  Tolerances (normalised max error = max|a-b| / max|b|): forward <= 1e-5 (north
+star), data gradient <= 1e-5 (tighter than the 1e-4 of the FMA kernels' tests: the split sits at ~1e-6); a single TF32
+MMA would be at ~8e-4 (tools/tf32x3_study.py), so these gates also prove that all three terms are there.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import conv3d_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops(dev):
+    from predict_pv_yield_b200 import lib, ops as _ops
+
+    lib.load()
+    return _ops
+
+
+def nerr(a, b):
+    return O.normalised_max_err(a, b)
+
+
+def _case(shape, seed=0):
+    B, Ci, T, H, W, Co = shape
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((B, Ci, T, H, W), generator=g)
+    w = (torch.rand((Co, Ci, 3, 3, 3), generator=g) * 2 - 1) / np.sqrt(Ci * 27)
+    b = torch.randn((Co,), generator=g) * 0.1
+    return x, w, b
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 3, 7, 9), (1, 32, 2, 5, 5), (3, 5, 1, 4, 6)])
+def test_blocked_f32_layout_round_trip(ops, dev, shape):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(shape, generator=g).to(dev)
+    B, Cc, T, H, W = shape
+    xb = ops.to_blocked_f32(x)
+    G = ops.blocked4_groups(Cc)
+    assert tuple(xb.shape) == (B, G, T, H, W, 4) and G % 2 == 0
+    want = torch.zeros((B, G * 4, T, H, W), device=dev)
+    want[:, :Cc] = x
+    assert torch.equal(xb, want.view(B, G, 4, T, H, W).permute(0, 1, 3, 4, 5, 2).contiguous())
+    assert torch.equal(ops.from_blocked_f32(xb, Cc), x)
+    xp = ops.to_blocked_f32(x, pad=2)
+    assert torch.equal(xp[:, :, 2:-2, 2:-2, 2:-2], xb)
+    assert float(xp.abs().sum()) == pytest.approx(float(xb.abs().sum()), rel=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 3, 9, 9), (1, 11, 2, 8, 10)])
+def test_normalise_blocked_f32_bit_exact(ops, dev, shape):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randint(-5, 1024, shape, generator=g, dtype=torch.int32).to(torch.int16)
+    mean, std = O.sat_constants(shape[1])
+    want = O.sat_normalise_numpy(x.numpy(), mean, std)
+    got = ops.sat_normalise_blocked_f32(x.to(dev), torch.from_numpy(mean).to(dev), torch.from_numpy(std).to(dev))
+    back = ops.from_blocked_f32(got, shape[1])
+    assert np.array_equal(back.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    G = ops.blocked4_groups(shape[1])
+    flat = got.permute(0, 1, 5, 2, 3, 4).reshape(shape[0], G * 4, *shape[2:])
+    assert float(flat[:, shape[1]:].abs().sum()) == 0.0  # pad channels are zero
+
+
+FWD_SHAPES = [
+    (2, 32, 5, 10, 10, 32),   # the 32 -> 32 layers in miniature
+    (1, 12, 4, 16, 16, 32),   # layer 0: 12 channels (one zero group)
+    (2, 11, 3, 9, 12, 32),    # the production yaml's 11 channels, rectangular plane
+    (1, 32, 3, 11, 13, 16),   # Cout = 16: a single half
+    (1, 8, 3, 8, 8, 24),      # Cout = 24: second half partly empty
+    (1, 32, 4, 64, 64, 32),   # full-size plane (30 position tiles, halo of 130 positions)
+    (1, 32, 21, 6, 6, 32),    # runs longer than the accumulator-block ring
+    (40, 4, 3, 5, 5, 8),      # more columns than CTAs per half with tiny planes
+]
+
+
+@pytest.mark.parametrize("shape", FWD_SHAPES)
+def test_conv3d_fwd_tf32x3(ops, dev, shape):
+    B, Ci, T, H, W, Co = shape
+    x, w, b = _case(shape)
+    want_pre = F.conv3d(x.double(), w.double(), b.double())
+    xb = ops.to_blocked_f32(x.to(dev))
+    y_blk, y_nc = ops.conv3d_fwd_tf32x3(xb, w.to(dev), b.to(dev), relu=True, want_blk=True, want_nc=True)
+    assert tuple(y_nc.shape) == (B, Co, T - 2, H - 2, W - 2)
+    err = nerr(y_nc, F.relu(want_pre))
+    print(f"tf32x3 fwd {shape}: normalised error {err:.2e}")
+    assert err <= TOL
+    assert torch.equal(ops.from_blocked_f32(y_blk, Co), y_nc)  # the two copies hold the same values
+    # no ReLU, no bias, padded blocked output only
+    y_pad, none = ops.conv3d_fwd_tf32x3(xb, w.to(dev), None, relu=False, out_pad=2, want_blk=True, want_nc=False)
+    assert none is None
+    want_nb = F.conv3d(x.double(), w.double(), None)
+    got = ops.from_blocked_f32(y_pad[:, :, 2:-2, 2:-2, 2:-2].contiguous(), Co)
+    assert nerr(got, want_nb) <= TOL
+    assert float(y_pad.abs().sum()) == pytest.approx(float(got.abs().sum()), rel=1e-5)  # border stayed zero
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 5, 10, 10, 32), (1, 32, 4, 20, 22, 32), (1, 16, 3, 9, 9, 32), (2, 32, 3, 8, 8, 12),
+                                   (1, 32, 19, 7, 7, 32)])
+def test_conv3d_dgrad_tf32x3(ops, dev, shape):
+    B, Ci, T, H, W, Co = shape
+    x, w, _ = _case(shape, seed=1)
+    g = torch.Generator().manual_seed(2)
+    gz = torch.randn((B, Co, T - 2, H - 2, W - 2), generator=g)
+    mask_src = torch.randn((B, Ci, T, H, W), generator=g)
+    xd = x.double().requires_grad_(True)
+    F.conv3d(xd, w.double(), None).backward(gz.double())
+    want = xd.grad
+    gzp = ops.to_blocked_f32(gz.to(dev), pad=2)
+    gx_blk, gx_nc = ops.conv3d_dgrad_tf32x3(gzp, w.to(dev), None, want_blk=True, want_nc=True)
+    err = nerr(gx_nc, want)
+    print(f"tf32x3 dgrad {shape}: normalised error {err:.2e}")
+    assert err <= TOL
+    assert torch.equal(ops.from_blocked_f32(gx_blk, Ci), gx_nc)
+    mb = ops.to_blocked_f32(mask_src.to(dev))
+    gx_pad, gx_nc_m = ops.conv3d_dgrad_tf32x3(gzp, w.to(dev), mb, out_pad=2, want_blk=True, want_nc=True)
+    want_m = want * (mask_src > 0).double()
+    assert nerr(gx_nc_m, want_m) <= TOL
+    assert torch.equal(ops.from_blocked_f32(gx_pad[:, :, 2:-2, 2:-2, 2:-2].contiguous(), Ci), gx_nc_m)
+    assert float(gx_pad.abs().sum()) == pytest.approx(float(gx_nc_m.abs().sum()), rel=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 5, 10, 10, 32), (1, 12, 1, 9, 9, 32), (2, 32, 19, 8, 8, 32)])
+def test_conv3d_tf32x3_time_padded(ops, dev, shape):
+    """padding (1, 0, 0) (the towers of conv3d_sat_nwp): the planes of the padding are skipped in the kernel."""
+    B, Ci, T, H, W, Co = shape
+    x, w, b = _case(shape, seed=21)
+    g = torch.Generator().manual_seed(22)
+    gz = torch.randn((B, Co, T, H - 2, W - 2), generator=g)
+    xd = x.double().requires_grad_(True)
+    pre = F.conv3d(xd, w.double(), b.double(), padding=(1, 0, 0))
+    pre.backward(gz.double())
+    xb = ops.to_blocked_f32(x.to(dev))
+    _, y = ops.conv3d_fwd_tf32x3(xb, w.to(dev), b.to(dev), relu=True, pad_t=1, want_blk=False, want_nc=True)
+    assert nerr(y, F.relu(pre.detach())) <= TOL
+    gzp = ops.to_blocked_f32(gz.to(dev), pad=2)
+    _, gx = ops.conv3d_dgrad_tf32x3(gzp, w.to(dev), None, pad_t=1, want_blk=False, want_nc=True)
+    assert tuple(gx.shape) == (B, Ci, T, H, W)
+    assert nerr(gx, xd.grad) <= TOL
+
+
+def test_conv3d_tf32x3_four_layer_chain(ops, dev):
+    """Four chained 32 -> 32 layers with ReLU (the depth of the BASELINE model): the toward-zero accumulator of the
+    tensor core must not let the error grow past the 1e-5 bound (per-plane accumulator blocks + corrections first)."""
+    g = torch.Generator().manual_seed(5)
+    x = F.relu(torch.randn((1, 32, 11, 24, 24), generator=g))
+    ws = [(torch.rand((32, 32, 3, 3, 3), generator=g) * 2 - 1) / np.sqrt(32 * 27) * 2.0 for _ in range(4)]
+    bs = [torch.randn((32,), generator=g) * 0.05 for _ in range(4)]
+    ref = x.double()
+    xb = ops.to_blocked_f32(x.to(dev))
+    y = None
+    for l in range(4):
+        ref = F.relu(F.conv3d(ref, ws[l].double(), bs[l].double()))
+        xb, y = ops.conv3d_fwd_tf32x3(xb, ws[l].to(dev), bs[l].to(dev), relu=True, want_blk=True, want_nc=True)
+    err = nerr(y, ref)
+    print(f"tf32x3 four-layer chain: normalised error {err:.2e}")
+    assert err <= TOL
+
+
+def test_fp32_model_tensor_core_and_fma_paths_agree(dev):
+    """The fp32 model through the 3xTF32 encoder and through the direct FMA kernels: same loss / forecast / gradients
+    within the fp32 parity bound, and the tensor-core path really launched its kernels."""
+    from oracle.golden_cases import CASES, golden_batch, golden_state_dict
+    from predict_pv_yield_b200.models.conv3d.model import Model
+
+    case = CASES["nwp_pv_small"]
+    batch = O.batch_to(golden_batch("nwp_pv_small"), dev)
+    outs = {}
+    for tc in (True, False):
+        m = Model(**case["model"]).to(dev)
+        m.fp32_tensor_cores = tc
+        m.batch_size = case["batch"]
+        m.load_state_dict(golden_state_dict(m))
+        loss = m.training_step(batch, 0)
+        loss.backward()
+        outs[tc] = (float(loss.detach()), {k: p.grad.clone() for k, p in m.named_parameters()})
+    assert abs(outs[True][0] - outs[False][0]) <= 1e-5 * abs(outs[False][0])
+    for k in outs[True][1]:
+        assert nerr(outs[True][1][k], outs[False][1][k]) <= (2e-2 if "conv" in k else 2e-3), k

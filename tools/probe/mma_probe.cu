@@ -99,12 +99,17 @@ int main() {
       {"K/K none N=32 A var B var x2 issuers", 0, 32, 6144, 128, 512, 128, 1, 128, 2, 0, 0, 0, 128, 64},
       {"K/K none N=128 A var B var", 0, 128, 6144, 128, 2048, 128, 1, 128, 1, 0, 0, 0, 128, 256},
       {"K/K none N=256 A var B var", 0, 256, 6144, 128, 4096, 128, 1, 128, 1, 0, 0, 0, 128, 512},
-      {"K/K sw128 N=256 A var B var", 2, 256, 8192, 1024, 8192, 1024, 1, 128, 1, 0, 0, 0, 128, 512},
-      {"K/K sw128 N=96 A var B var", 2, 96, 8192, 1024, 8192, 1024, 1, 128, 1, 0, 0, 0, 128, 192},
       // kind::tf32 (K = 8): the MAC/cycle column counts 16 per MMA row x column, so halve it for these lines
       {"tf32 K/K none N=32", 0, 32, 6144, 128, 512, 128, 1, 128, 1, 0, 0, 0, 128, 64, 1},
       {"tf32 K/K none N=96", 0, 96, 6144, 128, 1536, 128, 1, 128, 1, 0, 0, 0, 128, 192, 1},
       {"tf32 K/K none N=96 x2 issuers", 0, 96, 6144, 128, 1536, 128, 1, 128, 2, 0, 0, 0, 128, 192, 1},
+      {"tf32 K/K none N=48", 0, 48, 6144, 128, 768, 128, 1, 128, 1, 0, 0, 0, 128, 96, 1},
+      {"tf32 K/K none N=48 x2 issuers", 0, 48, 6144, 128, 768, 128, 1, 128, 2, 0, 0, 0, 128, 96, 1},
+      {"tf32 K/K none N=48 x4 issuers", 0, 48, 6144, 128, 768, 128, 1, 128, 4, 0, 0, 0, 128, 96, 1},
+      {"tf32 K/K none N=64", 0, 64, 6144, 128, 1024, 128, 1, 128, 1, 0, 0, 0, 128, 128, 1},
+      {"tf32 K/K none N=64 x2 issuers", 0, 64, 6144, 128, 1024, 128, 1, 128, 2, 0, 0, 0, 128, 128, 1},
+      {"tf32 MN/MN none N=32", 0, 32, 128, 4096, 128, 2048, 1, 128, 1, 0, 1, 1, 8, 0, 1},
+      {"tf32 MN/MN none N=96", 0, 96, 128, 4096, 128, 2048, 1, 128, 1, 0, 1, 1, 8, 0, 1},
       {"tf32 K/K none N=128", 0, 128, 6144, 128, 2048, 128, 1, 128, 1, 0, 0, 0, 128, 256, 1},
       {"tf32 K/K none N=256", 0, 256, 6144, 128, 4096, 128, 1, 128, 1, 0, 0, 0, 128, 512, 1},
   };

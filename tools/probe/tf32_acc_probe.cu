@@ -20,6 +20,7 @@ using namespace pvb;
 
 constexpr int kM = 128, kN = 16, kK = 8;            // one MMA
 constexpr int kABytes = kM * kK * 4, kBBytes = kN * kK * 4;
+constexpr int kChunk = 32;                           // MMAs staged in shared memory at a time
 
 // element (row, k) of a K-major SWIZZLE_NONE operand tile with 32-bit elements: core matrices of 8 rows x 16 bytes
 // (4 elements); the two K core matrices of a row group are adjacent (LBO = 128), row groups 256 bytes apart (SBO = 256)
@@ -31,28 +32,40 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* __restrict__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tptr;
+  // the operands go through shared memory in chunks of kChunk MMAs (108 MMAs of case (4) do not fit at once); the
+  // accumulator stays in TMEM across the chunks
   uint8_t* a_s = smem;
-  uint8_t* b_s = smem + nmma * kABytes;
-  for (int i = threadIdx.x; i < nmma * kABytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_s)[i] = reinterpret_cast<const uint32_t*>(a)[i];
-  for (int i = threadIdx.x; i < nmma * kBBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(b_s)[i] = reinterpret_cast<const uint32_t*>(b)[i];
+  uint8_t* b_s = smem + kChunk * kABytes;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
-  tc::fence_proxy_async();  // generic-proxy writes of the operands -> visible to the tensor core's async proxy
   if (warp == 0) tc::tmem_alloc(&tptr, 32);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tptr;
-  if (threadIdx.x == 0) {
-    const uint32_t idesc = tc::umma_idesc(kM, kN, /*fmt TF32=*/2, 0, 0);
-    for (int i = 0; i < nmma; ++i) {
-      const uint64_t ad = tc::umma_desc(tc::smem_u32(a_s + i * kABytes), 128, 256);
-      const uint64_t bd = tc::umma_desc(tc::smem_u32(b_s + i * kBBytes), 128, 256);
-      tc::umma_tf32(tmem, ad, bd, idesc, i > 0 ? 1u : 0u);
+  uint32_t phase = 0;
+  for (int c0 = 0; c0 < nmma; c0 += kChunk) {
+    const int nc = nmma - c0 < kChunk ? nmma - c0 : kChunk;
+    for (int i = threadIdx.x; i < nc * kABytes / 4; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(a_s)[i] = reinterpret_cast<const uint32_t*>(a + static_cast<size_t>(c0) * kABytes)[i];
+    for (int i = threadIdx.x; i < nc * kBBytes / 4; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(b_s)[i] = reinterpret_cast<const uint32_t*>(b + static_cast<size_t>(c0) * kBBytes)[i];
+    tc::fence_proxy_async();  // generic-proxy writes of the operands -> visible to the tensor core's async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc::tc_fence_after();
+      const uint32_t idesc = tc::umma_idesc(kM, kN, /*fmt TF32=*/2, 0, 0);
+      for (int i = 0; i < nc; ++i) {
+        const uint64_t ad = tc::umma_desc(tc::smem_u32(a_s + i * kABytes), 128, 256);
+        const uint64_t bd = tc::umma_desc(tc::smem_u32(b_s + i * kBBytes), 128, 256);
+        tc::umma_tf32(tmem, ad, bd, idesc, (c0 + i) > 0 ? 1u : 0u);
+      }
+      tc::umma_commit(&bar);
     }
-    tc::umma_commit(&bar);
+    tc::mbar_wait(&bar, phase);  // the chunk's MMAs have read their operands: shared memory may be overwritten
+    phase ^= 1u;
+    __syncthreads();
   }
-  tc::mbar_wait(&bar, 0);
   tc::tc_fence_after();
   uint32_t v[16];
   tc::tmem_ld_32x16(tmem + (static_cast<uint32_t>(warp * 32) << 16), v);  // warp w reads TMEM lanes 32w .. 32w+31
@@ -85,7 +98,7 @@ struct Run {
     cudaMalloc(&da, a.size()); cudaMalloc(&db, b.size()); cudaMalloc(&dd, d.size() * 4);
     cudaMemcpy(da, a.data(), a.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(db, b.data(), b.size(), cudaMemcpyHostToDevice);
-    const size_t smem = static_cast<size_t>(nmma) * (kABytes + kBBytes);
+    const size_t smem = static_cast<size_t>(kChunk) * (kABytes + kBBytes);
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     probe_kernel<<<1, 128, smem>>>(da, db, nmma, dd);
     const cudaError_t e = cudaDeviceSynchronize();
