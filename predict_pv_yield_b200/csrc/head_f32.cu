@@ -951,7 +951,7 @@ __global__ void history_flatten_kernel(const float* __restrict__ src, long long 
   const int t = (idx / ns) % nt;
   const int b = idx / (ns * nt);
   const float v = src[b * sb + t * st + s];
-  dst[b * lddst + t * ns + s] = (v != v) ? 0.f : v;  // NaN -> 0 (the history holds no infinities)
+  dst[b * lddst + t * ns + s] = nan_to_num_f(v);  // torch.nan_to_num defaults: NaN -> 0, +-inf -> +-FLT_MAX
 }
 
 }  // namespace pvb

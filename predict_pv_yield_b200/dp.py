@@ -93,7 +93,11 @@ class GradientExchange:
 
     def _can_shard(self, p: torch.nn.Parameter) -> bool:
         shadow = getattr(p, "_pvb_shadow", None)
-        return (self.shard_large and shadow is not None and getattr(shadow, "geom", None) is not None and p.dim() == 2
+        # ``trained_through``: the forward of THIS step read the weight through its bf16 shadow (ops.HeadBf16Fn /
+        # Fc1Bf16Fn).  A step that went through the fp32 head (training batch > 128 per GPU) reads the fp32 master,
+        # whose rows owned by other ranks are stale under a row-sharded optimiser: such a step must all-reduce.
+        return (self.shard_large and shadow is not None and getattr(shadow, "geom", None) is not None
+                and getattr(shadow, "trained_through", False) and p.dim() == 2
                 and p.shape[0] % self.world_size == 0 and p.grad.is_contiguous())
 
     def _reduce_scatter_async(self, p: torch.nn.Parameter) -> None:
@@ -130,7 +134,10 @@ class GradientExchange:
                 self._reduce_scatter_async(p)
             else:
                 if getattr(p, "_pvb_shard", None) is not None:
-                    raise RuntimeError("GradientExchange: a sharded parameter can no longer be sharded")
+                    raise RuntimeError("GradientExchange: a parameter whose optimiser is sharded by rows was used by a step "
+                                       "that cannot be sharded (forward through the fp32 master weight, e.g. a training "
+                                       "batch > 128 per GPU in bf16 mode): its foreign rows are stale.  Call "
+                                       "gather_master_weights() and rebuild the exchange with shard_large=False.")
                 self._all_reduce_async(p.grad)
         else:
             self._small.append(p)
@@ -149,6 +156,31 @@ class GradientExchange:
                 parts = [torch.empty_like(flat[lo * n: hi * n]) for _ in range(self.world_size)]
                 dist.all_gather(parts, flat[lo * n: hi * n].clone(), group=self.group)
                 flat.copy_(torch.cat(parts))
+
+    @torch.no_grad()
+    def gather_optimizer_state(self, optimizer) -> None:
+        """All-gather the Adam moments (``exp_avg`` / ``exp_avg_sq``) of the row-sharded parameters: each rank only keeps
+        the moments of its own rows current, so a checkpoint written from one rank would otherwise resume with zero /
+        stale moments for (world-1)/world of fc1.weight next to a large ``step``.  Wired as the optimizer's
+        state_dict pre-hook by ``attach_optimizer``; a collective: every rank must call ``optimizer.state_dict()``."""
+        for p in self._sharded:
+            st = optimizer.state.get(p)
+            if not st:
+                continue
+            lo, hi = p._pvb_shard.rows(p.shape[0])
+            n = p.shape[1]
+            for key in ("exp_avg", "exp_avg_sq"):
+                t = st.get(key)
+                if t is None:
+                    continue
+                flat = t.view(-1)
+                mine = flat[lo * n: hi * n].clone()
+                if self._reduce_scatter_ok:
+                    dist.all_gather_into_tensor(flat, mine, group=self.group)
+                else:
+                    parts = [torch.empty_like(mine) for _ in range(self.world_size)]
+                    dist.all_gather(parts, mine, group=self.group)
+                    flat.copy_(torch.cat(parts))
 
     # -- end of backward ------------------------------------------------------------------------------
     def finish(self) -> None:
@@ -179,6 +211,8 @@ class GradientExchange:
 
     def attach_optimizer(self, optimizer) -> None:
         """Wire ``finish`` as the optimizer's pre-step hook and fold the 1/world averaging into Adam."""
+        if self.shard_large and hasattr(optimizer, "register_state_dict_pre_hook"):
+            self._opt_sd_hook = optimizer.register_state_dict_pre_hook(lambda opt: self.gather_optimizer_state(opt))
         if hasattr(optimizer, "pre_step_hook") and hasattr(optimizer, "grad_scale"):
             optimizer.pre_step_hook = self.finish
             optimizer.grad_scale = 1.0 / self.world_size
@@ -203,6 +237,9 @@ class GradientExchange:
         if getattr(self, "_sd_hook", None) is not None:
             self._sd_hook.remove()
             self._sd_hook = None
+        if getattr(self, "_opt_sd_hook", None) is not None:
+            self._opt_sd_hook.remove()
+            self._opt_sd_hook = None
 
 
 def reduce_logged_scalars(values: Dict[str, torch.Tensor], process_group=None) -> Dict[str, torch.Tensor]:

@@ -36,7 +36,14 @@ except Exception:  # pytorch_lightning absent: minimal stand-in with the hooks t
         current_epoch = 0
         logger = None
 
-        def log_dict(self, dictionary, *args, **kwargs):
+        def log_dict(self, dictionary, *args, sync_dist: bool = False, **kwargs):
+            # Lightning's ``sync_dist=True`` (base_model.py:108-119) averages every logged scalar over the ranks, one
+            # collective per scalar; without Lightning the same mean is taken here as ONE all-reduce of the packed
+            # vector when a process group is initialised (dp.reduce_logged_scalars)
+            if sync_dist and torch.distributed.is_available() and torch.distributed.is_initialized():
+                from ..dp import reduce_logged_scalars
+
+                dictionary = reduce_logged_scalars(dictionary)
             self.logged_metrics = {**getattr(self, "logged_metrics", {}), **dictionary}
 
         def log(self, name, value, *args, **kwargs):

@@ -696,6 +696,8 @@ class HeadFn(torch.autograd.Function):
             _need_cuda(wn, "fc_nwp.weight", torch.float32)
             _need_cuda(bn, "fc_nwp.bias", torch.float32)
         h, ncat = HeadFn._desc(feats, pv_hist, nwp, w1, b1, w2, b2, wn, bn, w3, b3, w4, b4)
+        if w1.requires_grad and getattr(w1, "_pvb_shadow", None) is not None:
+            w1._pvb_shadow.trained_through = False  # this step reads the fp32 master, not the shadow
         dev, B = feats.device, feats.shape[0]
         h1 = torch.empty((B, h.F1), dtype=torch.float32, device=dev)
         cat = torch.empty((B, ncat), dtype=torch.float32, device=dev)
@@ -764,6 +766,10 @@ class Fc1Shadow:
         self.geom: Optional[Tuple[int, int, int, int]] = None
         self.key = None
         self.ready: Optional[torch.cuda.Event] = None  # set while a sharded refresh is in flight on the comm stream
+        # did the last grad-enabled forward read fc1 THROUGH this shadow?  Only then may data parallelism shard the
+        # optimiser of the master weight by rows (dp.GradientExchange._can_shard): a forward through the fp32 head reads
+        # the master itself, whose foreign rows would be stale.
+        self.trained_through = False
         self._send: Optional[torch.Tensor] = None
         self._gathered: Optional[torch.Tensor] = None
 
@@ -872,6 +878,8 @@ class HeadBf16Fn(torch.autograd.Function):
         if shadow_state is None:
             shadow_state = Fc1Shadow()
         shadow = shadow_state.ensure(w1, h.F1, Cg, T, H, W)
+        if w1.requires_grad:
+            shadow_state.trained_through = True
         ctx.shadow = shadow  # the very buffer the forward used (kept alive for the data gradient)
         S = int(L.pvb200_fc1_fwd_bf16_splits())
         partial = _workspace("head", S * B * h.F1 * 4, dev)
@@ -925,7 +933,7 @@ class HeadBf16Fn(torch.autograd.Function):
             if ctx.link is None:
                 raise RuntimeError("HeadBf16Fn: no link to hand the activation gradient to EncoderBf16Fn")
             ctx.link["gz"] = (gz_pad, gzw)
-            g_act = torch.empty_like(act)  # placeholder: the real gradient travels through the link
+            g_act = _zero_bordered("g_act_placeholder", tuple(act.shape), act.device, act.dtype)  # zeros, never written: the real gradient travels through the link
         return None, g_act, None, None, dw1, db1, dw2, db2, dwn, dbn, dw3, db3, dw4, db4
 
 
@@ -1023,6 +1031,8 @@ class Fc1Bf16Fn(torch.autograd.Function):
         if w1.shape[1] != Cg * 8 * T * H * W:
             raise RuntimeError(f"Fc1Bf16Fn: weight {tuple(w1.shape)} does not match the activation {tuple(act.shape)}")
         shadow = link["shadow"].ensure(w1, F1, Cg, T, H, W)
+        if w1.requires_grad:
+            link["shadow"].trained_through = True
         ctx.shadow = shadow
         S = int(L.pvb200_fc1_fwd_bf16_splits())
         partial = _workspace("head", S * B * F1 * 4, act.device)
@@ -1061,7 +1071,7 @@ class Fc1Bf16Fn(torch.autograd.Function):
                 rc = L.pvb200_fc1_dgrad_bf16(_p(g_pre), _p(ctx.shadow), _p(act), _p(gz_pad), _p(gzw), B, F1, Cg, T, H, W, _stream())
             _lib.check(rc, "fc1_dgrad_bf16")
             ctx.link["gz"] = (gz_pad, gzw)
-            g_act = torch.empty_like(act)  # placeholder: the real gradient travels through the link
+            g_act = _zero_bordered("g_act_placeholder", tuple(act.shape), act.device, act.dtype)  # zeros, never written: the real gradient travels through the link
         return None, g_act, dw1, db1
 
 
@@ -1082,6 +1092,8 @@ class LinearFn(torch.autograd.Function):
         N = w.shape[0]
         if tuple(w.shape) != (N, K) or tuple(b.shape) != (N,):
             raise RuntimeError(f"LinearFn: weight {tuple(w.shape)} / bias {tuple(b.shape)} do not match input features {K}")
+        if w.requires_grad and getattr(w, "_pvb_shadow", None) is not None:
+            w._pvb_shadow.trained_through = False  # this step reads the fp32 master, not the shadow
         w = w.contiguous()
         y = torch.empty((B, N), dtype=torch.float32, device=x.device)
         ws = _workspace("linear", L.pvb200_linear_workspace_bytes(B, N, K), x.device)
@@ -1112,7 +1124,11 @@ class LinearFn(torch.autograd.Function):
 
 class EmbeddingFn(torch.autograd.Function):
     """table[ids] (nn.Embedding(940, 16) of model_sat_nwp.py:146-149,252-260) with a dense deterministic gradient.
-    forward(table [V,D], ids int32 [B]) -> [B, D]."""
+    forward(table [V,D], ids int32 [B]) -> [B, D].  ``validate_ids``: raise IndexError for ids outside [0, V) as
+    nn.Embedding does (one 8-byte device->host read per call; the reference round-trips the ids through the CPU anyway,
+    model_sat_nwp.py:257-258).  With False the kernels return zeros / drop the gradient for such ids."""
+
+    validate_ids = True
 
     @staticmethod
     def forward(ctx, table, ids):
@@ -1121,6 +1137,10 @@ class EmbeddingFn(torch.autograd.Function):
         _need_cuda(ids, "ids", torch.int32)
         V, D = table.shape
         B = ids.shape[0]
+        if EmbeddingFn.validate_ids and B > 0:
+            lo, hi = (int(v) for v in torch.stack((ids.min(), ids.max())).tolist())
+            if lo < 0 or hi >= V:
+                raise IndexError(f"embedding: index out of range (ids span [{lo}, {hi}], table has {V} rows)")
         y = torch.empty((B, D), dtype=torch.float32, device=table.device)
         _lib.check(L.pvb200_embedding_fwd_f32(_p(table.contiguous()), _p(ids), _p(y), D, B, V, D, _stream()), "embedding_fwd")
         ctx.save_for_backward(ids)

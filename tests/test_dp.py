@@ -89,6 +89,7 @@ class _FakeShadow:
 
     def __init__(self):
         self.geom = (1, 1, 1, 1)
+        self.trained_through = True  # the forward read the weight through the shadow (ops.HeadBf16Fn sets this)
         self.full_bf16 = None
 
     def adam_step_sharded(self, w1, grad, m, v, lr, b1, b2, eps, step, grad_scale, rank, world, group, comm_stream):
@@ -147,7 +148,32 @@ def _worker_sharded(rank, world, port, q):
             ok = ok and torch.allclose(big.data, ref[0].weight.data, atol=1e-6)
         sd = model.state_dict()  # pre-hook gathers (collective)
         ok_sd = torch.allclose(sd["0.weight"], ref[0].weight.data, atol=1e-6)
-        q.put((rank, bool(ok), bool(ok_sd), spec.rows(128)))
+        # optimizer checkpoints: the moments of the rows other ranks own are gathered too (a checkpoint from
+        # rank 0 must not resume with zero moments next to a large step count)
+        lo, hi = spec.rows(128)
+        stale = not torch.allclose(m, ref_opt.state[ref[0].weight]["exp_avg"], atol=1e-7)
+
+        class _Opt:
+            state = {big: {"step": 3, "exp_avg": m, "exp_avg_sq": v}}
+
+        ex.gather_optimizer_state(_Opt())
+        ok_opt = stale and torch.allclose(m, ref_opt.state[ref[0].weight]["exp_avg"], atol=1e-7) and \
+            torch.allclose(v, ref_opt.state[ref[0].weight]["exp_avg_sq"], atol=1e-9)
+        # a step that did NOT read the weight through the shadow (fp32 head: batch > 128) must refuse to shard
+        big._pvb_shadow.trained_through = False
+        model.zero_grad()
+        try:
+            ((model(x) - y) ** 2).mean().backward()
+            ok_guard = False
+        except RuntimeError as e:
+            ok_guard = "stale" in str(e)
+        # the logged scalars of the stand-in LightningModule are averaged over the ranks (sync_dist=True)
+        from predict_pv_yield_b200.models.base_model import _Base
+
+        mod = _Base()
+        mod.log_dict({"MSE/Train": torch.tensor(float(rank + 1))}, on_step=True, sync_dist=True)
+        ok_log = abs(float(mod.logged_metrics["MSE/Train"]) - 1.5) < 1e-6
+        q.put((rank, bool(ok), bool(ok_sd and ok_opt and ok_guard and ok_log), spec.rows(128)))
     finally:
         dist.destroy_process_group()
 
@@ -168,7 +194,7 @@ def test_sharded_large_parameter_two_ranks_gloo():
     rows = set()
     for rank, ok, ok_sd, r in res:
         assert ok, f"rank {rank}: sharded step diverged from the replicated reference"
-        assert ok_sd, f"rank {rank}: state_dict() did not gather the master rows"
+        assert ok_sd, f"rank {rank}: state_dict() / optimizer-state gathering, the shard guard or the logged-scalar mean failed"
         rows.add(r)
     assert rows == {(0, 64), (64, 128)}
 
