@@ -234,6 +234,76 @@ class OracleModel(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------
+# bf16-mode checker: the same model in fp64 with the ROUNDING POINTS of the bf16 tensor-core path
+# ---------------------------------------------------------------------------------------------
+class _RoundFwd(torch.autograd.Function):
+    """value -> nearest bf16 in the forward pass, identity for the gradient (a tensor STORED as bf16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.float32).to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    """identity in the forward pass, gradient -> nearest bf16 (a GRADIENT tensor stored as bf16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.float32).to(torch.bfloat16).to(g.dtype)
+
+
+class Bf16EmulatedOracle(OracleModel):
+    """OracleModel evaluated in fp64 with every tensor the bf16 mode stores as bf16 rounded at the same place: the
+    normalised input cube, every conv activation (after bias + ReLU), the conv / fc1 weights as the tensor cores read
+    them, and on the way back the gradients w.r.t. the conv and fc1 pre-activations.  Accumulation is exact (fp64) where
+    the device accumulates in fp32, biases and the small layers of the head stay unrounded (fp32 on the device).
+    A bf16-mode result is expected within a few bf16 ulps (2^-8 = 3.9e-3 each) of THIS model -- far tighter than the
+    2e-2 the north star allows against the fp32 reference, and tight enough to catch a wrong tap or a missing term.
+    Use in .double()."""
+
+    def forward(self, x, return_activations: bool = False):
+        if isinstance(x, dict):
+            x = _NS(**x)
+        rf, rb = _RoundFwd.apply, _RoundBwd.apply
+        sat = x.satellite.data
+        if sat.dtype == torch.int16:
+            mean, std = sat_constants(sat.shape[1])
+            sat = sat_normalise(sat, torch.from_numpy(mean), torch.from_numpy(std))
+        dt = self.sat_conv0.weight.dtype
+        out = rf(sat.to(dt))
+        B = sat.shape[0]
+        convs = [self.sat_conv0] + [getattr(self, f"conv3d_{i + 1}") for i in range(self.number_of_conv3d_layers - 1)]
+        acts = []
+        for conv in convs:
+            out = rf(F.relu(rb(F.conv3d(out, rf(conv.weight), conv.bias))))
+            acts.append(out)
+        out = out.reshape(B, self.cnn_output_size)
+        out = F.relu(rb(F.linear(out, rf(self.fc1.weight), self.fc1.bias)))
+        out = F.relu(self.fc2(out))
+        if self.include_pv_yield:
+            h = x[self.output_variable][:, : self.history_len_30 + 1].nan_to_num(nan=0.0).to(out.dtype)
+            h = h.reshape(h.shape[0], h.shape[1] * h.shape[2])
+            out = torch.cat((out, h), dim=1)
+        if self.include_nwp:
+            nwp = x["nwp"].to(out.dtype).flatten(start_dim=1)
+            out = torch.cat((out, F.relu(self.fc_nwp(nwp))), dim=1)
+        out = F.relu(self.fc3(out))
+        out = self.fc4(out)
+        out = out.reshape(B, self.forecast_len)
+        if return_activations:
+            return out, acts
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
 # a12. Adam, restated as scalar arithmetic (torch.optim.Adam single-tensor path, defaults
 # betas=(0.9,0.999), eps=1e-8, weight_decay=0, amsgrad=False; base_model.py:256)
 # ---------------------------------------------------------------------------------------------

@@ -176,9 +176,20 @@ def test_bf16_model_within_tolerance_of_oracle(dev, name):
         y_hat = m(O.batch_to(batch, dev))
     assert O.normalised_max_err(y_hat, r["y_hat"]) <= 2e-2
     assert abs(float(loss.detach()) - float(r["nmae"])) <= 2e-2 * abs(float(r["nmae"]))
-    for (k, p), (_, q) in zip(m.named_parameters(), om.named_parameters()):
-        e = O.normalised_max_err(p.grad, q.grad)
-        assert e <= 1e-1, (k, e)  # gradients through bf16 activations: sanity gate (same direction, same scale)
+    # gradients: against the fp64 model that rounds where the bf16 path rounds (oracle.Bf16EmulatedOracle) the path sits
+    # at a few bf16 ulps; 2^-6 = 4 ulps per tensor (normalised max error).  The plain fp32 oracle only bounds the
+    # direction / scale (bf16 activations move gradients by several per cent of max|g|).
+    oe = O.Bf16EmulatedOracle(**case["model"]).double()
+    oe.batch_size = case["batch"]
+    oe.load_state_dict({k: v.double() for k, v in sd.items()})
+    re = oe.step_losses(O.batch_to(batch, float_dtype=torch.float64))
+    re["nmae"].backward()
+    assert O.normalised_max_err(y_hat, re["y_hat"]) <= 2.0 ** -7
+    for (k, p), (_, q), (_, qe) in zip(m.named_parameters(), om.named_parameters(), oe.named_parameters()):
+        e = O.normalised_max_err(p.grad, qe.grad)
+        print(f"bf16 {name} {k}: vs bf16-emulating fp64 {e:.2e}, vs fp32 oracle {O.normalised_max_err(p.grad, q.grad):.2e}")
+        assert e <= 2.0 ** -6, (k, e)
+        assert O.normalised_max_err(p.grad, q.grad) <= 1e-1, k
 
 
 FC1_CASES = [

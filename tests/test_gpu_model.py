@@ -81,7 +81,7 @@ def test_model_matches_reference_golden(dev, golden_dir, name):
         assert float(diff.max()) <= 2.1e-3, k
 
 
-@pytest.mark.parametrize("name", ["test_yaml_pv", "nwp_pv_small"])
+@pytest.mark.parametrize("name", list(CASES))
 def test_model_matches_fp64_oracle(dev, name):
     case = CASES[name]
     m = _model(case["model"], dev)
@@ -97,8 +97,19 @@ def test_model_matches_fp64_oracle(dev, name):
     loss = m.training_step(O.batch_to(batch, dev), 0)
     loss.backward()
     assert abs(float(loss.detach()) - float(r["nmae"])) <= 1e-5 * abs(float(r["nmae"]))
-    for (k, p), (_, q) in zip(m.named_parameters(), om.named_parameters()):
-        assert O.normalised_max_err(p.grad, q.grad) <= _grad_tol(k), k
+    # the same step by torch in fp32 (the reference's own arithmetic): its distance from fp64 is the noise floor of an
+    # end-to-end fp32 gradient.  Where no ReLU decision flips, both sit at ~1e-6; where one does (tiny batches: one
+    # position is a visible fraction of a conv gradient) torch-fp32 moves by 1e-3 and so may we.  Gate: 1e-5, or three
+    # times torch's own distance on that tensor -- a wrong tap / dropped term is orders of magnitude outside either.
+    o32 = O.OracleModel(**case["model"])
+    o32.batch_size = case["batch"]
+    o32.load_state_dict(sd)
+    r32 = o32.step_losses(batch)
+    r32["nmae"].backward()
+    for (k, p), (_, q), (_, q32) in zip(m.named_parameters(), om.named_parameters(), o32.named_parameters()):
+        e, floor = O.normalised_max_err(p.grad, q.grad), O.normalised_max_err(q32.grad, q.grad)
+        print(f"{name} {k}: cuda-vs-fp64 {e:.2e}  torch32-vs-fp64 {floor:.2e}")
+        assert e <= max(1e-5, 3.0 * floor), (k, e, floor)
 
 
 def test_model_float_input_equals_int16_input(dev):
