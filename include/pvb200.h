@@ -184,6 +184,16 @@ int pvb200_conv3d_dgrad_tf32x3(const float* gz_padded, const float* w, const flo
                                void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
                                int out_pad, int pad_t, pvb200_stream_t stream);
 
+/* weight / bias gradient of the same layers on the tensor cores (3xTF32; conv3d_wgrad_tf32x3.cu): dw [Cout][Cin][3][3][3],
+ * db [Cout] (or null) from x blocked fp32 [B][G(Cin)][Ti][Hi][Wi][4] and the pre-activation gradient gz blocked fp32,
+ * zero-padded by gz_pad on T, H, W (2 = the tensor the data gradient reads, 0 = plain).  `supported` says whether the
+ * layer fits (Cin, Cout <= 32, rows that fit shared memory); otherwise use pvb200_conv3d_wgrad_f32. */
+int pvb200_conv3d_wgrad_tf32x3_supported(int Cin, int Cout, int Hi, int Wi);
+size_t pvb200_conv3d_wgrad_tf32x3_workspace_bytes(void);
+int pvb200_conv3d_wgrad_tf32x3(const float* xb, const float* gzb, int gz_pad, float* dw, float* db, void* workspace,
+                               size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
+                               pvb200_stream_t stream);
+
 /* ---- general padding (pad_t, pad_hw, pad_hw), each 0 or 1, and MaxPool3d: the Conv3dMaxPool front-end of the Perceiver
  * hybrid (nn.Conv3d(..., padding=(1, 1, 1)) + nn.MaxPool3d(3, stride=(1, 2, 2), padding=(1, 1, 1)),
  * predict_pv_yield/models/perceiver/perceiver_conv3d_nwp_sat.py:42-57).  Ti/Hi/Wi are the INPUT extents. */

@@ -467,6 +467,33 @@ def conv3d_dgrad_tf32x3(gz_padded: torch.Tensor, w: torch.Tensor, mask_blk: Opti
     return gx_blk, gx_nc
 
 
+def wgrad_tf32x3_supported(Ci: int, Co: int, Hi: int, Wi: int) -> bool:
+    return bool(_lib.load().pvb200_conv3d_wgrad_tf32x3_supported(Ci, Co, Hi, Wi))
+
+
+def conv3d_wgrad_tf32x3(xb: torch.Tensor, gzb: torch.Tensor, Ci: int, Co: int, gz_pad: int = 0,
+                        pad_t: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(dw [Co,Ci,3,3,3], db [Co]) on the tensor cores (3xTF32) from x blocked fp32 [B,G,Ti,Hi,Wi,4] and the pre-activation
+    gradient blocked fp32, zero-padded by ``gz_pad`` on T, H, W (2 = the tensor the data gradient reads)."""
+    L = _lib.load()
+    _need_cuda(xb, "xb", torch.float32)
+    _need_cuda(gzb, "gzb", torch.float32)
+    B, G, Ti, Hi, Wi, e = xb.shape
+    To, Ho, Wo = Ti + 2 * pad_t - 2, Hi - 2, Wi - 2
+    want = (B, blocked4_groups(Co), To + 2 * gz_pad, Ho + 2 * gz_pad, Wo + 2 * gz_pad, 4)
+    if e != 4 or G != blocked4_groups(Ci) or tuple(gzb.shape) != want:
+        raise RuntimeError(f"conv3d_wgrad_tf32x3: shapes {tuple(xb.shape)} / {tuple(gzb.shape)} inconsistent (expected gz {want})")
+    dw = torch.empty((Co, Ci, 3, 3, 3), dtype=torch.float32, device=xb.device)
+    db = torch.empty((Co,), dtype=torch.float32, device=xb.device)
+    ws = _workspace("wgrad_tf32x3", L.pvb200_conv3d_wgrad_tf32x3_workspace_bytes(), xb.device)
+    npos = B * To * Ho * Wo
+    with _timed(f"conv3d_wgrad_tf32x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 4.0 * xb.numel() + 16.0 * blocked4_groups(Co) * npos):
+        rc = L.pvb200_conv3d_wgrad_tf32x3(_p(xb), _p(gzb), gz_pad, _p(dw), _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
+                                          _stream())
+    _lib.check(rc, "conv3d_wgrad_tf32x3")
+    return dw, db
+
+
 def adam_step(params: List[torch.Tensor], grads: List[torch.Tensor], exp_avg: List[torch.Tensor],
               exp_avg_sq: List[torch.Tensor], lr: float, beta1: float, beta2: float, eps: float, step: int,
               grad_scale: float = 1.0) -> None:
@@ -533,54 +560,73 @@ class EncoderFn(torch.autograd.Function):
 
 
 class EncoderTf32Fn(torch.autograd.Function):
-    """Conv3d stack of the fp32 mode with forward and data gradient on the tensor cores (3xTF32, fp32-class accuracy).
+    """Conv3d stack of the fp32 mode on the tensor cores (3xTF32: forward, data gradient AND weight gradient at fp32-class
+    accuracy, csrc/conv3d_igemm_tf32x3.cu / conv3d_wgrad_tf32x3.cu).
 
     forward(sat, mean, std, w0, b0, ...) -> features fp32 [B, cnn_output_size] (NCDHW flatten order, model.py:122).
-    Activations exist blocked ([B,G,T,H,W,4], what the tensor-core kernels read) and in NCDHW (what the fp32 head and
-    the fp32 weight-gradient kernels read): the convolution epilogues write both, there is no conversion pass.  Same
-    private protocol as ``EncoderFn``: the incoming gradient already carries the ReLU mask of the last layer."""
+    Activations and gradients live blocked ([B,G,T,H,W,4], what the tensor-core kernels read); the last activation is
+    also written in NCDHW for the fp32 head.  A layer whose rows do not fit the tensor-core weight gradient's shared
+    memory (128-wide planes) falls back to the fp32 FMA weight gradient, for which the producing kernels' epilogues write
+    an extra NCDHW copy (no conversion pass).  Same private protocol as ``EncoderFn``: the incoming gradient already
+    carries the ReLU mask of the last layer."""
 
     @staticmethod
     def forward(ctx, sat, mean, std, *wb):
-        n_layers = len(wb) // 2
+        n = len(wb) // 2
+        B, _, T, H, W = sat.shape
+        # per layer: does the tensor-core weight gradient take it?  (input plane of layer l: H - 2l)
+        tc_w = [wgrad_tf32x3_supported(wb[2 * l].shape[1], wb[2 * l].shape[0], H - 2 * l, W - 2 * l) for l in range(n)]
         if sat.dtype == torch.int16:
             x_blk = sat_normalise_blocked_f32(sat, mean, std)
-            x_nc = sat_normalise(sat, mean, std)  # layer 0's weight gradient reads NCDHW
+            x_nc = None if tc_w[0] else sat_normalise(sat, mean, std)
         else:
             x_blk = to_blocked_f32(sat)
-            x_nc = sat
-        acts_blk, acts_nc = [], []
-        for l in range(n_layers):
-            last = l == n_layers - 1
-            x_blk, y_nc = conv3d_fwd_tf32x3(x_blk, wb[2 * l], wb[2 * l + 1], relu=True, want_blk=not last, want_nc=True)
-            acts_nc.append(y_nc)
+            x_nc = None if tc_w[0] else sat
+        ins_blk, ins_nc = [x_blk], [x_nc]  # input of layer l, blocked / NCDHW (None when not needed)
+        y_nc = None
+        for l in range(n):
+            last = l == n - 1
+            want_nc = last or not tc_w[l + 1]
+            y_blk, y_nc = conv3d_fwd_tf32x3(ins_blk[l], wb[2 * l], wb[2 * l + 1], relu=True, want_blk=not last, want_nc=want_nc)
             if not last:
-                acts_blk.append(x_blk)
-        ctx.save_for_backward(x_nc, *wb, *acts_nc, *acts_blk)
-        ctx.n_layers = n_layers
-        return acts_nc[-1].view(sat.shape[0], -1)
+                ins_blk.append(y_blk)
+                ins_nc.append(y_nc if not tc_w[l + 1] else None)
+        keep = [t for t in ins_nc if t is not None]
+        ctx.save_for_backward(*wb, *ins_blk, *keep)
+        ctx.n_layers, ctx.tc_w = n, tc_w
+        ctx.nc_index = [i for i, t in enumerate(ins_nc) if t is not None]
+        ctx.out_shape = tuple(y_nc.shape)
+        return y_nc.view(B, -1)
 
     @staticmethod
     def backward(ctx, g):
-        n = ctx.n_layers
+        n, tc_w = ctx.n_layers, ctx.tc_w
         saved = ctx.saved_tensors
-        x_nc = saved[0]
-        wb = saved[1: 1 + 2 * n]
-        acts_nc = saved[1 + 2 * n: 1 + 3 * n]
-        acts_blk = saved[1 + 3 * n:]
-        gz_nc = g.contiguous().view(acts_nc[-1].shape)
-        gz_pad = None
+        wb = saved[: 2 * n]
+        ins_blk = saved[2 * n: 3 * n]
+        ins_nc: List[Optional[torch.Tensor]] = [None] * n
+        for i, t in zip(ctx.nc_index, saved[3 * n:]):
+            ins_nc[i] = t
+        gz_nc = g.contiguous().view(ctx.out_shape)
+        gz_blk, gz_pad = None, 0
+        if n > 1 or tc_w[n - 1]:
+            gz_blk, gz_pad = to_blocked_f32(gz_nc, pad=2, persistent=True), 2
         grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
         for l in range(n - 1, -1, -1):
-            x = x_nc if l == 0 else acts_nc[l - 1]
-            dw, db = conv3d_wgrad(x, gz_nc)
+            Co, Ci = wb[2 * l].shape[0], wb[2 * l].shape[1]
+            if tc_w[l]:
+                dw, db = conv3d_wgrad_tf32x3(ins_blk[l], gz_blk, Ci, Co, gz_pad=gz_pad)
+            else:
+                dw, db = conv3d_wgrad(ins_nc[l], gz_nc)
             grads[2 * l], grads[2 * l + 1] = dw, db
             if l > 0:
-                if gz_pad is None:
-                    gz_pad = to_blocked_f32(gz_nc, pad=2, persistent=True)
-                # the gradient w.r.t. layer 0's output only feeds layer 0's weight gradient: no blocked copy
-                gz_pad, gz_nc = conv3d_dgrad_tf32x3(gz_pad, wb[2 * l], acts_blk[l - 1], out_pad=2 if l > 1 else 0,
-                                                    want_blk=l > 1, want_nc=True, persistent=True)
+                # gradient w.r.t. layer l-1's pre-activation: blocked + padded by 2 when a data gradient still follows
+                # (l-1 >= 1), blocked when layer l-1's weight gradient runs on the tensor cores, NCDHW when it does not
+                nxt_pad = 2 if l - 1 >= 1 else 0
+                want_blk = (l - 1 >= 1) or tc_w[l - 1]
+                gz_blk, gz_nc = conv3d_dgrad_tf32x3(gz_blk, wb[2 * l], ins_blk[l], out_pad=nxt_pad if want_blk else 0,
+                                                    want_blk=want_blk, want_nc=not tc_w[l - 1], persistent=True)
+                gz_pad = nxt_pad
         return (None, None, None, *grads)
 
 

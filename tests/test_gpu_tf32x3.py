@@ -153,6 +153,64 @@ def test_conv3d_tf32x3_time_padded(ops, dev, shape):
     assert nerr(gx, xd.grad) <= TOL
 
 
+WGRAD_SHAPES = [
+    (2, 32, 5, 10, 10, 32),
+    (1, 12, 4, 16, 16, 32),   # layer 0: 12 channels
+    (2, 11, 3, 9, 12, 32),    # odd channel count, rectangular plane (Wo = 10: two K steps, the second half padding)
+    (1, 32, 3, 11, 13, 16),   # Cout = 16: N = 48
+    (1, 8, 3, 8, 8, 24),      # Cout = 24 padded to 32 columns per tap
+    (1, 32, 3, 64, 64, 32),   # full-size rows (the over-read of the M = 128 instruction stays inside shared memory)
+    (3, 32, 21, 6, 6, 32),    # many short steps: several flush windows per CTA
+    (37, 4, 3, 5, 5, 8),      # more (sample, plane, row) steps than CTAs
+]
+
+
+@pytest.mark.parametrize("shape", WGRAD_SHAPES)
+@pytest.mark.parametrize("gz_pad", [0, 2])
+def test_conv3d_wgrad_tf32x3(ops, dev, shape, gz_pad):
+    B, Ci, T, H, W, Co = shape
+    assert ops.wgrad_tf32x3_supported(Ci, Co, H, W)
+    x, w, b = _case(shape, seed=4)
+    g = torch.Generator().manual_seed(5)
+    gz = torch.randn((B, Co, T - 2, H - 2, W - 2), generator=g)
+    wd = w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    F.conv3d(x.double(), wd, bd).backward(gz.double())
+    xb = ops.to_blocked_f32(x.to(dev))
+    gzb = ops.to_blocked_f32(gz.to(dev), pad=gz_pad)
+    dw, db = ops.conv3d_wgrad_tf32x3(xb, gzb, Ci, Co, gz_pad=gz_pad)
+    e_w, e_b = nerr(dw, wd.grad), nerr(db, bd.grad)
+    print(f"tf32x3 wgrad {shape} pad {gz_pad}: dw {e_w:.2e} db {e_b:.2e}")
+    assert e_w <= TOL and e_b <= TOL
+    dw2, db2 = ops.conv3d_wgrad_tf32x3(xb, gzb, Ci, Co, gz_pad=gz_pad)  # deterministic: same bits on a second run
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+def test_conv3d_wgrad_tf32x3_time_padded(ops, dev):
+    shape = (2, 32, 5, 10, 10, 32)
+    B, Ci, T, H, W, Co = shape
+    x, w, b = _case(shape, seed=6)
+    g = torch.Generator().manual_seed(7)
+    gz = torch.randn((B, Co, T, H - 2, W - 2), generator=g)
+    wd = w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    F.conv3d(x.double(), wd, bd, padding=(1, 0, 0)).backward(gz.double())
+    dw, db = ops.conv3d_wgrad_tf32x3(ops.to_blocked_f32(x.to(dev)), ops.to_blocked_f32(gz.to(dev), pad=2), Ci, Co, gz_pad=2, pad_t=1)
+    assert nerr(dw, wd.grad) <= TOL and nerr(db, bd.grad) <= TOL
+
+
+def test_conv3d_wgrad_tf32x3_rejects_wide_planes(ops, dev):
+    """128-wide rows (the deep variant's first layers) do not fit the staging buffers: the host says so and the encoder
+    keeps those layers on the fp32 FMA weight gradient."""
+    from predict_pv_yield_b200 import lib
+
+    assert not ops.wgrad_tf32x3_supported(32, 32, 126, 126)
+    assert ops.wgrad_tf32x3_supported(32, 32, 64, 64)
+    L = lib.load()
+    rc = L.pvb200_conv3d_wgrad_tf32x3(1, 1, 0, 1, 1, 1, 0, 1, 32, 3, 126, 126, 32, 0, 0)
+    assert rc != 0 and b"not supported" in L.pvb200_last_error()
+
+
 def test_conv3d_tf32x3_four_layer_chain(ops, dev):
     """Four chained 32 -> 32 layers with ReLU (the depth of the BASELINE model): the toward-zero accumulator of the
     tensor core must not let the error grow past the 1e-5 bound (per-plane accumulator blocks + corrections first)."""
