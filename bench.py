@@ -84,7 +84,7 @@ def parse_args():
                     help="N > 1: SMs left to NCCL's kernels by the persistent kernels (default 0: measured at N = 8 bf16, "
                          "reserving 16 / 32 SMs speeds the overlapped kernels up but lengthens the step: 3.53 / 3.73 / 4.21 ms)")
     ap.add_argument("--no-shard", action="store_true",
-                    help="bf16, N > 1: replicate the fc1 optimiser instead of sharding it by output feature")
+                    help="N > 1: replicate the fc1 optimiser (all-reduce) instead of sharding it by output feature")
     ap.add_argument("--infer-batches", default="512,1024,2048,4096,8192", help="c4: global batch sizes of the sweep")
     return ap.parse_args()
 
@@ -387,7 +387,7 @@ class Job:
         if world > 1 and self.cfg["mode"] == "train":
             from predict_pv_yield_b200.dp import GradientExchange
 
-            self.sharded = precision == "bf16" and not args.no_shard
+            self.sharded = not args.no_shard  # fc1 optimiser sharded by rows (bf16: + shadow all-gather; fp32: row all-gather)
             self.exchange = GradientExchange(self.model, shard_large=self.sharded)
             lib.load().pvb200_reserve_sms(max(args.reserve_sms, 0))
             self.exchange.attach_optimizer(self.opt)

@@ -13,6 +13,10 @@ pass produces, so:
   ``finish()``;
 * averaging (1 / world_size) is folded into the Adam kernel (``FusedAdam.grad_scale``), so no extra pass.
 
+* ``shard_large=True``, fp32 mode: the optimiser of the large parameter is sharded by rows.  Its gradient is
+  REDUCE-SCATTERED (half the NVLink bytes of an all-reduce), rank r runs Adam on its rows only (1/N of the 4 GB optimiser
+  pass) and the updated fp32 rows are all-gathered in place on the communication stream, under the next step's
+  convolution forward (``ShardSpec.all_gather_rows``; readers call ``wait_ready``).
 * ``shard_large=True`` (bf16 mode, where ``fc1.weight`` has a tensor-core shadow): the optimiser of the large
   parameter is sharded by output feature.  Its gradient is REDUCE-SCATTERED (half the NVLink bytes of an
   all-reduce): rank r receives the summed rows [r*F/N, (r+1)*F/N), runs Adam on those rows only (1/N of the 4 GB
@@ -46,6 +50,38 @@ class ShardSpec:
     def rows(self, nrows_total: int):
         n = nrows_total // self.world
         return self.rank * n, (self.rank + 1) * n
+
+    @torch.no_grad()
+    def all_gather_rows(self, p: torch.Tensor) -> None:
+        """fp32 mode (no bf16 shadow): every rank has just updated its own rows of ``p``; all-gather them IN PLACE on the
+        communication stream.  ``p._pvb_ready`` is the event a reader of ``p`` waits on -- the head of the NEXT forward
+        pass, so the transfer hides under the next step's normalise + convolution forward (fc1 is the last consumer)."""
+        lo, hi = self.rows(p.shape[0])
+        n = p[0].numel()
+        flat = p.data.view(-1)
+        mine = flat[lo * n: hi * n]
+        if p.is_cuda and self._exchange._reduce_scatter_ok:
+            comm = self.comm_stream(p.device)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(p.device))
+            comm.wait_event(done)  # the Adam kernel on this rank's rows has finished
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(flat, mine, group=self.group)  # in place: mine == flat[rank * count ...]
+                ready = torch.cuda.Event()
+                ready.record(comm)
+            p._pvb_ready = ready
+        else:  # gloo (CPU tests)
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine.clone(), group=self.group)
+            flat.copy_(torch.cat(parts))
+            p._pvb_ready = None
+
+
+def wait_ready(p: torch.Tensor) -> None:
+    """Make the current stream wait for an in-flight all-gather of ``p``'s rows (``ShardSpec.all_gather_rows``)."""
+    ev = getattr(p, "_pvb_ready", None)
+    if ev is not None:
+        torch.cuda.current_stream(p.device).wait_event(ev)
 
 
 class GradientExchange:
@@ -96,9 +132,12 @@ class GradientExchange:
         # ``trained_through``: the forward of THIS step read the weight through its bf16 shadow (ops.HeadBf16Fn /
         # Fc1Bf16Fn).  A step that went through the fp32 head (training batch > 128 per GPU) reads the fp32 master,
         # whose rows owned by other ranks are stale under a row-sharded optimiser: such a step must all-reduce.
-        return (self.shard_large and shadow is not None and getattr(shadow, "geom", None) is not None
-                and getattr(shadow, "trained_through", False) and p.dim() == 2
-                and p.shape[0] % self.world_size == 0 and p.grad.is_contiguous())
+        rows_ok = (self.shard_large and p.dim() == 2 and p.shape[0] % self.world_size == 0 and p.grad.is_contiguous()
+                   and p.is_contiguous())
+        if shadow is None:
+            # fp32 mode: rows sharded, the updated fp32 rows are all-gathered in place under the next forward pass
+            return rows_ok
+        return rows_ok and getattr(shadow, "geom", None) is not None and getattr(shadow, "trained_through", False)
 
     def _reduce_scatter_async(self, p: torch.nn.Parameter) -> None:
         """Sum of the gradient rows this rank owns, in place in ``p.grad`` (the other rows keep the local values)."""
@@ -147,6 +186,9 @@ class GradientExchange:
         """All-gather the fp32 master rows of the sharded parameters (each rank only keeps its own rows current).
         Called before ``state_dict()``; a collective: every rank must call it."""
         for p in self._sharded:
+            if getattr(p, "_pvb_shadow", None) is None:
+                wait_ready(p)  # fp32 mode: the rows are re-gathered after every step, only the transfer may be in flight
+                continue
             lo, hi = p._pvb_shard.rows(p.shape[0])
             flat = p.data.view(-1)
             n = p.shape[1]

@@ -229,6 +229,12 @@ class Model(BaseModel):
             self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, wn, bn,
             self.fc3.weight, self.fc3.bias, self.fc4.weight, self.fc4.bias,
         )
+        if getattr(self.fc1.weight, "_pvb_ready", None) is not None:
+            # data parallel, fp32 mode: the rows of fc1.weight updated by the other ranks are still arriving on the
+            # communication stream (dp.ShardSpec.all_gather_rows); the head is their first reader
+            from ...dp import wait_ready
+
+            wait_ready(self.fc1.weight)
         out = ops.HeadBf16Fn.apply(link, *head_args) if bf16_head else ops.HeadFn.apply(*head_args)
         out = out.reshape(batch_size, self.forecast_len)
         return out

@@ -48,6 +48,20 @@ class FusedAdam(torch.optim.Optimizer):
                 st["step"] = int(st["step"]) + 1
                 grad = p.grad.data if p.grad.is_contiguous() else p.grad.data.contiguous()
                 shadow = getattr(p, "_pvb_shadow", None)
+                shard0 = getattr(p, "_pvb_shard", None)
+                if shadow is None and shard0 is not None:
+                    # fp32 mode under data parallelism: dp.GradientExchange reduce-scattered the gradient rows this rank
+                    # owns; Adam on those rows only (same kernel on the contiguous row range), then the updated rows of
+                    # every rank are all-gathered in place on the communication stream
+                    lo, hi = shard0.rows(p.shape[0])
+                    n = p[0].numel()
+                    sl = slice(lo * n, hi * n)
+                    b1, b2 = group["betas"]
+                    ops.adam_step([p.data.view(-1)[sl]], [grad.view(-1)[sl]], [st["exp_avg"].view(-1)[sl]],
+                                  [st["exp_avg_sq"].view(-1)[sl]], group["lr"], b1, b2, group["eps"], st["step"], self.grad_scale)
+                    shard0.all_gather_rows(p)
+                    p._pvb_gen = getattr(p, "_pvb_gen", 0) + 1
+                    continue
                 if shadow is not None:
                     # fc1.weight in bf16 mode: Adam + refresh of the tensor-core shadow in one pass over the weight
                     b1, b2 = group["betas"]

@@ -199,6 +199,60 @@ def test_sharded_large_parameter_two_ranks_gloo():
     assert rows == {(0, 64), (64, 128)}
 
 
+def _worker_fp32_rows(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from predict_pv_yield_b200.dp import GradientExchange
+
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.ReLU(), torch.nn.Linear(128, 3))
+        big = model[0].weight  # no shadow: the fp32 row-sharded path
+        ref = torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.ReLU(), torch.nn.Linear(128, 3))
+        ref.load_state_dict(model.state_dict())
+        ex = GradientExchange(model, large_numel=4096, shard_large=True)
+        ref_opt = torch.optim.SGD([ref[0].weight], lr=0.1)
+        ok = True
+        for step in range(3):
+            g = torch.Generator().manual_seed(100 * step + rank)
+            x, y = torch.randn(8, 64, generator=g), torch.randn(8, 3, generator=g)
+            model.zero_grad()
+            ((model(x) - y) ** 2).mean().backward()
+            ex.finish()
+            spec = big._pvb_shard
+            lo, hi = spec.rows(128)
+            with torch.no_grad():  # this rank's rows only (what FusedAdam does with the Adam kernel), then the row all-gather
+                big.data[lo:hi] -= 0.1 * big.grad[lo:hi] / world
+            spec.all_gather_rows(big)
+            ref.zero_grad()
+            ((ref(x) - y) ** 2).mean().backward()
+            gr = ref[0].weight.grad.clone()
+            dist.all_reduce(gr)
+            ref[0].weight.grad.copy_(gr / world)
+            ref_opt.step()
+            ok = ok and torch.allclose(big.data, ref[0].weight.data, atol=1e-6)  # EVERY row is current after the gather
+        q.put((rank, bool(ok), spec.rows(128)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fp32_row_sharded_parameter_two_ranks_gloo():
+    """fp32 mode: rows of the large parameter are updated by their owner and all-gathered in place every step."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fp32_rows, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert {r for _, _, r in res} == {(0, 64), (64, 128)}
+
+
 def test_gradient_exchange_requires_process_group():
     from predict_pv_yield_b200.dp import GradientExchange
 
