@@ -184,13 +184,15 @@ int pvb200_conv3d_dgrad_tf32x3(const float* gz_padded, const float* w, const flo
                                void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
                                int out_pad, int pad_t, pvb200_stream_t stream);
 
-/* weight / bias gradient of the same layers on the tensor cores (3xTF32; conv3d_wgrad_tf32x3.cu): dw [Cout][Cin][3][3][3],
+/* weight / bias gradient of the same layers on the tensor cores (conv3d_wgrad_bf16x3.cu: kind::tf32 cannot read the
+ * position-strided operands this reduction needs, so every fp32 value is split EXACTLY into three bf16 pieces and six of
+ * the nine piece products run as kind::f16 MMAs -- the same tensor time as 3xTF32, fp32-class accuracy): dw [Cout][Cin][3][3][3],
  * db [Cout] (or null) from x blocked fp32 [B][G(Cin)][Ti][Hi][Wi][4] and the pre-activation gradient gz blocked fp32,
  * zero-padded by gz_pad on T, H, W (2 = the tensor the data gradient reads, 0 = plain).  `supported` says whether the
  * layer fits (Cin, Cout <= 32, rows that fit shared memory); otherwise use pvb200_conv3d_wgrad_f32. */
-int pvb200_conv3d_wgrad_tf32x3_supported(int Cin, int Cout, int Hi, int Wi);
-size_t pvb200_conv3d_wgrad_tf32x3_workspace_bytes(void);
-int pvb200_conv3d_wgrad_tf32x3(const float* xb, const float* gzb, int gz_pad, float* dw, float* db, void* workspace,
+int pvb200_conv3d_wgrad_bf16x3_supported(int Cin, int Cout, int Hi, int Wi);
+size_t pvb200_conv3d_wgrad_bf16x3_workspace_bytes(void);
+int pvb200_conv3d_wgrad_bf16x3(const float* xb, const float* gzb, int gz_pad, float* dw, float* db, void* workspace,
                                size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
                                pvb200_stream_t stream);
 

@@ -1,0 +1,445 @@
+// conv3d_wgrad_bf16x3.cu -- a11 in fp32 MODE on the tensor cores: the Conv3d 3x3x3 weight (and bias) gradient as
+// tcgen05.mma.kind::f16 GEMMs over a THREE-WAY bf16 split of the fp32 operands (fp32-class accuracy).
+//
+// Reference: autograd of nn.Conv3d, predict_pv_yield/models/conv3d/model.py:80-90,117-120:
+//   dW[co][ci][kt][kh][kw] = sum_{b,t,h,w} gz[b][co][t][h][w] * x[b][ci][t+kt][h+kh][w+kw],   db[co] = sum gz.
+//
+// Why not 3xTF32 like the forward / data gradient (conv3d_igemm_tf32x3.cu): the reduction runs over output positions, so
+// positions are the K dimension and both operands must be read "MN-major" (channels contiguous, positions strided) from the
+// blocked layout.  kind::tf32 returns ZEROS for MN-major SWIZZLE_NONE operands (tools/probe/tf32_mn_probe.cu; CUTLASS:
+// "for mn-major tf32 operands, SW128_32B is the only available smem layout", a 32-bit-granular swizzle bulk copies cannot
+// produce).  kind::f16 has no such restriction, and an fp32 value is EXACTLY the sum of three bf16 values
+// (v = b0 + b1 + b2, 8 + 8 + 8 significand bits, round-to-nearest residuals), so
+//   x . g = x0 g0 + x0 g1 + x1 g0 + x1 g1 + x0 g2 + x2 g0      (the dropped terms are <= 2^-24 relative)
+// costs six K = 16 MMAs per 16 positions -- the same tensor time as three K = 8 TF32 MMAs per 8 positions.
+//
+// GEMM shape.  One step of the kernel = one input plane p of one sample and one output row h:
+//   * the TMA engine stages the raw fp32 rows (bulk copies: the three input rows h..h+2 of a channel group are contiguous
+//     in memory; row h of the gradient planes p, p-1, p-2); eight "split" warps turn them into the three bf16 pieces in
+//     the operand layout [group of 8 channels][row][position][8] (two fp32 channel groups merge into one bf16 group).
+//   * A (M = 128): pieces of the input rows as [g][kh][Wi]: M-group m = 3 g + kh sits at the uniform stride Wi * 16 B, so
+//     the kh taps cost no copies; M-group 3 G8 is a constant row of ones (bias gradient for free); the remaining M rows
+//     read whatever follows inside the buffer and are never looked at.
+//   * the kw taps are the descriptor START address (kw * 16 B): three accumulators, no copies.
+//   * B (N = 96): pieces of the gradient rows as [kt][g][WP] (WP = Wo rounded up to 16, the padding stays zero): plane p
+//     contributes to the three time taps at once; taps that fall outside the output are cut off by narrowing N.
+//   => per step 3 (kw) x WP/16 x 6 MMAs of 128 x 96 x 16 (72 for a 62-wide row) against 48 KB of fp32 operands from L2
+//      (rows are re-read by neighbouring steps: L2 hits; DRAM sees each tensor once).
+// Accuracy.  The tensor core's fp32 accumulator rounds toward zero (tools/probe/tf32_acc_probe.cu): every kFlush steps the
+// three accumulators are drained and added -- in fp32 round-to-nearest, by the drain warps -- to the CTA's private
+// partial in global memory (L2 resident, 147 KB per CTA); the drain of one accumulator overlaps the MMAs of the other two.
+// A second kernel reduces the per-CTA partials in fixed order (deterministic) into dW [Co][Ci][3][3][3] and db.
+// Warp roles (448 threads): warp 0 producer (lane-parallel bulk copies), warp 1 MMA issuer + TMEM owner, warps 2-9
+// split, warps 10-13 accumulator drain.  Pipeline: raw staging (one buffer) -> pieces (two buffers) -> MMA.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace pvb {
+
+constexpr int kW3Threads = 448;
+constexpr int kW3SplitWarps = 8;
+constexpr int kW3Stages = 2;    // piece buffers
+constexpr int kW3Flush = 8;     // steps between two drains of the accumulators
+constexpr int kW3AccCols = 96;  // TMEM columns per kw accumulator
+constexpr int kW3Pairs = 6;     // products of the three-way split that are kept
+
+struct W3Args {
+  const uint4* x;   // blocked fp32 [B][G][Ti][Hi][Wi] 16-byte elements (4 channels)
+  const uint4* gz;  // blocked fp32 gradient; element (b, go, t, h, 0) at gz_off0 + b*gz_sb + go*gz_sg + t*gz_st + h*gz_sh
+  long long gz_off0, gz_sb, gz_sg, gz_st, gz_sh;
+  float* partial;   // [grid][3 kw][128][96]
+  int B, G, Ti, Hi, Wi;  // G: fp32 groups of 4 channels (even)
+  int GOr;          // gradient fp32 channel groups present in memory (even)
+  int CoP;          // 16 or 32: columns per time tap (N = 3 * CoP)
+  int To, Ho, Wo, WP;
+  int plane_off;    // input plane of output t, tap kt: t + kt + plane_off
+  long long steps;  // B * Ti * Ho
+};
+
+__device__ __forceinline__ void w3_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
+}
+
+// v = b0 + b1 + b2 exactly (round-to-nearest pieces: every residual is exact in fp32 and fits the next piece)
+__device__ __forceinline__ void w3_split(float v, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  const __nv_bfloat16 b0 = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(b0);
+  const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(b1);
+  const __nv_bfloat16 b2 = __float2bfloat16_rn(r2);
+  p0 = __bfloat16_as_ushort(b0); p1 = __bfloat16_as_ushort(b1); p2 = __bfloat16_as_ushort(b2);
+}
+// two fp32 channel groups (8 channels of one position) -> the three bf16 pieces (16 bytes each)
+__device__ __forceinline__ void w3_split8(const float4 lo4, const float4 hi4, uint4& q0, uint4& q1, uint4& q2) {
+  const float f[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+  uint32_t a[8], b[8], c[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w3_split(f[i], a[i], b[i], c[i]);
+  q0 = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), a[4] | (a[5] << 16), a[6] | (a[7] << 16));
+  q1 = make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));
+  q2 = make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), c[6] | (c[7] << 16));
+}
+
+struct W3Step {
+  int b, p, h, kt_lo, kt_hi;  // time taps kt_lo..kt_hi of plane p fall on existing outputs (kt_lo > kt_hi: none)
+};
+__device__ __forceinline__ W3Step w3_step(long long s, const W3Args& a) {
+  W3Step r;
+  r.h = static_cast<int>(s % a.Ho);
+  const long long bp = s / a.Ho;
+  r.p = static_cast<int>(bp % a.Ti);
+  r.b = static_cast<int>(bp / a.Ti);
+  // t = p - kt - plane_off in [0, To)
+  const int tmax = r.p - a.plane_off;  // kt = 0
+  int lo = tmax - (a.To - 1);
+  r.kt_lo = lo > 0 ? lo : 0;
+  r.kt_hi = tmax < 2 ? tmax : 2;
+  return r;
+}
+
+// smem layout (bytes): [0,128) barriers | [128,256) a zero core matrix | piece buffers: stage s = A pieces 0..2 (a_piece
+// bytes each), for s = 0,1, then stage s = B pieces 0..2 (b_piece bytes each) | raw fp32 staging: A rows, B rows
+__global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(const W3Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem);  // [1] raw rows landed
+  uint64_t* raw_empty = raw_full + 1;                       // [1] raw rows converted
+  uint64_t* ready = raw_empty + 1;                          // [2] pieces written
+  uint64_t* empty = ready + kW3Stages;                      // [2] pieces consumed
+  uint64_t* afull = empty + kW3Stages;                      // [3] accumulator kw complete (flush window closed)
+  uint64_t* aempty = afull + 3;                             // [3] accumulator kw drained
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty + 3);
+  const int G = a.G, G8 = a.G / 2, Wi = a.Wi, WP = a.WP, CoP = a.CoP;
+  const int GP8 = CoP / 8;                                                   // gradient groups of 8 per time tap in the pieces
+  const uint32_t a_piece = ((static_cast<uint32_t>(3 * G8 + 4) * Wi * 16u) + 127u) & ~127u;  // staged rows + ones rows + slack
+  const uint32_t b_piece = static_cast<uint32_t>(3 * GP8 * WP) * 16u;
+  const uint32_t a_raw_bytes = static_cast<uint32_t>(G * 3 * Wi) * 16u;
+  const uint32_t b_raw_bytes = static_cast<uint32_t>(3 * a.GOr * WP) * 16u;
+  uint8_t* a_s = smem + 256;                          // [stage][piece]
+  uint8_t* b_s = a_s + kW3Stages * 3u * a_piece;      // [stage][piece]
+  uint8_t* a_raw = b_s + kW3Stages * 3u * b_piece;
+  uint8_t* b_raw = a_raw + a_raw_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // zero everything once: padding positions / groups, the slack rows and the zero core matrix stay zero for the whole kernel
+  {
+    const uint32_t total16 = (128u + kW3Stages * 3u * (a_piece + b_piece) + a_raw_bytes + b_raw_bytes) >> 4;
+    uint4* z = reinterpret_cast<uint4*>(smem + 128);
+    for (uint32_t i = threadIdx.x; i < total16; i += kW3Threads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  // the ones rows of piece 0 (M-group 3 G8 = "row" 3 G8 of the operand layout); pieces 1, 2 keep zeros there
+  for (int s = 0; s < kW3Stages; ++s) {
+    uint4* ones = reinterpret_cast<uint4*>(a_s + (s * 3u) * a_piece) + static_cast<uint32_t>(3 * G8) * Wi;
+    for (int i = threadIdx.x; i < 3 * Wi; i += kW3Threads) ones[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+  }
+  if (threadIdx.x == 0) {
+    tc::mbar_init(raw_full, 1);
+    tc::mbar_init(raw_empty, kW3SplitWarps);
+    for (int i = 0; i < kW3Stages; ++i) { tc::mbar_init(ready + i, kW3SplitWarps); tc::mbar_init(empty + i, 1); }
+    for (int i = 0; i < 3; ++i) { tc::mbar_init(afull + i, 1); tc::mbar_init(aempty + i, 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
+  tc::fence_proxy_async();  // the zero / ones fill is read by the tensor core
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const long long s_begin = a.steps * blockIdx.x / gridDim.x;
+  const long long s_end = a.steps * (blockIdx.x + 1) / gridDim.x;
+  const long long in_plane = static_cast<long long>(a.Hi) * Wi;
+
+  if (warp == 0) {
+    // =============================== producer ===============================
+    uint32_t seq = 0;
+    for (long long s = s_begin; s < s_end; ++s, ++seq) {
+      const W3Step st = w3_step(s, a);
+      const int nb = st.kt_hi - st.kt_lo + 1;
+      if (lane == 0) {
+        tc::mbar_wait(raw_empty, (seq & 1u) ^ 1u);
+        const uint32_t bytes = a_raw_bytes + (nb > 0 ? static_cast<uint32_t>(nb * a.GOr) * a.Wo * 16u : 0u);
+        tc::mbar_arrive_expect_tx(raw_full, bytes);
+      }
+      __syncwarp();
+      const int ncopy = G + (nb > 0 ? nb * a.GOr : 0);
+      for (int c = lane; c < ncopy; c += 32) {
+        if (c < G) {
+          const uint4* src = a.x + ((static_cast<long long>(st.b) * G + c) * a.Ti + st.p) * in_plane + static_cast<long long>(st.h) * Wi;
+          tc::bulk_g2s(a_raw + static_cast<uint32_t>(c) * 3u * Wi * 16u, src, 3u * Wi * 16u, raw_full);
+        } else {
+          const int j = c - G;
+          const int kt = st.kt_lo + j / a.GOr, go = j % a.GOr;
+          const int t = st.p - kt - a.plane_off;
+          const uint4* src = a.gz + a.gz_off0 + st.b * a.gz_sb + go * a.gz_sg + t * a.gz_st + st.h * a.gz_sh;
+          tc::bulk_g2s(b_raw + static_cast<uint32_t>((kt * a.GOr + go) * WP) * 16u, src, static_cast<uint32_t>(a.Wo) * 16u, raw_full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    const bool leader = tc::elect_one();
+    // MN-major SWIZZLE_NONE descriptors: SBO = stride between groups of 8 channels, LBO = stride between the two
+    // 8-position K groups of a K = 16 step (contiguous positions: 128 B)
+    const uint32_t a_hi_word = ((static_cast<uint32_t>(Wi) * 16u) >> 4) | (1u << 14);
+    const uint32_t b_hi_word = ((static_cast<uint32_t>(WP) * 16u) >> 4) | (1u << 14);
+    const uint32_t lbo_word = (128u >> 4) << 16;
+    const uint32_t a_addr16 = tc::smem_u32(a_s) >> 4, b_addr16 = tc::smem_u32(b_s) >> 4;
+    const uint32_t a_piece16 = a_piece >> 4, b_piece16 = b_piece >> 4;
+    const uint32_t idesc0 = tc::umma_idesc(128, 0, /*BF16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
+    const uint32_t idesc_blk = static_cast<uint32_t>(CoP >> 3) << 17;
+    // B operand of the MMA that opens a flush window: every N group reads the same all-zero core matrices (SBO = 0)
+    const uint32_t zero_lo = ((tc::smem_u32(smem + 128) >> 4) & 0x3fffu);  // LBO = 0 as well: both K groups read it
+    const uint32_t zero_hi = (1u << 14);
+    const int k16n = WP >> 4;
+    uint32_t seq = 0;
+    uint32_t nwin = 0;  // flush windows closed so far (phase of the accumulator barriers)
+    for (long long s = s_begin; s < s_end; ++s, ++seq) {
+      const W3Step st = w3_step(s, a);
+      const uint32_t stage = seq % kW3Stages;
+      const bool win_first = (seq % kW3Flush) == 0;
+      const bool win_last = ((seq + 1) % kW3Flush) == 0 || (s + 1 == s_end);
+      tc::mbar_wait(ready + stage, (seq / kW3Stages) & 1u);
+      tc::tc_fence_after();
+      const int nb = st.kt_hi - st.kt_lo + 1;
+      const uint32_t a0 = lbo_word | ((a_addr16 + (stage * 3u) * a_piece16) & 0x3fffu);
+      const uint32_t b0 = lbo_word | ((b_addr16 + (stage * 3u) * b_piece16 + static_cast<uint32_t>(st.kt_lo * GP8 * WP)) & 0x3fffu);
+      const uint32_t idesc = idesc0 + static_cast<uint32_t>(nb > 0 ? nb : 1) * idesc_blk;
+#pragma unroll 1
+      for (int kw = 0; kw < 3; ++kw) {
+        if (win_first) {
+          tc::mbar_wait(aempty + kw, (nwin & 1u) ^ 1u);  // the previous window of this accumulator has been drained
+          tc::tc_fence_after();
+        }
+        const uint32_t d = tmem_base + static_cast<uint32_t>(kw * kW3AccCols + st.kt_lo * CoP);
+        // a window opens with an MMA against the zero matrix that overwrites ALL three time-tap blocks of the accumulator
+        // (a narrowed step only touches its own columns: the others must not keep the drained window's values)
+        if (leader && win_first)
+          w3_mma(tmem_base + static_cast<uint32_t>(kw * kW3AccCols), a0, a_hi_word, zero_lo, zero_hi, idesc0 + 3u * idesc_blk, 0u);
+        if (leader && nb > 0) {
+#pragma unroll 1
+          for (int k16 = 0; k16 < k16n; ++k16) {
+            const uint32_t ao = static_cast<uint32_t>(k16 * 16 + kw), bo = static_cast<uint32_t>(k16 * 16);
+            // smallest products first: x0 g2, x2 g0, x1 g1, x1 g0, x0 g1, x0 g0
+            w3_mma(d, a0 + ao, a_hi_word, b0 + 2u * b_piece16 + bo, b_hi_word, idesc, 1u);
+            w3_mma(d, a0 + 2u * a_piece16 + ao, a_hi_word, b0 + bo, b_hi_word, idesc, 1u);
+            w3_mma(d, a0 + a_piece16 + ao, a_hi_word, b0 + b_piece16 + bo, b_hi_word, idesc, 1u);
+            w3_mma(d, a0 + a_piece16 + ao, a_hi_word, b0 + bo, b_hi_word, idesc, 1u);
+            w3_mma(d, a0 + ao, a_hi_word, b0 + b_piece16 + bo, b_hi_word, idesc, 1u);
+            w3_mma(d, a0 + ao, a_hi_word, b0 + bo, b_hi_word, idesc, 1u);
+          }
+        }
+        if (win_last && leader) tc::umma_commit(afull + kw);
+      }
+      if (leader) tc::umma_commit(empty + stage);
+      if (win_last) ++nwin;
+      __syncwarp();
+    }
+  } else if (warp < 2 + kW3SplitWarps) {
+    // =============================== split warps: fp32 rows -> three bf16 pieces in the operand layout ==============
+    const int tid = threadIdx.x - 64;
+    constexpr int NT = kW3SplitWarps * 32;
+    uint32_t seq = 0;
+    for (long long s = s_begin; s < s_end; ++s, ++seq) {
+      const W3Step st = w3_step(s, a);
+      const uint32_t stage = seq % kW3Stages;
+      tc::mbar_wait(empty + stage, ((seq / kW3Stages) & 1u) ^ 1u);  // the MMAs of the step that used these piece buffers are done
+      tc::mbar_wait(raw_full, seq & 1u);
+      const float4* ar = reinterpret_cast<const float4*>(a_raw);
+      uint4* ap0 = reinterpret_cast<uint4*>(a_s + (stage * 3u) * a_piece);
+      uint4* ap1 = reinterpret_cast<uint4*>(a_s + (stage * 3u + 1u) * a_piece);
+      uint4* ap2 = reinterpret_cast<uint4*>(a_s + (stage * 3u + 2u) * a_piece);
+      const int row = 3 * Wi;  // elements of one fp32 channel group (three rows)
+      for (int i = tid; i < G8 * row; i += NT) {
+        const int g8 = i / row, r = i - g8 * row;
+        uint4 q0, q1, q2;
+        w3_split8(ar[(2 * g8) * row + r], ar[(2 * g8 + 1) * row + r], q0, q1, q2);
+        ap0[i] = q0; ap1[i] = q1; ap2[i] = q2;
+      }
+      const int nb = st.kt_hi - st.kt_lo + 1;
+      if (nb > 0) {
+        const float4* br = reinterpret_cast<const float4*>(b_raw);
+        uint4* bp0 = reinterpret_cast<uint4*>(b_s + (stage * 3u) * b_piece);
+        uint4* bp1 = reinterpret_cast<uint4*>(b_s + (stage * 3u + 1u) * b_piece);
+        uint4* bp2 = reinterpret_cast<uint4*>(b_s + (stage * 3u + 2u) * b_piece);
+        const int go8 = a.GOr / 2;
+        const int nitem = nb * go8 * WP;
+        for (int i = tid; i < nitem; i += NT) {
+          const int w = i % WP;
+          const int g8 = (i / WP) % go8;
+          const int kt = st.kt_lo + i / (WP * go8);
+          uint4 q0, q1, q2;
+          w3_split8(br[(kt * a.GOr + 2 * g8) * WP + w], br[(kt * a.GOr + 2 * g8 + 1) * WP + w], q0, q1, q2);
+          const int o = (kt * GP8 + g8) * WP + w;
+          bp0[o] = q0; bp1[o] = q1; bp2[o] = q2;
+        }
+      }
+      tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(ready + stage);
+        tc::mbar_arrive(raw_empty);  // the raw rows have been read: the next step's copies may land
+      }
+    }
+  } else {
+    // =============================== accumulator drain (warps 10..13) ===============================
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+    const long long nsteps = s_end - s_begin;
+    const long long nwin_total = (nsteps + kW3Flush - 1) / kW3Flush;
+    float* mine = a.partial + static_cast<size_t>(blockIdx.x) * 3 * 128 * kW3AccCols + static_cast<size_t>(row) * kW3AccCols;
+    for (long long wdx = 0; wdx < nwin_total; ++wdx) {
+      for (int kw = 0; kw < 3; ++kw) {
+        tc::mbar_wait(afull + kw, static_cast<uint32_t>(wdx & 1));
+        tc::tc_fence_after();
+        float* dst = mine + static_cast<size_t>(kw) * 128 * kW3AccCols;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kW3AccCols; c0 += 32) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(lane_addr + static_cast<uint32_t>(kw * kW3AccCols + c0), v);
+          tc::tmem_ld_wait();
+          float4* d4 = reinterpret_cast<float4*>(dst + c0);
+          if (wdx == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3]));
+          } else {
+            float4 o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = d4[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              d4[j] = make_float4(o[j].x + __uint_as_float(v[4 * j]), o[j].y + __uint_as_float(v[4 * j + 1]),
+                                  o[j].z + __uint_as_float(v[4 * j + 2]), o[j].w + __uint_as_float(v[4 * j + 3]));
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(aempty + kw);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// dW[co][ci][kt][kh][kw] = sum over CTAs of partial[cta][kw][(3*(ci/8) + kh)*8 + ci%8][kt*CoP + co];
+// db[co] = sum over CTAs of partial[cta][0][(3*G8)*8][kt_bias*CoP + co]  (the row of ones against the time tap kt_bias = pad_t,
+// the one tap for which every output plane t = p meets an existing input plane exactly once)
+__global__ void wgrad_bf16x3_reduce_kernel(const float* __restrict__ partial, int ncta, float* __restrict__ dw, float* __restrict__ db,
+                                           int Ci, int Co, int G8, int CoP, int kt_bias) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = Co * Ci * 27;
+  const size_t per_cta = static_cast<size_t>(3) * 128 * kW3AccCols;
+  if (idx < total) {
+    const int tap = idx % 27;
+    const int ci = (idx / 27) % Ci;
+    const int co = idx / (27 * Ci);
+    const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+    const size_t off = (static_cast<size_t>(kw) * 128 + ((3 * (ci >> 3) + kh) * 8 + (ci & 7))) * kW3AccCols + kt * CoP + co;
+    float s = 0.f;
+    for (int c = 0; c < ncta; ++c) s += partial[c * per_cta + off];
+    dw[idx] = s;
+  } else if (idx < total + Co && db) {
+    const int co = idx - total;
+    const size_t off = (static_cast<size_t>(3 * G8) * 8) * kW3AccCols + kt_bias * CoP + co;
+    float s = 0.f;
+    for (int c = 0; c < ncta; ++c) s += partial[c * per_cta + off];
+    db[co] = s;
+  }
+}
+
+static int w3_groups(int C) { return 2 * ceil_div(C, 8); }
+static int w3_cop(int Co) { return Co <= 16 ? 16 : 32; }
+
+static size_t w3_smem_bytes(int G, int GOr, int Wi, int Wo, int CoP) {
+  const size_t WP = round_up(Wo, 16);
+  const size_t a_piece = round_up(static_cast<size_t>(3 * (G / 2) + 4) * Wi * 16, static_cast<size_t>(128));
+  const size_t b_piece = static_cast<size_t>(3) * (CoP / 8) * WP * 16;
+  return 256 + kW3Stages * 3 * (a_piece + b_piece) + static_cast<size_t>(G) * 3 * Wi * 16 + static_cast<size_t>(3) * GOr * WP * 16;
+}
+
+}  // namespace pvb
+
+extern "C" {
+
+/* 1 when the tensor-core weight gradient takes this layer (channel counts <= 32, rows that fit shared memory) */
+int pvb200_conv3d_wgrad_bf16x3_supported(int Cin, int Cout, int Hi, int Wi) {
+  using namespace pvb;
+  if (Cin <= 0 || Cout <= 0 || Cin > 32 || Cout > 32 || Hi < 3 || Wi < 3) return 0;
+  const int G = w3_groups(Cin);
+  // the M = 128 instruction reads 16 row groups at stride Wi*16 from the start of an A piece: it must stay inside the allocation
+  const size_t smem = w3_smem_bytes(G, w3_groups(Cout), Wi, Wi - 2, w3_cop(Cout));
+  const size_t a_piece = round_up(static_cast<size_t>(3 * (G / 2) + 4) * Wi * 16, static_cast<size_t>(128));
+  const size_t last_a = 256 + (3 * kW3Stages - 1) * a_piece;
+  const size_t reach = last_a + static_cast<size_t>(16) * Wi * 16 + static_cast<size_t>(round_up(Wi, 16) + 16) * 16;
+  return (smem <= 227 * 1024 && reach <= smem) ? 1 : 0;
+}
+
+size_t pvb200_conv3d_wgrad_bf16x3_workspace_bytes(void) {
+  int sms = pvb::sm_count();
+  if (sms <= 0) sms = 148;
+  return static_cast<size_t>(sms) * 3 * 128 * pvb::kW3AccCols * sizeof(float);
+}
+
+/* dw [Cout][Cin][3][3][3], db [Cout] (or null) from x blocked fp32 [B][G(Cin)][Ti][Hi][Wi][4] and the pre-activation gradient
+ * gz blocked fp32, zero-padded by gz_pad on T, H, W ([B][G(Cout)][To+2p][Ho+2p][Wo+2p][4], To = Ti + 2 pad_t - 2): the
+ * padded tensor the data gradient reads (gz_pad = 2) or a plain one (gz_pad = 0) */
+int pvb200_conv3d_wgrad_bf16x3(const float* xb, const float* gzb, int gz_pad, float* dw, float* db, void* workspace,
+                               size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
+                               pvb200_stream_t stream) {
+  using namespace pvb;
+  PVB_REQUIRE(xb && gzb && dw, "conv3d_wgrad_bf16x3: null pointer");
+  PVB_REQUIRE(B > 0 && gz_pad >= 0 && (pad_t == 0 || pad_t == 1), "conv3d_wgrad_bf16x3: bad argument");
+  PVB_REQUIRE(pvb200_conv3d_wgrad_bf16x3_supported(Cin, Cout, Hi, Wi), "conv3d_wgrad_bf16x3: Cin=%d Cout=%d plane %dx%d is not "
+              "supported by the tensor-core weight gradient (use pvb200_conv3d_wgrad_f32)", Cin, Cout, Hi, Wi);
+  W3Args a;
+  a.x = reinterpret_cast<const uint4*>(xb);
+  a.gz = reinterpret_cast<const uint4*>(gzb);
+  a.B = B; a.G = w3_groups(Cin); a.Ti = Ti; a.Hi = Hi; a.Wi = Wi;
+  a.GOr = w3_groups(Cout); a.CoP = w3_cop(Cout);
+  a.To = Ti + 2 * pad_t - 2; a.Ho = Hi - 2; a.Wo = Wi - 2; a.WP = round_up(a.Wo, 16);
+  PVB_REQUIRE(a.To > 0, "conv3d_wgrad_bf16x3: input too short");
+  a.plane_off = -pad_t;
+  const long long Tz = a.To + 2 * gz_pad, Hz = a.Ho + 2 * gz_pad, Wz = a.Wo + 2 * gz_pad;
+  a.gz_sh = Wz; a.gz_st = Hz * Wz; a.gz_sg = Tz * Hz * Wz; a.gz_sb = a.gz_sg * a.GOr;
+  a.gz_off0 = (static_cast<long long>(gz_pad) * Hz + gz_pad) * Wz + gz_pad;
+  a.steps = static_cast<long long>(B) * Ti * a.Ho;
+  const int sms = sm_count();
+  PVB_REQUIRE(sms > 0, "conv3d_wgrad_bf16x3: no CUDA device");
+  long long grid = a.steps < sms ? a.steps : sms;
+  const size_t need = static_cast<size_t>(grid) * 3 * 128 * kW3AccCols * sizeof(float);
+  if (!workspace || workspace_bytes < need) {
+    set_error("conv3d_wgrad_bf16x3: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return PVB200_ERR_WORKSPACE;
+  }
+  PVB_REQUIRE(reinterpret_cast<uintptr_t>(xb) % 16 == 0 && reinterpret_cast<uintptr_t>(gzb) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "conv3d_wgrad_bf16x3: pointers must be 16-byte aligned");
+  a.partial = static_cast<float*>(workspace);
+  const size_t smem = w3_smem_bytes(a.G, a.GOr, Wi, a.Wo, a.CoP);
+  PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv3d_wgrad_bf16x3_kernel<<<static_cast<unsigned>(grid), kW3Threads, smem, as_stream(stream)>>>(a);
+  PVB_LAUNCHED("conv3d_wgrad_bf16x3");
+  const int total = Cout * Cin * 27 + Cout;
+  wgrad_bf16x3_reduce_kernel<<<ceil_div(total, 128), 128, 0, as_stream(stream)>>>(a.partial, static_cast<int>(grid), dw, db, Cin, Cout,
+                                                                                  a.G / 2, a.CoP, pad_t);
+  PVB_LAUNCHED("wgrad_bf16x3_reduce");
+  return PVB200_OK;
+}
+
+}  // extern "C"

@@ -99,9 +99,9 @@ SIGNATURES = {
                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_dgrad_tf32x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "pvb200_conv3d_wgrad_tf32x3_supported": (c_int, [c_int, c_int, c_int, c_int]),
-    "pvb200_conv3d_wgrad_tf32x3_workspace_bytes": (c_size_t, []),
-    "pvb200_conv3d_wgrad_tf32x3": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+    "pvb200_conv3d_wgrad_bf16x3_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "pvb200_conv3d_wgrad_bf16x3_workspace_bytes": (c_size_t, []),
+    "pvb200_conv3d_wgrad_bf16x3": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_fwd_f32_pad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -467,11 +467,11 @@ def conv3d_dgrad_tf32x3(gz_padded: torch.Tensor, w: torch.Tensor, mask_blk: Opti
     return gx_blk, gx_nc
 
 
-def wgrad_tf32x3_supported(Ci: int, Co: int, Hi: int, Wi: int) -> bool:
-    return bool(_lib.load().pvb200_conv3d_wgrad_tf32x3_supported(Ci, Co, Hi, Wi))
+def wgrad_bf16x3_supported(Ci: int, Co: int, Hi: int, Wi: int) -> bool:
+    return bool(_lib.load().pvb200_conv3d_wgrad_bf16x3_supported(Ci, Co, Hi, Wi))
 
 
-def conv3d_wgrad_tf32x3(xb: torch.Tensor, gzb: torch.Tensor, Ci: int, Co: int, gz_pad: int = 0,
+def conv3d_wgrad_bf16x3(xb: torch.Tensor, gzb: torch.Tensor, Ci: int, Co: int, gz_pad: int = 0,
                         pad_t: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """(dw [Co,Ci,3,3,3], db [Co]) on the tensor cores (3xTF32) from x blocked fp32 [B,G,Ti,Hi,Wi,4] and the pre-activation
     gradient blocked fp32, zero-padded by ``gz_pad`` on T, H, W (2 = the tensor the data gradient reads)."""
@@ -482,15 +482,15 @@ def conv3d_wgrad_tf32x3(xb: torch.Tensor, gzb: torch.Tensor, Ci: int, Co: int, g
     To, Ho, Wo = Ti + 2 * pad_t - 2, Hi - 2, Wi - 2
     want = (B, blocked4_groups(Co), To + 2 * gz_pad, Ho + 2 * gz_pad, Wo + 2 * gz_pad, 4)
     if e != 4 or G != blocked4_groups(Ci) or tuple(gzb.shape) != want:
-        raise RuntimeError(f"conv3d_wgrad_tf32x3: shapes {tuple(xb.shape)} / {tuple(gzb.shape)} inconsistent (expected gz {want})")
+        raise RuntimeError(f"conv3d_wgrad_bf16x3: shapes {tuple(xb.shape)} / {tuple(gzb.shape)} inconsistent (expected gz {want})")
     dw = torch.empty((Co, Ci, 3, 3, 3), dtype=torch.float32, device=xb.device)
     db = torch.empty((Co,), dtype=torch.float32, device=xb.device)
-    ws = _workspace("wgrad_tf32x3", L.pvb200_conv3d_wgrad_tf32x3_workspace_bytes(), xb.device)
+    ws = _workspace("wgrad_bf16x3", L.pvb200_conv3d_wgrad_bf16x3_workspace_bytes(), xb.device)
     npos = B * To * Ho * Wo
-    with _timed(f"conv3d_wgrad_tf32x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 4.0 * xb.numel() + 16.0 * blocked4_groups(Co) * npos):
-        rc = L.pvb200_conv3d_wgrad_tf32x3(_p(xb), _p(gzb), gz_pad, _p(dw), _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
+    with _timed(f"conv3d_wgrad_bf16x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 4.0 * xb.numel() + 16.0 * blocked4_groups(Co) * npos):
+        rc = L.pvb200_conv3d_wgrad_bf16x3(_p(xb), _p(gzb), gz_pad, _p(dw), _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
                                           _stream())
-    _lib.check(rc, "conv3d_wgrad_tf32x3")
+    _lib.check(rc, "conv3d_wgrad_bf16x3")
     return dw, db
 
 
@@ -561,7 +561,7 @@ class EncoderFn(torch.autograd.Function):
 
 class EncoderTf32Fn(torch.autograd.Function):
     """Conv3d stack of the fp32 mode on the tensor cores (3xTF32: forward, data gradient AND weight gradient at fp32-class
-    accuracy, csrc/conv3d_igemm_tf32x3.cu / conv3d_wgrad_tf32x3.cu).
+    accuracy, csrc/conv3d_igemm_tf32x3.cu / conv3d_wgrad_bf16x3.cu).
 
     forward(sat, mean, std, w0, b0, ...) -> features fp32 [B, cnn_output_size] (NCDHW flatten order, model.py:122).
     Activations and gradients live blocked ([B,G,T,H,W,4], what the tensor-core kernels read); the last activation is
@@ -575,7 +575,7 @@ class EncoderTf32Fn(torch.autograd.Function):
         n = len(wb) // 2
         B, _, T, H, W = sat.shape
         # per layer: does the tensor-core weight gradient take it?  (input plane of layer l: H - 2l)
-        tc_w = [wgrad_tf32x3_supported(wb[2 * l].shape[1], wb[2 * l].shape[0], H - 2 * l, W - 2 * l) for l in range(n)]
+        tc_w = [wgrad_bf16x3_supported(wb[2 * l].shape[1], wb[2 * l].shape[0], H - 2 * l, W - 2 * l) for l in range(n)]
         if sat.dtype == torch.int16:
             x_blk = sat_normalise_blocked_f32(sat, mean, std)
             x_nc = None if tc_w[0] else sat_normalise(sat, mean, std)
@@ -615,7 +615,7 @@ class EncoderTf32Fn(torch.autograd.Function):
         for l in range(n - 1, -1, -1):
             Co, Ci = wb[2 * l].shape[0], wb[2 * l].shape[1]
             if tc_w[l]:
-                dw, db = conv3d_wgrad_tf32x3(ins_blk[l], gz_blk, Ci, Co, gz_pad=gz_pad)
+                dw, db = conv3d_wgrad_bf16x3(ins_blk[l], gz_blk, Ci, Co, gz_pad=gz_pad)
             else:
                 dw, db = conv3d_wgrad(ins_nc[l], gz_nc)
             grads[2 * l], grads[2 * l + 1] = dw, db

@@ -167,9 +167,9 @@ WGRAD_SHAPES = [
 
 @pytest.mark.parametrize("shape", WGRAD_SHAPES)
 @pytest.mark.parametrize("gz_pad", [0, 2])
-def test_conv3d_wgrad_tf32x3(ops, dev, shape, gz_pad):
+def test_conv3d_wgrad_bf16x3(ops, dev, shape, gz_pad):
     B, Ci, T, H, W, Co = shape
-    assert ops.wgrad_tf32x3_supported(Ci, Co, H, W)
+    assert ops.wgrad_bf16x3_supported(Ci, Co, H, W)
     x, w, b = _case(shape, seed=4)
     g = torch.Generator().manual_seed(5)
     gz = torch.randn((B, Co, T - 2, H - 2, W - 2), generator=g)
@@ -178,15 +178,15 @@ def test_conv3d_wgrad_tf32x3(ops, dev, shape, gz_pad):
     F.conv3d(x.double(), wd, bd).backward(gz.double())
     xb = ops.to_blocked_f32(x.to(dev))
     gzb = ops.to_blocked_f32(gz.to(dev), pad=gz_pad)
-    dw, db = ops.conv3d_wgrad_tf32x3(xb, gzb, Ci, Co, gz_pad=gz_pad)
+    dw, db = ops.conv3d_wgrad_bf16x3(xb, gzb, Ci, Co, gz_pad=gz_pad)
     e_w, e_b = nerr(dw, wd.grad), nerr(db, bd.grad)
     print(f"tf32x3 wgrad {shape} pad {gz_pad}: dw {e_w:.2e} db {e_b:.2e}")
     assert e_w <= TOL and e_b <= TOL
-    dw2, db2 = ops.conv3d_wgrad_tf32x3(xb, gzb, Ci, Co, gz_pad=gz_pad)  # deterministic: same bits on a second run
+    dw2, db2 = ops.conv3d_wgrad_bf16x3(xb, gzb, Ci, Co, gz_pad=gz_pad)  # deterministic: same bits on a second run
     assert torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
-def test_conv3d_wgrad_tf32x3_time_padded(ops, dev):
+def test_conv3d_wgrad_bf16x3_time_padded(ops, dev):
     shape = (2, 32, 5, 10, 10, 32)
     B, Ci, T, H, W, Co = shape
     x, w, b = _case(shape, seed=6)
@@ -195,19 +195,19 @@ def test_conv3d_wgrad_tf32x3_time_padded(ops, dev):
     wd = w.double().requires_grad_(True)
     bd = b.double().requires_grad_(True)
     F.conv3d(x.double(), wd, bd, padding=(1, 0, 0)).backward(gz.double())
-    dw, db = ops.conv3d_wgrad_tf32x3(ops.to_blocked_f32(x.to(dev)), ops.to_blocked_f32(gz.to(dev), pad=2), Ci, Co, gz_pad=2, pad_t=1)
+    dw, db = ops.conv3d_wgrad_bf16x3(ops.to_blocked_f32(x.to(dev)), ops.to_blocked_f32(gz.to(dev), pad=2), Ci, Co, gz_pad=2, pad_t=1)
     assert nerr(dw, wd.grad) <= TOL and nerr(db, bd.grad) <= TOL
 
 
-def test_conv3d_wgrad_tf32x3_rejects_wide_planes(ops, dev):
+def test_conv3d_wgrad_bf16x3_rejects_wide_planes(ops, dev):
     """128-wide rows (the deep variant's first layers) do not fit the staging buffers: the host says so and the encoder
     keeps those layers on the fp32 FMA weight gradient."""
     from predict_pv_yield_b200 import lib
 
-    assert not ops.wgrad_tf32x3_supported(32, 32, 126, 126)
-    assert ops.wgrad_tf32x3_supported(32, 32, 64, 64)
+    assert not ops.wgrad_bf16x3_supported(32, 32, 126, 126)
+    assert ops.wgrad_bf16x3_supported(32, 32, 64, 64)
     L = lib.load()
-    rc = L.pvb200_conv3d_wgrad_tf32x3(1, 1, 0, 1, 1, 1, 0, 1, 32, 3, 126, 126, 32, 0, 0)
+    rc = L.pvb200_conv3d_wgrad_bf16x3(1, 1, 0, 1, 1, 1, 0, 1, 32, 3, 126, 126, 32, 0, 0)
     assert rc != 0 and b"not supported" in L.pvb200_last_error()
 
 
