@@ -29,8 +29,8 @@
 // three accumulators are drained and added -- in fp32 round-to-nearest, by the drain warps -- to the CTA's private
 // partial in global memory (L2 resident, 147 KB per CTA); the drain of one accumulator overlaps the MMAs of the other two.
 // A second kernel reduces the per-CTA partials in fixed order (deterministic) into dW [Co][Ci][3][3][3] and db.
-// Warp roles (448 threads): warp 0 producer (lane-parallel bulk copies), warp 1 MMA issuer + TMEM owner, warps 2-9
-// split, warps 10-13 accumulator drain.  Pipeline: raw staging (one buffer) -> pieces (two buffers) -> MMA.
+// Warp roles (704 threads): warp 0 producer (lane-parallel bulk copies), warp 1 MMA issuer + TMEM owner, warps 2-9
+// split, warps 10-21 accumulator drain (four warps per kw accumulator).  Pipeline: raw staging (one buffer) -> pieces (two buffers) -> MMA.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -38,10 +38,10 @@
 
 namespace pvb {
 
-constexpr int kW3Threads = 448;
+constexpr int kW3Threads = 704;   // 2 + 8 split + 12 drain warps
 constexpr int kW3SplitWarps = 8;
 constexpr int kW3Stages = 2;    // piece buffers
-constexpr int kW3Flush = 8;     // steps between two drains of the accumulators
+constexpr int kW3Flush = 16;    // steps between two drains of the accumulators
 constexpr int kW3AccCols = 96;  // TMEM columns per kw accumulator
 constexpr int kW3Pairs = 6;     // products of the three-way split that are kept
 
@@ -49,13 +49,14 @@ struct W3Args {
   const uint4* x;   // blocked fp32 [B][G][Ti][Hi][Wi] 16-byte elements (4 channels)
   const uint4* gz;  // blocked fp32 gradient; element (b, go, t, h, 0) at gz_off0 + b*gz_sb + go*gz_sg + t*gz_st + h*gz_sh
   long long gz_off0, gz_sb, gz_sg, gz_st, gz_sh;
-  float* partial;   // [grid][3 kw][128][96]
+  float* partial;   // [grid][3 kw][96 columns][128 rows]
   int B, G, Ti, Hi, Wi;  // G: fp32 groups of 4 channels (even)
   int GOr;          // gradient fp32 channel groups present in memory (even)
   int CoP;          // 16 or 32: columns per time tap (N = 3 * CoP)
   int To, Ho, Wo, WP;
   int plane_off;    // input plane of output t, tap kt: t + kt + plane_off
   long long steps;  // B * Ti * Ho
+  int dbg_flags;    // tools only: 1 = no bulk copies, 2 = no split arithmetic, 4 = no MMAs, 8 = no drain traffic
 };
 
 __device__ __forceinline__ void w3_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
@@ -72,24 +73,31 @@ __device__ __forceinline__ void w3_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t 
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
 }
 
-// v = b0 + b1 + b2 exactly (round-to-nearest pieces: every residual is exact in fp32 and fits the next piece)
-__device__ __forceinline__ void w3_split(float v, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
-  const __nv_bfloat16 b0 = __float2bfloat16_rn(v);
-  const float r1 = v - __bfloat162float(b0);
-  const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(b1);
-  const __nv_bfloat16 b2 = __float2bfloat16_rn(r2);
-  p0 = __bfloat16_as_ushort(b0); p1 = __bfloat16_as_ushort(b1); p2 = __bfloat16_as_ushort(b2);
+// v = b0 + b1 + b2 exactly (round-to-nearest pieces: every residual is exact in fp32 and fits the next piece), two values
+// at a time: cvt.rn.bf16x2.f32 is one full-rate instruction (SASS F2FP.BF16.F32.PACK_AB; the scalar F2F.BF16.F32 runs
+// on the quarter-rate conversion pipe and made the split warps the bottleneck of the kernel)
+__device__ __forceinline__ void w3_split2(float v0, float v1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(v1), "f"(v0));  // high half <- first source
+  const float r0 = v0 - __uint_as_float(p0 << 16), r1 = v1 - __uint_as_float(p0 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(r1), "f"(r0));
+  const float s0 = r0 - __uint_as_float(p1 << 16), s1 = r1 - __uint_as_float(p1 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(s1), "f"(s0));
 }
 // two fp32 channel groups (8 channels of one position) -> the three bf16 pieces (16 bytes each)
 __device__ __forceinline__ void w3_split8(const float4 lo4, const float4 hi4, uint4& q0, uint4& q1, uint4& q2) {
-  const float f[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-  uint32_t a[8], b[8], c[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) w3_split(f[i], a[i], b[i], c[i]);
-  q0 = make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), a[4] | (a[5] << 16), a[6] | (a[7] << 16));
-  q1 = make_uint4(b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));
-  q2 = make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), c[6] | (c[7] << 16));
+  w3_split2(lo4.x, lo4.y, q0.x, q1.x, q2.x);
+  w3_split2(lo4.z, lo4.w, q0.y, q1.y, q2.y);
+  w3_split2(hi4.x, hi4.y, q0.z, q1.z, q2.z);
+  w3_split2(hi4.z, hi4.w, q0.w, q1.w, q2.w);
+}
+
+__device__ __forceinline__ float w3_ld_keep(const float* p, uint64_t policy) {
+  float v;
+  asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy) : "memory");
+  return v;
+}
+__device__ __forceinline__ void w3_st_keep(float* p, float v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
 }
 
 struct W3Step {
@@ -171,9 +179,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       if (lane == 0) {
         tc::mbar_wait(raw_empty, (seq & 1u) ^ 1u);
         const uint32_t bytes = a_raw_bytes + (nb > 0 ? static_cast<uint32_t>(nb * a.GOr) * a.Wo * 16u : 0u);
-        tc::mbar_arrive_expect_tx(raw_full, bytes);
+        if (a.dbg_flags & 1) tc::mbar_arrive(raw_full); else tc::mbar_arrive_expect_tx(raw_full, bytes);
       }
       __syncwarp();
+      if (a.dbg_flags & 1) continue;
       const int ncopy = G + (nb > 0 ? nb * a.GOr : 0);
       for (int c = lane; c < ncopy; c += 32) {
         if (c < G) {
@@ -228,9 +237,11 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
         // (a narrowed step only touches its own columns: the others must not keep the drained window's values)
         if (leader && win_first)
           w3_mma(tmem_base + static_cast<uint32_t>(kw * kW3AccCols), a0, a_hi_word, zero_lo, zero_hi, idesc0 + 3u * idesc_blk, 0u);
-        if (leader && nb > 0) {
-#pragma unroll 1
-          for (int k16 = 0; k16 < k16n; ++k16) {
+        if (leader && nb > 0 && !(a.dbg_flags & 4)) {
+          // fully unrolled (rows of at most 64 positions): the rolled loop issued one MMA per ~75 clk instead of ~55
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            if (k16 >= k16n) break;
             const uint32_t ao = static_cast<uint32_t>(k16 * 16 + kw), bo = static_cast<uint32_t>(k16 * 16);
             // smallest products first: x0 g2, x2 g0, x1 g1, x1 g0, x0 g1, x0 g0
             w3_mma(d, a0 + ao, a_hi_word, b0 + 2u * b_piece16 + bo, b_hi_word, idesc, 1u);
@@ -251,6 +262,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     // =============================== split warps: fp32 rows -> three bf16 pieces in the operand layout ==============
     const int tid = threadIdx.x - 64;
     constexpr int NT = kW3SplitWarps * 32;
+    // first item and per-iteration increments of this thread in the two item spaces (A: rows of 3 Wi, B: rows of WP)
+    const int a_g0 = tid / (3 * Wi), a_r0 = tid % (3 * Wi), a_dg = NT / (3 * Wi), a_dr = NT % (3 * Wi);
+    const int b_r0 = tid / WP, b_w0 = tid % WP, b_dr = NT / WP, b_dw = NT % WP;
+    const int go8 = a.GOr / 2;
     uint32_t seq = 0;
     for (long long s = s_begin; s < s_end; ++s, ++seq) {
       const W3Step st = w3_step(s, a);
@@ -262,28 +277,34 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       uint4* ap1 = reinterpret_cast<uint4*>(a_s + (stage * 3u + 1u) * a_piece);
       uint4* ap2 = reinterpret_cast<uint4*>(a_s + (stage * 3u + 2u) * a_piece);
       const int row = 3 * Wi;  // elements of one fp32 channel group (three rows)
-      for (int i = tid; i < G8 * row; i += NT) {
-        const int g8 = i / row, r = i - g8 * row;
-        uint4 q0, q1, q2;
-        w3_split8(ar[(2 * g8) * row + r], ar[(2 * g8 + 1) * row + r], q0, q1, q2);
-        ap0[i] = q0; ap1[i] = q1; ap2[i] = q2;
+      // item i = (g8, r): no divisions in the loop -- (g8, r) advance incrementally from the thread's first item
+      {
+        int g8 = a_g0, r = a_r0;
+        for (int i = tid; i < ((a.dbg_flags & 2) ? 0 : G8 * row); i += NT) {
+          uint4 q0, q1, q2;
+          w3_split8(ar[(2 * g8) * row + r], ar[(2 * g8 + 1) * row + r], q0, q1, q2);
+          ap0[i] = q0; ap1[i] = q1; ap2[i] = q2;
+          r += a_dr; g8 += a_dg;
+          if (r >= row) { r -= row; ++g8; }
+        }
       }
       const int nb = st.kt_hi - st.kt_lo + 1;
-      if (nb > 0) {
+      if (nb > 0 && !(a.dbg_flags & 2)) {
         const float4* br = reinterpret_cast<const float4*>(b_raw);
         uint4* bp0 = reinterpret_cast<uint4*>(b_s + (stage * 3u) * b_piece);
         uint4* bp1 = reinterpret_cast<uint4*>(b_s + (stage * 3u + 1u) * b_piece);
         uint4* bp2 = reinterpret_cast<uint4*>(b_s + (stage * 3u + 2u) * b_piece);
-        const int go8 = a.GOr / 2;
-        const int nitem = nb * go8 * WP;
-        for (int i = tid; i < nitem; i += NT) {
-          const int w = i % WP;
-          const int g8 = (i / WP) % go8;
-          const int kt = st.kt_lo + i / (WP * go8);
+        const int nrow = nb * go8;  // (kt, g8) rows of WP positions
+        int rw = b_r0, w = b_w0;
+        for (; rw < nrow;) {
+          const int ktl = rw / go8;  // go8 <= 4, nb <= 3: a handful of values, the compiler turns this into compares
+          const int g8 = rw - ktl * go8, kt = st.kt_lo + ktl;
           uint4 q0, q1, q2;
           w3_split8(br[(kt * a.GOr + 2 * g8) * WP + w], br[(kt * a.GOr + 2 * g8 + 1) * WP + w], q0, q1, q2);
           const int o = (kt * GP8 + g8) * WP + w;
           bp0[o] = q0; bp1[o] = q1; bp2[o] = q2;
+          w += b_dw; rw += b_dr;
+          if (w >= WP) { w -= WP; ++rw; }
         }
       }
       tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
@@ -294,42 +315,53 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       }
     }
   } else {
-    // =============================== accumulator drain (warps 10..13) ===============================
+    // =============================== accumulator drain (warps 10..21) ===============================
+    // three groups of four warps (one per TMEM lane quadrant), group g drains accumulator kw = g only: the read-modify-write
+    // of one accumulator's partial (L2 latency bound) no longer delays the release of the next one
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
     const long long nsteps = s_end - s_begin;
     const long long nwin_total = (nsteps + kW3Flush - 1) / kW3Flush;
-    float* mine = a.partial + static_cast<size_t>(blockIdx.x) * 3 * 128 * kW3AccCols + static_cast<size_t>(row) * kW3AccCols;
+    float* mine = a.partial + static_cast<size_t>(blockIdx.x) * 3 * 128 * kW3AccCols + row;  // [kw][column][row]
+    // the partials (22 MB over the grid) are re-read every window while ~100 MB of operands stream through L2 in between:
+    // without a retention hint they were evicted and every read-modify-write went to DRAM
+    uint64_t keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+    const int kw = (warp - 2 - kW3SplitWarps) >> 2;
     for (long long wdx = 0; wdx < nwin_total; ++wdx) {
-      for (int kw = 0; kw < 3; ++kw) {
+      {
         tc::mbar_wait(afull + kw, static_cast<uint32_t>(wdx & 1));
         tc::tc_fence_after();
         float* dst = mine + static_cast<size_t>(kw) * 128 * kW3AccCols;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kW3AccCols; c0 += 32) {
-          uint32_t v[32];
-          tc::tmem_ld_32x32(lane_addr + static_cast<uint32_t>(kw * kW3AccCols + c0), v);
+        // the whole accumulator row goes to registers first and the accumulator is handed back to the MMA warp at once:
+        // the read-modify-write of the partial (L2 latency) then overlaps the next window's MMAs instead of stalling them
+        uint32_t v[3][32];
+        if (!(a.dbg_flags & 8)) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) tc::tmem_ld_32x32(lane_addr + static_cast<uint32_t>(kw * kW3AccCols + c * 32), v[c]);
           tc::tmem_ld_wait();
-          float4* d4 = reinterpret_cast<float4*>(dst + c0);
-          if (wdx == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                  __uint_as_float(v[4 * j + 3]));
-          } else {
-            float4 o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = d4[j];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              d4[j] = make_float4(o[j].x + __uint_as_float(v[4 * j]), o[j].y + __uint_as_float(v[4 * j + 1]),
-                                  o[j].z + __uint_as_float(v[4 * j + 2]), o[j].w + __uint_as_float(v[4 * j + 3]));
-          }
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(aempty + kw);
+        if (a.dbg_flags & (8 | 16)) continue;  // 16: accumulators read and released, no partial traffic
+        // partial layout [kw][column][row]: a warp's 32 rows of one column are 128 contiguous bytes (one wavefront per
+        // instruction; the row-major layout cost 32 sectors per instruction and put the drain on the critical path)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float* pc = dst + static_cast<size_t>(c * 32) * 128;
+          float o[32];
+          if (wdx != 0) {  // all 32 loads in flight before the first add (one L2 round trip per 32 columns, not 32)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = w3_ld_keep(pc + j * 128, keep);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w3_st_keep(pc + j * 128, o[j] + __uint_as_float(v[c][j]), keep);
+        }
       }
     }
   }
@@ -338,8 +370,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// dW[co][ci][kt][kh][kw] = sum over CTAs of partial[cta][kw][(3*(ci/8) + kh)*8 + ci%8][kt*CoP + co];
-// db[co] = sum over CTAs of partial[cta][0][(3*G8)*8][kt_bias*CoP + co]  (the row of ones against the time tap kt_bias = pad_t,
+// dW[co][ci][kt][kh][kw] = sum over CTAs of partial[cta][kw][kt*CoP + co][(3*(ci/8) + kh)*8 + ci%8];
+// db[co] = sum over CTAs of partial[cta][0][kt_bias*CoP + co][(3*G8)*8]  (the row of ones against the time tap kt_bias = pad_t,
 // the one tap for which every output plane t = p meets an existing input plane exactly once)
 __global__ void wgrad_bf16x3_reduce_kernel(const float* __restrict__ partial, int ncta, float* __restrict__ dw, float* __restrict__ db,
                                            int Ci, int Co, int G8, int CoP, int kt_bias) {
@@ -351,18 +383,20 @@ __global__ void wgrad_bf16x3_reduce_kernel(const float* __restrict__ partial, in
     const int ci = (idx / 27) % Ci;
     const int co = idx / (27 * Ci);
     const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-    const size_t off = (static_cast<size_t>(kw) * 128 + ((3 * (ci >> 3) + kh) * 8 + (ci & 7))) * kW3AccCols + kt * CoP + co;
+    const size_t off = (static_cast<size_t>(kw) * kW3AccCols + kt * CoP + co) * 128 + ((3 * (ci >> 3) + kh) * 8 + (ci & 7));
     float s = 0.f;
     for (int c = 0; c < ncta; ++c) s += partial[c * per_cta + off];
     dw[idx] = s;
   } else if (idx < total + Co && db) {
     const int co = idx - total;
-    const size_t off = (static_cast<size_t>(3 * G8) * 8) * kW3AccCols + kt_bias * CoP + co;
+    const size_t off = static_cast<size_t>(kt_bias * CoP + co) * 128 + (3 * G8) * 8;
     float s = 0.f;
     for (int c = 0; c < ncta; ++c) s += partial[c * per_cta + off];
     db[co] = s;
   }
 }
+
+int g_w3_dbg_flags = 0;  // set through pvb200_debug_set_wgrad_flags (tools only)
 
 static int w3_groups(int C) { return 2 * ceil_div(C, 8); }
 static int w3_cop(int Co) { return Co <= 16 ? 16 : 32; }
@@ -378,6 +412,9 @@ static size_t w3_smem_bytes(int G, int GOr, int Wi, int Wo, int CoP) {
 
 extern "C" {
 
+/* tools only (not declared in pvb200.h): switch parts of the weight-gradient kernel off to time the others */
+void pvb200_debug_set_wgrad_flags(int f) { pvb::g_w3_dbg_flags = f; }
+
 /* 1 when the tensor-core weight gradient takes this layer (channel counts <= 32, rows that fit shared memory) */
 int pvb200_conv3d_wgrad_bf16x3_supported(int Cin, int Cout, int Hi, int Wi) {
   using namespace pvb;
@@ -388,7 +425,7 @@ int pvb200_conv3d_wgrad_bf16x3_supported(int Cin, int Cout, int Hi, int Wi) {
   const size_t a_piece = round_up(static_cast<size_t>(3 * (G / 2) + 4) * Wi * 16, static_cast<size_t>(128));
   const size_t last_a = 256 + (3 * kW3Stages - 1) * a_piece;
   const size_t reach = last_a + static_cast<size_t>(16) * Wi * 16 + static_cast<size_t>(round_up(Wi, 16) + 16) * 16;
-  return (smem <= 227 * 1024 && reach <= smem) ? 1 : 0;
+  return (smem <= 227 * 1024 && reach <= smem && Wi - 2 <= 64) ? 1 : 0;
 }
 
 size_t pvb200_conv3d_wgrad_bf16x3_workspace_bytes(void) {
@@ -420,6 +457,7 @@ int pvb200_conv3d_wgrad_bf16x3(const float* xb, const float* gzb, int gz_pad, fl
   a.gz_sh = Wz; a.gz_st = Hz * Wz; a.gz_sg = Tz * Hz * Wz; a.gz_sb = a.gz_sg * a.GOr;
   a.gz_off0 = (static_cast<long long>(gz_pad) * Hz + gz_pad) * Wz + gz_pad;
   a.steps = static_cast<long long>(B) * Ti * a.Ho;
+  a.dbg_flags = g_w3_dbg_flags;
   const int sms = sm_count();
   PVB_REQUIRE(sms > 0, "conv3d_wgrad_bf16x3: no CUDA device");
   long long grid = a.steps < sms ? a.steps : sms;
