@@ -31,6 +31,7 @@
 // A second kernel reduces the per-CTA partials in fixed order (deterministic) into dW [Co][Ci][3][3][3] and db.
 // Warp roles (704 threads): warp 0 producer (lane-parallel bulk copies), warp 1 MMA issuer + TMEM owner, warps 2-9
 // split, warps 10-21 accumulator drain (four warps per kw accumulator).  Pipeline: raw staging (one buffer) -> pieces (two buffers) -> MMA.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -46,9 +47,7 @@ constexpr int kW3AccCols = 96;  // TMEM columns per kw accumulator
 constexpr int kW3Pairs = 6;     // products of the three-way split that are kept
 
 struct W3Args {
-  const uint4* x;   // blocked fp32 [B][G][Ti][Hi][Wi] 16-byte elements (4 channels)
-  const uint4* gz;  // blocked fp32 gradient; element (b, go, t, h, 0) at gz_off0 + b*gz_sb + go*gz_sg + t*gz_st + h*gz_sh
-  long long gz_off0, gz_sb, gz_sg, gz_st, gz_sh;
+  int gz_pad;       // zero padding of the gradient tensor on T, H, W (coordinates of the gradient's tensor map are shifted by it)
   float* partial;   // [grid][3 kw][96 columns][128 rows]
   int B, G, Ti, Hi, Wi;  // G: fp32 groups of 4 channels (even)
   int GOr;          // gradient fp32 channel groups present in memory (even)
@@ -71,6 +70,15 @@ __device__ __forceinline__ void w3_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t 
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "}" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
+}
+
+// one tiled TMA load of a 5-D box (SASS UTMALDG): coordinates innermost first; out-of-bounds elements arrive as zeros
+__device__ __forceinline__ void w3_tma_5d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          tc::smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
 }
 
 // v = b0 + b1 + b2 exactly (round-to-nearest pieces: every residual is exact in fp32 and fits the next piece), two values
@@ -103,23 +111,36 @@ __device__ __forceinline__ void w3_st_keep(float* p, float v, uint64_t policy) {
 struct W3Step {
   int b, p, h, kt_lo, kt_hi;  // time taps kt_lo..kt_hi of plane p fall on existing outputs (kt_lo > kt_hi: none)
 };
+__device__ __forceinline__ void w3_taps(W3Step& r, const W3Args& a) {
+  // t = p - kt - plane_off in [0, To)
+  const int tmax = r.p - a.plane_off;  // kt = 0
+  const int lo = tmax - (a.To - 1);
+  r.kt_lo = lo > 0 ? lo : 0;
+  r.kt_hi = tmax < 2 ? tmax : 2;
+}
+// step s = (b * Ti + p) * Ho + h: decoded once per role (64-bit divisions), then advanced incrementally -- the per-step
+// divisions sat on the MMA warp's issue path and left the tensor pipe idle at every step boundary
 __device__ __forceinline__ W3Step w3_step(long long s, const W3Args& a) {
   W3Step r;
   r.h = static_cast<int>(s % a.Ho);
   const long long bp = s / a.Ho;
   r.p = static_cast<int>(bp % a.Ti);
   r.b = static_cast<int>(bp / a.Ti);
-  // t = p - kt - plane_off in [0, To)
-  const int tmax = r.p - a.plane_off;  // kt = 0
-  int lo = tmax - (a.To - 1);
-  r.kt_lo = lo > 0 ? lo : 0;
-  r.kt_hi = tmax < 2 ? tmax : 2;
+  w3_taps(r, a);
   return r;
+}
+__device__ __forceinline__ void w3_next(W3Step& r, const W3Args& a) {
+  if (++r.h == a.Ho) {
+    r.h = 0;
+    if (++r.p == a.Ti) { r.p = 0; ++r.b; }
+    w3_taps(r, a);
+  }
 }
 
 // smem layout (bytes): [0,128) barriers | [128,256) a zero core matrix | piece buffers: stage s = A pieces 0..2 (a_piece
 // bytes each), for s = 0,1, then stage s = B pieces 0..2 (b_piece bytes each) | raw fp32 staging: A rows, B rows
-__global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(const W3Args a) {
+__global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(const W3Args a, const __grid_constant__ CUtensorMap tm_x,
+                                                                            const __grid_constant__ CUtensorMap tm_gz) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem);  // [1] raw rows landed
   uint64_t* raw_empty = raw_full + 1;                       // [1] raw rows converted
@@ -132,17 +153,18 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
   const int GP8 = CoP / 8;                                                   // gradient groups of 8 per time tap in the pieces
   const uint32_t a_piece = ((static_cast<uint32_t>(3 * G8 + 4) * Wi * 16u) + 127u) & ~127u;  // staged rows + ones rows + slack
   const uint32_t b_piece = static_cast<uint32_t>(3 * GP8 * WP) * 16u;
-  const uint32_t a_raw_bytes = static_cast<uint32_t>(G * 3 * Wi) * 16u;
-  const uint32_t b_raw_bytes = static_cast<uint32_t>(3 * a.GOr * WP) * 16u;
+  const uint32_t a_raw_bytes = static_cast<uint32_t>(G * 3 * Wi) * 16u;        // box [G][3 rows][Wi] of x
+  const uint32_t a_raw_span = (a_raw_bytes + 127u) & ~127u;
+  const uint32_t b_raw_bytes = static_cast<uint32_t>(a.GOr * 3 * a.Wo) * 16u;  // box [GOr][3 planes][Wo] of gz
   uint8_t* a_s = smem + 256;                          // [stage][piece]
   uint8_t* b_s = a_s + kW3Stages * 3u * a_piece;      // [stage][piece]
   uint8_t* a_raw = b_s + kW3Stages * 3u * b_piece;
-  uint8_t* b_raw = a_raw + a_raw_bytes;
+  uint8_t* b_raw = a_raw + a_raw_span;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // zero everything once: padding positions / groups, the slack rows and the zero core matrix stay zero for the whole kernel
   {
-    const uint32_t total16 = (128u + kW3Stages * 3u * (a_piece + b_piece) + a_raw_bytes + b_raw_bytes) >> 4;
+    const uint32_t total16 = (128u + kW3Stages * 3u * (a_piece + b_piece) + a_raw_span + b_raw_bytes) >> 4;
     uint4* z = reinterpret_cast<uint4*>(smem + 128);
     for (uint32_t i = threadIdx.x; i < total16; i += kW3Threads) z[i] = make_uint4(0, 0, 0, 0);
   }
@@ -168,34 +190,25 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
 
   const long long s_begin = a.steps * blockIdx.x / gridDim.x;
   const long long s_end = a.steps * (blockIdx.x + 1) / gridDim.x;
-  const long long in_plane = static_cast<long long>(a.Hi) * Wi;
-
   if (warp == 0) {
     // =============================== producer ===============================
     uint32_t seq = 0;
-    for (long long s = s_begin; s < s_end; ++s, ++seq) {
-      const W3Step st = w3_step(s, a);
-      const int nb = st.kt_hi - st.kt_lo + 1;
+    W3Step st = w3_step(s_begin, a);
+    for (long long s = s_begin; s < s_end; ++s, ++seq, w3_next(st, a)) {
+      // two tiled TMA loads per step (tensor maps, SASS UTMALDG) instead of 32 small bulk copies: the three input rows
+      // of every channel group, and row h of the three gradient planes t = p - off - 2 .. p - off of every group (planes
+      // outside the tensor arrive as zeros: out-of-bounds fill / the tensor's own zero padding)
       if (lane == 0) {
         tc::mbar_wait(raw_empty, (seq & 1u) ^ 1u);
-        const uint32_t bytes = a_raw_bytes + (nb > 0 ? static_cast<uint32_t>(nb * a.GOr) * a.Wo * 16u : 0u);
-        if (a.dbg_flags & 1) tc::mbar_arrive(raw_full); else tc::mbar_arrive_expect_tx(raw_full, bytes);
-      }
-      __syncwarp();
-      if (a.dbg_flags & 1) continue;
-      const int ncopy = G + (nb > 0 ? nb * a.GOr : 0);
-      for (int c = lane; c < ncopy; c += 32) {
-        if (c < G) {
-          const uint4* src = a.x + ((static_cast<long long>(st.b) * G + c) * a.Ti + st.p) * in_plane + static_cast<long long>(st.h) * Wi;
-          tc::bulk_g2s(a_raw + static_cast<uint32_t>(c) * 3u * Wi * 16u, src, 3u * Wi * 16u, raw_full);
+        if (a.dbg_flags & 1) {
+          tc::mbar_arrive(raw_full);
         } else {
-          const int j = c - G;
-          const int kt = st.kt_lo + j / a.GOr, go = j % a.GOr;
-          const int t = st.p - kt - a.plane_off;
-          const uint4* src = a.gz + a.gz_off0 + st.b * a.gz_sb + go * a.gz_sg + t * a.gz_st + st.h * a.gz_sh;
-          tc::bulk_g2s(b_raw + static_cast<uint32_t>((kt * a.GOr + go) * WP) * 16u, src, static_cast<uint32_t>(a.Wo) * 16u, raw_full);
+          tc::mbar_arrive_expect_tx(raw_full, a_raw_bytes + b_raw_bytes);
+          w3_tma_5d(a_raw, &tm_x, 0, st.h, st.p, 0, st.b, raw_full);
+          w3_tma_5d(b_raw, &tm_gz, a.gz_pad * 4, st.h + a.gz_pad, st.p - a.plane_off - 2 + a.gz_pad, 0, st.b, raw_full);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
@@ -215,8 +228,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     const int k16n = WP >> 4;
     uint32_t seq = 0;
     uint32_t nwin = 0;  // flush windows closed so far (phase of the accumulator barriers)
-    for (long long s = s_begin; s < s_end; ++s, ++seq) {
-      const W3Step st = w3_step(s, a);
+    W3Step st = w3_step(s_begin, a);
+    for (long long s = s_begin; s < s_end; ++s, ++seq, w3_next(st, a)) {
       const uint32_t stage = seq % kW3Stages;
       const bool win_first = (seq % kW3Flush) == 0;
       const bool win_last = ((seq + 1) % kW3Flush) == 0 || (s + 1 == s_end);
@@ -267,8 +280,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     const int b_r0 = tid / WP, b_w0 = tid % WP, b_dr = NT / WP, b_dw = NT % WP;
     const int go8 = a.GOr / 2;
     uint32_t seq = 0;
-    for (long long s = s_begin; s < s_end; ++s, ++seq) {
-      const W3Step st = w3_step(s, a);
+    W3Step st = w3_step(s_begin, a);
+    for (long long s = s_begin; s < s_end; ++s, ++seq, w3_next(st, a)) {
       const uint32_t stage = seq % kW3Stages;
       tc::mbar_wait(empty + stage, ((seq / kW3Stages) & 1u) ^ 1u);  // the MMAs of the step that used these piece buffers are done
       tc::mbar_wait(raw_full, seq & 1u);
@@ -299,8 +312,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
         for (; rw < nrow;) {
           const int ktl = rw / go8;  // go8 <= 4, nb <= 3: a handful of values, the compiler turns this into compares
           const int g8 = rw - ktl * go8, kt = st.kt_lo + ktl;
-          uint4 q0, q1, q2;
-          w3_split8(br[(kt * a.GOr + 2 * g8) * WP + w], br[(kt * a.GOr + 2 * g8 + 1) * WP + w], q0, q1, q2);
+          uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;  // positions beyond the row: the K padding of the operand
+          if (w < a.Wo)
+            w3_split8(br[((2 * g8) * 3 + (2 - kt)) * a.Wo + w], br[((2 * g8 + 1) * 3 + (2 - kt)) * a.Wo + w], q0, q1, q2);
           const int o = (kt * GP8 + g8) * WP + w;
           bp0[o] = q0; bp1[o] = q1; bp2[o] = q2;
           w += b_dw; rw += b_dr;
@@ -398,6 +412,34 @@ __global__ void wgrad_bf16x3_reduce_kernel(const float* __restrict__ partial, in
 
 int g_w3_dbg_flags = 0;  // set through pvb200_debug_set_wgrad_flags (tools only)
 
+// 5-D fp32 tensor map, dense (strides follow the dimensions), no swizzle / interleave, zero fill outside the tensor.  The
+// encoder is a host-only driver function, fetched through the runtime so that the library keeps linking only libcudart.
+static int w3_make_tensor_map(CUtensorMap* tm, const void* base, const unsigned long long dims[5], const unsigned box[5]) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  unsigned long long stride = 4;
+  for (int i = 0; i < 5; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    stride *= dims[i];
+    if (i < 4) gstr[i] = stride;  // byte stride of dimension i + 1
+  }
+  return static_cast<int>(encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), gdim, gstr, bx, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+}
+
 static int w3_groups(int C) { return 2 * ceil_div(C, 8); }
 static int w3_cop(int Co) { return Co <= 16 ? 16 : 32; }
 
@@ -405,7 +447,7 @@ static size_t w3_smem_bytes(int G, int GOr, int Wi, int Wo, int CoP) {
   const size_t WP = round_up(Wo, 16);
   const size_t a_piece = round_up(static_cast<size_t>(3 * (G / 2) + 4) * Wi * 16, static_cast<size_t>(128));
   const size_t b_piece = static_cast<size_t>(3) * (CoP / 8) * WP * 16;
-  return 256 + kW3Stages * 3 * (a_piece + b_piece) + static_cast<size_t>(G) * 3 * Wi * 16 + static_cast<size_t>(3) * GOr * WP * 16;
+  return 256 + kW3Stages * 3 * (a_piece + b_piece) + round_up(static_cast<size_t>(G) * 3 * Wi * 16, static_cast<size_t>(128)) + static_cast<size_t>(3) * GOr * Wo * 16;
 }
 
 }  // namespace pvb
@@ -425,7 +467,7 @@ int pvb200_conv3d_wgrad_bf16x3_supported(int Cin, int Cout, int Hi, int Wi) {
   const size_t a_piece = round_up(static_cast<size_t>(3 * (G / 2) + 4) * Wi * 16, static_cast<size_t>(128));
   const size_t last_a = 256 + (3 * kW3Stages - 1) * a_piece;
   const size_t reach = last_a + static_cast<size_t>(16) * Wi * 16 + static_cast<size_t>(round_up(Wi, 16) + 16) * 16;
-  return (smem <= 227 * 1024 && reach <= smem && Wi - 2 <= 64) ? 1 : 0;
+  return (smem <= 227 * 1024 && reach <= smem && Wi <= 64) ? 1 : 0;  // Wi * 4 floats = the 256-element limit of a TMA box dimension
 }
 
 size_t pvb200_conv3d_wgrad_bf16x3_workspace_bytes(void) {
@@ -446,16 +488,12 @@ int pvb200_conv3d_wgrad_bf16x3(const float* xb, const float* gzb, int gz_pad, fl
   PVB_REQUIRE(pvb200_conv3d_wgrad_bf16x3_supported(Cin, Cout, Hi, Wi), "conv3d_wgrad_bf16x3: Cin=%d Cout=%d plane %dx%d is not "
               "supported by the tensor-core weight gradient (use pvb200_conv3d_wgrad_f32)", Cin, Cout, Hi, Wi);
   W3Args a;
-  a.x = reinterpret_cast<const uint4*>(xb);
-  a.gz = reinterpret_cast<const uint4*>(gzb);
   a.B = B; a.G = w3_groups(Cin); a.Ti = Ti; a.Hi = Hi; a.Wi = Wi;
   a.GOr = w3_groups(Cout); a.CoP = w3_cop(Cout);
   a.To = Ti + 2 * pad_t - 2; a.Ho = Hi - 2; a.Wo = Wi - 2; a.WP = round_up(a.Wo, 16);
   PVB_REQUIRE(a.To > 0, "conv3d_wgrad_bf16x3: input too short");
   a.plane_off = -pad_t;
-  const long long Tz = a.To + 2 * gz_pad, Hz = a.Ho + 2 * gz_pad, Wz = a.Wo + 2 * gz_pad;
-  a.gz_sh = Wz; a.gz_st = Hz * Wz; a.gz_sg = Tz * Hz * Wz; a.gz_sb = a.gz_sg * a.GOr;
-  a.gz_off0 = (static_cast<long long>(gz_pad) * Hz + gz_pad) * Wz + gz_pad;
+  a.gz_pad = gz_pad;
   a.steps = static_cast<long long>(B) * Ti * a.Ho;
   a.dbg_flags = g_w3_dbg_flags;
   const int sms = sm_count();
@@ -471,7 +509,21 @@ int pvb200_conv3d_wgrad_bf16x3(const float* xb, const float* gzb, int gz_pad, fl
   a.partial = static_cast<float*>(workspace);
   const size_t smem = w3_smem_bytes(a.G, a.GOr, Wi, a.Wo, a.CoP);
   PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv3d_wgrad_bf16x3_kernel<<<static_cast<unsigned>(grid), kW3Threads, smem, as_stream(stream)>>>(a);
+  // tensor maps (fp32 elements, innermost dimension = one row of 4-channel elements): x [B][G][Ti][Hi][Wi*4] with the box
+  // [1][G][1][3][Wi*4]; gz [B][GOr][Tz][Hz][Wz*4] with the box [1][GOr][3][1][Wo*4]
+  CUtensorMap tm_x, tm_gz;
+  {
+    const unsigned long long Tz = a.To + 2 * gz_pad, Hz = a.Ho + 2 * gz_pad, Wz = a.Wo + 2 * gz_pad;
+    const unsigned long long xd[5] = {static_cast<unsigned long long>(Wi) * 4, static_cast<unsigned long long>(Hi), static_cast<unsigned long long>(Ti),
+                                      static_cast<unsigned long long>(a.G), static_cast<unsigned long long>(B)};
+    const unsigned xb_[5] = {static_cast<unsigned>(Wi) * 4, 3, 1, static_cast<unsigned>(a.G), 1};
+    const unsigned long long gd[5] = {Wz * 4, Hz, Tz, static_cast<unsigned long long>(a.GOr), static_cast<unsigned long long>(B)};
+    const unsigned gb_[5] = {static_cast<unsigned>(a.Wo) * 4, 1, 3, static_cast<unsigned>(a.GOr), 1};
+    const int r1 = w3_make_tensor_map(&tm_x, xb, xd, xb_);
+    const int r2 = w3_make_tensor_map(&tm_gz, gzb, gd, gb_);
+    PVB_REQUIRE(r1 == 0 && r2 == 0, "conv3d_wgrad_bf16x3: cuTensorMapEncodeTiled failed (%d, %d)", r1, r2);
+  }
+  conv3d_wgrad_bf16x3_kernel<<<static_cast<unsigned>(grid), kW3Threads, smem, as_stream(stream)>>>(a, tm_x, tm_gz);
   PVB_LAUNCHED("conv3d_wgrad_bf16x3");
   const int total = Cout * Cin * 27 + Cout;
   wgrad_bf16x3_reduce_kernel<<<ceil_div(total, 128), 128, 0, as_stream(stream)>>>(a.partial, static_cast<int>(grid), dw, db, Cin, Cout,
