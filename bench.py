@@ -515,13 +515,18 @@ def measure_train(torch, dist, job, args, steps, warmup, with_e2e, with_roofline
             for i in range(n * job.micro):
                 yield job.host[i % len(job.host)]
 
+        # allocated ONCE, outside the timed region: the prefetcher's device staging buffers and copy stream, the pinned
+        # words the losses are read back into (a cudaHostAlloc / cudaMalloc inside the region synchronises the device)
+        prefetcher = DevicePrefetcher(None, dev, depth=job.micro + 2)
+        loss_pinned = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+
         def run_steps(n):
             losses_host = []
-            loss_pinned = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
             loss_ready = [None, None]
             group = []
             i = 0
-            for batch in DevicePrefetcher(host_batches(n), dev, depth=job.micro + 2):
+            prefetcher.batches = host_batches(n)
+            for batch in prefetcher:
                 group.append(batch)
                 if len(group) < job.micro:
                     continue
