@@ -428,16 +428,21 @@ class Job:
 
     def parity_check(self):
         """Step-0 loss and forecast of the benchmarked batch (rank 0's first resident batch, initial weights) against the
-        CPU oracle on the same bits.  Tolerances of BASELINE.json: 1e-5 (fp32), 2e-2 (bf16), normalised max error."""
+        CPU oracle on the same bits.  Tolerances of BASELINE.json: 1e-5 (fp32), 2e-2 (bf16), normalised max error.
+        EVERY rank runs the device half (training_step averages its logged scalars over the ranks: a collective), rank 0
+        alone runs the oracle and returns the record."""
         torch, O = self.torch, self.O
         tol = 1e-5 if self.precision == "fp32" else 2e-2
         t0 = time.perf_counter()
+        with torch.no_grad():
+            y = self.model(self.resident[0]).float().cpu()
+            loss = float(self.model.training_step(self.resident[0], 0).detach()) if self.cfg["mode"] == "train" else None
+        if self.rank != 0:
+            return None
         om = O.OracleModel(**self.cfg["model"])
         om.batch_size = self.B
         om.load_state_dict({k: v.detach().cpu() for k, v in self.model.state_dict().items()})
         with torch.no_grad():
-            y = self.model(self.resident[0]).float().cpu()
-            loss = float(self.model.training_step(self.resident[0], 0).detach()) if self.cfg["mode"] == "train" else None
             torch.set_num_threads(host_threads())
             want = om(self.host[0])
             want_loss = float(om.training_step(self.host[0], 0)) if self.cfg["mode"] == "train" else None
@@ -661,7 +666,7 @@ def run_ours(args):
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
     job = Job(torch, args.config, precision, B, micro, world, rank, dev, args)
-    parity = job.parity_check() if (rank == 0 and not args.no_parity) else None
+    parity = job.parity_check() if not args.no_parity else None
     if world > 1:
         dist.barrier()
 
@@ -698,7 +703,7 @@ def run_ours(args):
                 m3 = (per + 127) // 128
                 b3 = per // m3
             j3 = Job(torch, "c3", "bf16", b3, m3, world, rank, dev, args)
-            p3 = j3.parity_check() if (rank == 0 and not args.no_parity and tag == "weak") else None
+            p3 = j3.parity_check() if (not args.no_parity and tag == "weak") else None
             if world > 1:
                 dist.barrier()
             r3 = measure_train(torch, dist, j3, args, args.steps, args.warmup, tag == "weak" and not args.no_e2e, tag == "weak")
