@@ -495,10 +495,21 @@ def measure_train(torch, dist, job, args, steps, warmup, with_e2e, with_roofline
     lib.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    trace = os.environ.get("PVB_BENCH_TRACE")  # diagnostics: per-step device and host times of the timed region on stderr
+    marks, t_host = [], []
     for i in range(steps):
         job.step(job.resident_batches(i), i)
+        if trace:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
+            t_host.append(time.perf_counter())
     e1.record()
     barrier()
+    if trace:
+        dev_ms = [round(e0.elapsed_time(m), 2) for m in marks]
+        print(f"[trace rank {rank} {job.cfg_name} B={B}x{job.micro}] device ms at step ends: {dev_ms}; host enqueue ms: "
+              f"{[round((t - t_host[0]) * 1e3, 1) for t in t_host]}", file=sys.stderr, flush=True)
     launches = lib.launch_count()
     ops.set_timer(None)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)

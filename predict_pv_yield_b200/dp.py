@@ -121,7 +121,10 @@ class GradientExchange:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
                 done = torch.cuda.Event()
                 done.record(comm)
-            t.record_stream(comm)
+            # no t.record_stream(comm): finish() makes the compute stream wait for `done` before the optimizer step, and
+            # the gradient is only freed after that (zero_grad of the next step), so stream order already protects the
+            # buffer.  record_stream deferred the free of the 565 MB gradient past the next allocation: the caching
+            # allocator then rotated through extra blocks and hit cudaMalloc (a ~100 ms host stall) inside training loops.
             self._pending.append((None, done))
         else:
             work = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -159,8 +162,7 @@ class GradientExchange:
                 dist.reduce_scatter_tensor(mine, flat, op=dist.ReduceOp.SUM, group=self.group)  # in place (NCCL)
                 done = torch.cuda.Event()
                 done.record(comm)
-            g.record_stream(comm)
-            self._pending.append((None, done))
+            self._pending.append((None, done))  # no record_stream: see _all_reduce_async
         else:  # backends without reduce-scatter (gloo, CPU tests): all-reduce, the owned rows are what is used
             self._bytes -= mine.numel() * g.element_size()
             self._all_reduce_async(g)
