@@ -102,7 +102,8 @@ def n_params(model_kw):
 
 def workload_config(cfg_name, precision, batch, world, sharded, global_batch=0, micro=1):
     cfg = CONFIGS[cfg_name]
-    arith = {"fp32": "fp32 (3xTF32 tensor-core forward / data gradient, fp32 FMA weight gradient and head)",
+    arith = {"fp32": "fp32 (split-precision tensor-core convolutions -- 3xTF32 forward / data gradient, three-way bf16 split weight "
+                     "gradient -- at fp32 accuracy; fp32 FMA head)",
              "bf16": "bf16 tensor-core convolutions and fc1 (fp32 accumulate, fp32 master weights)"}[precision]
     return {
         "workload": f"{cfg['label']}, {arith}",
@@ -293,8 +294,8 @@ HBM_BOUND = {"adam_step_f32", "head_fwd_f32", "head_bwd_f32", "sat_normalise", "
 def roofline_from_timer(timer, steps, ms_total, peaks, fma_peak):
     """Dominant kernel class of the timed region against the roofline that bounds it:
     HBM for the streaming kernels, the bf16 tensor peak for the bf16 convolutions, the FP32 FMA pipe for the fp32 direct
-    kernels, and for the 3xTF32 convolutions the TF32 tensor peak / 3 (= bf16 peak / 6: every fp32 product is three MMAs
-    at half the bf16 rate)."""
+    kernels, and for the split-precision tensor-core convolutions of the fp32 mode the bf16 peak / 6 (3xTF32: every fp32
+    product is three kind::tf32 MMAs at half the bf16 rate; bf16x3: six kind::f16 MMAs)."""
     summ = timer.summary()
     classes = {}
     for name, d in summ.items():
@@ -307,7 +308,7 @@ def roofline_from_timer(timer, steps, ms_total, peaks, fma_peak):
     def bound_of(cls):
         if cls in HBM_BOUND:
             return "hbm", peaks["hbm_gbs"]
-        if cls.endswith("_tf32x3"):
+        if cls.endswith("_tf32x3") or cls.endswith("_bf16x3"):
             return "tensor", tf32x3_peak
         if cls.endswith("_bf16"):
             return "tensor", peaks["bf16_tflops_sustained"]
@@ -333,8 +334,8 @@ def roofline_from_timer(timer, steps, ms_total, peaks, fma_peak):
                 "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)"}
     elif bound == "tensor":
         ach = dd["flops"] / (dd["ms"] * 1e-3) / 1e12
-        src = (" (MEASURED_PEAKS.json bf16_tflops_sustained / 6: kind::tf32 runs at half the bf16 rate and 3xTF32 spends three "
-               "MMAs per fp32 product)") if dname.endswith("_tf32x3") else \
+        src = (" (MEASURED_PEAKS.json bf16_tflops_sustained / 6: fp32-accurate products cost three kind::tf32 MMAs at half the "
+               "bf16 rate (3xTF32) or six kind::f16 MMAs (three-way bf16 split)") if dname.endswith("x3") else \
             " (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
         roof = {"kernel": dname, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": peaks["source"] + src}

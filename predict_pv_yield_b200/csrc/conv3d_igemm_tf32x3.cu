@@ -67,8 +67,10 @@ __device__ __forceinline__ float t3_trunc(float v) { return __uint_as_float(__fl
 
 // weights fp32 [Co][Ci][27] -> [half][term][(kh,kw)][ks][kg][kt*16 + c][4 ci]; term 0 = the value as stored (the tensor
 // core truncates it to TF32), term 1 = the exact residual w - trunc(w); flipped / transposed roles for the data gradient
+// pair = 1 (CTA-pair kernel, Cout = 32): "half" is the CTA rank and holds columns 48*rank .. 48*rank+47 of the N = 96 = (kt, co)
+// operand instead of all three time taps of 16 output channels
 __global__ void t3_weight_prep_kernel(const float* __restrict__ w, float* __restrict__ wq, int Ci_role, int Co_role, int KS,
-                                      int nhalf, long long s_co, long long s_ci, int flip) {
+                                      int nhalf, long long s_co, long long s_ci, int flip, int pair) {
   const int per_term = 9 * KS * 2 * kT3N * 4;
   const int total = nhalf * 2 * per_term;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -79,8 +81,13 @@ __global__ void t3_weight_prep_kernel(const float* __restrict__ w, float* __rest
     const int hw = (idx / (8 * kT3N * KS)) % 9;
     const int term = (idx / per_term) & 1;
     const int half = idx / (2 * per_term);
-    const int kt = n / kT3Half, c = n - kt * kT3Half;
-    const int co = half * kT3Half + c;
+    int kt = n / kT3Half, c = n - kt * kT3Half;
+    int co = half * kT3Half + c;
+    if (pair) {
+      const int col = half * kT3N + n;  // column of the 96-wide operand
+      kt = col >> 5;
+      co = col & 31;
+    }
     const int ci = (ks * 2 + kg) * 4 + e4;
     const int tap = kt * 9 + hw;
     float v = 0.f;
@@ -401,6 +408,317 @@ __global__ void __launch_bounds__(kT3Threads, 1) conv3d_igemm_tf32x3_kernel(cons
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
+// ---- CTA-pair version (cta_group::2), Cout = 32 ----------------------------------------------------------------------
+// Two CTAs of a cluster (two SMs of a TPC) run ONE tcgen05.mma over M = 256 positions: each CTA stages the input planes of
+// its own position tile and holds HALF of the N = 96 (kt, co) weight columns (the 110 KB that fit beside the plane ring);
+// the tensor cores of both SMs read both halves.  Per plane the pair issues the same 27 x KS x 3 MMAs as one CTA of the
+// single-CTA kernel, but for 256 positions x 32 output channels instead of 128 x 16: twice the work per issued MMA, and
+// the MMA issue rate (one per ~55 clk) is what bounds these kernels.  Only the leader CTA (rank 0) issues MMAs; barriers
+// the leader waits on (segment ready, accumulator block free) collect arrivals of both CTAs through shared::cluster
+// addresses, barriers both CTAs wait on (segment consumed, block complete) are signalled by multicast commits.
+constexpr int kT3PairBlocks = 5;   // accumulator blocks of 96 columns (480 of 512 TMEM columns)
+constexpr int kT3PairN = 96;
+
+struct T3PairRun {
+  int col, t0, n;
+};
+__device__ __forceinline__ T3PairRun t3_pair_run(long long g, long long g_end, int To) {
+  T3PairRun r;
+  const long long pc = g / To;
+  r.t0 = static_cast<int>(g - pc * To);
+  r.col = static_cast<int>(pc);
+  const long long left = g_end - g;
+  r.n = static_cast<int>(left < (To - r.t0) ? left : (To - r.t0));
+  return r;
+}
+
+template <int KS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3d_igemm_tf32x3_pair_kernel(const T3Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [12] segment landed (local TMA)
+  uint64_t* ready = full + kT3MaxSlots;                 // [12] LEADER's: x_lo written in both CTAs (8 arrivals)
+  uint64_t* empty = ready + kT3MaxSlots;                // [12] segment consumed (multicast commit)
+  uint64_t* wfull = empty + kT3MaxSlots;                // [1]  weights landed (local)
+  uint64_t* wready = wfull + 1;                         // [1]  LEADER's: weights landed in both CTAs (2 arrivals)
+  uint64_t* bfull = wready + 1;                         // [5]  accumulator block complete (multicast commit)
+  uint64_t* bempty = bfull + kT3PairBlocks;             // [5]  LEADER's: block read out in both CTAs (8 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bempty + kT3PairBlocks);
+  float* bias_s = reinterpret_cast<float*>(smem + 512);  // [32]
+  uint8_t* w_s = smem + 640;
+  constexpr uint32_t w_term_bytes = 9u * KS * 2u * kT3N * 16u;  // one of hi / lo, this CTA's 48 columns
+  constexpr uint32_t w_bytes = 2u * w_term_bytes;
+  const uint32_t slot_term = 2u * static_cast<uint32_t>(a.NP) * 16u;
+  const uint32_t slot_bytes = 2u * slot_term;
+  uint8_t* slot_s = w_s + ((w_bytes + 127u) & ~127u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const long long cta = blockIdx.x >> 1;
+  const long long ncta = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kT3MaxSlots; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(ready + i, 8); tc::mbar_init(empty + i, 1); }
+    tc::mbar_init(wfull, 1);
+    tc::mbar_init(wready, 2);
+    for (int i = 0; i < kT3PairBlocks; ++i) { tc::mbar_init(bfull + i, 1); tc::mbar_init(bempty + i, 8); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_pair(tmem_ptr, 512);
+  if (threadIdx.x >= 64 && threadIdx.x < 96) bias_s[lane] = (a.bias && lane < a.Co) ? __ldg(a.bias + lane) : 0.f;
+  tc::tc_fence_before();
+  tc::cluster_sync();  // barriers of both CTAs initialised before any remote arrival / multicast commit
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // pair tiles: g = pc * To + t over column PAIRS pc; the leader takes column 2 pc, the peer column 2 pc + 1
+  const int ncol = a.B * a.tiles_q;
+  const long long npc = (ncol + 1) / 2;
+  const long long tiles = npc * a.To;
+  const long long g_begin = tiles * cta / ncta;
+  const long long g_end = tiles * (cta + 1) / ncta;
+  const long long in_plane = static_cast<long long>(a.Hi) * a.Wi;
+  const uint32_t nslot = static_cast<uint32_t>(a.nslot);
+
+  if (warp == 0) {
+    // =============================== producer (each CTA its own planes) ===============================
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(wfull, w_bytes);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wq) + static_cast<size_t>(rank) * w_bytes;
+      for (uint32_t off = 0; off < w_bytes; off += 32768u) {
+        const uint32_t n = (w_bytes - off < 32768u) ? (w_bytes - off) : 32768u;
+        tc::bulk_g2s(w_s + off, wsrc + off, n, wfull);
+      }
+      uint32_t seq = 0;
+      bool told = false;
+      for (long long g = g_begin; g < g_end;) {
+        const T3PairRun r = t3_pair_run(g, g_end, a.To);
+        int col = 2 * r.col + static_cast<int>(rank);
+        if (col >= ncol) col = ncol - 1;  // odd column count: the peer repeats the last column (its stores are skipped)
+        const int b = col / a.tiles_q, qt = col - b * a.tiles_q;
+        const int q0 = qt * kT3TileM;
+        const long long avail = in_plane - q0;
+        const uint32_t npos = static_cast<uint32_t>(avail < a.NP ? avail : a.NP);
+        for (int i = 0; i < r.n + 2; ++i) {
+          const int pa = r.t0 + i + a.plane_off;
+          if (pa < a.zero_planes || pa >= a.Ti - a.zero_planes) continue;
+#pragma unroll 1
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t slot = seq % nslot;
+            tc::mbar_wait(empty + slot, ((seq / nslot) & 1u) ^ 1u);
+            ++seq;
+            tc::mbar_arrive_expect_tx(full + slot, npos * 32u);
+#pragma unroll
+            for (int kg = 0; kg < 2; ++kg) {
+              const uint4* src = a.x + ((static_cast<long long>(b) * a.G + (ks * 2 + kg)) * a.Ti + pa) * in_plane + q0;
+              tc::bulk_g2s(slot_s + slot * slot_bytes + static_cast<uint32_t>(kg) * a.NP * 16u, src, npos * 16u, full + slot);
+            }
+          }
+          if (!told) {  // the first planes are in flight: now tell the leader that this CTA's weights have landed
+            tc::mbar_wait(wfull, 0);
+            tc::mbar_arrive_cluster(tc::map_to_cta(wready, 0));
+            told = true;
+          }
+        }
+        g += r.n;
+      }
+      if (!told) {
+        tc::mbar_wait(wfull, 0);
+        tc::mbar_arrive_cluster(tc::map_to_cta(wready, 0));
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA only) ===============================
+    if (rank == 0) {
+      const bool leader = tc::elect_one();
+      const uint32_t a_lbo = static_cast<uint32_t>(a.NP) * 16u;
+      const uint32_t b_lbo = static_cast<uint32_t>(kT3N) * 16u;  // 48 rows of B per CTA
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lo_base = ((a_lbo >> 4) << 16);
+      const uint32_t b_lo_base = ((b_lbo >> 4) << 16) | ((tc::smem_u32(w_s) >> 4) & 0x3fffu);
+      const uint32_t slot_addr16 = tc::smem_u32(slot_s) >> 4;
+      const uint32_t slot_16 = slot_bytes >> 4, slot_term16 = slot_term >> 4;
+      constexpr uint32_t w_term16 = w_term_bytes >> 4;
+      constexpr uint32_t b_step16 = 2u * kT3N;
+      uint32_t tap16[9];
+#pragma unroll
+      for (int hw = 0; hw < 9; ++hw) tap16[hw] = static_cast<uint32_t>((hw / 3) * a.Wi + (hw % 3));
+      const uint32_t idesc = tc::umma_idesc(256, kT3PairN, /*TF32*/ 2, /*K-major*/ 0, 0);
+      tc::mbar_wait_cluster(wready, 0);
+      uint32_t seq = 0, blk_ph = 0, pc0 = 0;
+      for (long long g = g_begin; g < g_end;) {
+        const T3PairRun r = t3_pair_run(g, g_end, a.To);
+        for (int i = 0; i < r.n + 2; ++i) {
+          const int pa = r.t0 + i + a.plane_off;
+          if (pa < a.zero_planes || pa >= a.Ti - a.zero_planes) continue;
+          const uint32_t blk = (pc0 + static_cast<uint32_t>(i)) % kT3PairBlocks;
+          tc::mbar_wait_cluster(bempty + blk, ((blk_ph >> blk) & 1u) ^ 1u);
+          tc::tc_fence_after();
+          const uint32_t d = tmem_base + blk * kT3PairN;
+          uint32_t a_seg[KS];
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t s = seq + ks;
+            const uint32_t slot = s % nslot;
+            tc::mbar_wait_cluster(ready + slot, (s / nslot) & 1u);
+            tc::tc_fence_after();
+            a_seg[ks] = a_lo_base | ((slot_addr16 + slot * slot_16) & 0x3fffu);
+            if (leader) {
+#pragma unroll
+              for (int hw = 0; hw < 9; ++hw) {
+                const uint32_t b_t = b_lo_base + static_cast<uint32_t>(hw * KS + ks) * b_step16;
+                tc::umma_tf32_pair_lohi(d, a_seg[ks] + tap16[hw], desc_hi, b_t + w_term16, desc_hi, idesc, (ks | hw) ? 1u : 0u);
+                tc::umma_tf32_pair_lohi(d, a_seg[ks] + slot_term16 + tap16[hw], desc_hi, b_t, desc_hi, idesc, 1u);
+              }
+            }
+          }
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            if (leader) {
+#pragma unroll
+              for (int hw = 0; hw < 9; ++hw)
+                tc::umma_tf32_pair_lohi(d, a_seg[ks] + tap16[hw], desc_hi, b_lo_base + static_cast<uint32_t>(hw * KS + ks) * b_step16,
+                                        desc_hi, idesc, 1u);
+              tc::umma_commit_pair(empty + (seq + ks) % nslot, 3);  // the segment is consumed in both CTAs
+            }
+          }
+          if (leader) tc::umma_commit_pair(bfull + blk, 3);
+          blk_ph ^= 1u << blk;
+          seq += KS;
+          __syncwarp();
+        }
+        pc0 += static_cast<uint32_t>(r.n + 2);
+        g += r.n;
+      }
+    }
+  } else if (warp < 6) {
+    // =============================== split warps: x_lo = x - trunc(x) ===============================
+    const int tid = threadIdx.x - 64;
+    uint32_t seq = 0;
+    const uint32_t ready0 = tc::map_to_cta(ready, 0);  // the leader's barrier array
+    for (long long g = g_begin; g < g_end;) {
+      const T3PairRun r = t3_pair_run(g, g_end, a.To);
+      int col = 2 * r.col + static_cast<int>(rank);
+      if (col >= ncol) col = ncol - 1;
+      const int qt = col % a.tiles_q;
+      const long long avail = in_plane - qt * kT3TileM;
+      const int npos = static_cast<int>(avail < a.NP ? avail : a.NP);
+      for (int i = 0; i < r.n + 2; ++i) {
+        const int pa = r.t0 + i + a.plane_off;
+        if (pa < a.zero_planes || pa >= a.Ti - a.zero_planes) continue;
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t slot = seq % nslot;
+          tc::mbar_wait(full + slot, (seq / nslot) & 1u);
+          ++seq;
+          float4* hi = reinterpret_cast<float4*>(slot_s + slot * slot_bytes);
+          float4* lo = reinterpret_cast<float4*>(slot_s + slot * slot_bytes + slot_term);
+#pragma unroll
+          for (int kg = 0; kg < 2; ++kg)
+            for (int p = tid; p < npos; p += 128) {
+              const float4 v = hi[kg * a.NP + p];
+              lo[kg * a.NP + p] = make_float4(v.x - t3_trunc(v.x), v.y - t3_trunc(v.y), v.z - t3_trunc(v.z), v.w - t3_trunc(v.w));
+            }
+          tc::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive_cluster(ready0 + slot * 8u);
+        }
+      }
+      g += r.n;
+    }
+  } else {
+    // =============================== epilogue (warps 6..9), all 32 output channels of this CTA's positions ========
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const int GO = a.GO;
+    const int Top = a.To + 2 * a.out_pad, Hop = a.Ho + 2 * a.out_pad, Wop = a.Wo + 2 * a.out_pad;
+    const long long oplane = static_cast<long long>(Hop) * Wop;
+    const long long mplane = static_cast<long long>(a.Ho) * a.Wo;
+    const long long o_cg = static_cast<long long>(Top) * oplane, m_cg = static_cast<long long>(a.To) * mplane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+    const uint32_t bempty0 = tc::map_to_cta(bempty, 0);
+    uint32_t blk_ph = 0, pc0 = 0;
+    for (long long g = g_begin; g < g_end;) {
+      const T3PairRun r = t3_pair_run(g, g_end, a.To);
+      int col = 2 * r.col + static_cast<int>(rank);
+      const bool dup = col >= ncol;
+      if (dup) col = ncol - 1;
+      const int b = col / a.tiles_q, qt = col - b * a.tiles_q;
+      const int q = qt * kT3TileM + row;
+      const int ho = q / a.Wi, wo = q - ho * a.Wi;
+      const bool valid = (ho < a.Ho) && (wo < a.Wo) && !dup;
+      long long o_off = (static_cast<long long>(b) * GO * Top + (r.t0 + a.out_pad)) * oplane + static_cast<long long>(ho + a.out_pad) * Wop +
+                        (wo + a.out_pad);
+      long long m_off = (static_cast<long long>(b) * GO * a.To + r.t0) * mplane + static_cast<long long>(ho) * a.Wo + wo;
+      long long n_off = (static_cast<long long>(b) * a.Co * a.To + r.t0) * mplane + static_cast<long long>(ho) * a.Wo + wo;
+      for (int j = 0; j < r.n; ++j, o_off += oplane, m_off += mplane, n_off += mplane) {
+        float f[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) f[c] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          const int pa = r.t0 + j + kt + a.plane_off;
+          if (pa < a.zero_planes || pa >= a.Ti - a.zero_planes) continue;  // warp-uniform
+          const uint32_t blk = (pc0 + static_cast<uint32_t>(j + kt)) % kT3PairBlocks;
+          tc::mbar_wait(bfull + blk, (blk_ph >> blk) & 1u);
+          tc::tc_fence_after();
+          uint32_t v[32];
+          tc::tmem_ld_32x32(lane_addr + blk * kT3PairN + static_cast<uint32_t>(kt * 32), v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) f[c] += __uint_as_float(v[c]);
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        {
+          const int last = (j == r.n - 1) ? 2 : 0;
+          for (int d = 0; d <= last; ++d) {
+            const int pa = r.t0 + j + d + a.plane_off;
+            if (pa < a.zero_planes || pa >= a.Ti - a.zero_planes) continue;
+            const uint32_t blk = (pc0 + static_cast<uint32_t>(j + d)) % kT3PairBlocks;
+            if (lane == 0) tc::mbar_arrive_cluster(bempty0 + blk * 8u);
+            blk_ph ^= 1u << blk;
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float s = f[c] + bias_s[c];
+            if (a.relu) s = fmaxf(s, 0.f);
+            f[c] = s;
+          }
+          if (a.mask) {
+#pragma unroll
+            for (int gi = 0; gi < 8; ++gi) {
+              if (gi >= GO) continue;
+              const uint4 mk = __ldg(a.mask + m_off + gi * m_cg);
+              const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) f[gi * 4 + e] = (__uint_as_float(mw[e]) > 0.f) ? f[gi * 4 + e] : 0.f;
+            }
+          }
+          if (a.y_blk) {
+#pragma unroll
+            for (int gi = 0; gi < 8; ++gi)
+              if (gi < GO)
+                a.y_blk[o_off + gi * o_cg] = make_uint4(__float_as_uint(f[gi * 4]), __float_as_uint(f[gi * 4 + 1]),
+                                                        __float_as_uint(f[gi * 4 + 2]), __float_as_uint(f[gi * 4 + 3]));
+          }
+          if (a.y_nc) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c < a.Co) a.y_nc[n_off + c * m_cg] = f[c];
+          }
+        }
+      }
+      pc0 += static_cast<uint32_t>(r.n + 2);
+      g += r.n;
+    }
+  }
+  tc::tc_fence_before();
+  tc::cluster_sync();  // both CTAs are done with tensor memory and with each other's barriers
+  if (warp == 1) tc::tmem_dealloc_pair(tmem_base, 512);
+}
+
 // ---- layout kernels ------------------------------------------------------------------------------------------
 // [B][C][T][H][W] fp32 -> blocked fp32 [B][G][T+2p][H+2p][W+2p][4] interior (channels >= C are zero)
 __global__ void nc_to_blocked_f32_kernel(const float* __restrict__ x, float4* __restrict__ y, int C, int G, int T, int H, int W,
@@ -465,6 +783,8 @@ __global__ void sat_normalise_blocked_f32_kernel(const int16_t* __restrict__ x, 
   }
 }
 
+int g_t3_pair = 1;  // CTA-pair kernel for Cout > 16 (tools may switch it off through pvb200_debug_set_tf32x3_pair)
+
 static int t3_groups(int C) { return 2 * ceil_div(C, 8); }  // channel groups of 4, padded to an even count (UMMA K = 8)
 static int t3_halves(int Co) { return Co <= kT3Half ? 1 : 2; }
 
@@ -507,9 +827,11 @@ static int launch_t3(const void* xb, const float* w, long long s_co, long long s
               "conv3d_tf32x3: pointers must be 16-byte aligned");
   a.wq = static_cast<const uint4*>(ws);
   const int KS = a.G / 2;
+  const bool pair = g_t3_pair && a.nhalf == 2 && sms >= 2;
   {
     const int total = static_cast<int>(need / 4);
-    t3_weight_prep_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, static_cast<float*>(ws), Ci, Co, KS, a.nhalf, s_co, s_ci, flip);
+    t3_weight_prep_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, static_cast<float*>(ws), Ci, Co, KS, a.nhalf, s_co, s_ci, flip,
+                                                                    pair ? 1 : 0);
     PVB_LAUNCHED("t3_weight_prep");
   }
   const size_t w_bytes = static_cast<size_t>(2) * 9 * KS * 2 * kT3N * 16;
@@ -520,6 +842,25 @@ static int launch_t3(const void* xb, const float* w, long long s_co, long long s
   PVB_REQUIRE(nslot >= KS, "conv3d_tf32x3: Cin=%d Cout=%d width=%d does not fit in shared memory", Ci, Co, Wi);
   a.nslot = static_cast<int>(nslot);
   const size_t smem = fixed + nslot * slot_bytes;
+  if (pair) {
+    const long long pair_tiles = ((static_cast<long long>(B) * a.tiles_q + 1) / 2) * a.To;
+    long long npairs = sms / 2;
+    if (npairs > pair_tiles) npairs = pair_tiles;
+#define PVB_T3P_LAUNCH(KSV)                                                                                                      \
+  do {                                                                                                                          \
+    PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_tf32x3_pair_kernel<KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv3d_igemm_tf32x3_pair_kernel<KSV><<<static_cast<unsigned>(2 * npairs), kT3Threads, smem, stream>>>(a);                  \
+  } while (0)
+    switch (KS) {
+      case 1: PVB_T3P_LAUNCH(1); break;
+      case 2: PVB_T3P_LAUNCH(2); break;
+      case 3: PVB_T3P_LAUNCH(3); break;
+      default: PVB_T3P_LAUNCH(4); break;
+    }
+#undef PVB_T3P_LAUNCH
+    PVB_LAUNCHED("conv3d_igemm_tf32x3_pair");
+    return PVB200_OK;
+  }
   long long per_half = sms / a.nhalf;
   if (per_half > a.tiles) per_half = a.tiles;
   if (per_half < 1) per_half = 1;
@@ -543,6 +884,9 @@ static int launch_t3(const void* xb, const float* w, long long s_co, long long s
 }  // namespace pvb
 
 extern "C" {
+
+/* tools only (not declared in pvb200.h): 0 = single-CTA kernel for every layer, 1 = CTA-pair kernel where it applies */
+void pvb200_debug_set_tf32x3_pair(int on) { pvb::g_t3_pair = on; }
 
 int pvb200_blocked4_channel_groups(int C) { return pvb::t3_groups(C); }
 
