@@ -78,10 +78,13 @@ class ShardSpec:
 
 
 def wait_ready(p: torch.Tensor) -> None:
-    """Make the current stream wait for an in-flight all-gather of ``p``'s rows (``ShardSpec.all_gather_rows``)."""
+    """Make the current stream wait for an in-flight update of ``p`` on another stream: the all-gather of its rows
+    (``ShardSpec.all_gather_rows``) or its Adam step on the optimiser's side stream (``FusedAdam.overlap_large``)."""
     ev = getattr(p, "_pvb_ready", None)
     if ev is not None:
         torch.cuda.current_stream(p.device).wait_event(ev)
+        p._pvb_ready = None
+        p._pvb_hold = None  # (FusedAdam.overlap_large) the current stream is now ordered after the update: safe to recycle
 
 
 class GradientExchange:

@@ -58,6 +58,9 @@ class BaseModel(_Base):
     # default batch_size (base_model.py:30)
     batch_size = 32
 
+    # not in the reference: see configure_optimizers
+    overlap_optimizer = False
+
     # results file name
     results_file_name = "results_epoch"
 
@@ -195,4 +198,6 @@ class BaseModel(_Base):
 
     def configure_optimizers(self):
         # base_model.py:255-257: torch.optim.Adam(self.parameters(), lr=0.0005)
-        return FusedAdam(self.parameters(), lr=0.0005)
+        # overlap_optimizer (class attribute, default False): run the Adam step of fc1.weight on a side stream under the next
+        # step's convolution forward (optim.FusedAdam.overlap_large)
+        return FusedAdam(self.parameters(), lr=0.0005, overlap_large=bool(getattr(self, "overlap_optimizer", False)))

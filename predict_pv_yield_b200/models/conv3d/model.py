@@ -144,8 +144,18 @@ class Model(BaseModel):
         self._fc1_shadow = ops.Fc1Shadow()
         if precision == "bf16":
             self.fc1.weight._pvb_shadow = self._fc1_shadow
+        else:
+            # fp32 mode: every reader of fc1.weight inside this module goes through wait_ready (forward) -- FusedAdam may run
+            # its update on a side stream under the next step's convolutions; state_dict() waits through the hook below
+            self.fc1.weight._pvb_overlap_ok = True
+        self.register_state_dict_pre_hook(lambda *a, **k: self._wait_params())
         self.register_buffer("sat_mean", torch.from_numpy(mean.copy()), persistent=False)
         self.register_buffer("sat_std", torch.from_numpy(std.copy()), persistent=False)
+
+    def _wait_params(self):
+        from ...dp import wait_ready
+
+        wait_ready(self.fc1.weight)
 
     def _conv_params(self):
         wb = [self.sat_conv0.weight, self.sat_conv0.bias]
@@ -230,8 +240,9 @@ class Model(BaseModel):
             self.fc3.weight, self.fc3.bias, self.fc4.weight, self.fc4.bias,
         )
         if getattr(self.fc1.weight, "_pvb_ready", None) is not None:
-            # data parallel, fp32 mode: the rows of fc1.weight updated by the other ranks are still arriving on the
-            # communication stream (dp.ShardSpec.all_gather_rows); the head is their first reader
+            # fc1.weight is still being written on another stream -- its Adam step on the optimiser's side stream
+            # (FusedAdam.overlap_large) or, data parallel in fp32 mode, the all-gather of the rows other ranks updated
+            # (dp.ShardSpec.all_gather_rows): the head is the first reader
             from ...dp import wait_ready
 
             wait_ready(self.fc1.weight)

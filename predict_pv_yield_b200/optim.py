@@ -17,12 +17,23 @@ from . import ops
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, overlap_large: bool = False):
         if lr < 0.0 or eps < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
             raise ValueError("FusedAdam: invalid hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.grad_scale = 1.0
         self.pre_step_hook: Optional[Callable[[], None]] = None  # e.g. wait for the gradient all-reduce
+        # The update of a LARGE parameter (fc1.weight: 141 M elements, 4 GB of HBM traffic, ~0.75 ms) is HBM bound and its
+        # first reader in the next step is the head at the END of the forward pass, while the Conv3d forward in front of it
+        # is tensor-core bound and leaves the memory system idle: with overlap_large the kernel runs on a side stream,
+        # under the next step's normalise + convolutions.  Readers of the parameter call dp.wait_ready(p) (Model.forward
+        # does; state_dict() does through a hook); the gradient buffer is kept alive until then.  OPT-IN: code that reads
+        # the parameter tensor directly between optimizer.step() and the next forward (EMA averaging, ad-hoc checks) must
+        # call dp.wait_ready(p) first, which torch.optim.Adam users do not expect -- hence off by default
+        # (Model.overlap_optimizer = True before configure_optimizers() switches it on).
+        self.overlap_large = bool(overlap_large)
+        self.large_numel = 1 << 22
+        self._side: Optional[torch.cuda.Stream] = None
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -79,6 +90,9 @@ class FusedAdam(torch.optim.Optimizer):
                                         st["step"], self.grad_scale):
                         continue
                 p._pvb_gen = getattr(p, "_pvb_gen", 0) + 1  # updated behind torch's back: derived copies are stale
+                if self.overlap_large and p.is_cuda and p.numel() >= self.large_numel and getattr(p, "_pvb_overlap_ok", False):
+                    self._step_on_side_stream(p, grad, st, group)
+                    continue
                 if step is None:
                     step = st["step"]
                 elif step != st["step"]:
@@ -91,3 +105,23 @@ class FusedAdam(torch.optim.Optimizer):
                 b1, b2 = group["betas"]
                 ops.adam_step(ps, gs, ms, vs, group["lr"], b1, b2, group["eps"], step, self.grad_scale)
         return loss
+
+    def _step_on_side_stream(self, p, grad, st, group) -> None:
+        from .dp import wait_ready
+
+        wait_ready(p)  # a previous update still in flight (two optimizer steps without a forward in between)
+        dev = p.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(main)  # the gradient (and, under data parallelism, its reduction) is complete
+        self._side.wait_event(ev)
+        b1, b2 = group["betas"]
+        with torch.cuda.stream(self._side):
+            ops.adam_step([p.data], [grad], [st["exp_avg"]], [st["exp_avg_sq"]], group["lr"], b1, b2, group["eps"], st["step"],
+                          self.grad_scale)
+            ready = torch.cuda.Event()
+            ready.record(self._side)
+        p._pvb_ready = ready
+        p._pvb_hold = grad  # keeps the gradient's memory from being recycled before the side stream has read it

@@ -245,3 +245,34 @@ def test_device_prefetcher_preserves_batches(dev):
     with torch.no_grad():
         want = m(O.batch_to(host[3], dev)).cpu()
     assert torch.equal(got[3], want)
+
+
+def test_overlapped_adam_equals_serial_adam(dev):
+    """FusedAdam(overlap_large=True) runs the update of fc1.weight on a side stream under the next forward pass: after three
+    steps the weights, the moments and the losses equal the serial optimiser's bit for bit, and state_dict() waits for it."""
+    kw = dict(include_pv_yield=False, include_nwp=False, forecast_minutes=60, history_minutes=30, image_size_pixels=24)
+    batch = O.batch_to(O.make_synthetic_batch(4, image_size_pixels=24, seed=9), dev)
+    out = {}
+    for overlap in (False, True):
+        torch.manual_seed(3)
+        m = _model(kw, dev)
+        m.batch_size = 4
+        m.overlap_optimizer = overlap
+        opt = m.configure_optimizers()
+        assert opt.overlap_large is overlap
+        losses = []
+        for step in range(3):
+            opt.zero_grad()
+            loss = m.training_step(batch, step)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        if overlap:
+            assert m.fc1.weight.numel() >= opt.large_numel and getattr(m.fc1.weight, "_pvb_ready", None) is not None
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}  # the pre-hook waits for the side stream
+        assert getattr(m.fc1.weight, "_pvb_ready", None) is None
+        out[overlap] = (losses, sd, opt.state[m.fc1.weight]["exp_avg"].clone())
+    assert out[True][0] == out[False][0]
+    for k in out[True][1]:
+        assert torch.equal(out[True][1][k], out[False][1][k]), k
+    assert torch.equal(out[True][2], out[False][2])
