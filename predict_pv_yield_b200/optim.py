@@ -33,6 +33,7 @@ class FusedAdam(torch.optim.Optimizer):
         # (Model.overlap_optimizer = True before configure_optimizers() switches it on).
         self.overlap_large = bool(overlap_large)
         self.large_numel = 1 << 22
+        self.overlap_width_sms = 36  # the side-stream launch is sized as if the device had this many SMs (x 8 CTAs)
         self._side: Optional[torch.cuda.Stream] = None
 
     @torch.no_grad()
@@ -118,10 +119,21 @@ class FusedAdam(torch.optim.Optimizer):
         ev.record(main)  # the gradient (and, under data parallelism, its reduction) is complete
         self._side.wait_event(ev)
         b1, b2 = group["betas"]
-        with torch.cuda.stream(self._side):
-            ops.adam_step([p.data], [grad], [st["exp_avg"]], [st["exp_avg_sq"]], group["lr"], b1, b2, group["eps"], st["step"],
-                          self.grad_scale)
-            ready = torch.cuda.Event()
-            ready.record(self._side)
+        # narrow grid (~2 CTAs of 256 threads per SM): at full width (8 per SM) the update's CTAs fill the register files and
+        # the persistent convolution kernels of the next forward pass (one 320-thread, 124-register CTA per SM) cannot
+        # become resident until it has drained -- no overlap at all, and the normalise kernel launched right behind it
+        # crawled from 0.1 to 0.7 ms.  Narrow, it runs at ~half of HBM speed beside them and still ends before the head.
+        L = ops._lib.load()
+        old = int(L.pvb200_reserve_sms(0))
+        full = int(L.pvb200_sm_count())
+        L.pvb200_reserve_sms(max(full - self.overlap_width_sms, 0))
+        try:
+            with torch.cuda.stream(self._side):
+                ops.adam_step([p.data], [grad], [st["exp_avg"]], [st["exp_avg_sq"]], group["lr"], b1, b2, group["eps"], st["step"],
+                              self.grad_scale)
+                ready = torch.cuda.Event()
+                ready.record(self._side)
+        finally:
+            L.pvb200_reserve_sms(old)
         p._pvb_ready = ready
         p._pvb_hold = grad  # keeps the gradient's memory from being recycled before the side stream has read it
