@@ -83,3 +83,23 @@ def test_warp_specialised_wgrad_uses_mbarriers_and_register_reallocation(sass):
     assert _count(loop, "FFMA2") == 432 and _count(loop, "LDS") <= 30
     for k in _find(sass, "conv3d_wgrad_f32_ws_narrow_kernel") + _find(sass, "conv3d_wgrad_f32_ws_kernel"):
         assert _count(sass[k], "USETMAXREG") == 0
+
+
+def test_fp32_mode_tensor_core_kernels(sass):
+    """The fp32-mode convolutions of round 2: 3xTF32 implicit GEMM (single CTA and CTA pair) and the three-way bf16 split
+    weight gradient -- tcgen05 MMAs, TMA-engine operands (bulk copies; tensor-map loads in the weight gradient), tensor
+    memory loads in the epilogues, mbarriers; the pair kernel issues the 2-CTA form of the MMA and of the commit."""
+    single = _find(sass, "conv3d_igemm_tf32x3_kernel")
+    pair = _find(sass, "conv3d_igemm_tf32x3_pair_kernel")
+    (wgrad,) = _find(sass, "conv3d_wgrad_bf16x3_kernel")
+    for k in single + pair:
+        ops = sass[k]
+        ks = int(re.search(r"kernelILi(\d)E", k).group(1))
+        assert _count(ops, "UTCHMMA") == 27 * ks, f"{k}: {_count(ops, 'UTCHMMA')} MMAs per plane, expected 27 x {ks}"
+        assert _count(ops, "UBLKCP") > 0 and _count(ops, "LDTM") > 0 and _count(ops, "SYNCS") > 0, k
+        two_cta = sum(1 for o in ops if o.startswith("UTCHMMA") and "2CTA" in o)
+        assert two_cta == (27 * ks if k in pair else 0), f"{k}: {two_cta} 2-CTA MMAs"
+    ops = sass[wgrad]
+    assert _count(ops, "UTCHMMA") >= 24 and _count(ops, "UTMALDG") == 2 and _count(ops, "LDTM") >= 3, wgrad
+    assert sum(1 for o in ops if o.startswith("F2FP")) >= 24, "packed bf16 conversion of the split warps"
+    assert _count(ops, "F2F") == 0, "scalar F2F.BF16.F32 (quarter-rate pipe) in the split loop"

@@ -1,5 +1,5 @@
 """Launch each hot kernel ONCE at its full BASELINE shape (layer conv1, batch 32), after one warm-up launch each, for
-`ncu --set full` captures:  ncu --set full --clock-control none -k regex:... -o gpurun_out/prof python tools/prof_kernels.py [f32|bf16]"""
+`ncu --set full` captures:  ncu --set full --clock-control none -k regex:... -o gpurun_out/prof python tools/prof_kernels.py [f32|bf16|tc32]"""
 import ctypes as C
 import os
 import sys
@@ -20,7 +20,13 @@ b = torch.randn(Co, device=dev, generator=g)
 x = torch.relu(torch.randn(B, Ci, T, S, S, device=dev, generator=g))
 gz = torch.randn(B, Co, T - 2, S - 2, S - 2, device=dev, generator=g)
 for rep in range(2):  # the second pass is the one to capture (ncu -s <launches of pass 0>)
-    if which == "f32":
+    if which == "tc32":  # fp32 mode on the tensor cores: 3xTF32 forward / data gradient (CTA pair), bf16x3 weight gradient
+        xb4 = ops.to_blocked_f32(x)
+        gz4 = ops.to_blocked_f32(gz, pad=2)
+        ops.conv3d_fwd_tf32x3(xb4, w, b, want_blk=True, want_nc=False)
+        ops.conv3d_dgrad_tf32x3(gz4, w, xb4, out_pad=2, want_blk=True, want_nc=False)
+        ops.conv3d_wgrad_bf16x3(xb4, gz4, Ci, Co, gz_pad=2)
+    elif which == "f32":
         ops.conv3d_fwd(x, w, b)
         ops.conv3d_dgrad(gz, w, x, x.shape)
         ops.conv3d_wgrad(x, gz)
