@@ -142,9 +142,9 @@ __device__ __forceinline__ void w3_next(W3Step& r, const W3Args& a) {
 __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(const W3Args a, const __grid_constant__ CUtensorMap tm_x,
                                                                             const __grid_constant__ CUtensorMap tm_gz) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem);  // [1] raw rows landed
-  uint64_t* raw_empty = raw_full + 1;                       // [1] raw rows converted
-  uint64_t* ready = raw_empty + 1;                          // [2] pieces written
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem);  // [2] raw rows landed: [0] input rows, [1] gradient rows
+  uint64_t* raw_empty = raw_full + 2;                       // [2] raw rows converted (each half is refilled as soon as it is read)
+  uint64_t* ready = raw_empty + 2;                          // [2] pieces written
   uint64_t* empty = ready + kW3Stages;                      // [2] pieces consumed
   uint64_t* afull = empty + kW3Stages;                      // [3] accumulator kw complete (flush window closed)
   uint64_t* aempty = afull + 3;                             // [3] accumulator kw drained
@@ -175,8 +175,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     for (int i = threadIdx.x; i < 3 * Wi; i += kW3Threads) ones[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
   }
   if (threadIdx.x == 0) {
-    tc::mbar_init(raw_full, 1);
-    tc::mbar_init(raw_empty, kW3SplitWarps);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(raw_full + i, 1); tc::mbar_init(raw_empty + i, kW3SplitWarps); }
     for (int i = 0; i < kW3Stages; ++i) { tc::mbar_init(ready + i, kW3SplitWarps); tc::mbar_init(empty + i, 1); }
     for (int i = 0; i < 3; ++i) { tc::mbar_init(afull + i, 1); tc::mbar_init(aempty + i, 4); }
     tc::fence_barrier_init();
@@ -198,14 +197,22 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       // two tiled TMA loads per step (tensor maps, SASS UTMALDG) instead of 32 small bulk copies: the three input rows
       // of every channel group, and row h of the three gradient planes t = p - off - 2 .. p - off of every group (planes
       // outside the tensor arrive as zeros: out-of-bounds fill / the tensor's own zero padding)
+      // the two halves of the raw staging have their own barriers: the input rows of step s+1 are fetched while the split
+      // warps still convert the gradient rows of step s
       if (lane == 0) {
-        tc::mbar_wait(raw_empty, (seq & 1u) ^ 1u);
+        tc::mbar_wait(raw_empty + 0, (seq & 1u) ^ 1u);
         if (a.dbg_flags & 1) {
-          tc::mbar_arrive(raw_full);
+          tc::mbar_arrive(raw_full + 0);
         } else {
-          tc::mbar_arrive_expect_tx(raw_full, a_raw_bytes + b_raw_bytes);
-          w3_tma_5d(a_raw, &tm_x, 0, st.h, st.p, 0, st.b, raw_full);
-          w3_tma_5d(b_raw, &tm_gz, a.gz_pad * 4, st.h + a.gz_pad, st.p - a.plane_off - 2 + a.gz_pad, 0, st.b, raw_full);
+          tc::mbar_arrive_expect_tx(raw_full + 0, a_raw_bytes);
+          w3_tma_5d(a_raw, &tm_x, 0, st.h, st.p, 0, st.b, raw_full + 0);
+        }
+        tc::mbar_wait(raw_empty + 1, (seq & 1u) ^ 1u);
+        if (a.dbg_flags & 1) {
+          tc::mbar_arrive(raw_full + 1);
+        } else {
+          tc::mbar_arrive_expect_tx(raw_full + 1, b_raw_bytes);
+          w3_tma_5d(b_raw, &tm_gz, a.gz_pad * 4, st.h + a.gz_pad, st.p - a.plane_off - 2 + a.gz_pad, 0, st.b, raw_full + 1);
         }
       }
       __syncwarp();
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     for (long long s = s_begin; s < s_end; ++s, ++seq, w3_next(st, a)) {
       const uint32_t stage = seq % kW3Stages;
       tc::mbar_wait(empty + stage, ((seq / kW3Stages) & 1u) ^ 1u);  // the MMAs of the step that used these piece buffers are done
-      tc::mbar_wait(raw_full, seq & 1u);
+      tc::mbar_wait(raw_full + 0, seq & 1u);
       const float4* ar = reinterpret_cast<const float4*>(a_raw);
       uint4* ap0 = reinterpret_cast<uint4*>(a_s + (stage * 3u) * a_piece);
       uint4* ap1 = reinterpret_cast<uint4*>(a_s + (stage * 3u + 1u) * a_piece);
@@ -301,6 +308,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
           if (r >= row) { r -= row; ++g8; }
         }
       }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(raw_empty + 0);  // the input rows have been read: the next step's may land
+      tc::mbar_wait(raw_full + 1, seq & 1u);
       const int nb = st.kt_hi - st.kt_lo + 1;
       if (nb > 0 && !(a.dbg_flags & 2)) {
         const float4* br = reinterpret_cast<const float4*>(b_raw);
@@ -325,7 +335,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       __syncwarp();
       if (lane == 0) {
         tc::mbar_arrive(ready + stage);
-        tc::mbar_arrive(raw_empty);  // the raw rows have been read: the next step's copies may land
+        tc::mbar_arrive(raw_empty + 1);  // the gradient rows have been read
       }
     }
   } else {
