@@ -196,6 +196,16 @@ int pvb200_conv3d_wgrad_bf16x3(const float* xb, const float* gzb, int gz_pad, fl
                                size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
                                pvb200_stream_t stream);
 
+/* bf16 mode, round 2: weight / bias gradient in the row-step formulation (conv3d_wgrad_bf16_rows.cu): the blocked bf16
+ * tensors go from the TMA engine (tensor maps) straight into the operand layout; gz is the tensor the data gradient reads
+ * (zero-padded by gz_pad = 2) or a plain one (gz_pad = 0).  `supported`: Cin, Cout <= 32 and rows of at most 64 positions;
+ * otherwise use pvb200_conv3d_wgrad_bf16. */
+int pvb200_conv3d_wgrad_bf16_rows_supported(int Cin, int Cout, int Hi, int Wi);
+size_t pvb200_conv3d_wgrad_bf16_rows_workspace_bytes(void);
+int pvb200_conv3d_wgrad_bf16_rows(const uint16_t* xb, const uint16_t* gzb, int gz_pad, float* dw, float* db, void* workspace,
+                                  size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
+                                  pvb200_stream_t stream);
+
 /* ---- general padding (pad_t, pad_hw, pad_hw), each 0 or 1, and MaxPool3d: the Conv3dMaxPool front-end of the Perceiver
  * hybrid (nn.Conv3d(..., padding=(1, 1, 1)) + nn.MaxPool3d(3, stride=(1, 2, 2), padding=(1, 1, 1)),
  * predict_pv_yield/models/perceiver/perceiver_conv3d_nwp_sat.py:42-57).  Ti/Hi/Wi are the INPUT extents. */

@@ -103,6 +103,10 @@ SIGNATURES = {
     "pvb200_conv3d_wgrad_bf16x3_workspace_bytes": (c_size_t, []),
     "pvb200_conv3d_wgrad_bf16x3": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_wgrad_bf16_rows_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "pvb200_conv3d_wgrad_bf16_rows_workspace_bytes": (c_size_t, []),
+    "pvb200_conv3d_wgrad_bf16_rows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_fwd_f32_pad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_conv3d_dgrad_f32_pad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

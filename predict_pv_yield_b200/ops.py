@@ -494,6 +494,33 @@ def conv3d_wgrad_bf16x3(xb: torch.Tensor, gzb: torch.Tensor, Ci: int, Co: int, g
     return dw, db
 
 
+def wgrad_bf16_rows_supported(Ci: int, Co: int, Hi: int, Wi: int) -> bool:
+    return bool(_lib.load().pvb200_conv3d_wgrad_bf16_rows_supported(Ci, Co, Hi, Wi))
+
+
+def conv3d_wgrad_bf16_rows(xb: torch.Tensor, gzb: torch.Tensor, Ci: int, Co: int, gz_pad: int = 0,
+                           pad_t: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(dw [Co,Ci,3,3,3], db [Co]) fp32 from blocked bf16 x [B,Cg,Ti,Hi,Wi,8] and the pre-activation gradient blocked bf16
+    zero-padded by ``gz_pad`` on T, H, W (row-step kernel: TMA tensor maps straight into the operand layout)."""
+    L = _lib.load()
+    _need_cuda(xb, "xb", torch.bfloat16)
+    _need_cuda(gzb, "gzb", torch.bfloat16)
+    B, Cgx, Ti, Hi, Wi, e = xb.shape
+    To, Ho, Wo = Ti + 2 * pad_t - 2, Hi - 2, Wi - 2
+    want = (B, blocked_groups(Co), To + 2 * gz_pad, Ho + 2 * gz_pad, Wo + 2 * gz_pad, 8)
+    if e != 8 or Cgx != blocked_groups(Ci) or tuple(gzb.shape) != want:
+        raise RuntimeError(f"conv3d_wgrad_bf16_rows: shapes {tuple(xb.shape)} / {tuple(gzb.shape)} inconsistent (expected gz {want})")
+    dw = torch.empty((Co, Ci, 3, 3, 3), dtype=torch.float32, device=xb.device)
+    db = torch.empty((Co,), dtype=torch.float32, device=xb.device)
+    ws = _workspace("wgrad_bf16_rows", L.pvb200_conv3d_wgrad_bf16_rows_workspace_bytes(), xb.device)
+    npos = B * To * Ho * Wo
+    with _timed(f"conv3d_wgrad_bf16[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 2.0 * (xb.numel() + 8 * blocked_groups(Co) * npos)):
+        rc = L.pvb200_conv3d_wgrad_bf16_rows(_p(xb), _p(gzb), gz_pad, _p(dw), _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
+                                             _stream())
+    _lib.check(rc, "conv3d_wgrad_bf16_rows")
+    return dw, db
+
+
 def adam_step(params: List[torch.Tensor], grads: List[torch.Tensor], exp_avg: List[torch.Tensor],
               exp_avg_sq: List[torch.Tensor], lr: float, beta1: float, beta2: float, eps: float, step: int,
               grad_scale: float = 1.0) -> None:
@@ -681,15 +708,27 @@ class EncoderBf16Fn(torch.autograd.Function):
             gzw = to_gzw_bf16(g)
         grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
         pad_t = ctx.pad_t
+        # per layer: the row-step weight gradient (round 2: tensor maps straight into the operand layout, reads the same
+        # zero-padded gradient tensor as the data gradient) or, for planes wider than 64, the round-1 tile kernel with its
+        # own "gzw" operand layout
+        rows = [wgrad_bf16_rows_supported(ch[l], ch[l + 1], acts[l].shape[3], acts[l].shape[4]) for l in range(n)]
+        gz_blk, gz_blk_pad = gz_pad, 2
+        if gz_blk is None and rows[n - 1]:
+            gz_blk, gz_blk_pad = to_blocked_bf16(g, pad=0), 0
         for l in range(n - 1, -1, -1):
-            dw, db = conv3d_wgrad_bf16(acts[l], gzw, ch[l], ch[l + 1], pad_t=pad_t)
+            if rows[l]:
+                dw, db = conv3d_wgrad_bf16_rows(acts[l], gz_blk, ch[l], ch[l + 1], gz_pad=gz_blk_pad, pad_t=pad_t)
+            else:
+                dw, db = conv3d_wgrad_bf16(acts[l], gzw, ch[l], ch[l + 1], pad_t=pad_t)
             grads[2 * l], grads[2 * l + 1] = dw, db
             if l > 0:
-                if l > 1:
-                    gz_pad, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=2, also_gzw=True, persistent=True,
-                                                    pad_t=pad_t)
-                else:  # the gradient w.r.t. layer 0's output only feeds layer 0's weight gradient
-                    _, gzw = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=0, also_gzw=True, persistent=True, pad_t=pad_t)
+                need_gzw = not rows[l - 1]
+                # the gradient w.r.t. layer 0's output only feeds layer 0's weight gradient: no zero border needed
+                out_pad = 2 if l > 1 else 0
+                res = conv3d_dgrad_bf16(gz_pad, wb[2 * l], acts[l], out_pad=out_pad, also_gzw=need_gzw, persistent=True, pad_t=pad_t)
+                gx, gzw = res if need_gzw else (res, None)
+                gz_blk, gz_blk_pad = gx, out_pad
+                gz_pad = gx if l > 1 else None
         return (None, None, None, None, *grads)
 
 

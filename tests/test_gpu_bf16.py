@@ -130,6 +130,42 @@ def test_conv3d_wgrad_bf16(ops, dev, shape):
     assert torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
+@pytest.mark.parametrize("shape", SHAPES + [(1, 32, 3, 64, 64, 32), (2, 12, 4, 16, 16, 32), (3, 32, 21, 6, 6, 16), (37, 16, 3, 5, 5, 32)])
+@pytest.mark.parametrize("gz_pad", [0, 2])
+def test_conv3d_wgrad_bf16_rows(ops, dev, shape, gz_pad):
+    """Round-2 row-step weight gradient: TMA tensor maps straight into the operand layout (zero fill of the K padding and of
+    the planes outside the tensor by the TMA engine), all three time taps per MMA, bias gradient from a row of ones."""
+    B, Ci, T, H, W, Co = shape
+    if not ops.wgrad_bf16_rows_supported(Ci, Co, H, W):
+        pytest.skip("shape not taken by the row-step kernel")
+    g = torch.Generator().manual_seed(3)
+    x = r16(torch.randn((B, Ci, T, H, W), generator=g))
+    gz = r16(torch.randn((B, Co, T - 2, H - 2, W - 2), generator=g))
+    wd = torch.zeros((Co, Ci, 3, 3, 3), dtype=torch.float64, requires_grad=True)
+    bd = torch.zeros((Co,), dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.double(), wd, bd).backward(gz.double())
+    xb = ops.to_blocked_bf16(x.to(dev))
+    gzb = ops.to_blocked_bf16(gz.to(dev), pad=gz_pad)
+    dw, db = ops.conv3d_wgrad_bf16_rows(xb, gzb, Ci, Co, gz_pad=gz_pad)
+    e_w, e_b = O.normalised_max_err(dw, wd.grad), O.normalised_max_err(db, bd.grad)
+    print(f"bf16 rows wgrad {shape} pad {gz_pad}: dw {e_w:.2e} db {e_b:.2e}")
+    assert e_w <= 1e-4 and e_b <= 1e-4  # exact products of bf16 inputs, fp32 accumulation in TMEM (toward zero)
+    dw2, db2 = ops.conv3d_wgrad_bf16_rows(xb, gzb, Ci, Co, gz_pad=gz_pad)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+def test_conv3d_wgrad_bf16_rows_time_padded(ops, dev):
+    B, Ci, T, H, W, Co = 2, 32, 5, 10, 10, 32
+    g = torch.Generator().manual_seed(8)
+    x = r16(torch.randn((B, Ci, T, H, W), generator=g))
+    gz = r16(torch.randn((B, Co, T, H - 2, W - 2), generator=g))
+    wd = torch.zeros((Co, Ci, 3, 3, 3), dtype=torch.float64, requires_grad=True)
+    bd = torch.zeros((Co,), dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.double(), wd, bd, padding=(1, 0, 0)).backward(gz.double())
+    dw, db = ops.conv3d_wgrad_bf16_rows(ops.to_blocked_bf16(x.to(dev)), ops.to_blocked_bf16(gz.to(dev), pad=2), Ci, Co, gz_pad=2, pad_t=1)
+    assert O.normalised_max_err(dw, wd.grad) <= 1e-4 and O.normalised_max_err(db, bd.grad) <= 1e-4
+
+
 def test_normalise_blocked_bf16(ops, dev):
     g = torch.Generator().manual_seed(4)
     x = torch.randint(-1, 1024, (2, 12, 3, 9, 10), generator=g, dtype=torch.int32).to(torch.int16)
