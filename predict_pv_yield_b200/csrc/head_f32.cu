@@ -712,6 +712,14 @@ static int check_head(const pvb200_head_t* h) {
   return PVB200_OK;
 }
 
+// fc1 on the tensor cores (fc1_bf16x3.cu); the FMA-pipe kernels above serve the shapes it does not take
+bool fc1x3_ok(int B, int max_b, int F1, long long K1, const void* x, const void* w);
+int fc1x3_fwd_ctas(long long K1);
+int fc1x3_fwd(const float* x, const float* w, float* partial, int S, int B, int F1, long long K1, cudaStream_t st);
+int fc1x3_dgrad(const float* g, const float* w, const float* x, float* gx, int B, int F1, long long K1, cudaStream_t st);
+int fc1x3_wgrad(const float* g, const float* x, float* dw, int B, int F1, long long K1, cudaStream_t st);
+constexpr int kFc1x3FwdMaxB = 1 << 30, kFc1x3BwdMaxB = 48;  // the forward chunks its batch; shared-memory budget of the backward
+
 static bool vec4_ok(const void* p, long long ld) { return (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(p) % 16 == 0); }
 
 }  // namespace pvb
@@ -721,7 +729,8 @@ extern "C" {
 size_t pvb200_head_fwd_workspace_bytes(int B, int F1, long long K1) {
   if (B <= 0 || F1 <= 0 || K1 <= 0) return 0;
   const pvb::Fc1Plan p = pvb::fc1_plan(B, F1, K1);
-  return static_cast<size_t>(p.S) * B * F1 * sizeof(float);
+  const int s3 = pvb::fc1x3_fwd_ctas(K1);
+  return static_cast<size_t>(p.S > s3 ? p.S : s3) * B * F1 * sizeof(float);
 }
 
 /* tail only: h->workspace holds S split-K partials [S][B][F1] of fc1 (e.g. from pvb200_fc1_fwd_bf16); fills h1, cat, h3, out */
@@ -746,7 +755,12 @@ int pvb200_head_fwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
   if (rc) return rc;
   PVB_REQUIRE(h->x, "head_fwd: null features");
   PVB_REQUIRE(h->h1 && h->cat && h->h3 && h->out, "head_fwd: null output");
-  const Fc1Plan p = fc1_plan(h->B, h->F1, h->K1);
+  Fc1Plan p = fc1_plan(h->B, h->F1, h->K1);
+  const bool tc3 = fc1x3_ok(h->B, kFc1x3FwdMaxB, h->F1, h->K1, h->x, h->w1);
+  if (tc3) {
+    p.S = fc1x3_fwd_ctas(h->K1);
+    PVB_REQUIRE(p.S > 0, "head_fwd: no CUDA device");
+  }
   const size_t need = static_cast<size_t>(p.S) * h->B * h->F1 * sizeof(float);
   if (!h->workspace || h->workspace_bytes < need) {
     set_error("head_fwd: workspace too small (%zu < %zu bytes)", h->workspace_bytes, need);
@@ -754,6 +768,15 @@ int pvb200_head_fwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
   }
   cudaStream_t st = as_stream(stream);
   float* partial = static_cast<float*>(h->workspace);
+  const int NCAT = h->F2 + h->NPV + (h->NNWP > 0 ? h->FNWP : 0);
+  const size_t smem = static_cast<size_t>(h->F1 + NCAT + h->F3 + h->NNWP + 8 * h->F1) * sizeof(float);
+  PVB_REQUIRE(smem <= 48 * 1024, "head_fwd: feature sizes too large for the tail kernel (%zu B smem)", smem);
+  if (tc3) {
+    if ((rc = fc1x3_fwd(h->x, h->w1, partial, p.S, h->B, h->F1, h->K1, st))) return rc;
+    head_tail_fwd_kernel<<<h->B, kHeadThreads, smem, st>>>(*h, partial, p.S);
+    PVB_LAUNCHED("head_tail_fwd");
+    return PVB200_OK;
+  }
   const int vec = vec4_ok(h->x, h->K1) && vec4_ok(h->w1, h->K1);
   const long long ctas = static_cast<long long>(p.S) * p.nbt * p.njt;
   if (vec) {
@@ -766,9 +789,6 @@ int pvb200_head_fwd_f32(const pvb200_head_t* h, pvb200_stream_t stream) {
                                                                                  p.nbt, p.njt, p.k_per_split, vec);
   }
   PVB_LAUNCHED("fc1_fwd_splitk");
-  const int NCAT = h->F2 + h->NPV + (h->NNWP > 0 ? h->FNWP : 0);
-  const size_t smem = static_cast<size_t>(h->F1 + NCAT + h->F3 + h->NNWP + 8 * h->F1) * sizeof(float);
-  PVB_REQUIRE(smem <= 48 * 1024, "head_fwd: feature sizes too large for the tail kernel (%zu B smem)", smem);
   head_tail_fwd_kernel<<<h->B, kHeadThreads, smem, st>>>(*h, partial, p.S);
   PVB_LAUNCHED("head_tail_fwd");
   return PVB200_OK;
@@ -816,6 +836,11 @@ static int head_bwd_impl(const pvb200_head_t* h, bool with_fc1, pvb200_stream_t 
     PVB_LAUNCHED("fc1_bias_grad");
   }
   if (!with_fc1) return PVB200_OK;
+  if (fc1x3_ok(h->B, kFc1x3BwdMaxB, h->F1, h->K1, h->x, h->w1) && vec4_ok(h->dw1, h->K1) && (!h->g_x || vec4_ok(h->g_x, h->K1))) {
+    if ((rc = fc1x3_wgrad(h->g_h1, h->x, h->dw1, h->B, h->F1, h->K1, st))) return rc;
+    if (h->g_x && (rc = fc1x3_dgrad(h->g_h1, h->w1, h->x, h->g_x, h->B, h->F1, h->K1, st))) return rc;
+    return PVB200_OK;
+  }
   const int vec = vec4_ok(h->x, h->K1) && vec4_ok(h->w1, h->K1) && vec4_ok(h->dw1, h->K1) && (!h->g_x || vec4_ok(h->g_x, h->K1));
   const int njt = ceil_div(h->F1, kFc1JT);
   const long long kt = ceil_div(h->K1, 128LL);

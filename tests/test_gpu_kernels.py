@@ -177,6 +177,9 @@ HEAD_CASES = [
     (5, 1001, 24, 40, 8, 2, (1, 32), False),   # K1 not a multiple of 4: scalar path; odd sizes
     (37, 4096, 128, 128, 64, 12, None, True),  # more than one batch tile
     (2, 300, 130, 16, 16, 4, None, False),     # F1 > one feature tile
+    (48, 8200, 100, 64, 32, 12, None, False),  # tensor-core fc1: K1 not a multiple of the 64 / 128 tiles, F1 < 128
+    (64, 12548, 128, 128, 64, 12, (2, 128), False),  # forward in two batch chunks (B > 48), backward on the FMA kernels
+    (17, 64 * 1300, 128, 128, 64, 12, None, False),  # several k tiles per CTA (accumulator folds, both TMEM windows)
 ]
 
 
@@ -232,6 +235,39 @@ def test_head_fwd_bwd(ops, dev, case):
         if pg is None:
             continue
         assert nerr(pg.grad, pw.grad) <= GRAD_TOL, nm
+
+
+def test_head_fc1_tensor_core_equals_fma_full_size(ops, dev):
+    """fc1 of the BASELINE model (32 x 1 103 872 -> 128) on the tensor cores (three-way bf16 split, fc1_bf16x3.cu) against
+    the FMA-pipe kernels on the same inputs: forward, data gradient (ReLU mask fused) and weight gradient."""
+    import ctypes
+
+    from predict_pv_yield_b200 import lib
+    L = lib.load()
+    L.pvb200_debug_set_fc1x3.argtypes = [ctypes.c_int]
+    L.pvb200_debug_set_fc1x3.restype = None
+    B, K1, F1 = 32, 32 * 11 * 56 * 56, 128
+    g = torch.Generator(device=dev).manual_seed(3)
+    feats = F.relu(torch.randn((B, K1), device=dev, generator=g))
+    gc = torch.Generator().manual_seed(4)
+    small = [t.to(dev) for pair in (_linear(gc, 128, F1), _linear(gc, 64, 128), _linear(gc, 12, 64)) for t in pair]
+    w1 = torch.randn((F1, K1), device=dev, generator=g) / np.sqrt(K1)
+    b1 = torch.randn((F1,), device=dev, generator=g) * 0.1
+    gout = torch.randn((B, 12), device=dev, generator=g)
+    res = {}
+    try:
+        for mode in (0, 1):
+            L.pvb200_debug_set_fc1x3(mode)
+            params = [t.clone().requires_grad_(True) for t in (w1, b1, small[0], small[1])] + [None, None] + \
+                     [t.clone().requires_grad_(True) for t in small[2:]]
+            fdev = feats.clone().requires_grad_(True)
+            out = ops.HeadFn.apply(fdev, None, None, *params)
+            out.backward(gout)
+            res[mode] = (out.detach(), fdev.grad, params[0].grad, params[1].grad)
+    finally:
+        L.pvb200_debug_set_fc1x3(1)
+    for nm, a, b in zip(("out", "g_feats", "dw1", "db1"), res[1], res[0]):
+        assert nerr(a, b) <= 2e-6, nm
 
 
 # ---------------------------------------------------------------------------------------- loss / adam
