@@ -172,17 +172,21 @@ int pvb200_conv3d_dgrad_bf16_tpad(const uint16_t* gz_padded, const float* w, con
  * W; mask_blk = the blocked activation whose ReLU mask is fused (or null). */
 int pvb200_blocked4_channel_groups(int C);
 size_t pvb200_conv3d_tf32x3_workspace_bytes(int Cin, int Cout);
-int pvb200_nc_to_blocked_f32(const float* x, float* y, int B, int C, int T, int H, int W, int pad, pvb200_stream_t stream);
+/* amax_out (here and below; may be NULL): device scalar that receives max(*amax_out, largest magnitude written), by an
+ * atomic max on the bit pattern of the non-negative float -- zero it first.  It is what the two-way fp16 split kernels
+ * (pvb200_conv3d_wgrad_f16x2) scale their operands by: producing it in the kernel that writes the tensor saves a pass. */
+int pvb200_nc_to_blocked_f32(const float* x, float* y, int B, int C, int T, int H, int W, int pad, float* amax_out,
+                             pvb200_stream_t stream);
 int pvb200_blocked_f32_to_nc(const float* x, float* y, int B, int C, int T, int H, int W, pvb200_stream_t stream);
 /* a1 fused with the layout change: int16 [B][C][T][H][W] -> normalised blocked fp32 (bit-identical arithmetic) */
 int pvb200_sat_normalise_blocked_f32(const int16_t* x, float* y, const float* mean, const float* std, int B, int C, int T,
-                                     int H, int W, pvb200_stream_t stream);
+                                     int H, int W, float* amax_out, pvb200_stream_t stream);
 int pvb200_conv3d_fwd_tf32x3(const float* xb, const float* w, const float* bias, float* y_blk, float* y_nc, void* workspace,
                              size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int out_pad,
-                             int pad_t, pvb200_stream_t stream);
+                             int pad_t, float* amax_out, pvb200_stream_t stream);
 int pvb200_conv3d_dgrad_tf32x3(const float* gz_padded, const float* w, const float* mask_blk, float* gx_blk, float* gx_nc,
                                void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
-                               int out_pad, int pad_t, pvb200_stream_t stream);
+                               int out_pad, int pad_t, float* amax_out, pvb200_stream_t stream);
 
 /* weight / bias gradient of the same layers on the tensor cores (conv3d_wgrad_bf16x3.cu: kind::tf32 cannot read the
  * position-strided operands this reduction needs, so every fp32 value is split EXACTLY into three bf16 pieces and six of
@@ -195,6 +199,16 @@ size_t pvb200_conv3d_wgrad_bf16x3_workspace_bytes(void);
 int pvb200_conv3d_wgrad_bf16x3(const float* xb, const float* gzb, int gz_pad, float* dw, float* db, void* workspace,
                                size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
                                pvb200_stream_t stream);
+/* the same gradient through a TWO-WAY fp16 split (x s = h0 + h1, 11 + 11 significand bits, three piece products: the
+ * accuracy class of the 3xTF32 forward at half the tensor time of the three-way split).  fp16 has 5 exponent bits: the kernel
+ * scales each operand by the power of two that brings the tensor's largest magnitude to [2^14, 2^15) and scales the sums
+ * back; amax_x / amax_gz = device scalars max |x|, max |gz| (the amax_out of the kernels that wrote the tensors, or
+ * pvb200_absmax_f32).  Same shapes, workspace, limits. */
+int pvb200_conv3d_wgrad_f16x2(const float* xb, const float* gzb, int gz_pad, const float* amax_x, const float* amax_gz, float* dw, float* db,
+                              void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
+                              int pad_t, pvb200_stream_t stream);
+/* *out = max(*out, max_i |x[i]|): out is a device scalar the caller zeroes first */
+int pvb200_absmax_f32(const float* x, long long n, float* out, pvb200_stream_t stream);
 
 /* bf16 mode, round 2: weight / bias gradient in the row-step formulation (conv3d_wgrad_bf16_rows.cu): the blocked bf16
  * tensors go from the TMA engine (tensor maps) straight into the operand layout; gz is the tensor the data gradient reads

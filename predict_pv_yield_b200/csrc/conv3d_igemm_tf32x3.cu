@@ -51,6 +51,7 @@ struct T3Args {
   const uint4* mask;  // blocked [B][GO][To][Ho][Wo] or null (ReLU-mask source of the data gradient)
   uint4* y_blk;       // [B][GO][To+2p][Ho+2p][Wo+2p] or null
   float* y_nc;        // [B][Co][To][Ho][Wo] or null
+  unsigned* amax_out; // or null: atomicMax of the bit pattern of max |y| (a non-negative float) over everything written
   int B, G, Ti, Hi, Wi;
   int Co, GO, To, Ho, Wo;
   int nhalf;        // 1 (Co <= 16) or 2
@@ -64,6 +65,13 @@ struct T3Args {
 };
 
 __device__ __forceinline__ float t3_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// largest magnitude a warp has seen -> one atomicMax per warp on the unsigned view of a non-negative float
+__device__ __forceinline__ void t3_publish_amax(unsigned* out, float am) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+  if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(out, __float_as_uint(am));
+}
 
 // weights fp32 [Co][Ci][27] -> [half][term][(kh,kw)][ks][kg][kt*16 + c][4 ci]; term 0 = the value as stored (the tensor
 // core truncates it to TF32), term 1 = the exact residual w - trunc(w); flipped / transposed roles for the data gradient
@@ -312,6 +320,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) conv3d_igemm_tf32x3_kernel(cons
     const long long o_cg = static_cast<long long>(Top) * oplane, m_cg = static_cast<long long>(a.To) * mplane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
     uint32_t blk_ph = 0, pc0 = 0;
+    float am = 0.f;  // largest magnitude this thread has written
     for (long long g = g_begin; g < g_end;) {
       const T3Run r = t3_run(g, g_end, a.To, a.tiles_q);
       const int q = r.qt * kT3TileM + row;
@@ -385,6 +394,8 @@ __global__ void __launch_bounds__(kT3Threads, 1) conv3d_igemm_tf32x3_kernel(cons
               for (int e = 0; e < 4; ++e) f[gi * 4 + e] = (__uint_as_float(mw[e]) > 0.f) ? f[gi * 4 + e] : 0.f;
             }
           }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) am = fmaxf(am, fabsf(f[c]));
           if (a.y_blk) {
 #pragma unroll
             for (int gi = 0; gi < 4; ++gi)
@@ -402,6 +413,7 @@ __global__ void __launch_bounds__(kT3Threads, 1) conv3d_igemm_tf32x3_kernel(cons
       pc0 += static_cast<uint32_t>(r.n + 2);
       g += r.n;
     }
+    if (a.amax_out) t3_publish_amax(a.amax_out, am);
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -637,6 +649,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
     const uint32_t bempty0 = tc::map_to_cta(bempty, 0);
     uint32_t blk_ph = 0, pc0 = 0;
+    float am = 0.f;  // largest magnitude this thread has written
     for (long long g = g_begin; g < g_end;) {
       const T3PairRun r = t3_pair_run(g, g_end, a.To);
       int col = 2 * r.col + static_cast<int>(rank);
@@ -696,6 +709,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
               for (int e = 0; e < 4; ++e) f[gi * 4 + e] = (__uint_as_float(mw[e]) > 0.f) ? f[gi * 4 + e] : 0.f;
             }
           }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) am = fmaxf(am, fabsf(f[c]));
           if (a.y_blk) {
 #pragma unroll
             for (int gi = 0; gi < 8; ++gi)
@@ -713,6 +728,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
       pc0 += static_cast<uint32_t>(r.n + 2);
       g += r.n;
     }
+    if (a.amax_out) t3_publish_amax(a.amax_out, am);
   }
   tc::tc_fence_before();
   tc::cluster_sync();  // both CTAs are done with tensor memory and with each other's barriers
@@ -722,7 +738,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
 // ---- layout kernels ------------------------------------------------------------------------------------------
 // [B][C][T][H][W] fp32 -> blocked fp32 [B][G][T+2p][H+2p][W+2p][4] interior (channels >= C are zero)
 __global__ void nc_to_blocked_f32_kernel(const float* __restrict__ x, float4* __restrict__ y, int C, int G, int T, int H, int W,
-                                         int pad, long long total) {
+                                         int pad, long long total, unsigned* __restrict__ amax_out) {
+  float am = 0.f;
   const long long thw = static_cast<long long>(T) * H * W;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, Tp = T + 2 * pad;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -741,7 +758,9 @@ __global__ void nc_to_blocked_f32_kernel(const float* __restrict__ x, float4* __
     const int h = static_cast<int>((pos / W) % H);
     const int t = static_cast<int>(pos / (static_cast<long long>(W) * H));
     y[((b * G + g) * Tp + (t + pad)) * Hp * Wp + static_cast<long long>(h + pad) * Wp + (w + pad)] = make_float4(f[0], f[1], f[2], f[3]);
+    am = fmaxf(fmaxf(am, fmaxf(fabsf(f[0]), fabsf(f[1]))), fmaxf(fabsf(f[2]), fabsf(f[3])));
   }
+  if (amax_out) t3_publish_amax(amax_out, am);  // (every thread of the grid reaches this line)
 }
 
 // blocked fp32 [B][G][T][H][W][4] -> [B][C][T][H][W] fp32
@@ -765,22 +784,41 @@ __global__ void blocked_f32_to_nc_kernel(const float4* __restrict__ x, float* __
 
 // int16 [B][C][T][H][W] -> normalised blocked fp32 [B][G][T][H][W][4] (a1 fused with the layout change; the arithmetic
 // is sat_norm of common.cuh: bit-identical to the reference)
-__global__ void sat_normalise_blocked_f32_kernel(const int16_t* __restrict__ x, float4* __restrict__ y, const float* __restrict__ mean,
-                                                 const float* __restrict__ stdv, int C, int G, long long thw, long long total) {
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long pos = idx % thw;
-    const long long r = idx / thw;
-    const int g = static_cast<int>(r % G);
-    const long long b = r / G;
+// grid: x = chunks of 1024 positions, y = (sample, channel group): no 64-bit division per element (the first version spent
+// 0.38 ms on them for 180 MB of traffic)
+__global__ void __launch_bounds__(256) sat_normalise_blocked_f32_kernel(const int16_t* __restrict__ x, float4* __restrict__ y,
+                                                                        const float* __restrict__ mean, const float* __restrict__ stdv,
+                                                                        int C, int G, int thw, unsigned* __restrict__ amax_out) {
+  float am = 0.f;
+  const int g = blockIdx.y % G, b = blockIdx.y / G;
+  const int16_t* xs = x + (static_cast<long long>(b) * C + g * 4) * thw;
+  float4* ys = y + static_cast<long long>(blockIdx.y) * thw;
+  float mu[4], sd[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool ok = g * 4 + j < C;
+    mu[j] = ok ? __ldg(mean + g * 4 + j) : 0.f;
+    sd[j] = ok ? __ldg(stdv + g * 4 + j) : 1.f;
+  }
+  const int p0 = blockIdx.x * 1024 + threadIdx.x;
+  int16_t v[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pos = p0 + i * 256;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[i][j] = (pos < thw && g * 4 + j < C) ? xs[static_cast<long long>(j) * thw + pos] : int16_t(0);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pos = p0 + i * 256;
+    if (pos >= thw) break;
     float f[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = g * 4 + j;
-      f[j] = (c < C) ? sat_norm(x[(b * C + c) * thw + pos], __ldg(mean + c), __ldg(stdv + c)) : 0.f;
-    }
-    y[idx] = make_float4(f[0], f[1], f[2], f[3]);
+    for (int j = 0; j < 4; ++j) f[j] = (g * 4 + j < C) ? sat_norm(v[i][j], mu[j], sd[j]) : 0.f;
+    ys[pos] = make_float4(f[0], f[1], f[2], f[3]);
+    am = fmaxf(fmaxf(am, fmaxf(fabsf(f[0]), fabsf(f[1]))), fmaxf(fabsf(f[2]), fabsf(f[3])));
   }
+  if (amax_out) t3_publish_amax(amax_out, am);
 }
 
 int g_t3_pair = 1;  // CTA-pair kernel for Cout > 16 (tools may switch it off through pvb200_debug_set_tf32x3_pair)
@@ -794,13 +832,14 @@ static size_t t3_ws_bytes(int Ci_role, int Co_role) {
 
 static int launch_t3(const void* xb, const float* w, long long s_co, long long s_ci, int flip, const float* bias, const void* mask,
                      void* y_blk, float* y_nc, void* ws, size_t ws_bytes, int B, int Ci, int Ti, int Hi, int Wi, int Co, int out_pad,
-                     int relu, int zero_planes, int To, int plane_off, cudaStream_t stream) {
+                     int relu, int zero_planes, int To, int plane_off, float* amax_out, cudaStream_t stream) {
   T3Args a;
   a.x = static_cast<const uint4*>(xb);
   a.bias = bias;
   a.mask = static_cast<const uint4*>(mask);
   a.y_blk = static_cast<uint4*>(y_blk);
   a.y_nc = y_nc;
+  a.amax_out = reinterpret_cast<unsigned*>(amax_out);
   a.B = B; a.G = t3_groups(Ci); a.Ti = Ti; a.Hi = Hi; a.Wi = Wi;
   PVB_REQUIRE(Co <= 32, "conv3d_tf32x3: Cout=%d > 32 is not supported by the tensor-core path", Co);
   PVB_REQUIRE(Ci <= 32, "conv3d_tf32x3: Cin=%d > 32 is not supported by the tensor-core path", Ci);
@@ -895,7 +934,8 @@ size_t pvb200_conv3d_tf32x3_workspace_bytes(int Cin, int Cout) {
   return f > d ? f : d;
 }
 
-int pvb200_nc_to_blocked_f32(const float* x, float* y, int B, int C, int T, int H, int W, int pad, pvb200_stream_t stream) {
+int pvb200_nc_to_blocked_f32(const float* x, float* y, int B, int C, int T, int H, int W, int pad, float* amax_out,
+                             pvb200_stream_t stream) {
   using namespace pvb;
   PVB_REQUIRE(x && y && B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && pad >= 0, "nc_to_blocked_f32: bad argument");
   const int G = t3_groups(C);
@@ -903,7 +943,7 @@ int pvb200_nc_to_blocked_f32(const float* x, float* y, int B, int C, int T, int 
   long long grid = ceil_div(total, 256LL);
   if (grid > 148 * 32) grid = 148 * 32;
   nc_to_blocked_f32_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), C, G, T, H, W,
-                                                                                        pad, total);
+                                                                                        pad, total, reinterpret_cast<unsigned*>(amax_out));
   PVB_LAUNCHED("nc_to_blocked_f32");
   return PVB200_OK;
 }
@@ -923,33 +963,32 @@ int pvb200_blocked_f32_to_nc(const float* x, float* y, int B, int C, int T, int 
 }
 
 int pvb200_sat_normalise_blocked_f32(const int16_t* x, float* y, const float* mean, const float* stdv, int B, int C, int T, int H,
-                                     int W, pvb200_stream_t stream) {
+                                     int W, float* amax_out, pvb200_stream_t stream) {
   using namespace pvb;
   PVB_REQUIRE(x && y && mean && stdv && B > 0 && C > 0 && T > 0 && H > 0 && W > 0, "sat_normalise_blocked_f32: bad argument");
   const int G = t3_groups(C);
   const long long thw = static_cast<long long>(T) * H * W;
-  const long long total = static_cast<long long>(B) * G * thw;
-  long long grid = ceil_div(total, 256LL);
-  if (grid > 148 * 32) grid = 148 * 32;
-  sat_normalise_blocked_f32_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), mean,
-                                                                                                stdv, C, G, thw, total);
+  PVB_REQUIRE(thw < (1LL << 31) - 1024 && static_cast<long long>(B) * G <= 65535, "sat_normalise_blocked_f32: input too large");
+  const dim3 grid(static_cast<unsigned>(ceil_div(thw, 1024LL)), static_cast<unsigned>(B * G));
+  sat_normalise_blocked_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), mean, stdv, C, G,
+                                                                       static_cast<int>(thw), reinterpret_cast<unsigned*>(amax_out));
   PVB_LAUNCHED("sat_normalise_blocked_f32");
   return PVB200_OK;
 }
 
 int pvb200_conv3d_fwd_tf32x3(const float* xb, const float* w, const float* bias, float* y_blk, float* y_nc, void* workspace,
                              size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int out_pad,
-                             int pad_t, pvb200_stream_t stream) {
+                             int pad_t, float* amax_out, pvb200_stream_t stream) {
   using namespace pvb;
   PVB_REQUIRE(xb && w, "conv3d_fwd_tf32x3: null pointer");
   PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && out_pad >= 0 && (pad_t == 0 || pad_t == 1), "conv3d_fwd_tf32x3: bad shape");
   return launch_t3(xb, w, static_cast<long long>(Cin) * 27, 27, 0, bias, nullptr, y_blk, y_nc, workspace, workspace_bytes, B, Cin, Ti,
-                   Hi, Wi, Cout, out_pad, relu, /*zero_planes=*/0, /*To=*/Ti + 2 * pad_t - 2, /*plane_off=*/-pad_t, as_stream(stream));
+                   Hi, Wi, Cout, out_pad, relu, /*zero_planes=*/0, /*To=*/Ti + 2 * pad_t - 2, /*plane_off=*/-pad_t, amax_out, as_stream(stream));
 }
 
 int pvb200_conv3d_dgrad_tf32x3(const float* gz_padded, const float* w, const float* mask_blk, float* gx_blk, float* gx_nc,
                                void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int out_pad,
-                               int pad_t, pvb200_stream_t stream) {
+                               int pad_t, float* amax_out, pvb200_stream_t stream) {
   using namespace pvb;
   PVB_REQUIRE(gz_padded && w, "conv3d_dgrad_tf32x3: null pointer");
   PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti + 2 * pad_t > 2 && Hi > 2 && Wi > 2 && out_pad >= 0 && (pad_t == 0 || pad_t == 1),
@@ -958,7 +997,7 @@ int pvb200_conv3d_dgrad_tf32x3(const float* gz_padded, const float* w, const flo
   // kernel output = gx [B][G(Cin)][Ti][Hi][Wi]: gx[t] reads the padded planes t + pad_t + {0,1,2}
   return launch_t3(gz_padded, w, /*s_co (out role = ci)*/ 27, /*s_ci (in role = co)*/ static_cast<long long>(Cin) * 27, 1, nullptr,
                    mask_blk, gx_blk, gx_nc, workspace, workspace_bytes, B, /*Ci role*/ Cout, Ti + 2 * pad_t + 2, Hi + 2, Wi + 2,
-                   /*Co role*/ Cin, out_pad, 0, /*zero_planes=*/2, /*To=*/Ti, /*plane_off=*/pad_t, as_stream(stream));
+                   /*Co role*/ Cin, out_pad, 0, /*zero_planes=*/2, /*To=*/Ti, /*plane_off=*/pad_t, amax_out, as_stream(stream));
 }
 
 }  // extern "C"

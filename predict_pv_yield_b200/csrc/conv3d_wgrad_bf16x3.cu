@@ -32,6 +32,7 @@
 // Warp roles (704 threads): warp 0 producer (lane-parallel bulk copies), warp 1 MMA issuer + TMEM owner, warps 2-9
 // split, warps 10-21 accumulator drain (four warps per kw accumulator).  Pipeline: raw staging (one buffer) -> pieces (two buffers) -> MMA.
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -45,6 +46,7 @@ constexpr int kW3Stages = 2;    // piece buffers
 constexpr int kW3Flush = 16;    // steps between two drains of the accumulators
 constexpr int kW3AccCols = 96;  // TMEM columns per kw accumulator
 constexpr int kW3Pairs = 6;     // products of the three-way split that are kept
+constexpr int kW3RowBlock = 6;  // output rows per block of the step order (see w3_step)
 
 struct W3Args {
   int gz_pad;       // zero padding of the gradient tensor on T, H, W (coordinates of the gradient's tensor map are shifted by it)
@@ -56,6 +58,8 @@ struct W3Args {
   int plane_off;    // input plane of output t, tap kt: t + kt + plane_off
   long long steps;  // B * Ti * Ho
   int dbg_flags;    // tools only: 1 = no bulk copies, 2 = no split arithmetic, 4 = no MMAs, 8 = no drain traffic
+  const float* amax_x;  // two-way fp16 split only: max |x| and max |gz| of the two tensors (device scalars)
+  const float* amax_g;
 };
 
 __device__ __forceinline__ void w3_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
@@ -99,6 +103,28 @@ __device__ __forceinline__ void w3_split8(const float4 lo4, const float4 hi4, ui
   w3_split2(hi4.z, hi4.w, q0.w, q1.w, q2.w);
 }
 
+// ---- two-way fp16 split: s v = h0 + h1 + O(2^-22 |s v|), s a power of two that brings the tensor's largest magnitude to
+// [2^14, 2^15) (w3_scale_exp): 11 + 11 significand bits, three of the four piece products -- the accuracy class of the 3xTF32
+// forward at HALF the MMAs of the three-way bf16 split.  Values below 2^-18 of the tensor's maximum lose relative (not
+// absolute) precision: their second piece is an fp16 subnormal with an absolute step of 2^-39 of the maximum.
+__device__ __forceinline__ int w3_scale_exp(float amax) {
+  if (!(amax > 0.f) || !(amax <= 3.0e38f)) return 0;
+  const int e = 14 - (static_cast<int>((__float_as_uint(amax) >> 23) & 0xffu) - 127);
+  return e < -100 ? -100 : (e > 100 ? 100 : e);
+}
+__device__ __forceinline__ float w3_exp2i(int e) { return __uint_as_float(static_cast<uint32_t>(e + 127) << 23); }
+__device__ __forceinline__ void w3_split2h(float v0, float v1, uint32_t& p0, uint32_t& p1) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(v1), "f"(v0));  // high half <- first source
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&p0));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(v1 - f.y), "f"(v0 - f.x));
+}
+__device__ __forceinline__ void w3_split8h(const float4 lo4, const float4 hi4, float s, uint4& q0, uint4& q1) {
+  w3_split2h(lo4.x * s, lo4.y * s, q0.x, q1.x);
+  w3_split2h(lo4.z * s, lo4.w * s, q0.y, q1.y);
+  w3_split2h(hi4.x * s, hi4.y * s, q0.z, q1.z);
+  w3_split2h(hi4.z * s, hi4.w * s, q0.w, q1.w);
+}
+
 __device__ __forceinline__ float w3_ld_keep(const float* p, uint64_t policy) {
   float v;
   asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy) : "memory");
@@ -110,6 +136,7 @@ __device__ __forceinline__ void w3_st_keep(float* p, float v, uint64_t policy) {
 
 struct W3Step {
   int b, p, h, kt_lo, kt_hi;  // time taps kt_lo..kt_hi of plane p fall on existing outputs (kt_lo > kt_hi: none)
+  int h0, hb;                 // the row block [h0, h0 + hb) the step belongs to
 };
 __device__ __forceinline__ void w3_taps(W3Step& r, const W3Args& a) {
   // t = p - kt - plane_off in [0, To)
@@ -118,33 +145,52 @@ __device__ __forceinline__ void w3_taps(W3Step& r, const W3Args& a) {
   r.kt_lo = lo > 0 ? lo : 0;
   r.kt_hi = tmax < 2 ? tmax : 2;
 }
-// step s = (b * Ti + p) * Ho + h: decoded once per role (64-bit divisions), then advanced incrementally -- the per-step
-// divisions sat on the MMA warp's issue path and left the tensor pipe idle at every step boundary
+// Step order inside a sample: blocks of kW3RowBlock output rows, all input planes of a block, the rows of the block.  A
+// gradient plane is read by the steps of three consecutive input planes: with the rows of a whole plane in between (the
+// first order: 60 steps x 148 CTAs x 48 KB = 4x the L2) every one of those reads came from DRAM -- 1.25 GB per launch
+// against 0.59 GB of tensors; now they are 2 x kW3RowBlock steps apart and hit L2, at the price of re-reading the two halo
+// rows of x per block.  Decoded once per role (64-bit divisions), then advanced incrementally -- the per-step divisions sat
+// on the MMA warp's issue path and left the tensor pipe idle at every step boundary.
 __device__ __forceinline__ W3Step w3_step(long long s, const W3Args& a) {
   W3Step r;
-  r.h = static_cast<int>(s % a.Ho);
-  const long long bp = s / a.Ho;
-  r.p = static_cast<int>(bp % a.Ti);
-  r.b = static_cast<int>(bp / a.Ti);
+  const long long per_b = static_cast<long long>(a.Ti) * a.Ho;
+  r.b = static_cast<int>(s / per_b);
+  const int rs = static_cast<int>(s - r.b * per_b);
+  const int k = rs / (kW3RowBlock * a.Ti);  // every block before the last one is full
+  r.h0 = k * kW3RowBlock;
+  r.hb = a.Ho - r.h0 < kW3RowBlock ? a.Ho - r.h0 : kW3RowBlock;
+  const int q = rs - k * kW3RowBlock * a.Ti;
+  r.p = q / r.hb;
+  r.h = r.h0 + q % r.hb;
   w3_taps(r, a);
   return r;
 }
 __device__ __forceinline__ void w3_next(W3Step& r, const W3Args& a) {
-  if (++r.h == a.Ho) {
-    r.h = 0;
-    if (++r.p == a.Ti) { r.p = 0; ++r.b; }
+  if (++r.h == r.h0 + r.hb) {
+    r.h = r.h0;
+    if (++r.p == a.Ti) {
+      r.p = 0;
+      r.h0 += r.hb;
+      if (r.h0 >= a.Ho) { r.h0 = 0; ++r.b; }
+      r.hb = a.Ho - r.h0 < kW3RowBlock ? a.Ho - r.h0 : kW3RowBlock;
+      r.h = r.h0;
+    }
     w3_taps(r, a);
   }
 }
 
-// smem layout (bytes): [0,128) barriers | [128,256) a zero core matrix | piece buffers: stage s = A pieces 0..2 (a_piece
-// bytes each), for s = 0,1, then stage s = B pieces 0..2 (b_piece bytes each) | raw fp32 staging: A rows, B rows
+// smem layout (bytes): [0,256) barriers | [256,384) a zero core matrix | piece buffers: stage s = A pieces 0..NP-1 (a_piece
+// bytes each), for s = 0,1, then stage s = B pieces (b_piece bytes each) | raw fp32 staging: RB x A rows, RB x B rows (the
+// two-way split leaves room for a second raw buffer: the loads of step s+1 fly while step s is converted)
+// NP = 3: three-way bf16 split (six products); NP = 2: two-way fp16 split of the scaled operands (three products)
+template <int NP>
 __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(const W3Args a, const __grid_constant__ CUtensorMap tm_x,
                                                                             const __grid_constant__ CUtensorMap tm_gz) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem);  // [2] raw rows landed: [0] input rows, [1] gradient rows
-  uint64_t* raw_empty = raw_full + 2;                       // [2] raw rows converted (each half is refilled as soon as it is read)
-  uint64_t* ready = raw_empty + 2;                          // [2] pieces written
+  constexpr uint32_t RB = NP == 2 ? 2u : 1u;                // raw staging buffers
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem);  // [2][RB] raw rows landed: [0] input rows, [1] gradient rows
+  uint64_t* raw_empty = raw_full + 2 * RB;                  // [2][RB] raw rows converted (each half is refilled as soon as it is read)
+  uint64_t* ready = raw_empty + 2 * RB;                     // [2] pieces written
   uint64_t* empty = ready + kW3Stages;                      // [2] pieces consumed
   uint64_t* afull = empty + kW3Stages;                      // [3] accumulator kw complete (flush window closed)
   uint64_t* aempty = afull + 3;                             // [3] accumulator kw drained
@@ -156,26 +202,28 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
   const uint32_t a_raw_bytes = static_cast<uint32_t>(G * 3 * Wi) * 16u;        // box [G][3 rows][Wi] of x
   const uint32_t a_raw_span = (a_raw_bytes + 127u) & ~127u;
   const uint32_t b_raw_bytes = static_cast<uint32_t>(a.GOr * 3 * a.Wo) * 16u;  // box [GOr][3 planes][Wo] of gz
-  uint8_t* a_s = smem + 256;                          // [stage][piece]
-  uint8_t* b_s = a_s + kW3Stages * 3u * a_piece;      // [stage][piece]
-  uint8_t* a_raw = b_s + kW3Stages * 3u * b_piece;
-  uint8_t* b_raw = a_raw + a_raw_span;
+  const uint32_t b_raw_span = (b_raw_bytes + 127u) & ~127u;
+  uint8_t* a_s = smem + 384;                          // [stage][piece]
+  uint8_t* b_s = a_s + kW3Stages * NP * a_piece;      // [stage][piece]
+  uint8_t* a_raw = b_s + kW3Stages * NP * b_piece;
+  uint8_t* b_raw = a_raw + RB * a_raw_span;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // zero everything once: padding positions / groups, the slack rows and the zero core matrix stay zero for the whole kernel
   {
-    const uint32_t total16 = (128u + kW3Stages * 3u * (a_piece + b_piece) + a_raw_span + b_raw_bytes) >> 4;
-    uint4* z = reinterpret_cast<uint4*>(smem + 128);
+    const uint32_t total16 = (128u + kW3Stages * NP * (a_piece + b_piece) + RB * (a_raw_span + b_raw_span)) >> 4;
+    uint4* z = reinterpret_cast<uint4*>(smem + 256);
     for (uint32_t i = threadIdx.x; i < total16; i += kW3Threads) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   // the ones rows of piece 0 (M-group 3 G8 = "row" 3 G8 of the operand layout); pieces 1, 2 keep zeros there
   for (int s = 0; s < kW3Stages; ++s) {
-    uint4* ones = reinterpret_cast<uint4*>(a_s + (s * 3u) * a_piece) + static_cast<uint32_t>(3 * G8) * Wi;
-    for (int i = threadIdx.x; i < 3 * Wi; i += kW3Threads) ones[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    uint4* ones = reinterpret_cast<uint4*>(a_s + (s * NP) * a_piece) + static_cast<uint32_t>(3 * G8) * Wi;
+    const uint32_t one2 = NP == 3 ? 0x3f803f80u : 0x3c003c00u;  // 1.0 in bf16 / fp16, twice
+    for (int i = threadIdx.x; i < 3 * Wi; i += kW3Threads) ones[i] = make_uint4(one2, one2, one2, one2);
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(raw_full + i, 1); tc::mbar_init(raw_empty + i, kW3SplitWarps); }
+    for (int i = 0; i < 2 * static_cast<int>(RB); ++i) { tc::mbar_init(raw_full + i, 1); tc::mbar_init(raw_empty + i, kW3SplitWarps); }
     for (int i = 0; i < kW3Stages; ++i) { tc::mbar_init(ready + i, kW3SplitWarps); tc::mbar_init(empty + i, 1); }
     for (int i = 0; i < 3; ++i) { tc::mbar_init(afull + i, 1); tc::mbar_init(aempty + i, 4); }
     tc::fence_barrier_init();
@@ -200,19 +248,21 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       // the two halves of the raw staging have their own barriers: the input rows of step s+1 are fetched while the split
       // warps still convert the gradient rows of step s
       if (lane == 0) {
-        tc::mbar_wait(raw_empty + 0, (seq & 1u) ^ 1u);
+        const uint32_t rb = seq % RB, ph = ((seq / RB) & 1u) ^ 1u;
+        tc::mbar_wait(raw_empty + rb, ph);
         if (a.dbg_flags & 1) {
-          tc::mbar_arrive(raw_full + 0);
+          tc::mbar_arrive(raw_full + rb);
         } else {
-          tc::mbar_arrive_expect_tx(raw_full + 0, a_raw_bytes);
-          w3_tma_5d(a_raw, &tm_x, 0, st.h, st.p, 0, st.b, raw_full + 0);
+          tc::mbar_arrive_expect_tx(raw_full + rb, a_raw_bytes);
+          w3_tma_5d(a_raw + rb * a_raw_span, &tm_x, 0, st.h, st.p, 0, st.b, raw_full + rb);
         }
-        tc::mbar_wait(raw_empty + 1, (seq & 1u) ^ 1u);
+        tc::mbar_wait(raw_empty + RB + rb, ph);
         if (a.dbg_flags & 1) {
-          tc::mbar_arrive(raw_full + 1);
+          tc::mbar_arrive(raw_full + RB + rb);
         } else {
-          tc::mbar_arrive_expect_tx(raw_full + 1, b_raw_bytes);
-          w3_tma_5d(b_raw, &tm_gz, a.gz_pad * 4, st.h + a.gz_pad, st.p - a.plane_off - 2 + a.gz_pad, 0, st.b, raw_full + 1);
+          tc::mbar_arrive_expect_tx(raw_full + RB + rb, b_raw_bytes);
+          w3_tma_5d(b_raw + rb * b_raw_span, &tm_gz, a.gz_pad * 4, st.h + a.gz_pad, st.p - a.plane_off - 2 + a.gz_pad, 0, st.b,
+                    raw_full + RB + rb);
         }
       }
       __syncwarp();
@@ -227,10 +277,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     const uint32_t lbo_word = (128u >> 4) << 16;
     const uint32_t a_addr16 = tc::smem_u32(a_s) >> 4, b_addr16 = tc::smem_u32(b_s) >> 4;
     const uint32_t a_piece16 = a_piece >> 4, b_piece16 = b_piece >> 4;
-    const uint32_t idesc0 = tc::umma_idesc(128, 0, /*BF16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
+    const uint32_t idesc0 = tc::umma_idesc(128, 0, /*BF16 : F16*/ NP == 3 ? 1 : 0, /*A MN-major*/ 1, /*B MN-major*/ 1);
     const uint32_t idesc_blk = static_cast<uint32_t>(CoP >> 3) << 17;
     // B operand of the MMA that opens a flush window: every N group reads the same all-zero core matrices (SBO = 0)
-    const uint32_t zero_lo = ((tc::smem_u32(smem + 128) >> 4) & 0x3fffu);  // LBO = 0 as well: both K groups read it
+    const uint32_t zero_lo = ((tc::smem_u32(smem + 256) >> 4) & 0x3fffu);  // LBO = 0 as well: both K groups read it
     const uint32_t zero_hi = (1u << 14);
     const int k16n = WP >> 4;
     uint32_t seq = 0;
@@ -243,8 +293,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       tc::mbar_wait(ready + stage, (seq / kW3Stages) & 1u);
       tc::tc_fence_after();
       const int nb = st.kt_hi - st.kt_lo + 1;
-      const uint32_t a0 = lbo_word | ((a_addr16 + (stage * 3u) * a_piece16) & 0x3fffu);
-      const uint32_t b0 = lbo_word | ((b_addr16 + (stage * 3u) * b_piece16 + static_cast<uint32_t>(st.kt_lo * GP8 * WP)) & 0x3fffu);
+      const uint32_t a0 = lbo_word | ((a_addr16 + (stage * NP) * a_piece16) & 0x3fffu);
+      const uint32_t b0 = lbo_word | ((b_addr16 + (stage * NP) * b_piece16 + static_cast<uint32_t>(st.kt_lo * GP8 * WP)) & 0x3fffu);
       const uint32_t idesc = idesc0 + static_cast<uint32_t>(nb > 0 ? nb : 1) * idesc_blk;
 #pragma unroll 1
       for (int kw = 0; kw < 3; ++kw) {
@@ -263,10 +313,12 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
           for (int k16 = 0; k16 < 4; ++k16) {
             if (k16 >= k16n) break;
             const uint32_t ao = static_cast<uint32_t>(k16 * 16 + kw), bo = static_cast<uint32_t>(k16 * 16);
-            // smallest products first: x0 g2, x2 g0, x1 g1, x1 g0, x0 g1, x0 g0
-            w3_mma(d, a0 + ao, a_hi_word, b0 + 2u * b_piece16 + bo, b_hi_word, idesc, 1u);
-            w3_mma(d, a0 + 2u * a_piece16 + ao, a_hi_word, b0 + bo, b_hi_word, idesc, 1u);
-            w3_mma(d, a0 + a_piece16 + ao, a_hi_word, b0 + b_piece16 + bo, b_hi_word, idesc, 1u);
+            // smallest products first: x0 g2, x2 g0, x1 g1, x1 g0, x0 g1, x0 g0 (two-way split: x1 g0, x0 g1, x0 g0)
+            if (NP == 3) {
+              w3_mma(d, a0 + ao, a_hi_word, b0 + 2u * b_piece16 + bo, b_hi_word, idesc, 1u);
+              w3_mma(d, a0 + 2u * a_piece16 + ao, a_hi_word, b0 + bo, b_hi_word, idesc, 1u);
+              w3_mma(d, a0 + a_piece16 + ao, a_hi_word, b0 + b_piece16 + bo, b_hi_word, idesc, 1u);
+            }
             w3_mma(d, a0 + a_piece16 + ao, a_hi_word, b0 + bo, b_hi_word, idesc, 1u);
             w3_mma(d, a0 + ao, a_hi_word, b0 + b_piece16 + bo, b_hi_word, idesc, 1u);
             w3_mma(d, a0 + ao, a_hi_word, b0 + bo, b_hi_word, idesc, 1u);
@@ -286,47 +338,58 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     const int a_g0 = tid / (3 * Wi), a_r0 = tid % (3 * Wi), a_dg = NT / (3 * Wi), a_dr = NT % (3 * Wi);
     const int b_r0 = tid / WP, b_w0 = tid % WP, b_dr = NT / WP, b_dw = NT % WP;
     const int go8 = a.GOr / 2;
+    const float sx = NP == 2 ? w3_exp2i(w3_scale_exp(__ldg(a.amax_x))) : 1.f;
+    const float sg = NP == 2 ? w3_exp2i(w3_scale_exp(__ldg(a.amax_g))) : 1.f;
     uint32_t seq = 0;
     W3Step st = w3_step(s_begin, a);
     for (long long s = s_begin; s < s_end; ++s, ++seq, w3_next(st, a)) {
       const uint32_t stage = seq % kW3Stages;
       tc::mbar_wait(empty + stage, ((seq / kW3Stages) & 1u) ^ 1u);  // the MMAs of the step that used these piece buffers are done
-      tc::mbar_wait(raw_full + 0, seq & 1u);
-      const float4* ar = reinterpret_cast<const float4*>(a_raw);
-      uint4* ap0 = reinterpret_cast<uint4*>(a_s + (stage * 3u) * a_piece);
-      uint4* ap1 = reinterpret_cast<uint4*>(a_s + (stage * 3u + 1u) * a_piece);
-      uint4* ap2 = reinterpret_cast<uint4*>(a_s + (stage * 3u + 2u) * a_piece);
+      const uint32_t rb = seq % RB, rph = (seq / RB) & 1u;
+      tc::mbar_wait(raw_full + rb, rph);
+      const float4* ar = reinterpret_cast<const float4*>(a_raw + rb * a_raw_span);
+      uint4* ap0 = reinterpret_cast<uint4*>(a_s + (stage * NP) * a_piece);
+      uint4* ap1 = reinterpret_cast<uint4*>(a_s + (stage * NP + 1u) * a_piece);
+      uint4* ap2 = reinterpret_cast<uint4*>(a_s + (stage * NP + (NP - 1u)) * a_piece);
       const int row = 3 * Wi;  // elements of one fp32 channel group (three rows)
       // item i = (g8, r): no divisions in the loop -- (g8, r) advance incrementally from the thread's first item
       {
         int g8 = a_g0, r = a_r0;
         for (int i = tid; i < ((a.dbg_flags & 2) ? 0 : G8 * row); i += NT) {
           uint4 q0, q1, q2;
-          w3_split8(ar[(2 * g8) * row + r], ar[(2 * g8 + 1) * row + r], q0, q1, q2);
-          ap0[i] = q0; ap1[i] = q1; ap2[i] = q2;
+          if (NP == 3) {
+            w3_split8(ar[(2 * g8) * row + r], ar[(2 * g8 + 1) * row + r], q0, q1, q2);
+            ap0[i] = q0; ap1[i] = q1; ap2[i] = q2;
+          } else {
+            w3_split8h(ar[(2 * g8) * row + r], ar[(2 * g8 + 1) * row + r], sx, q0, q1);
+            ap0[i] = q0; ap1[i] = q1;
+          }
           r += a_dr; g8 += a_dg;
           if (r >= row) { r -= row; ++g8; }
         }
       }
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(raw_empty + 0);  // the input rows have been read: the next step's may land
-      tc::mbar_wait(raw_full + 1, seq & 1u);
+      if (lane == 0) tc::mbar_arrive(raw_empty + rb);  // the input rows have been read: the next step's may land
+      tc::mbar_wait(raw_full + RB + rb, rph);
       const int nb = st.kt_hi - st.kt_lo + 1;
       if (nb > 0 && !(a.dbg_flags & 2)) {
-        const float4* br = reinterpret_cast<const float4*>(b_raw);
-        uint4* bp0 = reinterpret_cast<uint4*>(b_s + (stage * 3u) * b_piece);
-        uint4* bp1 = reinterpret_cast<uint4*>(b_s + (stage * 3u + 1u) * b_piece);
-        uint4* bp2 = reinterpret_cast<uint4*>(b_s + (stage * 3u + 2u) * b_piece);
+        const float4* br = reinterpret_cast<const float4*>(b_raw + rb * b_raw_span);
+        uint4* bp0 = reinterpret_cast<uint4*>(b_s + (stage * NP) * b_piece);
+        uint4* bp1 = reinterpret_cast<uint4*>(b_s + (stage * NP + 1u) * b_piece);
+        uint4* bp2 = reinterpret_cast<uint4*>(b_s + (stage * NP + (NP - 1u)) * b_piece);
         const int nrow = nb * go8;  // (kt, g8) rows of WP positions
         int rw = b_r0, w = b_w0;
         for (; rw < nrow;) {
           const int ktl = rw / go8;  // go8 <= 4, nb <= 3: a handful of values, the compiler turns this into compares
           const int g8 = rw - ktl * go8, kt = st.kt_lo + ktl;
           uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;  // positions beyond the row: the K padding of the operand
-          if (w < a.Wo)
-            w3_split8(br[((2 * g8) * 3 + (2 - kt)) * a.Wo + w], br[((2 * g8 + 1) * 3 + (2 - kt)) * a.Wo + w], q0, q1, q2);
+          if (w < a.Wo) {
+            if (NP == 3) w3_split8(br[((2 * g8) * 3 + (2 - kt)) * a.Wo + w], br[((2 * g8 + 1) * 3 + (2 - kt)) * a.Wo + w], q0, q1, q2);
+            else w3_split8h(br[((2 * g8) * 3 + (2 - kt)) * a.Wo + w], br[((2 * g8 + 1) * 3 + (2 - kt)) * a.Wo + w], sg, q0, q1);
+          }
           const int o = (kt * GP8 + g8) * WP + w;
-          bp0[o] = q0; bp1[o] = q1; bp2[o] = q2;
+          bp0[o] = q0; bp1[o] = q1;
+          if (NP == 3) bp2[o] = q2;
           w += b_dw; rw += b_dr;
           if (w >= WP) { w -= WP; ++rw; }
         }
@@ -335,7 +398,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       __syncwarp();
       if (lane == 0) {
         tc::mbar_arrive(ready + stage);
-        tc::mbar_arrive(raw_empty + 1);  // the gradient rows have been read
+        tc::mbar_arrive(raw_empty + RB + rb);  // the gradient rows have been read
       }
     }
   } else {
@@ -397,8 +460,11 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
 // dW[co][ci][kt][kh][kw] = sum over CTAs of partial[cta][kw][kt*CoP + co][(3*(ci/8) + kh)*8 + ci%8];
 // db[co] = sum over CTAs of partial[cta][0][kt_bias*CoP + co][(3*G8)*8]  (the row of ones against the time tap kt_bias = pad_t,
 // the one tap for which every output plane t = p meets an existing input plane exactly once)
+// amax != null (two-way fp16 split): the sums are in the scaled domain, 2^ex x 2^eg times too large (db: 2^eg)
 __global__ void wgrad_bf16x3_reduce_kernel(const float* __restrict__ partial, int ncta, float* __restrict__ dw, float* __restrict__ db,
-                                           int Ci, int Co, int G8, int CoP, int kt_bias) {
+                                           int Ci, int Co, int G8, int CoP, int kt_bias, const float* __restrict__ amax_x,
+                                           const float* __restrict__ amax_g) {
+  const float ux = amax_x ? w3_exp2i(-w3_scale_exp(__ldg(amax_x))) : 1.f, ug = amax_g ? w3_exp2i(-w3_scale_exp(__ldg(amax_g))) : 1.f;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = Co * Ci * 27;
   const size_t per_cta = static_cast<size_t>(3) * 128 * kW3AccCols;
@@ -410,13 +476,13 @@ __global__ void wgrad_bf16x3_reduce_kernel(const float* __restrict__ partial, in
     const size_t off = (static_cast<size_t>(kw) * kW3AccCols + kt * CoP + co) * 128 + ((3 * (ci >> 3) + kh) * 8 + (ci & 7));
     float s = 0.f;
     for (int c = 0; c < ncta; ++c) s += partial[c * per_cta + off];
-    dw[idx] = s;
+    dw[idx] = (s * ux) * ug;
   } else if (idx < total + Co && db) {
     const int co = idx - total;
     const size_t off = static_cast<size_t>(kt_bias * CoP + co) * 128 + (3 * G8) * 8;
     float s = 0.f;
     for (int c = 0; c < ncta; ++c) s += partial[c * per_cta + off];
-    db[co] = s;
+    db[co] = s * ug;
   }
 }
 
@@ -453,11 +519,96 @@ static int w3_make_tensor_map(CUtensorMap* tm, const void* base, const unsigned 
 static int w3_groups(int C) { return 2 * ceil_div(C, 8); }
 static int w3_cop(int Co) { return Co <= 16 ? 16 : 32; }
 
-static size_t w3_smem_bytes(int G, int GOr, int Wi, int Wo, int CoP) {
+static size_t w3_smem_bytes(int G, int GOr, int Wi, int Wo, int CoP, int NP = 3) {
   const size_t WP = round_up(Wo, 16);
   const size_t a_piece = round_up(static_cast<size_t>(3 * (G / 2) + 4) * Wi * 16, static_cast<size_t>(128));
   const size_t b_piece = static_cast<size_t>(3) * (CoP / 8) * WP * 16;
-  return 256 + kW3Stages * 3 * (a_piece + b_piece) + round_up(static_cast<size_t>(G) * 3 * Wi * 16, static_cast<size_t>(128)) + static_cast<size_t>(3) * GOr * Wo * 16;
+  const size_t RB = NP == 2 ? 2 : 1;
+  return 384 + kW3Stages * NP * (a_piece + b_piece) +
+         RB * (round_up(static_cast<size_t>(G) * 3 * Wi * 16, static_cast<size_t>(128)) + round_up(static_cast<size_t>(3) * GOr * Wo * 16, static_cast<size_t>(128)));
+}
+
+static int w3_supported(int Cin, int Cout, int Hi, int Wi, int NP) {
+  if (Cin <= 0 || Cout <= 0 || Cin > 32 || Cout > 32 || Hi < 3 || Wi < 3) return 0;
+  const int G = w3_groups(Cin);
+  // the M = 128 instruction reads 16 row groups at stride Wi*16 from the start of an A piece: it must stay inside the allocation
+  const size_t smem = w3_smem_bytes(G, w3_groups(Cout), Wi, Wi - 2, w3_cop(Cout), NP);
+  const size_t a_piece = round_up(static_cast<size_t>(3 * (G / 2) + 4) * Wi * 16, static_cast<size_t>(128));
+  const size_t last_a = 384 + (NP * kW3Stages - 1) * a_piece;
+  const size_t reach = last_a + static_cast<size_t>(16) * Wi * 16 + static_cast<size_t>(round_up(Wi, 16) + 16) * 16;
+  return (smem <= 227 * 1024 && reach <= smem && Wi <= 64) ? 1 : 0;  // Wi * 4 floats = the 256-element limit of a TMA box dimension
+}
+
+static int w3_launch(const char* who, int NP, const float* amax_x, const float* amax_g, const float* xb, const float* gzb, int gz_pad, float* dw, float* db,
+                     void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
+                     cudaStream_t stream) {
+  PVB_REQUIRE(xb && gzb && dw, "%s: null pointer", who);
+  PVB_REQUIRE(B > 0 && gz_pad >= 0 && (pad_t == 0 || pad_t == 1), "%s: bad argument", who);
+  PVB_REQUIRE(w3_supported(Cin, Cout, Hi, Wi, NP), "%s: Cin=%d Cout=%d plane %dx%d is not supported by the tensor-core weight "
+              "gradient (use pvb200_conv3d_wgrad_f32)", who, Cin, Cout, Hi, Wi);
+  W3Args a;
+  a.B = B; a.G = w3_groups(Cin); a.Ti = Ti; a.Hi = Hi; a.Wi = Wi;
+  a.GOr = w3_groups(Cout); a.CoP = w3_cop(Cout);
+  a.To = Ti + 2 * pad_t - 2; a.Ho = Hi - 2; a.Wo = Wi - 2; a.WP = round_up(a.Wo, 16);
+  PVB_REQUIRE(a.To > 0, "%s: input too short", who);
+  a.plane_off = -pad_t;
+  a.gz_pad = gz_pad;
+  a.steps = static_cast<long long>(B) * Ti * a.Ho;
+  a.dbg_flags = g_w3_dbg_flags;
+  a.amax_x = amax_x; a.amax_g = amax_g;
+  const int sms = sm_count();
+  PVB_REQUIRE(sms > 0, "%s: no CUDA device", who);
+  long long grid = a.steps < sms ? a.steps : sms;
+  const size_t need = static_cast<size_t>(grid) * 3 * 128 * kW3AccCols * sizeof(float);
+  if (!workspace || workspace_bytes < need) {
+    set_error("%s: workspace too small (%zu < %zu bytes)", who, workspace_bytes, need);
+    return PVB200_ERR_WORKSPACE;
+  }
+  PVB_REQUIRE(reinterpret_cast<uintptr_t>(xb) % 16 == 0 && reinterpret_cast<uintptr_t>(gzb) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "%s: pointers must be 16-byte aligned", who);
+  a.partial = static_cast<float*>(workspace);
+  const size_t smem = w3_smem_bytes(a.G, a.GOr, Wi, a.Wo, a.CoP, NP);
+  // tensor maps (fp32 elements, innermost dimension = one row of 4-channel elements): x [B][G][Ti][Hi][Wi*4] with the box
+  // [1][G][1][3][Wi*4]; gz [B][GOr][Tz][Hz][Wz*4] with the box [1][GOr][3][1][Wo*4]
+  CUtensorMap tm_x, tm_gz;
+  {
+    const unsigned long long Tz = a.To + 2 * gz_pad, Hz = a.Ho + 2 * gz_pad, Wz = a.Wo + 2 * gz_pad;
+    const unsigned long long xd[5] = {static_cast<unsigned long long>(Wi) * 4, static_cast<unsigned long long>(Hi), static_cast<unsigned long long>(Ti),
+                                      static_cast<unsigned long long>(a.G), static_cast<unsigned long long>(B)};
+    const unsigned xb_[5] = {static_cast<unsigned>(Wi) * 4, 3, 1, static_cast<unsigned>(a.G), 1};
+    const unsigned long long gd[5] = {Wz * 4, Hz, Tz, static_cast<unsigned long long>(a.GOr), static_cast<unsigned long long>(B)};
+    const unsigned gb_[5] = {static_cast<unsigned>(a.Wo) * 4, 1, 3, static_cast<unsigned>(a.GOr), 1};
+    const int r1 = w3_make_tensor_map(&tm_x, xb, xd, xb_);
+    const int r2 = w3_make_tensor_map(&tm_gz, gzb, gd, gb_);
+    PVB_REQUIRE(r1 == 0 && r2 == 0, "%s: cuTensorMapEncodeTiled failed (%d, %d)", who, r1, r2);
+  }
+  if (NP == 3) {
+    PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_bf16x3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_wgrad_bf16x3_kernel<3><<<static_cast<unsigned>(grid), kW3Threads, smem, stream>>>(a, tm_x, tm_gz);
+  } else {
+    PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_bf16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_wgrad_bf16x3_kernel<2><<<static_cast<unsigned>(grid), kW3Threads, smem, stream>>>(a, tm_x, tm_gz);
+  }
+  PVB_LAUNCHED(who);
+  const int total = Cout * Cin * 27 + Cout;
+  wgrad_bf16x3_reduce_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(a.partial, static_cast<int>(grid), dw, db, Cin, Cout, a.G / 2,
+                                                                       a.CoP, pad_t, NP == 2 ? amax_x : nullptr, NP == 2 ? amax_g : nullptr);
+  PVB_LAUNCHED("wgrad_bf16x3_reduce");
+  return PVB200_OK;
+}
+
+// largest magnitude of a tensor, as the bit pattern of a non-negative float (atomicMax on the unsigned view)
+__global__ void __launch_bounds__(256) absmax_f32_kernel(const float4* __restrict__ x, long long n4, const float* __restrict__ tail,
+                                                         int ntail, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+    const float4 v = __ldg(x + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < ntail) m = fmaxf(m, fabsf(tail[threadIdx.x]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
 }  // namespace pvb
@@ -468,17 +619,7 @@ extern "C" {
 void pvb200_debug_set_wgrad_flags(int f) { pvb::g_w3_dbg_flags = f; }
 
 /* 1 when the tensor-core weight gradient takes this layer (channel counts <= 32, rows that fit shared memory) */
-int pvb200_conv3d_wgrad_bf16x3_supported(int Cin, int Cout, int Hi, int Wi) {
-  using namespace pvb;
-  if (Cin <= 0 || Cout <= 0 || Cin > 32 || Cout > 32 || Hi < 3 || Wi < 3) return 0;
-  const int G = w3_groups(Cin);
-  // the M = 128 instruction reads 16 row groups at stride Wi*16 from the start of an A piece: it must stay inside the allocation
-  const size_t smem = w3_smem_bytes(G, w3_groups(Cout), Wi, Wi - 2, w3_cop(Cout));
-  const size_t a_piece = round_up(static_cast<size_t>(3 * (G / 2) + 4) * Wi * 16, static_cast<size_t>(128));
-  const size_t last_a = 256 + (3 * kW3Stages - 1) * a_piece;
-  const size_t reach = last_a + static_cast<size_t>(16) * Wi * 16 + static_cast<size_t>(round_up(Wi, 16) + 16) * 16;
-  return (smem <= 227 * 1024 && reach <= smem && Wi <= 64) ? 1 : 0;  // Wi * 4 floats = the 256-element limit of a TMA box dimension
-}
+int pvb200_conv3d_wgrad_bf16x3_supported(int Cin, int Cout, int Hi, int Wi) { return pvb::w3_supported(Cin, Cout, Hi, Wi, 3); }
 
 size_t pvb200_conv3d_wgrad_bf16x3_workspace_bytes(void) {
   int sms = pvb::sm_count();
@@ -492,53 +633,36 @@ size_t pvb200_conv3d_wgrad_bf16x3_workspace_bytes(void) {
 int pvb200_conv3d_wgrad_bf16x3(const float* xb, const float* gzb, int gz_pad, float* dw, float* db, void* workspace,
                                size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
                                pvb200_stream_t stream) {
+  return pvb::w3_launch("conv3d_wgrad_bf16x3", 3, nullptr, nullptr, xb, gzb, gz_pad, dw, db, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout,
+                        pad_t, pvb::as_stream(stream));
+}
+
+/* the same through the two-way fp16 split (three products instead of six).  amax_x, amax_gz: device scalars max |x|, max |gz|
+ * of the two tensors (pvb200_absmax_f32 or the amax_out of the kernel that wrote them): the operands are scaled by powers of
+ * two into fp16's range inside the kernel and the result is scaled back; workspace and shape limits as the bf16x3 entry */
+int pvb200_conv3d_wgrad_f16x2(const float* xb, const float* gzb, int gz_pad, const float* amax_x, const float* amax_gz, float* dw,
+                              float* db, void* workspace,
+                              size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int pad_t,
+                              pvb200_stream_t stream) {
+  PVB_REQUIRE(amax_x && amax_gz, "conv3d_wgrad_f16x2: null amax");
+  return pvb::w3_launch("conv3d_wgrad_f16x2", 2, amax_x, amax_gz, xb, gzb, gz_pad, dw, db, workspace, workspace_bytes, B, Cin, Ti, Hi, Wi, Cout,
+                        pad_t, pvb::as_stream(stream));
+}
+
+/* *out = max(*out, max |x[i]|) for a device scalar the caller has zeroed (several tensors may share it) */
+int pvb200_absmax_f32(const float* x, long long n, float* out, pvb200_stream_t stream) {
   using namespace pvb;
-  PVB_REQUIRE(xb && gzb && dw, "conv3d_wgrad_bf16x3: null pointer");
-  PVB_REQUIRE(B > 0 && gz_pad >= 0 && (pad_t == 0 || pad_t == 1), "conv3d_wgrad_bf16x3: bad argument");
-  PVB_REQUIRE(pvb200_conv3d_wgrad_bf16x3_supported(Cin, Cout, Hi, Wi), "conv3d_wgrad_bf16x3: Cin=%d Cout=%d plane %dx%d is not "
-              "supported by the tensor-core weight gradient (use pvb200_conv3d_wgrad_f32)", Cin, Cout, Hi, Wi);
-  W3Args a;
-  a.B = B; a.G = w3_groups(Cin); a.Ti = Ti; a.Hi = Hi; a.Wi = Wi;
-  a.GOr = w3_groups(Cout); a.CoP = w3_cop(Cout);
-  a.To = Ti + 2 * pad_t - 2; a.Ho = Hi - 2; a.Wo = Wi - 2; a.WP = round_up(a.Wo, 16);
-  PVB_REQUIRE(a.To > 0, "conv3d_wgrad_bf16x3: input too short");
-  a.plane_off = -pad_t;
-  a.gz_pad = gz_pad;
-  a.steps = static_cast<long long>(B) * Ti * a.Ho;
-  a.dbg_flags = g_w3_dbg_flags;
+  PVB_REQUIRE(x && out && n > 0, "absmax_f32: bad argument");
+  PVB_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0, "absmax_f32: x must be 16-byte aligned");
   const int sms = sm_count();
-  PVB_REQUIRE(sms > 0, "conv3d_wgrad_bf16x3: no CUDA device");
-  long long grid = a.steps < sms ? a.steps : sms;
-  const size_t need = static_cast<size_t>(grid) * 3 * 128 * kW3AccCols * sizeof(float);
-  if (!workspace || workspace_bytes < need) {
-    set_error("conv3d_wgrad_bf16x3: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
-    return PVB200_ERR_WORKSPACE;
-  }
-  PVB_REQUIRE(reinterpret_cast<uintptr_t>(xb) % 16 == 0 && reinterpret_cast<uintptr_t>(gzb) % 16 == 0 &&
-                  reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "conv3d_wgrad_bf16x3: pointers must be 16-byte aligned");
-  a.partial = static_cast<float*>(workspace);
-  const size_t smem = w3_smem_bytes(a.G, a.GOr, Wi, a.Wo, a.CoP);
-  PVB_CUDA(cudaFuncSetAttribute(conv3d_wgrad_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // tensor maps (fp32 elements, innermost dimension = one row of 4-channel elements): x [B][G][Ti][Hi][Wi*4] with the box
-  // [1][G][1][3][Wi*4]; gz [B][GOr][Tz][Hz][Wz*4] with the box [1][GOr][3][1][Wo*4]
-  CUtensorMap tm_x, tm_gz;
-  {
-    const unsigned long long Tz = a.To + 2 * gz_pad, Hz = a.Ho + 2 * gz_pad, Wz = a.Wo + 2 * gz_pad;
-    const unsigned long long xd[5] = {static_cast<unsigned long long>(Wi) * 4, static_cast<unsigned long long>(Hi), static_cast<unsigned long long>(Ti),
-                                      static_cast<unsigned long long>(a.G), static_cast<unsigned long long>(B)};
-    const unsigned xb_[5] = {static_cast<unsigned>(Wi) * 4, 3, 1, static_cast<unsigned>(a.G), 1};
-    const unsigned long long gd[5] = {Wz * 4, Hz, Tz, static_cast<unsigned long long>(a.GOr), static_cast<unsigned long long>(B)};
-    const unsigned gb_[5] = {static_cast<unsigned>(a.Wo) * 4, 1, 3, static_cast<unsigned>(a.GOr), 1};
-    const int r1 = w3_make_tensor_map(&tm_x, xb, xd, xb_);
-    const int r2 = w3_make_tensor_map(&tm_gz, gzb, gd, gb_);
-    PVB_REQUIRE(r1 == 0 && r2 == 0, "conv3d_wgrad_bf16x3: cuTensorMapEncodeTiled failed (%d, %d)", r1, r2);
-  }
-  conv3d_wgrad_bf16x3_kernel<<<static_cast<unsigned>(grid), kW3Threads, smem, as_stream(stream)>>>(a, tm_x, tm_gz);
-  PVB_LAUNCHED("conv3d_wgrad_bf16x3");
-  const int total = Cout * Cin * 27 + Cout;
-  wgrad_bf16x3_reduce_kernel<<<ceil_div(total, 128), 128, 0, as_stream(stream)>>>(a.partial, static_cast<int>(grid), dw, db, Cin, Cout,
-                                                                                  a.G / 2, a.CoP, pad_t);
-  PVB_LAUNCHED("wgrad_bf16x3_reduce");
+  PVB_REQUIRE(sms > 0, "absmax_f32: no CUDA device");
+  const long long n4 = n / 4;
+  long long grid = ceil_div(n4 > 0 ? n4 : 1LL, 256LL * 8);
+  if (grid > 8LL * sms) grid = 8LL * sms;
+  absmax_f32_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), n4, x + n4 * 4,
+                                                                                 static_cast<int>(n - n4 * 4),
+                                                                                 reinterpret_cast<unsigned*>(out));
+  PVB_LAUNCHED("absmax_f32");
   return PVB200_OK;
 }
 

@@ -91,18 +91,21 @@ SIGNATURES = {
                                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_blocked4_channel_groups": (c_int, [c_int]),
     "pvb200_conv3d_tf32x3_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "pvb200_nc_to_blocked_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_nc_to_blocked_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pvb200_blocked_f32_to_nc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_sat_normalise_blocked_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                                 c_int, c_void_p]),
+                                                 c_int, c_void_p, c_void_p]),
     "pvb200_conv3d_fwd_tf32x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                                         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pvb200_conv3d_dgrad_tf32x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pvb200_conv3d_wgrad_bf16x3_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "pvb200_conv3d_wgrad_bf16x3_workspace_bytes": (c_size_t, []),
     "pvb200_conv3d_wgrad_bf16x3": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_conv3d_wgrad_f16x2": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pvb200_absmax_f32": (c_int, [c_void_p, c_ll, c_void_p, c_void_p]),
     "pvb200_conv3d_wgrad_bf16_rows_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "pvb200_conv3d_wgrad_bf16_rows_workspace_bytes": (c_size_t, []),
     "pvb200_conv3d_wgrad_bf16_rows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -355,8 +355,9 @@ def tf32x3_supported(Ci: int, Co: int) -> bool:
     return Ci <= 32 and Co <= 32
 
 
-def to_blocked_f32(x: torch.Tensor, pad: int = 0, persistent: bool = False) -> torch.Tensor:
-    """[B,C,T,H,W] fp32 -> blocked fp32 [B,G,T+2p,H+2p,W+2p,4] (zero border, zero pad channels)."""
+def to_blocked_f32(x: torch.Tensor, pad: int = 0, persistent: bool = False, amax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B,C,T,H,W] fp32 -> blocked fp32 [B,G,T+2p,H+2p,W+2p,4] (zero border, zero pad channels).  ``amax`` (here and in the
+    operators below): one zeroed fp32 device element that receives the largest magnitude written."""
     L = _lib.load()
     _need_cuda(x, "x", torch.float32)
     B, Cc, T, H, W = x.shape
@@ -367,7 +368,7 @@ def to_blocked_f32(x: torch.Tensor, pad: int = 0, persistent: bool = False) -> t
     else:
         y = (torch.zeros if pad > 0 else torch.empty)(shape, dtype=torch.float32, device=x.device)
     with _timed("nc_to_blocked_f32", 0.0, 4.0 * x.numel() + 16.0 * G * B * T * H * W):
-        rc = L.pvb200_nc_to_blocked_f32(_p(x), _p(y), B, Cc, T, H, W, pad, _stream())
+        rc = L.pvb200_nc_to_blocked_f32(_p(x), _p(y), B, Cc, T, H, W, pad, _p(amax), _stream())
     _lib.check(rc, "nc_to_blocked_f32")
     return y
 
@@ -386,7 +387,7 @@ def from_blocked_f32(xb: torch.Tensor, C: int) -> torch.Tensor:
     return y
 
 
-def sat_normalise_blocked_f32(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor) -> torch.Tensor:
+def sat_normalise_blocked_f32(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, amax: Optional[torch.Tensor] = None) -> torch.Tensor:
     """int16 [B,C,T,H,W] -> normalised blocked fp32 [B,G,T,H,W,4] (a1 fused with the layout change, bit-identical)."""
     L = _lib.load()
     _need_cuda(x, "satellite.data", torch.int16)
@@ -397,13 +398,13 @@ def sat_normalise_blocked_f32(x: torch.Tensor, mean: torch.Tensor, std: torch.Te
         raise RuntimeError(f"sat_normalise: {Cc} channels but {mean.numel()} means / {std.numel()} stds")
     y = torch.empty((B, blocked4_groups(Cc), T, H, W, 4), dtype=torch.float32, device=x.device)
     with _timed("sat_normalise_blocked_f32", 0.0, 2.0 * x.numel() + 4.0 * y.numel()):
-        rc = L.pvb200_sat_normalise_blocked_f32(_p(x), _p(y), _p(mean), _p(std), B, Cc, T, H, W, _stream())
+        rc = L.pvb200_sat_normalise_blocked_f32(_p(x), _p(y), _p(mean), _p(std), B, Cc, T, H, W, _p(amax), _stream())
     _lib.check(rc, "sat_normalise_blocked_f32")
     return y
 
 
 def conv3d_fwd_tf32x3(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = True, out_pad: int = 0,
-                      pad_t: int = 0, want_blk: bool = True, want_nc: bool = False):
+                      pad_t: int = 0, want_blk: bool = True, want_nc: bool = False, amax: Optional[torch.Tensor] = None):
     """relu(conv3d(x, w, b)) on the tensor cores at fp32 accuracy (3xTF32).  xb blocked fp32 [B,G,Ti,Hi,Wi,4]; returns
     (blocked copy | None, NCDHW copy | None)."""
     L = _lib.load()
@@ -426,13 +427,14 @@ def conv3d_fwd_tf32x3(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tenso
     with _timed(f"conv3d_fwd_tf32x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
                 4.0 * xb.numel() + 4.0 * npos * (4 * GO * int(want_blk) + Co * int(want_nc))):
         rc = L.pvb200_conv3d_fwd_tf32x3(_p(xb), _p(w), _p(b), _p(y_blk), _p(y_nc), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co,
-                                        int(relu), out_pad, pad_t, _stream())
+                                        int(relu), out_pad, pad_t, _p(amax), _stream())
     _lib.check(rc, "conv3d_fwd_tf32x3")
     return y_blk, y_nc
 
 
 def conv3d_dgrad_tf32x3(gz_padded: torch.Tensor, w: torch.Tensor, mask_blk: Optional[torch.Tensor], out_pad: int = 0,
-                        want_blk: bool = True, want_nc: bool = False, persistent: bool = False, pad_t: int = 0):
+                        want_blk: bool = True, want_nc: bool = False, persistent: bool = False, pad_t: int = 0,
+                        amax: Optional[torch.Tensor] = None):
     """gx = conv_transpose3d(gz, w) * (mask > 0) on the tensor cores (3xTF32) from gz blocked fp32 zero-padded by 2 on
     T, H, W.  Returns (blocked copy | None, NCDHW copy | None)."""
     L = _lib.load()
@@ -462,7 +464,7 @@ def conv3d_dgrad_tf32x3(gz_padded: torch.Tensor, w: torch.Tensor, mask_blk: Opti
     with _timed(f"conv3d_dgrad_tf32x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
                 4.0 * gz_padded.numel() + 4.0 * npos * (4 * GI * (int(want_blk) + int(mask_blk is not None)) + Ci * int(want_nc))):
         rc = L.pvb200_conv3d_dgrad_tf32x3(_p(gz_padded), _p(w), _p(mask_blk), _p(gx_blk), _p(gx_nc), _p(ws), ws.numel(), B, Ci, Ti,
-                                          Hi, Wi, Co, out_pad, pad_t, _stream())
+                                          Hi, Wi, Co, out_pad, pad_t, _p(amax), _stream())
     _lib.check(rc, "conv3d_dgrad_tf32x3")
     return gx_blk, gx_nc
 
@@ -471,10 +473,25 @@ def wgrad_bf16x3_supported(Ci: int, Co: int, Hi: int, Wi: int) -> bool:
     return bool(_lib.load().pvb200_conv3d_wgrad_bf16x3_supported(Ci, Co, Hi, Wi))
 
 
+def absmax_f32(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[0] = max(out[0], max |x|) on the device (``out``: one fp32 element the caller has zeroed)."""
+    L = _lib.load()
+    _need_cuda(x, "x", torch.float32)
+    _need_cuda(out, "out", torch.float32)
+    if not x.is_contiguous():
+        raise RuntimeError("absmax_f32: x must be contiguous")
+    with _timed("absmax_f32", 0.0, 4.0 * x.numel()):
+        rc = L.pvb200_absmax_f32(_p(x), x.numel(), _p(out), _stream())
+    _lib.check(rc, "absmax_f32")
+    return out
+
+
 def conv3d_wgrad_bf16x3(xb: torch.Tensor, gzb: torch.Tensor, Ci: int, Co: int, gz_pad: int = 0,
-                        pad_t: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(dw [Co,Ci,3,3,3], db [Co]) on the tensor cores (3xTF32) from x blocked fp32 [B,G,Ti,Hi,Wi,4] and the pre-activation
-    gradient blocked fp32, zero-padded by ``gz_pad`` on T, H, W (2 = the tensor the data gradient reads)."""
+                        pad_t: int = 0, amax: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(dw [Co,Ci,3,3,3], db [Co]) on the tensor cores from x blocked fp32 [B,G,Ti,Hi,Wi,4] and the pre-activation
+    gradient blocked fp32, zero-padded by ``gz_pad`` on T, H, W (2 = the tensor the data gradient reads).  Three-way bf16
+    split, or -- when ``amax`` = (max |x|, max |gz|), two one-element device tensors, is given -- the two-way fp16 split of
+    the scaled operands."""
     L = _lib.load()
     _need_cuda(xb, "xb", torch.float32)
     _need_cuda(gzb, "gzb", torch.float32)
@@ -488,8 +505,14 @@ def conv3d_wgrad_bf16x3(xb: torch.Tensor, gzb: torch.Tensor, Ci: int, Co: int, g
     ws = _workspace("wgrad_bf16x3", L.pvb200_conv3d_wgrad_bf16x3_workspace_bytes(), xb.device)
     npos = B * To * Ho * Wo
     with _timed(f"conv3d_wgrad_bf16x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 4.0 * xb.numel() + 16.0 * blocked4_groups(Co) * npos):
-        rc = L.pvb200_conv3d_wgrad_bf16x3(_p(xb), _p(gzb), gz_pad, _p(dw), _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
-                                          _stream())
+        if amax is None:
+            rc = L.pvb200_conv3d_wgrad_bf16x3(_p(xb), _p(gzb), gz_pad, _p(dw), _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
+                                              _stream())
+        else:
+            _need_cuda(amax[0], "amax_x", torch.float32)
+            _need_cuda(amax[1], "amax_gz", torch.float32)
+            rc = L.pvb200_conv3d_wgrad_f16x2(_p(xb), _p(gzb), gz_pad, _p(amax[0]), _p(amax[1]), _p(dw), _p(db), _p(ws), ws.numel(), B, Ci,
+                                             Ti, Hi, Wi, Co, pad_t, _stream())
     _lib.check(rc, "conv3d_wgrad_bf16x3")
     return dw, db
 
@@ -586,6 +609,11 @@ class EncoderFn(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+# fp32 mode, tensor-core weight gradient: two-way fp16 split of the scaled operands (three products) instead of the three-way
+# bf16 split (six); the largest magnitudes it scales by come out of the kernels that write the tensors
+FP32_WGRAD_F16X2 = True
+
+
 class EncoderTf32Fn(torch.autograd.Function):
     """Conv3d stack of the fp32 mode on the tensor cores (3xTF32: forward, data gradient AND weight gradient at fp32-class
     accuracy, csrc/conv3d_igemm_tf32x3.cu / conv3d_wgrad_bf16x3.cu).
@@ -603,24 +631,28 @@ class EncoderTf32Fn(torch.autograd.Function):
         B, _, T, H, W = sat.shape
         # per layer: does the tensor-core weight gradient take it?  (input plane of layer l: H - 2l)
         tc_w = [wgrad_bf16x3_supported(wb[2 * l].shape[1], wb[2 * l].shape[0], H - 2 * l, W - 2 * l) for l in range(n)]
+        # amax[l] = max |input of layer l|, amax[n + l] = max |gradient w.r.t. layer l's pre-activation| (filled in backward)
+        amax = torch.zeros((2 * n,), dtype=torch.float32, device=sat.device) if FP32_WGRAD_F16X2 else None
+        am = (lambda i: amax[i:i + 1]) if amax is not None else (lambda i: None)
         if sat.dtype == torch.int16:
-            x_blk = sat_normalise_blocked_f32(sat, mean, std)
+            x_blk = sat_normalise_blocked_f32(sat, mean, std, amax=am(0))
             x_nc = None if tc_w[0] else sat_normalise(sat, mean, std)
         else:
-            x_blk = to_blocked_f32(sat)
+            x_blk = to_blocked_f32(sat, amax=am(0))
             x_nc = None if tc_w[0] else sat
         ins_blk, ins_nc = [x_blk], [x_nc]  # input of layer l, blocked / NCDHW (None when not needed)
         y_nc = None
         for l in range(n):
             last = l == n - 1
             want_nc = last or not tc_w[l + 1]
-            y_blk, y_nc = conv3d_fwd_tf32x3(ins_blk[l], wb[2 * l], wb[2 * l + 1], relu=True, want_blk=not last, want_nc=want_nc)
+            y_blk, y_nc = conv3d_fwd_tf32x3(ins_blk[l], wb[2 * l], wb[2 * l + 1], relu=True, want_blk=not last, want_nc=want_nc,
+                                            amax=None if last else am(l + 1))
             if not last:
                 ins_blk.append(y_blk)
                 ins_nc.append(y_nc if not tc_w[l + 1] else None)
         keep = [t for t in ins_nc if t is not None]
         ctx.save_for_backward(*wb, *ins_blk, *keep)
-        ctx.n_layers, ctx.tc_w = n, tc_w
+        ctx.n_layers, ctx.tc_w, ctx.amax = n, tc_w, amax
         ctx.nc_index = [i for i, t in enumerate(ins_nc) if t is not None]
         ctx.out_shape = tuple(y_nc.shape)
         return y_nc.view(B, -1)
@@ -636,13 +668,16 @@ class EncoderTf32Fn(torch.autograd.Function):
             ins_nc[i] = t
         gz_nc = g.contiguous().view(ctx.out_shape)
         gz_blk, gz_pad = None, 0
+        amax = ctx.amax
+        am = (lambda i: amax[i:i + 1]) if amax is not None else (lambda i: None)
         if n > 1 or tc_w[n - 1]:
-            gz_blk, gz_pad = to_blocked_f32(gz_nc, pad=2, persistent=True), 2
+            gz_blk, gz_pad = to_blocked_f32(gz_nc, pad=2, persistent=True, amax=am(2 * n - 1)), 2
         grads: List[Optional[torch.Tensor]] = [None] * (2 * n)
         for l in range(n - 1, -1, -1):
             Co, Ci = wb[2 * l].shape[0], wb[2 * l].shape[1]
             if tc_w[l]:
-                dw, db = conv3d_wgrad_bf16x3(ins_blk[l], gz_blk, Ci, Co, gz_pad=gz_pad)
+                dw, db = conv3d_wgrad_bf16x3(ins_blk[l], gz_blk, Ci, Co, gz_pad=gz_pad,
+                                             amax=None if amax is None else (am(l), am(n + l)))
             else:
                 dw, db = conv3d_wgrad(ins_nc[l], gz_nc)
             grads[2 * l], grads[2 * l + 1] = dw, db
@@ -652,7 +687,7 @@ class EncoderTf32Fn(torch.autograd.Function):
                 nxt_pad = 2 if l - 1 >= 1 else 0
                 want_blk = (l - 1 >= 1) or tc_w[l - 1]
                 gz_blk, gz_nc = conv3d_dgrad_tf32x3(gz_blk, wb[2 * l], ins_blk[l], out_pad=nxt_pad if want_blk else 0,
-                                                    want_blk=want_blk, want_nc=not tc_w[l - 1], persistent=True)
+                                                    want_blk=want_blk, want_nc=not tc_w[l - 1], persistent=True, amax=am(n + l - 1))
                 gz_pad = nxt_pad
         return (None, None, None, *grads)
 

@@ -186,6 +186,75 @@ def test_conv3d_wgrad_bf16x3(ops, dev, shape, gz_pad):
     assert torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
+def _amax(ops, dev, *tensors):
+    out = torch.zeros((len(tensors),), device=dev)
+    for i, t in enumerate(tensors):
+        ops.absmax_f32(t, out[i:i + 1])
+    return tuple(out[i:i + 1] for i in range(len(tensors)))
+
+
+@pytest.mark.parametrize("shape", WGRAD_SHAPES)
+@pytest.mark.parametrize("scales", [(1.0, 1.0), (3.0e4, 2.0e-9), (1.0e-12, 7.0e6)])
+def test_conv3d_wgrad_f16x2(ops, dev, shape, scales):
+    """Two-way fp16 split of the scaled operands (three products): the fp32 parity bound whatever the magnitudes of the
+    activations and of the gradient (the kernel scales by the tensors' largest magnitudes into fp16's range)."""
+    B, Ci, T, H, W, Co = shape
+    x, w, b = _case(shape, seed=4)
+    g = torch.Generator().manual_seed(5)
+    gz = torch.randn((B, Co, T - 2, H - 2, W - 2), generator=g) * scales[1]
+    x = x * scales[0]
+    wd = w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    F.conv3d(x.double(), wd, bd).backward(gz.double())
+    xb = ops.to_blocked_f32(x.to(dev))
+    gzb = ops.to_blocked_f32(gz.to(dev), pad=2)
+    amax = _amax(ops, dev, xb, gzb)
+    assert float(amax[0]) == float(x.abs().max()) and float(amax[1]) == float(gz.abs().max())
+    dw, db = ops.conv3d_wgrad_bf16x3(xb, gzb, Ci, Co, gz_pad=2, amax=amax)
+    e_w, e_b = nerr(dw, wd.grad), nerr(db, bd.grad)
+    print(f"f16x2 wgrad {shape} scales {scales}: dw {e_w:.2e} db {e_b:.2e}")
+    assert e_w <= TOL and e_b <= TOL
+    dw2, db2 = ops.conv3d_wgrad_bf16x3(xb, gzb, Ci, Co, gz_pad=2, amax=amax)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+def test_conv3d_wgrad_f16x2_wide_dynamic_range(ops, dev):
+    """Operands whose magnitudes span 2^40 inside one tensor: the small values lose RELATIVE precision in the fp16 split,
+    the gradient (dominated by the large ones) stays within the fp32 bound; an all-zero gradient gives exact zeros."""
+    shape = (2, 32, 5, 12, 12, 32)
+    B, Ci, T, H, W, Co = shape
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((B, Ci, T, H, W), generator=g) * torch.exp2(torch.randint(-30, 10, (B, Ci, T, H, W), generator=g).float())
+    gz = torch.randn((B, Co, T - 2, H - 2, W - 2), generator=g) * torch.exp2(torch.randint(-40, 0, (B, Co, T - 2, H - 2, W - 2), generator=g).float())
+    wd = torch.zeros((Co, Ci, 3, 3, 3), dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.double(), wd).backward(gz.double())
+    xb, gzb = ops.to_blocked_f32(x.to(dev)), ops.to_blocked_f32(gz.to(dev), pad=2)
+    dw, db = ops.conv3d_wgrad_bf16x3(xb, gzb, Ci, Co, gz_pad=2, amax=_amax(ops, dev, xb, gzb))
+    assert nerr(dw, wd.grad) <= TOL and nerr(db, gz.double().sum((0, 2, 3, 4))) <= TOL
+    gzb.zero_()
+    dw, db = ops.conv3d_wgrad_bf16x3(xb, gzb, Ci, Co, gz_pad=2, amax=_amax(ops, dev, xb, gzb))
+    assert not bool(dw.any()) and not bool(db.any())
+
+
+def test_amax_out_of_the_producing_kernels(ops, dev):
+    """Every kernel that writes a blocked fp32 tensor of the encoder can report the largest magnitude it wrote (what the
+    two-way fp16 split scales by): normalise, layout change, convolution forward and data gradient."""
+    g = torch.Generator().manual_seed(12)
+    am = torch.zeros((4,), device=dev)
+    sat = torch.randint(0, 1024, (2, 12, 5, 10, 10), generator=g, dtype=torch.int32).to(torch.int16).to(dev)
+    mean, std = torch.rand(12, generator=g).to(dev) * 500, (torch.rand(12, generator=g) * 100 + 50).to(dev)
+    xb = ops.sat_normalise_blocked_f32(sat, mean, std, amax=am[0:1])
+    assert float(am[0]) == float(xb.abs().max())
+    x, w, b = _case((2, 12, 5, 10, 10, 32), seed=13)
+    xb = ops.to_blocked_f32(x.to(dev), amax=am[1:2])
+    assert float(am[1]) == float(x.abs().max())
+    y_blk, _ = ops.conv3d_fwd_tf32x3(xb, w.to(dev), b.to(dev), relu=True, want_blk=True, amax=am[2:3])
+    assert float(am[2]) == float(y_blk.abs().max()) > 0
+    gz = torch.randn((2, 32, 3, 8, 8), generator=g).to(dev)
+    gx_blk, _ = ops.conv3d_dgrad_tf32x3(ops.to_blocked_f32(gz, pad=2), w.to(dev), xb, out_pad=2, want_blk=True, amax=am[3:4])
+    assert float(am[3]) == float(gx_blk.abs().max()) > 0
+
+
 def test_conv3d_wgrad_bf16x3_time_padded(ops, dev):
     shape = (2, 32, 5, 10, 10, 32)
     B, Ci, T, H, W, Co = shape

@@ -91,7 +91,8 @@ def test_fp32_mode_tensor_core_kernels(sass):
     memory loads in the epilogues, mbarriers; the pair kernel issues the 2-CTA form of the MMA and of the commit."""
     single = _find(sass, "conv3d_igemm_tf32x3_kernel")
     pair = _find(sass, "conv3d_igemm_tf32x3_pair_kernel")
-    (wgrad,) = _find(sass, "conv3d_wgrad_bf16x3_kernel")
+    wgrads = _find(sass, "conv3d_wgrad_bf16x3_kernel")  # <3>: three-way bf16 split, <2>: two-way fp16 split
+    assert len(wgrads) == 2
     for k in single + pair:
         ops = sass[k]
         ks = int(re.search(r"kernelILi(\d)E", k).group(1))
@@ -99,7 +100,10 @@ def test_fp32_mode_tensor_core_kernels(sass):
         assert _count(ops, "UBLKCP") > 0 and _count(ops, "LDTM") > 0 and _count(ops, "SYNCS") > 0, k
         two_cta = sum(1 for o in ops if o.startswith("UTCHMMA") and "2CTA" in o)
         assert two_cta == (27 * ks if k in pair else 0), f"{k}: {two_cta} 2-CTA MMAs"
-    ops = sass[wgrad]
-    assert _count(ops, "UTCHMMA") >= 24 and _count(ops, "UTMALDG") == 2 and _count(ops, "LDTM") >= 3, wgrad
-    assert sum(1 for o in ops if o.startswith("F2FP")) >= 24, "packed bf16 conversion of the split warps"
-    assert _count(ops, "F2F") == 0, "scalar F2F.BF16.F32 (quarter-rate pipe) in the split loop"
+    for wgrad in wgrads:
+        ops = sass[wgrad]
+        pieces = int(re.search(r"kernelILi(\d)E", wgrad).group(1))
+        # per 16 positions and kw tap: six products of the three-way split, three of the two-way split (4 x 16 positions unrolled)
+        assert _count(ops, "UTCHMMA") >= 4 * (6 if pieces == 3 else 3) and _count(ops, "UTMALDG") == 2 and _count(ops, "LDTM") >= 3, wgrad
+        assert sum(1 for o in ops if o.startswith("F2FP")) >= 8 * pieces, "packed bf16 / fp16 conversion of the split warps"
+        assert _count(ops, "F2F") == 0, "scalar F2F (quarter-rate pipe) in the split loop"
