@@ -175,6 +175,11 @@ size_t pvb200_conv3d_tf32x3_workspace_bytes(int Cin, int Cout);
 /* amax_out (here and below; may be NULL): device scalar that receives max(*amax_out, largest magnitude written), by an
  * atomic max on the bit pattern of the non-negative float -- zero it first.  It is what the two-way fp16 split kernels
  * (pvb200_conv3d_wgrad_f16x2) scale their operands by: producing it in the kernel that writes the tensor saves a pass. */
+/* amax_in (convolutions; may be NULL): device scalar max |input tensor| (an amax_out of the kernel that wrote it).  When it
+ * is given, Cout > 16 and Cin is in 9..16 or 25..32, the convolution runs the TWO-WAY fp16 split instead of 3xTF32: the input
+ * and the weights are scaled by powers of two into fp16's range, every value is split into two fp16 pieces (11 + 11 bits),
+ * three of the four piece products run as kind::f16 MMAs over 16 channels at a time -- half the tensor time, the same
+ * accuracy class (<= 1e-5) -- and the epilogue scales the sums back. */
 int pvb200_nc_to_blocked_f32(const float* x, float* y, int B, int C, int T, int H, int W, int pad, float* amax_out,
                              pvb200_stream_t stream);
 int pvb200_blocked_f32_to_nc(const float* x, float* y, int B, int C, int T, int H, int W, pvb200_stream_t stream);
@@ -183,10 +188,10 @@ int pvb200_sat_normalise_blocked_f32(const int16_t* x, float* y, const float* me
                                      int H, int W, float* amax_out, pvb200_stream_t stream);
 int pvb200_conv3d_fwd_tf32x3(const float* xb, const float* w, const float* bias, float* y_blk, float* y_nc, void* workspace,
                              size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int out_pad,
-                             int pad_t, float* amax_out, pvb200_stream_t stream);
+                             int pad_t, const float* amax_in, float* amax_out, pvb200_stream_t stream);
 int pvb200_conv3d_dgrad_tf32x3(const float* gz_padded, const float* w, const float* mask_blk, float* gx_blk, float* gx_nc,
                                void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout,
-                               int out_pad, int pad_t, float* amax_out, pvb200_stream_t stream);
+                               int out_pad, int pad_t, const float* amax_in, float* amax_out, pvb200_stream_t stream);
 
 /* weight / bias gradient of the same layers on the tensor cores (conv3d_wgrad_bf16x3.cu: kind::tf32 cannot read the
  * position-strided operands this reduction needs, so every fp32 value is split EXACTLY into three bf16 pieces and six of

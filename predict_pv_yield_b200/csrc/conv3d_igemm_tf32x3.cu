@@ -30,6 +30,7 @@
 //     thread issues the 27 x KS x 3 MMAs of a plane; four epilogue warps add the three blocks of an output plane from
 //     TMEM (tcgen05.ld), bias / ReLU (or the ReLU mask of the data gradient) and store the blocked and / or NCDHW copy.
 // Warp roles (320 threads): warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-5 split, warps 6-9 epilogue.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -51,6 +52,8 @@ struct T3Args {
   const uint4* mask;  // blocked [B][GO][To][Ho][Wo] or null (ReLU-mask source of the data gradient)
   uint4* y_blk;       // [B][GO][To+2p][Ho+2p][Wo+2p] or null
   float* y_nc;        // [B][Co][To][Ho][Wo] or null
+  const float* amax_in;  // two-way fp16 split only: max |x| of the input tensor and max |w| (device scalars)
+  const float* amax_w;
   unsigned* amax_out; // or null: atomicMax of the bit pattern of max |y| (a non-negative float) over everything written
   int B, G, Ti, Hi, Wi;
   int Co, GO, To, Ho, Wo;
@@ -71,6 +74,73 @@ __device__ __forceinline__ void t3_publish_amax(unsigned* out, float am) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
   if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(out, __float_as_uint(am));
+}
+
+// ---- two-way fp16 split (CTA-pair kernel, F16 = true) -------------------------------------------------------------------
+// s v = h0 + h1 + O(2^-22 |s v|) with s the power of two that brings the tensor's largest magnitude to [2^14, 2^15): the
+// same 11 + 11 significand bits as the TF32 split, but both pieces are 16-bit operands of kind::f16 -- K = 16 channels per
+// MMA instead of 8, half the MMAs and half the operand bytes per plane.  fp16 has 5 exponent bits, hence the scaling; the
+// epilogue multiplies the sums by 2^-(ex + ew) (exact).  Values below 2^-18 of the tensor's maximum lose relative (not
+// absolute) precision: their second piece is an fp16 subnormal with an absolute step of 2^-39 of the maximum.
+__device__ __forceinline__ int t3_scale_exp(float amax) {
+  if (!(amax > 0.f) || !(amax <= 3.0e38f)) return 0;
+  const int e = 14 - (static_cast<int>((__float_as_uint(amax) >> 23) & 0xffu) - 127);
+  return e < -100 ? -100 : (e > 100 ? 100 : e);
+}
+__device__ __forceinline__ float t3_exp2i(int e) { return __uint_as_float(static_cast<uint32_t>(e + 127) << 23); }
+__device__ __forceinline__ void t3_split2h(float v0, float v1, uint32_t& p0, uint32_t& p1) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(v1), "f"(v0));  // high half <- first source
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&p0));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(v1 - f.y), "f"(v0 - f.x));
+}
+__device__ __forceinline__ void t3_split8h(const float4 lo4, const float4 hi4, float s, uint4& q0, uint4& q1) {
+  t3_split2h(lo4.x * s, lo4.y * s, q0.x, q1.x);
+  t3_split2h(lo4.z * s, lo4.w * s, q0.y, q1.y);
+  t3_split2h(hi4.x * s, hi4.y * s, q0.z, q1.z);
+  t3_split2h(hi4.z * s, hi4.w * s, q0.w, q1.w);
+}
+
+// weights fp32 [Co][Ci][27] -> fp16 pieces [rank][piece][(kh,kw)][ks16][kg][48 columns of the N = 96 = (kt, co) operand][8 ci],
+// scaled by the power of two of max |w| -- which every block computes for itself (27 K values) and block 0 leaves at
+// `amax_w` for the main kernel's epilogue
+__global__ void __launch_bounds__(256) t3_weight_prep_f16_kernel(const float* __restrict__ w, uint32_t* __restrict__ wq, int Ci_role,
+                                                                 int Co_role, int KS16, long long s_co, long long s_ci, int flip,
+                                                                 int nw, float* __restrict__ amax_w) {
+  __shared__ float red[8];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < nw; i += 256) m = fmaxf(m, fabsf(__ldg(w + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *amax_w = m;
+  const float sw = t3_exp2i(t3_scale_exp(m));
+  const int per_piece = 9 * KS16 * 2 * kT3N * 4;  // 32-bit words (two channels each) of one piece of one rank
+  const int total = 2 * 2 * per_piece;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int e2 = idx & 3;  // channel pair inside the 8-channel group
+    const int n = (idx >> 2) % kT3N;
+    const int kg = (idx / (4 * kT3N)) & 1;
+    const int ks = (idx / (8 * kT3N)) % KS16;
+    const int hw = (idx / (8 * kT3N * KS16)) % 9;
+    const int piece = (idx / per_piece) & 1;
+    const int rank = idx / (2 * per_piece);
+    const int col = rank * kT3N + n;  // column of the 96-wide operand
+    const int kt = col >> 5, co = col & 31;
+    const int tap = kt * 9 + hw;
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int ci = (ks * 2 + kg) * 8 + e2 * 2 + e;
+      v[e] = (co < Co_role && ci < Ci_role) ? w[co * s_co + ci * s_ci + (flip ? 26 - tap : tap)] * sw : 0.f;
+    }
+    uint32_t p0, p1;
+    t3_split2h(v[0], v[1], p0, p1);
+    wq[idx] = piece ? p1 : p0;
+  }
 }
 
 // weights fp32 [Co][Ci][27] -> [half][term][(kh,kw)][ks][kg][kt*16 + c][4 ci]; term 0 = the value as stored (the tensor
@@ -114,6 +184,21 @@ __device__ __forceinline__ void t3_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t 
       "mov.b64 da, {%1, %2};\n\t"
       "mov.b64 db, {%3, %4};\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
+}
+
+// the CTA-pair MMA of kind::f16 (see tc::umma_tf32_pair_lohi)
+__device__ __forceinline__ void t3_mma_f16_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
       "}" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate));
 }
@@ -444,7 +529,10 @@ __device__ __forceinline__ T3PairRun t3_pair_run(long long g, long long g_end, i
   return r;
 }
 
-template <int KS>
+// F16 = false: 3xTF32, KS = 8-channel steps (two blocked groups).  F16 = true: two-way fp16 split, KS = 16-channel steps (four
+// blocked groups): a ring slot is [raw fp32: 4 groups][piece 0: 2 groups of 8 channels][piece 1], the split warps convert the
+// whole segment, and the three products of a (tap, step) are x0.w1, x1.w0 (corrections, first) and x0.w0.
+template <int KS, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3d_igemm_tf32x3_pair_kernel(const T3Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [12] segment landed (local TMA)
@@ -460,7 +548,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
   constexpr uint32_t w_term_bytes = 9u * KS * 2u * kT3N * 16u;  // one of hi / lo, this CTA's 48 columns
   constexpr uint32_t w_bytes = 2u * w_term_bytes;
   const uint32_t slot_term = 2u * static_cast<uint32_t>(a.NP) * 16u;
-  const uint32_t slot_bytes = 2u * slot_term;
+  const uint32_t slot_bytes = (F16 ? 4u : 2u) * slot_term;
+  constexpr int kRawGroups = F16 ? 4 : 2;  // blocked groups of 4 channels per segment
   uint8_t* slot_s = w_s + ((w_bytes + 127u) & ~127u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -518,10 +607,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
             const uint32_t slot = seq % nslot;
             tc::mbar_wait(empty + slot, ((seq / nslot) & 1u) ^ 1u);
             ++seq;
-            tc::mbar_arrive_expect_tx(full + slot, npos * 32u);
+            tc::mbar_arrive_expect_tx(full + slot, npos * 16u * kRawGroups);
 #pragma unroll
-            for (int kg = 0; kg < 2; ++kg) {
-              const uint4* src = a.x + ((static_cast<long long>(b) * a.G + (ks * 2 + kg)) * a.Ti + pa) * in_plane + q0;
+            for (int kg = 0; kg < kRawGroups; ++kg) {
+              const uint4* src = a.x + ((static_cast<long long>(b) * a.G + (ks * kRawGroups + kg)) * a.Ti + pa) * in_plane + q0;
               tc::bulk_g2s(slot_s + slot * slot_bytes + static_cast<uint32_t>(kg) * a.NP * 16u, src, npos * 16u, full + slot);
             }
           }
@@ -554,7 +643,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
       uint32_t tap16[9];
 #pragma unroll
       for (int hw = 0; hw < 9; ++hw) tap16[hw] = static_cast<uint32_t>((hw / 3) * a.Wi + (hw % 3));
-      const uint32_t idesc = tc::umma_idesc(256, kT3PairN, /*TF32*/ 2, /*K-major*/ 0, 0);
+      const uint32_t idesc = tc::umma_idesc(256, kT3PairN, /*F16 : TF32*/ F16 ? 0 : 2, /*K-major*/ 0, 0);
+      // operand pieces inside a slot: 3xTF32 reads the raw segment as x_hi (the hardware truncates) and x_lo behind it;
+      // the fp16 split reads piece 0 / piece 1 behind the raw segment
+      const uint32_t a_main16 = F16 ? 2u * slot_term16 : 0u, a_corr16 = F16 ? 3u * slot_term16 : slot_term16;
       tc::mbar_wait_cluster(wready, 0);
       uint32_t seq = 0, blk_ph = 0, pc0 = 0;
       for (long long g = g_begin; g < g_end;) {
@@ -578,8 +670,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
 #pragma unroll
               for (int hw = 0; hw < 9; ++hw) {
                 const uint32_t b_t = b_lo_base + static_cast<uint32_t>(hw * KS + ks) * b_step16;
-                tc::umma_tf32_pair_lohi(d, a_seg[ks] + tap16[hw], desc_hi, b_t + w_term16, desc_hi, idesc, (ks | hw) ? 1u : 0u);
-                tc::umma_tf32_pair_lohi(d, a_seg[ks] + slot_term16 + tap16[hw], desc_hi, b_t, desc_hi, idesc, 1u);
+                if (F16) {
+                  t3_mma_f16_pair(d, a_seg[ks] + a_main16 + tap16[hw], desc_hi, b_t + w_term16, desc_hi, idesc, (ks | hw) ? 1u : 0u);
+                  t3_mma_f16_pair(d, a_seg[ks] + a_corr16 + tap16[hw], desc_hi, b_t, desc_hi, idesc, 1u);
+                } else {
+                  tc::umma_tf32_pair_lohi(d, a_seg[ks] + tap16[hw], desc_hi, b_t + w_term16, desc_hi, idesc, (ks | hw) ? 1u : 0u);
+                  tc::umma_tf32_pair_lohi(d, a_seg[ks] + slot_term16 + tap16[hw], desc_hi, b_t, desc_hi, idesc, 1u);
+                }
               }
             }
           }
@@ -587,9 +684,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
           for (int ks = 0; ks < KS; ++ks) {
             if (leader) {
 #pragma unroll
-              for (int hw = 0; hw < 9; ++hw)
-                tc::umma_tf32_pair_lohi(d, a_seg[ks] + tap16[hw], desc_hi, b_lo_base + static_cast<uint32_t>(hw * KS + ks) * b_step16,
-                                        desc_hi, idesc, 1u);
+              for (int hw = 0; hw < 9; ++hw) {
+                if (F16)
+                  t3_mma_f16_pair(d, a_seg[ks] + a_main16 + tap16[hw], desc_hi, b_lo_base + static_cast<uint32_t>(hw * KS + ks) * b_step16,
+                                  desc_hi, idesc, 1u);
+                else
+                  tc::umma_tf32_pair_lohi(d, a_seg[ks] + tap16[hw], desc_hi, b_lo_base + static_cast<uint32_t>(hw * KS + ks) * b_step16,
+                                          desc_hi, idesc, 1u);
+              }
               tc::umma_commit_pair(empty + (seq + ks) % nslot, 3);  // the segment is consumed in both CTAs
             }
           }
@@ -607,6 +709,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
     const int tid = threadIdx.x - 64;
     uint32_t seq = 0;
     const uint32_t ready0 = tc::map_to_cta(ready, 0);  // the leader's barrier array
+    const float sx = F16 ? t3_exp2i(t3_scale_exp(__ldg(a.amax_in))) : 1.f;
     for (long long g = g_begin; g < g_end;) {
       const T3PairRun r = t3_pair_run(g, g_end, a.To);
       int col = 2 * r.col + static_cast<int>(rank);
@@ -623,13 +726,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
           tc::mbar_wait(full + slot, (seq / nslot) & 1u);
           ++seq;
           float4* hi = reinterpret_cast<float4*>(slot_s + slot * slot_bytes);
-          float4* lo = reinterpret_cast<float4*>(slot_s + slot * slot_bytes + slot_term);
+          if (F16) {
+            uint4* p0 = reinterpret_cast<uint4*>(slot_s + slot * slot_bytes + 2u * slot_term);
+            uint4* p1 = reinterpret_cast<uint4*>(slot_s + slot * slot_bytes + 3u * slot_term);
 #pragma unroll
-          for (int kg = 0; kg < 2; ++kg)
-            for (int p = tid; p < npos; p += 128) {
-              const float4 v = hi[kg * a.NP + p];
-              lo[kg * a.NP + p] = make_float4(v.x - t3_trunc(v.x), v.y - t3_trunc(v.y), v.z - t3_trunc(v.z), v.w - t3_trunc(v.w));
-            }
+            for (int g8 = 0; g8 < 2; ++g8)
+              for (int p = tid; p < npos; p += 128) {
+                uint4 q0, q1;
+                t3_split8h(hi[(2 * g8) * a.NP + p], hi[(2 * g8 + 1) * a.NP + p], sx, q0, q1);
+                p0[g8 * a.NP + p] = q0;
+                p1[g8 * a.NP + p] = q1;
+              }
+          } else {
+            float4* lo = reinterpret_cast<float4*>(slot_s + slot * slot_bytes + slot_term);
+#pragma unroll
+            for (int kg = 0; kg < 2; ++kg)
+              for (int p = tid; p < npos; p += 128) {
+                const float4 v = hi[kg * a.NP + p];
+                lo[kg * a.NP + p] = make_float4(v.x - t3_trunc(v.x), v.y - t3_trunc(v.y), v.z - t3_trunc(v.z), v.w - t3_trunc(v.w));
+              }
+          }
           tc::fence_proxy_async();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(ready0 + slot * 8u);
@@ -648,6 +764,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
     const long long o_cg = static_cast<long long>(Top) * oplane, m_cg = static_cast<long long>(a.To) * mplane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
     const uint32_t bempty0 = tc::map_to_cta(bempty, 0);
+    // two-way fp16 split: the sums carry the scales of both operands (two exact multiplications: 2^-(ex + ew) may not be a float)
+    const float unscale_x = F16 ? t3_exp2i(-t3_scale_exp(__ldg(a.amax_in))) : 1.f;
+    const float unscale_w = F16 ? t3_exp2i(-t3_scale_exp(__ldg(a.amax_w))) : 1.f;
     uint32_t blk_ph = 0, pc0 = 0;
     float am = 0.f;  // largest magnitude this thread has written
     for (long long g = g_begin; g < g_end;) {
@@ -695,7 +814,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
         if (valid) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            float s = f[c] + bias_s[c];
+            float s = F16 ? fmaf(f[c] * unscale_x, unscale_w, bias_s[c]) : f[c] + bias_s[c];
             if (a.relu) s = fmaxf(s, 0.f);
             f[c] = s;
           }
@@ -832,7 +951,7 @@ static size_t t3_ws_bytes(int Ci_role, int Co_role) {
 
 static int launch_t3(const void* xb, const float* w, long long s_co, long long s_ci, int flip, const float* bias, const void* mask,
                      void* y_blk, float* y_nc, void* ws, size_t ws_bytes, int B, int Ci, int Ti, int Hi, int Wi, int Co, int out_pad,
-                     int relu, int zero_planes, int To, int plane_off, float* amax_out, cudaStream_t stream) {
+                     int relu, int zero_planes, int To, int plane_off, const float* amax_in, float* amax_out, cudaStream_t stream) {
   T3Args a;
   a.x = static_cast<const uint4*>(xb);
   a.bias = bias;
@@ -867,6 +986,37 @@ static int launch_t3(const void* xb, const float* w, long long s_co, long long s
   a.wq = static_cast<const uint4*>(ws);
   const int KS = a.G / 2;
   const bool pair = g_t3_pair && a.nhalf == 2 && sms >= 2;
+  a.amax_in = amax_in;
+  a.amax_w = nullptr;
+  if (amax_in && pair && a.G % 4 == 0) {
+    // two-way fp16 split (CTA pair, 16-channel steps): half the weights, half the MMAs
+    const int KS16 = a.G / 4;
+    const size_t w_bytes = static_cast<size_t>(2) * 9 * KS16 * 2 * kT3N * 16;  // per CTA: two pieces
+    float* amax_w = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 2 * w_bytes);  // behind the weights of both ranks (<= need - 16)
+    a.amax_w = amax_w;
+    t3_weight_prep_f16_kernel<<<ceil_div(static_cast<int>(2 * w_bytes / 4), 256), 256, 0, stream>>>(
+        w, static_cast<uint32_t*>(ws), Ci, Co, KS16, s_co, s_ci, flip, Co * Ci * 27, amax_w);
+    PVB_LAUNCHED("t3_weight_prep_f16");
+    const size_t fixed = 640 + round_up(w_bytes, static_cast<size_t>(128));
+    const size_t slot_bytes = static_cast<size_t>(8) * a.NP * 16;
+    long long nslot = (227 * 1024 - static_cast<long long>(fixed)) / static_cast<long long>(slot_bytes);
+    if (nslot > kT3MaxSlots) nslot = kT3MaxSlots;
+    PVB_REQUIRE(nslot >= KS16, "conv3d_f16x2: Cin=%d Cout=%d width=%d does not fit in shared memory", Ci, Co, Wi);
+    a.nslot = static_cast<int>(nslot);
+    const size_t smem = fixed + nslot * slot_bytes;
+    const long long pair_tiles = ((static_cast<long long>(B) * a.tiles_q + 1) / 2) * a.To;
+    long long npairs = sms / 2;
+    if (npairs > pair_tiles) npairs = pair_tiles;
+    if (KS16 == 1) {
+      PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_tf32x3_pair_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv3d_igemm_tf32x3_pair_kernel<1, true><<<static_cast<unsigned>(2 * npairs), kT3Threads, smem, stream>>>(a);
+    } else {
+      PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_tf32x3_pair_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv3d_igemm_tf32x3_pair_kernel<2, true><<<static_cast<unsigned>(2 * npairs), kT3Threads, smem, stream>>>(a);
+    }
+    PVB_LAUNCHED("conv3d_igemm_f16x2_pair");
+    return PVB200_OK;
+  }
   {
     const int total = static_cast<int>(need / 4);
     t3_weight_prep_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(w, static_cast<float*>(ws), Ci, Co, KS, a.nhalf, s_co, s_ci, flip,
@@ -887,8 +1037,8 @@ static int launch_t3(const void* xb, const float* w, long long s_co, long long s
     if (npairs > pair_tiles) npairs = pair_tiles;
 #define PVB_T3P_LAUNCH(KSV)                                                                                                      \
   do {                                                                                                                          \
-    PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_tf32x3_pair_kernel<KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv3d_igemm_tf32x3_pair_kernel<KSV><<<static_cast<unsigned>(2 * npairs), kT3Threads, smem, stream>>>(a);                  \
+    PVB_CUDA(cudaFuncSetAttribute(conv3d_igemm_tf32x3_pair_kernel<KSV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv3d_igemm_tf32x3_pair_kernel<KSV, false><<<static_cast<unsigned>(2 * npairs), kT3Threads, smem, stream>>>(a);                  \
   } while (0)
     switch (KS) {
       case 1: PVB_T3P_LAUNCH(1); break;
@@ -978,17 +1128,17 @@ int pvb200_sat_normalise_blocked_f32(const int16_t* x, float* y, const float* me
 
 int pvb200_conv3d_fwd_tf32x3(const float* xb, const float* w, const float* bias, float* y_blk, float* y_nc, void* workspace,
                              size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int relu, int out_pad,
-                             int pad_t, float* amax_out, pvb200_stream_t stream) {
+                             int pad_t, const float* amax_in, float* amax_out, pvb200_stream_t stream) {
   using namespace pvb;
   PVB_REQUIRE(xb && w, "conv3d_fwd_tf32x3: null pointer");
   PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && out_pad >= 0 && (pad_t == 0 || pad_t == 1), "conv3d_fwd_tf32x3: bad shape");
   return launch_t3(xb, w, static_cast<long long>(Cin) * 27, 27, 0, bias, nullptr, y_blk, y_nc, workspace, workspace_bytes, B, Cin, Ti,
-                   Hi, Wi, Cout, out_pad, relu, /*zero_planes=*/0, /*To=*/Ti + 2 * pad_t - 2, /*plane_off=*/-pad_t, amax_out, as_stream(stream));
+                   Hi, Wi, Cout, out_pad, relu, /*zero_planes=*/0, /*To=*/Ti + 2 * pad_t - 2, /*plane_off=*/-pad_t, amax_in, amax_out, as_stream(stream));
 }
 
 int pvb200_conv3d_dgrad_tf32x3(const float* gz_padded, const float* w, const float* mask_blk, float* gx_blk, float* gx_nc,
                                void* workspace, size_t workspace_bytes, int B, int Cin, int Ti, int Hi, int Wi, int Cout, int out_pad,
-                               int pad_t, float* amax_out, pvb200_stream_t stream) {
+                               int pad_t, const float* amax_in, float* amax_out, pvb200_stream_t stream) {
   using namespace pvb;
   PVB_REQUIRE(gz_padded && w, "conv3d_dgrad_tf32x3: null pointer");
   PVB_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Ti + 2 * pad_t > 2 && Hi > 2 && Wi > 2 && out_pad >= 0 && (pad_t == 0 || pad_t == 1),
@@ -997,7 +1147,7 @@ int pvb200_conv3d_dgrad_tf32x3(const float* gz_padded, const float* w, const flo
   // kernel output = gx [B][G(Cin)][Ti][Hi][Wi]: gx[t] reads the padded planes t + pad_t + {0,1,2}
   return launch_t3(gz_padded, w, /*s_co (out role = ci)*/ 27, /*s_ci (in role = co)*/ static_cast<long long>(Cin) * 27, 1, nullptr,
                    mask_blk, gx_blk, gx_nc, workspace, workspace_bytes, B, /*Ci role*/ Cout, Ti + 2 * pad_t + 2, Hi + 2, Wi + 2,
-                   /*Co role*/ Cin, out_pad, 0, /*zero_planes=*/2, /*To=*/Ti, /*plane_off=*/pad_t, amax_out, as_stream(stream));
+                   /*Co role*/ Cin, out_pad, 0, /*zero_planes=*/2, /*To=*/Ti, /*plane_off=*/pad_t, amax_in, amax_out, as_stream(stream));
 }
 
 }  // extern "C"

@@ -96,9 +96,10 @@ SIGNATURES = {
     "pvb200_sat_normalise_blocked_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                                  c_int, c_void_p, c_void_p]),
     "pvb200_conv3d_fwd_tf32x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                                         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                         c_void_p]),
     "pvb200_conv3d_dgrad_tf32x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pvb200_conv3d_wgrad_bf16x3_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "pvb200_conv3d_wgrad_bf16x3_workspace_bytes": (c_size_t, []),
     "pvb200_conv3d_wgrad_bf16x3": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -404,7 +404,8 @@ def sat_normalise_blocked_f32(x: torch.Tensor, mean: torch.Tensor, std: torch.Te
 
 
 def conv3d_fwd_tf32x3(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool = True, out_pad: int = 0,
-                      pad_t: int = 0, want_blk: bool = True, want_nc: bool = False, amax: Optional[torch.Tensor] = None):
+                      pad_t: int = 0, want_blk: bool = True, want_nc: bool = False, amax: Optional[torch.Tensor] = None,
+                      amax_in: Optional[torch.Tensor] = None):
     """relu(conv3d(x, w, b)) on the tensor cores at fp32 accuracy (3xTF32).  xb blocked fp32 [B,G,Ti,Hi,Wi,4]; returns
     (blocked copy | None, NCDHW copy | None)."""
     L = _lib.load()
@@ -427,14 +428,14 @@ def conv3d_fwd_tf32x3(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tenso
     with _timed(f"conv3d_fwd_tf32x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
                 4.0 * xb.numel() + 4.0 * npos * (4 * GO * int(want_blk) + Co * int(want_nc))):
         rc = L.pvb200_conv3d_fwd_tf32x3(_p(xb), _p(w), _p(b), _p(y_blk), _p(y_nc), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co,
-                                        int(relu), out_pad, pad_t, _p(amax), _stream())
+                                        int(relu), out_pad, pad_t, _p(amax_in), _p(amax), _stream())
     _lib.check(rc, "conv3d_fwd_tf32x3")
     return y_blk, y_nc
 
 
 def conv3d_dgrad_tf32x3(gz_padded: torch.Tensor, w: torch.Tensor, mask_blk: Optional[torch.Tensor], out_pad: int = 0,
                         want_blk: bool = True, want_nc: bool = False, persistent: bool = False, pad_t: int = 0,
-                        amax: Optional[torch.Tensor] = None):
+                        amax: Optional[torch.Tensor] = None, amax_in: Optional[torch.Tensor] = None):
     """gx = conv_transpose3d(gz, w) * (mask > 0) on the tensor cores (3xTF32) from gz blocked fp32 zero-padded by 2 on
     T, H, W.  Returns (blocked copy | None, NCDHW copy | None)."""
     L = _lib.load()
@@ -464,7 +465,7 @@ def conv3d_dgrad_tf32x3(gz_padded: torch.Tensor, w: torch.Tensor, mask_blk: Opti
     with _timed(f"conv3d_dgrad_tf32x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
                 4.0 * gz_padded.numel() + 4.0 * npos * (4 * GI * (int(want_blk) + int(mask_blk is not None)) + Ci * int(want_nc))):
         rc = L.pvb200_conv3d_dgrad_tf32x3(_p(gz_padded), _p(w), _p(mask_blk), _p(gx_blk), _p(gx_nc), _p(ws), ws.numel(), B, Ci, Ti,
-                                          Hi, Wi, Co, out_pad, pad_t, _p(amax), _stream())
+                                          Hi, Wi, Co, out_pad, pad_t, _p(amax_in), _p(amax), _stream())
     _lib.check(rc, "conv3d_dgrad_tf32x3")
     return gx_blk, gx_nc
 
@@ -612,6 +613,8 @@ class EncoderFn(torch.autograd.Function):
 # fp32 mode, tensor-core weight gradient: two-way fp16 split of the scaled operands (three products) instead of the three-way
 # bf16 split (six); the largest magnitudes it scales by come out of the kernels that write the tensors
 FP32_WGRAD_F16X2 = True
+# the same split in the forward / data-gradient implicit GEMM (instead of 3xTF32): K = 16 channels per MMA, half the MMAs
+FP32_CONV_F16X2 = True
 
 
 class EncoderTf32Fn(torch.autograd.Function):
@@ -632,8 +635,9 @@ class EncoderTf32Fn(torch.autograd.Function):
         # per layer: does the tensor-core weight gradient take it?  (input plane of layer l: H - 2l)
         tc_w = [wgrad_bf16x3_supported(wb[2 * l].shape[1], wb[2 * l].shape[0], H - 2 * l, W - 2 * l) for l in range(n)]
         # amax[l] = max |input of layer l|, amax[n + l] = max |gradient w.r.t. layer l's pre-activation| (filled in backward)
-        amax = torch.zeros((2 * n,), dtype=torch.float32, device=sat.device) if FP32_WGRAD_F16X2 else None
+        amax = torch.zeros((2 * n,), dtype=torch.float32, device=sat.device) if (FP32_WGRAD_F16X2 or FP32_CONV_F16X2) else None
         am = (lambda i: amax[i:i + 1]) if amax is not None else (lambda i: None)
+        am_in = am if FP32_CONV_F16X2 else (lambda i: None)
         if sat.dtype == torch.int16:
             x_blk = sat_normalise_blocked_f32(sat, mean, std, amax=am(0))
             x_nc = None if tc_w[0] else sat_normalise(sat, mean, std)
@@ -646,13 +650,13 @@ class EncoderTf32Fn(torch.autograd.Function):
             last = l == n - 1
             want_nc = last or not tc_w[l + 1]
             y_blk, y_nc = conv3d_fwd_tf32x3(ins_blk[l], wb[2 * l], wb[2 * l + 1], relu=True, want_blk=not last, want_nc=want_nc,
-                                            amax=None if last else am(l + 1))
+                                            amax=None if last else am(l + 1), amax_in=am_in(l))
             if not last:
                 ins_blk.append(y_blk)
                 ins_nc.append(y_nc if not tc_w[l + 1] else None)
         keep = [t for t in ins_nc if t is not None]
         ctx.save_for_backward(*wb, *ins_blk, *keep)
-        ctx.n_layers, ctx.tc_w, ctx.amax = n, tc_w, amax
+        ctx.n_layers, ctx.tc_w, ctx.amax, ctx.f16 = n, tc_w, amax, (FP32_WGRAD_F16X2, FP32_CONV_F16X2)
         ctx.nc_index = [i for i, t in enumerate(ins_nc) if t is not None]
         ctx.out_shape = tuple(y_nc.shape)
         return y_nc.view(B, -1)
@@ -677,7 +681,7 @@ class EncoderTf32Fn(torch.autograd.Function):
             Co, Ci = wb[2 * l].shape[0], wb[2 * l].shape[1]
             if tc_w[l]:
                 dw, db = conv3d_wgrad_bf16x3(ins_blk[l], gz_blk, Ci, Co, gz_pad=gz_pad,
-                                             amax=None if amax is None else (am(l), am(n + l)))
+                                             amax=(am(l), am(n + l)) if ctx.f16[0] else None)
             else:
                 dw, db = conv3d_wgrad(ins_nc[l], gz_nc)
             grads[2 * l], grads[2 * l + 1] = dw, db
@@ -687,7 +691,8 @@ class EncoderTf32Fn(torch.autograd.Function):
                 nxt_pad = 2 if l - 1 >= 1 else 0
                 want_blk = (l - 1 >= 1) or tc_w[l - 1]
                 gz_blk, gz_nc = conv3d_dgrad_tf32x3(gz_blk, wb[2 * l], ins_blk[l], out_pad=nxt_pad if want_blk else 0,
-                                                    want_blk=want_blk, want_nc=not tc_w[l - 1], persistent=True, amax=am(n + l - 1))
+                                                    want_blk=want_blk, want_nc=not tc_w[l - 1], persistent=True, amax=am(n + l - 1),
+                                                    amax_in=am(n + l) if ctx.f16[1] else None)
                 gz_pad = nxt_pad
         return (None, None, None, *grads)
 

@@ -236,6 +236,43 @@ def test_conv3d_wgrad_f16x2_wide_dynamic_range(ops, dev):
     assert not bool(dw.any()) and not bool(db.any())
 
 
+F16_CONV_SHAPES = [
+    (2, 32, 5, 10, 10, 32),   # two 16-channel steps
+    (1, 12, 4, 16, 16, 32),   # Cin = 12 padded to one 16-channel step
+    (3, 32, 4, 64, 64, 32),   # full-size planes, an odd number of (sample, q-tile) columns
+    (1, 28, 6, 9, 12, 24),    # Cout = 24 (the pair kernel's 32 columns per tap, 8 of them zero)
+]
+
+
+@pytest.mark.parametrize("shape", F16_CONV_SHAPES)
+@pytest.mark.parametrize("scales", [(1.0, 1.0), (2.0e4, 3.0e-7), (1.0e-10, 5.0e3)])
+def test_conv3d_fwd_dgrad_f16x2(ops, dev, shape, scales):
+    """Forward and data gradient through the two-way fp16 split (CTA-pair kernel): the fp32 parity bound whatever the
+    magnitudes of the input and of the weights."""
+    B, Ci, T, H, W, Co = shape
+    x, w, b = _case(shape, seed=21)
+    x, w = x * scales[0], w * scales[1]
+    b = b * scales[0] * scales[1]
+    ref = F.conv3d(x.double(), w.double(), b.double())
+    xb = ops.to_blocked_f32(x.to(dev))
+    (ax,) = _amax(ops, dev, xb)
+    am_out = torch.zeros((1,), device=dev)
+    y_blk, y_nc = ops.conv3d_fwd_tf32x3(xb, w.to(dev), b.to(dev), relu=False, want_blk=True, want_nc=True, amax_in=ax, amax=am_out)
+    e_f = nerr(y_nc, ref)
+    assert float(am_out) == float(y_nc.abs().max())
+    g = torch.Generator().manual_seed(22)
+    gz = torch.randn(ref.shape, generator=g) * scales[0]
+    xd = x.double().requires_grad_(True)
+    F.conv3d(xd, w.double()).backward(gz.double())
+    mask = torch.rand(x.shape, generator=g) - 0.3  # ReLU mask source
+    gzb = ops.to_blocked_f32(gz.to(dev), pad=2)
+    (ag,) = _amax(ops, dev, gzb)
+    _, gx = ops.conv3d_dgrad_tf32x3(gzb, w.to(dev), ops.to_blocked_f32(mask.to(dev)), want_blk=False, want_nc=True, amax_in=ag)
+    e_d = nerr(gx, xd.grad * (mask > 0).double())
+    print(f"f16x2 conv {shape} scales {scales}: fwd {e_f:.2e} dgrad {e_d:.2e}")
+    assert e_f <= TOL and e_d <= TOL
+
+
 def test_amax_out_of_the_producing_kernels(ops, dev):
     """Every kernel that writes a blocked fp32 tensor of the encoder can report the largest magnitude it wrote (what the
     two-way fp16 split scales by): normalise, layout change, convolution forward and data gradient."""
