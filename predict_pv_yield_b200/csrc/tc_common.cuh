@@ -167,10 +167,13 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
-// arrive on an mbarrier of another CTA of the cluster (release at cluster scope: the writes of this thread -- generic or,
-// after fence.proxy.async, async-proxy visible -- are ordered before the arrival)
+// arrive on an mbarrier of another CTA of the cluster.  Release at CTA scope (the PTX default, what CUTLASS' ClusterBarrier
+// uses): everything these arrivals publish stays inside the arriving CTA -- shared-memory operand pieces read by its own
+// tensor core (after fence.proxy.async) and tensor-memory reads (after tcgen05.fence::before_thread_sync).  The
+// .release.cluster form compiled to MEMBAR.ALL.GPU + ERRBAR in front of every arrival: 29 % of the stall samples of the
+// CTA-pair convolution (profiles/ncu_f16x2_r02.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait on a local mbarrier whose arrivals may come from the peer CTA (acquire at cluster scope)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
