@@ -355,6 +355,12 @@ def tf32x3_supported(Ci: int, Co: int) -> bool:
     return Ci <= 32 and Co <= 32
 
 
+def conv_f16x2_applies(Ci: int, Co: int) -> bool:
+    """Shapes for which the implicit GEMM takes the two-way fp16 split when it is given the input's largest magnitude
+    (CTA-pair kernel, 16-channel steps); other shapes run 3xTF32.  ``Ci`` / ``Co``: the kernel's input / output role."""
+    return Co > 16 and blocked4_groups(Ci) % 4 == 0
+
+
 def to_blocked_f32(x: torch.Tensor, pad: int = 0, persistent: bool = False, amax: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[B,C,T,H,W] fp32 -> blocked fp32 [B,G,T+2p,H+2p,W+2p,4] (zero border, zero pad channels).  ``amax`` (here and in the
     operators below): one zeroed fp32 device element that receives the largest magnitude written."""
@@ -425,7 +431,8 @@ def conv3d_fwd_tf32x3(xb: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tenso
         y_nc = torch.empty((B, Co, To, Ho, Wo), dtype=torch.float32, device=xb.device)
     ws = _workspace("conv_tf32x3", L.pvb200_conv3d_tf32x3_workspace_bytes(Ci, Co), xb.device)
     npos = B * To * Ho * Wo
-    with _timed(f"conv3d_fwd_tf32x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
+    kind = "f16x2" if (amax_in is not None and conv_f16x2_applies(Ci, Co)) else "tf32x3"
+    with _timed(f"conv3d_fwd_{kind}[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
                 4.0 * xb.numel() + 4.0 * npos * (4 * GO * int(want_blk) + Co * int(want_nc))):
         rc = L.pvb200_conv3d_fwd_tf32x3(_p(xb), _p(w), _p(b), _p(y_blk), _p(y_nc), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co,
                                         int(relu), out_pad, pad_t, _p(amax_in), _p(amax), _stream())
@@ -462,7 +469,8 @@ def conv3d_dgrad_tf32x3(gz_padded: torch.Tensor, w: torch.Tensor, mask_blk: Opti
         gx_nc = torch.empty((B, Ci, Ti, Hi, Wi), dtype=torch.float32, device=gz_padded.device)
     ws = _workspace("conv_tf32x3", L.pvb200_conv3d_tf32x3_workspace_bytes(Ci, Co), gz_padded.device)
     npos = B * Ti * Hi * Wi
-    with _timed(f"conv3d_dgrad_tf32x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
+    kind = "f16x2" if (amax_in is not None and conv_f16x2_applies(Co, Ci)) else "tf32x3"
+    with _timed(f"conv3d_dgrad_{kind}[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos,
                 4.0 * gz_padded.numel() + 4.0 * npos * (4 * GI * (int(want_blk) + int(mask_blk is not None)) + Ci * int(want_nc))):
         rc = L.pvb200_conv3d_dgrad_tf32x3(_p(gz_padded), _p(w), _p(mask_blk), _p(gx_blk), _p(gx_nc), _p(ws), ws.numel(), B, Ci, Ti,
                                           Hi, Wi, Co, out_pad, pad_t, _p(amax_in), _p(amax), _stream())
@@ -505,7 +513,7 @@ def conv3d_wgrad_bf16x3(xb: torch.Tensor, gzb: torch.Tensor, Ci: int, Co: int, g
     db = torch.empty((Co,), dtype=torch.float32, device=xb.device)
     ws = _workspace("wgrad_bf16x3", L.pvb200_conv3d_wgrad_bf16x3_workspace_bytes(), xb.device)
     npos = B * To * Ho * Wo
-    with _timed(f"conv3d_wgrad_bf16x3[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 4.0 * xb.numel() + 16.0 * blocked4_groups(Co) * npos):
+    with _timed(f"conv3d_wgrad_{'bf16x3' if amax is None else 'f16x2'}[Ci={Ci}]", 2.0 * 27 * Ci * Co * npos, 4.0 * xb.numel() + 16.0 * blocked4_groups(Co) * npos):
         if amax is None:
             rc = L.pvb200_conv3d_wgrad_bf16x3(_p(xb), _p(gzb), gz_pad, _p(dw), _p(db), _p(ws), ws.numel(), B, Ci, Ti, Hi, Wi, Co, pad_t,
                                               _stream())
