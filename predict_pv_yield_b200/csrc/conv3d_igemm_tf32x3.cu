@@ -786,6 +786,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
         float f[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) f[c] = 0.f;
+        // data gradient: the ReLU-mask source of this position is fetched BEFORE the accumulator blocks are waited for (the
+        // loads sat behind the tensor-memory reads: 47 % of the stall samples, tensor pipe at 53 %)
+        uint4 mk[8];
+        if (a.mask && valid) {
+#pragma unroll
+          for (int gi = 0; gi < 8; ++gi)
+            if (gi < GO) mk[gi] = __ldg(a.mask + m_off + gi * m_cg);
+        }
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
           const int pa = r.t0 + j + kt + a.plane_off;
@@ -822,8 +830,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
 #pragma unroll
             for (int gi = 0; gi < 8; ++gi) {
               if (gi >= GO) continue;
-              const uint4 mk = __ldg(a.mask + m_off + gi * m_cg);
-              const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+              const uint32_t mw[4] = {mk[gi].x, mk[gi].y, mk[gi].z, mk[gi].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) f[gi * 4 + e] = (__uint_as_float(mw[e]) > 0.f) ? f[gi * 4 + e] : 0.f;
             }

@@ -100,10 +100,11 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamTensors t, co
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const long long i = off + (u * 256 + threadIdx.x) * 4;
-        pv[u] = *reinterpret_cast<const float4*>(p + i);
+        // streaming hints both ways: nothing here is read again before 4 GB have passed through the 126 MB L2
+        pv[u] = __ldcs(reinterpret_cast<const float4*>(p + i));
         gv[u] = __ldcs(reinterpret_cast<const float4*>(g + i));
-        mv[u] = *reinterpret_cast<const float4*>(m + i);
-        vv[u] = *reinterpret_cast<const float4*>(v + i);
+        mv[u] = __ldcs(reinterpret_cast<const float4*>(m + i));
+        vv[u] = __ldcs(reinterpret_cast<const float4*>(v + i));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -112,9 +113,9 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamTensors t, co
         adam_elem(pv[u].y, gv[u].y, mv[u].y, vv[u].y, s);
         adam_elem(pv[u].z, gv[u].z, mv[u].z, vv[u].z, s);
         adam_elem(pv[u].w, gv[u].w, mv[u].w, vv[u].w, s);
-        *reinterpret_cast<float4*>(p + i) = pv[u];
-        *reinterpret_cast<float4*>(m + i) = mv[u];
-        *reinterpret_cast<float4*>(v + i) = vv[u];
+        __stcs(reinterpret_cast<float4*>(p + i), pv[u]);
+        __stcs(reinterpret_cast<float4*>(m + i), mv[u]);
+        __stcs(reinterpret_cast<float4*>(v + i), vv[u]);
       }
     } else {
       const long long end = min(n, off + kAdamChunk);
