@@ -40,13 +40,14 @@
 
 namespace pvb {
 
-constexpr int kW3Threads = 704;   // 2 + 8 split + 12 drain warps
+constexpr int kW3Threads = 448;   // 2 + 8 split + 4 drain warps: 146 registers per thread (704 threads left 80 and the split spilled)
 constexpr int kW3SplitWarps = 8;
 constexpr int kW3Stages = 2;    // piece buffers
 constexpr int kW3Flush = 16;    // steps between two drains of the accumulators
 constexpr int kW3AccCols = 96;  // TMEM columns per kw accumulator
 constexpr int kW3Pairs = 6;     // products of the three-way split that are kept
 constexpr int kW3RowBlock = 6;  // output rows per block of the step order (see w3_step)
+constexpr int kW3Items = 3;     // items (8 channels of one position) a split thread converts per operand and step, at most
 
 struct W3Args {
   int gz_pad;       // zero padding of the gradient tensor on T, H, W (coordinates of the gradient's tensor map are shifted by it)
@@ -132,6 +133,10 @@ __device__ __forceinline__ float w3_ld_keep(const float* p, uint64_t policy) {
 }
 __device__ __forceinline__ void w3_st_keep(float* p, float v, uint64_t policy) {
   asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
+}
+
+__device__ __forceinline__ void w3_red_keep(float* p, float v, uint64_t policy) {
+  asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
 }
 
 struct W3Step {
@@ -353,19 +358,34 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       uint4* ap2 = reinterpret_cast<uint4*>(a_s + (stage * NP + (NP - 1u)) * a_piece);
       const int row = 3 * Wi;  // elements of one fp32 channel group (three rows)
       // item i = (g8, r): no divisions in the loop -- (g8, r) advance incrementally from the thread's first item
+      // (at most kW3Items items per thread: G8 <= 4 groups of 3 rows of <= 64 positions over 256 threads; all loads of a
+      // thread are issued before the first conversion -- two warps per scheduler cannot hide a load-convert-store chain)
       {
         int g8 = a_g0, r = a_r0;
-        for (int i = tid; i < ((a.dbg_flags & 2) ? 0 : G8 * row); i += NT) {
-          uint4 q0, q1, q2;
-          if (NP == 3) {
-            w3_split8(ar[(2 * g8) * row + r], ar[(2 * g8 + 1) * row + r], q0, q1, q2);
-            ap0[i] = q0; ap1[i] = q1; ap2[i] = q2;
-          } else {
-            w3_split8h(ar[(2 * g8) * row + r], ar[(2 * g8 + 1) * row + r], sx, q0, q1);
-            ap0[i] = q0; ap1[i] = q1;
+        const int n_items = (a.dbg_flags & 2) ? 0 : G8 * row;
+        float4 lo[kW3Items], hi[kW3Items];
+#pragma unroll
+        for (int u = 0; u < kW3Items; ++u) {
+          if (tid + u * NT < n_items) {
+            lo[u] = ar[(2 * g8) * row + r];
+            hi[u] = ar[(2 * g8 + 1) * row + r];
           }
           r += a_dr; g8 += a_dg;
           if (r >= row) { r -= row; ++g8; }
+        }
+#pragma unroll
+        for (int u = 0; u < kW3Items; ++u) {
+          const int i = tid + u * NT;
+          if (i < n_items) {
+            uint4 q0, q1, q2;
+            if (NP == 3) {
+              w3_split8(lo[u], hi[u], q0, q1, q2);
+              ap0[i] = q0; ap1[i] = q1; ap2[i] = q2;
+            } else {
+              w3_split8h(lo[u], hi[u], sx, q0, q1);
+              ap0[i] = q0; ap1[i] = q1;
+            }
+          }
         }
       }
       __syncwarp();
@@ -379,19 +399,36 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
         uint4* bp2 = reinterpret_cast<uint4*>(b_s + (stage * NP + (NP - 1u)) * b_piece);
         const int nrow = nb * go8;  // (kt, g8) rows of WP positions
         int rw = b_r0, w = b_w0;
-        for (; rw < nrow;) {
-          const int ktl = rw / go8;  // go8 <= 4, nb <= 3: a handful of values, the compiler turns this into compares
-          const int g8 = rw - ktl * go8, kt = st.kt_lo + ktl;
-          uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;  // positions beyond the row: the K padding of the operand
-          if (w < a.Wo) {
-            if (NP == 3) w3_split8(br[((2 * g8) * 3 + (2 - kt)) * a.Wo + w], br[((2 * g8 + 1) * 3 + (2 - kt)) * a.Wo + w], q0, q1, q2);
-            else w3_split8h(br[((2 * g8) * 3 + (2 - kt)) * a.Wo + w], br[((2 * g8 + 1) * 3 + (2 - kt)) * a.Wo + w], sg, q0, q1);
+        float4 lo[kW3Items], hi[kW3Items];
+        int o[kW3Items];
+#pragma unroll
+        for (int u = 0; u < kW3Items; ++u) {
+          o[u] = -1;
+          if (rw < nrow) {
+            const int ktl = rw / go8;  // go8 <= 4, nb <= 3: a handful of values, the compiler turns this into compares
+            const int g8 = rw - ktl * go8, kt = st.kt_lo + ktl;
+            o[u] = (kt * GP8 + g8) * WP + w;
+            lo[u] = hi[u] = make_float4(0.f, 0.f, 0.f, 0.f);  // positions beyond the row: the K padding of the operand
+            if (w < a.Wo) {
+              lo[u] = br[((2 * g8) * 3 + (2 - kt)) * a.Wo + w];
+              hi[u] = br[((2 * g8 + 1) * 3 + (2 - kt)) * a.Wo + w];
+            }
           }
-          const int o = (kt * GP8 + g8) * WP + w;
-          bp0[o] = q0; bp1[o] = q1;
-          if (NP == 3) bp2[o] = q2;
           w += b_dw; rw += b_dr;
           if (w >= WP) { w -= WP; ++rw; }
+        }
+#pragma unroll
+        for (int u = 0; u < kW3Items; ++u) {
+          if (o[u] >= 0) {
+            uint4 q0, q1, q2;
+            if (NP == 3) {
+              w3_split8(lo[u], hi[u], q0, q1, q2);
+              bp0[o[u]] = q0; bp1[o[u]] = q1; bp2[o[u]] = q2;
+            } else {
+              w3_split8h(lo[u], hi[u], sg, q0, q1);
+              bp0[o[u]] = q0; bp1[o[u]] = q1;
+            }
+          }
         }
       }
       tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
@@ -402,27 +439,25 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       }
     }
   } else {
-    // =============================== accumulator drain (warps 10..21) ===============================
-    // three groups of four warps (one per TMEM lane quadrant), group g drains accumulator kw = g only: the read-modify-write
-    // of one accumulator's partial (L2 latency bound) no longer delays the release of the next one
+    // =============================== accumulator drain (warps 10..13, one per TMEM lane quadrant) ===============================
+    // per window and accumulator: tcgen05.ld, the accumulator goes back to the MMA warp at once, and the window's sums are
+    // added to the CTA's private partial by fire-and-forget red.global.add.f32 (the first window stores): no read-modify-write
+    // round trip, so four warps are enough (the first version needed a group of four per accumulator)
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
     const long long nsteps = s_end - s_begin;
     const long long nwin_total = (nsteps + kW3Flush - 1) / kW3Flush;
     float* mine = a.partial + static_cast<size_t>(blockIdx.x) * 3 * 128 * kW3AccCols + row;  // [kw][column][row]
-    // the partials (22 MB over the grid) are re-read every window while ~100 MB of operands stream through L2 in between:
-    // without a retention hint they were evicted and every read-modify-write went to DRAM
+    // the partials (22 MB over the grid) are touched every window while ~100 MB of operands stream through L2 in between:
+    // without a retention hint they were evicted and every update went to DRAM
     uint64_t keep;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-    const int kw = (warp - 2 - kW3SplitWarps) >> 2;
     for (long long wdx = 0; wdx < nwin_total; ++wdx) {
-      {
+#pragma unroll 1
+      for (int kw = 0; kw < 3; ++kw) {
         tc::mbar_wait(afull + kw, static_cast<uint32_t>(wdx & 1));
         tc::tc_fence_after();
-        float* dst = mine + static_cast<size_t>(kw) * 128 * kW3AccCols;
-        // the whole accumulator row goes to registers first and the accumulator is handed back to the MMA warp at once:
-        // the read-modify-write of the partial (L2 latency) then overlaps the next window's MMAs instead of stalling them
         uint32_t v[3][32];
         if (!(a.dbg_flags & 8)) {
 #pragma unroll
@@ -433,21 +468,18 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(aempty + kw);
         if (a.dbg_flags & (8 | 16)) continue;  // 16: accumulators read and released, no partial traffic
-        // partial layout [kw][column][row]: a warp's 32 rows of one column are 128 contiguous bytes (one wavefront per
-        // instruction; the row-major layout cost 32 sectors per instruction and put the drain on the critical path)
+        // partial layout [kw][column][row]: a warp's 32 rows of one column are 128 contiguous bytes
+        float* dst = mine + static_cast<size_t>(kw) * 128 * kW3AccCols;
+        if (wdx == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float* pc = dst + static_cast<size_t>(c * 32) * 128;
-          float o[32];
-          if (wdx != 0) {  // all 32 loads in flight before the first add (one L2 round trip per 32 columns, not 32)
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = w3_ld_keep(pc + j * 128, keep);
-          } else {
+            for (int j = 0; j < 32; ++j) w3_st_keep(dst + static_cast<size_t>(c * 32 + j) * 128, __uint_as_float(v[c][j]), keep);
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = 0.f;
-          }
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) w3_st_keep(pc + j * 128, o[j] + __uint_as_float(v[c][j]), keep);
+            for (int j = 0; j < 32; ++j) w3_red_keep(dst + static_cast<size_t>(c * 32 + j) * 128, __uint_as_float(v[c][j]), keep);
         }
       }
     }
