@@ -85,6 +85,9 @@ def parse_args():
     ap.add_argument("--reserve-sms", type=int, default=-1,
                     help="N > 1: SMs left to NCCL's kernels by the persistent kernels (default 0: measured at N = 8 bf16, "
                          "reserving 16 / 32 SMs speeds the overlapped kernels up but lengthens the step: 3.53 / 3.73 / 4.21 ms)")
+    ap.add_argument("--static-tiles", action="store_true",
+                    help="N > 1: keep the static work split of the fp32 weight gradient (bit-reproducible sums) instead of chunks "
+                         "claimed from an atomic counter (no grid tail behind CTAs displaced by NCCL)")
     ap.add_argument("--no-shard", action="store_true",
                     help="N > 1: replicate the fc1 optimiser (all-reduce) instead of sharding it by output feature")
     ap.add_argument("--infer-batches", default="512,1024,2048,4096,8192", help="c4: global batch sizes of the sweep")
@@ -102,7 +105,7 @@ def n_params(model_kw):
     return n + fc3_in * 64 + 64 + 64 * 12 + 12
 
 
-def workload_config(cfg_name, precision, batch, world, sharded, global_batch=0, micro=1):
+def workload_config(cfg_name, precision, batch, world, sharded, global_batch=0, micro=1, dynamic=True):
     cfg = CONFIGS[cfg_name]
     arith = {"fp32": "fp32 storage and accumulation; convolutions and fc1 on the tensor cores through split-precision products at fp32 "
                      "accuracy (two-way fp16 split of operands scaled by their tensors' largest magnitudes, 22 significand bits, three "
@@ -118,7 +121,7 @@ def workload_config(cfg_name, precision, batch, world, sharded, global_batch=0, 
         "conv3d_layers": cfg["model"]["number_of_conv3d_layers"],
         "conv3d_channels": cfg["model"]["conv3d_channels"],
         "params": n_params(cfg["model"]),
-        "parallelism": f"dp{world}" + ("+fc1-optimizer-sharded" if sharded else ""),
+        "parallelism": f"dp{world}" + ("+fc1-optimizer-sharded" if sharded else "") + ("+dynamic-wgrad-chunks" if world > 1 and dynamic else ""),
         "optimizer": "FusedAdam (one launch for the small tensors; fc1.weight: row-sharded under data parallelism)",
         "l2_policy": "working set per step (>= 0.4 GB activations + 0.28-0.57 GB fc1 weights + 4 rotating input "
                      "batches) is far larger than the 126 MB L2; no explicit flush",
@@ -355,18 +358,30 @@ def roofline_from_timer(timer, steps, ms_total, peaks, fma_peak):
                 "frac": ach / fma_peak if fma_peak else None,
                 "peak_source": "FP32 FMA pipe measured live by pvb200_probe_fp32_fma (not in MEASURED_PEAKS.json; theoretical "
                                "148 SM x 128 FMA x 2 x 1.965 GHz = 74.5 TFLOP/s)"}
-    # DRAM traffic of the dominant kernel from a committed ncu --set full capture, when one exists for this kernel
+    # DRAM traffic of the dominant kernel from a committed ncu --set full capture, when one exists for this kernel: the file
+    # names the commit it was taken at and the sha1 of the kernel's source then -- compared with the source now
     roof["traffic"] = None
     for fn in ("traffic_r02.json", "traffic_r01c.json"):
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", fn))).get(dname)
+            table = json.load(open(os.path.join(ROOT, "profiles", fn)))
+            tr = table.get(dname)
         except Exception:
-            tr = None
+            table, tr = {}, None
         if tr:
             roof["traffic"] = tr["traffic"]
-            roof["traffic_note"] = {"algorithmic_bytes_same_launch": tr["algorithmic"], "launch": tr["launch"],
-                                    "source": f"profiles/{fn} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum; "
-                                              "a committed capture, not re-measured by this run)"}
+            note = {"algorithmic_bytes_same_launch": tr["algorithmic"], "launch": tr["launch"],
+                    "source": f"profiles/{fn} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum; "
+                              "a committed capture, not re-measured by this run)",
+                    "capture_commit": table.get("_commit")}
+            src = tr.get("source_file")
+            if src:
+                try:
+                    import hashlib
+                    now = hashlib.sha1(open(os.path.join(ROOT, src), "rb").read()).hexdigest()
+                    note["kernel_source_changed_since_capture"] = now != tr.get("source_sha1")
+                except Exception:
+                    note["kernel_source_changed_since_capture"] = None
+            roof["traffic_note"] = note
             break
     roof["share_of_step"] = dd["ms"] / ms_total
     roof["ms_per_step"] = dd["ms"] / steps
@@ -402,7 +417,7 @@ class Job:
             from predict_pv_yield_b200.dp import GradientExchange
 
             self.sharded = not args.no_shard  # fc1 optimiser sharded by rows (bf16: + shadow all-gather; fp32: row all-gather)
-            self.exchange = GradientExchange(self.model, shard_large=self.sharded)
+            self.exchange = GradientExchange(self.model, shard_large=self.sharded, dynamic_tiles=not args.static_tiles)
             lib.load().pvb200_reserve_sms(max(args.reserve_sms, 0))
             self.exchange.attach_optimizer(self.opt)
         legacy = self.cfg["model"]["include_pv_yield"] or self.cfg["model"]["include_nwp"]
@@ -734,7 +749,7 @@ def run_ours(args):
             r3 = measure_train(torch, dist, j3, args, args.steps, args.warmup, tag == "weak" and not args.no_e2e, tag == "weak")
             if rank == 0:
                 blk = {"value": r3["value"], "unit": UNIT, "ms_per_step": r3["ms_per_step"], "scaling": tag,
-                       "config": workload_config("c3", "bf16", b3, world, j3.sharded, global_batch=b3 * m3 * world, micro=m3),
+                       "config": workload_config("c3", "bf16", b3, world, j3.sharded, global_batch=b3 * m3 * world, micro=m3, dynamic=False),
                        "gpu_launches": r3["gpu_launches"]}
                 if "e2e" in r3:
                     blk["e2e"] = r3["e2e"]
@@ -756,7 +771,8 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
         "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
-        "config": workload_config(args.config, precision, B, world, sharded, global_batch=B * micro * world, micro=micro),
+        "config": workload_config(args.config, precision, B, world, sharded, global_batch=B * micro * world, micro=micro,
+                                  dynamic=(precision == "fp32" and not args.static_tiles)),
         "clocks": res["clocks"], "e2e": res.get("e2e"),
         "gpu_launches": res["gpu_launches"], "gpu_launches_per_step": res["gpu_launches_per_step"], "roofline": res.get("roofline"),
         "parity_check": parity,

@@ -48,6 +48,11 @@ void pvb200_reset_launch_count(void);
  * one CTA per SM then wait for the displaced CTAs.  pvb200_reserve_sms(n) makes every persistent kernel launched
  * afterwards size its grid for (SM count - n) SMs (n = 0: default).  Returns the previous value. */
 int pvb200_reserve_sms(int n);
+/* The other answer to the same problem: persistent kernels that support it (the fp32-mode weight gradient) stop splitting
+ * their work statically over the CTAs and claim it in chunks from an atomic counter, so that CTAs displaced by NCCL's kernels
+ * cost a chunk, not a grid tail.  Off by default (on one GPU the static split is perfectly balanced; chunks cost a few per
+ * cent of tail); predict_pv_yield_b200/dp.py switches it on when the world size is > 1.  Returns the previous setting. */
+int pvb200_set_dynamic_tiles(int on);
 int pvb200_sm_count(void);
 /* diagnostic: launch an FP32 FMA saturation kernel; *flops_out = FLOPs it performs.  bench.py times it
  * with CUDA events to get the FP32-FMA roofline denominator (not in MEASURED_PEAKS.json). */

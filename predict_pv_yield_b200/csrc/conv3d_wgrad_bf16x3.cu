@@ -59,6 +59,7 @@ struct W3Args {
   int plane_off;    // input plane of output t, tap kt: t + kt + plane_off
   long long steps;  // B * Ti * Ho
   int dbg_flags;    // tools only: 1 = no bulk copies, 2 = no split arithmetic, 4 = no MMAs, 8 = no drain traffic
+  int* sched;       // dynamic step ranges: global counter of claimed chunks (zeroed before the launch), or null = static split
   const float* amax_x;  // two-way fp16 split only: max |x| and max |gz| of the two tensors (device scalars)
   const float* amax_g;
 };
@@ -184,9 +185,56 @@ __device__ __forceinline__ void w3_next(W3Step& r, const W3Args& a) {
   }
 }
 
-// smem layout (bytes): [0,256) barriers | [256,384) a zero core matrix | piece buffers: stage s = A pieces 0..NP-1 (a_piece
+// smem layout (bytes): [0,256) barriers | [256,384) the ring of step ranges | [384,512) a zero core matrix | piece buffers: stage s = A pieces 0..NP-1 (a_piece
 // bytes each), for s = 0,1, then stage s = B pieces (b_piece bytes each) | raw fp32 staging: RB x A rows, RB x B rows (the
 // two-way split leaves room for a second raw buffer: the loads of step s+1 fly while step s is converted)
+// ---- step ranges of a CTA -------------------------------------------------------------------------------------------------
+// Static: one contiguous range per CTA (steps * cta / grid).  Dynamic (a.sched != null; switched on under data parallelism,
+// pvb200_set_dynamic_tiles): chunks of kW3Chunk steps claimed with an atomic counter -- when NCCL's kernels occupy some SMs
+// while this persistent grid is launched, the displaced CTAs start late (or never): with the static split the whole kernel
+// then waits for their ranges (a grid tail, +26 % measured on two GPUs), with chunks the resident CTAs simply take more.
+// The producer warp claims a range and publishes it through a small shared-memory ring; the other roles read the same
+// sequence.  A chunk is a whole number of flush windows, so windows never straddle ranges.
+constexpr int kW3Ring = 4;
+constexpr int kW3Chunk = kW3Flush;  // steps per claimed chunk
+struct W3Ranges {
+  long long* lo;     // [kW3Ring]
+  long long* hi;     // [kW3Ring]   lo >= hi: no more work
+  uint64_t* full;    // [kW3Ring]   range published (1 arrival)
+  uint64_t* empty;   // [kW3Ring]   range read by every consumer warp
+};
+// producer warp (all lanes): claim and publish range number ci
+__device__ __forceinline__ void w3_publish_range(const W3Ranges& r, uint32_t ci, const W3Args& a, long long& lo, long long& hi) {
+  const uint32_t slot = ci % kW3Ring;
+  if ((threadIdx.x & 31) == 0) {
+    tc::mbar_wait(r.empty + slot, ((ci / kW3Ring) & 1u) ^ 1u);
+    if (a.sched) {
+      const long long id = atomicAdd(a.sched, 1);
+      lo = id * kW3Chunk;
+      hi = lo + kW3Chunk < a.steps ? lo + kW3Chunk : a.steps;
+    } else if (ci == 0) {
+      lo = a.steps * blockIdx.x / gridDim.x;
+      hi = a.steps * (blockIdx.x + 1) / gridDim.x;
+    } else {
+      lo = hi = a.steps;
+    }
+    r.lo[slot] = lo;
+    r.hi[slot] = hi;
+    tc::mbar_arrive(r.full + slot);  // release: the range is visible to the warps that acquire the barrier
+  }
+  lo = __shfl_sync(0xffffffffu, lo, 0);
+  hi = __shfl_sync(0xffffffffu, hi, 0);
+}
+// consumer warps (all lanes)
+__device__ __forceinline__ void w3_next_range(const W3Ranges& r, uint32_t ci, long long& lo, long long& hi) {
+  const uint32_t slot = ci % kW3Ring;
+  tc::mbar_wait(r.full + slot, (ci / kW3Ring) & 1u);
+  lo = r.lo[slot];
+  hi = r.hi[slot];
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) tc::mbar_arrive(r.empty + slot);
+}
+
 // NP = 3: three-way bf16 split (six products); NP = 2: two-way fp16 split of the scaled operands (three products)
 template <int NP>
 __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(const W3Args a, const __grid_constant__ CUtensorMap tm_x,
@@ -199,7 +247,10 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
   uint64_t* empty = ready + kW3Stages;                      // [2] pieces consumed
   uint64_t* afull = empty + kW3Stages;                      // [3] accumulator kw complete (flush window closed)
   uint64_t* aempty = afull + 3;                             // [3] accumulator kw drained
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty + 3);
+  uint64_t* rfull = aempty + 3;                             // [4] step range published
+  uint64_t* rempty = rfull + kW3Ring;                       // [4] step range read by the consumer warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rempty + kW3Ring);
+  const W3Ranges ranges = {reinterpret_cast<long long*>(smem + 256), reinterpret_cast<long long*>(smem + 256) + kW3Ring, rfull, rempty};
   const int G = a.G, G8 = a.G / 2, Wi = a.Wi, WP = a.WP, CoP = a.CoP;
   const int GP8 = CoP / 8;                                                   // gradient groups of 8 per time tap in the pieces
   const uint32_t a_piece = ((static_cast<uint32_t>(3 * G8 + 4) * Wi * 16u) + 127u) & ~127u;  // staged rows + ones rows + slack
@@ -208,7 +259,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
   const uint32_t a_raw_span = (a_raw_bytes + 127u) & ~127u;
   const uint32_t b_raw_bytes = static_cast<uint32_t>(a.GOr * 3 * a.Wo) * 16u;  // box [GOr][3 planes][Wo] of gz
   const uint32_t b_raw_span = (b_raw_bytes + 127u) & ~127u;
-  uint8_t* a_s = smem + 384;                          // [stage][piece]
+  uint8_t* a_s = smem + 512;                          // [stage][piece]
   uint8_t* b_s = a_s + kW3Stages * NP * a_piece;      // [stage][piece]
   uint8_t* a_raw = b_s + kW3Stages * NP * b_piece;
   uint8_t* b_raw = a_raw + RB * a_raw_span;
@@ -217,7 +268,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
   // zero everything once: padding positions / groups, the slack rows and the zero core matrix stay zero for the whole kernel
   {
     const uint32_t total16 = (128u + kW3Stages * NP * (a_piece + b_piece) + RB * (a_raw_span + b_raw_span)) >> 4;
-    uint4* z = reinterpret_cast<uint4*>(smem + 256);
+    uint4* z = reinterpret_cast<uint4*>(smem + 384);
     for (uint32_t i = threadIdx.x; i < total16; i += kW3Threads) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
@@ -231,6 +282,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     for (int i = 0; i < 2 * static_cast<int>(RB); ++i) { tc::mbar_init(raw_full + i, 1); tc::mbar_init(raw_empty + i, kW3SplitWarps); }
     for (int i = 0; i < kW3Stages; ++i) { tc::mbar_init(ready + i, kW3SplitWarps); tc::mbar_init(empty + i, 1); }
     for (int i = 0; i < 3; ++i) { tc::mbar_init(afull + i, 1); tc::mbar_init(aempty + i, 4); }
+    for (int i = 0; i < kW3Ring; ++i) { tc::mbar_init(rfull + i, 1); tc::mbar_init(rempty + i, kW3Threads / 32 - 1); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
@@ -240,11 +292,13 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const long long s_begin = a.steps * blockIdx.x / gridDim.x;
-  const long long s_end = a.steps * (blockIdx.x + 1) / gridDim.x;
+  long long s_begin = 0, s_end = 0;
   if (warp == 0) {
     // =============================== producer ===============================
     uint32_t seq = 0;
+    for (uint32_t ci = 0;; ++ci) {
+    w3_publish_range(ranges, ci, a, s_begin, s_end);
+    if (s_begin >= s_end) break;
     W3Step st = w3_step(s_begin, a);
     for (long long s = s_begin; s < s_end; ++s, ++seq, w3_next(st, a)) {
       // two tiled TMA loads per step (tensor maps, SASS UTMALDG) instead of 32 small bulk copies: the three input rows
@@ -272,6 +326,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       }
       __syncwarp();
     }
+    }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     const bool leader = tc::elect_one();
@@ -285,11 +340,14 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     const uint32_t idesc0 = tc::umma_idesc(128, 0, /*BF16 : F16*/ NP == 3 ? 1 : 0, /*A MN-major*/ 1, /*B MN-major*/ 1);
     const uint32_t idesc_blk = static_cast<uint32_t>(CoP >> 3) << 17;
     // B operand of the MMA that opens a flush window: every N group reads the same all-zero core matrices (SBO = 0)
-    const uint32_t zero_lo = ((tc::smem_u32(smem + 256) >> 4) & 0x3fffu);  // LBO = 0 as well: both K groups read it
+    const uint32_t zero_lo = ((tc::smem_u32(smem + 384) >> 4) & 0x3fffu);  // LBO = 0 as well: both K groups read it
     const uint32_t zero_hi = (1u << 14);
     const int k16n = WP >> 4;
     uint32_t seq = 0;
     uint32_t nwin = 0;  // flush windows closed so far (phase of the accumulator barriers)
+    for (uint32_t ci = 0;; ++ci) {
+    w3_next_range(ranges, ci, s_begin, s_end);
+    if (s_begin >= s_end) break;
     W3Step st = w3_step(s_begin, a);
     for (long long s = s_begin; s < s_end; ++s, ++seq, w3_next(st, a)) {
       const uint32_t stage = seq % kW3Stages;
@@ -335,6 +393,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
       if (win_last) ++nwin;
       __syncwarp();
     }
+    }
   } else if (warp < 2 + kW3SplitWarps) {
     // =============================== split warps: fp32 rows -> three bf16 pieces in the operand layout ==============
     const int tid = threadIdx.x - 64;
@@ -346,6 +405,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     const float sx = NP == 2 ? w3_exp2i(w3_scale_exp(__ldg(a.amax_x))) : 1.f;
     const float sg = NP == 2 ? w3_exp2i(w3_scale_exp(__ldg(a.amax_g))) : 1.f;
     uint32_t seq = 0;
+    for (uint32_t ci = 0;; ++ci) {
+    w3_next_range(ranges, ci, s_begin, s_end);
+    if (s_begin >= s_end) break;
     W3Step st = w3_step(s_begin, a);
     for (long long s = s_begin; s < s_end; ++s, ++seq, w3_next(st, a)) {
       const uint32_t stage = seq % kW3Stages;
@@ -438,6 +500,7 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
         tc::mbar_arrive(raw_empty + RB + rb);  // the gradient rows have been read
       }
     }
+    }
   } else {
     // =============================== accumulator drain (warps 10..13, one per TMEM lane quadrant) ===============================
     // per window and accumulator: tcgen05.ld, the accumulator goes back to the MMA warp at once, and the window's sums are
@@ -446,36 +509,36 @@ __global__ void __launch_bounds__(kW3Threads, 1) conv3d_wgrad_bf16x3_kernel(cons
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-    const long long nsteps = s_end - s_begin;
-    const long long nwin_total = (nsteps + kW3Flush - 1) / kW3Flush;
     float* mine = a.partial + static_cast<size_t>(blockIdx.x) * 3 * 128 * kW3AccCols + row;  // [kw][column][row]
     // the partials (22 MB over the grid) are touched every window while ~100 MB of operands stream through L2 in between:
     // without a retention hint they were evicted and every update went to DRAM
     uint64_t keep;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-    for (long long wdx = 0; wdx < nwin_total; ++wdx) {
+    // every thread zeroes exactly the elements it later adds to (a CTA that never gets a range still owes the reduce zeros)
 #pragma unroll 1
-      for (int kw = 0; kw < 3; ++kw) {
-        tc::mbar_wait(afull + kw, static_cast<uint32_t>(wdx & 1));
-        tc::tc_fence_after();
-        uint32_t v[3][32];
-        if (!(a.dbg_flags & 8)) {
+    for (int c = 0; c < 3 * kW3AccCols; ++c) w3_st_keep(mine + static_cast<size_t>(c) * 128, 0.f, keep);
+    long long wdx = 0;
+    for (uint32_t ci = 0;; ++ci) {
+      w3_next_range(ranges, ci, s_begin, s_end);
+      if (s_begin >= s_end) break;
+      const long long nwin_range = (s_end - s_begin + kW3Flush - 1) / kW3Flush;
+      for (long long wr = 0; wr < nwin_range; ++wr, ++wdx) {
+#pragma unroll 1
+        for (int kw = 0; kw < 3; ++kw) {
+          tc::mbar_wait(afull + kw, static_cast<uint32_t>(wdx & 1));
+          tc::tc_fence_after();
+          uint32_t v[3][32];
+          if (!(a.dbg_flags & 8)) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) tc::tmem_ld_32x32(lane_addr + static_cast<uint32_t>(kw * kW3AccCols + c * 32), v[c]);
-          tc::tmem_ld_wait();
-        }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(aempty + kw);
-        if (a.dbg_flags & (8 | 16)) continue;  // 16: accumulators read and released, no partial traffic
-        // partial layout [kw][column][row]: a warp's 32 rows of one column are 128 contiguous bytes
-        float* dst = mine + static_cast<size_t>(kw) * 128 * kW3AccCols;
-        if (wdx == 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) w3_st_keep(dst + static_cast<size_t>(c * 32 + j) * 128, __uint_as_float(v[c][j]), keep);
-        } else {
+            for (int c = 0; c < 3; ++c) tc::tmem_ld_32x32(lane_addr + static_cast<uint32_t>(kw * kW3AccCols + c * 32), v[c]);
+            tc::tmem_ld_wait();
+          }
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(aempty + kw);
+          if (a.dbg_flags & (8 | 16)) continue;  // 16: accumulators read and released, no partial traffic
+          // partial layout [kw][column][row]: a warp's 32 rows of one column are 128 contiguous bytes
+          float* dst = mine + static_cast<size_t>(kw) * 128 * kW3AccCols;
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -519,6 +582,7 @@ __global__ void wgrad_bf16x3_reduce_kernel(const float* __restrict__ partial, in
 }
 
 int g_w3_dbg_flags = 0;  // set through pvb200_debug_set_wgrad_flags (tools only)
+extern int g_dynamic_tiles;  // runtime.cu: pvb200_set_dynamic_tiles
 
 // 5-D fp32 tensor map, dense (strides follow the dimensions), no swizzle / interleave, zero fill outside the tensor.  The
 // encoder is a host-only driver function, fetched through the runtime so that the library keeps linking only libcudart.
@@ -556,7 +620,7 @@ static size_t w3_smem_bytes(int G, int GOr, int Wi, int Wo, int CoP, int NP = 3)
   const size_t a_piece = round_up(static_cast<size_t>(3 * (G / 2) + 4) * Wi * 16, static_cast<size_t>(128));
   const size_t b_piece = static_cast<size_t>(3) * (CoP / 8) * WP * 16;
   const size_t RB = NP == 2 ? 2 : 1;
-  return 384 + kW3Stages * NP * (a_piece + b_piece) +
+  return 512 + kW3Stages * NP * (a_piece + b_piece) +
          RB * (round_up(static_cast<size_t>(G) * 3 * Wi * 16, static_cast<size_t>(128)) + round_up(static_cast<size_t>(3) * GOr * Wo * 16, static_cast<size_t>(128)));
 }
 
@@ -566,7 +630,7 @@ static int w3_supported(int Cin, int Cout, int Hi, int Wi, int NP) {
   // the M = 128 instruction reads 16 row groups at stride Wi*16 from the start of an A piece: it must stay inside the allocation
   const size_t smem = w3_smem_bytes(G, w3_groups(Cout), Wi, Wi - 2, w3_cop(Cout), NP);
   const size_t a_piece = round_up(static_cast<size_t>(3 * (G / 2) + 4) * Wi * 16, static_cast<size_t>(128));
-  const size_t last_a = 384 + (NP * kW3Stages - 1) * a_piece;
+  const size_t last_a = 512 + (NP * kW3Stages - 1) * a_piece;
   const size_t reach = last_a + static_cast<size_t>(16) * Wi * 16 + static_cast<size_t>(round_up(Wi, 16) + 16) * 16;
   return (smem <= 227 * 1024 && reach <= smem && Wi <= 64) ? 1 : 0;  // Wi * 4 floats = the 256-element limit of a TMA box dimension
 }
@@ -591,10 +655,15 @@ static int w3_launch(const char* who, int NP, const float* amax_x, const float* 
   const int sms = sm_count();
   PVB_REQUIRE(sms > 0, "%s: no CUDA device", who);
   long long grid = a.steps < sms ? a.steps : sms;
-  const size_t need = static_cast<size_t>(grid) * 3 * 128 * kW3AccCols * sizeof(float);
+  const size_t need = static_cast<size_t>(grid) * 3 * 128 * kW3AccCols * sizeof(float) + 64;  // partials + the chunk counter
   if (!workspace || workspace_bytes < need) {
     set_error("%s: workspace too small (%zu < %zu bytes)", who, workspace_bytes, need);
     return PVB200_ERR_WORKSPACE;
+  }
+  a.sched = nullptr;
+  if (g_dynamic_tiles) {
+    a.sched = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + need - 64);
+    PVB_CUDA(cudaMemsetAsync(a.sched, 0, sizeof(int), stream));
   }
   PVB_REQUIRE(reinterpret_cast<uintptr_t>(xb) % 16 == 0 && reinterpret_cast<uintptr_t>(gzb) % 16 == 0 &&
                   reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "%s: pointers must be 16-byte aligned", who);
@@ -656,7 +725,7 @@ int pvb200_conv3d_wgrad_bf16x3_supported(int Cin, int Cout, int Hi, int Wi) { re
 size_t pvb200_conv3d_wgrad_bf16x3_workspace_bytes(void) {
   int sms = pvb::sm_count();
   if (sms <= 0) sms = 148;
-  return static_cast<size_t>(sms) * 3 * 128 * pvb::kW3AccCols * sizeof(float);
+  return static_cast<size_t>(sms) * 3 * 128 * pvb::kW3AccCols * sizeof(float) + 64;
 }
 
 /* dw [Cout][Cin][3][3][3], db [Cout] (or null) from x blocked fp32 [B][G(Cin)][Ti][Hi][Wi][4] and the pre-activation gradient

@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...) {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static std::atomic<int> g_reserved_sms{0};
+int g_dynamic_tiles = 0;  // pvb200_set_dynamic_tiles: persistent kernels that support it claim their work in chunks
 
 // SMs the persistent kernels size their grids for: the device's SM count minus the SMs reserved for concurrently
 // running collectives (pvb200_reserve_sms).  A persistent grid of one CTA per SM with a static work split loses up to
@@ -52,6 +53,12 @@ void pvb200_reset_launch_count(void) { pvb::g_launches.store(0); }
 /* reserve `n` SMs for kernels of other libraries that run concurrently (NCCL collectives under data parallelism):
  * every persistent kernel launched afterwards uses (SM count - n) CTAs.  n = 0 restores the default.  Returns the old value. */
 int pvb200_reserve_sms(int n) { return pvb::g_reserved_sms.exchange(n < 0 ? 0 : n); }
+
+int pvb200_set_dynamic_tiles(int on) {
+  const int old = pvb::g_dynamic_tiles;
+  pvb::g_dynamic_tiles = on ? 1 : 0;
+  return old;
+}
 
 int pvb200_sm_count(void) {
   int n = pvb::sm_count();

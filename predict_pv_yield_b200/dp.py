@@ -88,7 +88,8 @@ def wait_ready(p: torch.Tensor) -> None:
 
 
 class GradientExchange:
-    def __init__(self, module: torch.nn.Module, process_group=None, large_numel: int = 1 << 22, shard_large: bool = False):
+    def __init__(self, module: torch.nn.Module, process_group=None, large_numel: int = 1 << 22, shard_large: bool = False,
+                 dynamic_tiles: bool = False):
         if not dist.is_available() or not dist.is_initialized():
             raise RuntimeError("GradientExchange needs an initialised torch.distributed process group")
         self.group = process_group
@@ -106,6 +107,13 @@ class GradientExchange:
         self._reduce_scatter_ok = dist.get_backend(process_group) == "nccl"  # gloo has no reduce-scatter
         if shard_large:
             self._sd_hook = module.register_state_dict_pre_hook(lambda *a, **k: self.gather_master_weights())
+        if dynamic_tiles and self.world_size > 1 and any(p.is_cuda for p in self.params):
+            # NCCL's kernels take SMs while the persistent convolution kernels run: the fp32-mode weight gradient then claims its
+            # work in chunks instead of splitting it statically (no grid tail behind displaced CTAs: 4.71 -> 4.53 ms per step on
+            # two GPUs).  OPT-IN: which CTA sums which chunk depends on timing, so the fp32 sums are no longer bit-reproducible
+            # from run to run (within the parity bound; `sharded == replicated` bit for bit holds with the static split only).
+            from . import lib as _lib
+            _lib.load().pvb200_set_dynamic_tiles(1)
 
     # -- hook ---------------------------------------------------------------------------------------
     def _comm(self, device: torch.device) -> torch.cuda.Stream:

@@ -130,6 +130,7 @@ SIGNATURES = {
     "pvb200_embedding_bwd_f32": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pvb200_history_flatten_f32": (c_int, [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "pvb200_reserve_sms": (c_int, [c_int]),
+    "pvb200_set_dynamic_tiles": (c_int, [c_int]),
     "pvb200_fc1_bf16_shadow_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "pvb200_fc1_make_shadow_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pvb200_adam_fc1_shadow": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -218,6 +218,32 @@ def test_conv3d_wgrad_f16x2(ops, dev, shape, scales):
     assert torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 5, 10, 10, 32), (3, 32, 21, 6, 6, 32), (37, 4, 3, 5, 5, 8), (2, 32, 7, 62, 62, 32)])
+@pytest.mark.parametrize("two_way", [True, False])
+def test_conv3d_wgrad_dynamic_chunks(ops, dev, shape, two_way):
+    """The weight gradient with its steps claimed in chunks from an atomic counter (what data parallelism switches on):
+    same result as the static split up to the order of the fp32 sums, more chunks than CTAs, and CTAs that get none."""
+    from predict_pv_yield_b200 import lib
+
+    B, Ci, T, H, W, Co = shape
+    x, w, b = _case(shape, seed=31)
+    g = torch.Generator().manual_seed(32)
+    gz = torch.randn((B, Co, T - 2, H - 2, W - 2), generator=g)
+    wd = w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    F.conv3d(x.double(), wd, bd).backward(gz.double())
+    xb, gzb = ops.to_blocked_f32(x.to(dev)), ops.to_blocked_f32(gz.to(dev), pad=2)
+    amax = _amax(ops, dev, xb, gzb) if two_way else None
+    L = lib.load()
+    old = L.pvb200_set_dynamic_tiles(1)
+    try:
+        for _ in range(3):  # the claim order differs from run to run
+            dw, db = ops.conv3d_wgrad_bf16x3(xb, gzb, Ci, Co, gz_pad=2, amax=amax)
+            assert nerr(dw, wd.grad) <= TOL and nerr(db, bd.grad) <= TOL
+    finally:
+        L.pvb200_set_dynamic_tiles(old)
+
+
 def test_conv3d_wgrad_f16x2_wide_dynamic_range(ops, dev):
     """Operands whose magnitudes span 2^40 inside one tensor: the small values lose RELATIVE precision in the fp16 split,
     the gradient (dominated by the large ones) stays within the fp32 bound; an all-zero gradient gives exact zeros."""

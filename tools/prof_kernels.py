@@ -39,6 +39,7 @@ for rep in range(2):  # the second pass is the one to capture (ncu -s <launches 
         ops.conv3d_fwd_bf16(xb, w, b)
         ops.conv3d_dgrad_bf16(gzp, w, xb)
         ops.conv3d_wgrad_bf16(xb, gzw, Ci, Co)
+        ops.conv3d_wgrad_bf16_rows(xb, gzp, Ci, Co, gz_pad=2)  # round 2: row-step weight gradient (what the encoder runs)
         # fc1 (last activation 32 x 11 x 56 x 56) and the fused Adam + shadow pass
         Cg, Tf, Hf, Wf, F1 = 4, 11, 56, 56, 128
         K1 = Cg * 8 * Tf * Hf * Wf

@@ -36,6 +36,18 @@ for (B, Ci, T, H, W, Co) in [(32, 32, 17, 62, 62, 32), (32, 12, 19, 64, 64, 32)]
             ms = e0.elapsed_time(e1) / 5
             print(f"Ci={Ci:2d} {variant} {name:22s} {ms:7.3f} ms  = {ms * 1e-3 * 1.965e9 * 148 / steps:7.0f} clk per step")
         L.pvb200_debug_set_wgrad_flags(0)
+    for dyn in (0, 1):
+        L.pvb200_set_dynamic_tiles(dyn)
+        for _ in range(2):
+            ops.conv3d_wgrad_bf16x3(xb, gzb, Ci, Co, gz_pad=2, amax=(amax[0:1], amax[1:2]))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.conv3d_wgrad_bf16x3(xb, gzb, Ci, Co, gz_pad=2, amax=(amax[0:1], amax[1:2]))
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"Ci={Ci:2d} f16x2 {'dynamic chunks' if dyn else 'static split'}: {e0.elapsed_time(e1) / 5:.3f} ms")
+    L.pvb200_set_dynamic_tiles(0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
