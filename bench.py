@@ -749,7 +749,7 @@ def run_ours(args):
             r3 = measure_train(torch, dist, j3, args, args.steps, args.warmup, tag == "weak" and not args.no_e2e, tag == "weak")
             if rank == 0:
                 blk = {"value": r3["value"], "unit": UNIT, "ms_per_step": r3["ms_per_step"], "scaling": tag,
-                       "config": workload_config("c3", "bf16", b3, world, j3.sharded, global_batch=b3 * m3 * world, micro=m3, dynamic=False),
+                       "config": workload_config("c3", "bf16", b3, world, j3.sharded, global_batch=b3 * m3 * world, micro=m3, dynamic=not args.static_tiles),
                        "gpu_launches": r3["gpu_launches"]}
                 if "e2e" in r3:
                     blk["e2e"] = r3["e2e"]
@@ -772,7 +772,7 @@ def run_ours(args):
         "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
         "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
         "config": workload_config(args.config, precision, B, world, sharded, global_batch=B * micro * world, micro=micro,
-                                  dynamic=(precision == "fp32" and not args.static_tiles)),
+                                  dynamic=not args.static_tiles),
         "clocks": res["clocks"], "e2e": res.get("e2e"),
         "gpu_launches": res["gpu_launches"], "gpu_launches_per_step": res["gpu_launches_per_step"], "roofline": res.get("roofline"),
         "parity_check": parity,

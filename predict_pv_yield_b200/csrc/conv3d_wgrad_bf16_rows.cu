@@ -30,13 +30,21 @@ namespace pvb {
 constexpr int kWrThreads = 192;
 constexpr int kWrMaxStages = 6;
 constexpr int kWrAccCols = 96;
+extern int g_dynamic_tiles;  // runtime.cu: pvb200_set_dynamic_tiles
 
 struct WrArgs {
   float* partial;  // [grid][3 kw][96 columns][128 rows]
   int B, Cg, CgO, Ti, Hi, Wi, To, Ho, Wo, WP;
   int plane_off, gz_pad, nstage;
   long long steps;  // B * Ti * Ho
+  int* sched;       // dynamic step ranges: global counter of claimed chunks (zeroed before the launch), or null = static split
 };
+
+constexpr int kWrRowBlock = 6;  // step order inside a sample: blocks of 6 output rows x all input planes x the rows of the block --
+                                // a gradient plane is re-read by the steps of the next two input planes 12 steps later (L2 hits),
+                                // not a whole plane of rows later (see conv3d_wgrad_bf16x3.cu, w3_step)
+constexpr int kWrChunk = 16;    // steps per chunk of the dynamic split (pvb200_set_dynamic_tiles)
+constexpr int kWrRing = 4;
 
 __device__ __forceinline__ void wr_tma_5d(void* dst_smem, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
   asm volatile(
@@ -46,20 +54,26 @@ __device__ __forceinline__ void wr_tma_5d(void* dst_smem, const CUtensorMap* tm,
       : "memory");
 }
 
-// smem: [0,128) barriers | stage s: A (a_bytes: box + ones rows + slack) then B (b_bytes)
+// smem: [0,256) barriers and the ring of step ranges | stage s: A (a_bytes: box + ones rows + slack) then B (b_bytes)
 __global__ void __launch_bounds__(kWrThreads, 1) conv3d_wgrad_bf16_rows_kernel(const WrArgs a, const __grid_constant__ CUtensorMap tm_x,
                                                                                const __grid_constant__ CUtensorMap tm_gz) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [6] operands landed
   uint64_t* empty = full + kWrMaxStages;                // [6] operands consumed
   uint64_t* done = empty + kWrMaxStages;                // [1] all MMAs complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* rfull = done + 1;                           // [4] step range published by the producer
+  uint64_t* rempty = rfull + kWrRing;                   // [4] step range read by the MMA warp
+  uint64_t* flagbar = rempty + kWrRing;                 // [1] `any` flag written
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(flagbar + 1);
+  volatile int* any_s = reinterpret_cast<volatile int*>(tmem_ptr + 1);  // did this CTA process a step?
+  long long* r_lo = reinterpret_cast<long long*>(smem + 192);            // [4]
+  long long* r_hi = r_lo + kWrRing;                                      // [4]  (lo >= hi: no more work)
   const int Cg = a.Cg, Wi = a.Wi, WP = a.WP;
   const uint32_t a_box = static_cast<uint32_t>(3 * Cg * Wi) * 16u;
   const uint32_t a_bytes = ((static_cast<uint32_t>(3 * Cg + 4) * Wi * 16u) + 127u) & ~127u;
   const uint32_t b_bytes = static_cast<uint32_t>(3 * a.CgO * WP) * 16u;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 127u) & ~127u);
-  uint8_t* st_s = smem + 128;
+  uint8_t* st_s = smem + 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t nstage = static_cast<uint32_t>(a.nstage);
 
@@ -77,6 +91,8 @@ __global__ void __launch_bounds__(kWrThreads, 1) conv3d_wgrad_bf16_rows_kernel(c
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWrMaxStages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
     tc::mbar_init(done, 1);
+    tc::mbar_init(flagbar, 1);
+    for (int i = 0; i < kWrRing; ++i) { tc::mbar_init(rfull + i, 1); tc::mbar_init(rempty + i, 1); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
@@ -86,24 +102,56 @@ __global__ void __launch_bounds__(kWrThreads, 1) conv3d_wgrad_bf16_rows_kernel(c
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const long long s_begin = a.steps * blockIdx.x / gridDim.x;
-  const long long s_end = a.steps * (blockIdx.x + 1) / gridDim.x;
-
   if (warp == 0) {
-    // =============================== producer ===============================
+    // =============================== producer: claims the step ranges and fills the stages ===============================
     if (lane == 0) {
-      int h = static_cast<int>(s_begin % a.Ho);
-      const long long bp = s_begin / a.Ho;
-      int p = static_cast<int>(bp % a.Ti), b = static_cast<int>(bp / a.Ti);
       uint32_t seq = 0;
-      for (long long s = s_begin; s < s_end; ++s, ++seq) {
-        const uint32_t stage = seq % nstage;
-        tc::mbar_wait(empty + stage, ((seq / nstage) & 1u) ^ 1u);
-        uint8_t* dst = st_s + stage * stage_bytes;
-        tc::mbar_arrive_expect_tx(full + stage, a_box + b_bytes);
-        wr_tma_5d(dst, &tm_x, 0, h, p, 0, b, full + stage);
-        wr_tma_5d(dst + a_bytes, &tm_gz, 0, h, p - a.plane_off - 2, 0, b, full + stage);
-        if (++h == a.Ho) { h = 0; if (++p == a.Ti) { p = 0; ++b; } }
+      for (uint32_t ci = 0;; ++ci) {
+        // static split: one contiguous range per CTA; dynamic: chunks of kWrChunk steps from an atomic counter, so that CTAs
+        // displaced by NCCL's kernels under data parallelism cost a chunk, not a grid tail
+        const uint32_t slot = ci % kWrRing;
+        tc::mbar_wait(rempty + slot, ((ci / kWrRing) & 1u) ^ 1u);
+        long long s_begin, s_end;
+        if (a.sched) {
+          s_begin = static_cast<long long>(atomicAdd(a.sched, 1)) * kWrChunk;
+          s_end = s_begin + kWrChunk < a.steps ? s_begin + kWrChunk : a.steps;
+        } else if (ci == 0) {
+          s_begin = a.steps * blockIdx.x / gridDim.x;
+          s_end = a.steps * (blockIdx.x + 1) / gridDim.x;
+        } else {
+          s_begin = s_end = a.steps;
+        }
+        r_lo[slot] = s_begin;
+        r_hi[slot] = s_end;
+        tc::mbar_arrive(rfull + slot);
+        if (s_begin >= s_end) break;
+        // decode (b, row block, p, row) once per range, then advance incrementally
+        const long long per_b = static_cast<long long>(a.Ti) * a.Ho;
+        int b = static_cast<int>(s_begin / per_b);
+        const int rs = static_cast<int>(s_begin - b * per_b);
+        const int k = rs / (kWrRowBlock * a.Ti);  // every block before the last one is full
+        int h0 = k * kWrRowBlock;
+        int hb = a.Ho - h0 < kWrRowBlock ? a.Ho - h0 : kWrRowBlock;
+        const int q = rs - k * kWrRowBlock * a.Ti;
+        int p = q / hb, h = h0 + q % hb;
+        for (long long s = s_begin; s < s_end; ++s, ++seq) {
+          const uint32_t stage = seq % nstage;
+          tc::mbar_wait(empty + stage, ((seq / nstage) & 1u) ^ 1u);
+          uint8_t* dst = st_s + stage * stage_bytes;
+          tc::mbar_arrive_expect_tx(full + stage, a_box + b_bytes);
+          wr_tma_5d(dst, &tm_x, 0, h, p, 0, b, full + stage);
+          wr_tma_5d(dst + a_bytes, &tm_gz, 0, h, p - a.plane_off - 2, 0, b, full + stage);
+          if (++h == h0 + hb) {
+            h = h0;
+            if (++p == a.Ti) {
+              p = 0;
+              h0 += hb;
+              if (h0 >= a.Ho) { h0 = 0; ++b; }
+              hb = a.Ho - h0 < kWrRowBlock ? a.Ho - h0 : kWrRowBlock;
+              h = h0;
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -116,6 +164,13 @@ __global__ void __launch_bounds__(kWrThreads, 1) conv3d_wgrad_bf16_rows_kernel(c
     const uint32_t idesc = tc::umma_idesc(128, 3 * a.CgO * 8, /*BF16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1);
     const int k16n = WP >> 4;
     uint32_t seq = 0;
+    for (uint32_t ci = 0;; ++ci) {
+    const uint32_t slot = ci % kWrRing;
+    tc::mbar_wait(rfull + slot, (ci / kWrRing) & 1u);
+    const long long s_begin = r_lo[slot], s_end = r_hi[slot];
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(rempty + slot);
+    if (s_begin >= s_end) break;
     for (long long s = s_begin; s < s_end; ++s, ++seq) {
       const uint32_t stage = seq % nstage;
       tc::mbar_wait(full + stage, (seq / nstage) & 1u);
@@ -137,6 +192,12 @@ __global__ void __launch_bounds__(kWrThreads, 1) conv3d_wgrad_bf16_rows_kernel(c
       }
       __syncwarp();
     }
+    }
+    if (lane == 0) {
+      *any_s = seq > 0 ? 1 : 0;
+      __threadfence_block();
+      tc::mbar_arrive(flagbar);
+    }
     if (leader) tc::umma_commit(done);
     __syncwarp();
   } else {
@@ -144,9 +205,10 @@ __global__ void __launch_bounds__(kWrThreads, 1) conv3d_wgrad_bf16_rows_kernel(c
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     tc::mbar_wait(done, 0);
+    tc::mbar_wait(flagbar, 0);
     tc::tc_fence_after();
     float* mine = a.partial + static_cast<size_t>(blockIdx.x) * 3 * 128 * kWrAccCols + row;  // [kw][column][row]
-    const bool any = s_end > s_begin;
+    const bool any = *any_s != 0;
     for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll 1
       for (int c0 = 0; c0 < kWrAccCols; c0 += 32) {
@@ -235,13 +297,13 @@ int pvb200_conv3d_wgrad_bf16_rows_supported(int Cin, int Cout, int Hi, int Wi) {
   const int Cg = wr_cg(Cin);
   // the M = 128 instruction reads 16 row groups at stride Wi * 16 B from the start of a stage: stay inside the allocation
   const size_t stage = wr_stage_bytes(Cg, wr_cg(Cout), Wi, Wi - 2);
-  return (2 * stage + 128 <= 227 * 1024 && static_cast<size_t>(16) * Wi * 16 + (round_up(Wi, 16) + 16) * 16 <= 2 * stage) ? 1 : 0;
+  return (2 * stage + 256 <= 227 * 1024 && static_cast<size_t>(16) * Wi * 16 + (round_up(Wi, 16) + 16) * 16 <= 2 * stage) ? 1 : 0;
 }
 
 size_t pvb200_conv3d_wgrad_bf16_rows_workspace_bytes(void) {
   int sms = pvb::sm_count();
   if (sms <= 0) sms = 148;
-  return static_cast<size_t>(sms) * 3 * 128 * pvb::kWrAccCols * sizeof(float);
+  return static_cast<size_t>(sms) * 3 * 128 * pvb::kWrAccCols * sizeof(float) + 64;
 }
 
 /* dw [Cout][Cin][3][3][3], db [Cout] (or null), fp32, from x blocked bf16 [B][Cg(Cin)][Ti][Hi][Wi][8] and the pre-activation
@@ -263,19 +325,24 @@ int pvb200_conv3d_wgrad_bf16_rows(const uint16_t* xb, const uint16_t* gzb, int g
   const int sms = sm_count();
   PVB_REQUIRE(sms > 0, "conv3d_wgrad_bf16_rows: no CUDA device");
   long long grid = a.steps < sms ? a.steps : sms;
-  const size_t need = static_cast<size_t>(grid) * 3 * 128 * kWrAccCols * sizeof(float);
+  const size_t need = static_cast<size_t>(grid) * 3 * 128 * kWrAccCols * sizeof(float) + 64;  // partials + the chunk counter
   if (!workspace || workspace_bytes < need) {
     set_error("conv3d_wgrad_bf16_rows: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     return PVB200_ERR_WORKSPACE;
+  }
+  a.sched = nullptr;
+  if (g_dynamic_tiles) {
+    a.sched = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + need - 64);
+    PVB_CUDA(cudaMemsetAsync(a.sched, 0, sizeof(int), as_stream(stream)));
   }
   PVB_REQUIRE(reinterpret_cast<uintptr_t>(xb) % 16 == 0 && reinterpret_cast<uintptr_t>(gzb) % 16 == 0 &&
                   reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "conv3d_wgrad_bf16_rows: pointers must be 16-byte aligned");
   a.partial = static_cast<float*>(workspace);
   const size_t stage = wr_stage_bytes(a.Cg, a.CgO, Wi, a.Wo);
-  long long nstage = (227 * 1024 - 128) / static_cast<long long>(stage);
+  long long nstage = (227 * 1024 - 256) / static_cast<long long>(stage);
   if (nstage > kWrMaxStages) nstage = kWrMaxStages;
   a.nstage = static_cast<int>(nstage);
-  const size_t smem = 128 + nstage * stage;
+  const size_t smem = 256 + nstage * stage;
   CUtensorMap tm_x, tm_gz;
   {
     // x: [B][Cg][Ti][Hi][Wi] 16-byte elements = Wi * 4 words per row; box [1][Cg][1][3][Wi * 4]

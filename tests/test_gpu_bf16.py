@@ -154,6 +154,30 @@ def test_conv3d_wgrad_bf16_rows(ops, dev, shape, gz_pad):
     assert torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 5, 10, 10, 32), (3, 32, 21, 6, 6, 16), (37, 16, 3, 5, 5, 32), (2, 32, 7, 62, 62, 32)])
+def test_conv3d_wgrad_bf16_rows_dynamic_chunks(ops, dev, shape):
+    """The same kernel with its steps claimed in chunks from an atomic counter (pvb200_set_dynamic_tiles, the data-parallel
+    setting): more chunks than CTAs, CTAs that get none, same result up to the order of the fp32 sums."""
+    from predict_pv_yield_b200 import lib
+
+    B, Ci, T, H, W, Co = shape
+    g = torch.Generator().manual_seed(5)
+    x = r16(torch.randn((B, Ci, T, H, W), generator=g))
+    gz = r16(torch.randn((B, Co, T - 2, H - 2, W - 2), generator=g))
+    wd = torch.zeros((Co, Ci, 3, 3, 3), dtype=torch.float64, requires_grad=True)
+    bd = torch.zeros((Co,), dtype=torch.float64, requires_grad=True)
+    F.conv3d(x.double(), wd, bd).backward(gz.double())
+    xb, gzb = ops.to_blocked_bf16(x.to(dev)), ops.to_blocked_bf16(gz.to(dev), pad=2)
+    L = lib.load()
+    old = L.pvb200_set_dynamic_tiles(1)
+    try:
+        for _ in range(3):
+            dw, db = ops.conv3d_wgrad_bf16_rows(xb, gzb, Ci, Co, gz_pad=2)
+            assert O.normalised_max_err(dw, wd.grad) <= 1e-4 and O.normalised_max_err(db, bd.grad) <= 1e-4
+    finally:
+        L.pvb200_set_dynamic_tiles(old)
+
+
 def test_conv3d_wgrad_bf16_rows_time_padded(ops, dev):
     B, Ci, T, H, W, Co = 2, 32, 5, 10, 10, 32
     g = torch.Generator().manual_seed(8)
