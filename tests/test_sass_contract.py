@@ -107,3 +107,19 @@ def test_fp32_mode_tensor_core_kernels(sass):
         assert _count(ops, "UTCHMMA") >= 4 * (6 if pieces == 3 else 3) and _count(ops, "UTMALDG") == 2 and _count(ops, "LDTM") >= 3, wgrad
         assert sum(1 for o in ops if o.startswith("F2FP")) >= 8 * pieces, "packed bf16 / fp16 conversion of the split warps"
         assert _count(ops, "F2F") == 0, "scalar F2F (quarter-rate pipe) in the split loop"
+
+
+def test_fc1_tensor_core_and_row_step_kernels(sass):
+    """fc1 of the fp32 head (three-way bf16 split): tcgen05 MMAs fed by tensor-map loads, the backward kernels leave through
+    tensor-map STORES (UTMASTG) -- 4-byte register stores to rows 4.4 MB apart ran at a third of the speed; the bf16 row-step
+    weight gradient: two tensor-map loads per step straight into the operand layout, no conversion instructions."""
+    for name, stores in (("fc1x3_fwd_kernel", 0), ("fc1x3_dgrad_kernel", 1), ("fc1x3_wgrad_kernel", 1)):
+        (k,) = _find(sass, name)
+        ops = sass[k]
+        assert _count(ops, "UTCHMMA") >= 12 and _count(ops, "LDTM") >= 1, k
+        assert _count(ops, "UTMALDG") >= 1 and _count(ops, "UTMASTG") == stores, k  # (unrolled loops repeat the load)
+        assert sum(1 for o in ops if o.startswith("F2FP")) >= 12 and _count(ops, "F2F") == 0, k
+    (k,) = _find(sass, "conv3d_wgrad_bf16_rows_kernel")
+    ops = sass[k]
+    assert _count(ops, "UTCHMMA") >= 12 and _count(ops, "UTMALDG") == 2 and _count(ops, "LDTM") >= 1, k
+    assert sum(1 for o in ops if o.startswith("F2FP")) == 0, k
