@@ -100,6 +100,20 @@ __device__ __forceinline__ void t3_split8h(const float4 lo4, const float4 hi4, f
   t3_split2h(hi4.z * s, hi4.w * s, q0.w, q1.w);
 }
 
+// the same for a whole block of 256 threads that ALL call it (layout / normalise kernels: one atomic per block, not per warp)
+__device__ __forceinline__ void t3_publish_amax_block(unsigned* out, float am) {
+  __shared__ unsigned red[8];
+  const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(am));  // non-negative floats order like their bit patterns
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned r = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r = r > red[i] ? r : red[i];
+    if (r) atomicMax(out, r);
+  }
+}
+
 // weights fp32 [Co][Ci][27] -> fp16 pieces [rank][piece][(kh,kw)][ks16][kg][48 columns of the N = 96 = (kt, co) operand][8 ci],
 // scaled by the power of two of max |w| -- which every block computes for itself (27 K values) and block 0 leaves at
 // `amax_w` for the main kernel's epilogue
@@ -863,30 +877,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT3Threads, 1) conv3
 
 // ---- layout kernels ------------------------------------------------------------------------------------------
 // [B][C][T][H][W] fp32 -> blocked fp32 [B][G][T+2p][H+2p][W+2p][4] interior (channels >= C are zero)
-__global__ void nc_to_blocked_f32_kernel(const float* __restrict__ x, float4* __restrict__ y, int C, int G, int T, int H, int W,
-                                         int pad, long long total, unsigned* __restrict__ amax_out) {
+// grid: x = chunks of 256 positions of a plane, y = (sample, channel group); a thread walks the time planes of its position:
+// one 32-bit division per thread (the grid-stride form over the flat index paid three 64-bit divisions per element), one
+// atomicMax per warp
+__global__ void __launch_bounds__(256) nc_to_blocked_f32_kernel(const float* __restrict__ x, float4* __restrict__ y, int C, int G, int T,
+                                                                int H, int W, int pad, unsigned* __restrict__ amax_out) {
   float am = 0.f;
-  const long long thw = static_cast<long long>(T) * H * W;
-  const int Hp = H + 2 * pad, Wp = W + 2 * pad, Tp = T + 2 * pad;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long pos = idx % thw;
-    const long long r = idx / thw;
-    const int g = static_cast<int>(r % G);
-    const long long b = r / G;
-    float f[4];
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int g = blockIdx.y % G, b = blockIdx.y / G;
+  if (p < H * W) {
+    const long long hw = static_cast<long long>(H) * W;
+    const int h = p / W, w = p - h * W;
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad, Tp = T + 2 * pad;
+    const float* xs = x + (static_cast<long long>(b) * C + g * 4) * T * hw + p;
+    float4* ys = y + ((static_cast<long long>(blockIdx.y) * Tp + pad) * Hp + (h + pad)) * Wp + (w + pad);
+#pragma unroll 2
+    for (int t = 0; t < T; ++t) {
+      float f[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = g * 4 + j;
-      f[j] = (c < C) ? x[(b * C + c) * thw + pos] : 0.f;
+      for (int j = 0; j < 4; ++j) f[j] = (g * 4 + j < C) ? xs[(static_cast<long long>(j) * T + t) * hw] : 0.f;
+      ys[static_cast<long long>(t) * Hp * Wp] = make_float4(f[0], f[1], f[2], f[3]);
+      am = fmaxf(fmaxf(am, fmaxf(fabsf(f[0]), fabsf(f[1]))), fmaxf(fabsf(f[2]), fabsf(f[3])));
     }
-    const int w = static_cast<int>(pos % W);
-    const int h = static_cast<int>((pos / W) % H);
-    const int t = static_cast<int>(pos / (static_cast<long long>(W) * H));
-    y[((b * G + g) * Tp + (t + pad)) * Hp * Wp + static_cast<long long>(h + pad) * Wp + (w + pad)] = make_float4(f[0], f[1], f[2], f[3]);
-    am = fmaxf(fmaxf(am, fmaxf(fabsf(f[0]), fabsf(f[1]))), fmaxf(fabsf(f[2]), fabsf(f[3])));
   }
-  if (amax_out) t3_publish_amax(amax_out, am);  // (every thread of the grid reaches this line)
+  if (amax_out) t3_publish_amax_block(amax_out, am);  // (every thread of the grid reaches this line)
 }
 
 // blocked fp32 [B][G][T][H][W][4] -> [B][C][T][H][W] fp32
@@ -944,7 +958,7 @@ __global__ void __launch_bounds__(256) sat_normalise_blocked_f32_kernel(const in
     ys[pos] = make_float4(f[0], f[1], f[2], f[3]);
     am = fmaxf(fmaxf(am, fmaxf(fabsf(f[0]), fabsf(f[1]))), fmaxf(fabsf(f[2]), fabsf(f[3])));
   }
-  if (amax_out) t3_publish_amax(amax_out, am);
+  if (amax_out) t3_publish_amax_block(amax_out, am);
 }
 
 int g_t3_pair = 1;  // CTA-pair kernel for Cout > 16 (tools may switch it off through pvb200_debug_set_tf32x3_pair)
@@ -1096,11 +1110,10 @@ int pvb200_nc_to_blocked_f32(const float* x, float* y, int B, int C, int T, int 
   using namespace pvb;
   PVB_REQUIRE(x && y && B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && pad >= 0, "nc_to_blocked_f32: bad argument");
   const int G = t3_groups(C);
-  const long long total = static_cast<long long>(B) * G * T * H * W;
-  long long grid = ceil_div(total, 256LL);
-  if (grid > 148 * 32) grid = 148 * 32;
-  nc_to_blocked_f32_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), C, G, T, H, W,
-                                                                                        pad, total, reinterpret_cast<unsigned*>(amax_out));
+  PVB_REQUIRE(static_cast<long long>(H) * W < (1LL << 31) - 256 && static_cast<long long>(B) * G <= 65535, "nc_to_blocked_f32: input too large");
+  const dim3 grid(static_cast<unsigned>(ceil_div(H * W, 256)), static_cast<unsigned>(B * G));
+  nc_to_blocked_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, reinterpret_cast<float4*>(y), C, G, T, H, W, pad,
+                                                                reinterpret_cast<unsigned*>(amax_out));
   PVB_LAUNCHED("nc_to_blocked_f32");
   return PVB200_OK;
 }

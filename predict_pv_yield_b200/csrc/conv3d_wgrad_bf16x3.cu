@@ -560,25 +560,23 @@ __global__ void wgrad_bf16x3_reduce_kernel(const float* __restrict__ partial, in
                                            int Ci, int Co, int G8, int CoP, int kt_bias, const float* __restrict__ amax_x,
                                            const float* __restrict__ amax_g) {
   const float ux = amax_x ? w3_exp2i(-w3_scale_exp(__ldg(amax_x))) : 1.f, ug = amax_g ? w3_exp2i(-w3_scale_exp(__ldg(amax_g))) : 1.f;
+  // one thread per element of the partial layout [kw][column][row]: a warp reads 32 consecutive rows = 128 contiguous bytes
+  // of every CTA's partial (indexing by dW element instead cost 32 sectors per load: 15 us per layer, L2 bound)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = Co * Ci * 27;
+  if (idx >= 3 * kW3AccCols * 128) return;
+  const int row = idx & 127, col = (idx >> 7) % kW3AccCols, kw = idx / (128 * kW3AccCols);
+  const int kt = col / CoP, co = col - kt * CoP;
+  const int mg = row >> 3, c8 = row & 7;  // M-group 3 g8 + kh, or the group of ones
+  const bool is_bias = (mg == 3 * G8) && c8 == 0 && kw == 0 && kt == kt_bias && db != nullptr;
+  const int g8 = mg / 3, kh = mg - 3 * g8, ci = g8 * 8 + c8;
+  const bool is_w = mg < 3 * G8 && ci < Ci;
+  if (co >= Co || kt >= 3 || !(is_w || is_bias)) return;
   const size_t per_cta = static_cast<size_t>(3) * 128 * kW3AccCols;
-  if (idx < total) {
-    const int tap = idx % 27;
-    const int ci = (idx / 27) % Ci;
-    const int co = idx / (27 * Ci);
-    const int kt = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-    const size_t off = (static_cast<size_t>(kw) * kW3AccCols + kt * CoP + co) * 128 + ((3 * (ci >> 3) + kh) * 8 + (ci & 7));
-    float s = 0.f;
-    for (int c = 0; c < ncta; ++c) s += partial[c * per_cta + off];
-    dw[idx] = (s * ux) * ug;
-  } else if (idx < total + Co && db) {
-    const int co = idx - total;
-    const size_t off = static_cast<size_t>(kt_bias * CoP + co) * 128 + (3 * G8) * 8;
-    float s = 0.f;
-    for (int c = 0; c < ncta; ++c) s += partial[c * per_cta + off];
-    db[co] = s * ug;
-  }
+  const float* src = partial + idx;
+  float s = 0.f;
+  for (int c = 0; c < ncta; ++c) s += src[c * per_cta];  // fixed order: deterministic
+  if (is_w) dw[((static_cast<size_t>(co) * Ci + ci) * 3 + kt) * 9 + kh * 3 + kw] = (s * ux) * ug;
+  else db[co] = s * ug;
 }
 
 int g_w3_dbg_flags = 0;  // set through pvb200_debug_set_wgrad_flags (tools only)
@@ -691,8 +689,7 @@ static int w3_launch(const char* who, int NP, const float* amax_x, const float* 
     conv3d_wgrad_bf16x3_kernel<2><<<static_cast<unsigned>(grid), kW3Threads, smem, stream>>>(a, tm_x, tm_gz);
   }
   PVB_LAUNCHED(who);
-  const int total = Cout * Cin * 27 + Cout;
-  wgrad_bf16x3_reduce_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(a.partial, static_cast<int>(grid), dw, db, Cin, Cout, a.G / 2,
+  wgrad_bf16x3_reduce_kernel<<<3 * kW3AccCols, 128, 0, stream>>>(a.partial, static_cast<int>(grid), dw, db, Cin, Cout, a.G / 2,
                                                                        a.CoP, pad_t, NP == 2 ? amax_x : nullptr, NP == 2 ? amax_g : nullptr);
   PVB_LAUNCHED("wgrad_bf16x3_reduce");
   return PVB200_OK;
