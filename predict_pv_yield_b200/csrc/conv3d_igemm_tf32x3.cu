@@ -1,5 +1,8 @@
 // conv3d_igemm_tf32x3.cu -- a3/a4/a11 in fp32 MODE on the tensor cores: Conv3d 3x3x3 forward and data gradient as an
-// implicit GEMM of tcgen05.mma.kind::tf32 instructions with the 3xTF32 split, fp32-class accuracy (<= 1e-5).
+// implicit GEMM of split-precision tcgen05 MMAs, fp32-class accuracy (<= 1e-5): the 3xTF32 split (kind::tf32) described
+// first, and -- in the CTA-pair kernel, when the caller passes the input tensor's largest magnitude (amax_in) -- the
+// two-way fp16 split of scaled operands (kind::f16, K = 16 channels per MMA, half the MMAs; see t3_scale_exp below), which
+// is what the model runs for Cout > 16.  The layout kernels at the end report the largest magnitude they write (amax_out).
 //
 // Reference call sites: predict_pv_yield/models/conv3d/model.py:80-90,117-120 (and their autograd).
 //

@@ -1,36 +1,41 @@
 // conv3d_wgrad_bf16x3.cu -- a11 in fp32 MODE on the tensor cores: the Conv3d 3x3x3 weight (and bias) gradient as
-// tcgen05.mma.kind::f16 GEMMs over a THREE-WAY bf16 split of the fp32 operands (fp32-class accuracy).
+// tcgen05.mma.kind::f16 GEMMs over a split of the fp32 operands into 16-bit pieces (fp32-class accuracy): the TWO-WAY
+// fp16 split of scaled operands (three products per fp32 product; pvb200_conv3d_wgrad_f16x2, what the model runs) or the
+// THREE-WAY bf16 split (six products; pvb200_conv3d_wgrad_bf16x3, needs no scaling) -- one kernel template.
 //
 // Reference: autograd of nn.Conv3d, predict_pv_yield/models/conv3d/model.py:80-90,117-120:
 //   dW[co][ci][kt][kh][kw] = sum_{b,t,h,w} gz[b][co][t][h][w] * x[b][ci][t+kt][h+kh][w+kw],   db[co] = sum gz.
 //
-// Why not 3xTF32 like the forward / data gradient (conv3d_igemm_tf32x3.cu): the reduction runs over output positions, so
-// positions are the K dimension and both operands must be read "MN-major" (channels contiguous, positions strided) from the
-// blocked layout.  kind::tf32 returns ZEROS for MN-major SWIZZLE_NONE operands (tools/probe/tf32_mn_probe.cu; CUTLASS:
+// Why not 3xTF32 like the first forward / data gradient (conv3d_igemm_tf32x3.cu): the reduction runs over output positions,
+// so positions are the K dimension and both operands must be read "MN-major" (channels contiguous, positions strided) from
+// the blocked layout.  kind::tf32 returns ZEROS for MN-major SWIZZLE_NONE operands (tools/probe/tf32_mn_probe.cu; CUTLASS:
 // "for mn-major tf32 operands, SW128_32B is the only available smem layout", a 32-bit-granular swizzle bulk copies cannot
-// produce).  kind::f16 has no such restriction, and an fp32 value is EXACTLY the sum of three bf16 values
+// produce).  kind::f16 has no such restriction.  Three-way bf16 split: an fp32 value is EXACTLY the sum of three bf16 values
 // (v = b0 + b1 + b2, 8 + 8 + 8 significand bits, round-to-nearest residuals), so
 //   x . g = x0 g0 + x0 g1 + x1 g0 + x1 g1 + x0 g2 + x2 g0      (the dropped terms are <= 2^-24 relative)
-// costs six K = 16 MMAs per 16 positions -- the same tensor time as three K = 8 TF32 MMAs per 8 positions.
+// costs six K = 16 MMAs per 16 positions.  Two-way fp16 split: s v = h0 + h1 with 11 + 11 significand bits after scaling
+// by the power of two that brings the tensor's largest magnitude into fp16's range (w3_scale_exp), x . g = x1 g0 + x0 g1 +
+// x0 g0 (dropped: 2^-22): three MMAs, half the operand bytes -- see w3_split2h.
 //
 // GEMM shape.  One step of the kernel = one input plane p of one sample and one output row h:
-//   * the TMA engine stages the raw fp32 rows (bulk copies: the three input rows h..h+2 of a channel group are contiguous
-//     in memory; row h of the gradient planes p, p-1, p-2); eight "split" warps turn them into the three bf16 pieces in
-//     the operand layout [group of 8 channels][row][position][8] (two fp32 channel groups merge into one bf16 group).
+//   * two tiled TMA loads through tensor maps stage the raw fp32 rows (the three input rows h..h+2 of every channel group --
+//     contiguous in memory; row h of the gradient planes p, p-1, p-2); eight "split" warps turn them into the 16-bit
+//     pieces in the operand layout [group of 8 channels][row][position][8] (two fp32 channel groups merge into one group).
 //   * A (M = 128): pieces of the input rows as [g][kh][Wi]: M-group m = 3 g + kh sits at the uniform stride Wi * 16 B, so
 //     the kh taps cost no copies; M-group 3 G8 is a constant row of ones (bias gradient for free); the remaining M rows
 //     read whatever follows inside the buffer and are never looked at.
 //   * the kw taps are the descriptor START address (kw * 16 B): three accumulators, no copies.
 //   * B (N = 96): pieces of the gradient rows as [kt][g][WP] (WP = Wo rounded up to 16, the padding stays zero): plane p
 //     contributes to the three time taps at once; taps that fall outside the output are cut off by narrowing N.
-//   => per step 3 (kw) x WP/16 x 6 MMAs of 128 x 96 x 16 (72 for a 62-wide row) against 48 KB of fp32 operands from L2
-//      (rows are re-read by neighbouring steps: L2 hits; DRAM sees each tensor once).
+//   => per step 3 (kw) x WP/16 x 3 (or 6) MMAs of 128 x 96 x 16 against 48 KB of fp32 operands from L2.
+// Step order (w3_step): blocks of 6 output rows x all input planes, so that the re-reads of a gradient plane hit L2; the
+// ranges of steps a CTA works on come through a shared-memory ring -- static split or chunks from an atomic counter.
 // Accuracy.  The tensor core's fp32 accumulator rounds toward zero (tools/probe/tf32_acc_probe.cu): every kFlush steps the
-// three accumulators are drained and added -- in fp32 round-to-nearest, by the drain warps -- to the CTA's private
-// partial in global memory (L2 resident, 147 KB per CTA); the drain of one accumulator overlaps the MMAs of the other two.
-// A second kernel reduces the per-CTA partials in fixed order (deterministic) into dW [Co][Ci][3][3][3] and db.
-// Warp roles (704 threads): warp 0 producer (lane-parallel bulk copies), warp 1 MMA issuer + TMEM owner, warps 2-9
-// split, warps 10-21 accumulator drain (four warps per kw accumulator).  Pipeline: raw staging (one buffer) -> pieces (two buffers) -> MMA.
+// three accumulators are drained and added -- in fp32 round-to-nearest, red.global.add.f32 -- to the CTA's private partial
+// in global memory (L2 resident, 147 KB per CTA).  A second kernel reduces the per-CTA partials in fixed order into
+// dW [Co][Ci][3][3][3] and db, and takes the operand scales out.
+// Warp roles (448 threads): warp 0 producer (TMA loads, step ranges), warp 1 MMA issuer + TMEM owner, warps 2-9 split,
+// warps 10-13 accumulator drain.  Pipeline: raw staging (two buffers; one for the three-way split) -> pieces (two buffers) -> MMA.
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_fp16.h>
 #include <stdlib.h>
