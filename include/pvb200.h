@@ -356,6 +356,8 @@ int pvb200_fc1_shadow_from_shards(const uint16_t* gathered, uint16_t* shadow, in
 int pvb200_fc1_fwd_bf16_splits(void);
 int pvb200_fc1_fwd_bf16(const uint16_t* xb, const uint16_t* shadow, float* partial, int B, int F1, int Cg, int T, int H,
                         int W, pvb200_stream_t stream);
+/* gzw (the gradient in the round-1 weight-gradient kernel's operand layout) may be NULL: the row-step weight gradient reads
+ * gz_pad, so the second copy is only written for layers it does not take (planes wider than 64) */
 int pvb200_fc1_dgrad_bf16(const float* g1, const uint16_t* shadow, const uint16_t* xb, uint16_t* gz_pad, uint16_t* gzw,
                           int B, int F1, int Cg, int T, int H, int W, pvb200_stream_t stream);
 int pvb200_fc1_wgrad_bf16(const float* g1, const uint16_t* xb, float* dw1, int B, int F1, int Cg, int T, int H, int W,

@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kF1ThreadsWgrad : kF1Threads, 1) f
                 const uint4 m = (i0 == 0) ? dmask[ii] : __ldg(a.xb + static_cast<long long>(b) * a.KG + dkg);
                 const uint4 o = make_uint4(sel(g.x, m.x), sel(g.y, m.y), sel(g.z, m.z), sel(g.w, m.w));
                 a.gz_pad[o_pad + b * s_pad] = o;
-                a.gzw[o_gzw + b * s_gzw] = o;
+                if (a.gzw) a.gzw[o_gzw + b * s_gzw] = o;
               }
             }
           }
@@ -665,7 +665,7 @@ int pvb200_fc1_fwd_bf16(const uint16_t* xb, const uint16_t* shadow, float* parti
 int pvb200_fc1_dgrad_bf16(const float* g1, const uint16_t* shadow, const uint16_t* xb, uint16_t* gz_pad, uint16_t* gzw,
                           int B, int F1, int Cg, int T, int H, int W, pvb200_stream_t stream) {
   using namespace pvb;
-  PVB_REQUIRE(g1 && shadow && xb && gz_pad && gzw, "fc1_dgrad_bf16: null pointer");
+  PVB_REQUIRE(g1 && shadow && xb && gz_pad, "fc1_dgrad_bf16: null pointer");  // gzw may be NULL: not written
   Fc1Bf16Args a{};
   int rc = fc1_bf16_fill(a, B, F1, Cg, T, H, W);
   if (rc) return rc;

@@ -735,6 +735,8 @@ class EncoderBf16Fn(torch.autograd.Function):
         ctx.channels = [wb[2 * l].shape[1] for l in range(n_layers)] + [wb[-2].shape[0]]
         ctx.link = link
         if link is not None:
+            # does the last layer's weight gradient need the gradient in the round-1 kernel's "gzw" layout as well?
+            link["need_gzw"] = not wgrad_bf16_rows_supported(ctx.channels[-2], ctx.channels[-1], acts[-2].shape[3], acts[-2].shape[4])
             return acts[-1]
         feats = from_blocked_bf16(acts[-1], ctx.channels[-1])
         return feats.view(sat.shape[0], -1)
@@ -1058,9 +1060,10 @@ class HeadBf16Fn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(H + 2, W + 2))
             gz_pad = _zero_bordered("gz_pad_head", (B, Cg, T + 4, H + 4, W + 4, 8), dev)
-            gzw = _zero_bordered(f"gzw_head_{H}x{W}", (B, Cg, T, QP, 8), dev)
+            need_gzw = ctx.link is None or ctx.link.get("need_gzw", True)
+            gzw = _zero_bordered(f"gzw_head_{H}x{W}", (B, Cg, T, QP, 8), dev) if need_gzw else None
             shadow = ctx.shadow
-            with _timed("fc1_dgrad_bf16", 2.0 * B * h.F1 * h.K1, 2.0 * (128 * h.K1 + 4 * B * h.K1)):
+            with _timed("fc1_dgrad_bf16", 2.0 * B * h.F1 * h.K1, 2.0 * (128 * h.K1 + (4 if need_gzw else 3) * B * h.K1)):
                 rc = L.pvb200_fc1_dgrad_bf16(_p(g_h1), _p(shadow), _p(act), _p(gz_pad), _p(gzw), B, h.F1, Cg, T, H, W, _stream())
             _lib.check(rc, "fc1_dgrad_bf16")
             if ctx.link is None:
@@ -1199,7 +1202,7 @@ class Fc1Bf16Fn(torch.autograd.Function):
             tag = ctx.link.get("tag", "tower")
             QP = int(L.pvb200_conv3d_wgrad_bf16_gz_plane(H + 2, W + 2))
             gz_pad = _zero_bordered("gz_pad_" + tag, (B, Cg, T + 4, H + 4, W + 4, 8), dev)
-            gzw = _zero_bordered(f"gzw_{tag}_{H}x{W}", (B, Cg, T, QP, 8), dev)
+            gzw = _zero_bordered(f"gzw_{tag}_{H}x{W}", (B, Cg, T, QP, 8), dev) if ctx.link.get("need_gzw", True) else None
             with _timed("fc1_dgrad_bf16", 2.0 * B * F1 * K1, 2.0 * (128 * K1 + 4 * B * K1)):
                 rc = L.pvb200_fc1_dgrad_bf16(_p(g_pre), _p(ctx.shadow), _p(act), _p(gz_pad), _p(gzw), B, F1, Cg, T, H, W, _stream())
             _lib.check(rc, "fc1_dgrad_bf16")
