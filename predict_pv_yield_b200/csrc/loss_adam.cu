@@ -82,7 +82,11 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
   p = fmaf(s.neg_step_size, __fdiv_rn(m, denom), p);      // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
 
-__global__ void __launch_bounds__(256, 3) adam_multi_kernel(const AdamTensors t, const AdamScalars s, long long total_chunks) {
+// MINB = CTAs per SM the register allocation aims at: 3 (80 registers) for the stand-alone launch, one CTA per chunk -- 0.64 ms
+// for fc1.weight, 0.94 of HBM; with 2 per SM or a persistent grid it took 0.77 ms -- and 2 (86 registers) for the narrow
+// side-stream launch, whose CTAs must leave room for the convolution CTAs of the next forward pass on their SMs
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) adam_multi_kernel(const AdamTensors t, const AdamScalars s, long long total_chunks) {
   for (long long ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
     // locate tensor (n <= 48: linear scan over a kernel-parameter array)
     int ti = 0;
@@ -224,8 +228,10 @@ int pvb200_adam_step_f32(int n, float* const* params, const float* const* grads,
     // SMs are reserved (pvb200_reserve_sms: the side-stream update under the next forward pass wants a NARROW grid)
     int dev = 0, dev_sms = sms;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev);
-    long long grid = (sms < dev_sms && chunks > static_cast<long long>(sms) * 8) ? static_cast<long long>(sms) * 8 : chunks;
-    adam_multi_kernel<<<static_cast<unsigned>(grid), 256, 0, as_stream(stream)>>>(t, s, chunks);
+    if (sms < dev_sms && chunks > static_cast<long long>(sms) * 8)
+      adam_multi_kernel<2><<<static_cast<unsigned>(sms * 8), 256, 0, as_stream(stream)>>>(t, s, chunks);
+    else
+      adam_multi_kernel<3><<<static_cast<unsigned>(chunks), 256, 0, as_stream(stream)>>>(t, s, chunks);
     PVB_LAUNCHED("adam_multi");
   }
   return PVB200_OK;
