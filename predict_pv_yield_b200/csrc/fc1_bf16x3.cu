@@ -15,8 +15,13 @@
 // gradient (MN-major B).
 //   forward   D[j, b]  = sum_k W[j,k] X[b,k]      k tiles of 64; split-K over the CTAs; the accumulator is folded into
 //                                                 fp32 registers every two tiles (the tensor core rounds toward zero)
-//   dgrad     D[k, b]  = sum_j W[j,k] G[b,j]      k tiles of 128; ReLU mask (x > 0) fused; coalesced stores along k
-//   wgrad     D[k, j]  = sum_b X[b,k] G[b,j]      k tiles of 128; dW[j][k] written straight from tensor memory, coalesced along k
+//   dgrad     D[k, b]  = sum_j W[j,k] G[b,j]      k tiles of 128, fetched and accumulated in four quarters of 32 features;
+//                                                 the ReLU-mask source x arrives by a tensor-map load into the buffer the
+//                                                 result is written to in place, which leaves as ONE tensor-map store
+//   wgrad     D[k, j]  = sum_b X[b,k] G[b,j]      k tiles of 128; dW goes through a shared-memory tile [j][64 k] per warp
+//                                                 pair and leaves as tensor-map stores
+// (Register stores of 4 bytes to rows 4.4 MB apart cost a translation per access: the first version of the weight
+// gradient spent 230 of its 304 us on them.)  Tiles are dealt round-robin over the CTAs.
 // Warp roles (448 threads): warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-9 split, warps 10-13 epilogue.
 #include <cuda.h>
 #include <stdlib.h>
@@ -32,7 +37,7 @@ constexpr int kFxKT = 64;                 // k per raw tile (256 B per row: one 
 constexpr uint32_t kFxWS = 128 * 16 + 16; // stride between 8-k groups of the W pieces (padded: fewer bank conflicts)
 
 struct FxArgs {
-  int flags;        // debug: 1 = epilogues skip their global stores, 2 = the data gradient skips the mask loads
+  int flags;        // tools only: 1 = epilogues skip their stores, 4 = the data gradient issues no MMAs, 8 = ... no split arithmetic
   const float* x;   // [B][K1]
   const float* g;   // [B][F1] gradient w.r.t. the fc1 pre-activation (dgrad, wgrad)
   float* out;       // fwd: partial [S][B][F1]; dgrad: gx [B][K1]; wgrad: dW [F1][K1]
