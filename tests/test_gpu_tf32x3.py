@@ -244,6 +244,29 @@ def test_conv3d_wgrad_dynamic_chunks(ops, dev, shape, two_way):
         L.pvb200_set_dynamic_tiles(old)
 
 
+def test_conv3d_wgrad_full_size_accuracy(ops, dev):
+    """The weight gradient at the FULL conv1 shape of the BASELINE model (32 -> 32 channels, 17x62x62 input, batch 32): a CTA
+    then runs ~220 steps = 14 flush windows of the toward-zero accumulators, which is where their length shows (16 steps:
+    3.4e-6 -- torch's own fp32 convolution is 3.4e-6 from fp64 here; 32 steps: 7e-6; 8 steps: 1.8e-6).  Checker: torch fp64
+    on the GPU, in slices of four samples."""
+    torch.backends.cudnn.allow_tf32 = False
+    B, Ci, T, S, Co = 32, 32, 17, 62, 32
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.relu(torch.randn(B, Ci, T, S, S, device=dev, generator=g))
+    gz = torch.randn(B, Co, T - 2, S - 2, S - 2, device=dev, generator=g)
+    wd = torch.zeros(Co, Ci, 3, 3, 3, device=dev, dtype=torch.float64, requires_grad=True)
+    bd = torch.zeros(Co, device=dev, dtype=torch.float64, requires_grad=True)
+    for b0 in range(0, B, 4):
+        F.conv3d(x[b0:b0 + 4].double(), wd, bd).backward(gz[b0:b0 + 4].double())
+    am = torch.zeros(2, device=dev)
+    xb, gzb = ops.to_blocked_f32(x, amax=am[0:1]), ops.to_blocked_f32(gz, pad=2, amax=am[1:2])
+    for name, kw in (("f16x2", dict(amax=(am[0:1], am[1:2]))), ("bf16x3", {})):
+        dw, db = ops.conv3d_wgrad_bf16x3(xb, gzb, Ci, Co, gz_pad=2, **kw)
+        e_w, e_b = nerr(dw, wd.grad), nerr(db, bd.grad)
+        print(f"full-size wgrad {name}: dw {e_w:.2e} db {e_b:.2e}")
+        assert e_w <= TOL and e_b <= TOL, name
+
+
 def test_conv3d_wgrad_f16x2_wide_dynamic_range(ops, dev):
     """Operands whose magnitudes span 2^40 inside one tensor: the small values lose RELATIVE precision in the fp16 split,
     the gradient (dominated by the large ones) stays within the fp32 bound; an all-zero gradient gives exact zeros."""
