@@ -43,6 +43,7 @@ struct FxArgs {
   float* out;       // fwd: partial [S][B][F1]; dgrad: gx [B][K1]; wgrad: dW [F1][K1]
   int B, BP, F1;
   int Btot;         // fwd: samples in the whole partial buffer (B is this launch's chunk of them)
+  int accumulate;   // wgrad: add this launch's tile sums to dW (a later chunk of the batch) instead of storing them
   long long K1, tiles;  // tiles: k tiles of 64 (fwd) / 128 (dgrad, wgrad)
 };
 
@@ -56,6 +57,14 @@ __device__ __forceinline__ void fx_tma_2d(void* dst_smem, const CUtensorMap* tm,
 // shared -> global tile store through a tensor map (rows / columns outside the tensor are clipped by the hardware)
 __device__ __forceinline__ void fx_tma_store_2d(const CUtensorMap* tm, const void* src_smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(tc::smem_u32(src_smem)), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the same as an element-wise ADD to global memory (cp.reduce: the TMA engine reads, adds and writes back)
+__device__ __forceinline__ void fx_tma_add_2d(const CUtensorMap* tm, const void* src_smem, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
                "r"(tc::smem_u32(src_smem)), "r"(c0), "r"(c1)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -553,7 +562,10 @@ __global__ void __launch_bounds__(kFxThreads, 1) fc1x3_wgrad_kernel(const FxArgs
       if (lane == 0) tc::mbar_arrive(dempty + st);
       tc::fence_proxy_async();
       fx_pair_sync(pair);
-      if (lane == 0 && (qd & 1) == 0 && !(a.flags & 1)) fx_tma_store_2d(&tm_out, out_s, static_cast<int>(t * 128 + pair * 64), 0);
+      if (lane == 0 && (qd & 1) == 0 && !(a.flags & 1)) {
+        if (a.accumulate) fx_tma_add_2d(&tm_out, out_s, static_cast<int>(t * 128 + pair * 64), 0);
+        else fx_tma_store_2d(&tm_out, out_s, static_cast<int>(t * 128 + pair * 64), 0);
+      }
     }
     if (lane == 0 && (qd & 1) == 0) fx_store_wait_all();
   }
@@ -615,7 +627,7 @@ int fc1x3_fwd(const float* x, const float* w, float* partial, int S, int B, int 
   for (int b0 = 0; b0 < B; b0 += kChunk) {
     FxArgs a;
     a.flags = g_fc1x3_flags; a.x = x + b0 * K1; a.g = nullptr; a.out = partial + static_cast<long long>(b0) * F1;
-    a.B = B - b0 < kChunk ? B - b0 : kChunk; a.BP = round_up(a.B, 16); a.F1 = F1; a.Btot = B; a.K1 = K1;
+    a.B = B - b0 < kChunk ? B - b0 : kChunk; a.BP = round_up(a.B, 16); a.F1 = F1; a.Btot = B; a.accumulate = 0; a.K1 = K1;
     a.tiles = ceil_div(K1, static_cast<long long>(kFxKT));
     CUtensorMap tx;
     PVB_REQUIRE(fx_make_map(&tx, a.x, K1, a.B, a.BP) == 0, "fc1x3_fwd: cuTensorMapEncodeTiled failed");
@@ -628,41 +640,53 @@ int fc1x3_fwd(const float* x, const float* w, float* partial, int S, int B, int 
   return PVB200_OK;
 }
 
+// Batches larger than 48 go through in chunks of 48 samples, each streaming W (dgrad) / writing dW (wgrad) once: the data
+// gradient's samples are independent; the weight gradient's later chunks ADD their sums to dW through the TMA engine
+// (cp.reduce.async.bulk.tensor ... .add), launch after launch in stream order -- deterministic.
+constexpr int kFxBwdChunk = 48;
+
 int fc1x3_dgrad(const float* g, const float* w, const float* x, float* gx, int B, int F1, long long K1, cudaStream_t st) {
-  FxArgs a;
-  a.flags = g_fc1x3_flags; a.x = x; a.g = g; a.out = gx; a.B = B; a.BP = round_up(B, 16); a.F1 = F1; a.K1 = K1;
-  a.tiles = ceil_div(K1, 128LL);
-  CUtensorMap tw, tx, to;
-  PVB_REQUIRE(fx_make_map(&tw, w, K1, F1, 32, 128) == 0 && fx_make_map(&tx, x, K1, B, a.BP, 128) == 0 &&
-                  fx_make_map(&to, gx, K1, B, a.BP, 128) == 0,
-              "fc1x3_dgrad: cuTensorMapEncodeTiled failed");
-  const uint32_t gs = a.BP * 16 + 16;
-  const size_t smem = 256 + 4 * 32 * 512 + kFxDSets * 3 * 16 * kFxDS + 3 * round_up(16 * gs, 128u) + 2 * a.BP * 512;
   const int sms = sm_count();
   PVB_REQUIRE(sms > 0, "fc1x3_dgrad: no CUDA device");
-  const long long grid = a.tiles < sms ? a.tiles : sms;
-  PVB_CUDA(cudaFuncSetAttribute(fc1x3_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fc1x3_dgrad_kernel<<<static_cast<unsigned>(grid), kFxThreads, smem, st>>>(a, tw, tx, to);
-  PVB_LAUNCHED("fc1x3_dgrad");
+  CUtensorMap tw;
+  PVB_REQUIRE(fx_make_map(&tw, w, K1, F1, 32, 128) == 0, "fc1x3_dgrad: cuTensorMapEncodeTiled failed");
+  for (int b0 = 0; b0 < B; b0 += kFxBwdChunk) {
+    FxArgs a;
+    a.flags = g_fc1x3_flags; a.x = x + b0 * K1; a.g = g + static_cast<long long>(b0) * F1; a.out = gx + b0 * K1;
+    a.B = B - b0 < kFxBwdChunk ? B - b0 : kFxBwdChunk; a.BP = round_up(a.B, 16); a.F1 = F1; a.Btot = B; a.accumulate = 0; a.K1 = K1;
+    a.tiles = ceil_div(K1, 128LL);
+    CUtensorMap tx, to;
+    PVB_REQUIRE(fx_make_map(&tx, a.x, K1, a.B, a.BP, 128) == 0 && fx_make_map(&to, a.out, K1, a.B, a.BP, 128) == 0,
+                "fc1x3_dgrad: cuTensorMapEncodeTiled failed");
+    const uint32_t gs = a.BP * 16 + 16;
+    const size_t smem = 256 + 4 * 32 * 512 + kFxDSets * 3 * 16 * kFxDS + 3 * round_up(16 * gs, 128u) + 2 * a.BP * 512;
+    const long long grid = a.tiles < sms ? a.tiles : sms;
+    PVB_CUDA(cudaFuncSetAttribute(fc1x3_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fc1x3_dgrad_kernel<<<static_cast<unsigned>(grid), kFxThreads, smem, st>>>(a, tw, tx, to);
+    PVB_LAUNCHED("fc1x3_dgrad");
+  }
   return PVB200_OK;
 }
 
 int fc1x3_wgrad(const float* g, const float* x, float* dw, int B, int F1, long long K1, cudaStream_t st) {
-  FxArgs a;
-  a.flags = g_fc1x3_flags; a.x = x; a.g = g; a.out = dw; a.B = B; a.BP = round_up(B, 16); a.F1 = F1; a.K1 = K1;
-  a.tiles = ceil_div(K1, 128LL);
-  CUtensorMap tx;
-  PVB_REQUIRE(fx_make_map(&tx, x, K1, B, a.BP) == 0, "fc1x3_wgrad: cuTensorMapEncodeTiled failed");
-  const uint32_t xs = a.BP * 16 + 16;
-  const size_t smem = 256 + 4 * a.BP * 256 + 3 * 3 * round_up(16 * xs, 128u) + 2 * 32768;
-  CUtensorMap to;
-  PVB_REQUIRE(fx_make_map(&to, dw, K1, F1, 128) == 0, "fc1x3_wgrad: cuTensorMapEncodeTiled failed");
   const int sms = sm_count();
   PVB_REQUIRE(sms > 0, "fc1x3_wgrad: no CUDA device");
-  const long long grid = a.tiles < sms ? a.tiles : sms;
-  PVB_CUDA(cudaFuncSetAttribute(fc1x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fc1x3_wgrad_kernel<<<static_cast<unsigned>(grid), kFxThreads, smem, st>>>(a, tx, to);
-  PVB_LAUNCHED("fc1x3_wgrad");
+  CUtensorMap to;
+  PVB_REQUIRE(fx_make_map(&to, dw, K1, F1, 128) == 0, "fc1x3_wgrad: cuTensorMapEncodeTiled failed");
+  for (int b0 = 0; b0 < B; b0 += kFxBwdChunk) {
+    FxArgs a;
+    a.flags = g_fc1x3_flags; a.x = x + b0 * K1; a.g = g + static_cast<long long>(b0) * F1; a.out = dw;
+    a.B = B - b0 < kFxBwdChunk ? B - b0 : kFxBwdChunk; a.BP = round_up(a.B, 16); a.F1 = F1; a.Btot = B; a.accumulate = b0 > 0; a.K1 = K1;
+    a.tiles = ceil_div(K1, 128LL);
+    CUtensorMap tx;
+    PVB_REQUIRE(fx_make_map(&tx, a.x, K1, a.B, a.BP) == 0, "fc1x3_wgrad: cuTensorMapEncodeTiled failed");
+    const uint32_t xs = a.BP * 16 + 16;
+    const size_t smem = 256 + 4 * a.BP * 256 + 3 * 3 * round_up(16 * xs, 128u) + 2 * 32768;
+    const long long grid = a.tiles < sms ? a.tiles : sms;
+    PVB_CUDA(cudaFuncSetAttribute(fc1x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fc1x3_wgrad_kernel<<<static_cast<unsigned>(grid), kFxThreads, smem, st>>>(a, tx, to);
+    PVB_LAUNCHED("fc1x3_wgrad");
+  }
   return PVB200_OK;
 }
 

@@ -718,7 +718,7 @@ int fc1x3_fwd_ctas(long long K1);
 int fc1x3_fwd(const float* x, const float* w, float* partial, int S, int B, int F1, long long K1, cudaStream_t st);
 int fc1x3_dgrad(const float* g, const float* w, const float* x, float* gx, int B, int F1, long long K1, cudaStream_t st);
 int fc1x3_wgrad(const float* g, const float* x, float* dw, int B, int F1, long long K1, cudaStream_t st);
-constexpr int kFc1x3FwdMaxB = 1 << 30, kFc1x3BwdMaxB = 48;  // the forward chunks its batch; shared-memory budget of the backward
+constexpr int kFc1x3FwdMaxB = 1 << 30, kFc1x3BwdMaxB = 1 << 30;  // all three kernels chunk their batch (48 samples per launch)
 
 static bool vec4_ok(const void* p, long long ld) { return (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(p) % 16 == 0); }
 

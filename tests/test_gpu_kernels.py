@@ -178,7 +178,7 @@ HEAD_CASES = [
     (37, 4096, 128, 128, 64, 12, None, True),  # more than one batch tile
     (2, 300, 130, 16, 16, 4, None, False),     # F1 > one feature tile
     (48, 8200, 100, 64, 32, 12, None, False),  # tensor-core fc1: K1 not a multiple of the 64 / 128 tiles, F1 < 128
-    (64, 12548, 128, 128, 64, 12, (2, 128), False),  # forward in two batch chunks (B > 48), backward on the FMA kernels
+    (64, 12548, 128, 128, 64, 12, (2, 128), False),  # two batch chunks (B > 48) in all three tensor-core kernels; the weight gradient's second chunk adds through the TMA engine
     (17, 64 * 1300, 128, 128, 64, 12, None, False),  # several k tiles per CTA (accumulator folds, both TMEM windows)
 ]
 

@@ -119,6 +119,7 @@ def test_fc1_tensor_core_and_row_step_kernels(sass):
         assert _count(ops, "UTCHMMA") >= 12 and _count(ops, "LDTM") >= 1, k
         assert _count(ops, "UTMALDG") >= 1 and _count(ops, "UTMASTG") == stores, k  # (unrolled loops repeat the load)
         assert sum(1 for o in ops if o.startswith("F2FP")) >= 12 and _count(ops, "F2F") == 0, k
+        assert _count(ops, "UTMAREDG") == (1 if name == "fc1x3_wgrad_kernel" else 0), k  # later batch chunks add to dW
     (k,) = _find(sass, "conv3d_wgrad_bf16_rows_kernel")
     ops = sass[k]
     assert _count(ops, "UTCHMMA") >= 12 and _count(ops, "UTMALDG") == 2 and _count(ops, "LDTM") >= 1, k

@@ -7,7 +7,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "predict_pv_yield_b200", "libpvb200.so")
-WATCH = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "UTCBAR.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGSTS", "FFMA2", "FFMA", "HMMA", "F2FP",
+WATCH = ["UTCHMMA", "UTCHMMA.2CTA", "UTCBAR", "UTCBAR.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UBLKCP", "SYNCS", "LDGSTS", "FFMA2", "FFMA", "HMMA", "F2FP",
          "USETMAXREG", "UCGABAR_ARV", "LDL", "STL"]
 
 
@@ -29,7 +29,7 @@ def main():
     print(f"# {os.path.relpath(SO, ROOT)}: SASS opcode counts of the kernels that use the tensor cores, the TMA engine or packed FMA")
     print(f"{'kernel':<64}" + "".join(f"{w[:11]:>12}" for w in WATCH) + f"{'instr':>8}")
     for k, c in kernels.items():
-        if not any(c[w] for w in ("UTCHMMA", "UBLKCP", "UTMALDG", "UTMASTG", "FFMA2")):
+        if not any(c[w] for w in ("UTCHMMA", "UBLKCP", "UTMALDG", "UTMASTG", "UTMAREDG", "FFMA2")):
             continue
         short = subprocess.run(["c++filt", k], capture_output=True, text=True).stdout.strip().replace("pvb::", "")
         short = re.sub(r"\(.*", "", short).replace("void ", "")
