@@ -45,3 +45,37 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == pytest.approx(d["value"])
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d.get("gpu_launches", 0) == 0
+
+
+def test_committed_bench_lines_and_traffic_table():
+    """The bench lines committed under profiles/ carry the keys of the contract (metric, value, e2e, roofline with its
+    provenance, cpu_baseline, clocks, gpu_launches, parity_check), and the traffic table names the commit of its ncu capture
+    and the hash of every kernel source it describes."""
+    import glob
+    import hashlib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    table = json.load(open(os.path.join(root, "profiles", "traffic_r02.json")))
+    assert table.get("_commit")
+    for name, row in table.items():
+        if name.startswith("_"):
+            continue
+        assert row["traffic"] > 0 and row["algorithmic"] > 0 and row["traffic"] < 2 * row["algorithmic"], name
+        src = os.path.join(root, row["source_file"])
+        assert os.path.exists(src) and len(row["source_sha1"]) == 40, name
+        hashlib.sha1(open(src, "rb").read()).hexdigest()  # (a changed source is flagged by bench.py, not an error)
+    files = sorted(glob.glob(os.path.join(root, "profiles", "bench_r02", "bench_n*_default.json")))
+    assert len(files) >= 4
+    for fn in files:
+        line = json.loads(open(fn).read().strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+                    "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "parity_check"):
+            assert key in line, (fn, key)
+        assert line["metric"] == "train_samples_per_sec" or line["metric"], fn
+        assert line["gpu_launches"] > 0 and line["parity_check"]["ok"], fn
+        r = line["roofline"]
+        assert r["bound"] in ("hbm", "tensor") and 0 < r["frac"] < 1.5 and r["peak"] > 0, fn
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0, fn
+        if line["n_gpus"] == 1:
+            assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["value"] > 0, fn
+        assert "c3_bf16" in line and line["c3_bf16"]["weak"]["value"] > 0, fn
