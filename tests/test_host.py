@@ -183,3 +183,16 @@ def test_device_prefetcher_rejects_cpu():
 
     with pytest.raises(RuntimeError, match="CUDA"):
         DevicePrefetcher([], torch.device("cpu"))
+
+
+def test_split_precision_shape_rules(built):
+    """Which shapes the two-way fp16 split of the implicit GEMM takes (CTA-pair kernel, whole 16-channel steps; the rest
+    runs 3xTF32), and the blocked-layout group counts behind the rule -- host logic, no device needed."""
+    from predict_pv_yield_b200 import ops
+
+    assert [ops.blocked4_groups(c) for c in (1, 8, 9, 12, 16, 24, 32)] == [2, 2, 4, 4, 4, 6, 8]
+    assert ops.conv_f16x2_applies(12, 32) and ops.conv_f16x2_applies(32, 32) and ops.conv_f16x2_applies(16, 24)
+    assert not ops.conv_f16x2_applies(8, 32)     # half a 16-channel step
+    assert not ops.conv_f16x2_applies(24, 32)    # one and a half
+    assert not ops.conv_f16x2_applies(32, 16)    # single-CTA kernel (Cout <= 16)
+    assert ops.tf32x3_supported(32, 32) and not ops.tf32x3_supported(33, 32) and not ops.tf32x3_supported(32, 64)
