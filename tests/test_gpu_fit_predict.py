@@ -1,0 +1,141 @@
+"""Trainer-style GPU test: dataloader -> fit (N optimiser steps) -> validate -> predict, through the hooks a
+``pl.Trainer`` drives, mirroring the reference's ``tests/models/conv3d/test_conv3d_model.py:42-62`` (``test_train``:
+``FakeDataset`` -> ``DataLoader(batch_size=None)`` -> ``trainer.fit`` -> ``trainer.predict``).
+
+pytorch_lightning is not in this image, so ``_fit`` / ``_predict`` below do what ``Trainer.fit`` / ``Trainer.predict`` do
+on one device with the model's own hooks (``configure_optimizers``, ``training_step``, ``validation_step``,
+``predict_step``) and nothing else.  On top of the reference's shape checks, the same loop is run by the oracle on the CPU
+(torch.optim.Adam, lr 5e-4, ``base_model.py:255-257``) and the loss trajectory and the forecasts after the fit are compared.
+
+Tolerances: step 0 at the forward gate (1e-5 fp32 / 2e-2 bf16).  Later steps see weights that went through Adam, whose
+first updates are ~lr * sign(g): a gradient entry at rounding-noise level may move its weight the other way (see
+test_gpu_model.py::test_model_matches_reference_golden), so the trajectory is gated at 2e-4 / 5e-2 of the loss and the
+forecasts after the fit at 2e-3 / 5e-2 of their largest magnitude (torch's own fp32 loop sits 1e-6 / 1e-4 from the fp64
+loop on these cases) -- a dropped layer, a stale shadow weight or an optimiser that skips a parameter moves them by tens
+of percent.
+"""
+import pytest
+import torch
+
+from oracle import conv3d_oracle as O
+from oracle.golden_cases import CASES, golden_state_dict, seq_len_of
+
+pytestmark = pytest.mark.gpu
+
+N_STEPS = 4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+class _FakeDataset(torch.utils.data.Dataset):
+    """Role of ``nowcasting_dataloader.fake.FakeDataset`` in the reference test: ``length`` pre-batched nested dicts."""
+
+    def __init__(self, kw: dict, batch: int, length: int, seed: int = 7000):
+        self.kw, self.batch, self.length, self.seed = kw, batch, length, seed
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, i):
+        if i >= self.length:
+            raise IndexError(i)
+        kw = self.kw
+        return O.make_synthetic_batch(self.batch, kw["number_sat_channels"], seq_len_of(kw), kw["image_size_pixels"],
+                                      output_variable=kw.get("output_variable", "pv_yield"), seed=self.seed + i)
+
+
+def _fit(model, loader, dev, max_epochs: int = 1):
+    """One-device ``Trainer.fit``: the optimiser of ``configure_optimizers``, one ``training_step`` + backward + step per
+    batch, then one ``validation_step`` per batch without gradients."""
+    from predict_pv_yield_b200.data import DevicePrefetcher
+
+    opt = model.configure_optimizers()
+    losses = []
+    for _ in range(max_epochs):
+        model.train()
+        for i, batch in enumerate(DevicePrefetcher(loader, dev)):
+            opt.zero_grad()
+            loss = model.training_step(batch, i)
+            loss.backward()
+            opt.step()
+            losses.append(loss.detach())
+        model.eval()
+        val = []
+        with torch.no_grad():
+            for i, batch in enumerate(DevicePrefetcher(loader, dev)):
+                val.append(model.validation_step(batch, i).detach())
+    return [float(v) for v in losses], [float(v) for v in val]
+
+
+def _predict(model, loader, dev):
+    from predict_pv_yield_b200.data import DevicePrefetcher
+
+    model.eval()
+    return [model.predict_step(batch, i).cpu() for i, batch in enumerate(DevicePrefetcher(loader, dev))]
+
+
+def _oracle_fit_predict(kw, batch_size, sd, loader):
+    om = O.OracleModel(**kw)
+    om.batch_size = batch_size
+    om.load_state_dict(sd)
+    opt = torch.optim.Adam(om.parameters(), lr=0.0005)
+    losses = []
+    for batch in loader:
+        opt.zero_grad()
+        r = om.step_losses(batch)
+        r["nmae"].backward()
+        opt.step()
+        losses.append(float(r["nmae"].detach()))
+    with torch.no_grad():
+        val = [float(om.step_losses(batch)["nmae"]) for batch in loader]
+        preds = [om(batch) for batch in loader]
+    return losses, val, preds
+
+
+@pytest.mark.parametrize("name,precision", [("test_yaml_pv", "fp32"), ("nwp_pv_small", "fp32"), ("nwp_pv_small", "bf16")])
+def test_fit_then_predict_like_the_reference_trainer_test(dev, name, precision):
+    from predict_pv_yield_b200.models.conv3d.model import Model
+
+    case = CASES[name]
+    kw, B = case["model"], case["batch"]
+    loader = torch.utils.data.DataLoader(_FakeDataset(kw, B, N_STEPS), batch_size=None)
+
+    model = Model(**kw, precision=precision).to(dev)
+    model.batch_size = B
+    sd = golden_state_dict(model)
+    model.load_state_dict(sd)
+
+    losses, val = _fit(model, loader, dev)
+    preds = _predict(model, loader, dev)
+
+    # the reference test's own checks (test_conv3d_model.py:34-37): one forecast per sample, forecast_len_5 wide
+    assert len(preds) == N_STEPS
+    for y in preds:
+        assert y.dim() == 2 and y.shape[0] == B and y.shape[1] == model.forecast_len
+        assert bool(torch.isfinite(y).all())
+    assert len(losses) == N_STEPS and len(val) == N_STEPS
+    assert set(model.logged_metrics) >= {"MSE/Train", "NMAE/Train", "MSE_EXP/Train", "MAE_EXP/Train", "NMAE/Validation"}
+
+    want_losses, want_val, want_preds = _oracle_fit_predict(kw, B, sd, loader)
+    tol0, tol_traj, tol_pred = (1e-5, 2e-4, 2e-3) if precision == "fp32" else (2e-2, 5e-2, 5e-2)
+    for i, (a, b) in enumerate(zip(losses, want_losses)):
+        rel = abs(a - b) / abs(b)
+        print(f"{name} {precision} train step {i}: loss {a:.7f} oracle {b:.7f} rel {rel:.2e}")
+        assert rel <= (tol0 if i == 0 else tol_traj), (i, a, b)
+    for i, (a, b) in enumerate(zip(val, want_val)):
+        rel = abs(a - b) / abs(b)
+        print(f"{name} {precision} validation batch {i}: loss {a:.7f} oracle {b:.7f} rel {rel:.2e}")
+        assert rel <= tol_traj, (i, a, b)
+    for i, (y, w) in enumerate(zip(preds, want_preds)):
+        e = O.normalised_max_err(y, w)
+        print(f"{name} {precision} predict batch {i}: normalised max err {e:.2e}")
+        assert e <= tol_pred, (i, e)
+    # the fit moved the model: the last training loss of a 4-step fit on fresh batches need not fall, but the weights
+    # must differ from the initial ones in every parameter tensor (no parameter skipped by the fused optimiser)
+    for k, p in model.state_dict().items():
+        assert not torch.equal(p.cpu(), sd[k]), k
