@@ -7,12 +7,15 @@ on one device with the model's own hooks (``configure_optimizers``, ``training_s
 ``predict_step``) and nothing else.  On top of the reference's shape checks, the same loop is run by the oracle on the CPU
 (torch.optim.Adam, lr 5e-4, ``base_model.py:255-257``) and the loss trajectory and the forecasts after the fit are compared.
 
-Tolerances: step 0 at the forward gate (1e-5 fp32 / 2e-2 bf16).  Later steps see weights that went through Adam, whose
-first updates are ~lr * sign(g): a gradient entry at rounding-noise level may move its weight the other way (see
-test_gpu_model.py::test_model_matches_reference_golden), so the trajectory is gated at 2e-4 / 5e-2 of the loss and the
-forecasts after the fit at 2e-3 / 5e-2 of their largest magnitude (torch's own fp32 loop sits 1e-6 / 1e-4 from the fp64
-loop on these cases) -- a dropped layer, a stale shadow weight or an optimiser that skips a parameter moves them by tens
-of percent.
+Tolerances.  fp32 mode against the fp32 oracle: step 0 at the forward gate (1e-5).  Later steps see weights that went
+through Adam, whose first updates are ~lr * sign(g): a gradient entry at rounding-noise level may move its weight the other
+way (see test_gpu_model.py::test_model_matches_reference_golden), so the trajectory is gated at 2e-4 of the loss and the
+forecasts after the fit at 2e-3 of their largest magnitude (measured 2.5e-5 / 3.9e-4; torch's own fp32 loop sits 1e-6 /
+1e-4 from the fp64 loop on these cases).  bf16 mode: the same amplification acts on bf16 rounding -- after four steps the
+fp64 model that rounds where the bf16 path rounds (``oracle.Bf16EmulatedOracle``) is 5e-2 (loss) / 1.6e-1 (forecast) away
+from the fp32 loop, and so is the device (4e-2 / 1.3e-1) -- so bf16 is gated against THAT model's loop (measured 5.6e-3 on
+the training losses, 1.2e-2 on the validation losses, 3.3e-2 on the forecasts; gates 3e-2 / 5e-2 / 1e-1), with the first step also within the north star's 2e-2 of the fp32
+oracle.  A dropped layer, a stale shadow weight or an optimiser that skips a parameter moves all of these by tens of percent.
 """
 import pytest
 import torch
@@ -23,6 +26,9 @@ from oracle.golden_cases import CASES, golden_state_dict, seq_len_of
 pytestmark = pytest.mark.gpu
 
 N_STEPS = 4
+
+# precision -> gates of (first training loss, later training losses, validation losses, forecasts after the fit)
+TOL = {"fp32": (1e-5, 2e-4, 2e-4, 2e-3), "bf16": (1e-3, 3e-2, 5e-2, 1e-1)}
 
 
 @pytest.fixture(scope="module")
@@ -79,21 +85,29 @@ def _predict(model, loader, dev):
     return [model.predict_step(batch, i).cpu() for i, batch in enumerate(DevicePrefetcher(loader, dev))]
 
 
-def _oracle_fit_predict(kw, batch_size, sd, loader):
-    om = O.OracleModel(**kw)
+def _oracle_fit_predict(kw, batch_size, sd, loader, emulate_bf16: bool = False):
+    """The same fit / validate / predict loop on the CPU: the fp32 oracle, or (``emulate_bf16``) the fp64 model that rounds
+    to bf16 wherever the bf16 mode stores bf16 (``oracle.Bf16EmulatedOracle``)."""
+    if emulate_bf16:
+        om = O.Bf16EmulatedOracle(**kw).double()
+        sd = {k: v.double() for k, v in sd.items()}
+        cast = lambda b: O.batch_to(b, float_dtype=torch.float64)  # noqa: E731
+    else:
+        om = O.OracleModel(**kw)
+        cast = lambda b: b  # noqa: E731
     om.batch_size = batch_size
     om.load_state_dict(sd)
     opt = torch.optim.Adam(om.parameters(), lr=0.0005)
     losses = []
     for batch in loader:
         opt.zero_grad()
-        r = om.step_losses(batch)
+        r = om.step_losses(cast(batch))
         r["nmae"].backward()
         opt.step()
         losses.append(float(r["nmae"].detach()))
     with torch.no_grad():
-        val = [float(om.step_losses(batch)["nmae"]) for batch in loader]
-        preds = [om(batch) for batch in loader]
+        val = [float(om.step_losses(cast(batch))["nmae"]) for batch in loader]
+        preds = [om(cast(batch)) for batch in loader]
     return losses, val, preds
 
 
@@ -121,20 +135,20 @@ def test_fit_then_predict_like_the_reference_trainer_test(dev, name, precision):
     assert len(losses) == N_STEPS and len(val) == N_STEPS
     assert set(model.logged_metrics) >= {"MSE/Train", "NMAE/Train", "MSE_EXP/Train", "MAE_EXP/Train", "NMAE/Validation"}
 
-    want_losses, want_val, want_preds = _oracle_fit_predict(kw, B, sd, loader)
-    tol0, tol_traj, tol_pred = (1e-5, 2e-4, 2e-3) if precision == "fp32" else (2e-2, 5e-2, 5e-2)
-    for i, (a, b) in enumerate(zip(losses, want_losses)):
-        rel = abs(a - b) / abs(b)
-        print(f"{name} {precision} train step {i}: loss {a:.7f} oracle {b:.7f} rel {rel:.2e}")
-        assert rel <= (tol0 if i == 0 else tol_traj), (i, a, b)
-    for i, (a, b) in enumerate(zip(val, want_val)):
-        rel = abs(a - b) / abs(b)
-        print(f"{name} {precision} validation batch {i}: loss {a:.7f} oracle {b:.7f} rel {rel:.2e}")
-        assert rel <= tol_traj, (i, a, b)
-    for i, (y, w) in enumerate(zip(preds, want_preds)):
-        e = O.normalised_max_err(y, w)
-        print(f"{name} {precision} predict batch {i}: normalised max err {e:.2e}")
-        assert e <= tol_pred, (i, e)
+    want_losses, want_val, want_preds = _oracle_fit_predict(kw, B, sd, loader, emulate_bf16=(precision == "bf16"))
+    tol0, tol_traj, tol_val, tol_pred = TOL[precision]
+    rel = lambda a, b: abs(a - b) / abs(b)  # noqa: E731
+    e_train = [rel(a, b) for a, b in zip(losses, want_losses)]
+    e_val = [rel(a, b) for a, b in zip(val, want_val)]
+    e_pred = [O.normalised_max_err(y, w) for y, w in zip(preds, want_preds)]
+    print(f"{name} {precision} train losses {losses}\n  against the oracle loop: train {e_train}\n  validation {e_val}\n  forecasts {e_pred}")
+    if precision == "bf16":  # north star: the bf16 forward within 2e-2 of the fp32 reference (first step: identical weights)
+        ref0 = _oracle_fit_predict(kw, B, sd, [next(iter(loader))])[0][0]
+        assert rel(losses[0], ref0) <= 2e-2
+    assert e_train[0] <= tol0, e_train
+    assert max(e_train[1:]) <= tol_traj, e_train
+    assert max(e_val) <= tol_val, e_val
+    assert max(e_pred) <= tol_pred, e_pred
     # the fit moved the model: the last training loss of a 4-step fit on fresh batches need not fall, but the weights
     # must differ from the initial ones in every parameter tensor (no parameter skipped by the fused optimiser)
     for k, p in model.state_dict().items():

@@ -137,11 +137,11 @@ def test_batch_size_attribute_truncates_target_like_reference(dev):
         m.training_step(O.batch_to(golden_batch("test_yaml_pv"), dev), 0)
 
 
-def test_full_size_config2_vs_oracle(dev):
-    """BASELINE config 2 shape at a reduced batch (B=4; the oracle needs seconds on CPU): 12x19x64x64 int16,
-    sat-only, fp32, forward + backward, size-independent checks on top."""
+@pytest.mark.parametrize("B", [4, 32])
+def test_full_size_config2_vs_oracle(dev, B):
+    """BASELINE config 2 shape (12x19x64x64 int16, sat-only, fp32) at B = 4 and at the benchmarked B = 32 (the oracle's
+    forward + backward takes ~1 s on the host cores): forward + backward, size-independent checks on top."""
     kw = dict(include_pv_yield=False, include_nwp=False, forecast_minutes=60, history_minutes=30)
-    B = 4
     torch.manual_seed(518)
     om = O.OracleModel(**kw)
     om.batch_size = B
@@ -162,7 +162,7 @@ def test_full_size_config2_vs_oracle(dev):
         # the conv weights; isolated kernels are gated at 1e-4 in test_gpu_kernels.py
         assert O.normalised_max_err(p.grad, q.grad) <= _grad_tol(k), k
     # size-independent property: samples are independent -> permuting the batch permutes the forecast
-    perm = torch.tensor([2, 0, 3, 1])
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(B))
     pb = {"satellite": {"data": batch["satellite"]["data"][perm]}, "pv": {"pv_yield": batch["pv"]["pv_yield"][perm]}}
     with torch.no_grad():
         y_perm = m(O.batch_to(pb, dev))
@@ -215,8 +215,8 @@ def test_deep_variant_config5_vs_oracle(dev, precision, tol):
     m.load_state_dict(om.state_dict())
     assert m.cnn_output_size == 32 * 112 * 112 * 3
     batch = O.make_synthetic_batch(1, image_size_pixels=128, seed=3)
-    with torch.no_grad():
-        r = om.step_losses(batch)
+    r = om.step_losses(batch)
+    r["nmae"].backward()
     loss = m.training_step(O.batch_to(batch, dev), 0)
     loss.backward()
     with torch.no_grad():
@@ -224,6 +224,45 @@ def test_deep_variant_config5_vs_oracle(dev, precision, tol):
     assert O.normalised_max_err(y_hat, r["y_hat"]) <= tol
     assert abs(float(loss.detach()) - float(r["nmae"])) <= tol * abs(float(r["nmae"]))
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+    if precision == "bf16":
+        # eight layers of bf16 roundings (and the ReLU decisions they flip) put a bf16 gradient 0.06-0.3 of max|g| from the
+        # fp32 oracle's on this case -- the fp64 model that rounds where the bf16 path rounds (oracle.Bf16EmulatedOracle)
+        # sits exactly there too (sat_conv0.weight: 0.201 against the device's 0.202).  Gate: against THAT model, 2^-4 or
+        # half of its own distance from the fp32 oracle, per tensor (measured: convolutions 2.8e-2 .. 7.7e-2, fully
+        # connected layers <= 4.7e-3, forecast 1.3e-5; profiles/parity_r02_tests.txt).
+        oe = O.Bf16EmulatedOracle(**kw).double()
+        oe.batch_size = 1
+        oe.load_state_dict({k: v.double() for k, v in om.state_dict().items()})
+        re = oe.step_losses(O.batch_to(batch, float_dtype=torch.float64))
+        re["nmae"].backward()
+        worst = []
+        for (k, p), (_, q), (_, qe) in zip(m.named_parameters(), om.named_parameters(), oe.named_parameters()):
+            e, e32, floor = O.normalised_max_err(p.grad, qe.grad), O.normalised_max_err(p.grad, q.grad), O.normalised_max_err(qe.grad, q.grad)
+            gate = max(2.0 ** -4, 0.5 * floor)
+            print(f"config5 bf16 {k}: vs bf16-emulating fp64 {e:.2e} (gate {gate:.2e}), vs fp32 oracle {e32:.2e}, emulation vs fp32 oracle {floor:.2e}")
+            if e > gate:
+                worst.append((k, e, gate))
+        ey = O.normalised_max_err(y_hat, re["y_hat"])
+        print(f"config5 bf16 forecast vs bf16-emulating fp64 {ey:.2e}")
+        assert ey <= 2.0 ** -7
+        assert not worst, worst
+        return
+    # fp32 mode: gradients against the fp64 oracle.  torch's own fp32 step sits 2-4e-3 of max|g| from fp64 on the
+    # convolution weights of this case (ReLU decisions that flip under rounding; 1e-6 where none does), and the CUDA
+    # path flips OTHER decisions at the same rate: the convolution tensors are gated at three times the largest of
+    # torch's distances, the fully connected ones (no flip reaches them) at 1e-5 or three times torch's distance.
+    o64 = O.OracleModel(**kw).double()
+    o64.batch_size = 1
+    o64.load_state_dict({k: v.double() for k, v in om.state_dict().items()})
+    r64 = o64.step_losses(O.batch_to(batch, float_dtype=torch.float64))
+    r64["nmae"].backward()
+    floors = {k: O.normalised_max_err(q.grad, q64.grad) for (k, q), (_, q64) in zip(om.named_parameters(), o64.named_parameters())}
+    conv_gate = 3.0 * max(v for k, v in floors.items() if "conv" in k)
+    for (k, p), (_, q64) in zip(m.named_parameters(), o64.named_parameters()):
+        e = O.normalised_max_err(p.grad, q64.grad)
+        gate = conv_gate if "conv" in k else max(1e-5, 3.0 * floors[k])
+        print(f"config5 fp32 {k}: cuda-vs-fp64 {e:.2e}  torch32-vs-fp64 {floors[k]:.2e}  gate {gate:.2e}")
+        assert e <= gate, (k, e, gate)
 
 
 def test_device_prefetcher_preserves_batches(dev):
