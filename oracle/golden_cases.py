@@ -42,6 +42,23 @@ CASES = {
                    output_variable="gsp_yield"),
         batch=2,
     ),
+    # edges none of the yaml-shaped cases reach: ONLY the PV-history branch (fc3 in = 384), 16 channels (the fp32 mode's
+    # 3xTF32 kernels instead of the fp16 split), an odd crop (17 -> 13x13 planes) and an odd number of positions per
+    # channel (9 * 13 * 13 = 1521: the scalar tail of the fused Adam + shadow kernel), two layers, hist 30 / fcst 30 => T=13
+    "pv_only_odd": dict(
+        model=dict(include_pv_yield=True, include_nwp=False, forecast_minutes=30, history_minutes=30,
+                   number_of_conv3d_layers=2, conv3d_channels=16, image_size_pixels=17, number_sat_channels=12,
+                   fc1_output_features=128, fc2_output_features=128, fc3_output_features=64),
+        batch=3,
+    ),
+    # ONLY the NWP branch (fc3 in = 256) behind a ONE-layer encoder (model.py:86-90: the loop over conv3d_1.. is empty):
+    # no data gradient at all, sat_conv0 feeds fc1 directly; 11 channels, 12x12 crops
+    "nwp_only_one_layer": dict(
+        model=dict(include_pv_yield=False, include_nwp=True, forecast_minutes=60, history_minutes=30,
+                   number_of_conv3d_layers=1, conv3d_channels=32, image_size_pixels=12, number_sat_channels=11,
+                   fc1_output_features=64, fc2_output_features=32, fc3_output_features=16),
+        batch=2,
+    ),
 }
 
 # ---- the two-tower model (predict_pv_yield/models/conv3d/model_sat_nwp.py) ---------------------

@@ -2,7 +2,7 @@
 
 Run in the build container (where ``/root/reference`` exists):
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py [case ...]
 
 For every case in ``oracle/golden_cases.py`` it imports the reference ``Model``
 (``/root/reference/predict_pv_yield/models/conv3d/model.py``, through ``oracle/ref_shims.py``),
@@ -98,6 +98,13 @@ def normalise_digest() -> str:
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # the reference's conv wgrad is thread-count dependent at the 1e-5 level
+    only = sys.argv[1:]  # optional: names of the cases to (re)generate; default = every fixture
+    if only:
+        for name in only:
+            res = run_maxpool_case(name) if name in MAXPOOL_CASES else run_case(name)
+            np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **res)
+            print(name, "written")
+        return
     for name in list(CASES) + list(SAT_NWP_CASES):
         res = run_case(name)
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **res)

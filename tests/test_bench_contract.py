@@ -79,3 +79,19 @@ def test_committed_bench_lines_and_traffic_table():
         if line["n_gpus"] == 1:
             assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["value"] > 0, fn
         assert "c3_bf16" in line and line["c3_bf16"]["weak"]["value"] > 0, fn
+
+
+@pytest.mark.parametrize("cfg,params", [("c1", 141_414_732), ("c3", 141_536_716), ("c5", 154_370_508)])
+def test_parameter_counts_of_the_benchmarked_models(cfg, params):
+    """``config.params`` of the bench line: SURVEY.md section 8 (probe of the unmodified reference: 141 414 732 for the
+    default model, 141 536 716 with the NWP + PV-history branches, 154 370 508 for the deep variant) == bench.n_params ==
+    the oracle model built on the meta device (no allocation)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import conv3d_oracle as O
+
+    kw = bench.CONFIGS[cfg]["model"]
+    assert bench.n_params(kw) == params
+    with torch.device("meta"):
+        m = O.OracleModel(**kw)
+    assert sum(p.numel() for p in m.parameters()) == params

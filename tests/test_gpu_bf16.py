@@ -213,7 +213,7 @@ def test_normalise_blocked_bf16_exhaustive_table_path(ops, dev):
             assert torch.equal(got[b, :, t].view(torch.int16), want[0, :, 0].view(torch.int16))
 
 
-@pytest.mark.parametrize("name", ["nwp_pv_small", "test_yaml_pv"])
+@pytest.mark.parametrize("name", ["nwp_pv_small", "test_yaml_pv", "pv_only_odd"])
 def test_bf16_model_within_tolerance_of_oracle(dev, name):
     """North star: bf16 loss / forecast within 2e-2 of the torch reference (normalised max error)."""
     from oracle.golden_cases import CASES, golden_batch, golden_state_dict
@@ -312,17 +312,18 @@ def test_fc1_bf16_kernels(ops, dev, case):
     assert torch.equal(gzw, ops.to_gzw_bf16(got))
 
 
-def test_bf16_shadow_tracks_weight_updates(dev):
+@pytest.mark.parametrize("name", ["nwp_pv_small", "pv_only_odd"])
+def test_bf16_shadow_tracks_weight_updates(dev, name):
     """The tensor-core shadow of fc1.weight must follow every way the master weight can change: FusedAdam's fused
     update, an Adam step by a foreign optimiser, and in-place edits / load_state_dict through torch."""
     from oracle.golden_cases import CASES, golden_batch, golden_state_dict
     from predict_pv_yield_b200.models.conv3d.model import Model
 
-    case = CASES["nwp_pv_small"]
+    case = CASES[name]
     m = Model(**case["model"], precision="bf16").to(dev)
     m.batch_size = case["batch"]
     m.load_state_dict(golden_state_dict(m))
-    batch = O.batch_to(golden_batch("nwp_pv_small"), dev)
+    batch = O.batch_to(golden_batch(name), dev)
 
     def fresh_forward():
         ref = Model(**case["model"], precision="bf16").to(dev)  # a model that has never cached anything
@@ -354,14 +355,15 @@ def test_bf16_shadow_tracks_weight_updates(dev):
         assert torch.equal(m(batch), fresh_forward())
 
 
+@pytest.mark.parametrize("thw", [(3, 5, 6), (3, 5, 5)])  # 75 positions per channel: the scalar path of an odd T*H*W
 @pytest.mark.parametrize("nshards", [2, 8])
-def test_adam_fc1_row_shards_equal_the_fused_update(dev, nshards):
+def test_adam_fc1_row_shards_equal_the_fused_update(dev, nshards, thw):
     """Optimiser sharded by output feature (data parallel): the row-wise Adam kernel run once per shard + the shard
     interleave must reproduce the fused full update (weights, moments AND the bf16 shadow) bit for bit."""
     from predict_pv_yield_b200 import lib
 
     L = lib.load()
-    F1, Cg, T, H, W = 128, 2, 3, 5, 6
+    F1, Cg, (T, H, W) = 128, 2, thw
     KG = Cg * T * H * W
     K1 = KG * 8
     g = torch.Generator().manual_seed(11)
@@ -395,6 +397,12 @@ def test_adam_fc1_row_shards_equal_the_fused_update(dev, nshards):
     p.grad = grad * hyper[5]
     opt.step()
     assert O.normalised_max_err(wb, p.detach()) <= 1e-6
+    # every element moved (an update that skipped the odd positions would leave half of them at their old values), and
+    # the shadow written by the fused pass is the bf16 image of the UPDATED weights in the [kg][128][8] order
+    assert float((wa != w0).float().mean()) > 0.999
+    shadow = sha.view(torch.bfloat16).view(KG, 128, 8)
+    want = wa.view(F1, Cg, 8, T * H * W).permute(1, 3, 0, 2).reshape(KG, F1, 8).to(torch.bfloat16)
+    assert torch.equal(shadow[:, :F1], want)
 
 
 def test_fc1_bf16_forward_batch_256_and_training_limit(ops, dev):
