@@ -36,6 +36,57 @@ def test_library_exports_every_declared_symbol(built):
     assert L.pvb200_abi_version() == 1
 
 
+def _c_kind(decl: str, named: bool = True) -> str:
+    """C parameter (``named``) / return declaration -> the ctypes class it must be bound as."""
+    d = re.sub(r"/\*.*?\*/", " ", decl).strip()
+    if d.endswith("pvb200_stream_t") or re.search(r"\bpvb200_stream_t\s+\w+$", d):
+        return "c_void_p"
+    if "*" in d:
+        if re.match(r"(const\s+)?char\s*\*$", d):
+            return "c_char_p"
+        if re.match(r"double\s*\*", d):
+            return "LP_c_double"
+        return "c_void_p"  # every other pointer (device or host) is passed as an address
+    if named:
+        d = re.sub(r"\s+\w+$", "", d)  # drop the parameter name
+    d = re.sub(r"\bconst\b", "", d).strip()
+    return {"int": "c_int", "long long": "c_longlong", "unsigned long long": "c_ulonglong", "size_t": "c_size_t",
+            "float": "c_float", "double": "c_double", "void": "None"}[d]
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """ABI drift guard: argument count and C type of every prototype in include/pvb200.h == lib.SIGNATURES (a c_int bound
+    where the header says long long, or a missing argument, corrupts the call silently)."""
+    from predict_pv_yield_b200 import lib
+
+    header = open(os.path.join(ROOT, "include", "pvb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"^\s*((?:const\s+)?(?:unsigned\s+)?[a-z_]+(?:\s+long)?(?:\s*\*)?)\s*(pvb200_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header, flags=re.M)
+    assert len(protos) == len(lib.SIGNATURES), (len(protos), len(lib.SIGNATURES))
+
+    def name_of(t):
+        if t is None:
+            return "None"
+        n = t.__name__
+        return {"c_long": "c_longlong", "c_ulong": "c_ulonglong"}.get(n, n) if ctypes.sizeof(ctypes.c_long) == 8 else n
+
+    for ret, name, args in protos:
+        restype, argtypes = lib.SIGNATURES[name]
+        assert name_of(restype) in (_c_kind(ret, False), {"c_size_t": "c_ulonglong"}.get(_c_kind(ret, False), "")), (name, ret, restype)
+        params = [a.strip() for a in args.split(",")] if args.strip() not in ("", "void") else []
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for i, (a, t) in enumerate(zip(params, argtypes)):
+            want, got = _c_kind(a), name_of(t)
+            if want == "c_size_t" or got == "c_size_t":  # ctypes aliases c_size_t to c_ulong on LP64
+                want, got = want.replace("c_size_t", "c_ulonglong"), got.replace("c_size_t", "c_ulonglong")
+            if a.replace(" ", "").startswith("constpvb200_head_t*") or a.replace(" ", "").startswith("pvb200_head_t*"):
+                assert got in ("c_void_p", "LP_Head"), (name, i, a, got)
+                continue
+            if want in ("c_void_p", "LP_c_double") and got.startswith("LP_"):  # typed host pointers (arrays of pointers, out-parameters)
+                continue
+            assert want == got, (name, i, a, got)
+
+
 def test_head_struct_layout_matches_header(built, tmp_path):
     """sizeof/offsetof of the ctypes mirror == the C compiler's view of pvb200_head_t."""
     from predict_pv_yield_b200 import lib
