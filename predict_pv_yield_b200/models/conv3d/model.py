@@ -157,6 +157,14 @@ class Model(BaseModel):
 
         wait_ready(self.fc1.weight)
 
+    def invalidate_shadow(self) -> None:
+        """bf16 mode: force the tensor-core shadow of ``fc1.weight`` to be rebuilt by the next forward.  The shadow follows
+        ``load_state_dict``, in-place edits of the parameter and optimiser steps by itself (``ops.Fc1Shadow``); writes
+        through ``fc1.weight.data`` (EMA / SWA weight swaps, custom initialisers) do not bump the parameter's version
+        counter, so call this after them.  Under a row-sharded optimiser (``dp.GradientExchange(shard_large=True)``) gather the master rows
+        first (``gather_master_weights()``): the rebuild reads the fp32 master."""
+        self._fc1_shadow.key = None
+
     def _conv_params(self):
         wb = [self.sat_conv0.weight, self.sat_conv0.bias]
         for i in range(0, self.number_of_conv3d_layers - 1):

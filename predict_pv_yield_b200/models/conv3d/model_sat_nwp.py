@@ -191,6 +191,12 @@ class Model(BaseModel):
                 f"predict_pv_yield_b200 conv3d_sat_nwp is CUDA (sm_100a) only: {what} is on {t.device} (there is no CPU fallback)"
             )
 
+    def invalidate_shadow(self) -> None:
+        """bf16 mode: force the tensor-core shadows of ``fc1.weight`` / ``nwp_fc1.weight`` to be rebuilt by the next forward
+        (needed only after writes through ``.data``, which torch's version counter does not see; ``ops.Fc1Shadow``)."""
+        self._fc1_shadow.key = None
+        self._nwp_fc1_shadow.key = None
+
     def forward(self, x):
         x = as_batch(x)
 

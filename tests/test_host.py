@@ -247,3 +247,29 @@ def test_split_precision_shape_rules(built):
     assert not ops.conv_f16x2_applies(24, 32)    # one and a half
     assert not ops.conv_f16x2_applies(32, 16)    # single-CTA kernel (Cout <= 16)
     assert ops.tf32x3_supported(32, 32) and not ops.tf32x3_supported(33, 32) and not ops.tf32x3_supported(32, 64)
+
+
+def test_invalidate_shadow_forces_a_rebuild_of_the_bf16_copy():
+    """writes through ``fc1.weight.data`` do not bump the parameter's version counter, so the staleness key
+    of the tensor-core shadow cannot see them -- ``Model.invalidate_shadow()`` is the explicit switch (both models)."""
+    from predict_pv_yield_b200.models.conv3d.model import Model
+    from predict_pv_yield_b200.models.conv3d.model_sat_nwp import Model as SatNwp
+    from oracle.golden_cases import CASES, SAT_NWP_CASES
+
+    m = Model(**CASES["test_yaml_pv"]["model"], precision="bf16")
+    w = m.fc1.weight
+    assert w._pvb_shadow is m._fc1_shadow
+    key = m._fc1_shadow._key(w)
+    m._fc1_shadow.key = key
+    w.data.mul_(0.5)  # invisible to the key ...
+    assert m._fc1_shadow._key(w) == key
+    with torch.no_grad():
+        w.mul_(0.5)  # ... while an in-place edit of the parameter itself is not
+    assert m._fc1_shadow._key(w) != key
+    m._fc1_shadow.key = m._fc1_shadow._key(w)
+    m.invalidate_shadow()
+    assert m._fc1_shadow.key is None
+    s = SatNwp(**SAT_NWP_CASES["sat_nwp_pv"]["model"], precision="bf16")
+    s._fc1_shadow.key = s._nwp_fc1_shadow.key = ("x",)
+    s.invalidate_shadow()
+    assert s._fc1_shadow.key is None and s._nwp_fc1_shadow.key is None
