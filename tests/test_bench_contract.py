@@ -95,3 +95,23 @@ def test_parameter_counts_of_the_benchmarked_models(cfg, params):
     with torch.device("meta"):
         m = O.OracleModel(**kw)
     assert sum(p.numel() for p in m.parameters()) == params
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """The driver launches both arms the same way (torchrun for N > 1): rank 0 alone times the CPU reference and prints
+    the line, the other ranks exit 0 without work and without output."""
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--gpus", "2", "--steps", "1", "--warmup", "1"], cwd=ROOT, env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
