@@ -20,7 +20,10 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, overlap_large: bool = False):
         if lr < 0.0 or eps < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
             raise ValueError("FusedAdam: invalid hyper-parameter")
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        # weight_decay / amsgrad / maximize are carried at torch.optim.Adam's defaults (the reference's settings,
+        # base_model.py:256) so that a FusedAdam checkpoint resumes under torch.optim.Adam and the reverse; step() refuses
+        # any other value (e.g. from a checkpoint trained with weight decay) instead of silently ignoring it
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0.0, amsgrad=False, maximize=False))
         self.grad_scale = 1.0
         self.pre_step_hook: Optional[Callable[[], None]] = None  # e.g. wait for the gradient all-reduce
         # The update of a LARGE parameter (fc1.weight: 141 M elements, 4 GB of HBM traffic, ~0.75 ms) is HBM bound and its
@@ -45,6 +48,9 @@ class FusedAdam(torch.optim.Optimizer):
         if self.pre_step_hook is not None:
             self.pre_step_hook()
         for group in self.param_groups:
+            if group.get("weight_decay", 0.0) != 0.0 or group.get("amsgrad", False) or group.get("maximize", False):
+                raise RuntimeError("FusedAdam implements torch.optim.Adam with weight_decay=0, amsgrad=False, maximize=False "
+                                   "(the reference's optimiser, base_model.py:255-257); this parameter group asks for more")
             ps, gs, ms, vs = [], [], [], []
             step = None
             for p in group["params"]:

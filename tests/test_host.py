@@ -273,3 +273,51 @@ def test_invalidate_shadow_forces_a_rebuild_of_the_bf16_copy():
     s._fc1_shadow.key = s._nwp_fc1_shadow.key = ("x",)
     s.invalidate_shadow()
     assert s._fc1_shadow.key is None and s._nwp_fc1_shadow.key is None
+
+
+def test_optimizer_checkpoints_move_between_fused_adam_and_torch_adam():
+    """Same state names and group keys as ``torch.optim.Adam`` (base_model.py:255-257): a FusedAdam checkpoint resumes under
+    torch's optimiser (and continues exactly like a torch run with the same moments), a torch checkpoint loads into
+    FusedAdam, and settings the kernel does not implement are refused instead of ignored."""
+    from predict_pv_yield_b200.optim import FusedAdam
+
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+    fused = FusedAdam(params, lr=5e-4)
+    for q in params:  # the state FusedAdam.step() keeps: int step, two moments
+        fused.state[q] = {"step": 3, "exp_avg": torch.randn_like(q) * 0.1, "exp_avg_sq": torch.rand_like(q) * 0.01}
+    import copy
+
+    sd = copy.deepcopy(fused.state_dict())  # torch's load_state_dict may alias the tensors it is handed
+    grads = [torch.randn_like(q) for q in params]
+
+    def run(opt_params, loader):
+        opt = torch.optim.Adam(opt_params, lr=1.0)  # every hyper-parameter must come from the checkpoint
+        loader(opt)
+        for q, g in zip(opt_params, grads):
+            q.grad = g.clone()
+        opt.step()
+        return opt
+
+    a_params = [torch.nn.Parameter(q.detach().clone()) for q in params]
+    a = run(a_params, lambda opt: opt.load_state_dict(sd))
+    assert a.param_groups[0]["lr"] == 5e-4 and float(a.state[a_params[0]]["step"]) == 4.0
+    b_params = [torch.nn.Parameter(q.detach().clone()) for q in params]
+
+    def seed_state(opt):
+        opt.param_groups[0]["lr"] = 5e-4
+        for q, src in zip(b_params, params):
+            opt.state[q] = {"step": torch.tensor(3.0), "exp_avg": fused.state[src]["exp_avg"].clone(),
+                            "exp_avg_sq": fused.state[src]["exp_avg_sq"].clone()}
+
+    run(b_params, seed_state)
+    for x, y in zip(a_params, b_params):
+        assert torch.equal(x, y)
+    # torch -> FusedAdam
+    f2 = FusedAdam([torch.nn.Parameter(q.detach().clone()) for q in params], lr=1.0)
+    f2.load_state_dict(a.state_dict())
+    assert f2.param_groups[0]["lr"] == 5e-4 and int(f2.state[f2.param_groups[0]["params"][0]]["step"]) == 4
+    # refused, not ignored
+    f2.param_groups[0]["weight_decay"] = 0.01
+    with pytest.raises(RuntimeError, match="weight_decay"):
+        f2.step()
