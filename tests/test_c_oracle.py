@@ -127,3 +127,62 @@ def test_adam_two_steps_match_torch(lib):
                           ctypes.c_float(0.999), ctypes.c_float(1e-8), step)
         want = pt_.detach().numpy()
         assert np.abs(p - want).max() <= 2e-7 * np.abs(want).max() + 1e-9, (step, np.abs(p - want).max())
+
+
+@pytest.mark.parametrize("name", ["test_yaml_pv", "test_yaml_gsp", "nwp_pv_small", "pv_only_odd", "nwp_only_one_layer"])
+def test_torch_free_forward_reproduces_the_reference_golden(lib, name):
+    """The whole forward of the path (model.py:107-156) and the returned loss (base_model.py:90-98), composed from the plain-C
+    operators (scalar loops, double accumulation) with numpy for the glue (nan_to_num, concat, slices) -- no torch in the
+    arithmetic -- against ``y_hat`` / ``nmae`` recorded from the UNMODIFIED reference (tests/golden/, oracle/make_golden.py).
+    A second, library-independent pin of the oracle: flatten order, Linear layout, branch order of the concat, target slice."""
+    from oracle import conv3d_oracle as O
+    from oracle.golden_cases import CASES, golden_batch, golden_state_dict
+
+    case = CASES[name]
+    kw, B = case["model"], case["batch"]
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz")))
+    om = O.OracleModel(**kw)  # only for the state_dict key order / shapes of golden_state_dict and the derived sizes
+    sd = {k: v.numpy() for k, v in golden_state_dict(om).items()}
+    batch = golden_batch(name)
+
+    # a1: int16 normalisation (netcdf_dataset.py:96-101)
+    sat = np.ascontiguousarray(batch["satellite"]["data"].numpy())
+    _, C, T, H, W = sat.shape
+    mean, std = (a.copy() for a in O.sat_constants(C))
+    x = np.empty(sat.shape, np.float32)
+    lib.ora_sat_normalise(_p(sat), _p(x), _p(mean), _p(std), B, C, ctypes.c_long(T * H * W))
+
+    # a3, a4: Conv3d + ReLU stack (model.py:117-120)
+    L = kw["number_of_conv3d_layers"]
+    for layer in range(L):
+        key = "sat_conv0" if layer == 0 else f"conv3d_{layer}"
+        w, b = np.ascontiguousarray(sd[key + ".weight"]), np.ascontiguousarray(sd[key + ".bias"])
+        Co, Ci = w.shape[0], w.shape[1]
+        y = np.empty((B, Co, T - 2, H - 2, W - 2), np.float32)
+        lib.ora_conv3d_relu(_p(x), _p(w), _p(b), _p(y), B, Ci, T, H, W, Co, 1)
+        x, T, H, W = y, T - 2, H - 2, W - 2
+
+    def linear(inp, key, relu):
+        w, b = np.ascontiguousarray(sd[key + ".weight"]), np.ascontiguousarray(sd[key + ".bias"])
+        inp = np.ascontiguousarray(inp, np.float32)
+        out = np.empty((inp.shape[0], w.shape[0]), np.float32)
+        lib.ora_linear(_p(inp), _p(w), _p(b), _p(out), inp.shape[0], ctypes.c_long(w.shape[1]), w.shape[0], int(relu))
+        return out
+
+    # a5, a6: NCDHW flatten, fc1, fc2 (model.py:122-126)
+    out = linear(linear(x.reshape(B, -1), "fc1", True), "fc2", True)
+    var = kw.get("output_variable", "pv_yield")
+    if kw["include_pv_yield"]:  # a7 (model.py:130-136)
+        hist = np.nan_to_num(batch[var].numpy()[:, : om.history_len_30 + 1], nan=0.0).astype(np.float32)
+        out = np.concatenate([out, hist.reshape(B, -1)], axis=1)
+    if kw["include_nwp"]:  # a8 (model.py:139-148)
+        out = np.concatenate([out, linear(batch["nwp"].numpy().reshape(B, -1), "fc_nwp", True)], axis=1)
+    y_hat = linear(linear(out, "fc3", True), "fc4", False).reshape(B, om.forecast_len)  # a9 (model.py:151-154)
+    _close(y_hat, g["y_hat"], tol=1e-5)
+
+    # a10: target slice and the returned L1 loss (base_model.py:90-98)
+    target = batch["pv" if var == "pv_yield" else "gsp"][var].numpy()[0:B, -om.forecast_len:, 0].astype(np.float32)
+    target = np.ascontiguousarray(target)
+    lib.ora_l1_loss.restype = ctypes.c_float
+    nmae = lib.ora_l1_loss(_p(np.ascontiguousarray(y_hat)), _p(target), ctypes.c_long(y_hat.size))
+    assert abs(nmae - float(g["nmae"])) <= 1e-5 * abs(float(g["nmae"]))
