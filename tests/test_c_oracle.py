@@ -129,21 +129,19 @@ def test_adam_two_steps_match_torch(lib):
         assert np.abs(p - want).max() <= 2e-7 * np.abs(want).max() + 1e-9, (step, np.abs(p - want).max())
 
 
-@pytest.mark.parametrize("name", ["test_yaml_pv", "test_yaml_gsp", "nwp_pv_small", "pv_only_odd", "nwp_only_one_layer"])
-def test_torch_free_forward_reproduces_the_reference_golden(lib, name):
-    """The whole forward of the path (model.py:107-156) and the returned loss (base_model.py:90-98), composed from the plain-C
-    operators (scalar loops, double accumulation) with numpy for the glue (nan_to_num, concat, slices) -- no torch in the
-    arithmetic -- against ``y_hat`` / ``nmae`` recorded from the UNMODIFIED reference (tests/golden/, oracle/make_golden.py).
-    A second, library-independent pin of the oracle: flatten order, Linear layout, branch order of the concat, target slice."""
+def _torch_free_step(lib, name):
+    """Forward, returned L1 loss and backward of the whole path from the plain-C operators (scalar loops, double accumulation)
+    with numpy for the glue (nan_to_num, concat / split, ReLU masks, slices): no torch in the arithmetic.
+    Returns (y_hat, nmae, {parameter name: gradient})."""
     from oracle import conv3d_oracle as O
     from oracle.golden_cases import CASES, golden_batch, golden_state_dict
 
     case = CASES[name]
     kw, B = case["model"], case["batch"]
-    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz")))
     om = O.OracleModel(**kw)  # only for the state_dict key order / shapes of golden_state_dict and the derived sizes
-    sd = {k: v.numpy() for k, v in golden_state_dict(om).items()}
+    sd = {k: np.ascontiguousarray(v.numpy()) for k, v in golden_state_dict(om).items()}
     batch = golden_batch(name)
+    c32 = lambda a: np.ascontiguousarray(a, np.float32)  # noqa: E731
 
     # a1: int16 normalisation (netcdf_dataset.py:96-101)
     sat = np.ascontiguousarray(batch["satellite"]["data"].numpy())
@@ -154,35 +152,104 @@ def test_torch_free_forward_reproduces_the_reference_golden(lib, name):
 
     # a3, a4: Conv3d + ReLU stack (model.py:117-120)
     L = kw["number_of_conv3d_layers"]
-    for layer in range(L):
-        key = "sat_conv0" if layer == 0 else f"conv3d_{layer}"
-        w, b = np.ascontiguousarray(sd[key + ".weight"]), np.ascontiguousarray(sd[key + ".bias"])
-        Co, Ci = w.shape[0], w.shape[1]
-        y = np.empty((B, Co, T - 2, H - 2, W - 2), np.float32)
-        lib.ora_conv3d_relu(_p(x), _p(w), _p(b), _p(y), B, Ci, T, H, W, Co, 1)
-        x, T, H, W = y, T - 2, H - 2, W - 2
+    conv_keys = ["sat_conv0"] + [f"conv3d_{i}" for i in range(1, L)]
+    acts = [x]  # acts[l] = input of layer l, acts[L] = last activation
+    for key in conv_keys:
+        w, b = sd[key + ".weight"], sd[key + ".bias"]
+        xin = acts[-1]
+        _, Ci, T, H, W = xin.shape
+        y = np.empty((B, w.shape[0], T - 2, H - 2, W - 2), np.float32)
+        lib.ora_conv3d_relu(_p(xin), _p(w), _p(b), _p(y), B, Ci, T, H, W, w.shape[0], 1)
+        acts.append(y)
 
     def linear(inp, key, relu):
-        w, b = np.ascontiguousarray(sd[key + ".weight"]), np.ascontiguousarray(sd[key + ".bias"])
-        inp = np.ascontiguousarray(inp, np.float32)
+        w, b = sd[key + ".weight"], sd[key + ".bias"]
         out = np.empty((inp.shape[0], w.shape[0]), np.float32)
         lib.ora_linear(_p(inp), _p(w), _p(b), _p(out), inp.shape[0], ctypes.c_long(w.shape[1]), w.shape[0], int(relu))
         return out
 
     # a5, a6: NCDHW flatten, fc1, fc2 (model.py:122-126)
-    out = linear(linear(x.reshape(B, -1), "fc1", True), "fc2", True)
+    feats = c32(acts[-1].reshape(B, -1))
+    h1 = linear(feats, "fc1", True)
+    h2 = linear(h1, "fc2", True)
+    parts = [h2]
     var = kw.get("output_variable", "pv_yield")
     if kw["include_pv_yield"]:  # a7 (model.py:130-136)
         hist = np.nan_to_num(batch[var].numpy()[:, : om.history_len_30 + 1], nan=0.0).astype(np.float32)
-        out = np.concatenate([out, hist.reshape(B, -1)], axis=1)
+        parts.append(hist.reshape(B, -1))
     if kw["include_nwp"]:  # a8 (model.py:139-148)
-        out = np.concatenate([out, linear(batch["nwp"].numpy().reshape(B, -1), "fc_nwp", True)], axis=1)
-    y_hat = linear(linear(out, "fc3", True), "fc4", False).reshape(B, om.forecast_len)  # a9 (model.py:151-154)
-    _close(y_hat, g["y_hat"], tol=1e-5)
+        nwp_in = c32(batch["nwp"].numpy().reshape(B, -1))
+        nwp_out = linear(nwp_in, "fc_nwp", True)
+        parts.append(nwp_out)
+    cat = c32(np.concatenate(parts, axis=1))
+    h3 = linear(cat, "fc3", True)
+    y_hat = linear(h3, "fc4", False).reshape(B, om.forecast_len)  # a9 (model.py:151-154)
 
     # a10: target slice and the returned L1 loss (base_model.py:90-98)
-    target = batch["pv" if var == "pv_yield" else "gsp"][var].numpy()[0:B, -om.forecast_len:, 0].astype(np.float32)
-    target = np.ascontiguousarray(target)
+    target = c32(batch["pv" if var == "pv_yield" else "gsp"][var].numpy()[0:B, -om.forecast_len:, 0])
     lib.ora_l1_loss.restype = ctypes.c_float
-    nmae = lib.ora_l1_loss(_p(np.ascontiguousarray(y_hat)), _p(target), ctypes.c_long(y_hat.size))
+    nmae = lib.ora_l1_loss(_p(c32(y_hat)), _p(target), ctypes.c_long(y_hat.size))
+
+    # a11: backward of the returned loss
+    grads = {}
+
+    def linear_bwd(gy, inp, key):
+        w = sd[key + ".weight"]
+        gx, dw, db = np.empty_like(inp), np.empty_like(w), np.empty(w.shape[0], np.float32)
+        lib.ora_linear_bwd(_p(c32(gy)), _p(inp), _p(w), _p(gx), _p(dw), _p(db), inp.shape[0], ctypes.c_long(w.shape[1]), w.shape[0])
+        grads[key + ".weight"], grads[key + ".bias"] = dw, db
+        return gx
+
+    g = (np.sign(y_hat - target) / np.float32(y_hat.size)).astype(np.float32)  # d mean|y_hat - y| / d y_hat
+    g = linear_bwd(g, h3, "fc4") * (h3 > 0)
+    g_cat = linear_bwd(g, cat, "fc3")
+    if kw["include_nwp"]:
+        linear_bwd(g_cat[:, -nwp_out.shape[1]:] * (nwp_out > 0), nwp_in, "fc_nwp")  # the NWP input itself needs no gradient
+    g = linear_bwd(g_cat[:, : h2.shape[1]] * (h2 > 0), h1, "fc2") * (h1 > 0)
+    g = linear_bwd(g, feats, "fc1")
+    gz = c32(g.reshape(acts[-1].shape) * (acts[-1] > 0))
+    for layer in range(L - 1, -1, -1):
+        key = conv_keys[layer]
+        w = sd[key + ".weight"]
+        xin = acts[layer]
+        _, Ci, T, H, W = xin.shape
+        dw, db = np.empty_like(w), np.empty(w.shape[0], np.float32)
+        lib.ora_conv3d_wgrad(_p(xin), _p(gz), _p(dw), _p(db), B, Ci, T, H, W, w.shape[0], 0, 0)
+        grads[key + ".weight"], grads[key + ".bias"] = dw, db
+        if layer > 0:
+            gx = np.empty_like(xin)
+            lib.ora_conv3d_dgrad(_p(gz), _p(w), _p(gx), B, Ci, T, H, W, w.shape[0], 0, 0)
+            gz = c32(gx * (xin > 0))  # xin = relu output of the layer below
+    return y_hat, nmae, grads
+
+
+@pytest.mark.parametrize("name", ["test_yaml_pv", "test_yaml_gsp", "nwp_pv_small", "pv_only_odd", "nwp_only_one_layer"])
+def test_torch_free_step_reproduces_the_reference_golden(lib, name):
+    """Against ``y_hat`` / ``nmae`` / ``grad.*`` recorded from the UNMODIFIED reference (tests/golden/, oracle/make_golden.py):
+    a second, library-independent pin of the oracle -- flatten order, Linear layout, branch order of the concat and its
+    split on the way back, ReLU masks, target slice, tap orientation of both convolution gradients.
+    Gradients: the C step accumulates in double, the reference in fp32, and a ReLU decision near zero may differ between
+    them -- on these 2-3 sample batches one flip moves a convolution gradient by 1e-3 of max|g|.  So
+    each tensor is gated at 1e-5 against the fp64 torch oracle (no flips between two double computations), and against the
+    golden at 1e-5 or three times the golden's own distance from that fp64 oracle."""
+    from oracle import conv3d_oracle as O
+    from oracle.golden_cases import CASES, golden_batch, golden_state_dict, thin
+
+    y_hat, nmae, grads = _torch_free_step(lib, name)
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz")))
+    _close(y_hat, g["y_hat"], tol=1e-5)
     assert abs(nmae - float(g["nmae"])) <= 1e-5 * abs(float(g["nmae"]))
+
+    case = CASES[name]
+    o64 = O.OracleModel(**case["model"]).double()
+    o64.batch_size = case["batch"]
+    o64.load_state_dict({k: v.double() for k, v in golden_state_dict(o64).items()})
+    o64.step_losses(O.batch_to(golden_batch(name), float_dtype=torch.float64))["nmae"].backward()
+    nerr = lambda a, b: float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(np.abs(b).max(), 1e-30))  # noqa: E731
+    for k, p in o64.named_parameters():
+        want64 = p.grad.numpy()
+        assert grads[k].shape == want64.shape, k
+        assert nerr(grads[k], want64) <= 1e-5, (k, nerr(grads[k], want64))
+        floor = nerr(g["grad." + k], thin(p.grad))
+        e = nerr(thin(torch.from_numpy(grads[k])), g["grad." + k])
+        assert e <= max(1e-5, 3.0 * floor), (k, e, floor)
