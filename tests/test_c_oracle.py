@@ -240,8 +240,19 @@ def test_torch_free_step_reproduces_the_reference_golden(lib, name):
     g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz")))
     _close(y_hat, g["y_hat"], tol=1e-5)
     assert abs(nmae - float(g["nmae"])) <= 1e-5 * abs(float(g["nmae"]))
-
+    # the three logged-only losses (base_model.py:98-103) in numpy: MSE, and the exponentially weighted pair with the weights
+    # of nowcasting_utils.models.loss.WeightedLosses as restated (w_i ~ exp(-ln2 * i), normalised to mean 1; the package is
+    # absent here, so those two are pinned to the restatement, not to the package)
     case = CASES[name]
+    var = case["model"].get("output_variable", "pv_yield")
+    F_ = y_hat.shape[1]
+    target = golden_batch(name)["pv" if var == "pv_yield" else "gsp"][var].numpy()[0: case["batch"], -F_:, 0].astype(np.float64)
+    d = y_hat.astype(np.float64) - target
+    wts = np.exp(-np.log(2.0) * np.arange(F_))
+    wts = wts / wts.sum() * F_
+    for key, val in (("mse", np.mean(d * d)), ("mse_exp", np.mean(wts * d * d)), ("mae_exp", np.mean(wts * np.abs(d)))):
+        assert abs(val - float(g[key])) <= 1e-5 * abs(float(g[key])), (key, val, float(g[key]))
+
     o64 = O.OracleModel(**case["model"]).double()
     o64.batch_size = case["batch"]
     o64.load_state_dict({k: v.double() for k, v in golden_state_dict(o64).items()})
