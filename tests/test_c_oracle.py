@@ -291,3 +291,67 @@ def test_torch_free_two_adam_steps_reproduce_the_reference_golden(lib, name):
         diff = np.abs(thin(torch.from_numpy(sd[k])).astype(np.float64) - g["adam2." + k].astype(np.float64))
         assert float(np.median(diff)) <= 2e-5, (k, float(np.median(diff)))
         assert float(diff.max()) <= 2.1e-3, (k, float(diff.max()))
+
+
+@pytest.mark.parametrize("name", ["sat_nwp_pv", "sat_nwp_gsp"])
+def test_torch_free_two_tower_forward_reproduces_the_reference_golden(lib, name):
+    """the forward of the two-tower ``conv3d_sat_nwp`` model (model_sat_nwp.py:174-268) and its returned loss
+    from the plain-C operators -- time-padded towers (padding (1, 0, 0)), the no-future-satellite slice, PV history through
+    ``pv_fc1``, the embedding lookup, the order of the five concat blocks -- against ``y_hat`` / ``nmae`` recorded from the
+    unmodified reference class (tests/golden/sat_nwp_*.npz)."""
+    from oracle.golden_cases import SAT_NWP_CASES, golden_state_dict, sat_nwp_batch
+    from oracle.sat_nwp_oracle import OracleSatNwpModel
+    from oracle import conv3d_oracle as O
+
+    case = SAT_NWP_CASES[name]
+    kw, B = case["model"], case["batch"]
+    om = OracleSatNwpModel(**kw)  # state_dict key order / shapes and the derived sizes only
+    sd = {k: np.ascontiguousarray(v.numpy()) for k, v in golden_state_dict(om).items()}
+    batch = sat_nwp_batch(name)
+    c32 = lambda a: np.ascontiguousarray(a, np.float32)  # noqa: E731
+    L = kw["number_of_conv3d_layers"]
+
+    def tower(x, prefix):
+        for i in range(L):
+            w, b = sd[f"{prefix}{i}.weight"], sd[f"{prefix}{i}.bias"]
+            _, Ci, T, H, W = x.shape
+            y = np.empty((B, w.shape[0], T, H - 2, W - 2), np.float32)
+            lib.ora_conv3d_pad(_p(x), _p(w), _p(b), _p(y), B, Ci, T, H, W, w.shape[0], 1, 0, 1)
+            x = y
+        return c32(x.reshape(B, -1))
+
+    def linear(inp, key, relu):
+        w, b = sd[key + ".weight"], sd[key + ".bias"]
+        assert inp.shape[1] == w.shape[1], (key, inp.shape, w.shape)
+        out = np.empty((inp.shape[0], w.shape[0]), np.float32)
+        lib.ora_linear(_p(c32(inp)), _p(w), _p(b), _p(out), inp.shape[0], ctypes.c_long(w.shape[1]), w.shape[0], int(relu))
+        return out
+
+    sat = np.ascontiguousarray(batch["satellite"]["data"].numpy())
+    _, C, T, H, W = sat.shape
+    mean, std = (a.copy() for a in O.sat_constants(C))
+    x = np.empty(sat.shape, np.float32)
+    lib.ora_sat_normalise(_p(sat), _p(x), _p(mean), _p(std), B, C, ctypes.c_long(T * H * W))
+    if not kw["include_future_satellite"]:  # model_sat_nwp.py:183-184
+        x = c32(x[:, :, : om.history_len_5 + 1])
+    parts = [linear(linear(tower(x, "sat_conv"), "fc1", True), "fc2", True)]  # :187-196
+    var = kw["output_variable"]
+    yld = batch["pv" if var == "pv_yield" else "gsp"][var].numpy()
+    if kw["include_pv_or_gsp_yield_history"]:  # :200-216
+        parts.append(np.nan_to_num(yld[:, : om.history_len_30 + 1], nan=0.0).reshape(B, -1))
+    if kw["include_pv_yield_history"]:  # :219-232
+        h = np.nan_to_num(batch["pv"]["pv_yield"].numpy()[:, : om.history_len_5 + 1, :128], nan=0.0).reshape(B, -1)
+        parts.append(linear(h, "pv_fc1", True))
+    if kw["include_nwp"]:  # :235-249
+        n = tower(c32(batch["nwp"]["data"].numpy()), "nwp_conv")
+        parts.append(linear(linear(n, "nwp_fc1", True), "nwp_fc2", True))
+    if kw["embedding_dem"]:  # :252-260
+        ids = (batch["pv"]["pv_system_row_number"] if var == "pv_yield" else batch["gsp"]["gsp_id"]).numpy()[0:B, 0]
+        parts.append(sd["pv_system_id_embedding.weight"][ids])
+    y_hat = linear(linear(np.concatenate([c32(p) for p in parts], axis=1), "fc3", True), "fc4", False)  # :263-266
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz")))
+    _close(y_hat, g["y_hat"], tol=1e-5)
+    target = c32(yld[0:B, -om.forecast_len:, 0])
+    lib.ora_l1_loss.restype = ctypes.c_float
+    nmae = lib.ora_l1_loss(_p(c32(y_hat)), _p(target), ctypes.c_long(y_hat.size))
+    assert abs(nmae - float(g["nmae"])) <= 1e-5 * abs(float(g["nmae"]))
