@@ -4,6 +4,9 @@
  * torch-based oracle (oracle/conv3d_oracle.py) on small cases: it pins the MEANING of the operators the
  * reference delegates to torch (cross-correlation orientation, NCDHW flatten order, Linear layout).
  * Scalar loops, double accumulation, float results.  Never linked into the product.
+ * Pinned against outputs of the UNMODIFIED reference: composed by tests/test_c_oracle.py into the whole step (forward, the
+ * returned and logged losses, backward, two Adam steps), the two-tower forward and the Conv3dMaxPool block, these functions
+ * reproduce the golden vectors of tests/golden/ (oracle/make_golden.py) to 1e-5.
  *
  *   ora_sat_normalise : predict_pv_yield/netcdf_dataset.py:96-101
  *   ora_conv3d_relu   : nn.Conv3d(k=3, padding=0) + F.relu, predict_pv_yield/models/conv3d/model.py:80-90,117-120
